@@ -1,0 +1,368 @@
+#!/usr/bin/env python3
+"""bench.py — fwd+bwd train steps/s on BASELINE.json's headline configuration.
+
+Workload (config C3 of BASELINE.json / SURVEY.md §8d): 1 M synthetic Gaussians, SH degree 3,
+1920x1080, a batch of 8 views per step, loss 0.8*L1 + 0.2*(1-SSIM), Adam on all six tensors.
+A *step* = for each view: activations → projection → tile binning + sort → raster → loss →
+raster backward → projection backward (gradients accumulated), then [DP all-reduce] and Adam.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo (libgsb.so)
+    python bench.py --impl reference ...                            # the reference's kernels on host cores
+
+N > 1 is launched by torchrun (one rank per GPU); the 8 views are split round-robin over the ranks
+(strong scaling: the batch is fixed) and the per-Gaussian gradient block is all-reduced with NCCL.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "fwd+bwd train steps/s (1M Gaussians, 1080p, batch of 8 views)"
+UNIT = "steps/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": float(d["hbm_gbs"]), "sm_max_mhz": float(d.get("sm_max_mhz", 1965.0)), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (nvidia-smi sampled DURING the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in Path(self.path).read_text().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own kernels (oracle/_ref) or the C port, on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_view_sample(wl, params, cams, targets, view: int):
+    """One view's forward + loss + backward through the CPU oracle; returns (seconds, kind, M)."""
+    from oracle import pipeline as pl
+    from oracle.api import Port, Ref
+    o = Ref() if Ref.available() else Port()
+    t0 = time.perf_counter()
+    fr, lo, bw = pl.loss_and_grads(o, params, cams[view], targets[view], wl.sh_degree, 0.2, wl.tile, wl.tile)
+    dt = time.perf_counter() - t0
+    return dt, o.kind, int(fr["bins"]["M"]), bw["grads"], float(lo["loss"])
+
+
+def cpu_adam_sample(params, grads):
+    from oracle.api import Port
+    from oracle import pipeline as pl
+    o = Port()
+    p = {k: v.copy() for k, v in params.items()}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v_ = {k: np.zeros_like(v) for k, v in p.items()}
+    acc = np.zeros(p["_xyz"].shape[0], np.float32)
+    lrs = pl.learning_rates(0, 30000)
+    t0 = time.perf_counter()
+    o.accum_grad_norm(grads["_xyz"], acc)
+    for i, k in enumerate(pl.PARAM_ORDER):
+        o.adam(p[k], np.ascontiguousarray(grads[k].reshape(p[k].shape)), m[k], v_[k], lrs[i])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(wl, params, cams, targets, views: int):
+    cores = os.cpu_count() or 1
+    dt, kind, M, grads, _ = cpu_view_sample(wl, params, cams, targets, 0)
+    t_adam = cpu_adam_sample(params, grads)
+    step_s = views * dt + t_adam
+    return {"value": 1.0 / step_s, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"1 of {views} views (fwd+L1/SSIM loss+bwd, {dt:.2f} s, M={M}) x{views} + Adam ({t_adam:.3f} s), "
+                      f"OpenMP on all {cores} host threads",
+            "seconds_per_view": dt}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from gaussiansplattingmlx_b200.scene import make_workload
+    wl, params, cams, targets = make_workload(args.workload, n_override=args.n, views_override=args.views)
+    views = len(cams)
+    cores = os.cpu_count() or 1
+    budget = float(os.environ.get("GSB_REF_BUDGET_S", "240"))
+    t_start = time.perf_counter()
+    times, kind, grads = [], "port", None
+    done_warm = 0
+    for i in range(args.warmup + args.steps):
+        v = i % views
+        dt, kind, M, grads, _ = cpu_view_sample(wl, params, cams, targets, v)
+        if i < args.warmup and (time.perf_counter() - t_start) < budget * 0.4:
+            done_warm += 1
+            continue
+        times.append(dt)
+        if time.perf_counter() - t_start > budget:
+            break
+    t_adam = cpu_adam_sample(params, grads)
+    t_view = float(np.mean(times))
+    step_s = views * t_view + t_adam
+    value = 1.0 / step_s
+    sample = (f"each step = 1 of {views} views of the workload (fwd+L1/SSIM loss+bwd) through the reference's shipped kernels "
+              f"compiled for the host ({kind}); step time = {views} x mean view time ({t_view:.2f} s) + Adam ({t_adam:.3f} s); "
+              f"{len(times)} timed samples (requested {args.steps}, wall budget {budget:.0f} s), OpenMP on {cores} threads")
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+           "warmup": done_warm, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": workload_config(wl, params, views, world=1),
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(wl, params, views, world):
+    n = params["_xyz"].shape[0]
+    return {"workload": f"{wl.name}: {n} Gaussians, SH deg {wl.sh_degree}, {wl.width}x{wl.height}, batch of {views} views, "
+                        f"L1+SSIM loss, Adam; seed {wl.seed} (SURVEY.md 8d generator)",
+            "gaussians": n, "width": wl.width, "height": wl.height, "views_per_step": views, "tile": wl.tile,
+            "parallelism": f"view-parallel dp{world}" if world > 1 else "single GPU",
+            "l2_policy": "inputs larger than L2 (per step: 236 MB params + 236 MB grads + 472 MB Adam state + per-view "
+                         "key/record streams > 126 MB L2); no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gsb(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from gaussiansplattingmlx_b200 import _lib
+    from gaussiansplattingmlx_b200.context import Context
+    from gaussiansplattingmlx_b200.scene import make_workload
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl, params, cams, targets = make_workload(args.workload, n_override=args.n, views_override=args.views)
+    views = len(cams)
+    n = params["_xyz"].shape[0]
+    my_views = [v for v in range(views) if v % world == rank]
+    log(f"[rank {rank}] workload {wl.name}: N={n}, {wl.width}x{wl.height}, views {my_views} of {views}")
+
+    ctx = Context(wl.width, wl.height, tile_w=wl.tile, tile_h=wl.tile, sh_degree=wl.sh_degree, max_gaussians=n, device=local_rank)
+    ctx.trainer_init({k: torch.from_numpy(v) for k, v in params.items()})
+    gcams = [_lib.make_camera(cams[v]) for v in my_views]
+    host_targets = [torch.from_numpy(targets[v]).pin_memory() for v in my_views]
+    dev_targets = [t.to(dev, non_blocking=True) for t in host_targets]
+    grad_block = ctx.trainer_grad_block() if world > 1 else None
+    total_iters = 30000
+    gscale = 1.0 / views
+
+    def step(it, host: bool, want_loss: bool):
+        tg = host_targets if host else dev_targets
+        loss = None
+        if my_views:
+            loss = ctx.trainer_accumulate(gcams, tg, zero_grads=True, grad_scale=gscale, want_loss=want_loss)
+        if world > 1:
+            dist.all_reduce(grad_block)
+        ctx.trainer_apply(it, total_iters, reset_state=False)
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(host: bool, want_loss: bool, k: int, it0: int):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            step(it0 + i, host, want_loss)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- warm-up (also sizes the intersection buffers)
+    it = 0
+    for _ in range(args.warmup):
+        step(it, False, False); it += 1
+    barrier()
+
+    # blend evaluations per step on this rank (for the raster rooflines), from lastContrib of each view
+    evals = 0
+    pairs = 0
+    for cam in gcams:
+        ctx.render_forward(ctx.trainer_tensors()["params"], cam, want_outputs=False)
+        evals += ctx.last_contrib_sum()
+        pairs += ctx.stats()["pairs_last_view"]
+
+    # ---- timed region 1: inputs resident in HBM
+    ctx.stats_reset()
+    ctx.enable_stage_timing(True)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_dev = timed(False, False, args.steps, it); it += args.steps
+    st = ctx.stats()
+    ctx.enable_stage_timing(False)
+
+    # ---- timed region 2: end to end through the public API (pinned host targets H2D + loss D2H every step)
+    step(it, True, True); it += 1
+    ms_e2e = timed(True, True, args.steps, it); it += args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    K = args.steps
+    value = K / (ms_dev * 1e-3)
+    e2e_value = K / (ms_e2e * 1e-3)
+    img_bytes = wl.width * wl.height * 3 * 4
+    peaks = measured_peaks()
+    fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12   # TFLOP/s, non-tensor FP32 pipe at max clock
+
+    # per-stage averages on rank 0 (CUDA-event pairs recorded on the work stream during timed region 1)
+    nv = max(len(my_views), 1)
+    P = wl.width * wl.height
+    passes = -(-(32 + max(1, (ctx.num_tiles - 1).bit_length())) // 8)
+    M = pairs / nv
+    E = evals / nv
+    alg = {  # algorithmic bytes / flops per LAUNCH, per view unless noted
+        "project_fwd": ("hbm", 284.0 * n), "project_bwd": ("hbm", 516.0 * n), "scan": ("hbm", 8.0 * n),
+        "keygen": ("hbm", 28.0 * n + 12.0 * M), "sort": ("hbm", M * (8.0 + 24.0 * passes)),
+        "ranges_gather": ("hbm", M * (12.0 + 96.0)), "raster_fwd": ("fp32", 27.0 * E), "raster_bwd": ("fp32", 80.0 * E),
+        "loss": ("fp32", (225.0 + 170.0) * P * 3), "adam": ("hbm", 28.0 * 59 * n + 12.0 * n),
+    }
+    kernels = {}
+    for name, (bound, work) in alg.items():
+        calls = st["stage_calls"].get(name, 0)
+        if not calls:
+            continue
+        ms = st["stage_ms"][name] / calls
+        if bound == "hbm":
+            ach = work / (ms * 1e-3) / 1e9
+            kernels[name] = {"bound": "hbm", "ms": ms, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": ach / peaks["hbm_gbs"], "share_of_step": st["stage_ms"][name] / (ms_dev) }
+        else:
+            ach = work / (ms * 1e-3) / 1e12
+            kernels[name] = {"bound": "fp32", "ms": ms, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                             "frac": ach / fp32_peak, "share_of_step": st["stage_ms"][name] / (ms_dev)}
+    dominant = max(kernels, key=lambda k: kernels[k]["share_of_step"]) if kernels else None
+    roof = None
+    if dominant:
+        d = kernels[dominant]
+        roof = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
+                "frac": d["frac"], "traffic": None,
+                "peak_source": (f"{peaks['source']} MEASURED_PEAKS.json hbm_gbs" if d["bound"] == "hbm" else
+                                f"non-tensor FP32 pipe: 148 SM x 128 lanes x 2 flop x sm_max_mhz ({peaks['source']}); "
+                                "no measured FP32 figure exists in MEASURED_PEAKS.json"),
+                "units_per_launch": {"pairs_M": M, "blend_evals_E": E, "gaussians": n, "pixels": P}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(wl, params, cams, targets, views)
+        except Exception as ex:  # the oracle is a checker, never a dependency of the GPU arm
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+           "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": workload_config(wl, params, views, world),
+           "views_per_s": value * views,
+           "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
+                   "h2d_bytes_per_step": img_bytes * len(my_views), "d2h_bytes_per_step": 4,
+                   "api": "Context.trainer_accumulate(pinned host targets, want_loss) [+ NCCL all_reduce] + trainer_apply"},
+           "gpu_launches": st["kernel_launches"], "clocks": clk, "roofline": roof, "roofline_kernels": kernels,
+           "cpu_baseline": cpu}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gsb", choices=["gsb", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--n", type=int, default=None, help="override the Gaussian count (debugging only)")
+    ap.add_argument("--views", type=int, default=None, help="override the views per step (debugging only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        log(f"--gpus {args.gpus} requires torchrun (WORLD_SIZE={world}); running on 1 GPU")
+    run_gsb(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,343 @@
+"""``Context`` — thin object wrapper over a ``gsb_ctx`` for callers that hold torch CUDA tensors.
+
+torch is used for device memory and streams only (plumbing); every computation is a call into
+``libgsb.so``.  All methods enqueue on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import GsbCamera, GsbConfig, GsbError, GsbStats
+
+PARAM_NAMES = ("_xyz", "_features_dc", "_features_rest", "_scales", "_rotation", "_opacity")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "gsb takes contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.float32, "gsb arithmetic is f32"
+    return t.contiguous()
+
+
+class Context:
+    def __init__(self, width: int, height: int, tile_w: int = 16, tile_h: int = 16, sh_degree: int = 3,
+                 sh_coeffs: Optional[int] = None, white_background: bool = False, max_gaussians: int = 0,
+                 device: int = 0, flags: int = 0, lambda_dssim: float = 0.2):
+        self.lib = _lib.load()
+        cfg = GsbConfig()
+        self.lib.gsb_default_config(C.byref(cfg))
+        cfg.width, cfg.height, cfg.tile_w, cfg.tile_h = width, height, tile_w, tile_h
+        cfg.sh_degree = sh_degree
+        cfg.sh_coeffs = sh_coeffs if sh_coeffs is not None else (sh_degree + 1) ** 2
+        cfg.white_background = int(bool(white_background))
+        cfg.max_gaussians = max_gaussians
+        cfg.device = device
+        cfg.flags = flags
+        cfg.lambda_dssim = lambda_dssim
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        self.W, self.H, self.K = width, height, cfg.sh_coeffs
+        self.P = width * height
+        self.grid_w = (width + tile_w - 1) // tile_w
+        self.grid_h = (height + tile_h - 1) // tile_h
+        self.num_tiles = self.grid_w * self.grid_h
+        h = C.c_void_p()
+        rc = self.lib.gsb_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise GsbError(rc, (self.lib.gsb_last_error(None) or b"").decode())
+        self.h = h
+        self._stream = None
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gsb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise GsbError(rc, (self.lib.gsb_last_error(self.h) or b"").decode())
+
+    def _sync_stream(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if s != self._stream:
+            self._check(self.lib.gsb_set_stream(self.h, C.c_void_p(s)))
+            self._stream = s
+
+    def _new(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def synchronize(self):
+        self._check(self.lib.gsb_synchronize(self.h))
+
+    # ---- activations ------------------------------------------------------------------------
+    def activate_fwd(self, params: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        self._sync_stream()
+        n = params["_xyz"].shape[0]
+        shs, scales, rot, op = self._new(n, self.K, 3), self._new(n, 3), self._new(n, 4), self._new(n, 1)
+        self._check(self.lib.gsb_activate_fwd(self.h, n, _ptr(_f32(params["_features_dc"])), _ptr(_f32(params["_features_rest"])),
+                                              _ptr(_f32(params["_scales"])), _ptr(_f32(params["_rotation"])),
+                                              _ptr(_f32(params["_opacity"])), _ptr(shs), _ptr(scales), _ptr(rot), _ptr(op)))
+        return {"means3d": params["_xyz"], "shs": shs, "scales": scales, "rotations": rot, "opacity": op}
+
+    def activate_bwd(self, params, g_act) -> Dict[str, torch.Tensor]:
+        self._sync_stream()
+        n = params["_xyz"].shape[0]
+        out = {k: torch.empty_like(params[k]) for k in PARAM_NAMES[1:]}
+        self._check(self.lib.gsb_activate_bwd(self.h, n, _ptr(_f32(params["_scales"])), _ptr(_f32(params["_rotation"])),
+                                              _ptr(_f32(params["_opacity"])), _ptr(_f32(g_act["shs"])), _ptr(_f32(g_act["scales"])),
+                                              _ptr(_f32(g_act["rotations"])), _ptr(_f32(g_act["opacity"])),
+                                              _ptr(out["_features_dc"]), _ptr(out["_features_rest"]), _ptr(out["_scales"]),
+                                              _ptr(out["_rotation"]), _ptr(out["_opacity"])))
+        out["_xyz"] = g_act["means3d"]
+        return out
+
+    # ---- K1 / K2 ----------------------------------------------------------------------------
+    def project_fwd(self, act, cam: GsbCamera) -> Dict[str, torch.Tensor]:
+        self._sync_stream()
+        n = act["means3d"].shape[0]
+        o = {"means2d": self._new(n, 2), "depths": self._new(n), "color": self._new(n, 3), "cov2d": self._new(n, 2, 2),
+             "conic": self._new(n, 2, 2), "radii": self._new(n), "rectMin": self._new(n, 2), "rectMax": self._new(n, 2)}
+        self._check(self.lib.gsb_project_fwd(self.h, n, _ptr(_f32(act["scales"])), _ptr(_f32(act["rotations"])),
+                                             _ptr(_f32(act["means3d"])), _ptr(_f32(act["shs"])), C.byref(cam), _ptr(o["means2d"]),
+                                             _ptr(o["depths"]), _ptr(o["color"]), _ptr(o["cov2d"]), _ptr(o["conic"]),
+                                             _ptr(o["radii"]), _ptr(o["rectMin"]), _ptr(o["rectMax"])))
+        return o
+
+    def project_bwd(self, act, cam: GsbCamera, cot) -> Dict[str, torch.Tensor]:
+        self._sync_stream()
+        n = act["means3d"].shape[0]
+        g = {"scales": self._new(n, 3), "rotations": self._new(n, 4), "means3d": self._new(n, 3),
+             "shs": self._new(n, self.K, 3), "cameraCenterPoint": self._new(n, 3)}
+        self._check(self.lib.gsb_project_bwd(self.h, n, _ptr(_f32(act["scales"])), _ptr(_f32(act["rotations"])),
+                                             _ptr(_f32(act["means3d"])), _ptr(_f32(act["shs"])), C.byref(cam),
+                                             _ptr(_f32(cot["depths"])), _ptr(_f32(cot["means2d"])), _ptr(_f32(cot["cov2d"])),
+                                             _ptr(_f32(cot["color"])), _ptr(_f32(cot["conic"])), _ptr(g["scales"]),
+                                             _ptr(g["rotations"]), _ptr(g["means3d"]), _ptr(g["shs"]), _ptr(g["cameraCenterPoint"])))
+        return g
+
+    # ---- K3..K8 -----------------------------------------------------------------------------
+    def bin(self, proj, read_lists: bool = True) -> Dict[str, torch.Tensor]:
+        self._sync_stream()
+        n = proj["radii"].shape[0]
+        touched = self._new(n, dtype=torch.int32)
+        ranges = self._new(self.num_tiles, 2, dtype=torch.int32)
+        counts = self._new(self.num_tiles, dtype=torch.int32)
+        m = C.c_uint32(0)
+        self._check(self.lib.gsb_bin(self.h, n, _ptr(_f32(proj["rectMin"])), _ptr(_f32(proj["rectMax"])), _ptr(_f32(proj["radii"])),
+                                     _ptr(_f32(proj["depths"])), _ptr(touched), _ptr(ranges), _ptr(counts), C.byref(m)))
+        out = {"tilesTouched": touched, "tileRanges": ranges, "tileCounts": counts, "M": int(m.value)}
+        if read_lists:
+            out.update(self.bin_read(unsorted=True))
+        return out
+
+    def bin_read(self, unsorted: bool = False) -> Dict[str, torch.Tensor]:
+        self._sync_stream()
+        st = GsbStats()
+        self._check(self.lib.gsb_stats_get(self.h, C.byref(st)))
+        m = int(st.pairs_last_view)
+        names = ["sortedKeysHigh", "sortedKeysLow", "sortedGaussIdx"]
+        if unsorted:
+            names = ["keysHigh", "keysLow", "gaussIdx"] + names
+        bufs = {k: self._new(m, dtype=torch.int32) for k in names}
+        args = [_ptr(bufs[k]) if k in bufs else None for k in
+                ("keysHigh", "keysLow", "gaussIdx", "sortedKeysHigh", "sortedKeysLow", "sortedGaussIdx")]
+        self._check(self.lib.gsb_bin_read(self.h, *args))
+        return bufs
+
+    def sort_tile_keys(self, keys_high, keys_low, values, tile_bits: int, use_cub: bool = False):
+        self._sync_stream()
+        m = keys_high.numel()
+        outs = [torch.empty_like(keys_high), torch.empty_like(keys_low), torch.empty_like(values)]
+        self._check(self.lib.gsb_sort_tile_keys(self.h, m, tile_bits, _ptr(keys_high.contiguous()), _ptr(keys_low.contiguous()),
+                                                _ptr(values.contiguous()), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]),
+                                                int(use_cub)))
+        return outs
+
+    # ---- K9 / K10 ---------------------------------------------------------------------------
+    def raster_fwd(self, packed) -> Dict[str, torch.Tensor]:
+        self._sync_stream()
+        n = packed.shape[0]
+        o = {"color": self._new(self.P, 3), "depth": self._new(self.P, 1), "alpha": self._new(self.P, 1),
+             "lastContrib": self._new(self.P, 1, dtype=torch.int32)}
+        self._check(self.lib.gsb_raster_fwd(self.h, n, _ptr(_f32(packed)), _ptr(o["color"]), _ptr(o["depth"]), _ptr(o["alpha"]),
+                                            _ptr(o["lastContrib"])))
+        return o
+
+    def raster_bwd(self, packed, cot, fwd) -> torch.Tensor:
+        self._sync_stream()
+        n = packed.shape[0]
+        g = self._new(n, 11)
+        self._check(self.lib.gsb_raster_bwd(self.h, n, _ptr(_f32(packed)), _ptr(_f32(cot["color"])),
+                                            _ptr(_f32(cot["depth"])) if cot.get("depth") is not None else None,
+                                            _ptr(_f32(cot["alpha"])) if cot.get("alpha") is not None else None,
+                                            _ptr(fwd["color"]), _ptr(fwd["depth"]), _ptr(fwd["alpha"]), _ptr(fwd["lastContrib"]),
+                                            _ptr(g)))
+        return g
+
+    # ---- K11 / K12 --------------------------------------------------------------------------
+    def ssim_fwd(self, img1, img2, saved: bool = True) -> Dict[str, torch.Tensor]:
+        self._sync_stream()
+        H, W, Cn = img1.shape
+        names = ("ssim", "mu1", "mu2", "sigma1", "sigma2", "sigma12")
+        o = {k: self._new(H, W, Cn) for k in (names if saved else names[:1])}
+        self._check(self.lib.gsb_ssim_fwd(self.h, H, W, Cn, _ptr(_f32(img1)), _ptr(_f32(img2)),
+                                          *[_ptr(o[k]) if k in o else None for k in names]))
+        return o
+
+    def ssim_bwd(self, grad_out, img1, img2) -> torch.Tensor:
+        self._sync_stream()
+        H, W, Cn = img1.shape
+        g = self._new(H, W, Cn)
+        self._check(self.lib.gsb_ssim_bwd(self.h, H, W, Cn, _ptr(_f32(grad_out)), _ptr(_f32(img1)), _ptr(_f32(img2)), _ptr(g)))
+        return g
+
+    # ---- fused renderer / loss ---------------------------------------------------------------
+    def render_forward(self, params: Dict[str, torch.Tensor], cam: GsbCamera, want_outputs: bool = True):
+        self._sync_stream()
+        n = params["_xyz"].shape[0]
+        render = self._new(self.H, self.W, 3) if want_outputs else None
+        depth = self._new(self.H, self.W, 1) if want_outputs else None
+        alpha = self._new(self.H, self.W, 1) if want_outputs else None
+        vis = self._new(n, dtype=torch.uint8) if want_outputs else None
+        radii = self._new(n) if want_outputs else None
+        self._saved_params = params  # keep the tensors alive until the backward
+        self._check(self.lib.gsb_render_forward(self.h, n, *[_ptr(_f32(params[k])) for k in PARAM_NAMES], C.byref(cam),
+                                                _ptr(render), _ptr(depth), _ptr(alpha), _ptr(vis), _ptr(radii)))
+        return render, depth, alpha, (vis.bool() if vis is not None else None), radii
+
+    def render_backward(self, cot_render, cot_depth=None, cot_alpha=None, grads: Optional[Dict[str, torch.Tensor]] = None,
+                        accumulate: bool = False) -> Dict[str, torch.Tensor]:
+        self._sync_stream()
+        params = self._saved_params
+        if grads is None:
+            grads = {k: torch.empty_like(params[k]) for k in PARAM_NAMES}
+            accumulate = False
+        self._check(self.lib.gsb_render_backward(self.h, _ptr(_f32(cot_render)), _ptr(cot_depth), _ptr(cot_alpha),
+                                                 *[_ptr(grads[k]) for k in PARAM_NAMES], int(accumulate)))
+        return grads
+
+    def loss_fwd_bwd(self, render, target, grad_scale: float = 1.0):
+        """Returns (loss tensor [1] on device, cot_render[H,W,3])."""
+        self._sync_stream()
+        cot = torch.empty_like(render)
+        loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._check(self.lib.gsb_loss_fwd_bwd(self.h, _ptr(_f32(render)), _ptr(_f32(target)), C.c_float(grad_scale), _ptr(cot),
+                                              _ptr(loss)))
+        return loss, cot
+
+    # ---- Adam -------------------------------------------------------------------------------
+    def adam_step(self, params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], m: Sequence[torch.Tensor],
+                  v: Sequence[torch.Tensor], lrs: Sequence[float], grad_norm_accum: Optional[torch.Tensor] = None):
+        self._sync_stream()
+        arr = lambda ts: (C.c_void_p * 6)(*[t.data_ptr() for t in ts])
+        counts = (C.c_int64 * 6)(*[t.numel() for t in params])
+        lr = (C.c_float * 6)(*lrs)
+        n = params[0].shape[0]
+        self._check(self.lib.gsb_adam_step(self.h, n, arr(params), arr(grads), arr(m), arr(v), counts, lr, _ptr(grad_norm_accum)))
+
+    # ---- trainer ----------------------------------------------------------------------------
+    def trainer_init(self, params: Dict[str, torch.Tensor]):
+        """``params`` may be host (numpy-backed CPU tensors) or CUDA tensors."""
+        self._sync_stream()
+        n = params["_xyz"].shape[0]
+        ptrs = [C.c_void_p(params[k].contiguous().data_ptr()) for k in PARAM_NAMES]
+        self._trainer_src = params
+        self._check(self.lib.gsb_trainer_init(self.h, n, *ptrs))
+        self.tN = n
+
+    def trainer_tensors(self):
+        """Zero-copy torch views of the context-owned params / grads / m / v / accum buffers."""
+        P = (C.c_void_p * 6)(); G = (C.c_void_p * 6)(); M = (C.c_void_p * 6)(); V = (C.c_void_p * 6)()
+        A = C.c_void_p()
+        self._check(self.lib.gsb_trainer_param_ptrs(self.h, P, G, M, V, C.byref(A)))
+        K = self.K
+        shapes = [(self.tN, 3), (self.tN, 1, 3), (self.tN, K - 1, 3), (self.tN, 3), (self.tN, 4), (self.tN, 1)]
+        def view(ptr, shape):
+            return _wrap_device_memory(ptr, shape, self.device)
+        out = {}
+        for name, arr in (("params", P), ("grads", G), ("m", M), ("v", V)):
+            out[name] = {k: view(arr[i], shapes[i]) for i, k in enumerate(PARAM_NAMES)}
+        out["accum"] = view(A.value, (self.tN,))
+        return out
+
+    def trainer_grad_block(self) -> torch.Tensor:
+        p = C.c_void_p(); n = C.c_int64()
+        self._check(self.lib.gsb_trainer_grad_block(self.h, C.byref(p), C.byref(n)))
+        return _wrap_device_memory(p.value, (int(n.value),), self.device)
+
+    def _cams_targets(self, cams: Sequence[GsbCamera], targets: Sequence[torch.Tensor]):
+        B = len(cams)
+        cam_arr = (GsbCamera * B)(*cams)
+        on_host = not targets[0].is_cuda
+        for t in targets:
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda != on_host
+            if on_host:
+                assert t.is_pinned(), "host targets must be pinned"
+        tp = (C.c_void_p * B)(*[t.data_ptr() for t in targets])
+        return B, cam_arr, tp, int(on_host)
+
+    def trainer_accumulate(self, cams, targets, zero_grads: bool = True, grad_scale: Optional[float] = None,
+                           want_loss: bool = True) -> Optional[float]:
+        self._sync_stream()
+        B, cam_arr, tp, on_host = self._cams_targets(cams, targets)
+        loss = C.c_float(0.0)
+        scale = (1.0 / B) if grad_scale is None else grad_scale
+        self._check(self.lib.gsb_trainer_accumulate(self.h, B, cam_arr, tp, on_host, int(zero_grads), C.c_float(scale),
+                                                    C.byref(loss) if want_loss else None))
+        return float(loss.value) if want_loss else None
+
+    def trainer_apply(self, iteration: int, total_iterations: int, reset_state: bool = False):
+        self._sync_stream()
+        self._check(self.lib.gsb_trainer_apply(self.h, iteration, total_iterations, int(reset_state)))
+
+    def train_step(self, cams, targets, iteration: int, total_iterations: int, want_loss: bool = True) -> Optional[float]:
+        self._sync_stream()
+        B, cam_arr, tp, on_host = self._cams_targets(cams, targets)
+        loss = C.c_float(0.0)
+        self._check(self.lib.gsb_train_step(self.h, B, cam_arr, tp, on_host, iteration, total_iterations,
+                                            C.byref(loss) if want_loss else None))
+        return float(loss.value) if want_loss else None
+
+    # ---- stats ------------------------------------------------------------------------------
+    def stats(self) -> Dict:
+        st = GsbStats()
+        self._check(self.lib.gsb_stats_get(self.h, C.byref(st)))
+        names = [self.lib.gsb_stage_name(i).decode() for i in range(_lib.STAGE_COUNT)]
+        return {"kernel_launches": int(st.kernel_launches), "pairs_last_view": int(st.pairs_last_view),
+                "pairs_total": int(st.pairs_total), "views": int(st.views), "pair_capacity": int(st.pair_capacity),
+                "stage_ms": {n: float(st.stage_ms[i]) for i, n in enumerate(names)},
+                "stage_calls": {n: int(st.stage_calls[i]) for i, n in enumerate(names)}}
+
+    def stats_reset(self):
+        self._check(self.lib.gsb_stats_reset(self.h))
+
+    def enable_stage_timing(self, on: bool):
+        self._check(self.lib.gsb_enable_stage_timing(self.h, int(on)))
+
+
+class _DevMem:
+    """``__cuda_array_interface__`` carrier so torch can view library-owned device memory."""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def _wrap_device_memory(ptr: int, shape, device) -> torch.Tensor:
+    return torch.as_tensor(_DevMem(ptr, shape), device=device)

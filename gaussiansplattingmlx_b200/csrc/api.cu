@@ -1,0 +1,1090 @@
+// api.cu — the C ABI of libgsb.so (include/gsb.h): context, buffer management, stage sequencing.
+//
+// Sequencing mirrors the reference's host glue:
+//   GaussianRenderer.forwardWithCameraParams → render → buildGlobalTileSliceInfo
+//                                       (Trainer/GaussianRenderer.swift:823-880, 769-821, 333-490)
+//   VJPs                                (Trainer/GaussianRenderer.swift:187-226, 605-701)
+//   lossFn / Adam loop                  (Trainer/GaussianTrainer.swift:634-716, 1060-1086)
+// but with no host synchronisation on the data path: the pair count M stays on the device, kernels
+// are launched for the buffer capacity, and M is read back asynchronously only to detect overflow
+// (the view is then redone with larger buffers).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "kernels.h"
+
+namespace gsb {
+
+static thread_local std::string g_create_error;
+
+struct Ctx {
+    gsb_config cfg{};
+    cudaStream_t stream = nullptr;       // work stream (caller's, or own_stream)
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of targets
+    std::string err;
+    int gridW = 0, gridH = 0, numTiles = 0, tileBits = 1, P = 0;
+
+    // per-Gaussian buffers (capacity capN)
+    int capN = 0;
+    float* rec = nullptr;          // [N,12]
+    float* grad_rec = nullptr;     // [N,12]
+    uint2* tile_rects = nullptr;   // [N]
+    uint32_t* touched = nullptr;   // [N]
+    uint32_t* offsets = nullptr;   // [N]
+    void* scan_ws = nullptr;
+    float* act_tmp = nullptr;      // scratch for the reference-layout parity API ([N,12] floats)
+
+    // per-pair buffers (capacity capM)
+    uint32_t capM = 0;
+    uint64_t* keys[2] = {nullptr, nullptr};
+    uint32_t* vals[2] = {nullptr, nullptr};
+    float* staged = nullptr;       // [M,12]
+    void* sort_ws = nullptr;
+    SortPlan plan;
+    void* cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
+    uint64_t* dbg_keys = nullptr;  // unsorted copies for gsb_bin_read
+    uint32_t* dbg_vals = nullptr;
+    uint32_t dbg_cap = 0;
+    const uint32_t* d_result_buf = nullptr;  // device flag: which ping-pong buffer holds the sorted list
+    uint32_t* d_zero = nullptr;              // constant 0 (CUB path result buffer selector = 1 → d_one)
+    uint32_t* d_one = nullptr;
+
+    // per-tile / per-pixel
+    uint32_t* tile_ranges = nullptr;  // [numTiles,2]
+    float* out_color = nullptr;       // saved forward outputs
+    float* out_depth = nullptr;
+    float* out_alpha = nullptr;
+    uint32_t* out_last = nullptr;
+    float* mapA = nullptr;            // SSIM backward maps, [P*3] each
+    float* mapB = nullptr;
+    float* mapC = nullptr;
+    float* cot_render = nullptr;      // [P*3]
+    double* partial = nullptr;        // [2]
+    float* loss_accum = nullptr;      // device scalar
+    float* h_loss = nullptr;          // pinned
+
+    // control words: [0] = M of the current view, [1] = overflow flag
+    uint32_t* d_ctl = nullptr;
+    uint32_t* h_ctl = nullptr;        // pinned mirror
+    cudaEvent_t ev_ctl = nullptr;
+    uint32_t last_M = 0;
+
+    // saved forward (one in flight, like the reference's closure-captured state)
+    struct Saved {
+        bool valid = false;
+        int N = 0;
+        const float *xyz = nullptr, *f_dc = nullptr, *f_rest = nullptr, *scales_log = nullptr, *rot_raw = nullptr,
+                    *op_logit = nullptr;
+        ViewParams vp{};
+    } saved;
+    bool bin_valid = false;           // gsb_bin ran (parity API)
+    ViewParams bin_vp{};
+
+    // trainer state
+    int tN = 0;
+    float* t_block = nullptr;         // params | grads | m | v, each 6 tensors, 16-byte aligned segments
+    float* t_p[6]{}; float* t_g[6]{}; float* t_m[6]{}; float* t_v[6]{};
+    long long t_count[6]{};
+    size_t t_floats = 0;              // padded floats of one copy of the six tensors
+    float* t_accum = nullptr;         // D1 accumulator [N]
+    float* t_target[2] = {nullptr, nullptr};
+    cudaEvent_t t_target_ready[2] = {nullptr, nullptr};
+    cudaEvent_t t_target_free[2] = {nullptr, nullptr};
+
+    // stats.  Stage timing records CUDA-event pairs on the work stream WITHOUT synchronising; the
+    // pairs are resolved (one stream sync) when the statistics are read.
+    gsb_stats stats{};
+    bool timing = false;
+    struct StageEv { cudaEvent_t a = nullptr, b = nullptr; int stage = 0; };
+    std::vector<StageEv> ev_pool;
+    size_t ev_used = 0;
+};
+
+static void resolve_stage_events(Ctx* c)
+{
+    if (c->ev_used == 0) return;
+    cudaStreamSynchronize(c->stream);
+    for (size_t i = 0; i < c->ev_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev_pool[i].a, c->ev_pool[i].b) == cudaSuccess) {
+            c->stats.stage_ms[c->ev_pool[i].stage] += ms;
+            c->stats.stage_calls[c->ev_pool[i].stage] += 1;
+        }
+    }
+    c->ev_used = 0;
+}
+
+void set_error(Ctx* ctx, const std::string& msg)
+{
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+}
+
+static const char* kStageNames[GSB_STAGE_COUNT] = {"project_fwd", "scan", "keygen", "sort", "ranges_gather", "raster_fwd",
+                                                   "loss", "raster_bwd", "project_bwd", "adam", "h2d"};
+
+struct StageTimer {
+    Ctx* c; int stage; bool on;
+    StageTimer(Ctx* ctx, int s) : c(ctx), stage(s), on(ctx->timing)
+    {
+        if (!on) return;
+        if (c->ev_used >= 16384) resolve_stage_events(c);
+        if (c->ev_used == c->ev_pool.size()) {
+            Ctx::StageEv e;
+            if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) { on = false; return; }
+            c->ev_pool.push_back(e);
+        }
+        c->ev_pool[c->ev_used].stage = stage;
+        cudaEventRecord(c->ev_pool[c->ev_used].a, c->stream);
+    }
+    ~StageTimer()
+    {
+        if (!on) return;
+        cudaEventRecord(c->ev_pool[c->ev_used].b, c->stream);
+        c->ev_used += 1;
+    }
+};
+
+#define GSB_REQUIRE(ctx, cond, msg)                 \
+    do {                                            \
+        if (!(cond)) {                              \
+            gsb::set_error(ctx, msg);               \
+            return GSB_ERR_INVALID;                 \
+        }                                           \
+    } while (0)
+
+template <class T>
+static cudaError_t dev_alloc(T** p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+}
+template <class T>
+static void dev_free(T*& p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+static int tile_bit_count(int numTiles)  // GaussianRenderer.swift:246-255
+{
+    if (numTiles <= 1) return 1;
+    int v = numTiles - 1, bits = 0;
+    while (v > 0) { ++bits; v >>= 1; }
+    return bits;
+}
+
+static ViewParams make_view(const Ctx* c, const gsb_camera* cam)
+{
+    ViewParams vp{};
+    memcpy(vp.V, cam->view, sizeof(vp.V));
+    memcpy(vp.P, cam->proj, sizeof(vp.P));
+    memcpy(vp.cam, cam->cam_center, sizeof(vp.cam));
+    vp.fovX = cam->fov_x; vp.fovY = cam->fov_y; vp.focalX = cam->focal_x; vp.focalY = cam->focal_y;
+    vp.tanHalfX = tanf(cam->fov_x * 0.5f);   // gaussian_projection_screen_shared.slang:200-201, host libm
+    vp.tanHalfY = tanf(cam->fov_y * 0.5f);
+    vp.imageW = (float)c->cfg.width; vp.imageH = (float)c->cfg.height;
+    vp.W = c->cfg.width; vp.H = c->cfg.height; vp.tileW = c->cfg.tile_w; vp.tileH = c->cfg.tile_h;
+    vp.gridW = c->gridW; vp.gridH = c->gridH;
+    vp.degree = c->cfg.sh_degree; vp.K = c->cfg.sh_coeffs;
+    vp.coeffCount = std::min((c->cfg.sh_degree + 1) * (c->cfg.sh_degree + 1), 25);
+    vp.whiteBg = c->cfg.white_background;
+    return vp;
+}
+static ViewParams make_view_nocam(const Ctx* c)
+{
+    gsb_camera cam{};
+    return make_view(c, &cam);
+}
+
+static int ensure_gaussians(Ctx* c, int N)
+{
+    if (N <= c->capN) return GSB_OK;
+    if (c->cfg.max_gaussians > 0 && N > c->cfg.max_gaussians) {
+        set_error(c, "N exceeds gsb_config.max_gaussians");
+        return GSB_ERR_INVALID;
+    }
+    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    dev_free(c->rec); dev_free(c->grad_rec); dev_free(c->tile_rects); dev_free(c->touched); dev_free(c->offsets);
+    dev_free(c->scan_ws); dev_free(c->act_tmp);
+    const int cap = c->cfg.max_gaussians > 0 ? c->cfg.max_gaussians : std::max(N, 1024);
+    GSB_CUDA_CHECK(c, dev_alloc(&c->rec, (size_t)cap * REC_FLOATS));
+    GSB_CUDA_CHECK(c, dev_alloc(&c->grad_rec, (size_t)cap * REC_FLOATS));
+    GSB_CUDA_CHECK(c, dev_alloc(&c->tile_rects, (size_t)cap));
+    GSB_CUDA_CHECK(c, dev_alloc(&c->touched, (size_t)cap));
+    GSB_CUDA_CHECK(c, dev_alloc(&c->offsets, (size_t)cap));
+    GSB_CUDA_CHECK(c, dev_alloc(&c->act_tmp, (size_t)cap * REC_FLOATS));
+    GSB_CUDA_CHECK(c, cudaMalloc(&c->scan_ws, scan_ws_bytes(cap)));
+    c->capN = cap;
+    return GSB_OK;
+}
+
+static int ensure_pairs(Ctx* c, uint64_t M)
+{
+    if (M <= c->capM) return GSB_OK;
+    if (M > 0xfffffff0ull / 3ull) {  // u32 offsets (the reference's cumsum is u32 too)
+        set_error(c, "intersection list exceeds the 32-bit index range");
+        return GSB_ERR_CAPACITY;
+    }
+    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 2; ++i) { dev_free(c->keys[i]); dev_free(c->vals[i]); }
+    dev_free(c->staged);
+    if (c->sort_ws) { cudaFree(c->sort_ws); c->sort_ws = nullptr; }
+    if (c->cub_tmp) { cudaFree(c->cub_tmp); c->cub_tmp = nullptr; c->cub_tmp_bytes = 0; }
+    uint64_t cap = std::max<uint64_t>(M + M / 4, 1u << 16);
+    cap = (cap + 4095) & ~4095ull;
+    for (int i = 0; i < 2; ++i) {
+        GSB_CUDA_CHECK(c, dev_alloc(&c->keys[i], (size_t)cap));
+        GSB_CUDA_CHECK(c, dev_alloc(&c->vals[i], (size_t)cap));
+    }
+    GSB_CUDA_CHECK(c, dev_alloc(&c->staged, (size_t)cap * REC_FLOATS));
+    c->plan = sort_plan((uint32_t)cap, 32u + (uint32_t)c->tileBits);
+    GSB_CUDA_CHECK(c, cudaMalloc(&c->sort_ws, c->plan.ws_bytes));
+    c->capM = (uint32_t)cap;
+    c->stats.pair_capacity = cap;
+    return GSB_OK;
+}
+
+// count → keys → sort → ranges (+ gather when rec != NULL).  tile_rects / touched must be filled.
+static int run_binning(Ctx* c, int N, const ViewParams& vp, const float* depth_ptr, int depth_stride, const float* rec,
+                       bool keep_unsorted)
+{
+    int launches = 0;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        {
+            StageTimer t(c, GSB_STAGE_SCAN);
+            GSB_CUDA_CHECK(c, cudaMemsetAsync(c->d_ctl, 0, 2 * sizeof(uint32_t), c->stream));
+            GSB_CUDA_CHECK(c, launch_exclusive_scan(c->stream, N, c->touched, c->offsets, &c->d_ctl[0], c->scan_ws));
+            ++launches;
+        }
+        GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        GSB_CUDA_CHECK(c, cudaEventRecord(c->ev_ctl, c->stream));
+        if (c->capM == 0) {  // first use: size the pair buffers from the actual count
+            GSB_CUDA_CHECK(c, cudaEventSynchronize(c->ev_ctl));
+            int rc = ensure_pairs(c, std::max<uint64_t>(c->h_ctl[0], 1));
+            if (rc != GSB_OK) return rc;
+        }
+        {
+            StageTimer t(c, GSB_STAGE_KEYGEN);
+            GSB_CUDA_CHECK(c, launch_generate_keys(c->stream, N, vp, c->tile_rects, c->offsets, depth_ptr, depth_stride,
+                                                   c->keys[0], c->vals[0], c->capM, &c->d_ctl[0], &c->d_ctl[1]));
+            ++launches;
+        }
+        if (keep_unsorted) {
+            if (c->dbg_cap < c->capM) {
+                GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+                dev_free(c->dbg_keys); dev_free(c->dbg_vals);
+                GSB_CUDA_CHECK(c, dev_alloc(&c->dbg_keys, (size_t)c->capM));
+                GSB_CUDA_CHECK(c, dev_alloc(&c->dbg_vals, (size_t)c->capM));
+                c->dbg_cap = c->capM;
+            }
+            GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->dbg_keys, c->keys[0], (size_t)c->capM * 8, cudaMemcpyDeviceToDevice, c->stream));
+            GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->dbg_vals, c->vals[0], (size_t)c->capM * 4, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        {
+            StageTimer t(c, GSB_STAGE_SORT);
+            if (c->cfg.flags & GSB_FLAG_SORT_CUB) {
+                // checked baseline: needs the host-known count
+                GSB_CUDA_CHECK(c, cudaEventSynchronize(c->ev_ctl));
+                const uint32_t M = std::min(c->h_ctl[0], c->capM);
+                size_t need = 0;
+                GSB_CUDA_CHECK(c, cub_sort_pairs(c->stream, c->keys[0], c->keys[1], c->vals[0], c->vals[1], M,
+                                                 32u + (uint32_t)c->tileBits, nullptr, 0, &need));
+                if (need > c->cub_tmp_bytes) {
+                    if (c->cub_tmp) cudaFree(c->cub_tmp);
+                    GSB_CUDA_CHECK(c, cudaMalloc(&c->cub_tmp, need));
+                    c->cub_tmp_bytes = need;
+                }
+                if (M > 0)
+                    GSB_CUDA_CHECK(c, cub_sort_pairs(c->stream, c->keys[0], c->keys[1], c->vals[0], c->vals[1], M,
+                                                     32u + (uint32_t)c->tileBits, c->cub_tmp, c->cub_tmp_bytes, nullptr));
+                c->d_result_buf = M > 0 ? c->d_one : c->d_zero;
+            } else {
+                GSB_CUDA_CHECK(c, launch_onesweep_sort(c->stream, c->plan, c->keys[0], c->keys[1], c->vals[0], c->vals[1],
+                                                       &c->d_ctl[0], c->sort_ws, &c->d_result_buf, &launches));
+            }
+        }
+        {
+            StageTimer t(c, GSB_STAGE_RANGES_GATHER);
+            GSB_CUDA_CHECK(c, launch_ranges_gather(c->stream, vp, c->keys[0], c->keys[1], c->vals[0], c->vals[1],
+                                                   c->d_result_buf, &c->d_ctl[0], c->capM, rec, c->tile_ranges, c->staged,
+                                                   c->numTiles));
+            ++launches;
+        }
+        // overflow check: the event fired right after the scan, long before the queue drains
+        GSB_CUDA_CHECK(c, cudaEventSynchronize(c->ev_ctl));
+        const uint32_t M = c->h_ctl[0];
+        if (M <= c->capM) {
+            c->last_M = M;
+            c->stats.kernel_launches += launches;
+            return GSB_OK;
+        }
+        int rc = ensure_pairs(c, M);
+        if (rc != GSB_OK) return rc;
+    }
+    set_error(c, "intersection buffers kept overflowing");
+    return GSB_ERR_CAPACITY;
+}
+
+static int check_ctx(Ctx* c)
+{
+    if (!c) return GSB_ERR_INVALID;
+    cudaError_t e = cudaSetDevice(c->cfg.device);
+    if (e != cudaSuccess) {
+        set_error(c, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+        return GSB_ERR_CUDA;
+    }
+    return GSB_OK;
+}
+
+static void destroy_ctx(Ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    dev_free(c->rec); dev_free(c->grad_rec); dev_free(c->tile_rects); dev_free(c->touched); dev_free(c->offsets);
+    dev_free(c->act_tmp);
+    if (c->scan_ws) cudaFree(c->scan_ws);
+    for (int i = 0; i < 2; ++i) { dev_free(c->keys[i]); dev_free(c->vals[i]); dev_free(c->t_target[i]); }
+    dev_free(c->staged);
+    if (c->sort_ws) cudaFree(c->sort_ws);
+    if (c->cub_tmp) cudaFree(c->cub_tmp);
+    dev_free(c->dbg_keys); dev_free(c->dbg_vals);
+    dev_free(c->tile_ranges); dev_free(c->out_color); dev_free(c->out_depth); dev_free(c->out_alpha); dev_free(c->out_last);
+    dev_free(c->mapA); dev_free(c->mapB); dev_free(c->mapC); dev_free(c->cot_render); dev_free(c->partial);
+    dev_free(c->loss_accum); dev_free(c->d_ctl); dev_free(c->d_zero);
+    dev_free(c->t_block); dev_free(c->t_accum);
+    if (c->h_ctl) cudaFreeHost(c->h_ctl);
+    if (c->h_loss) cudaFreeHost(c->h_loss);
+    for (auto& e : c->ev_pool) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
+    cudaEvent_t* evs[] = {&c->ev_ctl, &c->t_target_ready[0], &c->t_target_ready[1],
+                          &c->t_target_free[0], &c->t_target_free[1]};
+    for (cudaEvent_t* e : evs) if (*e) cudaEventDestroy(*e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+}  // namespace gsb
+
+using gsb::Ctx;
+struct gsb_ctx : gsb::Ctx {};
+static inline Ctx* C(gsb_ctx* p) { return static_cast<Ctx*>(p); }
+
+#define CTX_PROLOGUE(ctxp)                        \
+    Ctx* c = C(ctxp);                             \
+    {                                             \
+        int _rc = gsb::check_ctx(c);              \
+        if (_rc != GSB_OK) return _rc;            \
+    }
+
+extern "C" {
+
+int gsb_abi_version(void) { return GSB_ABI_VERSION; }
+
+void gsb_default_config(gsb_config* cfg)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->width = 64; cfg->height = 64;
+    cfg->tile_w = 16; cfg->tile_h = 16;
+    cfg->sh_degree = 3; cfg->sh_coeffs = 16;
+    cfg->white_background = 0;
+    cfg->max_gaussians = 0;
+    cfg->device = 0;
+    cfg->flags = 0;
+    cfg->lambda_dssim = 0.2f;
+    cfg->adam_beta1 = 0.9f; cfg->adam_beta2 = 0.999f; cfg->adam_eps = 1e-15f;
+}
+
+const char* gsb_last_error(const gsb_ctx* ctx)
+{
+    if (!ctx) return gsb::g_create_error.c_str();
+    return static_cast<const Ctx*>(ctx)->err.c_str();
+}
+
+int gsb_create(const gsb_config* cfg, gsb_ctx** out)
+{
+    using namespace gsb;
+    if (!cfg || !out) { set_error(nullptr, "gsb_create: null argument"); return GSB_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->width < 1 || cfg->height < 1 || cfg->tile_w < 1 || cfg->tile_h < 1 || cfg->sh_degree < 0 || cfg->sh_degree > 4 ||
+        cfg->sh_coeffs < (cfg->sh_degree + 1) * (cfg->sh_degree + 1) || cfg->sh_coeffs > 25 || cfg->sh_coeffs < 1) {
+        set_error(nullptr, "gsb_create: invalid configuration (size, tile, sh_degree 0..4, (deg+1)^2 <= sh_coeffs <= 25)");
+        return GSB_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error(nullptr, std::string("gsb_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+        return GSB_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { set_error(nullptr, "gsb_create: bad device ordinal"); return GSB_ERR_INVALID; }
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { set_error(nullptr, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); return GSB_ERR_CUDA; }
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major != 10) {
+        set_error(nullptr, "gsb_create: this library contains sm_100a code only (Blackwell B200 required)");
+        return GSB_ERR_UNSUPPORTED;
+    }
+    gsb_ctx* h = new (std::nothrow) gsb_ctx();
+    if (!h) { set_error(nullptr, "out of host memory"); return GSB_ERR_INVALID; }
+    Ctx* c = h;
+    c->cfg = *cfg;
+    c->gridW = (cfg->width + cfg->tile_w - 1) / cfg->tile_w;
+    c->gridH = (cfg->height + cfg->tile_h - 1) / cfg->tile_h;
+    if (c->gridW > 65535 || c->gridH > 65535) { delete h; set_error(nullptr, "tile grid too large"); return GSB_ERR_UNSUPPORTED; }
+    c->numTiles = c->gridW * c->gridH;
+    c->tileBits = tile_bit_count(c->numTiles);
+    c->P = cfg->width * cfg->height;
+#define CREATE_CHECK(expr)                                                                  \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            set_error(nullptr, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+            destroy_ctx(c);                                                                 \
+            return GSB_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+    CREATE_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CREATE_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CREATE_CHECK(cudaEventCreateWithFlags(&c->ev_ctl, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        CREATE_CHECK(cudaEventCreateWithFlags(&c->t_target_ready[i], cudaEventDisableTiming));
+        CREATE_CHECK(cudaEventCreateWithFlags(&c->t_target_free[i], cudaEventDisableTiming));
+    }
+    const size_t P = (size_t)c->P;
+    CREATE_CHECK(dev_alloc(&c->tile_ranges, (size_t)c->numTiles * 2));
+    CREATE_CHECK(dev_alloc(&c->out_color, P * 3));
+    CREATE_CHECK(dev_alloc(&c->out_depth, P));
+    CREATE_CHECK(dev_alloc(&c->out_alpha, P));
+    CREATE_CHECK(dev_alloc(&c->out_last, P));
+    CREATE_CHECK(dev_alloc(&c->mapA, P * 3));
+    CREATE_CHECK(dev_alloc(&c->mapB, P * 3));
+    CREATE_CHECK(dev_alloc(&c->mapC, P * 3));
+    CREATE_CHECK(dev_alloc(&c->cot_render, P * 3));
+    CREATE_CHECK(dev_alloc(&c->partial, 2));
+    CREATE_CHECK(dev_alloc(&c->loss_accum, 4));
+    CREATE_CHECK(dev_alloc(&c->d_ctl, 4));
+    CREATE_CHECK(dev_alloc(&c->d_zero, 4));
+    c->d_one = c->d_zero + 1;
+    const uint32_t zo[4] = {0u, 1u, 0u, 0u};
+    CREATE_CHECK(cudaMemcpy(c->d_zero, zo, sizeof(zo), cudaMemcpyHostToDevice));
+    CREATE_CHECK(cudaMemset(c->loss_accum, 0, 4 * sizeof(float)));
+    CREATE_CHECK(cudaMallocHost(reinterpret_cast<void**>(&c->h_ctl), 4 * sizeof(uint32_t)));
+    CREATE_CHECK(cudaMallocHost(reinterpret_cast<void**>(&c->h_loss), 4 * sizeof(float)));
+#undef CREATE_CHECK
+    if (cfg->max_gaussians > 0) {
+        int rc = ensure_gaussians(c, cfg->max_gaussians);
+        if (rc != GSB_OK) { g_create_error = c->err; destroy_ctx(c); return rc; }
+    }
+    *out = h;
+    return GSB_OK;
+}
+
+void gsb_destroy(gsb_ctx* ctx) { gsb::destroy_ctx(C(ctx)); }
+
+int gsb_set_stream(gsb_ctx* ctx, void* cuda_stream)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : cudaStreamLegacy;
+    return GSB_OK;
+}
+
+int gsb_synchronize(gsb_ctx* ctx)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return GSB_OK;
+}
+
+// ---- activations ---------------------------------------------------------------------------------
+int gsb_activate_fwd(gsb_ctx* ctx, int32_t N, const float* f_dc, const float* f_rest, const float* scales_log,
+                     const float* rot_raw, const float* opacity_logit, float* shs, float* scales, float* rotations,
+                     float* opacity)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, N >= 0 && f_dc && scales_log && rot_raw && opacity_logit && shs && scales && rotations && opacity &&
+                       (f_rest || c->cfg.sh_coeffs == 1),
+                "gsb_activate_fwd: null argument");
+    GSB_CUDA_CHECK(c, gsb::launch_activate_fwd(c->stream, N, c->cfg.sh_coeffs, f_dc, f_rest, scales_log, rot_raw, opacity_logit,
+                                               shs, scales, rotations, opacity));
+    c->stats.kernel_launches += N > 0;
+    return GSB_OK;
+}
+
+int gsb_activate_bwd(gsb_ctx* ctx, int32_t N, const float* scales_log, const float* rot_raw, const float* opacity_logit,
+                     const float* g_shs, const float* g_scales, const float* g_rotations, const float* g_opacity,
+                     float* g_f_dc, float* g_f_rest, float* g_scales_log, float* g_rot_raw, float* g_opacity_logit)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, N >= 0 && scales_log && rot_raw && opacity_logit && g_shs && g_scales && g_rotations && g_opacity &&
+                       g_f_dc && (g_f_rest || c->cfg.sh_coeffs == 1) && g_scales_log && g_rot_raw && g_opacity_logit,
+                "gsb_activate_bwd: null argument");
+    GSB_CUDA_CHECK(c, gsb::launch_activate_bwd(c->stream, N, c->cfg.sh_coeffs, scales_log, rot_raw, opacity_logit, g_shs,
+                                               g_scales, g_rotations, g_opacity, g_f_dc, g_f_rest, g_scales_log, g_rot_raw,
+                                               g_opacity_logit));
+    c->stats.kernel_launches += N > 0;
+    return GSB_OK;
+}
+
+// ---- K1 / K2 -------------------------------------------------------------------------------------
+int gsb_project_fwd(gsb_ctx* ctx, int32_t N, const float* scales, const float* rotations, const float* means3d,
+                    const float* shs, const gsb_camera* host_cam, float* means2d, float* depths, float* color, float* cov2d,
+                    float* conic, float* radii, float* rect_min, float* rect_max)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, N >= 0 && scales && rotations && means3d && shs && host_cam && means2d && depths && color && cov2d &&
+                       conic && radii && rect_min && rect_max,
+                "gsb_project_fwd: null argument");
+    const gsb::ViewParams vp = gsb::make_view(c, host_cam);
+    gsb::StageTimer t(c, GSB_STAGE_PROJECT_FWD);
+    GSB_CUDA_CHECK(c, gsb::launch_project_fwd_api(c->stream, N, vp, scales, rotations, means3d, shs, means2d, depths, color,
+                                                  cov2d, conic, radii, rect_min, rect_max));
+    c->stats.kernel_launches += N > 0;
+    return GSB_OK;
+}
+
+int gsb_project_bwd(gsb_ctx* ctx, int32_t N, const float* scales, const float* rotations, const float* means3d,
+                    const float* shs, const gsb_camera* host_cam, const float* cot_depths, const float* cot_means2d,
+                    const float* cot_cov2d, const float* cot_color, const float* cot_conic, float* g_scales,
+                    float* g_rotations, float* g_means3d, float* g_shs, float* g_cam_center_point)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, N >= 0 && scales && rotations && means3d && shs && host_cam && cot_depths && cot_means2d && cot_cov2d &&
+                       cot_color && cot_conic && g_scales && g_rotations && g_means3d && g_shs && g_cam_center_point,
+                "gsb_project_bwd: null argument");
+    const gsb::ViewParams vp = gsb::make_view(c, host_cam);
+    gsb::StageTimer t(c, GSB_STAGE_PROJECT_BWD);
+    GSB_CUDA_CHECK(c, gsb::launch_project_bwd_api(c->stream, N, vp, scales, rotations, means3d, shs, cot_depths, cot_means2d,
+                                                  cot_cov2d, cot_color, cot_conic, g_scales, g_rotations, g_means3d, g_shs,
+                                                  g_cam_center_point));
+    c->stats.kernel_launches += N > 0;
+    return GSB_OK;
+}
+
+// ---- K3..K8 --------------------------------------------------------------------------------------
+int gsb_bin(gsb_ctx* ctx, int32_t N, const float* rect_min, const float* rect_max, const float* radii, const float* depths,
+            uint32_t* tiles_touched, uint32_t* tile_ranges, uint32_t* tile_counts, uint32_t* host_M)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, N >= 0 && rect_min && rect_max && radii && depths, "gsb_bin: null argument");
+    int rc = gsb::ensure_gaussians(c, N);
+    if (rc != GSB_OK) return rc;
+    const gsb::ViewParams vp = gsb::make_view_nocam(c);
+    c->saved.valid = false;
+    GSB_CUDA_CHECK(c, gsb::launch_count_tiles(c->stream, N, vp, rect_min, rect_max, radii, c->tile_rects, c->touched));
+    c->stats.kernel_launches += N > 0;
+    rc = gsb::run_binning(c, N, vp, depths, 1, nullptr, true);
+    if (rc != GSB_OK) return rc;
+    c->bin_valid = true;
+    c->bin_vp = vp;
+    if (tiles_touched && N > 0)
+        GSB_CUDA_CHECK(c, cudaMemcpyAsync(tiles_touched, c->touched, (size_t)N * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (tile_ranges)
+        GSB_CUDA_CHECK(c, cudaMemcpyAsync(tile_ranges, c->tile_ranges, (size_t)c->numTiles * 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (tile_counts) {
+        GSB_CUDA_CHECK(c, gsb::launch_tile_counts(c->stream, c->numTiles, c->tile_ranges, tile_counts));
+        c->stats.kernel_launches += 1;
+    }
+    if (host_M) *host_M = c->last_M;
+    c->stats.pairs_last_view = c->last_M;
+    return GSB_OK;
+}
+
+int gsb_bin_read(gsb_ctx* ctx, uint32_t* keys_high, uint32_t* keys_low, uint32_t* gauss_idx, uint32_t* sorted_keys_high,
+                 uint32_t* sorted_keys_low, uint32_t* sorted_gauss_idx)
+{
+    CTX_PROLOGUE(ctx);
+    if (!c->bin_valid && !c->saved.valid) { gsb::set_error(c, "gsb_bin_read: no binning result on this context"); return GSB_ERR_STATE; }
+    const uint32_t M = c->last_M;
+    if (M == 0) return GSB_OK;
+    if (keys_high || keys_low || gauss_idx) {
+        if (!c->dbg_keys) { gsb::set_error(c, "gsb_bin_read: unsorted keys are only kept by gsb_bin"); return GSB_ERR_STATE; }
+        GSB_CUDA_CHECK(c, gsb::launch_split_keys(c->stream, M, c->dbg_keys, keys_high, keys_low));
+        if (gauss_idx) GSB_CUDA_CHECK(c, cudaMemcpyAsync(gauss_idx, c->dbg_vals, (size_t)M * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (sorted_keys_high || sorted_keys_low || sorted_gauss_idx) {
+        uint32_t buf = 0;
+        GSB_CUDA_CHECK(c, cudaMemcpyAsync(&c->h_ctl[2], c->d_result_buf, 4, cudaMemcpyDeviceToHost, c->stream));
+        GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        buf = c->h_ctl[2];
+        GSB_CUDA_CHECK(c, gsb::launch_split_keys(c->stream, M, c->keys[buf], sorted_keys_high, sorted_keys_low));
+        if (sorted_gauss_idx)
+            GSB_CUDA_CHECK(c, cudaMemcpyAsync(sorted_gauss_idx, c->vals[buf], (size_t)M * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return GSB_OK;
+}
+
+int gsb_sort_tile_keys(gsb_ctx* ctx, uint32_t M, uint32_t tile_bits, const uint32_t* keys_high, const uint32_t* keys_low,
+                       const uint32_t* values, uint32_t* sorted_high, uint32_t* sorted_low, uint32_t* sorted_values,
+                       int32_t use_cub)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, tile_bits >= 1 && tile_bits <= 32, "gsb_sort_tile_keys: tile_bits must be 1..32");
+    if (M == 0) return GSB_OK;
+    GSB_REQUIRE(c, keys_high && keys_low && values && sorted_high && sorted_low && sorted_values, "gsb_sort_tile_keys: null argument");
+    // stand-alone buffers (does not disturb the context's tile lists)
+    uint64_t* k[2] = {nullptr, nullptr};
+    uint32_t* v[2] = {nullptr, nullptr};
+    void* ws = nullptr;
+    void* tmp = nullptr;
+    uint32_t* d_count = nullptr;
+    int rc = GSB_OK;
+    cudaError_t e = cudaSuccess;
+    const uint32_t end_bit = 32u + tile_bits;
+    const uint32_t hi_mask = tile_bits >= 32 ? 0xffffffffu : ((1u << tile_bits) - 1u);
+    auto fail = [&](cudaError_t err, const char* what) {
+        gsb::set_error(c, std::string(what) + ": " + cudaGetErrorString(err));
+        rc = GSB_ERR_CUDA;
+    };
+    do {
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = gsb::dev_alloc(&k[i], (size_t)M);
+            if (e == cudaSuccess) e = gsb::dev_alloc(&v[i], (size_t)M);
+        }
+        if (e == cudaSuccess) e = gsb::dev_alloc(&d_count, 1);
+        if (e != cudaSuccess) { fail(e, "cudaMalloc"); break; }
+        e = cudaMemcpyAsync(d_count, &M, 4, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = gsb::launch_merge_keys(c->stream, M, keys_high, keys_low, hi_mask, k[0]);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(v[0], values, (size_t)M * 4, cudaMemcpyDeviceToDevice, c->stream);
+        if (e != cudaSuccess) { fail(e, "merge keys"); break; }
+        uint32_t buf = 1;
+        if (use_cub) {
+            size_t need = 0;
+            e = gsb::cub_sort_pairs(c->stream, k[0], k[1], v[0], v[1], M, end_bit, nullptr, 0, &need);
+            if (e == cudaSuccess) e = cudaMalloc(&tmp, need ? need : 1);
+            if (e == cudaSuccess) e = gsb::cub_sort_pairs(c->stream, k[0], k[1], v[0], v[1], M, end_bit, tmp, need, nullptr);
+            if (e != cudaSuccess) { fail(e, "cub sort"); break; }
+        } else {
+            gsb::SortPlan plan = gsb::sort_plan(M, end_bit);
+            e = cudaMalloc(&ws, plan.ws_bytes);
+            const uint32_t* d_res = nullptr;
+            int launches = 0;
+            if (e == cudaSuccess) e = gsb::launch_onesweep_sort(c->stream, plan, k[0], k[1], v[0], v[1], d_count, ws, &d_res, &launches);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&c->h_ctl[2], d_res, 4, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) { fail(e, "onesweep sort"); break; }
+            buf = c->h_ctl[2];
+            c->stats.kernel_launches += launches;
+        }
+        e = gsb::launch_split_keys(c->stream, M, k[buf], sorted_high, sorted_low);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sorted_values, v[buf], (size_t)M * 4, cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { fail(e, "split keys"); break; }
+    } while (0);
+    if (rc != GSB_OK) cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 2; ++i) { if (k[i]) cudaFree(k[i]); if (v[i]) cudaFree(v[i]); }
+    if (ws) cudaFree(ws);
+    if (tmp) cudaFree(tmp);
+    if (d_count) cudaFree(d_count);
+    return rc;
+}
+
+// ---- K9 / K10 ------------------------------------------------------------------------------------
+static int restage_packed(Ctx* c, int32_t N, const float* packed)
+{
+    if (!c->bin_valid && !c->saved.valid) { gsb::set_error(c, "raster: call gsb_bin (or gsb_render_forward) first"); return GSB_ERR_STATE; }
+    if (N > c->capN) { gsb::set_error(c, "raster: N larger than the binned scene"); return GSB_ERR_INVALID; }
+    GSB_CUDA_CHECK(c, gsb::launch_packed_to_rec(c->stream, N, packed, c->rec));
+    GSB_CUDA_CHECK(c, gsb::launch_ranges_gather(c->stream, c->bin_vp, c->keys[0], c->keys[1], c->vals[0], c->vals[1],
+                                                c->d_result_buf, &c->d_ctl[0], c->capM, c->rec, c->tile_ranges, c->staged,
+                                                c->numTiles));
+    c->stats.kernel_launches += 2;
+    return GSB_OK;
+}
+
+int gsb_raster_fwd(gsb_ctx* ctx, int32_t N, const float* packed, float* out_color, float* out_depth, float* out_alpha,
+                   uint32_t* out_last_contrib)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, N >= 0 && packed && out_color && out_depth && out_alpha && out_last_contrib, "gsb_raster_fwd: null argument");
+    if (c->saved.valid) c->bin_vp = c->saved.vp;
+    int rc = restage_packed(c, N, packed);
+    if (rc != GSB_OK) return rc;
+    gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
+    GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, c->bin_vp, c->tile_ranges, c->staged, out_color, out_depth, out_alpha,
+                                             out_last_contrib));
+    c->stats.kernel_launches += 1;
+    return GSB_OK;
+}
+
+int gsb_raster_bwd(gsb_ctx* ctx, int32_t N, const float* packed, const float* cot_color, const float* cot_depth,
+                   const float* cot_alpha, const float* out_color, const float* out_depth, const float* out_alpha,
+                   const uint32_t* last_contrib, float* grad_packed)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, N >= 0 && packed && cot_color && out_color && out_depth && out_alpha && last_contrib && grad_packed,
+                "gsb_raster_bwd: null argument");
+    if (c->saved.valid) c->bin_vp = c->saved.vp;
+    int rc = restage_packed(c, N, packed);
+    if (rc != GSB_OK) return rc;
+    GSB_CUDA_CHECK(c, cudaMemsetAsync(c->grad_rec, 0, (size_t)N * gsb::REC_FLOATS * 4, c->stream));
+    {
+        gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
+        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, c->bin_vp, c->tile_ranges, c->staged, cot_color, cot_depth, cot_alpha,
+                                                 out_color, out_depth, out_alpha, last_contrib, c->grad_rec));
+    }
+    GSB_CUDA_CHECK(c, gsb::launch_rec_to_packed(c->stream, N, c->grad_rec, grad_packed));
+    c->stats.kernel_launches += 2;
+    return GSB_OK;
+}
+
+// ---- K11 / K12 -----------------------------------------------------------------------------------
+int gsb_ssim_fwd(gsb_ctx* ctx, int32_t H, int32_t W, int32_t Cn, const float* img1, const float* img2, float* ssim_map,
+                 float* mu1, float* mu2, float* sigma1_sq, float* sigma2_sq, float* sigma12)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, H >= 0 && W >= 0 && Cn >= 0 && img1 && img2 && ssim_map, "gsb_ssim_fwd: null argument");
+    GSB_CUDA_CHECK(c, gsb::launch_ssim_fwd(c->stream, H, W, Cn, img1, img2, ssim_map, mu1, mu2, sigma1_sq, sigma2_sq, sigma12));
+    c->stats.kernel_launches += 1;
+    return GSB_OK;
+}
+
+int gsb_ssim_bwd(gsb_ctx* ctx, int32_t H, int32_t W, int32_t Cn, const float* grad_out, const float* img1, const float* img2,
+                 float* grad_img1)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, H >= 0 && W >= 0 && Cn >= 0 && grad_out && img1 && img2 && grad_img1, "gsb_ssim_bwd: null argument");
+    const size_t n = (size_t)H * W * Cn;
+    float *a = c->mapA, *b = c->mapB, *m = c->mapC;
+    float* tmp = nullptr;
+    if (n > (size_t)c->P * 3) {  // image larger than the context's: temporary maps
+        GSB_CUDA_CHECK(c, gsb::dev_alloc(&tmp, n * 3));
+        a = tmp; b = tmp + n; m = tmp + 2 * n;
+    }
+    cudaError_t e = gsb::launch_ssim_bwd_api(c->stream, H, W, Cn, grad_out, img1, img2, a, b, m, grad_img1);
+    c->stats.kernel_launches += 3;
+    if (tmp) { cudaStreamSynchronize(c->stream); cudaFree(tmp); }
+    GSB_CUDA_CHECK(c, e);
+    return GSB_OK;
+}
+
+// ---- fused renderer ------------------------------------------------------------------------------
+static int render_forward_impl(Ctx* c, int32_t N, const float* xyz, const float* f_dc, const float* f_rest,
+                               const float* scales_log, const float* rot_raw, const float* opacity_logit,
+                               const gsb::ViewParams& vp, float* radii, uint8_t* visibility)
+{
+    int rc = gsb::ensure_gaussians(c, N);
+    if (rc != GSB_OK) return rc;
+    c->saved.valid = false;
+    c->bin_valid = false;
+    {
+        gsb::StageTimer t(c, GSB_STAGE_PROJECT_FWD);
+        GSB_CUDA_CHECK(c, gsb::launch_project_fused_fwd(c->stream, N, vp, xyz, f_dc, f_rest, scales_log, rot_raw, opacity_logit,
+                                                        c->rec, c->tile_rects, c->touched, radii, visibility));
+        c->stats.kernel_launches += N > 0;
+    }
+    rc = gsb::run_binning(c, N, vp, c->rec + 10, gsb::REC_FLOATS, c->rec, false);
+    if (rc != GSB_OK) return rc;
+    {
+        gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
+        GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, vp, c->tile_ranges, c->staged, c->out_color, c->out_depth,
+                                                 c->out_alpha, c->out_last));
+        c->stats.kernel_launches += 1;
+    }
+    c->saved.valid = true;
+    c->saved.N = N;
+    c->saved.xyz = xyz; c->saved.f_dc = f_dc; c->saved.f_rest = f_rest; c->saved.scales_log = scales_log;
+    c->saved.rot_raw = rot_raw; c->saved.op_logit = opacity_logit;
+    c->saved.vp = vp;
+    c->bin_vp = vp;
+    c->stats.pairs_last_view = c->last_M;
+    c->stats.pairs_total += c->last_M;
+    c->stats.views += 1;
+    return GSB_OK;
+}
+
+static int render_backward_impl(Ctx* c, const float* cot_render, const float* cot_depth, const float* cot_alpha, float* g_xyz,
+                                float* g_f_dc, float* g_f_rest, float* g_scales_log, float* g_rot_raw, float* g_opacity_logit,
+                                int accumulate)
+{
+    if (!c->saved.valid) { gsb::set_error(c, "gsb_render_backward: no forward saved on this context"); return GSB_ERR_STATE; }
+    const int N = c->saved.N;
+    const gsb::ViewParams& vp = c->saved.vp;
+    GSB_CUDA_CHECK(c, cudaMemsetAsync(c->grad_rec, 0, (size_t)N * gsb::REC_FLOATS * 4, c->stream));
+    {
+        gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
+        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, vp, c->tile_ranges, c->staged, cot_render, cot_depth, cot_alpha,
+                                                 c->out_color, c->out_depth, c->out_alpha, c->out_last, c->grad_rec));
+    }
+    {
+        gsb::StageTimer t(c, GSB_STAGE_PROJECT_BWD);
+        GSB_CUDA_CHECK(c, gsb::launch_project_fused_bwd(c->stream, N, vp, c->saved.xyz, c->saved.f_dc, c->saved.f_rest,
+                                                        c->saved.scales_log, c->saved.rot_raw, c->saved.op_logit, c->grad_rec,
+                                                        g_xyz, g_f_dc, g_f_rest, g_scales_log, g_rot_raw, g_opacity_logit,
+                                                        accumulate));
+    }
+    c->stats.kernel_launches += 1 + (N > 0);
+    return GSB_OK;
+}
+
+int gsb_render_forward(gsb_ctx* ctx, int32_t N, const float* xyz, const float* f_dc, const float* f_rest,
+                       const float* scales_log, const float* rot_raw, const float* opacity_logit, const gsb_camera* host_cam,
+                       float* render, float* depth, float* alpha, uint8_t* visibility, float* radii)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, N >= 0 && xyz && f_dc && (f_rest || c->cfg.sh_coeffs == 1) && scales_log && rot_raw && opacity_logit && host_cam,
+                "gsb_render_forward: null argument");
+    const gsb::ViewParams vp = gsb::make_view(c, host_cam);
+    int rc = render_forward_impl(c, N, xyz, f_dc, f_rest, scales_log, rot_raw, opacity_logit, vp, radii, visibility);
+    if (rc != GSB_OK) return rc;
+    const size_t P = (size_t)c->P;
+    if (render) GSB_CUDA_CHECK(c, cudaMemcpyAsync(render, c->out_color, P * 12, cudaMemcpyDeviceToDevice, c->stream));
+    if (depth) GSB_CUDA_CHECK(c, cudaMemcpyAsync(depth, c->out_depth, P * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (alpha) GSB_CUDA_CHECK(c, cudaMemcpyAsync(alpha, c->out_alpha, P * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return GSB_OK;
+}
+
+int gsb_render_backward(gsb_ctx* ctx, const float* cot_render, const float* cot_depth, const float* cot_alpha, float* g_xyz,
+                        float* g_f_dc, float* g_f_rest, float* g_scales_log, float* g_rot_raw, float* g_opacity_logit,
+                        int32_t accumulate)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, cot_render && g_xyz && g_f_dc && (g_f_rest || c->cfg.sh_coeffs == 1) && g_scales_log && g_rot_raw && g_opacity_logit,
+                "gsb_render_backward: null argument");
+    return render_backward_impl(c, cot_render, cot_depth, cot_alpha, g_xyz, g_f_dc, g_f_rest, g_scales_log, g_rot_raw,
+                                g_opacity_logit, accumulate);
+}
+
+// ---- loss ----------------------------------------------------------------------------------------
+static int loss_impl(Ctx* c, const float* render, const float* target, float grad_scale, float* cot_render, float* loss_accum)
+{
+    gsb::StageTimer t(c, GSB_STAGE_LOSS);
+    const int H = c->cfg.height, W = c->cfg.width;
+    const double n = (double)H * W * 3.0;
+    const float lambda = c->cfg.lambda_dssim;
+    // d total / d ssim_map = -lambda/n ; d total / d render (L1) = (1-lambda)/n * sign
+    const float upstream = (float)(-(double)lambda / n) * grad_scale;
+    const float l1_scale = (float)((1.0 - (double)lambda) / n) * grad_scale;
+    GSB_CUDA_CHECK(c, gsb::launch_loss_fwd(c->stream, H, W, 3, render, target, upstream, c->mapA, c->mapB, c->mapC, c->partial));
+    if (loss_accum) GSB_CUDA_CHECK(c, gsb::launch_loss_finalize(c->stream, c->partial, 1.0 / n, lambda, grad_scale, loss_accum));
+    GSB_CUDA_CHECK(c, gsb::launch_loss_bwd(c->stream, H, W, 3, render, target, c->mapA, c->mapB, c->mapC, l1_scale, cot_render));
+    c->stats.kernel_launches += 2 + (loss_accum != nullptr);
+    return GSB_OK;
+}
+
+int gsb_loss_fwd_bwd(gsb_ctx* ctx, const float* render, const float* target_rgb, float grad_scale, float* cot_render,
+                     float* loss_accum)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, render && target_rgb && cot_render, "gsb_loss_fwd_bwd: null argument");
+    return loss_impl(c, render, target_rgb, grad_scale, cot_render, loss_accum);
+}
+
+// ---- Adam ----------------------------------------------------------------------------------------
+int gsb_adam_step(gsb_ctx* ctx, int32_t N, float* const* host_params, const float* const* host_grads, float* const* host_m,
+                  float* const* host_v, const int64_t* host_counts, const float* host_lrs, float* grad_norm_accum)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, N >= 0 && host_params && host_grads && host_m && host_v && host_counts && host_lrs, "gsb_adam_step: null argument");
+    gsb::AdamTensors t{};
+    for (int k = 0; k < 6; ++k) {
+        GSB_REQUIRE(c, host_counts[k] >= 0 && (host_counts[k] == 0 || (host_params[k] && host_grads[k] && host_m[k] && host_v[k])),
+                    "gsb_adam_step: null tensor");
+        t.p[k] = host_params[k]; t.g[k] = host_grads[k]; t.m[k] = host_m[k]; t.v[k] = host_v[k];
+        t.count[k] = host_counts[k]; t.lr[k] = host_lrs[k];
+    }
+    GSB_REQUIRE(c, !grad_norm_accum || host_counts[0] >= (int64_t)N * 3, "gsb_adam_step: xyz tensor smaller than N*3");
+    gsb::StageTimer tm(c, GSB_STAGE_ADAM);
+    int launches = 0;
+    GSB_CUDA_CHECK(c, gsb::launch_adam(c->stream, t, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, N,
+                                       grad_norm_accum, nullptr, &launches));
+    c->stats.kernel_launches += launches;
+    return GSB_OK;
+}
+
+// ---- trainer -------------------------------------------------------------------------------------
+int gsb_trainer_init(gsb_ctx* ctx, int32_t N, const float* host_xyz, const float* host_f_dc, const float* host_f_rest,
+                     const float* host_scales_log, const float* host_rot_raw, const float* host_opacity_logit)
+{
+    CTX_PROLOGUE(ctx);
+    const int K = c->cfg.sh_coeffs;
+    GSB_REQUIRE(c, N > 0 && host_xyz && host_f_dc && (host_f_rest || K == 1) && host_scales_log && host_rot_raw && host_opacity_logit,
+                "gsb_trainer_init: null argument");
+    int rc = gsb::ensure_gaussians(c, N);
+    if (rc != GSB_OK) return rc;
+    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    gsb::dev_free(c->t_block); gsb::dev_free(c->t_accum);
+    const long long cnt[6] = {(long long)N * 3, (long long)N * 3, (long long)N * (K - 1) * 3, (long long)N * 3, (long long)N * 4, (long long)N};
+    size_t off[7];
+    off[0] = 0;
+    for (int k = 0; k < 6; ++k) {
+        c->t_count[k] = cnt[k];
+        off[k + 1] = off[k] + (((size_t)cnt[k] + 31) & ~(size_t)31);   // 128-byte aligned segments
+    }
+    c->t_floats = off[6];
+    GSB_CUDA_CHECK(c, gsb::dev_alloc(&c->t_block, c->t_floats * 4));
+    GSB_CUDA_CHECK(c, gsb::dev_alloc(&c->t_accum, (size_t)N));
+    GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block, 0, c->t_floats * 4 * sizeof(float), c->stream));
+    GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_accum, 0, (size_t)N * sizeof(float), c->stream));
+    const float* src[6] = {host_xyz, host_f_dc, host_f_rest, host_scales_log, host_rot_raw, host_opacity_logit};
+    for (int k = 0; k < 6; ++k) {
+        c->t_p[k] = c->t_block + off[k];
+        c->t_g[k] = c->t_block + c->t_floats + off[k];
+        c->t_m[k] = c->t_block + 2 * c->t_floats + off[k];
+        c->t_v[k] = c->t_block + 3 * c->t_floats + off[k];
+        if (cnt[k] > 0)
+            GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->t_p[k], src[k], (size_t)cnt[k] * 4, cudaMemcpyDefault, c->stream));
+    }
+    for (int i = 0; i < 2; ++i)
+        if (!c->t_target[i]) GSB_CUDA_CHECK(c, gsb::dev_alloc(&c->t_target[i], (size_t)c->P * 3));
+    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    c->tN = N;
+    return GSB_OK;
+}
+
+int gsb_trainer_param_ptrs(gsb_ctx* ctx, float** host_params6, float** host_grads6, float** host_m6, float** host_v6,
+                           float** grad_norm_accum)
+{
+    CTX_PROLOGUE(ctx);
+    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    for (int k = 0; k < 6; ++k) {
+        if (host_params6) host_params6[k] = c->t_p[k];
+        if (host_grads6) host_grads6[k] = c->t_g[k];
+        if (host_m6) host_m6[k] = c->t_m[k];
+        if (host_v6) host_v6[k] = c->t_v[k];
+    }
+    if (grad_norm_accum) *grad_norm_accum = c->t_accum;
+    return GSB_OK;
+}
+
+int gsb_trainer_grad_block(gsb_ctx* ctx, float** grad_block, int64_t* floats)
+{
+    CTX_PROLOGUE(ctx);
+    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    if (grad_block) *grad_block = c->t_block + c->t_floats;
+    if (floats) *floats = (int64_t)c->t_floats;
+    return GSB_OK;
+}
+
+int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
+                           int32_t targets_on_host, int32_t zero_grads, float grad_scale, float* host_loss)
+{
+    CTX_PROLOGUE(ctx);
+    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    GSB_REQUIRE(c, B >= 0 && (B == 0 || (host_cams && host_targets)), "gsb_trainer_accumulate: null argument");
+    const int N = c->tN;
+    const size_t img_bytes = (size_t)c->P * 3 * sizeof(float);
+    if (host_loss) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->loss_accum, 0, sizeof(float), c->stream));
+    if (zero_grads && B == 0) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + c->t_floats, 0, c->t_floats * 4, c->stream));
+    // prefetch of view 0's target
+    auto prefetch = [&](int b) -> int {
+        const int s = b & 1;
+        GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->copy_stream, c->t_target_free[s], 0));
+        GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->t_target[s], host_targets[b], img_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        GSB_CUDA_CHECK(c, cudaEventRecord(c->t_target_ready[s], c->copy_stream));
+        c->stats.stage_calls[GSB_STAGE_H2D] += 1;
+        return GSB_OK;
+    };
+    if (targets_on_host && B > 0) {
+        int rc = prefetch(0);
+        if (rc != GSB_OK) return rc;
+    }
+    for (int b = 0; b < B; ++b) {
+        GSB_REQUIRE(c, host_targets[b] != nullptr, "gsb_trainer_accumulate: null target");
+        if (targets_on_host && b + 1 < B) {
+            int rc = prefetch(b + 1);
+            if (rc != GSB_OK) return rc;
+        }
+        const gsb::ViewParams vp = gsb::make_view(c, &host_cams[b]);
+        int rc = render_forward_impl(c, N, c->t_p[0], c->t_p[1], c->t_p[2], c->t_p[3], c->t_p[4], c->t_p[5], vp, nullptr, nullptr);
+        if (rc != GSB_OK) return rc;
+        const float* target = host_targets[b];
+        if (targets_on_host) {
+            GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->t_target_ready[b & 1], 0));
+            target = c->t_target[b & 1];
+        }
+        rc = loss_impl(c, c->out_color, target, grad_scale, c->cot_render, host_loss ? c->loss_accum : nullptr);
+        if (rc != GSB_OK) return rc;
+        if (targets_on_host) GSB_CUDA_CHECK(c, cudaEventRecord(c->t_target_free[b & 1], c->stream));
+        const int accumulate = (b > 0 || !zero_grads) ? 1 : 0;
+        rc = render_backward_impl(c, c->cot_render, nullptr, nullptr, c->t_g[0], c->t_g[1], c->t_g[2], c->t_g[3], c->t_g[4],
+                                  c->t_g[5], accumulate);
+        if (rc != GSB_OK) return rc;
+    }
+    if (host_loss) {
+        GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->h_loss, c->loss_accum, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        *host_loss = c->h_loss[0];
+    }
+    return GSB_OK;
+}
+
+static void learning_rates(int iteration, int total, float* lrs)
+{
+    // GaussianModel.swift:56-65 (f32 arithmetic)
+    const float frac = 1.0f - (float)iteration / (float)total;
+    lrs[0] = 0.00016f * (frac > 0.01f ? frac : 0.01f);
+    lrs[1] = 0.0025f;
+    lrs[2] = 0.0025f / 20.0f;
+    lrs[3] = 0.005f;
+    lrs[4] = 0.001f;
+    lrs[5] = 0.025f;
+}
+
+int gsb_trainer_apply(gsb_ctx* ctx, int32_t iteration, int32_t total_iterations, int32_t reset_state)
+{
+    CTX_PROLOGUE(ctx);
+    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    GSB_REQUIRE(c, total_iterations > 0, "gsb_trainer_apply: total_iterations must be positive");
+    if (reset_state) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + 2 * c->t_floats, 0, 2 * c->t_floats * sizeof(float), c->stream));
+    gsb::AdamTensors t{};
+    learning_rates(iteration, total_iterations, t.lr);
+    for (int k = 0; k < 6; ++k) { t.p[k] = c->t_p[k]; t.g[k] = c->t_g[k]; t.m[k] = c->t_m[k]; t.v[k] = c->t_v[k]; t.count[k] = c->t_count[k]; }
+    gsb::StageTimer tm(c, GSB_STAGE_ADAM);
+    int launches = 0;
+    GSB_CUDA_CHECK(c, gsb::launch_adam(c->stream, t, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, c->tN,
+                                       c->t_accum, nullptr, &launches));
+    c->stats.kernel_launches += launches;
+    return GSB_OK;
+}
+
+int gsb_train_step(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
+                   int32_t targets_on_host, int32_t iteration, int32_t total_iterations, float* host_loss)
+{
+    GSB_REQUIRE(C(ctx), B > 0, "gsb_train_step: B must be positive");
+    int rc = gsb_trainer_accumulate(ctx, B, host_cams, host_targets, targets_on_host, 1, 1.0f / (float)B, host_loss);
+    if (rc != GSB_OK) return rc;
+    return gsb_trainer_apply(ctx, iteration, total_iterations, 0);
+}
+
+// ---- stats ---------------------------------------------------------------------------------------
+int gsb_stats_reset(gsb_ctx* ctx)
+{
+    CTX_PROLOGUE(ctx);
+    gsb::resolve_stage_events(c);
+    const uint64_t cap = c->stats.pair_capacity;
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->stats.pair_capacity = cap;
+    return GSB_OK;
+}
+int gsb_stats_get(gsb_ctx* ctx, gsb_stats* host_out)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, host_out, "gsb_stats_get: null argument");
+    gsb::resolve_stage_events(c);
+    *host_out = c->stats;
+    return GSB_OK;
+}
+int gsb_enable_stage_timing(gsb_ctx* ctx, int32_t on)
+{
+    CTX_PROLOGUE(ctx);
+    gsb::resolve_stage_events(c);
+    c->timing = on != 0;
+    return GSB_OK;
+}
+const char* gsb_stage_name(int32_t stage)
+{
+    return (stage >= 0 && stage < GSB_STAGE_COUNT) ? gsb::kStageNames[stage] : "";
+}
+
+}  // extern "C"

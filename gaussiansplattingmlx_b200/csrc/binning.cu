@@ -1,0 +1,593 @@
+// binning.cu — tile-intersection lists (K3..K8 of the reference) for sm_100a.
+//
+//   count (fused into projection) → single-pass decoupled-look-back scan → key duplication →
+//   hand-written ONESWEEP radix sort of 64-bit (tile_id << 32 | depth_bits) keys with 32-bit payloads →
+//   tile ranges + gather of the projected records into depth order.
+//
+// Reference: slang/gaussian_tile_global_kernels.slang:17-404 and the driver
+// Trainer/GaussianRenderer.swift:333-490 (two host syncs, single-threadgroup 4-bit sort, dense
+// [numTiles,maxTilePairs] padding).  Here nothing synchronises with the host: every kernel reads the
+// pair count M from device memory and is launched for the buffer capacity.
+//
+// All of this is HBM-bound integer work; the figures of merit are bytes moved per pair.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+
+#include "kernels.h"
+
+namespace gsb {
+
+// ------------------------------------------------------------------------------------------------
+// K3 on reference-layout inputs (parity API)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_count_tiles(int N, const __grid_constant__ ViewParams vp, const float* __restrict__ rectMin,
+                              const float* __restrict__ rectMax, const float* __restrict__ radii,
+                              uint2* __restrict__ tile_rects, uint32_t* __restrict__ touched)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    uint32_t cnt = 0;
+    if (radii[i] > 0.0f) {
+        // slang/gaussian_tile_global_kernels.slang:39-57
+        int tMinX = (int)floorf(rectMin[i * 2 + 0] / (float)vp.tileW);
+        int tMinY = (int)floorf(rectMin[i * 2 + 1] / (float)vp.tileH);
+        int tMaxX = (int)floorf(rectMax[i * 2 + 0] / (float)vp.tileW) + 1;
+        int tMaxY = (int)floorf(rectMax[i * 2 + 1] / (float)vp.tileH) + 1;
+        x0 = max(0, min(tMinX, vp.gridW));
+        y0 = max(0, min(tMinY, vp.gridH));
+        x1 = max(0, min(tMaxX, vp.gridW));
+        y1 = max(0, min(tMaxY, vp.gridH));
+        cnt = (uint32_t)((x1 - x0) * (y1 - y0));
+    }
+    if (cnt == 0) { x0 = y0 = x1 = y1 = 0; }
+    tile_rects[i] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
+    touched[i] = cnt;
+}
+
+cudaError_t launch_count_tiles(cudaStream_t st, int N, const ViewParams& vp, const float* rectMin, const float* rectMax,
+                               const float* radii, uint2* tile_rects, uint32_t* touched)
+{
+    if (N > 0) k_count_tiles<<<cdiv(N, 256), 256, 0, st>>>(N, vp, rectMin, rectMax, radii, tile_rects, touched);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan (replaces MLX cumsum + `.item()` host sync, GaussianRenderer.swift:398-409)
+// single pass, decoupled look-back; 2048 items per CTA
+// ------------------------------------------------------------------------------------------------
+constexpr int SC_THREADS = 256;
+constexpr int SC_IPT = 8;
+constexpr int SC_TILE = SC_THREADS * SC_IPT;
+constexpr uint64_t SC_FLAG_LOCAL = 1ull << 62;
+constexpr uint64_t SC_FLAG_INCL = 2ull << 62;
+constexpr uint64_t SC_VALUE_MASK = (1ull << 62) - 1;
+
+size_t scan_ws_bytes(int N) { return 16 + (size_t)cdiv(N > 0 ? N : 1, SC_TILE) * sizeof(uint64_t); }
+
+__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_exclusive_scan(int N, const uint32_t* __restrict__ in,
+                                                               uint32_t* __restrict__ out, uint32_t* __restrict__ total,
+                                                               uint32_t* counter, uint64_t* status)
+{
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[SC_THREADS / 32];
+    __shared__ uint32_t s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int base = tile * SC_TILE + threadIdx.x * SC_IPT;
+    uint32_t v[SC_IPT];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < SC_IPT; ++i) {
+        v[i] = (base + i < N) ? in[base + i] : 0u;
+        sum += v[i];
+    }
+    // block inclusive scan of per-thread sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < SC_THREADS / 32 ? s_warp[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        if (lane < SC_THREADS / 32) s_warp[lane] = winc - w;  // exclusive warp prefix
+        uint32_t block_total = __shfl_sync(0xffffffffu, winc, SC_THREADS / 32 - 1);
+        if (lane == 0) {
+            uint64_t excl = 0;
+            if (tile == 0) {
+                st_release_u64(&status[0], SC_FLAG_INCL | block_total);
+            } else {
+                st_release_u64(&status[tile], SC_FLAG_LOCAL | block_total);
+                int t = (int)tile - 1;
+                while (true) {
+                    uint64_t s = ld_acquire_u64(&status[t]);
+                    if ((s >> 62) == 0) continue;
+                    excl += s & SC_VALUE_MASK;
+                    if ((s >> 62) == 2) break;
+                    --t;
+                }
+                st_release_u64(&status[tile], SC_FLAG_INCL | (excl + block_total));
+            }
+            s_prefix = (uint32_t)excl;
+            if ((long long)(tile + 1) * SC_TILE >= N) *total = (uint32_t)excl + block_total;
+        }
+    }
+    __syncthreads();
+    uint32_t run = s_prefix + s_warp[warp] + (inc - sum);
+#pragma unroll
+    for (int i = 0; i < SC_IPT; ++i) {
+        if (base + i < N) out[base + i] = run;
+        run += v[i];
+    }
+}
+
+cudaError_t launch_exclusive_scan(cudaStream_t st, int N, const uint32_t* touched, uint32_t* offsets, uint32_t* total,
+                                  void* scan_ws)
+{
+    if (N <= 0) return cudaMemsetAsync(total, 0, sizeof(uint32_t), st);
+    cudaError_t e = cudaMemsetAsync(scan_ws, 0, scan_ws_bytes(N), st);
+    if (e != cudaSuccess) return e;
+    uint32_t* counter = reinterpret_cast<uint32_t*>(scan_ws);
+    uint64_t* status = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(scan_ws) + 16);
+    k_exclusive_scan<<<cdiv(N, SC_TILE), SC_THREADS, 0, st>>>(N, touched, offsets, total, counter, status);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 generate_keys (slang/gaussian_tile_global_kernels.slang:73-126): row-major tile order per
+// Gaussian, key = tile id (high word) | asuint(depth) (low word), payload = Gaussian index.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_generate_keys(int N, const __grid_constant__ ViewParams vp, const uint2* __restrict__ tile_rects,
+                                const uint32_t* __restrict__ offsets, const float* __restrict__ depth_ptr,
+                                int depth_stride, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                uint32_t capacity, const uint32_t* __restrict__ total, uint32_t* overflow_flag)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && *total > capacity) *overflow_flag = 1u;
+    if (i >= N) return;
+    uint2 r = tile_rects[i];
+    int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
+    if (x1 <= x0 || y1 <= y0) return;
+    uint32_t off = offsets[i];
+    uint32_t cnt = (uint32_t)((x1 - x0) * (y1 - y0));
+    if (off + cnt > capacity) return;  // flagged above; the step is redone with larger buffers
+    uint32_t depthBits = __float_as_uint(depth_ptr[(size_t)i * depth_stride]);
+    for (int ty = y0; ty < y1; ++ty)
+        for (int tx = x0; tx < x1; ++tx) {
+            uint32_t tile = (uint32_t)(ty * vp.gridW + tx);
+            keys[off] = ((uint64_t)tile << 32) | depthBits;
+            vals[off] = (uint32_t)i;
+            ++off;
+        }
+}
+
+cudaError_t launch_generate_keys(cudaStream_t st, int N, const ViewParams& vp, const uint2* tile_rects,
+                                 const uint32_t* offsets, const float* depth_ptr, int depth_stride, uint64_t* keys,
+                                 uint32_t* vals, uint32_t capacity, const uint32_t* total, uint32_t* overflow_flag)
+{
+    if (N > 0)
+        k_generate_keys<<<cdiv(N, 256), 256, 0, st>>>(N, vp, tile_rects, offsets, depth_ptr, depth_stride, keys, vals,
+                                                      capacity, total, overflow_flag);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// ONESWEEP radix sort: 8-bit digits, one upfront histogram of every digit place, then one
+// chained-scan (decoupled look-back) + scatter kernel per digit place.  Stable.
+// Replaces radix_sort_tile_keys_fused_forward (one 128-thread threadgroup, 4-bit digits,
+// slang/gaussian_tile_global_kernels.slang:143-305).
+// Digit places whose histogram has a single occupied bin are skipped (device-side decision).
+// ------------------------------------------------------------------------------------------------
+constexpr int OS_THREADS = 256;
+constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr int OS_IPT = 16;
+constexpr int OS_TILE = OS_THREADS * OS_IPT;  // 4096 pairs per CTA
+constexpr int OS_RADIX = 256;
+constexpr int OS_MAX_PASSES = 8;
+constexpr uint32_t OS_FLAG_LOCAL = 1u << 30;
+constexpr uint32_t OS_FLAG_INCL = 2u << 30;
+constexpr uint32_t OS_VALUE_MASK = (1u << 30) - 1;
+
+__host__ __device__ inline uint32_t os_digit_mask(int end_bit, int pass)
+{
+    int bits = end_bit - 8 * pass;
+    return bits >= 8 ? 255u : ((1u << (bits > 0 ? bits : 0)) - 1u);
+}
+
+struct SortCtl {
+    uint32_t tile_counter[OS_MAX_PASSES];
+    uint32_t skip[OS_MAX_PASSES];
+    uint32_t src_buf[OS_MAX_PASSES];
+    uint32_t result_buf;
+    uint32_t count;
+    uint32_t num_tiles;
+    uint32_t pad[5];
+};
+static_assert(sizeof(SortCtl) == 128, "SortCtl layout");
+
+SortPlan sort_plan(uint32_t capacity, uint32_t end_bit)
+{
+    SortPlan p;
+    p.capacity = capacity;
+    p.max_tiles = (uint32_t)cdiv(capacity > 0 ? capacity : 1, OS_TILE);
+    p.end_bit = end_bit;
+    p.passes = (end_bit + 7) / 8;
+    if (p.passes < 1) p.passes = 1;
+    if (p.passes > OS_MAX_PASSES) p.passes = OS_MAX_PASSES;
+    p.ws_bytes = sizeof(SortCtl) + (size_t)OS_MAX_PASSES * OS_RADIX * 4 + (size_t)p.passes * p.max_tiles * OS_RADIX * 4;
+    return p;
+}
+
+__global__ void __launch_bounds__(256) k_os_histogram(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ d_count,
+                                                      uint32_t capacity, int passes, int end_bit, uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t sh[OS_MAX_PASSES * OS_RADIX];
+    for (int i = threadIdx.x; i < passes * OS_RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint32_t count = min(*d_count, capacity);
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {
+        uint32_t idx = base + lane;
+        bool valid = idx < count;
+        uint64_t key = valid ? keys[idx] : 0ull;
+        uint32_t m = __ballot_sync(0xffffffffu, valid);
+        int leader = __ffs(m) - 1;
+        for (int p = 0; p < passes; ++p) {
+            uint32_t d = (uint32_t)(key >> (8 * p)) & os_digit_mask(end_bit, p);
+            uint32_t d0 = __shfl_sync(0xffffffffu, d, leader);
+            bool uni = __all_sync(0xffffffffu, !valid || d == d0);
+            if (uni) {
+                if (lane == leader) atomicAdd(&sh[p * OS_RADIX + d], (uint32_t)__popc(m));
+            } else if (valid) {
+                atomicAdd(&sh[p * OS_RADIX + d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * OS_RADIX; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// one CTA: per digit place, exclusive scan of the 256 bins, skip decision, buffer ping-pong plan
+__global__ void __launch_bounds__(OS_RADIX) k_os_scan(SortCtl* ctl, uint32_t* hist, const uint32_t* __restrict__ d_count,
+                                                      uint32_t capacity, int passes)
+{
+    __shared__ uint32_t s_warp[OS_RADIX / 32];
+    __shared__ uint32_t s_skip[OS_MAX_PASSES];
+    const uint32_t count = min(*d_count, capacity);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int p = 0; p < passes; ++p) {
+        uint32_t c = hist[p * OS_RADIX + threadIdx.x];
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        int trivial = __syncthreads_or(count > 0 && c == count);
+        uint32_t wprefix = 0;
+        for (int w = 0; w < warp; ++w) wprefix += s_warp[w];
+        hist[p * OS_RADIX + threadIdx.x] = wprefix + inc - c;
+        if (threadIdx.x == 0) s_skip[p] = (trivial || count <= 1) ? 1u : 0u;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint32_t cur = 0;
+        for (int p = 0; p < passes; ++p) {
+            ctl->skip[p] = s_skip[p];
+            ctl->src_buf[p] = cur;
+            if (!s_skip[p]) cur ^= 1u;
+        }
+        ctl->result_buf = cur;
+        ctl->count = count;
+        ctl->num_tiles = (count + OS_TILE - 1) / OS_TILE;
+    }
+}
+
+struct OsSmem {
+    uint64_t keys[OS_TILE];
+    uint32_t vals[OS_TILE];
+    uint32_t warp_hist[OS_WARPS][OS_RADIX];
+    uint32_t block_excl[OS_RADIX];
+    uint32_t digit_base[OS_RADIX];
+    uint32_t warp_tot[OS_RADIX / 32];
+    uint32_t tile;
+};
+
+__global__ void __launch_bounds__(OS_THREADS) k_os_pass(int pass, uint32_t dmask, SortCtl* ctl, const uint32_t* __restrict__ hist_excl,
+                                                        uint32_t* lookback, uint32_t max_tiles, uint64_t* keys0,
+                                                        uint64_t* keys1, uint32_t* vals0, uint32_t* vals1)
+{
+    extern __shared__ __align__(16) unsigned char os_raw[];
+    OsSmem& S = *reinterpret_cast<OsSmem*>(os_raw);
+    if (ctl->skip[pass]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) S.tile = atomicAdd(&ctl->tile_counter[pass], 1u);
+    for (int i = tid; i < OS_WARPS * OS_RADIX; i += OS_THREADS) (&S.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = S.tile;
+    const uint32_t count = ctl->count;
+    if (tile >= ctl->num_tiles) return;
+    const uint32_t src = ctl->src_buf[pass];
+    const uint64_t* kin = src ? keys1 : keys0;
+    const uint32_t* vin = src ? vals1 : vals0;
+    uint64_t* kout = src ? keys0 : keys1;
+    uint32_t* vout = src ? vals0 : vals1;
+    const uint32_t tile_base = tile * OS_TILE;
+    const uint32_t valid = min((uint32_t)OS_TILE, count - tile_base);
+    const int shift = pass * 8;
+
+    // warp-striped load: stability order is (warp, item, lane)
+    uint64_t key[OS_IPT];
+    const uint32_t wbase = warp * (OS_IPT * 32);
+#pragma unroll
+    for (int i = 0; i < OS_IPT; ++i) {
+        uint32_t idx = wbase + i * 32 + lane;
+        key[i] = idx < valid ? kin[tile_base + idx] : ~0ull;
+    }
+    // per-warp stable ranking with match.any
+    uint16_t rank[OS_IPT];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < OS_IPT; ++i) {
+        uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
+        uint32_t m = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(m) - 1;
+        uint32_t old = 0;
+        if (lane == leader) {
+            old = S.warp_hist[warp][d];
+            S.warp_hist[warp][d] = old + __popc(m);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[i] = (uint16_t)(old + __popc(m & lt_mask));
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: prefix over warps, publish, look back, block-exclusive scan
+    {
+        const int d = tid;  // OS_THREADS == OS_RADIX
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < OS_WARPS; ++w) {
+            uint32_t c = S.warp_hist[w][d];
+            S.warp_hist[w][d] = run;
+            run += c;
+        }
+        uint32_t total_valid = run;
+        if ((uint32_t)d == dmask) total_valid -= (OS_TILE - valid);
+        uint32_t* lb = lookback + ((size_t)pass * max_tiles + tile) * OS_RADIX + d;
+        uint32_t excl_prev = 0;
+        if (tile == 0) {
+            st_release_u32(lb, OS_FLAG_INCL | total_valid);
+        } else {
+            st_release_u32(lb, OS_FLAG_LOCAL | total_valid);
+            int t = (int)tile - 1;
+            while (true) {
+                uint32_t v = ld_acquire_u32(lookback + ((size_t)pass * max_tiles + t) * OS_RADIX + d);
+                if ((v >> 30) == 0) continue;
+                excl_prev += v & OS_VALUE_MASK;
+                if ((v >> 30) == 2) break;
+                --t;
+            }
+            st_release_u32(lb, OS_FLAG_INCL | (excl_prev + total_valid));
+        }
+        // block-exclusive scan of `run` over the 256 digits
+        uint32_t inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) S.warp_tot[warp] = inc;
+        __syncthreads();
+        uint32_t wprefix = 0;
+        for (int w = 0; w < warp; ++w) wprefix += S.warp_tot[w];
+        uint32_t bex = wprefix + inc - run;
+        S.block_excl[d] = bex;
+        S.digit_base[d] = hist_excl[pass * OS_RADIX + d] + excl_prev - bex;
+    }
+    __syncthreads();
+    // scatter into block-sorted order in shared memory
+#pragma unroll
+    for (int i = 0; i < OS_IPT; ++i) {
+        uint32_t idx = wbase + i * 32 + lane;
+        uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
+        uint32_t pos = S.block_excl[d] + S.warp_hist[warp][d] + rank[i];
+        S.keys[pos] = key[i];
+        S.vals[pos] = idx < valid ? vin[tile_base + idx] : 0u;
+    }
+    __syncthreads();
+    // coalesced runs out
+    for (uint32_t idx = tid; idx < valid; idx += OS_THREADS) {
+        uint64_t k = S.keys[idx];
+        uint32_t d = (uint32_t)(k >> shift) & dmask;
+        uint32_t dst = S.digit_base[d] + idx;
+        kout[dst] = k;
+        vout[dst] = S.vals[idx];
+    }
+}
+
+cudaError_t launch_onesweep_sort(cudaStream_t st, const SortPlan& plan, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0,
+                                 uint32_t* vals1, const uint32_t* d_count, void* ws, const uint32_t** result_buf_ptr,
+                                 int* launches)
+{
+    SortCtl* ctl = reinterpret_cast<SortCtl*>(ws);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + sizeof(SortCtl));
+    uint32_t* lookback = hist + OS_MAX_PASSES * OS_RADIX;
+    if (result_buf_ptr) *result_buf_ptr = &ctl->result_buf;
+    cudaError_t e = cudaMemsetAsync(ws, 0, plan.ws_bytes, st);
+    if (e != cudaSuccess) return e;
+    int hist_blocks = (int)std::min<uint32_t>(plan.max_tiles, 148u * 8u);
+    k_os_histogram<<<hist_blocks, 256, 0, st>>>(keys0, d_count, plan.capacity, (int)plan.passes, (int)plan.end_bit, hist);
+    k_os_scan<<<1, OS_RADIX, 0, st>>>(ctl, hist, d_count, plan.capacity, (int)plan.passes);
+    static bool attr_set = false;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(k_os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    for (uint32_t p = 0; p < plan.passes; ++p)
+        k_os_pass<<<plan.max_tiles, OS_THREADS, sizeof(OsSmem), st>>>((int)p, os_digit_mask((int)plan.end_bit, (int)p), ctl, hist, lookback, plan.max_tiles, keys0,
+                                                                      keys1, vals0, vals1);
+    if (launches) *launches += 2 + (int)plan.passes;
+    return cudaGetLastError();
+}
+
+cudaError_t cub_sort_pairs(cudaStream_t st, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1,
+                           uint32_t count, uint32_t end_bit, void* tmp, size_t tmp_bytes, size_t* tmp_needed)
+{
+    size_t need = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, need, keys0, keys1, vals0, vals1, (int)count, 0, (int)end_bit, st);
+    if (e != cudaSuccess) return e;
+    if (tmp_needed) *tmp_needed = need;
+    if (!tmp || tmp_bytes < need) return cudaSuccess;  // size query only
+    return cub::DeviceRadixSort::SortPairs(tmp, need, keys0, keys1, vals0, vals1, (int)count, 0, (int)end_bit, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6/K7 (slang/gaussian_tile_global_kernels.slang:314-367) + gather of records into tile/depth order.
+// Three threads per pair: each moves one 16-byte third of the 48-byte record (coalesced stores);
+// the first of the three also does the tile-boundary detection.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ranges_gather(const uint64_t* __restrict__ keys0, const uint64_t* __restrict__ keys1,
+                                                       const uint32_t* __restrict__ vals0, const uint32_t* __restrict__ vals1,
+                                                       const uint32_t* __restrict__ d_result_buf,
+                                                       const uint32_t* __restrict__ d_count, uint32_t capacity,
+                                                       const float4* __restrict__ rec, uint32_t* __restrict__ tile_ranges,
+                                                       float4* __restrict__ staged)
+{
+    const uint32_t M = min(*d_count, capacity);
+    const uint32_t buf = d_result_buf ? *d_result_buf : 0u;
+    const uint64_t* keys = buf ? keys1 : keys0;
+    const uint32_t* vals = buf ? vals1 : vals0;
+    const uint64_t total = (uint64_t)M * 3u;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t j = (uint32_t)(g / 3u), part = (uint32_t)(g - (uint64_t)j * 3u);
+        uint32_t gi = vals[j];
+        if (rec) staged[(size_t)j * 3 + part] = rec[(size_t)gi * 3 + part];
+        if (part == 0) {
+            uint32_t cur = (uint32_t)(keys[j] >> 32);
+            if (j == 0) {
+                tile_ranges[cur * 2 + 0] = 0;
+            } else {
+                uint32_t prev = (uint32_t)(keys[j - 1] >> 32);
+                if (cur != prev) {
+                    tile_ranges[prev * 2 + 1] = j;
+                    tile_ranges[cur * 2 + 0] = j;
+                }
+            }
+            if (j == M - 1) tile_ranges[cur * 2 + 1] = M;
+        }
+    }
+}
+
+cudaError_t launch_ranges_gather(cudaStream_t st, const ViewParams& vp, const uint64_t* keys0, const uint64_t* keys1,
+                                 const uint32_t* vals0, const uint32_t* vals1, const uint32_t* d_result_buf,
+                                 const uint32_t* d_count, uint32_t capacity, const float* rec, uint32_t* tile_ranges,
+                                 float* staged, int numTiles)
+{
+    cudaError_t e = cudaMemsetAsync(tile_ranges, 0, (size_t)numTiles * 2 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    if (capacity == 0) return cudaSuccess;
+    int blocks = (int)std::min<uint64_t>(((uint64_t)capacity * 3 + 255) / 256, 148ull * 16ull);
+    k_ranges_gather<<<blocks, 256, 0, st>>>(keys0, keys1, vals0, vals1, d_result_buf, d_count, capacity,
+                                            reinterpret_cast<const float4*>(rec), tile_ranges,
+                                            reinterpret_cast<float4*>(staged));
+    return cudaGetLastError();
+}
+
+__global__ void k_tile_counts(int numTiles, const uint32_t* __restrict__ ranges, uint32_t* __restrict__ counts)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numTiles) return;
+    uint32_t s = ranges[t * 2], e = ranges[t * 2 + 1];
+    counts[t] = e > s ? e - s : 0u;
+}
+
+cudaError_t launch_tile_counts(cudaStream_t st, int numTiles, const uint32_t* tile_ranges, uint32_t* tile_counts)
+{
+    if (numTiles > 0) k_tile_counts<<<cdiv(numTiles, 256), 256, 0, st>>>(numTiles, tile_ranges, tile_counts);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout helpers for the parity API
+// ------------------------------------------------------------------------------------------------
+__global__ void k_packed_to_rec(int N, const float* __restrict__ packed, float* __restrict__ rec)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * REC_FLOATS) return;
+    int p = i / REC_FLOATS, c = i - p * REC_FLOATS;
+    rec[i] = c < 11 ? packed[(size_t)p * 11 + c] : __uint_as_float((uint32_t)p);
+}
+__global__ void k_rec_to_packed(int N, const float* __restrict__ rec, float* __restrict__ packed)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * 11) return;
+    int p = i / 11, c = i - p * 11;
+    packed[i] = rec[(size_t)p * REC_FLOATS + c];
+}
+cudaError_t launch_packed_to_rec(cudaStream_t st, int N, const float* packed, float* rec)
+{
+    if (N > 0) k_packed_to_rec<<<cdiv((long long)N * REC_FLOATS, 256), 256, 0, st>>>(N, packed, rec);
+    return cudaGetLastError();
+}
+cudaError_t launch_rec_to_packed(cudaStream_t st, int N, const float* rec, float* packed)
+{
+    if (N > 0) k_rec_to_packed<<<cdiv((long long)N * 11, 256), 256, 0, st>>>(N, rec, packed);
+    return cudaGetLastError();
+}
+
+__global__ void k_split_keys(uint32_t M, const uint64_t* __restrict__ keys, uint32_t* __restrict__ hi, uint32_t* __restrict__ lo)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    uint64_t k = keys[i];
+    if (hi) hi[i] = (uint32_t)(k >> 32);
+    if (lo) lo[i] = (uint32_t)k;
+}
+__global__ void k_merge_keys(uint32_t M, const uint32_t* __restrict__ hi, const uint32_t* __restrict__ lo, uint32_t hi_mask,
+                             uint64_t* __restrict__ keys)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    keys[i] = ((uint64_t)(hi[i] & hi_mask) << 32) | lo[i];
+}
+cudaError_t launch_split_keys(cudaStream_t st, uint32_t M, const uint64_t* keys, uint32_t* hi, uint32_t* lo)
+{
+    if (M > 0) k_split_keys<<<cdiv(M, 256), 256, 0, st>>>(M, keys, hi, lo);
+    return cudaGetLastError();
+}
+cudaError_t launch_merge_keys(cudaStream_t st, uint32_t M, const uint32_t* hi, const uint32_t* lo, uint32_t hi_mask,
+                              uint64_t* keys)
+{
+    if (M > 0) k_merge_keys<<<cdiv(M, 256), 256, 0, st>>>(M, hi, lo, hi_mask, keys);
+    return cudaGetLastError();
+}
+
+}  // namespace gsb

@@ -1,0 +1,121 @@
+// kernels.h — internal launcher declarations (one per .cu), all enqueue on the given stream.
+#pragma once
+#include "common.cuh"
+
+namespace gsb {
+
+// ---- project.cu --------------------------------------------------------------------------------
+cudaError_t launch_activate_fwd(cudaStream_t st, int N, int K, const float* f_dc, const float* f_rest,
+                                const float* scales_log, const float* rot_raw, const float* op_logit, float* shs,
+                                float* scales, float* rotations, float* opacity);
+cudaError_t launch_activate_bwd(cudaStream_t st, int N, int K, const float* scales_log, const float* rot_raw,
+                                const float* op_logit, const float* g_shs, const float* g_scales, const float* g_rot,
+                                const float* g_op, float* g_f_dc, float* g_f_rest, float* g_scales_log, float* g_rot_raw,
+                                float* g_op_logit);
+cudaError_t launch_project_fwd_api(cudaStream_t st, int N, const ViewParams& vp, const float* scales,
+                                   const float* rotations, const float* means3d, const float* shs, float* means2d,
+                                   float* depths, float* color, float* cov2d, float* conic, float* radii, float* rectMin,
+                                   float* rectMax);
+cudaError_t launch_project_bwd_api(cudaStream_t st, int N, const ViewParams& vp, const float* scales,
+                                   const float* rotations, const float* means3d, const float* shs,
+                                   const float* cotDepths, const float* cotMeans2d, const float* cotCov2d,
+                                   const float* cotColor, const float* cotConic, float* gScales, float* gRot,
+                                   float* gMeans3d, float* gShs, float* gCam);
+cudaError_t launch_project_fused_fwd(cudaStream_t st, int N, const ViewParams& vp, const float* xyz, const float* f_dc,
+                                     const float* f_rest, const float* scales_log, const float* rot_raw,
+                                     const float* op_logit, float* rec, uint2* tile_rects, uint32_t* touched,
+                                     float* radii_out, uint8_t* vis_out);
+size_t project_fused_smem_bytes(int K);
+cudaError_t launch_project_fused_bwd(cudaStream_t st, int N, const ViewParams& vp, const float* xyz, const float* f_dc,
+                                     const float* f_rest, const float* scales_log, const float* rot_raw,
+                                     const float* op_logit, const float* grad_rec, float* g_xyz, float* g_f_dc,
+                                     float* g_f_rest, float* g_scales, float* g_rot, float* g_op, int accumulate);
+
+// ---- binning.cu --------------------------------------------------------------------------------
+// Tile rectangles + counts from reference-layout rect/radii (K3).
+cudaError_t launch_count_tiles(cudaStream_t st, int N, const ViewParams& vp, const float* rectMin, const float* rectMax,
+                               const float* radii, uint2* tile_rects, uint32_t* touched);
+// Exclusive scan of touched[N] → offsets[N]; *total (device) = M.  scan_ws: >= scan_ws_bytes(N).
+size_t scan_ws_bytes(int N);
+cudaError_t launch_exclusive_scan(cudaStream_t st, int N, const uint32_t* touched, uint32_t* offsets, uint32_t* total,
+                                  void* scan_ws);
+// K4: emit 64-bit keys (tile << 32 | depth bits) and gaussian indices; depth read at depth_ptr[i*depth_stride].
+cudaError_t launch_generate_keys(cudaStream_t st, int N, const ViewParams& vp, const uint2* tile_rects,
+                                 const uint32_t* offsets, const float* depth_ptr, int depth_stride, uint64_t* keys,
+                                 uint32_t* vals, uint32_t capacity, const uint32_t* total, uint32_t* overflow_flag);
+
+// Onesweep LSD radix sort of (u64 key, u32 value) over key bits [0, end_bit).
+struct SortPlan {
+    uint32_t capacity = 0;      // max number of pairs
+    uint32_t max_tiles = 0;
+    uint32_t passes = 0;
+    uint32_t end_bit = 0;
+    size_t ws_bytes = 0;        // workspace: histograms, look-back state, counters, control block
+};
+SortPlan sort_plan(uint32_t capacity, uint32_t end_bit);
+// keys/vals double buffers [2]; count read from device *d_count (clamped to capacity).  On return the
+// sorted data sits in buffer index *d_result_buf (device u32, inside the workspace control block,
+// pointer returned via result_buf_ptr).
+cudaError_t launch_onesweep_sort(cudaStream_t st, const SortPlan& plan, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0,
+                                 uint32_t* vals1, const uint32_t* d_count, void* ws, const uint32_t** result_buf_ptr,
+                                 int* launches);
+// CUB baseline (checked against, never the product path unless GSB_FLAG_SORT_CUB): sorts count pairs
+// (host-known) from keys0/vals0 into keys1/vals1.
+cudaError_t cub_sort_pairs(cudaStream_t st, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1,
+                           uint32_t count, uint32_t end_bit, void* tmp, size_t tmp_bytes, size_t* tmp_needed);
+
+// K6/K7 + record gather: tile ranges/counts from the sorted keys, and the depth-ordered contiguous
+// record stream staged[j] = rec[sorted_val[j]] that the rasteriser bulk-copies.
+cudaError_t launch_ranges_gather(cudaStream_t st, const ViewParams& vp, const uint64_t* keys0, const uint64_t* keys1,
+                                 const uint32_t* vals0, const uint32_t* vals1, const uint32_t* d_result_buf,
+                                 const uint32_t* d_count, uint32_t capacity, const float* rec, uint32_t* tile_ranges,
+                                 float* staged, int numTiles);
+cudaError_t launch_tile_counts(cudaStream_t st, int numTiles, const uint32_t* tile_ranges, uint32_t* tile_counts);
+// packed[N,11] (reference layout) → rec[N,12]
+cudaError_t launch_packed_to_rec(cudaStream_t st, int N, const float* packed, float* rec);
+cudaError_t launch_rec_to_packed(cudaStream_t st, int N, const float* rec, float* packed);
+// split / merge helpers for the parity API
+cudaError_t launch_split_keys(cudaStream_t st, uint32_t M, const uint64_t* keys, uint32_t* hi, uint32_t* lo);
+cudaError_t launch_merge_keys(cudaStream_t st, uint32_t M, const uint32_t* hi, const uint32_t* lo, uint32_t hi_mask,
+                              uint64_t* keys);
+
+// ---- raster.cu ---------------------------------------------------------------------------------
+cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges, const float* staged,
+                              float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last);
+cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges, const float* staged,
+                              const float* cot_color, const float* cot_depth, const float* cot_alpha,
+                              const float* out_color, const float* out_depth, const float* out_alpha,
+                              const uint32_t* last_contrib, float* grad_rec);
+
+// ---- loss.cu -----------------------------------------------------------------------------------
+// separable SSIM (11x11, sigma 1.5, centre 5.5) forward with optional saved maps
+cudaError_t launch_ssim_fwd(cudaStream_t st, int H, int W, int C, const float* img1, const float* img2, float* ssim_map,
+                            float* mu1, float* mu2, float* s1, float* s2, float* s12);
+// fused loss forward: writes the three "dSSIM/d(window statistic) x upstream" maps and accumulates
+// sum|d| and sum(ssim) into partial[2] (double).
+cudaError_t launch_loss_fwd(cudaStream_t st, int H, int W, int C, const float* render, const float* target,
+                            float upstream, float* mapA, float* mapB, float* mapC, double* partial);
+// fused loss backward: cot_render = l1_scale*sign(render-target) + conv^T(maps); finalises the loss scalar.
+cudaError_t launch_loss_bwd(cudaStream_t st, int H, int W, int C, const float* render, const float* target,
+                            const float* mapA, const float* mapB, const float* mapC, float l1_scale, float* cot_render);
+cudaError_t launch_loss_finalize(cudaStream_t st, const double* partial, double inv_count, float lambda, float scale,
+                                 float* loss_accum);
+// generic ssim backward for the parity API (upstream map given)
+cudaError_t launch_ssim_bwd_api(cudaStream_t st, int H, int W, int C, const float* grad_out, const float* img1,
+                                const float* img2, float* mapA, float* mapB, float* mapC, float* grad_img1);
+
+// ---- adam.cu -----------------------------------------------------------------------------------
+struct AdamTensors {
+    float* p[6];
+    const float* g[6];
+    float* m[6];
+    float* v[6];
+    long long count[6];
+    float lr[6];
+};
+// gscale multiplies every gradient before use (1.0 on the training path); launches (may be NULL) is
+// incremented by the number of kernels launched.
+cudaError_t launch_adam(cudaStream_t st, const AdamTensors& t, float beta1, float beta2, float eps, float gscale, int N,
+                        float* grad_norm_accum, const uint32_t* skip_flag, int* launches);
+
+}  // namespace gsb

@@ -1,0 +1,330 @@
+"""GPU parity: every stage of libgsb.so (through the C ABI) against the CPU oracle on seeded scenes.
+
+Tolerances are the ones BASELINE.json's north_star states: tile-intersection counts and sorted key
+lists bit-exact, forward pixels <= 1e-4 max-abs, gradients <= 1e-3 relative
+(||delta||_inf / max(||g||_inf, 1e-8) per tensor).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from gaussiansplattingmlx_b200.scene import make_workload, make_gaussians, make_cameras, make_targets
+from oracle import pipeline as pl
+from oracle.api import tile_bit_count, ssim_window
+
+PIX_TOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-8))
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def gsb():
+    from gaussiansplattingmlx_b200.context import Context
+    from gaussiansplattingmlx_b200 import _lib
+    return Context, _lib
+
+
+def make_ctx(gsb, wl_or_wh, **kw):
+    Context, _ = gsb
+    if isinstance(wl_or_wh, tuple):
+        W, H = wl_or_wh
+        return Context(W, H, **kw)
+    wl = wl_or_wh
+    return Context(wl.width, wl.height, tile_w=wl.tile, tile_h=wl.tile, sh_degree=wl.sh_degree, **kw)
+
+
+SCENES = {
+    "C1": dict(n=1000, W=64, H=64, seed=1, degree=3),
+    "deg4": dict(n=700, W=80, H=48, seed=11, degree=4),
+    "ragged": dict(n=1500, W=100, H=70, seed=12, degree=2),      # image not a multiple of the tile
+    "deg0": dict(n=300, W=32, H=32, seed=13, degree=0),
+}
+
+
+def scene(name):
+    s = SCENES[name]
+    params = make_gaussians(s["n"], s["seed"], s["degree"])
+    cam = make_cameras(s["W"], s["H"], 3)[1]
+    target = make_targets(s["W"], s["H"], 1, s["seed"])[0]
+    return s, params, cam, target
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_stagewise_parity(gsb, best_oracle, name):
+    Context, L = gsb
+    o = best_oracle
+    s, params, cam, target = scene(name)
+    W, H, degree = s["W"], s["H"], s["degree"]
+    ctx = Context(W, H, sh_degree=degree)
+    gcam = L.make_camera(cam)
+
+    # --- activations
+    act_o = o.activate_fwd(params)
+    dparams = {k: dev(v) for k, v in params.items()}
+    act_g = ctx.activate_fwd(dparams)
+    for k in ("shs", "scales", "rotations", "opacity"):
+        assert rel_err(act_g[k].cpu().numpy(), act_o[k]) < 1e-6, k
+
+    # --- K1 on the oracle's activated tensors: geometry must be BIT-EXACT
+    act_d = {k: dev(v) for k, v in act_o.items()}
+    proj_o = o.project_fwd(act_o, cam, degree)
+    proj_g = ctx.project_fwd(act_d, gcam)
+    for k in ("means2d", "depths", "radii", "rectMin", "rectMax", "cov2d", "conic", "color"):
+        a, b = proj_g[k].cpu().numpy(), proj_o[k]
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"project_fwd {k} not bit-exact (max diff {np.abs(a-b).max()})"
+
+    # --- K3..K8 on identical inputs: bit-exact counts, keys, sorted lists, ranges
+    bins_o = o.bin(proj_o, W, H, 16, 16)
+    bins_g = ctx.bin({k: dev(v) for k, v in proj_o.items()})
+    assert bins_g["M"] == bins_o["M"]
+    assert np.array_equal(u32(bins_g["tilesTouched"]), bins_o["tilesTouched"])
+    for k in ("keysHigh", "keysLow", "gaussIdx", "sortedKeysHigh", "sortedKeysLow", "sortedGaussIdx"):
+        assert np.array_equal(u32(bins_g[k]), bins_o[k]), k
+    assert np.array_equal(u32(bins_g["tileCounts"]), bins_o["tileCounts"])
+    nz = bins_o["tileCounts"] > 0
+    assert np.array_equal(u32(bins_g["tileRanges"])[nz], bins_o["tileRanges"][nz])
+
+    # --- K9
+    packed = o.pack(proj_o, act_o["opacity"])
+    for white in (False, True):
+        ctxw = Context(W, H, sh_degree=degree, white_background=white)
+        ctxw.bin({k: dev(v) for k, v in proj_o.items()}, read_lists=False)
+        fwd_o = o.raster_fwd(packed, bins_o, W, H, 16, 16, white)
+        fwd_g = ctxw.raster_fwd(dev(packed))
+        assert np.abs(fwd_g["color"].cpu().numpy() - fwd_o["color"]).max() <= PIX_TOL
+        assert np.abs(fwd_g["depth"].cpu().numpy() - fwd_o["depth"]).max() <= PIX_TOL * 10  # depth ~ 4 units
+        assert np.abs(fwd_g["alpha"].cpu().numpy() - fwd_o["alpha"]).max() <= PIX_TOL
+        lc_g, lc_o = u32(fwd_g["lastContrib"]).astype(np.int64), fwd_o["lastContrib"].astype(np.int64)
+        assert (np.abs(lc_g - lc_o) <= 1).all() and (lc_g != lc_o).mean() < 0.01
+
+        # --- K10 on the ORACLE's saved forward (isolates the backward)
+        rng = np.random.default_rng(5)
+        cot = {"color": rng.standard_normal((W * H, 3)).astype(np.float32),
+               "depth": rng.standard_normal((W * H, 1)).astype(np.float32) * 0.1,
+               "alpha": rng.standard_normal((W * H, 1)).astype(np.float32)}
+        g_o = o.raster_bwd(packed, bins_o, W, H, 16, 16, white, cot, fwd_o)
+        g_g = ctxw.raster_bwd(dev(packed), {k: dev(v) for k, v in cot.items()}, {k: dev(v) for k, v in fwd_o.items()})
+        g_g = g_g.cpu().numpy()
+        for lo, hi, nm in ((0, 2, "means2d"), (2, 6, "conic"), (6, 9, "color"), (9, 10, "opacity"), (10, 11, "depth")):
+            assert rel_err(g_g[:, lo:hi], g_o[:, lo:hi]) < GRAD_TOL, f"raster_bwd {nm} white={white}"
+        ctxw.close()
+
+    # --- K2
+    rng = np.random.default_rng(6)
+    n = s["n"]
+    cotp = {"depths": rng.standard_normal(n).astype(np.float32), "means2d": rng.standard_normal((n, 2)).astype(np.float32),
+            "cov2d": rng.standard_normal((n, 4)).astype(np.float32) * 0.0, "color": rng.standard_normal((n, 3)).astype(np.float32),
+            "conic": rng.standard_normal((n, 4)).astype(np.float32)}
+    gp_o = o.project_bwd(act_o, cam, degree, cotp)
+    gp_g = ctx.project_bwd(act_d, gcam, {k: dev(v) for k, v in cotp.items()})
+    for k in ("scales", "rotations", "means3d", "shs", "cameraCenterPoint"):
+        assert rel_err(gp_g[k].cpu().numpy(), gp_o[k]) < GRAD_TOL, f"project_bwd {k}"
+    ctx.close()
+
+
+def test_project_bwd_with_cov2d_cotangent(gsb, best_oracle):
+    Context, L = gsb
+    o = best_oracle
+    s, params, cam, _ = scene("C1")
+    act_o = o.activate_fwd(params)
+    ctx = Context(64, 64)
+    rng = np.random.default_rng(7)
+    n = s["n"]
+    cotp = {"depths": rng.standard_normal(n).astype(np.float32), "means2d": rng.standard_normal((n, 2)).astype(np.float32),
+            "cov2d": rng.standard_normal((n, 4)).astype(np.float32), "color": rng.standard_normal((n, 3)).astype(np.float32),
+            "conic": rng.standard_normal((n, 4)).astype(np.float32)}
+    gp_o = o.project_bwd(act_o, cam, 3, cotp)
+    gp_g = ctx.project_bwd({k: dev(v) for k, v in act_o.items()}, L.make_camera(cam), {k: dev(v) for k, v in cotp.items()})
+    for k in ("scales", "rotations", "means3d", "shs"):
+        assert rel_err(gp_g[k].cpu().numpy(), gp_o[k]) < GRAD_TOL, k
+
+
+@pytest.mark.parametrize("M,tile_bits", [(0, 4), (1, 4), (2, 1), (777, 4), (4096, 8), (4097, 8), (100_000, 13), (1_000_003, 15)])
+def test_sort_matches_stable_sort_and_cub(gsb, M, tile_bits):
+    Context, _ = gsb
+    ctx = Context(64, 64)
+    rng = np.random.default_rng(M + tile_bits)
+    kh = rng.integers(0, 1 << tile_bits, M, dtype=np.uint32)
+    # depths: positive floats with many duplicates so stability is exercised
+    kl = (rng.integers(0, 50, M).astype(np.float32) * 0.25 + 0.2).view(np.uint32)
+    vals = np.arange(M, dtype=np.uint32)
+    order = np.lexsort((kl, kh))   # stable, like the reference's LSD radix sort
+    for use_cub in (False, True):
+        sh, sl, sv = ctx.sort_tile_keys(dev(kh.view(np.int32)), dev(kl.view(np.int32)), dev(vals.view(np.int32)), tile_bits, use_cub)
+        assert np.array_equal(u32(sh), kh[order]), f"keys high (cub={use_cub})"
+        assert np.array_equal(u32(sl), kl[order])
+        assert np.array_equal(u32(sv), vals[order]), "payload order (stability)"
+
+
+def test_sort_full_range_keys(gsb):
+    """Full 32-bit low words + 15 tile bits: sortedness + permutation checksum at 4M pairs."""
+    Context, _ = gsb
+    ctx = Context(64, 64)
+    M = 4_000_000
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    kh = torch.randint(0, 1 << 15, (M,), device="cuda", dtype=torch.int32, generator=g)
+    kl = torch.randint(0, 2 ** 31 - 1, (M,), device="cuda", dtype=torch.int32, generator=g)
+    vals = torch.arange(M, device="cuda", dtype=torch.int32)
+    sh, sl, sv = ctx.sort_tile_keys(kh, kl, vals, 15)
+    key = (sh.to(torch.int64) << 32) | sl.to(torch.int64)
+    assert bool((key[1:] >= key[:-1]).all())
+    assert int(sv.to(torch.int64).sum()) == M * (M - 1) // 2
+    assert bool((kh[sv.long()] == sh).all()) and bool((kl[sv.long()] == sl).all())
+    eq = key[1:] == key[:-1]
+    assert bool((sv[1:][eq] > sv[:-1][eq]).all()), "ties must keep emission order"
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 3), (37, 53, 3), (8, 5, 1), (11, 200, 3)])
+def test_ssim_parity(gsb, best_oracle, shape):
+    Context, _ = gsb
+    o = best_oracle
+    H, W, Cn = shape
+    ctx = Context(max(W, 1), max(H, 1))
+    rng = np.random.default_rng(H * W)
+    a = rng.random(shape, dtype=np.float32); b = rng.random(shape, dtype=np.float32)
+    _, win = ssim_window()
+    so = o.ssim_fwd(a, b, win)
+    sg = ctx.ssim_fwd(dev(a), dev(b))
+    for k in ("ssim", "mu1", "mu2", "sigma1", "sigma2", "sigma12"):
+        assert np.abs(sg[k].cpu().numpy().reshape(-1) - so[k]).max() < 2e-5, k
+    up = rng.standard_normal(H * W * Cn).astype(np.float32)
+    g1o, _ = o.ssim_bwd(up, a, b, win, so)
+    g1g = ctx.ssim_bwd(dev(up.reshape(shape)), dev(a), dev(b)).cpu().numpy()
+    assert rel_err(g1g, g1o) < GRAD_TOL
+
+
+def test_loss_fwd_bwd_parity(gsb, best_oracle):
+    Context, _ = gsb
+    o = best_oracle
+    H, W = 48, 72
+    ctx = Context(W, H)
+    rng = np.random.default_rng(9)
+    render = rng.random((H, W, 3), dtype=np.float32); target = rng.random((H, W, 3), dtype=np.float32)
+    lo = pl.loss_forward_backward(o, render, target, 0.2)
+    loss, cot = ctx.loss_fwd_bwd(dev(render), dev(target), 1.0)
+    assert abs(float(loss.item()) - lo["loss"]) < 1e-5
+    assert rel_err(cot.cpu().numpy(), lo["cot_render"]) < GRAD_TOL
+
+
+def test_adam_bit_exact(gsb, port):
+    Context, _ = gsb
+    ctx = Context(64, 64)
+    n = 1237
+    rng = np.random.default_rng(10)
+    shapes = [(n, 3), (n, 1, 3), (n, 15, 3), (n, 3), (n, 4), (n, 1)]
+    p = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    g = [rng.standard_normal(s).astype(np.float32) * 1e-3 for s in shapes]
+    m = [rng.standard_normal(s).astype(np.float32) * 1e-3 for s in shapes]
+    v = [(rng.standard_normal(s).astype(np.float32) * 1e-3) ** 2 for s in shapes]
+    acc = rng.random(n, dtype=np.float32)
+    lrs = pl.learning_rates(7, 100)
+    dp, dg, dm, dv = ([dev(x) for x in xs] for xs in (p, g, m, v))
+    dacc = dev(acc)
+    ctx.adam_step(dp, dg, dm, dv, lrs, dacc)
+    port.accum_grad_norm(g[0], acc)
+    for i in range(6):
+        port.adam(p[i], g[i], m[i], v[i], lrs[i])
+        assert np.array_equal(dp[i].cpu().numpy().view(np.uint32), p[i].view(np.uint32)), f"param {i}"
+        assert np.array_equal(dm[i].cpu().numpy().view(np.uint32), m[i].view(np.uint32))
+        assert np.array_equal(dv[i].cpu().numpy().view(np.uint32), v[i].view(np.uint32))
+    assert np.array_equal(dacc.cpu().numpy().view(np.uint32), acc.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["C1", "deg4", "ragged"])
+def test_fused_render_and_backward_vs_oracle(gsb, best_oracle, name):
+    """gsb_render_forward / gsb_loss_fwd_bwd / gsb_render_backward (raw tensors, fused activations)
+    against the oracle's restatement of lossFn + VJPs (GaussianTrainer.swift:634-716)."""
+    Context, L = gsb
+    o = best_oracle
+    s, params, cam, target = scene(name)
+    W, H, degree = s["W"], s["H"], s["degree"]
+    fr, lo, bw = pl.loss_and_grads(o, params, cam, target, degree)
+    ctx = Context(W, H, sh_degree=degree)
+    dparams = {k: dev(v) for k, v in params.items()}
+    render, depth, alpha, vis, radii = ctx.render_forward(dparams, L.make_camera(cam))
+    assert np.abs(render.cpu().numpy() - fr["render"]).max() <= PIX_TOL
+    assert np.abs(alpha.cpu().numpy() - fr["alpha"]).max() <= PIX_TOL
+    assert np.abs(depth.cpu().numpy() - fr["depth"]).max() <= PIX_TOL * 10
+    assert (vis.cpu().numpy() == fr["visibility_filter"]).all()
+    # device expf differs from libm by <= 1 ulp in the scale activation: radii may flip for a handful
+    assert (radii.cpu().numpy() != fr["radii"]).mean() < 1e-3
+    st = ctx.stats()
+    assert abs(st["pairs_last_view"] - fr["bins"]["M"]) <= max(4, fr["bins"]["M"] // 1000)
+    loss, cot = ctx.loss_fwd_bwd(render, dev(target), 1.0)
+    assert abs(float(loss.item()) - lo["loss"]) < 2e-5
+    grads = ctx.render_backward(cot)
+    for k, g in grads.items():
+        assert rel_err(g.cpu().numpy().reshape(bw["grads"][k].shape), bw["grads"][k]) < GRAD_TOL, k
+    # accumulate=True adds onto existing buffers
+    grads2 = ctx.render_backward(cot, grads={k: v.clone() for k, v in grads.items()}, accumulate=True)
+    for k in grads:
+        assert rel_err(grads2[k].cpu().numpy(), 2.0 * grads[k].cpu().numpy()) < 1e-5, k
+
+
+def test_train_steps_vs_oracle(gsb, best_oracle):
+    """Three batched train steps (B = 2 views) through gsb_train_step vs the oracle loop."""
+    Context, L = gsb
+    o = best_oracle
+    n, W, H = 600, 64, 48
+    params = make_gaussians(n, 21, 3)
+    cams = make_cameras(W, H, 2)
+    targets = make_targets(W, H, 2, 21)
+    p_o, m_o, v_o, acc_o, losses_o = pl.train_steps(o, params, cams, targets, 3, 3, 100)
+    ctx = Context(W, H)
+    ctx.trainer_init({k: torch.from_numpy(v) for k, v in params.items()})
+    gcams = [L.make_camera(c) for c in cams]
+    for host in (True,):
+        tg = [torch.from_numpy(t).pin_memory() for t in targets]
+        losses = [ctx.train_step(gcams, tg, it, 100) for it in range(3)]
+    tt = ctx.trainer_tensors()
+    for a, b in zip(losses, losses_o):
+        assert abs(a - b) < 5e-5
+    # Adam normalises the step to ~lr regardless of gradient scale: compare the parameter DELTAS
+    for k in params:
+        d_g = tt["params"][k].cpu().numpy().reshape(params[k].shape) - params[k]
+        d_o = p_o[k] - params[k]
+        assert rel_err(d_g, d_o) < 2e-2, k
+    assert rel_err(tt["accum"].cpu().numpy(), acc_o) < GRAD_TOL
+
+
+def test_empty_and_culled_scenes(gsb):
+    Context, L = gsb
+    cam = make_cameras(32, 32, 1)[0]
+    ctx = Context(32, 32)
+    params = make_gaussians(64, 3, 3)
+    params["_xyz"][:] = np.array([0, 0, -100.0], np.float32)   # everything behind the camera
+    render, depth, alpha, vis, radii = ctx.render_forward({k: dev(v) for k, v in params.items()}, L.make_camera(cam))
+    assert float(render.abs().max()) == 0.0 and float(alpha.abs().max()) == 0.0 and not bool(vis.any())
+    assert ctx.stats()["pairs_last_view"] == 0
+    grads = ctx.render_backward(torch.ones_like(render))
+    assert all(float(g.abs().max()) == 0.0 for g in grads.values())
+
+
+def test_error_paths(gsb):
+    Context, L = gsb
+    from gaussiansplattingmlx_b200._lib import GsbError
+    with pytest.raises(GsbError):
+        Context(0, 64)
+    with pytest.raises(GsbError):
+        Context(64, 64, sh_degree=5)
+    ctx = Context(32, 32)
+    with pytest.raises(GsbError):   # backward without forward
+        ctx._saved_params = {k: torch.zeros(1, device="cuda") for k in ("_xyz", "_features_dc", "_features_rest", "_scales", "_rotation", "_opacity")}
+        ctx.render_backward(torch.zeros(32, 32, 3, device="cuda"))
