@@ -79,6 +79,7 @@ SIGNATURES = {
     "gsb_trainer_accumulate": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), _I, _I, _F, C.POINTER(_F)]),
     "gsb_trainer_apply": (C.c_int, [_P, _I, _I, _I]),
     "gsb_train_step": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), _I, _I, _I, C.POINTER(_F)]),
+    "gsb_last_contrib_sum": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "gsb_stats_reset": (C.c_int, [_P]),
     "gsb_stats_get": (C.c_int, [_P, C.POINTER(GsbStats)]),
     "gsb_enable_stage_timing": (C.c_int, [_P, _I]),

@@ -324,6 +324,11 @@ class Context:
                 "stage_ms": {n: float(st.stage_ms[i]) for i, n in enumerate(names)},
                 "stage_calls": {n: int(st.stage_calls[i]) for i, n in enumerate(names)}}
 
+    def last_contrib_sum(self) -> int:
+        v = C.c_uint64(0)
+        self._check(self.lib.gsb_last_contrib_sum(self.h, C.byref(v)))
+        return int(v.value)
+
     def stats_reset(self):
         self._check(self.lib.gsb_stats_reset(self.h))
 

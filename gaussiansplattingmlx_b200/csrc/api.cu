@@ -1058,6 +1058,21 @@ int gsb_train_step(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams, const f
 }
 
 // ---- stats ---------------------------------------------------------------------------------------
+int gsb_last_contrib_sum(gsb_ctx* ctx, uint64_t* host_out)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, host_out, "gsb_last_contrib_sum: null argument");
+    if (!c->saved.valid) { gsb::set_error(c, "gsb_last_contrib_sum: no forward saved on this context"); return GSB_ERR_STATE; }
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(c->partial);   // 16-byte scratch
+    GSB_CUDA_CHECK(c, gsb::launch_sum_u32(c->stream, (size_t)c->P, c->out_last, d));
+    unsigned long long h = 0;
+    GSB_CUDA_CHECK(c, cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    *host_out = h;
+    c->stats.kernel_launches += 1;
+    return GSB_OK;
+}
+
 int gsb_stats_reset(gsb_ctx* ctx)
 {
     CTX_PROLOGUE(ctx);

@@ -87,6 +87,8 @@ cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint3
                               const float* out_color, const float* out_depth, const float* out_alpha,
                               const uint32_t* last_contrib, float* grad_rec);
 
+cudaError_t launch_sum_u32(cudaStream_t st, size_t n, const uint32_t* v, unsigned long long* out);
+
 // ---- loss.cu -----------------------------------------------------------------------------------
 // separable SSIM (11x11, sigma 1.5, centre 5.5) forward with optional saved maps
 cudaError_t launch_ssim_fwd(cudaStream_t st, int H, int W, int C, const float* img1, const float* img2, float* ssim_map,

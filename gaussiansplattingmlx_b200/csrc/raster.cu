@@ -8,6 +8,8 @@
 // `staged` stream (binning.cu), so batches are pulled into shared memory with TMA 1-D bulk copies
 // (cp.async.bulk → SASS UBLKCP) signalled through mbarriers, double-buffered against the blend loop.
 // FP32-pipe bound: 27 flop + 1 ex2 per (pixel, Gaussian) forward, ≈80 flop + 1 ex2 + 1 div backward.
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace gsb {
@@ -304,6 +306,23 @@ __global__ void __launch_bounds__(RT) k_raster_bwd(const __grid_constant__ ViewP
         }
         __syncthreads();
     }
+}
+
+// sum of lastContrib over the image = number of (pixel, Gaussian) blend evaluations (bench statistics)
+__global__ void __launch_bounds__(256) k_sum_u32(size_t n, const uint32_t* __restrict__ v, unsigned long long* __restrict__ out)
+{
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += v[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+cudaError_t launch_sum_u32(cudaStream_t st, size_t n, const uint32_t* v, unsigned long long* out)
+{
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    if (n > 0) k_sum_u32<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(n, v, out);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,111 @@
+"""``GaussianTrainer`` — host-side mirror of the reference train loop
+(``Trainer/GaussianTrainer.swift:448-477`` init, ``:934-1114`` startTrain) over the fused CUDA step.
+
+One iteration = ``gsb_trainer_accumulate`` (per view: render → loss → backward, gradients summed with
+weight 1/B) → optional view-parallel all-reduce → ``gsb_trainer_apply`` (Adam + D1 grad-norm accumulation).
+With ``views_per_step == 1`` and one rank this is the reference iteration; densification (D2/D3) is a
+"next" row and is not run here — only the optimiser-state reset cadence is kept.
+"""
+from __future__ import annotations
+
+import random
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .camera import Camera
+from .dp import ViewParallel
+from .model import GaussModel, PARAM_ORDER
+from .renderer import GaussianRenderer
+
+
+@dataclass
+class TrainData:
+    """``GaussianTrainer.swift`` TrainData: cameras + rgbArray[V,H,W,3] (f32)."""
+    cameras: List[Camera]
+    rgbArray: Sequence[np.ndarray]
+
+    def getNumCameras(self) -> int:
+        return len(self.cameras)
+
+    def getViewPointCamera(self, index: int) -> Camera:
+        return self.cameras[index]
+
+
+class GaussianTrainer:
+    # reference defaults (GaussianTrainer.swift:277-300)
+    lambda_dssim = 0.2
+    lambda_depth = 0.0
+    optimizer_reset_interval = 100
+
+    def __init__(self, model: GaussModel, data: TrainData, gaussRender: GaussianRenderer, iterationCount: int,
+                 views_per_step: int = 1, parallel: Optional[ViewParallel] = None, seed: Optional[int] = None,
+                 reset_optimizer_state: bool = True):
+        self.model, self.data, self.gaussRender = model, data, gaussRender
+        self.iterationCount = iterationCount
+        self.views_per_step = views_per_step
+        self.parallel = parallel or ViewParallel()
+        self.reset_optimizer_state = reset_optimizer_state
+        self.forceStop = False
+        self.delegate: Optional[Callable[[float, int], None]] = None   # pushLoss(loss, iteration)
+        self._rng = random.Random(seed)
+        ctx = gaussRender.ctx
+        ctx.trainer_init({k: torch.from_numpy(np.ascontiguousarray(getattr(model, k))) for k in PARAM_ORDER})
+        self._gcams = [_lib.make_camera(c) for c in data.cameras]
+        self._targets = [torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)).pin_memory() for t in data.rgbArray]
+        self._grad_block = ctx.trainer_grad_block() if self.parallel.world > 1 else None
+        self.losses: List[float] = []
+
+    def stopTrain(self):
+        self.forceStop = True
+
+    def fetchTrainData(self) -> List[int]:
+        """Random view indices for this iteration (``GaussianTrainer.swift:486-498``, batched)."""
+        n = self.data.getNumCameras()
+        return [self._rng.randrange(n) for _ in range(self.views_per_step)]
+
+    def train_iteration(self, iteration: int, view_indices: Optional[Sequence[int]] = None, want_loss: bool = True):
+        ctx = self.gaussRender.ctx
+        views = list(view_indices) if view_indices is not None else self.fetchTrainData()
+        B = len(views)
+        mine = [views[i] for i in self.parallel.my_views(B)]
+        loss = None
+        if mine:
+            loss = ctx.trainer_accumulate([self._gcams[v] for v in mine], [self._targets[v] for v in mine], zero_grads=True,
+                                          grad_scale=1.0 / B, want_loss=want_loss)
+        elif self.parallel.world > 1:
+            self._grad_block.zero_()
+        if self.parallel.world > 1:
+            self.parallel.all_reduce_sum(self._grad_block)
+        reset = self.reset_optimizer_state and iteration % self.optimizer_reset_interval == 0
+        # the reference re-creates the Adam state AFTER the update of every 100th iteration
+        # (GaussianTrainer.swift:1098-1109); zeroing before the next update is the same thing
+        ctx.trainer_apply(iteration, self.iterationCount, reset_state=False)
+        if reset:
+            tt = ctx.trainer_tensors()
+            for k in PARAM_ORDER:
+                tt["m"][k].zero_(); tt["v"][k].zero_()
+        return loss
+
+    def startTrain(self, earlyStoppingThreshold: float = 1e-4):
+        for iteration in range(self.iterationCount):
+            if self.forceStop:
+                break
+            report = iteration % 10 == 0
+            loss = self.train_iteration(iteration, want_loss=report)
+            if report and loss is not None:
+                self.losses.append(loss)
+                if self.delegate:
+                    self.delegate(loss, iteration)
+                if loss < earlyStoppingThreshold:
+                    break
+        self.sync_model()
+
+    def sync_model(self):
+        """Copy the trained parameters back into the host-side ``GaussModel``."""
+        tt = self.gaussRender.ctx.trainer_tensors()
+        for k in PARAM_ORDER:
+            setattr(self.model, k, tt["params"][k].cpu().numpy().reshape(getattr(self.model, k).shape))

@@ -219,6 +219,9 @@ typedef struct gsb_stats {
 enum { GSB_STAGE_PROJECT_FWD = 0, GSB_STAGE_SCAN, GSB_STAGE_KEYGEN, GSB_STAGE_SORT, GSB_STAGE_RANGES_GATHER,
        GSB_STAGE_RASTER_FWD, GSB_STAGE_LOSS, GSB_STAGE_RASTER_BWD, GSB_STAGE_PROJECT_BWD, GSB_STAGE_ADAM,
        GSB_STAGE_H2D, GSB_STAGE_COUNT };
+/* Sum of lastContrib over the image of the last gsb_render_forward = number of (pixel, Gaussian)
+ * blend evaluations E of that view (the unit of the raster rooflines).  Synchronises. */
+GSB_API int gsb_last_contrib_sum(gsb_ctx*, uint64_t* host_out);
 GSB_API int gsb_stats_reset(gsb_ctx*);
 GSB_API int gsb_stats_get(gsb_ctx*, gsb_stats* host_out);
 GSB_API int gsb_enable_stage_timing(gsb_ctx*, int32_t on);   /* brackets every stage with CUDA-event pairs; no syncs until stats are read */

@@ -1,0 +1,64 @@
+"""The N > 1 path on CPU: world_size-2 gloo.  Each rank computes the gradients of ITS views with the
+oracle (weight 1/B), the gradient block is summed with ViewParallel.all_reduce_sum, and the result
+must equal the single-process batch gradient — the identity the GPU view-parallel step relies on."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ["OMP_NUM_THREADS"] = "2"
+    from gaussiansplattingmlx_b200.dp import ViewParallel, grad_scale
+    from gaussiansplattingmlx_b200.scene import make_cameras, make_gaussians, make_targets
+    from oracle import pipeline as pl
+    from oracle.api import Port
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    vp = ViewParallel.from_env()
+    assert (vp.rank, vp.world) == (rank, world)
+    n, W, H, B = 150, 32, 24, 4
+    params = make_gaussians(n, 77, 2)
+    cams = make_cameras(W, H, B); targets = make_targets(W, H, B, 77)
+    o = Port()
+    keys = list(params)
+    block = torch.zeros(sum(params[k].size for k in keys), dtype=torch.float64)
+    for v in vp.my_views(B):
+        _, _, bw = pl.loss_and_grads(o, params, cams[v], targets[v], 2)
+        block += grad_scale(B) * torch.from_numpy(np.concatenate([bw["grads"][k].reshape(-1) for k in keys]).astype(np.float64))
+    vp.all_reduce_sum(block)
+    t_max = vp.all_reduce_max(float(rank + 1))
+    assert t_max == float(world)
+    np.save(Path(out_dir) / f"block_{rank}.npy", block.numpy())
+    dist.destroy_process_group()
+
+
+def test_view_parallel_gradient_equals_batch_gradient(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    b0 = np.load(tmp_path / "block_0.npy"); b1 = np.load(tmp_path / "block_1.npy")
+    assert np.array_equal(b0, b1)                       # replicas stay identical
+    from gaussiansplattingmlx_b200.scene import make_cameras, make_gaussians, make_targets
+    from oracle import pipeline as pl
+    from oracle.api import Port
+    n, W, H, B = 150, 32, 24, 4
+    params = make_gaussians(n, 77, 2)
+    cams = make_cameras(W, H, B); targets = make_targets(W, H, B, 77)
+    o = Port()
+    ref = np.zeros_like(b0)
+    for v in range(B):
+        _, _, bw = pl.loss_and_grads(o, params, cams[v], targets[v], 2)
+        ref += np.concatenate([bw["grads"][k].reshape(-1) for k in params]).astype(np.float64) / B
+    assert np.abs(b0 - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())

@@ -328,3 +328,85 @@ def test_error_paths(gsb):
     with pytest.raises(GsbError):   # backward without forward
         ctx._saved_params = {k: torch.zeros(1, device="cuda") for k in ("_xyz", "_features_dc", "_features_rest", "_scales", "_rotation", "_opacity")}
         ctx.render_backward(torch.zeros(32, 32, 3, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------
+# committed golden fixtures (outputs of the reference's own kernels, tests/golden/make_golden.py)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1", "deg4_ragged"])
+def test_cuda_path_vs_reference_golden(gsb, port, name):
+    from test_oracle_pinning import load_case
+    Context, L = gsb
+    g, params, cam, target, degree = load_case(name)
+    n, W, H = (int(x) for x in g["meta"][:3])
+    ctx = Context(W, H, sh_degree=degree)
+    gcam = L.make_camera(cam)
+    act = port.activate_fwd(params)                     # MLX-op activations: host-side inputs of K1
+    proj = ctx.project_fwd({k: dev(v) for k, v in act.items()}, gcam)
+    for k in ("means2d", "depths", "radii", "conic", "color"):
+        assert np.array_equal(proj[k].cpu().numpy().view(np.uint32), g[k].view(np.uint32)), k
+    bins = ctx.bin(proj)
+    assert bins["M"] == int(g["M"][0])
+    for k in ("tilesTouched", "tileCounts", "sortedKeysHigh", "sortedKeysLow", "sortedGaussIdx"):
+        assert np.array_equal(u32(bins[k]), g[k]), k
+    # fused path against the golden image, loss and gradients
+    render, depth, alpha, vis, radii = ctx.render_forward({k: dev(v) for k, v in params.items()}, gcam)
+    assert np.abs(render.cpu().numpy() - g["render"]).max() <= PIX_TOL
+    assert np.abs(alpha.cpu().numpy() - g["alpha"]).max() <= PIX_TOL
+    loss, cot = ctx.loss_fwd_bwd(render, dev(target), 1.0)
+    assert abs(float(loss.item()) - float(g["loss"][0])) < 2e-5 * max(1.0, float(g["loss"][0]))
+    grads = ctx.render_backward(cot)
+    for k, gr in grads.items():
+        assert rel_err(gr.cpu().numpy().reshape(g["grad" + k].shape), g["grad" + k]) < GRAD_TOL, k
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties (the oracle would take minutes here)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wl_name,n", [("C2", None), ("C3", None)])
+def test_full_size_properties(gsb, wl_name, n):
+    Context, L = gsb
+    wl, params, cams, targets = make_workload(wl_name, views_override=1)
+    N = params["_xyz"].shape[0]
+    ctx = Context(wl.width, wl.height, sh_degree=wl.sh_degree, max_gaussians=N)
+    dparams = {k: dev(v) for k, v in params.items()}
+    gcam = L.make_camera(cams[0])
+    render, depth, alpha, vis, radii = ctx.render_forward(dparams, gcam)
+    M = ctx.stats()["pairs_last_view"]
+    lists = ctx.bin_read()
+    key = (lists["sortedKeysHigh"].to(torch.int64) << 32) | (lists["sortedKeysLow"].to(torch.int64) & 0xffffffff)
+    assert key.numel() == M and bool((key[1:] >= key[:-1]).all()), "sorted (tile, depth) keys must be non-decreasing"
+    eq = key[1:] == key[:-1]
+    sv = lists["sortedGaussIdx"]
+    assert bool((sv[1:][eq] > sv[:-1][eq]).all()), "equal keys keep emission (Gaussian index) order"
+    # every listed Gaussian is visible, and the multiset of values matches tiles-touched
+    cnt = torch.bincount(sv.long(), minlength=N)
+    assert bool(((cnt > 0) == vis).all())
+    # the API path on the API projection must produce the same number of pairs (geometry is activation independent
+    # except for radii, which may flip by one step for a handful of Gaussians)
+    act = ctx.activate_fwd(dparams)
+    proj = ctx.project_fwd(act, gcam)
+    bins = ctx.bin(proj, read_lists=False)
+    assert abs(bins["M"] - M) <= max(8, M // 100000)
+    tc = bins["tileCounts"].long()
+    assert int(tc.sum()) == bins["M"] == int(bins["tilesTouched"].long().sum())
+    rg = bins["tileRanges"].long()
+    nz = tc > 0
+    assert bool((rg[nz, 1] - rg[nz, 0] == tc[nz]).all())
+    starts = rg[nz, 0]
+    assert bool((starts[1:] == rg[nz, 1][:-1]).all()) and int(starts[0]) == 0 and int(rg[nz, 1][-1]) == bins["M"]
+    # image sanity
+    a = alpha
+    assert float(a.min()) >= 0.0 and float(a.max()) <= 1.0 and bool(torch.isfinite(render).all())
+    # re-render after the API calls (state was replaced) and check backward linearity in the cotangent
+    render2, *_ = ctx.render_forward(dparams, gcam)
+    assert torch.equal(render, render2), "the forward is deterministic"
+    cot = torch.from_numpy(targets[0]).cuda() - 0.5
+    g1 = ctx.render_backward(cot)
+    g1 = {k: v.clone() for k, v in g1.items()}
+    g2 = ctx.render_backward(cot * 2.0)
+    for k in g1:
+        assert rel_err(g2[k].cpu().numpy(), 2.0 * g1[k].cpu().numpy()) < 1e-4, k
+    assert all(bool(torch.isfinite(v).all()) for v in g1.values())
+    if wl_name == "C3":
+        assert abs(M - 12_031_308) <= 200     # SURVEY.md 8d-workload (reference kernels on CPU), view 0
