@@ -540,10 +540,11 @@ cudaError_t launch_tile_counts(cudaStream_t st, int numTiles, const uint32_t* ti
 // ------------------------------------------------------------------------------------------------
 __global__ void k_packed_to_rec(int N, const float* __restrict__ packed, float* __restrict__ rec)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N * REC_FLOATS) return;
-    int p = i / REC_FLOATS, c = i - p * REC_FLOATS;
-    rec[i] = c < 11 ? packed[(size_t)p * 11 + c] : __uint_as_float((uint32_t)p);
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const float* s = packed + (size_t)p * 11;
+    make_raster_record(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], s[9], s[10], (uint32_t)p,
+                       reinterpret_cast<float4*>(rec) + (size_t)p * 3);
 }
 __global__ void k_rec_to_packed(int N, const float* __restrict__ rec, float* __restrict__ packed)
 {
@@ -554,7 +555,7 @@ __global__ void k_rec_to_packed(int N, const float* __restrict__ rec, float* __r
 }
 cudaError_t launch_packed_to_rec(cudaStream_t st, int N, const float* packed, float* rec)
 {
-    if (N > 0) k_packed_to_rec<<<cdiv((long long)N * REC_FLOATS, 256), 256, 0, st>>>(N, packed, rec);
+    if (N > 0) k_packed_to_rec<<<cdiv(N, 256), 256, 0, st>>>(N, packed, rec);
     return cudaGetLastError();
 }
 cudaError_t launch_rec_to_packed(cudaStream_t st, int N, const float* rec, float* packed)

@@ -10,9 +10,15 @@
 
 namespace gsb {
 
-constexpr int REC_FLOATS = 12;  // internal projected record: 11 packed floats + gaussian index bits (48 B, 16B aligned)
-// record word order (kept equal to the reference's packed[N,11] order, GaussianRenderer.swift:45-51):
-//   0 meanX 1 meanY 2 c00 3 c01 | 4 c10 5 c11 6 r 7 g | 8 b 9 opacity 10 depth 11 idx(bits)
+constexpr int REC_FLOATS = 12;  // internal projected record (48 B, three 16-byte quads)
+// Raster record = the reference's packed[N,11] (GaussianRenderer.swift:45-51) with the conic and the
+// opacity pre-folded for the blend loop (exponent evaluated directly in log2 units):
+//   0 meanX 1 meanY 2 A 3 B | 4 C 5 lo 6 r 7 g | 8 b 9 opacity 10 depth 11 idx(bits)
+//   A = -0.5*log2(e)*c00,  B = -0.5*log2(e)*(c01 + c10),  C = -0.5*log2(e)*c11,  lo = log2(opacity)
+//   alpha = min(0.99, 2^(A dx^2 + B dx dy + C dy^2 + lo))   ( == min(0.99, exp(-0.5 d^T conic d) * opacity) )
+// Gradient record (raster backward -> projection backward) keeps the reference's packed order:
+//   0 g_meanX 1 g_meanY 2 g_c00 3 g_c01 | 4 g_c10 5 g_c11 6 g_r 7 g_g | 8 g_b 9 g_opacity 10 g_depth 11 unused
+constexpr float LOG2E_F = 1.4426950408889634f;
 
 // Per-view constants handed to kernels by value (__grid_constant__).
 struct ViewParams {
@@ -120,6 +126,33 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// packed-order fields -> raster record quads
+__device__ __forceinline__ void make_raster_record(float mx, float my, float c00, float c01, float c10, float c11, float r,
+                                                   float g, float b, float opacity, float depth, uint32_t idx, float4* out)
+{
+    const float s = -0.5f * LOG2E_F;
+    out[0] = make_float4(mx, my, s * c00, s * (c01 + c10));
+    out[1] = make_float4(s * c11, log2f(opacity), r, g);
+    out[2] = make_float4(b, opacity, depth, __uint_as_float(idx));
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ void red_add_f32(float* p, float v)
 {

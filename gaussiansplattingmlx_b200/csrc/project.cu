@@ -215,9 +215,8 @@ __global__ void __launch_bounds__(PB) k_project_fused_fwd(int N, const float* __
         project_forward<MAXK>(sm[L.xyz + t * 3], sm[L.xyz + t * 3 + 1], sm[L.xyz + t * 3 + 2], s0, s1, s2, rw, rx, ry, rz,
                               [&](int k, int c) { return k == 0 ? dc[c] : rest[(k - 1) * 3 + c]; }, vp, o);
         float4* r4 = reinterpret_cast<float4*>(sm + L.rec + t * REC_FLOATS);
-        r4[0] = make_float4(o.sx, o.sy, o.conic[0], o.conic[1]);
-        r4[1] = make_float4(o.conic[2], o.conic[3], o.color[0], o.color[1]);
-        r4[2] = make_float4(o.color[2], opac, o.depth, __uint_as_float((uint32_t)p));
+        make_raster_record(o.sx, o.sy, o.conic[0], o.conic[1], o.conic[2], o.conic[3], o.color[0], o.color[1], o.color[2],
+                           opac, o.depth, (uint32_t)p, r4);
         int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
         uint32_t cnt = 0;
         if (o.radius > 0.0f) {

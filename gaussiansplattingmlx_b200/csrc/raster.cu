@@ -3,40 +3,50 @@
 // Reference: slang/gaussian_tile_global_kernels.slang:437-614 (forward), :501-521 + :648-881
 // (backward), call sites Trainer/GaussianRenderer.swift:124-147,187-226.
 //
-// One CTA = one 16x16 pixel block of one tile (a tile larger than 16x16 is covered by several
-// CTAs that share the tile's list).  The tile's depth-ordered 48-byte records are contiguous in the
-// `staged` stream (binning.cu), so batches are pulled into shared memory with TMA 1-D bulk copies
-// (cp.async.bulk → SASS UBLKCP) signalled through mbarriers, double-buffered against the blend loop.
-// FP32-pipe bound: 27 flop + 1 ex2 per (pixel, Gaussian) forward, ≈80 flop + 1 ex2 + 1 div backward.
+// Both kernels are FP32-issue bound (ncu: issue slots ~90 % busy), so the design goal is the fewest
+// instructions per (pixel, Gaussian) evaluation:
+//   * the tile's depth-ordered 48-byte records are contiguous in the `staged` stream (binning.cu);
+//     batches are pulled into shared memory by TMA 1-D bulk copies (cp.async.bulk -> SASS UBLKCP)
+//     signalled through mbarriers, double-buffered against the blend loop;
+//   * records carry the conic/opacity pre-folded into log2 units (common.cuh), so
+//     alpha = min(0.99, ex2(A dx^2 + B dx dy + C dy^2 + lo)): 5 FMA-pipe ops + 1 MUFU;
+//   * forward: one pixel per thread, 256 threads = one 16x16 block; a terminated pixel keeps running
+//     with T = 0 (adds exact zeros) so the loop body has no per-lane predicate, and the warp votes
+//     only every 4 Gaussians;
+//   * backward: ONE WARP per 16x16 block, 8 pixels per thread.  The 11 per-Gaussian gradient sums are
+//     first accumulated over the thread's 8 pixels in registers (the accumulation is the FMA that
+//     produces the term), so the 13-shuffle warp butterfly is paid once per 256 evaluations instead
+//     of once per 32, and there is no cross-warp reduction at all.  One vector red per (block,
+//     Gaussian, quad) then goes to L2.
+// Work per evaluation: forward 27 flop + 1 ex2; backward ~80 flop + 1 ex2 + 1 rcp.
 #include <algorithm>
 
 #include "kernels.h"
 
 namespace gsb {
 
-constexpr int RT = 256;          // threads per CTA = 16x16 pixels
+constexpr int RT = 256;          // forward: threads per CTA = 16x16 pixels
 constexpr int RB_FWD = 128;      // records per forward batch (6 KB)
 constexpr int RB_BWD = 64;       // records per backward batch
-constexpr int RWARPS = RT / 32;
+constexpr int BPPT = 8;          // backward: pixels per thread (rows)
 
-struct PixelMap {
-    int tile, px, py;
-    bool active;
+// (tile, 16x16 sub-block) of this CTA; tiles larger than 16x16 are covered by several CTAs
+struct BlockMap {
+    int tile, x0, y0;   // pixel origin of the 16x16 block
+    int xmax, ymax;     // exclusive pixel bounds of the tile clipped to the image
 };
-
-__device__ __forceinline__ PixelMap map_pixel(const ViewParams& vp)
+__device__ __forceinline__ BlockMap map_block(const ViewParams& vp)
 {
     const int subX = (vp.tileW + 15) >> 4, subY = (vp.tileH + 15) >> 4;
     const int per = subX * subY;
-    PixelMap m;
+    BlockMap m;
     m.tile = blockIdx.x / per;
     const int sb = blockIdx.x - m.tile * per;
     const int tileX = m.tile % vp.gridW, tileY = m.tile / vp.gridW;
-    const int lx = (sb % subX) * 16 + (threadIdx.x & 15);
-    const int ly = (sb / subX) * 16 + (threadIdx.x >> 4);
-    m.px = tileX * vp.tileW + lx;
-    m.py = tileY * vp.tileH + ly;
-    m.active = lx < vp.tileW && ly < vp.tileH && m.px < vp.W && m.py < vp.H;
+    m.x0 = tileX * vp.tileW + (sb % subX) * 16;
+    m.y0 = tileY * vp.tileH + (sb / subX) * 16;
+    m.xmax = min((tileX + 1) * vp.tileW, vp.W);
+    m.ymax = min((tileY + 1) * vp.tileH, vp.H);
     return m;
 }
 
@@ -51,8 +61,10 @@ __global__ void __launch_bounds__(RT) k_raster_fwd(const __grid_constant__ ViewP
 {
     __shared__ __align__(128) float4 s_rec[2][RB_FWD * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
-    const PixelMap pm = map_pixel(vp);
-    const uint32_t start = tile_ranges[pm.tile * 2], end = tile_ranges[pm.tile * 2 + 1];
+    const BlockMap bm = map_block(vp);
+    const int pxi = bm.x0 + (threadIdx.x & 15), pyi = bm.y0 + (threadIdx.x >> 4);
+    const bool active = pxi < bm.xmax && pyi < bm.ymax;
+    const uint32_t start = tile_ranges[bm.tile * 2], end = tile_ranges[bm.tile * 2 + 1];
     const uint32_t count = end > start ? end - start : 0u;
     const int nb = (int)((count + RB_FWD - 1) / RB_FWD);
 
@@ -70,53 +82,67 @@ __global__ void __launch_bounds__(RT) k_raster_fwd(const __grid_constant__ ViewP
     };
     if (threadIdx.x == 0 && nb > 0) issue(0);
 
-    const float px = (float)pm.px, py = (float)pm.py;
-    float cx = 0.f, cy = 0.f, cz = 0.f, dep = 0.f, T = 1.0f;
+    const float px = (float)pxi, py = (float)pyi;
+    float cx = 0.f, cy = 0.f, cz = 0.f, dep = 0.f;
+    float T = active ? 1.0f : 0.0f;   // T == 0  <=>  this pixel is finished (terminated or outside)
+    float Tfin = -1.0f;               // transmittance at termination (valid when >= 0)
     uint32_t nContrib = count;
-    bool done = !pm.active;
+    const uint32_t rec_base = smem_u32(&s_rec[0][0]);
+
+    // one Gaussian: slang/gaussian_tile_global_kernels.slang:437-499 + the termination test :599-603
+    auto blend = [&](uint32_t addr, uint32_t index) {
+        const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
+        const float dx = px - a.x, dy = py - a.y;
+        const float t = fmaf(a.w, dy, a.z * dx);
+        const float u = q.x * dy;
+        const float p = fmaf(u, dy, fmaf(dx, t, q.y));
+        const float alpha = fminf(ex2_approx(p), 0.99f);
+        const float contrib = T * alpha;
+        cx = fmaf(contrib, q.z, cx);
+        cy = fmaf(contrib, q.w, cy);
+        cz = fmaf(contrib, c.x, cz);
+        dep = fmaf(contrib, c.z, dep);
+        float Tn = fmaf(-T, alpha, T);
+        if (Tn < 1e-4f && T != 0.0f) {   // terminating Gaussian is included (reference quirk)
+            nContrib = index + 1u;
+            Tfin = Tn;
+            Tn = 0.0f;
+        }
+        T = Tn;
+    };
 
     for (int b = 0; b < nb; ++b) {
         if (threadIdx.x == 0 && b + 1 < nb) issue(b + 1);
         mbar_wait(&s_bar[b & 1], (uint32_t)(b >> 1) & 1u);
         const int n = (int)min((uint32_t)RB_FWD, count - (uint32_t)b * RB_FWD);
-        const float4* r = &s_rec[b & 1][0];
-        if (!__all_sync(0xffffffffu, done)) {
-            for (int j = 0; j < n; ++j) {
-                if (!done) {
-                    const float4 a = r[j * 3], q = r[j * 3 + 1], c = r[j * 3 + 2];
-                    const float dx = px - a.x, dy = py - a.y;
-                    const float dxdy = dx * dy;
-                    const float expo = -0.5f * (dx * dx * a.z + dy * dy * q.y + dxdy * a.w + dxdy * q.x);
-                    const float raw = __expf(expo) * c.y;
-                    const float alpha = raw > 0.99f ? 0.99f : raw;
-                    const float contrib = T * alpha;
-                    cx += contrib * q.z;
-                    cy += contrib * q.w;
-                    cz += contrib * c.x;
-                    dep += contrib * c.z;
-                    T *= (1.0f - alpha);
-                    if (T < 1e-4f) {
-                        nContrib = (uint32_t)(b * RB_FWD + j + 1);
-                        done = true;
-                    }
-                }
-                if (__all_sync(0xffffffffu, done)) break;
+        if (!__all_sync(0xffffffffu, T == 0.0f)) {
+            uint32_t addr = rec_base + (uint32_t)(b & 1) * (RB_FWD * 48u);
+            const uint32_t i0 = (uint32_t)b * RB_FWD;
+            int j = 0;
+            for (; j + 4 <= n; j += 4, addr += 4 * 48u) {
+                blend(addr, i0 + j);
+                blend(addr + 48u, i0 + j + 1);
+                blend(addr + 96u, i0 + j + 2);
+                blend(addr + 144u, i0 + j + 3);
+                if (__all_sync(0xffffffffu, T == 0.0f)) { j = n; break; }
             }
+            for (; j < n; ++j, addr += 48u) blend(addr, i0 + j);
         }
         // releases the stage buffer for the copy issued two batches later, and votes on early exit
-        if (__syncthreads_and(done)) {
+        if (__syncthreads_and(T == 0.0f)) {
             if (b + 1 < nb) mbar_wait(&s_bar[(b + 1) & 1], (uint32_t)((b + 1) >> 1) & 1u);  // drain the in-flight copy
             break;
         }
     }
-    if (pm.active) {
-        const size_t p = (size_t)pm.py * vp.W + pm.px;
-        const float bg = vp.whiteBg ? T : 0.0f;
+    if (active) {
+        const float Tend = Tfin >= 0.0f ? Tfin : T;
+        const size_t p = (size_t)pyi * vp.W + pxi;
+        const float bg = vp.whiteBg ? Tend : 0.0f;
         out_color[p * 3 + 0] = cx + bg;
         out_color[p * 3 + 1] = cy + bg;
         out_color[p * 3 + 2] = cz + bg;
         out_depth[p] = dep;
-        out_alpha[p] = 1.0f - T;
+        out_alpha[p] = 1.0f - Tend;
         out_last[p] = nContrib;
     }
 }
@@ -159,61 +185,58 @@ __device__ __forceinline__ float warp_reduce12(float (&v)[12], int lane)
     return v[0];
 }
 
-__global__ void __launch_bounds__(RT) k_raster_bwd(const __grid_constant__ ViewParams vp,
-                                                   const uint32_t* __restrict__ tile_ranges,
-                                                   const float4* __restrict__ staged, const float* __restrict__ cot_color,
-                                                   const float* __restrict__ cot_depth, const float* __restrict__ cot_alpha,
-                                                   const float* __restrict__ out_color, const float* __restrict__ out_depth,
-                                                   const float* __restrict__ out_alpha, const uint32_t* __restrict__ last_contrib,
-                                                   float* __restrict__ grad_rec)
+__global__ void __launch_bounds__(32, 16) k_raster_bwd(const __grid_constant__ ViewParams vp,
+                                                       const uint32_t* __restrict__ tile_ranges,
+                                                       const float4* __restrict__ staged, const float* __restrict__ cot_color,
+                                                       const float* __restrict__ cot_depth, const float* __restrict__ cot_alpha,
+                                                       const float* __restrict__ out_alpha,
+                                                       const uint32_t* __restrict__ last_contrib, float* __restrict__ grad_rec)
 {
     __shared__ __align__(128) float4 s_rec[2][RB_BWD * 3];
-    __shared__ __align__(16) float s_acc[RWARPS][RB_BWD][12];   // per-warp partial sums, no atomics
+    __shared__ __align__(16) float s_out[RB_BWD][12];   // per-Gaussian sums of this block for one batch
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_max[RWARPS];
-    const PixelMap pm = map_pixel(vp);
-    const uint32_t start = tile_ranges[pm.tile * 2], end = tile_ranges[pm.tile * 2 + 1];
+    const BlockMap bm = map_block(vp);
+    const int lane = threadIdx.x;
+    const uint32_t start = tile_ranges[bm.tile * 2], end = tile_ranges[bm.tile * 2 + 1];
     const uint32_t count = end > start ? end - start : 0u;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    float sX = 0.f, sY = 0.f, sZ = 0.f, sD = 0.f, sT = 0.f;
-    float kX = 0.f, kY = 0.f, kZ = 0.f, kD = 0.f, kT = 0.f;
-    uint32_t nContrib = 0;
-    const float px = (float)pm.px, py = (float)pm.py;
-    if (pm.active) {
-        // slang/gaussian_tile_global_kernels.slang:696-723
-        const size_t p = (size_t)pm.py * vp.W + pm.px;
-        kX = cot_color[p * 3];
-        kY = cot_color[p * 3 + 1];
-        kZ = cot_color[p * 3 + 2];
-        kD = cot_depth ? cot_depth[p] : 0.0f;
-        const float cotA = cot_alpha ? cot_alpha[p] : 0.0f;
-        const float trans = 1.0f - out_alpha[p];
-        const float bg = vp.whiteBg ? trans : 0.0f;
-        sX = out_color[p * 3] - bg;
-        sY = out_color[p * 3 + 1] - bg;
-        sZ = out_color[p * 3 + 2] - bg;
-        sD = out_depth[p];
-        sT = trans;
-        kT = -cotA + (vp.whiteBg ? (kX + kY + kZ) : 0.0f);
-        nContrib = min(last_contrib[p], count);
+    // thread = column (lane & 15) x 8 consecutive rows starting at (lane >> 4) * 8
+    const int pxi = bm.x0 + (lane & 15);
+    const int py0 = bm.y0 + (lane >> 4) * BPPT;
+    float sT[BPPT], kX[BPPT], kY[BPPT], kZ[BPPT], kD[BPPT], kT[BPPT];
+    uint32_t nC[BPPT];
+    uint32_t nmax = 0;
+#pragma unroll
+    for (int p = 0; p < BPPT; ++p) {
+        const int pyi = py0 + p;
+        sT[p] = 0.f; kX[p] = 0.f; kY[p] = 0.f; kZ[p] = 0.f; kD[p] = 0.f; kT[p] = 0.f;
+        nC[p] = 0;
+        if (pxi < bm.xmax && pyi < bm.ymax) {
+            // slang/gaussian_tile_global_kernels.slang:696-723
+            const size_t pix = (size_t)pyi * vp.W + pxi;
+            kX[p] = cot_color[pix * 3];
+            kY[p] = cot_color[pix * 3 + 1];
+            kZ[p] = cot_color[pix * 3 + 2];
+            kD[p] = cot_depth ? cot_depth[pix] : 0.0f;
+            const float cotA = cot_alpha ? cot_alpha[pix] : 0.0f;
+            sT[p] = 1.0f - out_alpha[pix];
+            kT[p] = -cotA + (vp.whiteBg ? (kX[p] + kY[p] + kZ[p]) : 0.0f);
+            nC[p] = min(last_contrib[pix], count);
+        }
+        nmax = max(nmax, nC[p]);
     }
     // only Gaussians below the block-wide max nContrib can contribute
-    uint32_t wmax = __reduce_max_sync(0xffffffffu, nContrib);
-    if (lane == 0) s_max[warp] = wmax;
-    if (threadIdx.x == 0) {
+    const uint32_t used = __reduce_max_sync(0xffffffffu, nmax);
+    const int nb = (int)((used + RB_BWD - 1) / RB_BWD);
+    if (nb == 0) return;
+    if (lane == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         mbar_fence_init();
     }
-    __syncthreads();
-    uint32_t used = 0;
-#pragma unroll
-    for (int w = 0; w < RWARPS; ++w) used = max(used, s_max[w]);
-    const int nb = (int)((used + RB_BWD - 1) / RB_BWD);
-    if (nb == 0) return;
+    __syncwarp();
 
-    // batches are visited last → first; sequence number s = nb-1-b selects stage / parity
+    // batches are visited last -> first; sequence number s = nb-1-b selects stage / parity
     auto issue = [&](int b) {
         const int s = nb - 1 - b;
         const uint32_t n = min((uint32_t)RB_BWD, used - (uint32_t)b * RB_BWD);
@@ -221,90 +244,95 @@ __global__ void __launch_bounds__(RT) k_raster_bwd(const __grid_constant__ ViewP
         mbar_expect_tx(bar, n * 48u);
         bulk_g2s(&s_rec[s & 1][0], staged + ((size_t)start + (size_t)b * RB_BWD) * 3, n * 48u, bar);
     };
-    if (threadIdx.x == 0) issue(nb - 1);
+    if (lane == 0) issue(nb - 1);
+
+    const float pxf = (float)pxi, pyf = (float)py0;
+    const uint32_t rec_base = smem_u32(&s_rec[0][0]);
+    const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
+    const int comp = 6 * b4 + 3 * b3 + (b2 ? 2 : b1);
+    const bool writer = !(lane & 1) && !(b2 && b1);
 
     for (int b = nb - 1; b >= 0; --b) {
         const int s = nb - 1 - b;
-        if (threadIdx.x == 0 && b > 0) issue(b - 1);
-        // zero this warp's partial sums (own slice only → no barrier needed before use)
+        __syncwarp();                               // every lane is done with the stage being refilled
+        if (lane == 0 && b > 0) issue(b - 1);
         {
-            float4* z = reinterpret_cast<float4*>(&s_acc[warp][0][0]);
+            float4* z = reinterpret_cast<float4*>(&s_out[0][0]);
             for (int i = lane; i < RB_BWD * 3; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        __syncwarp();
         mbar_wait(&s_bar[s & 1], (uint32_t)(s >> 1) & 1u);
+        __syncwarp();
         const int n = (int)min((uint32_t)RB_BWD, used - (uint32_t)b * RB_BWD);
-        const float4* r = &s_rec[s & 1][0];
+        const uint32_t stage_addr = rec_base + (uint32_t)(s & 1) * (RB_BWD * 48u);
         for (int j = n - 1; j >= 0; --j) {
             const uint32_t i = (uint32_t)(b * RB_BWD + j);
-            const bool act = i < nContrib;
-            if (!__any_sync(0xffffffffu, act)) continue;
+            if (!__any_sync(0xffffffffu, i < nmax)) continue;
+            const uint32_t addr = stage_addr + (uint32_t)j * 48u;
+            const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
+            const float dx = pxf - a.x, dyb = pyf - a.y;
+            const float A2 = a.z + a.z, C2 = q.x + q.x;
+            const float Bdx = a.w * dx;
+            const float Adx = a.z * dx;
             float g[12];
 #pragma unroll
             for (int k = 0; k < 12; ++k) g[k] = 0.0f;
-            if (act) {
-                const float4 a = r[j * 3], q = r[j * 3 + 1], c = r[j * 3 + 2];
-                const float dx = px - a.x, dy = py - a.y;
-                const float dxdy = dx * dy;
-                const float expo = -0.5f * (dx * dx * a.z + dy * dy * q.y + dxdy * a.w + dxdy * q.x);
-                const float ex = __expf(expo);
-                const float raw = ex * c.y;
-                const bool clamped = raw > 0.99f;
-                const float alpha = clamped ? 0.99f : raw;
-                // undoTileGlobalPixelState (:501-521)
-                float denom = 1.0f - alpha;
-                if (denom < 1e-6f) denom = 1e-6f;
-                const float prevT = sT / denom;
-                const float contrib = prevT * alpha;
-                sX -= contrib * q.z;
-                sY -= contrib * q.w;
-                sZ -= contrib * c.x;
-                sD -= contrib * c.z;
-                sT = prevT;
-                // VJP of updateTileGlobalPixelState (:485-499)
-                const float dotc = kX * q.z + kY * q.w + kZ * c.x + kD * c.z;
-                const float g_alpha = prevT * (dotc - kT);
-                kT = alpha * dotc + (1.0f - alpha) * kT;
-                g[6] = contrib * kX;
-                g[7] = contrib * kY;
-                g[8] = contrib * kZ;
-                g[10] = contrib * kD;
-                // VJP of evaluateTileGlobalSample / tileGlobalAlphaFromGaussian (:437-483)
-                const float g_raw = clamped ? 0.0f : g_alpha;
-                g[9] = g_raw * ex;
-                const float gq = -0.5f * (g_raw * raw);
-                g[2] = gq * dx * dx;
-                g[5] = gq * dy * dy;
-                g[3] = gq * dxdy;
-                g[4] = g[3];
-                const float csum = a.w + q.x;
-                g[0] = -gq * (2.0f * dx * a.z + dy * csum);
-                g[1] = -gq * (2.0f * dy * q.y + dx * csum);
-            }
-            const float tot = warp_reduce12(g, lane);
-            const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
-            const int comp = 6 * b4 + 3 * b3 + (b2 ? 2 : b1);
-            if (!(lane & 1) && !(b2 && b1)) s_acc[warp][j][comp] = tot;
-        }
-        __syncthreads();
-        // flush: sum the 8 warp slices, one 16-byte vector reduction per (record, quad)
-        for (int it = threadIdx.x; it < n * 3; it += RT) {
-            const int j = it / 3, qd = it - j * 3;
-            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int w = 0; w < RWARPS; ++w) {
-                const float4 v = *reinterpret_cast<const float4*>(&s_acc[w][j][qd * 4]);
-                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            for (int p = 0; p < BPPT; ++p) {
+                if (i < nC[p]) {
+                    const float dy = dyb + (float)p;
+                    // alpha (:437-483) in log2 units
+                    const float t = fmaf(a.w, dy, Adx);
+                    const float u = q.x * dy;
+                    const float ex = ex2_approx(fmaf(u, dy, dx * t));
+                    const float raw = ex * c.y;
+                    const bool clamped = raw > 0.99f;
+                    const float alpha = fminf(raw, 0.99f);
+                    // undoTileGlobalPixelState (:501-521): only the transmittance matters for the gradients
+                    const float prevT = sT[p] * rcp_approx(fmaxf(1.0f - alpha, 1e-6f));
+                    const float contrib = prevT * alpha;
+                    sT[p] = prevT;
+                    // VJP of updateTileGlobalPixelState (:485-499)
+                    const float dotc = fmaf(kD[p], c.z, fmaf(kZ[p], c.x, fmaf(kY[p], q.w, kX[p] * q.z)));
+                    const float d = dotc - kT[p];
+                    const float g_alpha = prevT * d;
+                    kT[p] = fmaf(alpha, d, kT[p]);
+                    g[6] = fmaf(contrib, kX[p], g[6]);
+                    g[7] = fmaf(contrib, kY[p], g[7]);
+                    g[8] = fmaf(contrib, kZ[p], g[8]);
+                    g[10] = fmaf(contrib, kD[p], g[10]);
+                    // VJP of evaluateTileGlobalSample: the alpha clamp branch has zero gradient
+                    const float h = clamped ? 0.0f : g_alpha * ex;   // d/d opacity
+                    g[9] += h;
+                    const float gp = h * c.y;                        // d/d (natural exponent)
+                    const float w = -0.5f * gp;
+                    const float wdx = w * dx, wdy = w * dy;
+                    g[2] = fmaf(wdx, dx, g[2]);
+                    g[3] = fmaf(wdx, dy, g[3]);
+                    g[5] = fmaf(wdy, dy, g[5]);
+                    // d exponent / d mean = -(2a dx + b dy, 2c dy + b dx) with (a,b,c) = (A,B,C)/log2(e)
+                    g[0] = fmaf(gp, fmaf(A2, dx, a.w * dy), g[0]);
+                    g[1] = fmaf(gp, fmaf(C2, dy, Bdx), g[1]);
+                }
             }
+            g[0] *= -(1.0f / LOG2E_F);
+            g[1] *= -(1.0f / LOG2E_F);
+            g[4] = g[3];   // g_c10 == g_c01
+            const float tot = warp_reduce12(g, lane);
+            if (writer) s_out[j][comp] = tot;
+        }
+        __syncwarp();
+        // flush: one 16-byte vector reduction per (record, quad) with a non-zero sum
+        for (int it = lane; it < n * 3; it += 32) {
+            const int j = it / 3, qd = it - j * 3;
+            const float4 sum = *reinterpret_cast<const float4*>(&s_out[j][qd * 4]);
             if (sum.x != 0.f || sum.y != 0.f || sum.z != 0.f || sum.w != 0.f) {
-                const uint32_t gi = __float_as_uint(r[j * 3 + 2].w);
+                const uint32_t gi = __float_as_uint(lds128(stage_addr + (uint32_t)j * 48u + 32u).w);
                 float* dst = grad_rec + (size_t)gi * REC_FLOATS + qd * 4;
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(sum.x), "f"(sum.y), "f"(sum.z),
                              "f"(sum.w)
                              : "memory");
             }
         }
-        __syncthreads();
     }
 }
 
@@ -349,10 +377,17 @@ cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint3
                               const float* out_color, const float* out_depth, const float* out_alpha,
                               const uint32_t* last_contrib, float* grad_rec)
 {
+    (void)out_color; (void)out_depth;   // the colour/depth state is not needed by the gradients (see kernel)
     const int blocks = raster_blocks(vp);
-    if (blocks > 0)
-        k_raster_bwd<<<blocks, RT, 0, st>>>(vp, tile_ranges, reinterpret_cast<const float4*>(staged), cot_color, cot_depth,
-                                            cot_alpha, out_color, out_depth, out_alpha, last_contrib, grad_rec);
+    if (blocks > 0) {
+        static bool carveout_set = false;
+        if (!carveout_set) {
+            cudaFuncSetAttribute(k_raster_bwd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carveout_set = true;
+        }
+        k_raster_bwd<<<blocks, 32, 0, st>>>(vp, tile_ranges, reinterpret_cast<const float4*>(staged), cot_color, cot_depth,
+                                            cot_alpha, out_alpha, last_contrib, grad_rec);
+    }
     return cudaGetLastError();
 }
 
