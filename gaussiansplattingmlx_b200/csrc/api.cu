@@ -56,6 +56,7 @@ struct Ctx {
 
     // per-tile / per-pixel
     uint32_t* tile_ranges = nullptr;  // [numTiles,2]
+    uint32_t* tile_order = nullptr;   // [numTiles] tile ids, longest list first
     float* out_color = nullptr;       // saved forward outputs
     float* out_depth = nullptr;
     float* out_alpha = nullptr;
@@ -314,7 +315,8 @@ static int run_binning(Ctx* c, int N, const ViewParams& vp, const float* depth_p
             GSB_CUDA_CHECK(c, launch_ranges_gather(c->stream, vp, c->keys[0], c->keys[1], c->vals[0], c->vals[1],
                                                    c->d_result_buf, &c->d_ctl[0], c->capM, rec, c->tile_ranges, c->staged,
                                                    c->numTiles));
-            ++launches;
+            GSB_CUDA_CHECK(c, launch_tile_order(c->stream, c->numTiles, c->tile_ranges, c->tile_order));
+            launches += 2;
         }
         // overflow check: the event fired right after the scan, long before the queue drains
         GSB_CUDA_CHECK(c, cudaEventSynchronize(c->ev_ctl));
@@ -355,7 +357,7 @@ static void destroy_ctx(Ctx* c)
     if (c->sort_ws) cudaFree(c->sort_ws);
     if (c->cub_tmp) cudaFree(c->cub_tmp);
     dev_free(c->dbg_keys); dev_free(c->dbg_vals);
-    dev_free(c->tile_ranges); dev_free(c->out_color); dev_free(c->out_depth); dev_free(c->out_alpha); dev_free(c->out_last);
+    dev_free(c->tile_ranges); dev_free(c->tile_order); dev_free(c->out_color); dev_free(c->out_depth); dev_free(c->out_alpha); dev_free(c->out_last);
     dev_free(c->mapA); dev_free(c->mapB); dev_free(c->mapC); dev_free(c->cot_render); dev_free(c->partial);
     dev_free(c->loss_accum); dev_free(c->d_ctl); dev_free(c->d_zero);
     dev_free(c->t_block); dev_free(c->t_accum);
@@ -462,6 +464,7 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
     }
     const size_t P = (size_t)c->P;
     CREATE_CHECK(dev_alloc(&c->tile_ranges, (size_t)c->numTiles * 2));
+    CREATE_CHECK(dev_alloc(&c->tile_order, (size_t)c->numTiles));
     CREATE_CHECK(dev_alloc(&c->out_color, P * 3));
     CREATE_CHECK(dev_alloc(&c->out_depth, P));
     CREATE_CHECK(dev_alloc(&c->out_alpha, P));
@@ -698,7 +701,8 @@ static int restage_packed(Ctx* c, int32_t N, const float* packed)
     GSB_CUDA_CHECK(c, gsb::launch_ranges_gather(c->stream, c->bin_vp, c->keys[0], c->keys[1], c->vals[0], c->vals[1],
                                                 c->d_result_buf, &c->d_ctl[0], c->capM, c->rec, c->tile_ranges, c->staged,
                                                 c->numTiles));
-    c->stats.kernel_launches += 2;
+    GSB_CUDA_CHECK(c, gsb::launch_tile_order(c->stream, c->numTiles, c->tile_ranges, c->tile_order));
+    c->stats.kernel_launches += 3;
     return GSB_OK;
 }
 
@@ -711,7 +715,7 @@ int gsb_raster_fwd(gsb_ctx* ctx, int32_t N, const float* packed, float* out_colo
     int rc = restage_packed(c, N, packed);
     if (rc != GSB_OK) return rc;
     gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
-    GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, c->bin_vp, c->tile_ranges, c->staged, out_color, out_depth, out_alpha,
+    GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, c->bin_vp, c->tile_ranges, c->tile_order, c->staged, out_color, out_depth, out_alpha,
                                              out_last_contrib));
     c->stats.kernel_launches += 1;
     return GSB_OK;
@@ -730,7 +734,7 @@ int gsb_raster_bwd(gsb_ctx* ctx, int32_t N, const float* packed, const float* co
     GSB_CUDA_CHECK(c, cudaMemsetAsync(c->grad_rec, 0, (size_t)N * gsb::REC_FLOATS * 4, c->stream));
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, c->bin_vp, c->tile_ranges, c->staged, cot_color, cot_depth, cot_alpha,
+        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, c->bin_vp, c->tile_ranges, c->tile_order, c->staged, cot_color, cot_depth, cot_alpha,
                                                  out_color, out_depth, out_alpha, last_contrib, c->grad_rec));
     }
     GSB_CUDA_CHECK(c, gsb::launch_rec_to_packed(c->stream, N, c->grad_rec, grad_packed));
@@ -787,7 +791,7 @@ static int render_forward_impl(Ctx* c, int32_t N, const float* xyz, const float*
     if (rc != GSB_OK) return rc;
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, vp, c->tile_ranges, c->staged, c->out_color, c->out_depth,
+        GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, vp, c->tile_ranges, c->tile_order, c->staged, c->out_color, c->out_depth,
                                                  c->out_alpha, c->out_last));
         c->stats.kernel_launches += 1;
     }
@@ -813,7 +817,7 @@ static int render_backward_impl(Ctx* c, const float* cot_render, const float* co
     GSB_CUDA_CHECK(c, cudaMemsetAsync(c->grad_rec, 0, (size_t)N * gsb::REC_FLOATS * 4, c->stream));
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, vp, c->tile_ranges, c->staged, cot_render, cot_depth, cot_alpha,
+        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, vp, c->tile_ranges, c->tile_order, c->staged, cot_render, cot_depth, cot_alpha,
                                                  c->out_color, c->out_depth, c->out_alpha, c->out_last, c->grad_rec));
     }
     {

@@ -70,6 +70,8 @@ cudaError_t launch_ranges_gather(cudaStream_t st, const ViewParams& vp, const ui
                                  const uint32_t* vals0, const uint32_t* vals1, const uint32_t* d_result_buf,
                                  const uint32_t* d_count, uint32_t capacity, const float* rec, uint32_t* tile_ranges,
                                  float* staged, int numTiles);
+// tile ids by descending list length (raster launch order)
+cudaError_t launch_tile_order(cudaStream_t st, int numTiles, const uint32_t* tile_ranges, uint32_t* order);
 cudaError_t launch_tile_counts(cudaStream_t st, int numTiles, const uint32_t* tile_ranges, uint32_t* tile_counts);
 // packed[N,11] (reference layout) → rec[N,12]
 cudaError_t launch_packed_to_rec(cudaStream_t st, int N, const float* packed, float* rec);
@@ -80,9 +82,11 @@ cudaError_t launch_merge_keys(cudaStream_t st, uint32_t M, const uint32_t* hi, c
                               uint64_t* keys);
 
 // ---- raster.cu ---------------------------------------------------------------------------------
-cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges, const float* staged,
+cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
+                              const uint32_t* tile_order, const float* staged,
                               float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last);
-cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges, const float* staged,
+cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
+                              const uint32_t* tile_order, const float* staged,
                               const float* cot_color, const float* cot_depth, const float* cot_alpha,
                               const float* out_color, const float* out_depth, const float* out_alpha,
                               const uint32_t* last_contrib, float* grad_rec);

@@ -35,13 +35,14 @@ struct BlockMap {
     int tile, x0, y0;   // pixel origin of the 16x16 block
     int xmax, ymax;     // exclusive pixel bounds of the tile clipped to the image
 };
-__device__ __forceinline__ BlockMap map_block(const ViewParams& vp)
+__device__ __forceinline__ BlockMap map_block(const ViewParams& vp, const uint32_t* __restrict__ tile_order)
 {
     const int subX = (vp.tileW + 15) >> 4, subY = (vp.tileH + 15) >> 4;
     const int per = subX * subY;
     BlockMap m;
-    m.tile = blockIdx.x / per;
-    const int sb = blockIdx.x - m.tile * per;
+    const int slot = blockIdx.x / per;
+    const int sb = blockIdx.x - slot * per;
+    m.tile = (int)tile_order[slot];   // heavy tiles first (binning.cu k_tile_order)
     const int tileX = m.tile % vp.gridW, tileY = m.tile / vp.gridW;
     m.x0 = tileX * vp.tileW + (sb % subX) * 16;
     m.y0 = tileY * vp.tileH + (sb / subX) * 16;
@@ -55,13 +56,14 @@ __device__ __forceinline__ BlockMap map_block(const ViewParams& vp)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RT) k_raster_fwd(const __grid_constant__ ViewParams vp,
                                                    const uint32_t* __restrict__ tile_ranges,
+                                                   const uint32_t* __restrict__ tile_order,
                                                    const float4* __restrict__ staged, float* __restrict__ out_color,
                                                    float* __restrict__ out_depth, float* __restrict__ out_alpha,
                                                    uint32_t* __restrict__ out_last)
 {
     __shared__ __align__(128) float4 s_rec[2][RB_FWD * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
-    const BlockMap bm = map_block(vp);
+    const BlockMap bm = map_block(vp, tile_order);
     const int pxi = bm.x0 + (threadIdx.x & 15), pyi = bm.y0 + (threadIdx.x >> 4);
     const bool active = pxi < bm.xmax && pyi < bm.ymax;
     const uint32_t start = tile_ranges[bm.tile * 2], end = tile_ranges[bm.tile * 2 + 1];
@@ -185,8 +187,9 @@ __device__ __forceinline__ float warp_reduce12(float (&v)[12], int lane)
     return v[0];
 }
 
-__global__ void __launch_bounds__(32, 16) k_raster_bwd(const __grid_constant__ ViewParams vp,
+__global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ ViewParams vp,
                                                        const uint32_t* __restrict__ tile_ranges,
+                                                       const uint32_t* __restrict__ tile_order,
                                                        const float4* __restrict__ staged, const float* __restrict__ cot_color,
                                                        const float* __restrict__ cot_depth, const float* __restrict__ cot_alpha,
                                                        const float* __restrict__ out_alpha,
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(32, 16) k_raster_bwd(const __grid_constant__ V
     __shared__ __align__(128) float4 s_rec[2][RB_BWD * 3];
     __shared__ __align__(16) float s_out[RB_BWD][12];   // per-Gaussian sums of this block for one batch
     __shared__ __align__(8) uint64_t s_bar[2];
-    const BlockMap bm = map_block(vp);
+    const BlockMap bm = map_block(vp, tile_order);
     const int lane = threadIdx.x;
     const uint32_t start = tile_ranges[bm.tile * 2], end = tile_ranges[bm.tile * 2 + 1];
     const uint32_t count = end > start ? end - start : 0u;
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(32, 16) k_raster_bwd(const __grid_constant__ V
     const int py0 = bm.y0 + (lane >> 4) * BPPT;
     float sT[BPPT], kX[BPPT], kY[BPPT], kZ[BPPT], kD[BPPT], kT[BPPT];
     uint32_t nC[BPPT];
-    uint32_t nmax = 0;
+    uint32_t nmax = 0, nmin = 0xffffffffu;
 #pragma unroll
     for (int p = 0; p < BPPT; ++p) {
         const int pyi = py0 + p;
@@ -224,6 +227,7 @@ __global__ void __launch_bounds__(32, 16) k_raster_bwd(const __grid_constant__ V
             nC[p] = min(last_contrib[pix], count);
         }
         nmax = max(nmax, nC[p]);
+        nmin = min(nmin, nC[p]);
     }
     // only Gaussians below the block-wide max nContrib can contribute
     const uint32_t used = __reduce_max_sync(0xffffffffu, nmax);
@@ -276,43 +280,52 @@ __global__ void __launch_bounds__(32, 16) k_raster_bwd(const __grid_constant__ V
             float g[12];
 #pragma unroll
             for (int k = 0; k < 12; ++k) g[k] = 0.0f;
+            // one pixel of this thread.  MASKED = false when every pixel of the block is known to be active.
+            // Neither variant branches, so the compiler interleaves the 8 dependent chains; in the masked
+            // variant an inactive pixel (i >= nContrib) computes and discards (selects keep its state).
+            auto pixel = [&](int p, bool masked) {
+                const bool act = !masked || (i < nC[p]);
+                const float dy = dyb + (float)p;
+                // alpha (:437-483) in log2 units
+                const float t = fmaf(a.w, dy, Adx);
+                const float u = q.x * dy;
+                const float ex = ex2_approx(fmaf(u, dy, dx * t));
+                const float raw = ex * c.y;
+                const bool keep = act && !(raw > 0.99f);   // the alpha clamp branch has zero gradient
+                const float alpha = fminf(raw, 0.99f);
+                // undoTileGlobalPixelState (:501-521): only the transmittance matters for the gradients;
+                // max(1 - alpha, 1e-6) == 1 - alpha because alpha <= 0.99
+                const float prevT = sT[p] * rcp_approx(1.0f - alpha);
+                const float contrib = act ? prevT * alpha : 0.0f;
+                sT[p] = act ? prevT : sT[p];
+                // VJP of updateTileGlobalPixelState (:485-499)
+                const float dotc = fmaf(kD[p], c.z, fmaf(kZ[p], c.x, fmaf(kY[p], q.w, kX[p] * q.z)));
+                const float d = dotc - kT[p];
+                const float g_alpha = prevT * d;
+                kT[p] = act ? fmaf(alpha, d, kT[p]) : kT[p];
+                g[6] = fmaf(contrib, kX[p], g[6]);
+                g[7] = fmaf(contrib, kY[p], g[7]);
+                g[8] = fmaf(contrib, kZ[p], g[8]);
+                g[10] = fmaf(contrib, kD[p], g[10]);
+                // VJP of evaluateTileGlobalSample
+                const float h = keep ? g_alpha * ex : 0.0f;      // d/d opacity
+                g[9] += h;
+                const float gp = h * c.y;                        // d/d (natural exponent)
+                const float w = -0.5f * gp;
+                const float wdx = w * dx, wdy = w * dy;
+                g[2] = fmaf(wdx, dx, g[2]);
+                g[3] = fmaf(wdx, dy, g[3]);
+                g[5] = fmaf(wdy, dy, g[5]);
+                // d exponent / d mean = -(2a dx + b dy, 2c dy + b dx) with (a,b,c) = (A,B,C)/log2(e)
+                g[0] = fmaf(gp, fmaf(A2, dx, a.w * dy), g[0]);
+                g[1] = fmaf(gp, fmaf(C2, dy, Bdx), g[1]);
+            };
+            if (__all_sync(0xffffffffu, i < nmin)) {
 #pragma unroll
-            for (int p = 0; p < BPPT; ++p) {
-                if (i < nC[p]) {
-                    const float dy = dyb + (float)p;
-                    // alpha (:437-483) in log2 units
-                    const float t = fmaf(a.w, dy, Adx);
-                    const float u = q.x * dy;
-                    const float ex = ex2_approx(fmaf(u, dy, dx * t));
-                    const float raw = ex * c.y;
-                    const bool clamped = raw > 0.99f;
-                    const float alpha = fminf(raw, 0.99f);
-                    // undoTileGlobalPixelState (:501-521): only the transmittance matters for the gradients
-                    const float prevT = sT[p] * rcp_approx(fmaxf(1.0f - alpha, 1e-6f));
-                    const float contrib = prevT * alpha;
-                    sT[p] = prevT;
-                    // VJP of updateTileGlobalPixelState (:485-499)
-                    const float dotc = fmaf(kD[p], c.z, fmaf(kZ[p], c.x, fmaf(kY[p], q.w, kX[p] * q.z)));
-                    const float d = dotc - kT[p];
-                    const float g_alpha = prevT * d;
-                    kT[p] = fmaf(alpha, d, kT[p]);
-                    g[6] = fmaf(contrib, kX[p], g[6]);
-                    g[7] = fmaf(contrib, kY[p], g[7]);
-                    g[8] = fmaf(contrib, kZ[p], g[8]);
-                    g[10] = fmaf(contrib, kD[p], g[10]);
-                    // VJP of evaluateTileGlobalSample: the alpha clamp branch has zero gradient
-                    const float h = clamped ? 0.0f : g_alpha * ex;   // d/d opacity
-                    g[9] += h;
-                    const float gp = h * c.y;                        // d/d (natural exponent)
-                    const float w = -0.5f * gp;
-                    const float wdx = w * dx, wdy = w * dy;
-                    g[2] = fmaf(wdx, dx, g[2]);
-                    g[3] = fmaf(wdx, dy, g[3]);
-                    g[5] = fmaf(wdy, dy, g[5]);
-                    // d exponent / d mean = -(2a dx + b dy, 2c dy + b dx) with (a,b,c) = (A,B,C)/log2(e)
-                    g[0] = fmaf(gp, fmaf(A2, dx, a.w * dy), g[0]);
-                    g[1] = fmaf(gp, fmaf(C2, dy, Bdx), g[1]);
-                }
+                for (int p = 0; p < BPPT; ++p) pixel(p, false);
+            } else {
+#pragma unroll
+                for (int p = 0; p < BPPT; ++p) pixel(p, true);
             }
             g[0] *= -(1.0f / LOG2E_F);
             g[1] *= -(1.0f / LOG2E_F);
@@ -362,17 +375,19 @@ static int raster_blocks(const ViewParams& vp)
     return vp.gridW * vp.gridH * subX * subY;
 }
 
-cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges, const float* staged,
+cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
+                              const uint32_t* tile_order, const float* staged,
                               float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last)
 {
     const int blocks = raster_blocks(vp);
     if (blocks > 0)
-        k_raster_fwd<<<blocks, RT, 0, st>>>(vp, tile_ranges, reinterpret_cast<const float4*>(staged), out_color, out_depth,
+        k_raster_fwd<<<blocks, RT, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(staged), out_color, out_depth,
                                             out_alpha, out_last);
     return cudaGetLastError();
 }
 
-cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges, const float* staged,
+cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
+                              const uint32_t* tile_order, const float* staged,
                               const float* cot_color, const float* cot_depth, const float* cot_alpha,
                               const float* out_color, const float* out_depth, const float* out_alpha,
                               const uint32_t* last_contrib, float* grad_rec)
@@ -385,7 +400,7 @@ cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint3
             cudaFuncSetAttribute(k_raster_bwd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             carveout_set = true;
         }
-        k_raster_bwd<<<blocks, 32, 0, st>>>(vp, tile_ranges, reinterpret_cast<const float4*>(staged), cot_color, cot_depth,
+        k_raster_bwd<<<blocks, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(staged), cot_color, cot_depth,
                                             cot_alpha, out_alpha, last_contrib, grad_rec);
     }
     return cudaGetLastError();
