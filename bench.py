@@ -286,12 +286,14 @@ def run_gsb(args, rank, local_rank, world):
     # per-stage averages on rank 0 (CUDA-event pairs recorded on the work stream during timed region 1)
     nv = max(len(my_views), 1)
     P = wl.width * wl.height
-    passes = -(-(32 + max(1, (ctx.num_tiles - 1).bit_length())) // 8)
+    passes = -(-max(1, (ctx.num_tiles - 1).bit_length()) // 8)
     M = pairs / nv
     E = evals / nv
     alg = {  # algorithmic bytes / flops per LAUNCH, per view unless noted
         "project_fwd": ("hbm", 284.0 * n), "project_bwd": ("hbm", 516.0 * n), "scan": ("hbm", 8.0 * n),
-        "keygen": ("hbm", 28.0 * n + 12.0 * M), "sort": ("hbm", M * (8.0 + 24.0 * passes)),
+        "depth_sort": ("hbm", n * (4.0 + 16.0 * 4)),          # 32-bit key + index, 4 onesweep passes (r+w) + histogram read
+        "keygen": ("hbm", 16.0 * n + 8.0 * M),              # perm, offset, rect in; (tile id, index) out
+        "sort": ("hbm", M * (4.0 + 16.0 * passes)),          # 8-byte pairs, `passes` onesweep passes on the tile id
         "ranges_gather": ("hbm", M * (12.0 + 96.0)), "raster_fwd": ("fp32", 27.0 * E), "raster_bwd": ("fp32", 80.0 * E),
         "loss": ("fp32", (225.0 + 170.0) * P * 3), "adam": ("hbm", 28.0 * 59 * n + 12.0 * n),
     }

@@ -16,7 +16,7 @@ LIB_PATH = HERE / "libgsb.so"
 GSB_OK = 0
 GSB_ERR_INVALID, GSB_ERR_CUDA, GSB_ERR_UNSUPPORTED, GSB_ERR_STATE, GSB_ERR_CAPACITY = -1, -2, -3, -4, -5
 GSB_FLAG_SORT_CUB = 1
-STAGE_COUNT = 11
+STAGE_COUNT = 12
 
 
 class GsbConfig(C.Structure):

@@ -34,14 +34,23 @@ struct Ctx {
     float* grad_rec = nullptr;     // [N,12]
     uint2* tile_rects = nullptr;   // [N]
     uint32_t* touched = nullptr;   // [N]
-    uint32_t* offsets = nullptr;   // [N]
+    uint32_t* offsets = nullptr;   // [N] exclusive scan of touched, in DEPTH order
+    uint32_t* dkeys[2] = {nullptr, nullptr};   // [N] asuint(depth) sort keys (ping-pong)
+    uint32_t* dvals[2] = {nullptr, nullptr};   // [N] Gaussian indices in depth order (ping-pong)
+    void* dsort_ws = nullptr;
+    SortPlan dplan;
+    const uint32_t* d_dresult_buf = nullptr;   // which dvals buffer holds the depth order
+    uint32_t* d_nvalue = nullptr;              // device copy of N (count of the depth sort)
+    uint32_t* offsets_ref = nullptr;           // [N] scan in index order (parity API: reference emission order)
+    const float* depth_src = nullptr;          // depth of Gaussian g at depth_src[g * depth_src_stride]
+    int depth_src_stride = 1;
     void* scan_ws = nullptr;
     float* act_tmp = nullptr;      // scratch for the reference-layout parity API ([N,12] floats)
 
     // per-pair buffers (capacity capM)
     uint32_t capM = 0;
-    uint64_t* keys[2] = {nullptr, nullptr};
-    uint32_t* vals[2] = {nullptr, nullptr};
+    uint32_t* keys[2] = {nullptr, nullptr};   // tile ids
+    uint32_t* vals[2] = {nullptr, nullptr};   // Gaussian indices
     float* staged = nullptr;       // [M,12]
     void* sort_ws = nullptr;
     SortPlan plan;
@@ -126,7 +135,7 @@ void set_error(Ctx* ctx, const std::string& msg)
 }
 
 static const char* kStageNames[GSB_STAGE_COUNT] = {"project_fwd", "scan", "keygen", "sort", "ranges_gather", "raster_fwd",
-                                                   "loss", "raster_bwd", "project_bwd", "adam", "h2d"};
+                                                   "loss", "raster_bwd", "project_bwd", "adam", "h2d", "depth_sort"};
 
 struct StageTimer {
     Ctx* c; int stage; bool on;
@@ -212,7 +221,9 @@ static int ensure_gaussians(Ctx* c, int N)
     }
     GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     dev_free(c->rec); dev_free(c->grad_rec); dev_free(c->tile_rects); dev_free(c->touched); dev_free(c->offsets);
-    dev_free(c->scan_ws); dev_free(c->act_tmp);
+    dev_free(c->scan_ws); dev_free(c->act_tmp); dev_free(c->offsets_ref);
+    for (int i = 0; i < 2; ++i) { dev_free(c->dkeys[i]); dev_free(c->dvals[i]); }
+    if (c->dsort_ws) { cudaFree(c->dsort_ws); c->dsort_ws = nullptr; }
     const int cap = c->cfg.max_gaussians > 0 ? c->cfg.max_gaussians : std::max(N, 1024);
     GSB_CUDA_CHECK(c, dev_alloc(&c->rec, (size_t)cap * REC_FLOATS));
     GSB_CUDA_CHECK(c, dev_alloc(&c->grad_rec, (size_t)cap * REC_FLOATS));
@@ -221,6 +232,13 @@ static int ensure_gaussians(Ctx* c, int N)
     GSB_CUDA_CHECK(c, dev_alloc(&c->offsets, (size_t)cap));
     GSB_CUDA_CHECK(c, dev_alloc(&c->act_tmp, (size_t)cap * REC_FLOATS));
     GSB_CUDA_CHECK(c, cudaMalloc(&c->scan_ws, scan_ws_bytes(cap)));
+    GSB_CUDA_CHECK(c, dev_alloc(&c->offsets_ref, (size_t)cap));
+    for (int i = 0; i < 2; ++i) {
+        GSB_CUDA_CHECK(c, dev_alloc(&c->dkeys[i], (size_t)cap));
+        GSB_CUDA_CHECK(c, dev_alloc(&c->dvals[i], (size_t)cap));
+    }
+    c->dplan = sort_plan((uint32_t)cap, 32u);
+    GSB_CUDA_CHECK(c, cudaMalloc(&c->dsort_ws, c->dplan.ws_bytes));
     c->capN = cap;
     return GSB_OK;
 }
@@ -244,23 +262,63 @@ static int ensure_pairs(Ctx* c, uint64_t M)
         GSB_CUDA_CHECK(c, dev_alloc(&c->vals[i], (size_t)cap));
     }
     GSB_CUDA_CHECK(c, dev_alloc(&c->staged, (size_t)cap * REC_FLOATS));
-    c->plan = sort_plan((uint32_t)cap, 32u + (uint32_t)c->tileBits);
+    c->plan = sort_plan((uint32_t)cap, (uint32_t)c->tileBits);
     GSB_CUDA_CHECK(c, cudaMalloc(&c->sort_ws, c->plan.ws_bytes));
     c->capM = (uint32_t)cap;
     c->stats.pair_capacity = cap;
     return GSB_OK;
 }
 
-// count → keys → sort → ranges (+ gather when rec != NULL).  tile_rects / touched must be filled.
+// depth sort → scan → keys → tile sort → ranges (+ gather when rec != NULL).
+// tile_rects / touched / dkeys[0] must be filled; depth of Gaussian g is depth_ptr[g * depth_stride].
+static int cub_sort32(Ctx* c, uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, uint32_t count, uint32_t end_bit)
+{
+    size_t need = 0;
+    GSB_CUDA_CHECK(c, cub_sort_pairs32(c->stream, k0, k1, v0, v1, count, end_bit, nullptr, 0, &need));
+    if (need > c->cub_tmp_bytes) {
+        GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        if (c->cub_tmp) cudaFree(c->cub_tmp);
+        c->cub_tmp = nullptr; c->cub_tmp_bytes = 0;
+        GSB_CUDA_CHECK(c, cudaMalloc(&c->cub_tmp, need));
+        c->cub_tmp_bytes = need;
+    }
+    if (count > 0) GSB_CUDA_CHECK(c, cub_sort_pairs32(c->stream, k0, k1, v0, v1, count, end_bit, c->cub_tmp, c->cub_tmp_bytes, nullptr));
+    return GSB_OK;
+}
+
 static int run_binning(Ctx* c, int N, const ViewParams& vp, const float* depth_ptr, int depth_stride, const float* rec,
                        bool keep_unsorted)
 {
     int launches = 0;
+    const bool use_cub = (c->cfg.flags & GSB_FLAG_SORT_CUB) != 0;
+    c->depth_src = depth_ptr;
+    c->depth_src_stride = depth_stride;
     for (int attempt = 0; attempt < 4; ++attempt) {
         {
-            StageTimer t(c, GSB_STAGE_SCAN);
+            StageTimer t(c, GSB_STAGE_DEPTH_SORT);
+            // 1. Gaussians into depth order (stable: ties keep index order)
+            const uint32_t n32 = (uint32_t)N;
             GSB_CUDA_CHECK(c, cudaMemsetAsync(c->d_ctl, 0, 2 * sizeof(uint32_t), c->stream));
-            GSB_CUDA_CHECK(c, launch_exclusive_scan(c->stream, N, c->touched, c->offsets, &c->d_ctl[0], c->scan_ws));
+            GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_nvalue, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+            if (use_cub) {
+                GSB_CUDA_CHECK(c, launch_iota(c->stream, n32, c->dvals[0]));
+                int rc = cub_sort32(c, c->dkeys[0], c->dkeys[1], c->dvals[0], c->dvals[1], n32, 32u);
+                if (rc != GSB_OK) return rc;
+                c->d_dresult_buf = N > 0 ? c->d_one : c->d_zero;
+                launches += 2;
+            } else {
+                SortPlan dp = c->dplan;
+                dp.capacity = n32;
+                dp.max_tiles = (uint32_t)cdiv(N > 0 ? N : 1, 4096);
+                GSB_CUDA_CHECK(c, launch_onesweep_sort32(c->stream, dp, c->dkeys[0], c->dkeys[1], c->dvals[0], c->dvals[1], 1,
+                                                         c->d_nvalue, c->dsort_ws, &c->d_dresult_buf, &launches));
+            }
+        }
+        {
+            StageTimer t(c, GSB_STAGE_SCAN);
+            // 2. offsets in depth order, M
+            GSB_CUDA_CHECK(c, launch_exclusive_scan(c->stream, N, c->touched, c->dvals[0], c->dvals[1], c->d_dresult_buf, c->offsets,
+                                                    &c->d_ctl[0], c->scan_ws));
             ++launches;
         }
         GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -272,42 +330,23 @@ static int run_binning(Ctx* c, int N, const ViewParams& vp, const float* depth_p
         }
         {
             StageTimer t(c, GSB_STAGE_KEYGEN);
-            GSB_CUDA_CHECK(c, launch_generate_keys(c->stream, N, vp, c->tile_rects, c->offsets, depth_ptr, depth_stride,
-                                                   c->keys[0], c->vals[0], c->capM, &c->d_ctl[0], &c->d_ctl[1]));
+            GSB_CUDA_CHECK(c, launch_generate_keys(c->stream, N, vp, c->tile_rects, c->offsets, c->dvals[0], c->dvals[1],
+                                                   c->d_dresult_buf, c->keys[0], c->vals[0], c->capM, &c->d_ctl[0], &c->d_ctl[1]));
             ++launches;
-        }
-        if (keep_unsorted) {
-            if (c->dbg_cap < c->capM) {
-                GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-                dev_free(c->dbg_keys); dev_free(c->dbg_vals);
-                GSB_CUDA_CHECK(c, dev_alloc(&c->dbg_keys, (size_t)c->capM));
-                GSB_CUDA_CHECK(c, dev_alloc(&c->dbg_vals, (size_t)c->capM));
-                c->dbg_cap = c->capM;
-            }
-            GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->dbg_keys, c->keys[0], (size_t)c->capM * 8, cudaMemcpyDeviceToDevice, c->stream));
-            GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->dbg_vals, c->vals[0], (size_t)c->capM * 4, cudaMemcpyDeviceToDevice, c->stream));
         }
         {
             StageTimer t(c, GSB_STAGE_SORT);
-            if (c->cfg.flags & GSB_FLAG_SORT_CUB) {
-                // checked baseline: needs the host-known count
-                GSB_CUDA_CHECK(c, cudaEventSynchronize(c->ev_ctl));
+            // 3. stable sort on the tile id alone (the list is already in (depth, index) order)
+            if (use_cub) {
+                GSB_CUDA_CHECK(c, cudaEventSynchronize(c->ev_ctl));   // checked baseline: needs the host-known count
                 const uint32_t M = std::min(c->h_ctl[0], c->capM);
-                size_t need = 0;
-                GSB_CUDA_CHECK(c, cub_sort_pairs(c->stream, c->keys[0], c->keys[1], c->vals[0], c->vals[1], M,
-                                                 32u + (uint32_t)c->tileBits, nullptr, 0, &need));
-                if (need > c->cub_tmp_bytes) {
-                    if (c->cub_tmp) cudaFree(c->cub_tmp);
-                    GSB_CUDA_CHECK(c, cudaMalloc(&c->cub_tmp, need));
-                    c->cub_tmp_bytes = need;
-                }
-                if (M > 0)
-                    GSB_CUDA_CHECK(c, cub_sort_pairs(c->stream, c->keys[0], c->keys[1], c->vals[0], c->vals[1], M,
-                                                     32u + (uint32_t)c->tileBits, c->cub_tmp, c->cub_tmp_bytes, nullptr));
+                int rc = cub_sort32(c, c->keys[0], c->keys[1], c->vals[0], c->vals[1], M, (uint32_t)c->tileBits);
+                if (rc != GSB_OK) return rc;
                 c->d_result_buf = M > 0 ? c->d_one : c->d_zero;
+                launches += 1;
             } else {
-                GSB_CUDA_CHECK(c, launch_onesweep_sort(c->stream, c->plan, c->keys[0], c->keys[1], c->vals[0], c->vals[1],
-                                                       &c->d_ctl[0], c->sort_ws, &c->d_result_buf, &launches));
+                GSB_CUDA_CHECK(c, launch_onesweep_sort32(c->stream, c->plan, c->keys[0], c->keys[1], c->vals[0], c->vals[1], 0,
+                                                         &c->d_ctl[0], c->sort_ws, &c->d_result_buf, &launches));
             }
         }
         {
@@ -324,13 +363,31 @@ static int run_binning(Ctx* c, int N, const ViewParams& vp, const float* depth_p
         if (M <= c->capM) {
             c->last_M = M;
             c->stats.kernel_launches += launches;
-            return GSB_OK;
+            break;
+        }
+        if (attempt == 3) {
+            set_error(c, "intersection buffers kept overflowing");
+            return GSB_ERR_CAPACITY;
         }
         int rc = ensure_pairs(c, M);
         if (rc != GSB_OK) return rc;
     }
-    set_error(c, "intersection buffers kept overflowing");
-    return GSB_ERR_CAPACITY;
+    if (keep_unsorted) {
+        // the reference's UNSORTED lists (emission order = Gaussian index order, 64-bit keys): parity API only
+        if (c->dbg_cap < c->capM) {
+            GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+            dev_free(c->dbg_keys); dev_free(c->dbg_vals);
+            GSB_CUDA_CHECK(c, dev_alloc(&c->dbg_keys, (size_t)c->capM));
+            GSB_CUDA_CHECK(c, dev_alloc(&c->dbg_vals, (size_t)c->capM));
+            c->dbg_cap = c->capM;
+        }
+        GSB_CUDA_CHECK(c, launch_exclusive_scan(c->stream, N, c->touched, nullptr, nullptr, nullptr, c->offsets_ref, &c->d_ctl[2],
+                                                c->scan_ws));
+        GSB_CUDA_CHECK(c, launch_generate_keys_ref(c->stream, N, vp, c->tile_rects, c->offsets_ref, depth_ptr, depth_stride,
+                                                   c->dbg_keys, c->dbg_vals, c->capM));
+        c->stats.kernel_launches += 2;
+    }
+    return GSB_OK;
 }
 
 static int check_ctx(Ctx* c)
@@ -350,7 +407,9 @@ static void destroy_ctx(Ctx* c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     dev_free(c->rec); dev_free(c->grad_rec); dev_free(c->tile_rects); dev_free(c->touched); dev_free(c->offsets);
-    dev_free(c->act_tmp);
+    dev_free(c->act_tmp); dev_free(c->offsets_ref); dev_free(c->d_nvalue);
+    for (int i = 0; i < 2; ++i) { dev_free(c->dkeys[i]); dev_free(c->dvals[i]); }
+    if (c->dsort_ws) cudaFree(c->dsort_ws);
     if (c->scan_ws) cudaFree(c->scan_ws);
     for (int i = 0; i < 2; ++i) { dev_free(c->keys[i]); dev_free(c->vals[i]); dev_free(c->t_target[i]); }
     dev_free(c->staged);
@@ -477,6 +536,7 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
     CREATE_CHECK(dev_alloc(&c->loss_accum, 4));
     CREATE_CHECK(dev_alloc(&c->d_ctl, 4));
     CREATE_CHECK(dev_alloc(&c->d_zero, 4));
+    CREATE_CHECK(dev_alloc(&c->d_nvalue, 4));
     c->d_one = c->d_zero + 1;
     const uint32_t zo[4] = {0u, 1u, 0u, 0u};
     CREATE_CHECK(cudaMemcpy(c->d_zero, zo, sizeof(zo), cudaMemcpyHostToDevice));
@@ -584,9 +644,12 @@ int gsb_bin(gsb_ctx* ctx, int32_t N, const float* rect_min, const float* rect_ma
     if (rc != GSB_OK) return rc;
     const gsb::ViewParams vp = gsb::make_view_nocam(c);
     c->saved.valid = false;
-    GSB_CUDA_CHECK(c, gsb::launch_count_tiles(c->stream, N, vp, rect_min, rect_max, radii, c->tile_rects, c->touched));
+    // keep a private copy of the depths: gsb_bin_read rebuilds the reference's sortedKeysLow from them
+    if (N > 0) GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->act_tmp, depths, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    GSB_CUDA_CHECK(c, gsb::launch_count_tiles(c->stream, N, vp, rect_min, rect_max, radii, c->act_tmp, c->tile_rects, c->touched,
+                                              c->dkeys[0]));
     c->stats.kernel_launches += N > 0;
-    rc = gsb::run_binning(c, N, vp, depths, 1, nullptr, true);
+    rc = gsb::run_binning(c, N, vp, c->act_tmp, 1, nullptr, true);
     if (rc != GSB_OK) return rc;
     c->bin_valid = true;
     c->bin_vp = vp;
@@ -620,7 +683,8 @@ int gsb_bin_read(gsb_ctx* ctx, uint32_t* keys_high, uint32_t* keys_low, uint32_t
         GSB_CUDA_CHECK(c, cudaMemcpyAsync(&c->h_ctl[2], c->d_result_buf, 4, cudaMemcpyDeviceToHost, c->stream));
         GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
         buf = c->h_ctl[2];
-        GSB_CUDA_CHECK(c, gsb::launch_split_keys(c->stream, M, c->keys[buf], sorted_keys_high, sorted_keys_low));
+        GSB_CUDA_CHECK(c, gsb::launch_sorted_keys_out(c->stream, M, c->keys[buf], c->vals[buf], c->depth_src, c->depth_src_stride,
+                                                      sorted_keys_high, sorted_keys_low));
         if (sorted_gauss_idx)
             GSB_CUDA_CHECK(c, cudaMemcpyAsync(sorted_gauss_idx, c->vals[buf], (size_t)M * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
@@ -784,7 +848,7 @@ static int render_forward_impl(Ctx* c, int32_t N, const float* xyz, const float*
     {
         gsb::StageTimer t(c, GSB_STAGE_PROJECT_FWD);
         GSB_CUDA_CHECK(c, gsb::launch_project_fused_fwd(c->stream, N, vp, xyz, f_dc, f_rest, scales_log, rot_raw, opacity_logit,
-                                                        c->rec, c->tile_rects, c->touched, radii, visibility));
+                                                        c->rec, c->tile_rects, c->touched, c->dkeys[0], radii, visibility));
         c->stats.kernel_launches += N > 0;
     }
     rc = gsb::run_binning(c, N, vp, c->rec + 10, gsb::REC_FLOATS, c->rec, false);

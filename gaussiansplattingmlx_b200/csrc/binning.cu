@@ -1,15 +1,26 @@
 // binning.cu — tile-intersection lists (K3..K8 of the reference) for sm_100a.
 //
-//   count (fused into projection) → single-pass decoupled-look-back scan → key duplication →
-//   hand-written ONESWEEP radix sort of 64-bit (tile_id << 32 | depth_bits) keys with 32-bit payloads →
-//   tile ranges + gather of the projected records into depth order.
-//
 // Reference: slang/gaussian_tile_global_kernels.slang:17-404 and the driver
-// Trainer/GaussianRenderer.swift:333-490 (two host syncs, single-threadgroup 4-bit sort, dense
-// [numTiles,maxTilePairs] padding).  Here nothing synchronises with the host: every kernel reads the
-// pair count M from device memory and is launched for the buffer capacity.
+// Trainer/GaussianRenderer.swift:333-490 (two host syncs, ONE 128-thread threadgroup doing a 4-bit LSD
+// sort of (tile, depth) keys over 12 passes, dense [numTiles,maxTilePairs] padding).
 //
-// All of this is HBM-bound integer work; the figures of merit are bytes moved per pair.
+// The reference order is: ascending tile id, then ascending asuint(depth), ties in emission order
+// (Gaussian index ascending).  It is produced here WITHOUT ever sorting 64-bit keys over the M pairs:
+//
+//   1. sort the N Gaussians by asuint(depth) (stable, 32-bit keys, payload = Gaussian index);
+//   2. exclusive scan of tiles-touched in that order (single pass, decoupled look-back);
+//   3. emit the (tile id, Gaussian) pairs in that order — the pair list is then already sorted by
+//      (depth, index) — with one thread per OUTPUT pair (binary search in shared memory), so the
+//      writes are fully coalesced;
+//   4. one STABLE radix sort of the M pairs on the tile id alone: ceil(tileBits/8) = 2 onesweep
+//      passes over 8-byte pairs instead of 6 passes over 12-byte pairs;
+//   5. tile ranges from the sorted tile ids + gather of the 48-byte records into tile/depth order.
+//
+// Nothing synchronises with the host: every kernel reads the pair count M from device memory and is
+// launched for the buffer capacity.  All of this is HBM-bound integer work; the figure of merit is
+// bytes moved per pair.  The hand-written onesweep (8-bit digits, chained-scan look-back, stable) is
+// also exposed stand-alone on 64-bit keys (gsb_sort_tile_keys = the reference's K5), with
+// cub::DeviceRadixSort as the checked baseline.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -19,11 +30,12 @@
 namespace gsb {
 
 // ------------------------------------------------------------------------------------------------
-// K3 on reference-layout inputs (parity API)
+// K3 on reference-layout inputs (parity API): tile rect, count and the depth sort key
 // ------------------------------------------------------------------------------------------------
 __global__ void k_count_tiles(int N, const __grid_constant__ ViewParams vp, const float* __restrict__ rectMin,
                               const float* __restrict__ rectMax, const float* __restrict__ radii,
-                              uint2* __restrict__ tile_rects, uint32_t* __restrict__ touched)
+                              const float* __restrict__ depths, uint2* __restrict__ tile_rects,
+                              uint32_t* __restrict__ touched, uint32_t* __restrict__ depth_keys)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -44,18 +56,20 @@ __global__ void k_count_tiles(int N, const __grid_constant__ ViewParams vp, cons
     if (cnt == 0) { x0 = y0 = x1 = y1 = 0; }
     tile_rects[i] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
     touched[i] = cnt;
+    depth_keys[i] = cnt ? __float_as_uint(depths[i]) : 0xffffffffu;   // Gaussians without tiles sort last
 }
 
 cudaError_t launch_count_tiles(cudaStream_t st, int N, const ViewParams& vp, const float* rectMin, const float* rectMax,
-                               const float* radii, uint2* tile_rects, uint32_t* touched)
+                               const float* radii, const float* depths, uint2* tile_rects, uint32_t* touched,
+                               uint32_t* depth_keys)
 {
-    if (N > 0) k_count_tiles<<<cdiv(N, 256), 256, 0, st>>>(N, vp, rectMin, rectMax, radii, tile_rects, touched);
+    if (N > 0) k_count_tiles<<<cdiv(N, 256), 256, 0, st>>>(N, vp, rectMin, rectMax, radii, depths, tile_rects, touched, depth_keys);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
 // exclusive scan (replaces MLX cumsum + `.item()` host sync, GaussianRenderer.swift:398-409)
-// single pass, decoupled look-back; 2048 items per CTA
+// single pass, decoupled look-back; 2048 items per CTA; optional gather through a permutation
 // ------------------------------------------------------------------------------------------------
 constexpr int SC_THREADS = 256;
 constexpr int SC_IPT = 8;
@@ -78,6 +92,9 @@ __device__ __forceinline__ void st_release_u64(uint64_t* p, uint64_t v)
 }
 
 __global__ void __launch_bounds__(SC_THREADS) k_exclusive_scan(int N, const uint32_t* __restrict__ in,
+                                                               const uint32_t* __restrict__ perm,
+                                                               const uint32_t* __restrict__ perm_sel,
+                                                               const uint32_t* __restrict__ perm_alt,
                                                                uint32_t* __restrict__ out, uint32_t* __restrict__ total,
                                                                uint32_t* counter, uint64_t* status)
 {
@@ -86,13 +103,14 @@ __global__ void __launch_bounds__(SC_THREADS) k_exclusive_scan(int N, const uint
     __shared__ uint32_t s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
     __syncthreads();
+    if (perm && perm_sel && *perm_sel) perm = perm_alt;   // which ping-pong buffer holds the sorted order
     const uint32_t tile = s_tile;
     const int base = tile * SC_TILE + threadIdx.x * SC_IPT;
     uint32_t v[SC_IPT];
     uint32_t sum = 0;
 #pragma unroll
     for (int i = 0; i < SC_IPT; ++i) {
-        v[i] = (base + i < N) ? in[base + i] : 0u;
+        v[i] = (base + i < N) ? (perm ? in[perm[base + i]] : in[base + i]) : 0u;
         sum += v[i];
     }
     // block inclusive scan of per-thread sums
@@ -144,36 +162,36 @@ __global__ void __launch_bounds__(SC_THREADS) k_exclusive_scan(int N, const uint
     }
 }
 
-cudaError_t launch_exclusive_scan(cudaStream_t st, int N, const uint32_t* touched, uint32_t* offsets, uint32_t* total,
-                                  void* scan_ws)
+cudaError_t launch_exclusive_scan(cudaStream_t st, int N, const uint32_t* in, const uint32_t* perm0, const uint32_t* perm1,
+                                  const uint32_t* perm_sel, uint32_t* offsets, uint32_t* total, void* scan_ws)
 {
     if (N <= 0) return cudaMemsetAsync(total, 0, sizeof(uint32_t), st);
     cudaError_t e = cudaMemsetAsync(scan_ws, 0, scan_ws_bytes(N), st);
     if (e != cudaSuccess) return e;
     uint32_t* counter = reinterpret_cast<uint32_t*>(scan_ws);
     uint64_t* status = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(scan_ws) + 16);
-    k_exclusive_scan<<<cdiv(N, SC_TILE), SC_THREADS, 0, st>>>(N, touched, offsets, total, counter, status);
+    k_exclusive_scan<<<cdiv(N, SC_TILE), SC_THREADS, 0, st>>>(N, in, perm0, perm_sel, perm1, offsets, total, counter, status);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4 generate_keys (slang/gaussian_tile_global_kernels.slang:73-126): row-major tile order per
-// Gaussian, key = tile id (high word) | asuint(depth) (low word), payload = Gaussian index.
+// K4 generate_keys (slang/gaussian_tile_global_kernels.slang:73-126).
+// (a) reference emission order, 64-bit keys: only for the unsorted lists of the parity API;
+// (b) depth order, tile-id keys, one thread per OUTPUT pair: the production path.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_generate_keys(int N, const __grid_constant__ ViewParams vp, const uint2* __restrict__ tile_rects,
-                                const uint32_t* __restrict__ offsets, const float* __restrict__ depth_ptr,
-                                int depth_stride, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                uint32_t capacity, const uint32_t* __restrict__ total, uint32_t* overflow_flag)
+__global__ void k_generate_keys_ref(int N, const __grid_constant__ ViewParams vp, const uint2* __restrict__ tile_rects,
+                                    const uint32_t* __restrict__ offsets, const float* __restrict__ depth_ptr,
+                                    int depth_stride, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                    uint32_t capacity)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0 && *total > capacity) *overflow_flag = 1u;
     if (i >= N) return;
     uint2 r = tile_rects[i];
     int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
     if (x1 <= x0 || y1 <= y0) return;
     uint32_t off = offsets[i];
     uint32_t cnt = (uint32_t)((x1 - x0) * (y1 - y0));
-    if (off + cnt > capacity) return;  // flagged above; the step is redone with larger buffers
+    if (off + cnt > capacity) return;
     uint32_t depthBits = __float_as_uint(depth_ptr[(size_t)i * depth_stride]);
     for (int ty = y0; ty < y1; ++ty)
         for (int tx = x0; tx < x1; ++tx) {
@@ -184,22 +202,85 @@ __global__ void k_generate_keys(int N, const __grid_constant__ ViewParams vp, co
         }
 }
 
-cudaError_t launch_generate_keys(cudaStream_t st, int N, const ViewParams& vp, const uint2* tile_rects,
-                                 const uint32_t* offsets, const float* depth_ptr, int depth_stride, uint64_t* keys,
-                                 uint32_t* vals, uint32_t capacity, const uint32_t* total, uint32_t* overflow_flag)
+cudaError_t launch_generate_keys_ref(cudaStream_t st, int N, const ViewParams& vp, const uint2* tile_rects,
+                                     const uint32_t* offsets, const float* depth_ptr, int depth_stride, uint64_t* keys,
+                                     uint32_t* vals, uint32_t capacity)
 {
     if (N > 0)
-        k_generate_keys<<<cdiv(N, 256), 256, 0, st>>>(N, vp, tile_rects, offsets, depth_ptr, depth_stride, keys, vals,
-                                                      capacity, total, overflow_flag);
+        k_generate_keys_ref<<<cdiv(N, 256), 256, 0, st>>>(N, vp, tile_rects, offsets, depth_ptr, depth_stride, keys, vals, capacity);
+    return cudaGetLastError();
+}
+
+constexpr int KG_THREADS = 256;
+
+__global__ void __launch_bounds__(KG_THREADS) k_generate_keys(int N, int gridW, const uint2* __restrict__ tile_rects,
+                                                              const uint32_t* __restrict__ offsets,
+                                                              const uint32_t* __restrict__ perm0,
+                                                              const uint32_t* __restrict__ perm1,
+                                                              const uint32_t* __restrict__ perm_sel,
+                                                              uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                              uint32_t capacity, const uint32_t* __restrict__ total,
+                                                              uint32_t* overflow_flag)
+{
+    __shared__ uint32_t s_off[KG_THREADS + 1];
+    __shared__ uint2 s_rect[KG_THREADS];
+    __shared__ uint32_t s_g[KG_THREADS];
+    const uint32_t* perm = (perm_sel && *perm_sel) ? perm1 : perm0;
+    const int i0 = blockIdx.x * KG_THREADS;
+    const int i = i0 + threadIdx.x;
+    const uint32_t M = *total;
+    if (i == 0 && M > capacity) *overflow_flag = 1u;
+    if (i < N) {
+        const uint32_t g = perm[i];
+        s_g[threadIdx.x] = g;
+        s_rect[threadIdx.x] = tile_rects[g];
+        s_off[threadIdx.x] = offsets[i];
+    } else {
+        s_off[threadIdx.x] = M;
+        s_rect[threadIdx.x] = make_uint2(0u, 0u);
+        s_g[threadIdx.x] = 0u;
+    }
+    if (threadIdx.x == 0) s_off[KG_THREADS] = (i0 + KG_THREADS < N) ? offsets[i0 + KG_THREADS] : M;
+    __syncthreads();
+    const uint32_t begin = s_off[0];
+    const uint32_t end = min(s_off[KG_THREADS], capacity);
+    for (uint32_t j = begin + threadIdx.x; j < end; j += KG_THREADS) {
+        // owner of output slot j = the LAST index k with s_off[k] <= j (indices on a plateau before it own nothing)
+        int lo = 0, hi = KG_THREADS;   // invariant: s_off[lo] <= j < s_off[hi]
+#pragma unroll
+        for (int step = 0; step < 8; ++step) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= j) lo = mid; else hi = mid;
+        }
+        const uint2 r = s_rect[lo];
+        const uint32_t x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff;
+        const uint32_t w = x1 - x0;
+        const uint32_t rel = j - s_off[lo];
+        const uint32_t dy = rel / w;
+        const uint32_t dx = rel - dy * w;
+        keys[j] = (y0 + dy) * (uint32_t)gridW + (x0 + dx);
+        vals[j] = s_g[lo];
+    }
+}
+
+cudaError_t launch_generate_keys(cudaStream_t st, int N, const ViewParams& vp, const uint2* tile_rects,
+                                 const uint32_t* offsets, const uint32_t* perm0, const uint32_t* perm1,
+                                 const uint32_t* perm_sel, uint32_t* keys, uint32_t* vals, uint32_t capacity,
+                                 const uint32_t* total, uint32_t* overflow_flag)
+{
+    if (N > 0)
+        k_generate_keys<<<cdiv(N, KG_THREADS), KG_THREADS, 0, st>>>(N, vp.gridW, tile_rects, offsets, perm0, perm1, perm_sel, keys,
+                                                                    vals, capacity, total, overflow_flag);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
 // ONESWEEP radix sort: 8-bit digits, one upfront histogram of every digit place, then one
-// chained-scan (decoupled look-back) + scatter kernel per digit place.  Stable.
+// chained-scan (decoupled look-back) + scatter kernel per digit place.  Stable.  KeyT = u32 | u64.
 // Replaces radix_sort_tile_keys_fused_forward (one 128-thread threadgroup, 4-bit digits,
 // slang/gaussian_tile_global_kernels.slang:143-305).
 // Digit places whose histogram has a single occupied bin are skipped (device-side decision).
+// iota != 0 means "payload = element index", synthesised by the first executed pass.
 // ------------------------------------------------------------------------------------------------
 constexpr int OS_THREADS = 256;
 constexpr int OS_WARPS = OS_THREADS / 32;
@@ -224,7 +305,8 @@ struct SortCtl {
     uint32_t result_buf;
     uint32_t count;
     uint32_t num_tiles;
-    uint32_t pad[5];
+    uint32_t first_pass;   // first pass that is not skipped (OS_MAX_PASSES when all are)
+    uint32_t pad[4];
 };
 static_assert(sizeof(SortCtl) == 128, "SortCtl layout");
 
@@ -241,7 +323,8 @@ SortPlan sort_plan(uint32_t capacity, uint32_t end_bit)
     return p;
 }
 
-__global__ void __launch_bounds__(256) k_os_histogram(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ d_count,
+template <typename KeyT>
+__global__ void __launch_bounds__(256) k_os_histogram(const KeyT* __restrict__ keys, const uint32_t* __restrict__ d_count,
                                                       uint32_t capacity, int passes, int end_bit, uint32_t* __restrict__ hist)
 {
     __shared__ uint32_t sh[OS_MAX_PASSES * OS_RADIX];
@@ -253,7 +336,7 @@ __global__ void __launch_bounds__(256) k_os_histogram(const uint64_t* __restrict
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {
         uint32_t idx = base + lane;
         bool valid = idx < count;
-        uint64_t key = valid ? keys[idx] : 0ull;
+        KeyT key = valid ? keys[idx] : (KeyT)0;
         uint32_t m = __ballot_sync(0xffffffffu, valid);
         int leader = __ffs(m) - 1;
         for (int p = 0; p < passes; ++p) {
@@ -297,20 +380,25 @@ __global__ void __launch_bounds__(OS_RADIX) k_os_scan(SortCtl* ctl, uint32_t* hi
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        uint32_t cur = 0;
+        uint32_t cur = 0, first = OS_MAX_PASSES;
         for (int p = 0; p < passes; ++p) {
             ctl->skip[p] = s_skip[p];
             ctl->src_buf[p] = cur;
-            if (!s_skip[p]) cur ^= 1u;
+            if (!s_skip[p]) {
+                if (first == OS_MAX_PASSES) first = (uint32_t)p;
+                cur ^= 1u;
+            }
         }
+        ctl->first_pass = first;
         ctl->result_buf = cur;
         ctl->count = count;
         ctl->num_tiles = (count + OS_TILE - 1) / OS_TILE;
     }
 }
 
+template <typename KeyT>
 struct OsSmem {
-    uint64_t keys[OS_TILE];
+    KeyT keys[OS_TILE];
     uint32_t vals[OS_TILE];
     uint32_t warp_hist[OS_WARPS][OS_RADIX];
     uint32_t block_excl[OS_RADIX];
@@ -319,12 +407,13 @@ struct OsSmem {
     uint32_t tile;
 };
 
+template <typename KeyT>
 __global__ void __launch_bounds__(OS_THREADS) k_os_pass(int pass, uint32_t dmask, SortCtl* ctl, const uint32_t* __restrict__ hist_excl,
-                                                        uint32_t* lookback, uint32_t max_tiles, uint64_t* keys0,
-                                                        uint64_t* keys1, uint32_t* vals0, uint32_t* vals1)
+                                                        uint32_t* lookback, uint32_t max_tiles, KeyT* keys0, KeyT* keys1,
+                                                        uint32_t* vals0, uint32_t* vals1, int iota)
 {
     extern __shared__ __align__(16) unsigned char os_raw[];
-    OsSmem& S = *reinterpret_cast<OsSmem*>(os_raw);
+    OsSmem<KeyT>& S = *reinterpret_cast<OsSmem<KeyT>*>(os_raw);
     if (ctl->skip[pass]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) S.tile = atomicAdd(&ctl->tile_counter[pass], 1u);
@@ -334,21 +423,22 @@ __global__ void __launch_bounds__(OS_THREADS) k_os_pass(int pass, uint32_t dmask
     const uint32_t count = ctl->count;
     if (tile >= ctl->num_tiles) return;
     const uint32_t src = ctl->src_buf[pass];
-    const uint64_t* kin = src ? keys1 : keys0;
+    const bool synth = iota && (uint32_t)pass == ctl->first_pass;   // payload = element index
+    const KeyT* kin = src ? keys1 : keys0;
     const uint32_t* vin = src ? vals1 : vals0;
-    uint64_t* kout = src ? keys0 : keys1;
+    KeyT* kout = src ? keys0 : keys1;
     uint32_t* vout = src ? vals0 : vals1;
     const uint32_t tile_base = tile * OS_TILE;
     const uint32_t valid = min((uint32_t)OS_TILE, count - tile_base);
     const int shift = pass * 8;
 
     // warp-striped load: stability order is (warp, item, lane)
-    uint64_t key[OS_IPT];
+    KeyT key[OS_IPT];
     const uint32_t wbase = warp * (OS_IPT * 32);
 #pragma unroll
     for (int i = 0; i < OS_IPT; ++i) {
         uint32_t idx = wbase + i * 32 + lane;
-        key[i] = idx < valid ? kin[tile_base + idx] : ~0ull;
+        key[i] = idx < valid ? kin[tile_base + idx] : ~(KeyT)0;
     }
     // per-warp stable ranking with match.any
     uint16_t rank[OS_IPT];
@@ -419,12 +509,12 @@ __global__ void __launch_bounds__(OS_THREADS) k_os_pass(int pass, uint32_t dmask
         uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
         uint32_t pos = S.block_excl[d] + S.warp_hist[warp][d] + rank[i];
         S.keys[pos] = key[i];
-        S.vals[pos] = idx < valid ? vin[tile_base + idx] : 0u;
+        S.vals[pos] = idx < valid ? (synth ? tile_base + idx : vin[tile_base + idx]) : 0u;
     }
     __syncthreads();
     // coalesced runs out
     for (uint32_t idx = tid; idx < valid; idx += OS_THREADS) {
-        uint64_t k = S.keys[idx];
+        KeyT k = S.keys[idx];
         uint32_t d = (uint32_t)(k >> shift) & dmask;
         uint32_t dst = S.digit_base[d] + idx;
         kout[dst] = k;
@@ -432,9 +522,17 @@ __global__ void __launch_bounds__(OS_THREADS) k_os_pass(int pass, uint32_t dmask
     }
 }
 
-cudaError_t launch_onesweep_sort(cudaStream_t st, const SortPlan& plan, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0,
-                                 uint32_t* vals1, const uint32_t* d_count, void* ws, const uint32_t** result_buf_ptr,
-                                 int* launches)
+// when every pass was skipped and the payload is synthetic, the "sorted" payload is the identity
+__global__ void k_os_iota_if_unsorted(const SortCtl* ctl, uint32_t* vals0)
+{
+    if (ctl->first_pass != OS_MAX_PASSES) return;
+    const uint32_t count = ctl->count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) vals0[i] = i;
+}
+
+template <typename KeyT>
+static cudaError_t onesweep_impl(cudaStream_t st, const SortPlan& plan, KeyT* keys0, KeyT* keys1, uint32_t* vals0, uint32_t* vals1,
+                                 int iota, const uint32_t* d_count, void* ws, const uint32_t** result_buf_ptr, int* launches)
 {
     SortCtl* ctl = reinterpret_cast<SortCtl*>(ws);
     uint32_t* hist = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + sizeof(SortCtl));
@@ -443,19 +541,39 @@ cudaError_t launch_onesweep_sort(cudaStream_t st, const SortPlan& plan, uint64_t
     cudaError_t e = cudaMemsetAsync(ws, 0, plan.ws_bytes, st);
     if (e != cudaSuccess) return e;
     int hist_blocks = (int)std::min<uint32_t>(plan.max_tiles, 148u * 8u);
-    k_os_histogram<<<hist_blocks, 256, 0, st>>>(keys0, d_count, plan.capacity, (int)plan.passes, (int)plan.end_bit, hist);
+    k_os_histogram<KeyT><<<hist_blocks, 256, 0, st>>>(keys0, d_count, plan.capacity, (int)plan.passes, (int)plan.end_bit, hist);
     k_os_scan<<<1, OS_RADIX, 0, st>>>(ctl, hist, d_count, plan.capacity, (int)plan.passes);
     static bool attr_set = false;
     if (!attr_set) {
-        e = cudaFuncSetAttribute(k_os_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem));
+        e = cudaFuncSetAttribute(k_os_pass<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem<KeyT>));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     for (uint32_t p = 0; p < plan.passes; ++p)
-        k_os_pass<<<plan.max_tiles, OS_THREADS, sizeof(OsSmem), st>>>((int)p, os_digit_mask((int)plan.end_bit, (int)p), ctl, hist, lookback, plan.max_tiles, keys0,
-                                                                      keys1, vals0, vals1);
-    if (launches) *launches += 2 + (int)plan.passes;
+        k_os_pass<KeyT><<<plan.max_tiles, OS_THREADS, sizeof(OsSmem<KeyT>), st>>>((int)p, os_digit_mask((int)plan.end_bit, (int)p), ctl,
+                                                                                    hist, lookback, plan.max_tiles, keys0, keys1, vals0,
+                                                                                    vals1, iota);
+    int n = 2 + (int)plan.passes;
+    if (iota) {
+        k_os_iota_if_unsorted<<<std::max(1, std::min((int)plan.max_tiles, 148 * 4)), 256, 0, st>>>(ctl, vals0);
+        ++n;
+    }
+    if (launches) *launches += n;
     return cudaGetLastError();
+}
+
+cudaError_t launch_onesweep_sort(cudaStream_t st, const SortPlan& plan, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0,
+                                 uint32_t* vals1, const uint32_t* d_count, void* ws, const uint32_t** result_buf_ptr,
+                                 int* launches)
+{
+    return onesweep_impl<uint64_t>(st, plan, keys0, keys1, vals0, vals1, 0, d_count, ws, result_buf_ptr, launches);
+}
+
+cudaError_t launch_onesweep_sort32(cudaStream_t st, const SortPlan& plan, uint32_t* keys0, uint32_t* keys1, uint32_t* vals0,
+                                   uint32_t* vals1, int iota, const uint32_t* d_count, void* ws,
+                                   const uint32_t** result_buf_ptr, int* launches)
+{
+    return onesweep_impl<uint32_t>(st, plan, keys0, keys1, vals0, vals1, iota, d_count, ws, result_buf_ptr, launches);
 }
 
 cudaError_t cub_sort_pairs(cudaStream_t st, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1,
@@ -469,12 +587,34 @@ cudaError_t cub_sort_pairs(cudaStream_t st, uint64_t* keys0, uint64_t* keys1, ui
     return cub::DeviceRadixSort::SortPairs(tmp, need, keys0, keys1, vals0, vals1, (int)count, 0, (int)end_bit, st);
 }
 
+cudaError_t cub_sort_pairs32(cudaStream_t st, uint32_t* keys0, uint32_t* keys1, uint32_t* vals0, uint32_t* vals1,
+                             uint32_t count, uint32_t end_bit, void* tmp, size_t tmp_bytes, size_t* tmp_needed)
+{
+    size_t need = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, need, keys0, keys1, vals0, vals1, (int)count, 0, (int)end_bit, st);
+    if (e != cudaSuccess) return e;
+    if (tmp_needed) *tmp_needed = need;
+    if (!tmp || tmp_bytes < need) return cudaSuccess;
+    return cub::DeviceRadixSort::SortPairs(tmp, need, keys0, keys1, vals0, vals1, (int)count, 0, (int)end_bit, st);
+}
+
+__global__ void k_iota(uint32_t n, uint32_t* v)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+cudaError_t launch_iota(cudaStream_t st, uint32_t n, uint32_t* v)
+{
+    if (n > 0) k_iota<<<cdiv(n, 256), 256, 0, st>>>(n, v);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // K6/K7 (slang/gaussian_tile_global_kernels.slang:314-367) + gather of records into tile/depth order.
 // Three threads per pair: each moves one 16-byte third of the 48-byte record (coalesced stores);
 // the first of the three also does the tile-boundary detection.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ranges_gather(const uint64_t* __restrict__ keys0, const uint64_t* __restrict__ keys1,
+__global__ void __launch_bounds__(256) k_ranges_gather(const uint32_t* __restrict__ keys0, const uint32_t* __restrict__ keys1,
                                                        const uint32_t* __restrict__ vals0, const uint32_t* __restrict__ vals1,
                                                        const uint32_t* __restrict__ d_result_buf,
                                                        const uint32_t* __restrict__ d_count, uint32_t capacity,
@@ -483,7 +623,7 @@ __global__ void __launch_bounds__(256) k_ranges_gather(const uint64_t* __restric
 {
     const uint32_t M = min(*d_count, capacity);
     const uint32_t buf = d_result_buf ? *d_result_buf : 0u;
-    const uint64_t* keys = buf ? keys1 : keys0;
+    const uint32_t* keys = buf ? keys1 : keys0;
     const uint32_t* vals = buf ? vals1 : vals0;
     const uint64_t total = (uint64_t)M * 3u;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
@@ -491,11 +631,11 @@ __global__ void __launch_bounds__(256) k_ranges_gather(const uint64_t* __restric
         uint32_t gi = vals[j];
         if (rec) staged[(size_t)j * 3 + part] = rec[(size_t)gi * 3 + part];
         if (part == 0) {
-            uint32_t cur = (uint32_t)(keys[j] >> 32);
+            uint32_t cur = keys[j];
             if (j == 0) {
                 tile_ranges[cur * 2 + 0] = 0;
             } else {
-                uint32_t prev = (uint32_t)(keys[j - 1] >> 32);
+                uint32_t prev = keys[j - 1];
                 if (cur != prev) {
                     tile_ranges[prev * 2 + 1] = j;
                     tile_ranges[cur * 2 + 0] = j;
@@ -506,11 +646,12 @@ __global__ void __launch_bounds__(256) k_ranges_gather(const uint64_t* __restric
     }
 }
 
-cudaError_t launch_ranges_gather(cudaStream_t st, const ViewParams& vp, const uint64_t* keys0, const uint64_t* keys1,
+cudaError_t launch_ranges_gather(cudaStream_t st, const ViewParams& vp, const uint32_t* keys0, const uint32_t* keys1,
                                  const uint32_t* vals0, const uint32_t* vals1, const uint32_t* d_result_buf,
                                  const uint32_t* d_count, uint32_t capacity, const float* rec, uint32_t* tile_ranges,
                                  float* staged, int numTiles)
 {
+    (void)vp;
     cudaError_t e = cudaMemsetAsync(tile_ranges, 0, (size_t)numTiles * 2 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     if (capacity == 0) return cudaSuccess;
@@ -629,6 +770,16 @@ __global__ void k_merge_keys(uint32_t M, const uint32_t* __restrict__ hi, const 
     if (i >= M) return;
     keys[i] = ((uint64_t)(hi[i] & hi_mask) << 32) | lo[i];
 }
+// sorted (tile id, Gaussian) lists -> the reference's sortedKeysHigh / sortedKeysLow (= asuint(depth of the Gaussian))
+__global__ void k_sorted_keys_out(uint32_t M, const uint32_t* __restrict__ tile_keys, const uint32_t* __restrict__ vals,
+                                  const float* __restrict__ depth_ptr, int depth_stride, uint32_t* __restrict__ hi,
+                                  uint32_t* __restrict__ lo)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    if (hi) hi[i] = tile_keys[i];
+    if (lo) lo[i] = __float_as_uint(depth_ptr[(size_t)vals[i] * depth_stride]);
+}
 cudaError_t launch_split_keys(cudaStream_t st, uint32_t M, const uint64_t* keys, uint32_t* hi, uint32_t* lo)
 {
     if (M > 0) k_split_keys<<<cdiv(M, 256), 256, 0, st>>>(M, keys, hi, lo);
@@ -638,6 +789,12 @@ cudaError_t launch_merge_keys(cudaStream_t st, uint32_t M, const uint32_t* hi, c
                               uint64_t* keys)
 {
     if (M > 0) k_merge_keys<<<cdiv(M, 256), 256, 0, st>>>(M, hi, lo, hi_mask, keys);
+    return cudaGetLastError();
+}
+cudaError_t launch_sorted_keys_out(cudaStream_t st, uint32_t M, const uint32_t* tile_keys, const uint32_t* vals,
+                                   const float* depth_ptr, int depth_stride, uint32_t* hi, uint32_t* lo)
+{
+    if (M > 0) k_sorted_keys_out<<<cdiv(M, 256), 256, 0, st>>>(M, tile_keys, vals, depth_ptr, depth_stride, hi, lo);
     return cudaGetLastError();
 }
 

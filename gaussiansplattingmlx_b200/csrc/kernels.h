@@ -24,7 +24,7 @@ cudaError_t launch_project_bwd_api(cudaStream_t st, int N, const ViewParams& vp,
 cudaError_t launch_project_fused_fwd(cudaStream_t st, int N, const ViewParams& vp, const float* xyz, const float* f_dc,
                                      const float* f_rest, const float* scales_log, const float* rot_raw,
                                      const float* op_logit, float* rec, uint2* tile_rects, uint32_t* touched,
-                                     float* radii_out, uint8_t* vis_out);
+                                     uint32_t* depth_keys, float* radii_out, uint8_t* vis_out);
 size_t project_fused_smem_bytes(int K);
 cudaError_t launch_project_fused_bwd(cudaStream_t st, int N, const ViewParams& vp, const float* xyz, const float* f_dc,
                                      const float* f_rest, const float* scales_log, const float* rot_raw,
@@ -32,19 +32,26 @@ cudaError_t launch_project_fused_bwd(cudaStream_t st, int N, const ViewParams& v
                                      float* g_f_rest, float* g_scales, float* g_rot, float* g_op, int accumulate);
 
 // ---- binning.cu --------------------------------------------------------------------------------
-// Tile rectangles + counts from reference-layout rect/radii (K3).
+// Tile rectangles + counts + depth sort keys from reference-layout rect/radii/depths (K3).
 cudaError_t launch_count_tiles(cudaStream_t st, int N, const ViewParams& vp, const float* rectMin, const float* rectMax,
-                               const float* radii, uint2* tile_rects, uint32_t* touched);
-// Exclusive scan of touched[N] → offsets[N]; *total (device) = M.  scan_ws: >= scan_ws_bytes(N).
+                               const float* radii, const float* depths, uint2* tile_rects, uint32_t* touched,
+                               uint32_t* depth_keys);
+// Exclusive scan of in[perm[i]] (perm = perm_sel && *perm_sel ? perm1 : perm0; NULL perm0 = identity)
+// → offsets[N]; *total (device) = M.  scan_ws: >= scan_ws_bytes(N).
 size_t scan_ws_bytes(int N);
-cudaError_t launch_exclusive_scan(cudaStream_t st, int N, const uint32_t* touched, uint32_t* offsets, uint32_t* total,
-                                  void* scan_ws);
-// K4: emit 64-bit keys (tile << 32 | depth bits) and gaussian indices; depth read at depth_ptr[i*depth_stride].
+cudaError_t launch_exclusive_scan(cudaStream_t st, int N, const uint32_t* in, const uint32_t* perm0, const uint32_t* perm1,
+                                  const uint32_t* perm_sel, uint32_t* offsets, uint32_t* total, void* scan_ws);
+// K4 in depth order: tile-id keys + Gaussian indices, one thread per output pair (coalesced).
 cudaError_t launch_generate_keys(cudaStream_t st, int N, const ViewParams& vp, const uint2* tile_rects,
-                                 const uint32_t* offsets, const float* depth_ptr, int depth_stride, uint64_t* keys,
-                                 uint32_t* vals, uint32_t capacity, const uint32_t* total, uint32_t* overflow_flag);
+                                 const uint32_t* offsets, const uint32_t* perm0, const uint32_t* perm1,
+                                 const uint32_t* perm_sel, uint32_t* keys, uint32_t* vals, uint32_t capacity,
+                                 const uint32_t* total, uint32_t* overflow_flag);
+// K4 in the reference's emission order with 64-bit (tile << 32 | depth bits) keys (parity API only).
+cudaError_t launch_generate_keys_ref(cudaStream_t st, int N, const ViewParams& vp, const uint2* tile_rects,
+                                     const uint32_t* offsets, const float* depth_ptr, int depth_stride, uint64_t* keys,
+                                     uint32_t* vals, uint32_t capacity);
 
-// Onesweep LSD radix sort of (u64 key, u32 value) over key bits [0, end_bit).
+// Onesweep LSD radix sort of (key, u32 value) pairs over key bits [0, end_bit).
 struct SortPlan {
     uint32_t capacity = 0;      // max number of pairs
     uint32_t max_tiles = 0;
@@ -53,20 +60,26 @@ struct SortPlan {
     size_t ws_bytes = 0;        // workspace: histograms, look-back state, counters, control block
 };
 SortPlan sort_plan(uint32_t capacity, uint32_t end_bit);
-// keys/vals double buffers [2]; count read from device *d_count (clamped to capacity).  On return the
-// sorted data sits in buffer index *d_result_buf (device u32, inside the workspace control block,
-// pointer returned via result_buf_ptr).
+// keys/vals double buffers; count read from device *d_count (clamped to capacity).  On return the
+// sorted data sits in buffer index *d_result_buf (device u32 inside the workspace control block,
+// pointer returned via result_buf_ptr).  sort32: iota != 0 synthesises the payload (= element index).
 cudaError_t launch_onesweep_sort(cudaStream_t st, const SortPlan& plan, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0,
                                  uint32_t* vals1, const uint32_t* d_count, void* ws, const uint32_t** result_buf_ptr,
                                  int* launches);
-// CUB baseline (checked against, never the product path unless GSB_FLAG_SORT_CUB): sorts count pairs
+cudaError_t launch_onesweep_sort32(cudaStream_t st, const SortPlan& plan, uint32_t* keys0, uint32_t* keys1, uint32_t* vals0,
+                                   uint32_t* vals1, int iota, const uint32_t* d_count, void* ws,
+                                   const uint32_t** result_buf_ptr, int* launches);
+// CUB baselines (checked against, never the product path unless GSB_FLAG_SORT_CUB): sort count pairs
 // (host-known) from keys0/vals0 into keys1/vals1.
 cudaError_t cub_sort_pairs(cudaStream_t st, uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1,
                            uint32_t count, uint32_t end_bit, void* tmp, size_t tmp_bytes, size_t* tmp_needed);
+cudaError_t cub_sort_pairs32(cudaStream_t st, uint32_t* keys0, uint32_t* keys1, uint32_t* vals0, uint32_t* vals1,
+                             uint32_t count, uint32_t end_bit, void* tmp, size_t tmp_bytes, size_t* tmp_needed);
+cudaError_t launch_iota(cudaStream_t st, uint32_t n, uint32_t* v);
 
-// K6/K7 + record gather: tile ranges/counts from the sorted keys, and the depth-ordered contiguous
-// record stream staged[j] = rec[sorted_val[j]] that the rasteriser bulk-copies.
-cudaError_t launch_ranges_gather(cudaStream_t st, const ViewParams& vp, const uint64_t* keys0, const uint64_t* keys1,
+// K6/K7 + record gather: tile ranges/counts from the sorted tile ids, and the depth-ordered contiguous
+// record stream staged[j] = rec[sorted_val[j]] that the rasteriser bulk-copies (rec == NULL: ranges only).
+cudaError_t launch_ranges_gather(cudaStream_t st, const ViewParams& vp, const uint32_t* keys0, const uint32_t* keys1,
                                  const uint32_t* vals0, const uint32_t* vals1, const uint32_t* d_result_buf,
                                  const uint32_t* d_count, uint32_t capacity, const float* rec, uint32_t* tile_ranges,
                                  float* staged, int numTiles);
@@ -80,6 +93,8 @@ cudaError_t launch_rec_to_packed(cudaStream_t st, int N, const float* rec, float
 cudaError_t launch_split_keys(cudaStream_t st, uint32_t M, const uint64_t* keys, uint32_t* hi, uint32_t* lo);
 cudaError_t launch_merge_keys(cudaStream_t st, uint32_t M, const uint32_t* hi, const uint32_t* lo, uint32_t hi_mask,
                               uint64_t* keys);
+cudaError_t launch_sorted_keys_out(cudaStream_t st, uint32_t M, const uint32_t* tile_keys, const uint32_t* vals,
+                                   const float* depth_ptr, int depth_stride, uint32_t* hi, uint32_t* lo);
 
 // ---- raster.cu ---------------------------------------------------------------------------------
 cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,

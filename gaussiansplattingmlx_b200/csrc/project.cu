@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(PB) k_project_fused_fwd(int N, const float* __
                                                           const float* __restrict__ op_logit,
                                                           const __grid_constant__ ViewParams vp, int tma_ok,
                                                           float* __restrict__ rec, uint2* __restrict__ tile_rects,
-                                                          uint32_t* __restrict__ touched, float* __restrict__ radii_out,
+                                                          uint32_t* __restrict__ touched, uint32_t* __restrict__ depth_keys,
+                                                          float* __restrict__ radii_out,
                                                           uint8_t* __restrict__ vis_out)
 {
     extern __shared__ __align__(128) float sm[];
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(PB) k_project_fused_fwd(int N, const float* __
         if (cnt == 0) { x0 = y0 = x1 = y1 = 0; }
         tile_rects[p] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
         touched[p] = cnt;
+        depth_keys[p] = cnt ? __float_as_uint(o.depth) : 0xffffffffu;   // Gaussians without tiles sort last
         if (radii_out) radii_out[p] = o.radius;
         if (vis_out) vis_out[p] = o.radius > 0.0f ? 1 : 0;
     }
@@ -385,7 +387,7 @@ size_t project_fused_smem_bytes(int K) { return (size_t)fused_layout(K).total * 
 cudaError_t launch_project_fused_fwd(cudaStream_t st, int N, const ViewParams& vp, const float* xyz, const float* f_dc,
                                      const float* f_rest, const float* scales_log, const float* rot_raw,
                                      const float* op_logit, float* rec, uint2* tile_rects, uint32_t* touched,
-                                     float* radii_out, uint8_t* vis_out)
+                                     uint32_t* depth_keys, float* radii_out, uint8_t* vis_out)
 {
     if (N <= 0) return cudaSuccess;
     int tma_ok = aligned16(xyz) && aligned16(f_dc) && aligned16(f_rest) && aligned16(scales_log) && aligned16(rot_raw) &&
@@ -395,11 +397,11 @@ cudaError_t launch_project_fused_fwd(cudaStream_t st, int N, const ViewParams& v
     if (vp.coeffCount > 16 || vp.K > 16) {
         e = cudaFuncSetAttribute(k_project_fused_fwd<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k_project_fused_fwd<25><<<cdiv(N, PB), PB, smem, st>>>(N, xyz, f_dc, f_rest, scales_log, rot_raw, op_logit, vp, tma_ok, rec, tile_rects, touched, radii_out, vis_out);
+        k_project_fused_fwd<25><<<cdiv(N, PB), PB, smem, st>>>(N, xyz, f_dc, f_rest, scales_log, rot_raw, op_logit, vp, tma_ok, rec, tile_rects, touched, depth_keys, radii_out, vis_out);
     } else {
         e = cudaFuncSetAttribute(k_project_fused_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k_project_fused_fwd<16><<<cdiv(N, PB), PB, smem, st>>>(N, xyz, f_dc, f_rest, scales_log, rot_raw, op_logit, vp, tma_ok, rec, tile_rects, touched, radii_out, vis_out);
+        k_project_fused_fwd<16><<<cdiv(N, PB), PB, smem, st>>>(N, xyz, f_dc, f_rest, scales_log, rot_raw, op_logit, vp, tma_ok, rec, tile_rects, touched, depth_keys, radii_out, vis_out);
     }
     return cudaGetLastError();
 }

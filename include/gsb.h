@@ -218,7 +218,7 @@ typedef struct gsb_stats {
 } gsb_stats;
 enum { GSB_STAGE_PROJECT_FWD = 0, GSB_STAGE_SCAN, GSB_STAGE_KEYGEN, GSB_STAGE_SORT, GSB_STAGE_RANGES_GATHER,
        GSB_STAGE_RASTER_FWD, GSB_STAGE_LOSS, GSB_STAGE_RASTER_BWD, GSB_STAGE_PROJECT_BWD, GSB_STAGE_ADAM,
-       GSB_STAGE_H2D, GSB_STAGE_COUNT };
+       GSB_STAGE_H2D, GSB_STAGE_DEPTH_SORT, GSB_STAGE_COUNT };
 /* Sum of lastContrib over the image of the last gsb_render_forward = number of (pixel, Gaussian)
  * blend evaluations E of that view (the unit of the raster rooflines).  Synchronises. */
 GSB_API int gsb_last_contrib_sum(gsb_ctx*, uint64_t* host_out);
