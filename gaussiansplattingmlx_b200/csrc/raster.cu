@@ -187,6 +187,7 @@ __device__ __forceinline__ float warp_reduce12(float (&v)[12], int lane)
     return v[0];
 }
 
+template <bool DEPTH>
 __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ ViewParams vp,
                                                        const uint32_t* __restrict__ tile_ranges,
                                                        const uint32_t* __restrict__ tile_order,
@@ -274,22 +275,20 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
             const uint32_t addr = stage_addr + (uint32_t)j * 48u;
             const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
             const float dx = pxf - a.x, dyb = pyf - a.y;
-            const float A2 = a.z + a.z, C2 = q.x + q.x;
-            const float Bdx = a.w * dx;
-            const float Adx = a.z * dx;
-            float g[12];
-#pragma unroll
-            for (int k = 0; k < 12; ++k) g[k] = 0.0f;
+            // The thread's 8 pixels share dx and have dy = dyb + p, so the exponent is a quadratic in the
+            // compile-time row offset p:  e(p) = E0 + p*E1 + p^2*C  (log2 units, opacity not included)
+            const float E0 = fmaf(dx, fmaf(a.z, dx, a.w * dyb), q.x * dyb * dyb);
+            const float E1 = fmaf(a.w, dx, 2.0f * q.x * dyb);
+            // per-thread partial sums over the 8 pixels: colour/depth terms and the moments of
+            // h = dL/d(opacity-free alpha) in the row offset: H0 = sum h, H1 = sum p h, H2 = sum p^2 h
+            float Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f, H0 = 0.f, H1 = 0.f, H2 = 0.f;
             // one pixel of this thread.  MASKED = false when every pixel of the block is known to be active.
             // Neither variant branches, so the compiler interleaves the 8 dependent chains; in the masked
             // variant an inactive pixel (i >= nContrib) computes and discards (selects keep its state).
             auto pixel = [&](int p, bool masked) {
                 const bool act = !masked || (i < nC[p]);
-                const float dy = dyb + (float)p;
-                // alpha (:437-483) in log2 units
-                const float t = fmaf(a.w, dy, Adx);
-                const float u = q.x * dy;
-                const float ex = ex2_approx(fmaf(u, dy, dx * t));
+                const float pf = (float)p;
+                const float ex = ex2_approx(fmaf(pf, fmaf(pf, q.x, E1), E0));    // :437-483
                 const float raw = ex * c.y;
                 const bool keep = act && !(raw > 0.99f);   // the alpha clamp branch has zero gradient
                 const float alpha = fminf(raw, 0.99f);
@@ -299,26 +298,22 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
                 const float contrib = act ? prevT * alpha : 0.0f;
                 sT[p] = act ? prevT : sT[p];
                 // VJP of updateTileGlobalPixelState (:485-499)
-                const float dotc = fmaf(kD[p], c.z, fmaf(kZ[p], c.x, fmaf(kY[p], q.w, kX[p] * q.z)));
+                float dotc = fmaf(kZ[p], c.x, fmaf(kY[p], q.w, kX[p] * q.z));
+                if (DEPTH) dotc = fmaf(kD[p], c.z, dotc);
                 const float d = dotc - kT[p];
                 const float g_alpha = prevT * d;
                 kT[p] = act ? fmaf(alpha, d, kT[p]) : kT[p];
-                g[6] = fmaf(contrib, kX[p], g[6]);
-                g[7] = fmaf(contrib, kY[p], g[7]);
-                g[8] = fmaf(contrib, kZ[p], g[8]);
-                g[10] = fmaf(contrib, kD[p], g[10]);
-                // VJP of evaluateTileGlobalSample
-                const float h = keep ? g_alpha * ex : 0.0f;      // d/d opacity
-                g[9] += h;
-                const float gp = h * c.y;                        // d/d (natural exponent)
-                const float w = -0.5f * gp;
-                const float wdx = w * dx, wdy = w * dy;
-                g[2] = fmaf(wdx, dx, g[2]);
-                g[3] = fmaf(wdx, dy, g[3]);
-                g[5] = fmaf(wdy, dy, g[5]);
-                // d exponent / d mean = -(2a dx + b dy, 2c dy + b dx) with (a,b,c) = (A,B,C)/log2(e)
-                g[0] = fmaf(gp, fmaf(A2, dx, a.w * dy), g[0]);
-                g[1] = fmaf(gp, fmaf(C2, dy, Bdx), g[1]);
+                Cr = fmaf(contrib, kX[p], Cr);
+                Cg = fmaf(contrib, kY[p], Cg);
+                Cb = fmaf(contrib, kZ[p], Cb);
+                if (DEPTH) Cd = fmaf(contrib, kD[p], Cd);
+                // VJP of evaluateTileGlobalSample: everything geometric is a moment of h
+                const float h = keep ? g_alpha * ex : 0.0f;
+                H0 += h;
+                if (p > 0) {
+                    H1 = fmaf(h, pf, H1);
+                    H2 = fmaf(h, pf * pf, H2);
+                }
             };
             if (__all_sync(0xffffffffu, i < nmin)) {
 #pragma unroll
@@ -327,24 +322,36 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
 #pragma unroll
                 for (int p = 0; p < BPPT; ++p) pixel(p, true);
             }
-            g[0] *= -(1.0f / LOG2E_F);
-            g[1] *= -(1.0f / LOG2E_F);
-            g[4] = g[3];   // g_c10 == g_c01
+            // moments in (dx, dy) of this thread's pixels: sum h dy = dyb H0 + H1, sum h dy^2 = dyb^2 H0 + 2 dyb H1 + H2
+            const float Sy = fmaf(dyb, H0, H1);
+            const float Syy = fmaf(dyb, fmaf(dyb, H0, H1 + H1), H2);
+            const float Sx = dx * H0;
+            float g[12] = {Cr, Cg, Cb, Cd, H0, Sx, Sy, dx * Sx, dx * Sy, Syy, 0.0f, 0.0f};
             const float tot = warp_reduce12(g, lane);
             if (writer) s_out[j][comp] = tot;
         }
         __syncwarp();
-        // flush: one 16-byte vector reduction per (record, quad) with a non-zero sum
-        for (int it = lane; it < n * 3; it += 32) {
-            const int j = it / 3, qd = it - j * 3;
-            const float4 sum = *reinterpret_cast<const float4*>(&s_out[j][qd * 4]);
-            if (sum.x != 0.f || sum.y != 0.f || sum.z != 0.f || sum.w != 0.f) {
-                const uint32_t gi = __float_as_uint(lds128(stage_addr + (uint32_t)j * 48u + 32u).w);
-                float* dst = grad_rec + (size_t)gi * REC_FLOATS + qd * 4;
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(sum.x), "f"(sum.y), "f"(sum.z),
-                             "f"(sum.w)
-                             : "memory");
-            }
+        // flush: finish the per-Gaussian chain rule on the block sums and send one 16-byte vector
+        // reduction per quad to L2 (records that no pixel of this block reached are skipped)
+        for (int j = lane; j < n; j += 32) {
+            const float4 s0 = *reinterpret_cast<const float4*>(&s_out[j][0]);   // Cr Cg Cb Cd
+            const float4 s1 = *reinterpret_cast<const float4*>(&s_out[j][4]);   // S0 Sx Sy Sxx
+            const float4 s2 = *reinterpret_cast<const float4*>(&s_out[j][8]);   // Sxy Syy - -
+            const bool any = s0.x != 0.f || s0.y != 0.f || s0.z != 0.f || s0.w != 0.f || s1.x != 0.f || s1.y != 0.f ||
+                             s1.z != 0.f || s1.w != 0.f || s2.x != 0.f || s2.y != 0.f;
+            if (!any) continue;
+            const uint32_t addr = stage_addr + (uint32_t)j * 48u;
+            const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
+            const float op = c.y;
+            const float kc = -0.5f * op;                 // d(natural exponent)/d conic = -0.5 * (dx^2, dx dy, dy^2)
+            const float km = -op * (1.0f / LOG2E_F);     // d(natural exponent)/d mean = -(2a dx + b dy, ...), (a,b,c) = (A,B,C)/log2 e
+            const float g_mx = km * fmaf(a.z + a.z, s1.y, a.w * s1.z);
+            const float g_my = km * fmaf(q.x + q.x, s1.z, a.w * s1.y);
+            const float g_c00 = kc * s1.w, g_c01 = kc * s2.x, g_c11 = kc * s2.y;
+            float* dst = grad_rec + (size_t)__float_as_uint(c.w) * REC_FLOATS;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g_mx), "f"(g_my), "f"(g_c00), "f"(g_c01) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(g_c01), "f"(g_c11), "f"(s0.x), "f"(s0.y) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8), "f"(s0.z), "f"(s1.x), "f"(s0.w), "f"(0.0f) : "memory");
         }
     }
 }
@@ -397,11 +404,16 @@ cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint3
     if (blocks > 0) {
         static bool carveout_set = false;
         if (!carveout_set) {
-            cudaFuncSetAttribute(k_raster_bwd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_raster_bwd<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_raster_bwd<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             carveout_set = true;
         }
-        k_raster_bwd<<<blocks, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(staged), cot_color, cot_depth,
-                                            cot_alpha, out_alpha, last_contrib, grad_rec);
+        if (cot_depth)
+            k_raster_bwd<true><<<blocks, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(staged), cot_color,
+                                                      cot_depth, cot_alpha, out_alpha, last_contrib, grad_rec);
+        else
+            k_raster_bwd<false><<<blocks, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(staged), cot_color,
+                                                       cot_depth, cot_alpha, out_alpha, last_contrib, grad_rec);
     }
     return cudaGetLastError();
 }
