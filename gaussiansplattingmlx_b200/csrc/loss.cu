@@ -16,10 +16,8 @@
 
 namespace gsb {
 
-constexpr int ST = 16;            // tile edge in pixels
 constexpr int SPAD = 5;           // window radius (K/2)
 constexpr int SK = 11;
-constexpr int SH = ST + 2 * SPAD; // halo edge (26)
 constexpr float SSIM_C1 = 0.0001f, SSIM_C2 = 0.0009f;
 
 struct SsimWindow {
@@ -62,70 +60,100 @@ __device__ __forceinline__ SsimPoint ssim_point(float mu1, float mu2, float e11,
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward statistics for one 16x16xC tile: horizontal pass into s_h, vertical pass per thread.
+// Streaming separable convolution.  The HWC image is treated as H rows of W*C floats; a horizontal tap
+// k of the per-channel window sits at element offset (k - 5) * C.  A CTA owns a strip of SW consecutive
+// row elements and a chunk of SROWS output rows and marches down the rows: each input row is loaded once
+// into shared memory (strip + 5*C halo on both sides), filtered horizontally (11 taps) into a ring of
+// the last 11 filtered rows, and one output row is produced from the ring (11 vertical taps).  Compared
+// with 2-D tiles the halo overhead is 10 rows per SROWS-row chunk and 10*C floats per SW-float strip.
 // MODE 0: parity API (writes ssim + optional saved maps)
 // MODE 1: training (writes upstream-scaled A/B/C maps, accumulates sum|d| and sum(ssim))
 // ------------------------------------------------------------------------------------------------
+constexpr int SW = 192;        // strip width in floats = threads per CTA (1080p: 5760 = 30 strips)
+constexpr int SROWS = 60;      // output rows per CTA
+constexpr int SMAXC = 4;       // channels supported by the halo buffer
+constexpr int SHALO = SPAD * SMAXC;
+
 template <int MODE>
-__global__ void __launch_bounds__(256) k_ssim_fwd(int H, int W, int C, const float* __restrict__ img1,
-                                                  const float* __restrict__ img2, const __grid_constant__ SsimWindow win,
-                                                  float upstream, float* __restrict__ o0, float* __restrict__ o1,
-                                                  float* __restrict__ o2, float* __restrict__ o3, float* __restrict__ o4,
-                                                  float* __restrict__ o5, double* __restrict__ partial)
+__global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int C, const float* __restrict__ img1,
+                                                 const float* __restrict__ img2, const __grid_constant__ SsimWindow win,
+                                                 float upstream, float* __restrict__ o0, float* __restrict__ o1,
+                                                 float* __restrict__ o2, float* __restrict__ o3, float* __restrict__ o4,
+                                                 float* __restrict__ o5, double* __restrict__ partial)
 {
-    __shared__ float s_a[SH][SH + 1];
-    __shared__ float s_b[SH][SH + 1];
-    __shared__ float s_h[5][SH][ST + 1];
-    __shared__ double s_red[2][8];
-    const int tx0 = blockIdx.x * ST, ty0 = blockIdx.y * ST;
-    const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+    __shared__ float s_row[4][SW + 2 * SHALO];   // [parity][image]
+    __shared__ float s_ring[SK][5][SW];
+    __shared__ double s_red[2][SW / 32];
+    const int RW = W * C;                          // floats per image row
+    const int e0 = blockIdx.x * SW;                // first row element of the strip
+    const int r0 = blockIdx.y * SROWS, r1 = min(r0 + SROWS, H);
+    const int t = threadIdx.x;
+    const int e = e0 + t;
+    const int halo = SPAD * C;
     double accL1 = 0.0, accS = 0.0;
-    for (int c = 0; c < C; ++c) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < SH * SH; i += 256) {
-            const int hy = i / SH, hx = i - hy * SH;
-            const int y = ty0 + hy - SPAD, x = tx0 + hx - SPAD;
-            float a = 0.f, b = 0.f;
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-                const size_t si = ((size_t)y * W + x) * C + c;
-                a = img1[si];
-                b = img2[si];
+    // row r+1 is fetched into registers while row r is filtered (each thread owns elements t and t + SW of the
+    // haloed strip); zero outside the image
+    const int nload = SW + 2 * halo;
+    float pa[2], pb[2];
+    auto fetch = [&](int r) {
+        const bool row_ok = r >= 0 && r < H;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = t + u * SW;
+            const int ee = e0 - halo + i;
+            pa[u] = 0.f; pb[u] = 0.f;
+            if (row_ok && i < nload && ee >= 0 && ee < RW) {
+                const size_t si = (size_t)r * RW + ee;
+                pa[u] = img1[si];
+                pb[u] = img2[si];
             }
-            s_a[hy][hx] = a;
-            s_b[hy][hx] = b;
         }
-        __syncthreads();
-        // horizontal: SH rows x ST columns x 5 statistics
-        for (int i = threadIdx.x; i < SH * ST; i += 256) {
-            const int hy = i / ST, ox = i - hy * ST;
+    };
+    fetch(r0 - SPAD);
+    for (int r = r0 - SPAD; r < r1 + SPAD; ++r) {
+        float (*row)[SW + 2 * SHALO] = reinterpret_cast<float (*)[SW + 2 * SHALO]>(&s_row[(r & 1) * 2][0]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = t + u * SW;
+            if (i < nload) { row[0][i] = pa[u]; row[1][i] = pb[u]; }
+        }
+        __syncthreads();   // the only barrier per row: the two row buffers alternate
+        if (r + 1 < r1 + SPAD) fetch(r + 1);
+        // ---- horizontal 11 taps -> ring slot of row r
+        {
             float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
 #pragma unroll
             for (int k = 0; k < SK; ++k) {
                 const float w = win.g[k];
-                const float a = s_a[hy][ox + k], b = s_b[hy][ox + k];
-                m1 += w * a;
-                m2 += w * b;
-                e11 += w * (a * a);
-                e22 += w * (b * b);
-                e12 += w * (a * b);
+                const float a = row[0][t + k * C], b = row[1][t + k * C];
+                m1 = fmaf(w, a, m1);
+                m2 = fmaf(w, b, m2);
+                e11 = fmaf(w, a * a, e11);
+                e22 = fmaf(w, b * b, e22);
+                e12 = fmaf(w, a * b, e12);
             }
-            s_h[0][hy][ox] = m1; s_h[1][hy][ox] = m2; s_h[2][hy][ox] = e11; s_h[3][hy][ox] = e22; s_h[4][hy][ox] = e12;
+            const int slot = (r + SK) % SK;
+            s_ring[slot][0][t] = m1; s_ring[slot][1][t] = m2; s_ring[slot][2][t] = e11; s_ring[slot][3][t] = e22;
+            s_ring[slot][4][t] = e12;
         }
-        __syncthreads();
-        const int x = tx0 + lx, y = ty0 + ly;
-        if (x < W && y < H) {
+        // ---- vertical 11 taps -> output row ro = r - 5 (each thread reads only its own ring column)
+        const int ro = r - SPAD;
+        if (ro >= r0 && e < RW) {
             float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+            const int base = (ro - SPAD + 2 * SK) % SK;
 #pragma unroll
             for (int k = 0; k < SK; ++k) {
                 const float w = win.g[k];
-                m1 += w * s_h[0][ly + k][lx];
-                m2 += w * s_h[1][ly + k][lx];
-                e11 += w * s_h[2][ly + k][lx];
-                e22 += w * s_h[3][ly + k][lx];
-                e12 += w * s_h[4][ly + k][lx];
+                int slot = base + k;
+                if (slot >= SK) slot -= SK;
+                m1 = fmaf(w, s_ring[slot][0][t], m1);
+                m2 = fmaf(w, s_ring[slot][1][t], m2);
+                e11 = fmaf(w, s_ring[slot][2][t], e11);
+                e22 = fmaf(w, s_ring[slot][3][t], e22);
+                e12 = fmaf(w, s_ring[slot][4][t], e12);
             }
             const SsimPoint sp = ssim_point(m1, m2, e11, e22, e12);
-            const size_t idx = ((size_t)y * W + x) * C + c;
+            const size_t idx = (size_t)ro * RW + e;
             if (MODE == 0) {
                 o0[idx] = sp.ssim;
                 if (o1) o1[idx] = m1;
@@ -138,7 +166,7 @@ __global__ void __launch_bounds__(256) k_ssim_fwd(int H, int W, int C, const flo
                 o1[idx] = upstream * sp.gs1;
                 o2[idx] = upstream * sp.gs12;
                 accS += (double)sp.ssim;
-                accL1 += (double)fabsf(s_a[ly + SPAD][lx + SPAD] - s_b[ly + SPAD][lx + SPAD]);
+                accL1 += (double)fabsf(img1[idx] - img2[idx]);
             }
         }
     }
@@ -152,7 +180,7 @@ __global__ void __launch_bounds__(256) k_ssim_fwd(int H, int W, int C, const flo
         __syncthreads();
         if (threadIdx.x == 0 && partial) {
             double a = 0.0, b = 0.0;
-            for (int w = 0; w < 8; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
+            for (int w = 0; w < SW / 32; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
             atomicAdd(&partial[0], a);
             atomicAdd(&partial[1], b);
         }
@@ -160,65 +188,80 @@ __global__ void __launch_bounds__(256) k_ssim_fwd(int H, int W, int C, const flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: transposed separable convolution of the three maps, then the pointwise combination.
-// PRE = true : maps already hold upstream * (gm1, gs1, gs12)            (training path)
-// PRE = false: maps are computed here from (grad_out, img1, img2)        (parity API) — done by the
-//              launcher through k_ssim_fwd<1>-style statistics, see k_ssim_maps below.
+// backward: transposed (flipped-window) separable convolution of the three maps, then the pointwise
+// combination  grad1 = convT(A) + 2 v1 convT(B) + v2 convT(C)  [+ l1_scale * sign(v1 - v2)].
+// Pixel x receives from centre x - (k - 5) with weight g[k]  ->  tap k reads element offset (5 - k) * C.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ssim_bwd(int H, int W, int C, const float* __restrict__ img1,
-                                                  const float* __restrict__ img2, const float* __restrict__ mapA,
-                                                  const float* __restrict__ mapB, const float* __restrict__ mapC,
-                                                  const __grid_constant__ SsimWindow win, float l1_scale,
-                                                  float* __restrict__ grad1)
+__global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int C, const float* __restrict__ img1,
+                                                 const float* __restrict__ img2, const float* __restrict__ mapA,
+                                                 const float* __restrict__ mapB, const float* __restrict__ mapC,
+                                                 const __grid_constant__ SsimWindow win, float l1_scale,
+                                                 float* __restrict__ grad1)
 {
-    __shared__ float s_m[3][SH][SH + 1];
-    __shared__ float s_h[3][SH][ST + 1];
-    const int tx0 = blockIdx.x * ST, ty0 = blockIdx.y * ST;
-    const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
-    for (int c = 0; c < C; ++c) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < SH * SH; i += 256) {
-            const int hy = i / SH, hx = i - hy * SH;
-            const int y = ty0 + hy - SPAD, x = tx0 + hx - SPAD;
-            float a = 0.f, b = 0.f, cc = 0.f;
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-                const size_t si = ((size_t)y * W + x) * C + c;
-                a = mapA[si];
-                b = mapB[si];
-                cc = mapC[si];
+    __shared__ float s_row[6][SW + 2 * SHALO];   // [parity][map]
+    __shared__ float s_ring[SK][3][SW];
+    const int RW = W * C;
+    const int e0 = blockIdx.x * SW;
+    const int r0 = blockIdx.y * SROWS, r1 = min(r0 + SROWS, H);
+    const int t = threadIdx.x;
+    const int e = e0 + t;
+    const int halo = SPAD * C;
+    const int nload = SW + 2 * halo;
+    float pa[2], pb[2], pc[2];
+    auto fetch = [&](int r) {
+        const bool row_ok = r >= 0 && r < H;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = t + u * SW;
+            const int ee = e0 - halo + i;
+            pa[u] = 0.f; pb[u] = 0.f; pc[u] = 0.f;
+            if (row_ok && i < nload && ee >= 0 && ee < RW) {
+                const size_t si = (size_t)r * RW + ee;
+                pa[u] = mapA[si];
+                pb[u] = mapB[si];
+                pc[u] = mapC[si];
             }
-            s_m[0][hy][hx] = a; s_m[1][hy][hx] = b; s_m[2][hy][hx] = cc;
+        }
+    };
+    fetch(r0 - SPAD);
+    for (int r = r0 - SPAD; r < r1 + SPAD; ++r) {
+        float (*row)[SW + 2 * SHALO] = reinterpret_cast<float (*)[SW + 2 * SHALO]>(&s_row[(r & 1) * 3][0]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = t + u * SW;
+            if (i < nload) { row[0][i] = pa[u]; row[1][i] = pb[u]; row[2][i] = pc[u]; }
         }
         __syncthreads();
-        // pixel x receives from centre cx = x - k + pad with weight g[k]: halo column (ox + 2*pad - k)
-        for (int i = threadIdx.x; i < SH * ST; i += 256) {
-            const int hy = i / ST, ox = i - hy * ST;
-            float a = 0.f, b = 0.f, cc = 0.f;
+        if (r + 1 < r1 + SPAD) fetch(r + 1);
+        {
+            float a = 0.f, b = 0.f, c = 0.f;
 #pragma unroll
             for (int k = 0; k < SK; ++k) {
                 const float w = win.g[k];
-                const int hx = ox + 2 * SPAD - k;
-                a += w * s_m[0][hy][hx];
-                b += w * s_m[1][hy][hx];
-                cc += w * s_m[2][hy][hx];
+                const int off = t + (2 * SPAD - k) * C;
+                a = fmaf(w, row[0][off], a);
+                b = fmaf(w, row[1][off], b);
+                c = fmaf(w, row[2][off], c);
             }
-            s_h[0][hy][ox] = a; s_h[1][hy][ox] = b; s_h[2][hy][ox] = cc;
+            const int slot = (r + SK) % SK;
+            s_ring[slot][0][t] = a; s_ring[slot][1][t] = b; s_ring[slot][2][t] = c;
         }
-        __syncthreads();
-        const int x = tx0 + lx, y = ty0 + ly;
-        if (x < W && y < H) {
-            float a = 0.f, b = 0.f, cc = 0.f;
+        const int ro = r - SPAD;
+        if (ro >= r0 && e < RW) {
+            float a = 0.f, b = 0.f, c = 0.f;
+            const int base = (ro + SPAD + SK) % SK;
 #pragma unroll
             for (int k = 0; k < SK; ++k) {
                 const float w = win.g[k];
-                const int hy = ly + 2 * SPAD - k;
-                a += w * s_h[0][hy][lx];
-                b += w * s_h[1][hy][lx];
-                cc += w * s_h[2][hy][lx];
+                int slot = base - k;
+                if (slot < 0) slot += SK;
+                a = fmaf(w, s_ring[slot][0][t], a);
+                b = fmaf(w, s_ring[slot][1][t], b);
+                c = fmaf(w, s_ring[slot][2][t], c);
             }
-            const size_t idx = ((size_t)y * W + x) * C + c;
+            const size_t idx = (size_t)ro * RW + e;
             const float v1 = img1[idx], v2 = img2[idx];
-            float g = a + 2.0f * v1 * b + v2 * cc;
+            float g = a + 2.0f * v1 * b + v2 * c;
             if (l1_scale != 0.0f) {
                 const float d = v1 - v2;
                 g += d > 0.0f ? l1_scale : (d < 0.0f ? -l1_scale : 0.0f);
@@ -261,8 +304,8 @@ cudaError_t launch_ssim_fwd(cudaStream_t st, int H, int W, int C, const float* i
                             float* mu1, float* mu2, float* s1, float* s2, float* s12)
 {
     if (H <= 0 || W <= 0 || C <= 0) return cudaSuccess;
-    dim3 grid(cdiv(W, ST), cdiv(H, ST));
-    k_ssim_fwd<0><<<grid, 256, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, ssim_map, mu1, mu2, s1, s2, s12, nullptr);
+    dim3 grid(cdiv((long long)W * C, SW), cdiv(H, SROWS));
+    k_ssim_fwd<0><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, ssim_map, mu1, mu2, s1, s2, s12, nullptr);
     return cudaGetLastError();
 }
 
@@ -272,8 +315,8 @@ cudaError_t launch_loss_fwd(cudaStream_t st, int H, int W, int C, const float* r
     cudaError_t e = cudaMemsetAsync(partial, 0, 2 * sizeof(double), st);
     if (e != cudaSuccess) return e;
     if (H <= 0 || W <= 0 || C <= 0) return cudaSuccess;
-    dim3 grid(cdiv(W, ST), cdiv(H, ST));
-    k_ssim_fwd<1><<<grid, 256, 0, st>>>(H, W, C, render, target, window(), upstream, mapA, mapB, mapC, nullptr, nullptr,
+    dim3 grid(cdiv((long long)W * C, SW), cdiv(H, SROWS));
+    k_ssim_fwd<1><<<grid, SW, 0, st>>>(H, W, C, render, target, window(), upstream, mapA, mapB, mapC, nullptr, nullptr,
                                         nullptr, partial);
     return cudaGetLastError();
 }
@@ -282,8 +325,8 @@ cudaError_t launch_loss_bwd(cudaStream_t st, int H, int W, int C, const float* r
                             const float* mapA, const float* mapB, const float* mapC, float l1_scale, float* cot_render)
 {
     if (H <= 0 || W <= 0 || C <= 0) return cudaSuccess;
-    dim3 grid(cdiv(W, ST), cdiv(H, ST));
-    k_ssim_bwd<<<grid, 256, 0, st>>>(H, W, C, render, target, mapA, mapB, mapC, window(), l1_scale, cot_render);
+    dim3 grid(cdiv((long long)W * C, SW), cdiv(H, SROWS));
+    k_ssim_bwd<<<grid, SW, 0, st>>>(H, W, C, render, target, mapA, mapB, mapC, window(), l1_scale, cot_render);
     return cudaGetLastError();
 }
 
@@ -298,13 +341,13 @@ cudaError_t launch_ssim_bwd_api(cudaStream_t st, int H, int W, int C, const floa
                                 const float* img2, float* mapA, float* mapB, float* mapC, float* grad_img1)
 {
     if (H <= 0 || W <= 0 || C <= 0) return cudaSuccess;
-    dim3 grid(cdiv(W, ST), cdiv(H, ST));
+    dim3 grid(cdiv((long long)W * C, SW), cdiv(H, SROWS));
     // maps with unit upstream, then scaled by the caller's per-centre gradient
-    k_ssim_fwd<1><<<grid, 256, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, mapA, mapB, mapC, nullptr, nullptr, nullptr,
+    k_ssim_fwd<1><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, mapA, mapB, mapC, nullptr, nullptr, nullptr,
                                         nullptr);
     const size_t n = (size_t)H * W * C;
     k_scale_maps<<<cdiv((long long)n, 256), 256, 0, st>>>(n, grad_out, mapA, mapB, mapC);
-    k_ssim_bwd<<<grid, 256, 0, st>>>(H, W, C, img1, img2, mapA, mapB, mapC, window(), 0.0f, grad_img1);
+    k_ssim_bwd<<<grid, SW, 0, st>>>(H, W, C, img1, img2, mapA, mapB, mapC, window(), 0.0f, grad_img1);
     return cudaGetLastError();
 }
 
