@@ -261,7 +261,6 @@ static int ensure_pairs(Ctx* c, uint64_t M)
         GSB_CUDA_CHECK(c, dev_alloc(&c->keys[i], (size_t)cap));
         GSB_CUDA_CHECK(c, dev_alloc(&c->vals[i], (size_t)cap));
     }
-    GSB_CUDA_CHECK(c, dev_alloc(&c->staged, (size_t)cap * REC_FLOATS));
     c->plan = sort_plan((uint32_t)cap, (uint32_t)c->tileBits);
     GSB_CUDA_CHECK(c, cudaMalloc(&c->sort_ws, c->plan.ws_bytes));
     c->capM = (uint32_t)cap;
@@ -352,8 +351,9 @@ static int run_binning(Ctx* c, int N, const ViewParams& vp, const float* depth_p
         {
             StageTimer t(c, GSB_STAGE_RANGES_GATHER);
             GSB_CUDA_CHECK(c, launch_ranges_gather(c->stream, vp, c->keys[0], c->keys[1], c->vals[0], c->vals[1],
-                                                   c->d_result_buf, &c->d_ctl[0], c->capM, rec, c->tile_ranges, c->staged,
+                                                   c->d_result_buf, &c->d_ctl[0], c->capM, nullptr, c->tile_ranges, nullptr,
                                                    c->numTiles));
+            (void)rec;
             GSB_CUDA_CHECK(c, launch_tile_order(c->stream, c->numTiles, c->tile_ranges, c->tile_order));
             launches += 2;
         }
@@ -762,11 +762,7 @@ static int restage_packed(Ctx* c, int32_t N, const float* packed)
     if (!c->bin_valid && !c->saved.valid) { gsb::set_error(c, "raster: call gsb_bin (or gsb_render_forward) first"); return GSB_ERR_STATE; }
     if (N > c->capN) { gsb::set_error(c, "raster: N larger than the binned scene"); return GSB_ERR_INVALID; }
     GSB_CUDA_CHECK(c, gsb::launch_packed_to_rec(c->stream, N, packed, c->rec));
-    GSB_CUDA_CHECK(c, gsb::launch_ranges_gather(c->stream, c->bin_vp, c->keys[0], c->keys[1], c->vals[0], c->vals[1],
-                                                c->d_result_buf, &c->d_ctl[0], c->capM, c->rec, c->tile_ranges, c->staged,
-                                                c->numTiles));
-    GSB_CUDA_CHECK(c, gsb::launch_tile_order(c->stream, c->numTiles, c->tile_ranges, c->tile_order));
-    c->stats.kernel_launches += 3;
+    c->stats.kernel_launches += 1;
     return GSB_OK;
 }
 
@@ -779,7 +775,7 @@ int gsb_raster_fwd(gsb_ctx* ctx, int32_t N, const float* packed, float* out_colo
     int rc = restage_packed(c, N, packed);
     if (rc != GSB_OK) return rc;
     gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
-    GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, c->bin_vp, c->tile_ranges, c->tile_order, c->staged, out_color, out_depth, out_alpha,
+    GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, c->bin_vp, c->tile_ranges, c->tile_order, c->rec, c->vals[0], c->vals[1], c->d_result_buf, out_color, out_depth, out_alpha,
                                              out_last_contrib));
     c->stats.kernel_launches += 1;
     return GSB_OK;
@@ -798,7 +794,7 @@ int gsb_raster_bwd(gsb_ctx* ctx, int32_t N, const float* packed, const float* co
     GSB_CUDA_CHECK(c, cudaMemsetAsync(c->grad_rec, 0, (size_t)N * gsb::REC_FLOATS * 4, c->stream));
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, c->bin_vp, c->tile_ranges, c->tile_order, c->staged, cot_color, cot_depth, cot_alpha,
+        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, c->bin_vp, c->tile_ranges, c->tile_order, c->rec, c->vals[0], c->vals[1], c->d_result_buf, cot_color, cot_depth, cot_alpha,
                                                  out_color, out_depth, out_alpha, last_contrib, c->grad_rec));
     }
     GSB_CUDA_CHECK(c, gsb::launch_rec_to_packed(c->stream, N, c->grad_rec, grad_packed));
@@ -855,7 +851,7 @@ static int render_forward_impl(Ctx* c, int32_t N, const float* xyz, const float*
     if (rc != GSB_OK) return rc;
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, vp, c->tile_ranges, c->tile_order, c->staged, c->out_color, c->out_depth,
+        GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, vp, c->tile_ranges, c->tile_order, c->rec, c->vals[0], c->vals[1], c->d_result_buf, c->out_color, c->out_depth,
                                                  c->out_alpha, c->out_last));
         c->stats.kernel_launches += 1;
     }
@@ -881,7 +877,7 @@ static int render_backward_impl(Ctx* c, const float* cot_render, const float* co
     GSB_CUDA_CHECK(c, cudaMemsetAsync(c->grad_rec, 0, (size_t)N * gsb::REC_FLOATS * 4, c->stream));
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, vp, c->tile_ranges, c->tile_order, c->staged, cot_render, cot_depth, cot_alpha,
+        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, vp, c->tile_ranges, c->tile_order, c->rec, c->vals[0], c->vals[1], c->d_result_buf, cot_render, cot_depth, cot_alpha,
                                                  c->out_color, c->out_depth, c->out_alpha, c->out_last, c->grad_rec));
     }
     {

@@ -625,11 +625,11 @@ __global__ void __launch_bounds__(256) k_ranges_gather(const uint32_t* __restric
     const uint32_t buf = d_result_buf ? *d_result_buf : 0u;
     const uint32_t* keys = buf ? keys1 : keys0;
     const uint32_t* vals = buf ? vals1 : vals0;
-    const uint64_t total = (uint64_t)M * 3u;
+    const uint32_t per = rec ? 3u : 1u;   // threads per pair (3 x 16 bytes when the records are gathered too)
+    const uint64_t total = (uint64_t)M * per;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t j = (uint32_t)(g / 3u), part = (uint32_t)(g - (uint64_t)j * 3u);
-        uint32_t gi = vals[j];
-        if (rec) staged[(size_t)j * 3 + part] = rec[(size_t)gi * 3 + part];
+        uint32_t j = (uint32_t)(g / per), part = (uint32_t)(g - (uint64_t)j * per);
+        if (rec) staged[(size_t)j * 3 + part] = rec[(size_t)vals[j] * 3 + part];
         if (part == 0) {
             uint32_t cur = keys[j];
             if (j == 0) {

@@ -97,11 +97,14 @@ cudaError_t launch_sorted_keys_out(cudaStream_t st, uint32_t M, const uint32_t* 
                                    const float* depth_ptr, int depth_stride, uint32_t* hi, uint32_t* lo);
 
 // ---- raster.cu ---------------------------------------------------------------------------------
+// rec = record table [N,12]; (vals0|vals1 selected by *d_result_buf) = Gaussian indices in (tile, depth) order
 cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
-                              const uint32_t* tile_order, const float* staged,
+                              const uint32_t* tile_order, const float* rec, const uint32_t* vals0, const uint32_t* vals1,
+                              const uint32_t* d_result_buf,
                               float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last);
 cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
-                              const uint32_t* tile_order, const float* staged,
+                              const uint32_t* tile_order, const float* rec, const uint32_t* vals0, const uint32_t* vals1,
+                              const uint32_t* d_result_buf,
                               const float* cot_color, const float* cot_depth, const float* cot_alpha,
                               const float* out_color, const float* out_depth, const float* out_alpha,
                               const uint32_t* last_contrib, float* grad_rec);

@@ -29,6 +29,11 @@ constexpr int RT = 256;          // forward: threads per CTA = 16x16 pixels
 constexpr int RB_FWD = 128;      // records per forward batch (6 KB)
 constexpr int RB_BWD = 64;       // records per backward batch
 constexpr int BPPT = 8;          // backward: pixels per thread (rows)
+// Gather staging engine for the 48-byte records: 1 = one TMA bulk copy per record (cp.async.bulk, UBLKCP),
+// 0 = three 16-byte cp.async (LDGSTS) per record.  Both complete on the batch's mbarrier.
+#ifndef GSB_GATHER_TMA
+#define GSB_GATHER_TMA 0
+#endif
 
 // (tile, 16x16 sub-block) of this CTA; tiles larger than 16x16 are covered by several CTAs
 struct BlockMap {
@@ -57,7 +62,9 @@ __device__ __forceinline__ BlockMap map_block(const ViewParams& vp, const uint32
 __global__ void __launch_bounds__(RT) k_raster_fwd(const __grid_constant__ ViewParams vp,
                                                    const uint32_t* __restrict__ tile_ranges,
                                                    const uint32_t* __restrict__ tile_order,
-                                                   const float4* __restrict__ staged, float* __restrict__ out_color,
+                                                   const float4* __restrict__ rec, const uint32_t* __restrict__ vals0,
+                                                   const uint32_t* __restrict__ vals1,
+                                                   const uint32_t* __restrict__ d_result_buf, float* __restrict__ out_color,
                                                    float* __restrict__ out_depth, float* __restrict__ out_alpha,
                                                    uint32_t* __restrict__ out_last)
 {
@@ -71,18 +78,42 @@ __global__ void __launch_bounds__(RT) k_raster_fwd(const __grid_constant__ ViewP
     const int nb = (int)((count + RB_FWD - 1) / RB_FWD);
 
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar[0], GSB_GATHER_TMA ? 1 : RB_FWD);
+        mbar_init(&s_bar[1], GSB_GATHER_TMA ? 1 : RB_FWD);
         mbar_fence_init();
     }
     __syncthreads();
-    auto issue = [&](int b) {
-        const uint32_t n = min((uint32_t)RB_FWD, count - (uint32_t)b * RB_FWD);
-        uint64_t* bar = &s_bar[b & 1];
-        mbar_expect_tx(bar, n * 48u);
-        bulk_g2s(&s_rec[b & 1][0], staged + ((size_t)start + (size_t)b * RB_FWD) * 3, n * 48u, bar);
+    // Gather staging: the tile's list is (tile_ranges, sorted Gaussian indices); threads 0..RB_FWD-1 each pull
+    // ONE 48-byte record of the next batch from the (L2-resident) record table straight into shared memory with
+    // a TMA bulk copy; all copies of a batch complete on one mbarrier.  Indices are prefetched two batches ahead.
+    const uint32_t* __restrict__ vals = (*d_result_buf) ? vals1 : vals0;
+    auto load_idx = [&](int b) -> uint32_t {
+        const uint32_t j = (uint32_t)b * RB_FWD + threadIdx.x;
+        return (threadIdx.x < RB_FWD && b < nb && j < count) ? vals[start + j] : 0xffffffffu;
     };
-    if (threadIdx.x == 0 && nb > 0) issue(0);
+    auto issue = [&](int b, uint32_t idx) {
+        uint64_t* bar = &s_bar[b & 1];
+#if GSB_GATHER_TMA
+        if (threadIdx.x == 0) mbar_expect_tx(bar, min((uint32_t)RB_FWD, count - (uint32_t)b * RB_FWD) * 48u);
+        if (idx != 0xffffffffu) bulk_g2s(&s_rec[b & 1][threadIdx.x * 3], rec + (size_t)idx * 3, 48u, bar);
+#else
+        if (threadIdx.x < RB_FWD) {
+            if (idx != 0xffffffffu) {
+                float4* dst = &s_rec[b & 1][threadIdx.x * 3];
+                const float4* src = rec + (size_t)idx * 3;
+                cp_async16(dst, src);
+                cp_async16(dst + 1, src + 1);
+                cp_async16(dst + 2, src + 2);
+                cp_async_mbar_arrive_noinc(bar);
+            } else {
+                mbar_arrive(bar);
+            }
+        }
+#endif
+    };
+    uint32_t idx_next = load_idx(0);
+    if (nb > 0) issue(0, idx_next);
+    idx_next = load_idx(1);
 
     const float px = (float)pxi, py = (float)pyi;
     float cx = 0.f, cy = 0.f, cz = 0.f, dep = 0.f;
@@ -114,7 +145,8 @@ __global__ void __launch_bounds__(RT) k_raster_fwd(const __grid_constant__ ViewP
     };
 
     for (int b = 0; b < nb; ++b) {
-        if (threadIdx.x == 0 && b + 1 < nb) issue(b + 1);
+        if (b + 1 < nb) issue(b + 1, idx_next);
+        idx_next = load_idx(b + 2);
         mbar_wait(&s_bar[b & 1], (uint32_t)(b >> 1) & 1u);
         const int n = (int)min((uint32_t)RB_FWD, count - (uint32_t)b * RB_FWD);
         if (!__all_sync(0xffffffffu, T == 0.0f)) {
@@ -191,7 +223,10 @@ template <bool DEPTH>
 __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ ViewParams vp,
                                                        const uint32_t* __restrict__ tile_ranges,
                                                        const uint32_t* __restrict__ tile_order,
-                                                       const float4* __restrict__ staged, const float* __restrict__ cot_color,
+                                                       const float4* __restrict__ rec, const uint32_t* __restrict__ vals0,
+                                                       const uint32_t* __restrict__ vals1,
+                                                       const uint32_t* __restrict__ d_result_buf,
+                                                       const float* __restrict__ cot_color,
                                                        const float* __restrict__ cot_depth, const float* __restrict__ cot_alpha,
                                                        const float* __restrict__ out_alpha,
                                                        const uint32_t* __restrict__ last_contrib, float* __restrict__ grad_rec)
@@ -235,21 +270,45 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
     const int nb = (int)((used + RB_BWD - 1) / RB_BWD);
     if (nb == 0) return;
     if (lane == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar[0], GSB_GATHER_TMA ? 1 : 32);
+        mbar_init(&s_bar[1], GSB_GATHER_TMA ? 1 : 32);
         mbar_fence_init();
     }
     __syncwarp();
 
     // batches are visited last -> first; sequence number s = nb-1-b selects stage / parity
+    // gather staging as in the forward: each lane pulls two 48-byte records per batch with TMA bulk copies
+    const uint32_t* __restrict__ vals = (*d_result_buf) ? vals1 : vals0;
+    uint32_t ia = 0xffffffffu, ib = 0xffffffffu;   // indices of this lane's two slots of the next batch to issue
+    auto load_idx = [&](int b) {
+        const uint32_t j0 = (uint32_t)b * RB_BWD + lane, j1 = j0 + 32;
+        ia = (b >= 0 && j0 < used) ? vals[start + j0] : 0xffffffffu;
+        ib = (b >= 0 && j1 < used) ? vals[start + j1] : 0xffffffffu;
+    };
     auto issue = [&](int b) {
         const int s = nb - 1 - b;
-        const uint32_t n = min((uint32_t)RB_BWD, used - (uint32_t)b * RB_BWD);
         uint64_t* bar = &s_bar[s & 1];
-        mbar_expect_tx(bar, n * 48u);
-        bulk_g2s(&s_rec[s & 1][0], staged + ((size_t)start + (size_t)b * RB_BWD) * 3, n * 48u, bar);
+#if GSB_GATHER_TMA
+        if (lane == 0) mbar_expect_tx(bar, min((uint32_t)RB_BWD, used - (uint32_t)b * RB_BWD) * 48u);
+        if (ia != 0xffffffffu) bulk_g2s(&s_rec[s & 1][lane * 3], rec + (size_t)ia * 3, 48u, bar);
+        if (ib != 0xffffffffu) bulk_g2s(&s_rec[s & 1][(lane + 32) * 3], rec + (size_t)ib * 3, 48u, bar);
+#else
+        if (ia != 0xffffffffu) {
+            float4* dst = &s_rec[s & 1][lane * 3];
+            const float4* src = rec + (size_t)ia * 3;
+            cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
+        }
+        if (ib != 0xffffffffu) {
+            float4* dst = &s_rec[s & 1][(lane + 32) * 3];
+            const float4* src = rec + (size_t)ib * 3;
+            cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
+        }
+        cp_async_mbar_arrive_noinc(bar);   // fires when this lane's copies have landed (immediately if it has none)
+#endif
     };
-    if (lane == 0) issue(nb - 1);
+    load_idx(nb - 1);
+    issue(nb - 1);
+    load_idx(nb - 2);
 
     const float pxf = (float)pxi, pyf = (float)py0;
     const uint32_t rec_base = smem_u32(&s_rec[0][0]);
@@ -260,7 +319,8 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
     for (int b = nb - 1; b >= 0; --b) {
         const int s = nb - 1 - b;
         __syncwarp();                               // every lane is done with the stage being refilled
-        if (lane == 0 && b > 0) issue(b - 1);
+        if (b > 0) issue(b - 1);
+        load_idx(b - 2);
         {
             float4* z = reinterpret_cast<float4*>(&s_out[0][0]);
             for (int i = lane; i < RB_BWD * 3; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -383,18 +443,20 @@ static int raster_blocks(const ViewParams& vp)
 }
 
 cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
-                              const uint32_t* tile_order, const float* staged,
+                              const uint32_t* tile_order, const float* rec, const uint32_t* vals0, const uint32_t* vals1,
+                              const uint32_t* d_result_buf,
                               float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last)
 {
     const int blocks = raster_blocks(vp);
     if (blocks > 0)
-        k_raster_fwd<<<blocks, RT, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(staged), out_color, out_depth,
-                                            out_alpha, out_last);
+        k_raster_fwd<<<blocks, RT, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
+                                            d_result_buf, out_color, out_depth, out_alpha, out_last);
     return cudaGetLastError();
 }
 
 cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
-                              const uint32_t* tile_order, const float* staged,
+                              const uint32_t* tile_order, const float* rec, const uint32_t* vals0, const uint32_t* vals1,
+                              const uint32_t* d_result_buf,
                               const float* cot_color, const float* cot_depth, const float* cot_alpha,
                               const float* out_color, const float* out_depth, const float* out_alpha,
                               const uint32_t* last_contrib, float* grad_rec)
@@ -409,11 +471,11 @@ cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint3
             carveout_set = true;
         }
         if (cot_depth)
-            k_raster_bwd<true><<<blocks, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(staged), cot_color,
-                                                      cot_depth, cot_alpha, out_alpha, last_contrib, grad_rec);
+            k_raster_bwd<true><<<blocks, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
+                                                      d_result_buf, cot_color, cot_depth, cot_alpha, out_alpha, last_contrib, grad_rec);
         else
-            k_raster_bwd<false><<<blocks, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(staged), cot_color,
-                                                       cot_depth, cot_alpha, out_alpha, last_contrib, grad_rec);
+            k_raster_bwd<false><<<blocks, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
+                                                       d_result_buf, cot_color, cot_depth, cot_alpha, out_alpha, last_contrib, grad_rec);
     }
     return cudaGetLastError();
 }
