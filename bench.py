@@ -191,6 +191,8 @@ def run_gsb(args, rank, local_rank, world):
     from gaussiansplattingmlx_b200.context import Context
     from gaussiansplattingmlx_b200.scene import make_workload
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -294,7 +296,8 @@ def run_gsb(args, rank, local_rank, world):
         "depth_sort": ("hbm", n * (4.0 + 16.0 * 4)),          # 32-bit key + index, 4 onesweep passes (r+w) + histogram read
         "keygen": ("hbm", 16.0 * n + 8.0 * M),              # perm, offset, rect in; (tile id, index) out
         "sort": ("hbm", M * (4.0 + 16.0 * passes)),          # 8-byte pairs, `passes` onesweep passes on the tile id
-        "ranges_gather": ("hbm", M * 4.0 + 16.0 * ctx.num_tiles),   # sorted tile ids in, ranges + launch order out "raster_fwd": ("fp32", 27.0 * E), "raster_bwd": ("fp32", 80.0 * E),
+        "ranges_gather": ("hbm", M * 4.0 + 16.0 * ctx.num_tiles),   # sorted tile ids in, ranges + launch order out
+        "raster_fwd": ("fp32", 27.0 * E), "raster_bwd": ("fp32", 80.0 * E),
         "loss": ("fp32", (225.0 + 170.0) * P * 3), "adam": ("hbm", 28.0 * 59 * n + 12.0 * n),
     }
     kernels = {}
