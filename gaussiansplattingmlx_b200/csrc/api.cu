@@ -835,7 +835,7 @@ int gsb_ssim_bwd(gsb_ctx* ctx, int32_t H, int32_t W, int32_t Cn, const float* gr
 // ---- fused renderer ------------------------------------------------------------------------------
 static int render_forward_impl(Ctx* c, int32_t N, const float* xyz, const float* f_dc, const float* f_rest,
                                const float* scales_log, const float* rot_raw, const float* opacity_logit,
-                               const gsb::ViewParams& vp, float* radii, uint8_t* visibility)
+                               const gsb::ViewParams& vp, float* radii, uint8_t* visibility, bool want_depth)
 {
     int rc = gsb::ensure_gaussians(c, N);
     if (rc != GSB_OK) return rc;
@@ -851,8 +851,8 @@ static int render_forward_impl(Ctx* c, int32_t N, const float* xyz, const float*
     if (rc != GSB_OK) return rc;
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, vp, c->tile_ranges, c->tile_order, c->rec, c->vals[0], c->vals[1], c->d_result_buf, c->out_color, c->out_depth,
-                                                 c->out_alpha, c->out_last));
+        GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, vp, c->tile_ranges, c->tile_order, c->rec, c->vals[0], c->vals[1], c->d_result_buf, c->out_color,
+                                                 want_depth ? c->out_depth : nullptr, c->out_alpha, c->out_last));
         c->stats.kernel_launches += 1;
     }
     c->saved.valid = true;
@@ -899,7 +899,7 @@ int gsb_render_forward(gsb_ctx* ctx, int32_t N, const float* xyz, const float* f
     GSB_REQUIRE(c, N >= 0 && xyz && f_dc && (f_rest || c->cfg.sh_coeffs == 1) && scales_log && rot_raw && opacity_logit && host_cam,
                 "gsb_render_forward: null argument");
     const gsb::ViewParams vp = gsb::make_view(c, host_cam);
-    int rc = render_forward_impl(c, N, xyz, f_dc, f_rest, scales_log, rot_raw, opacity_logit, vp, radii, visibility);
+    int rc = render_forward_impl(c, N, xyz, f_dc, f_rest, scales_log, rot_raw, opacity_logit, vp, radii, visibility, depth != nullptr);
     if (rc != GSB_OK) return rc;
     const size_t P = (size_t)c->P;
     if (render) GSB_CUDA_CHECK(c, cudaMemcpyAsync(render, c->out_color, P * 12, cudaMemcpyDeviceToDevice, c->stream));
@@ -1060,7 +1060,7 @@ int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
             if (rc != GSB_OK) return rc;
         }
         const gsb::ViewParams vp = gsb::make_view(c, &host_cams[b]);
-        int rc = render_forward_impl(c, N, c->t_p[0], c->t_p[1], c->t_p[2], c->t_p[3], c->t_p[4], c->t_p[5], vp, nullptr, nullptr);
+        int rc = render_forward_impl(c, N, c->t_p[0], c->t_p[1], c->t_p[2], c->t_p[3], c->t_p[4], c->t_p[5], vp, nullptr, nullptr, false);
         if (rc != GSB_OK) return rc;
         const float* target = host_targets[b];
         if (targets_on_host) {

@@ -25,7 +25,7 @@
 
 namespace gsb {
 
-constexpr int RT = 256;          // forward: threads per CTA = 16x16 pixels
+constexpr int RT = 64;           // forward: threads per CTA (16x16 pixels, 4 per thread)
 constexpr int RB_FWD = 128;      // records per forward batch (6 KB)
 constexpr int RB_BWD = 64;       // records per backward batch
 constexpr int BPPT = 8;          // backward: pixels per thread (rows)
@@ -59,123 +59,204 @@ __device__ __forceinline__ BlockMap map_block(const ViewParams& vp, const uint32
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RT) k_raster_fwd(const __grid_constant__ ViewParams vp,
-                                                   const uint32_t* __restrict__ tile_ranges,
-                                                   const uint32_t* __restrict__ tile_order,
-                                                   const float4* __restrict__ rec, const uint32_t* __restrict__ vals0,
-                                                   const uint32_t* __restrict__ vals1,
-                                                   const uint32_t* __restrict__ d_result_buf, float* __restrict__ out_color,
-                                                   float* __restrict__ out_depth, float* __restrict__ out_alpha,
-                                                   uint32_t* __restrict__ out_last)
+// A thread owns a column of FPPT = 4 vertically adjacent pixels; a warp covers 16 x 8 pixels and the
+// 64-thread CTA one 16 x 16 block.  Per Gaussian a thread reads the record ONCE (4 LDS instead of 16)
+// and evaluates the exponent as a quadratic in the compile-time row offset r:
+//     e(r) = E0 + r*E1 + r^2*C          (log2 units, log2(opacity) folded into E0)
+// so a row costs 2 FFMA + ex2 + min + the blend FMAs.  Termination bookkeeping is kept out of the inner
+// loop: a pixel whose transmittance drops below 1e-4 just gets T = 0 (all later Gaussians then add
+// exact zeros); lastContrib and the transmittance AT termination are recovered once per pixel in the
+// epilogue by replaying the (at most FCHUNK) Gaussians of the chunk in which the pixel died, starting
+// from the transmittance saved at that chunk's start, with bit-identical arithmetic (fwd_exponents).
+constexpr int FPPT = 4;          // forward: pixels (rows) per thread
+constexpr int FCHUNK = 4;        // Gaussians between termination bookkeeping / warp votes
+static_assert(RB_FWD % FCHUNK == 0, "batch must be a whole number of chunks");
+
+struct FwdExp {
+    float E0, E1, C;
+};
+// shared by the blend loop and the termination replay: identical instruction sequence => identical bits
+__device__ __forceinline__ FwdExp fwd_exponents(const float4& a, float C, float lo, float pxf, float pyf)
+{
+    const float dx = pxf - a.x, dyb = pyf - a.y;
+    const float Cd = __fmul_rn(C, dyb);
+    FwdExp e;
+    e.E0 = fmaf(dx, fmaf(a.z, dx, __fmul_rn(a.w, dyb)), fmaf(Cd, dyb, lo));
+    e.E1 = fmaf(a.w, dx, __fadd_rn(Cd, Cd));
+    e.C = C;
+    return e;
+}
+template <int R>
+__device__ __forceinline__ float fwd_alpha(const FwdExp& e)
+{
+    const float rf = (float)R;
+    const float p = R == 0 ? e.E0 : fmaf(rf, fmaf(rf, e.C, e.E1), e.E0);
+    return fminf(ex2_approx(p), 0.99f);
+}
+__device__ __forceinline__ float fwd_alpha_rt(const FwdExp& e, int r)
+{
+    switch (r) {
+        case 0: return fwd_alpha<0>(e);
+        case 1: return fwd_alpha<1>(e);
+        case 2: return fwd_alpha<2>(e);
+        default: return fwd_alpha<3>(e);
+    }
+}
+
+template <bool DEPTH>
+__global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ ViewParams vp,
+                                                       const uint32_t* __restrict__ tile_ranges,
+                                                       const uint32_t* __restrict__ tile_order,
+                                                       const float4* __restrict__ rec, const uint32_t* __restrict__ vals0,
+                                                       const uint32_t* __restrict__ vals1,
+                                                       const uint32_t* __restrict__ d_result_buf, float* __restrict__ out_color,
+                                                       float* __restrict__ out_depth, float* __restrict__ out_alpha,
+                                                       uint32_t* __restrict__ out_last)
 {
     __shared__ __align__(128) float4 s_rec[2][RB_FWD * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
     const BlockMap bm = map_block(vp, tile_order);
-    const int pxi = bm.x0 + (threadIdx.x & 15), pyi = bm.y0 + (threadIdx.x >> 4);
-    const bool active = pxi < bm.xmax && pyi < bm.ymax;
+    const int tid = threadIdx.x;
+    const int pxi = bm.x0 + (tid & 15), py0 = bm.y0 + (tid >> 4) * FPPT;
     const uint32_t start = tile_ranges[bm.tile * 2], end = tile_ranges[bm.tile * 2 + 1];
     const uint32_t count = end > start ? end - start : 0u;
     const int nb = (int)((count + RB_FWD - 1) / RB_FWD);
 
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar[0], GSB_GATHER_TMA ? 1 : RB_FWD);
-        mbar_init(&s_bar[1], GSB_GATHER_TMA ? 1 : RB_FWD);
+    if (tid == 0) {
+        mbar_init(&s_bar[0], RT);
+        mbar_init(&s_bar[1], RT);
         mbar_fence_init();
     }
     __syncthreads();
-    // Gather staging: the tile's list is (tile_ranges, sorted Gaussian indices); threads 0..RB_FWD-1 each pull
-    // ONE 48-byte record of the next batch from the (L2-resident) record table straight into shared memory with
-    // a TMA bulk copy; all copies of a batch complete on one mbarrier.  Indices are prefetched two batches ahead.
+    // Gather staging: the tile's list is (tile_ranges, sorted Gaussian indices); every thread pulls RB_FWD / RT
+    // 48-byte records of the next batch from the (L2-resident) record table straight into shared memory with
+    // 16-byte async copies that complete on the batch's mbarrier.  Indices are prefetched two batches ahead.
+    // Slots past the end of the list (up to the next chunk boundary) are filled with a null record
+    // (log2(opacity) = -inf => alpha = +0), so the blend loop always runs whole chunks.
     const uint32_t* __restrict__ vals = (*d_result_buf) ? vals1 : vals0;
-    auto load_idx = [&](int b) -> uint32_t {
-        const uint32_t j = (uint32_t)b * RB_FWD + threadIdx.x;
-        return (threadIdx.x < RB_FWD && b < nb && j < count) ? vals[start + j] : 0xffffffffu;
+    constexpr int SLOTS = RB_FWD / RT;
+    uint32_t idx_next[SLOTS];
+    auto load_idx = [&](int b) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const uint32_t j = (uint32_t)b * RB_FWD + s * RT + tid;
+            idx_next[s] = (b < nb && j < count) ? vals[start + j] : 0xffffffffu;
+        }
     };
-    auto issue = [&](int b, uint32_t idx) {
+    auto issue = [&](int b) {
         uint64_t* bar = &s_bar[b & 1];
-#if GSB_GATHER_TMA
-        if (threadIdx.x == 0) mbar_expect_tx(bar, min((uint32_t)RB_FWD, count - (uint32_t)b * RB_FWD) * 48u);
-        if (idx != 0xffffffffu) bulk_g2s(&s_rec[b & 1][threadIdx.x * 3], rec + (size_t)idx * 3, 48u, bar);
-#else
-        if (threadIdx.x < RB_FWD) {
-            if (idx != 0xffffffffu) {
-                float4* dst = &s_rec[b & 1][threadIdx.x * 3];
-                const float4* src = rec + (size_t)idx * 3;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            float4* dst = &s_rec[b & 1][(s * RT + tid) * 3];
+            if (idx_next[s] != 0xffffffffu) {
+                const float4* src = rec + (size_t)idx_next[s] * 3;
                 cp_async16(dst, src);
                 cp_async16(dst + 1, src + 1);
                 cp_async16(dst + 2, src + 2);
-                cp_async_mbar_arrive_noinc(bar);
             } else {
-                mbar_arrive(bar);
+                dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                dst[1] = make_float4(0.f, __int_as_float(0xff800000), 0.f, 0.f);
+                dst[2] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-#endif
+        cp_async_mbar_arrive_noinc(bar);   // fires when this thread's copies have landed
     };
-    uint32_t idx_next = load_idx(0);
-    if (nb > 0) issue(0, idx_next);
-    idx_next = load_idx(1);
+    load_idx(0);
+    if (nb > 0) issue(0);
+    load_idx(1);
+    __syncthreads();   // null-record fills of batch 0 are plain shared stores
 
-    const float px = (float)pxi, py = (float)pyi;
-    float cx = 0.f, cy = 0.f, cz = 0.f, dep = 0.f;
-    float T = active ? 1.0f : 0.0f;   // T == 0  <=>  this pixel is finished (terminated or outside)
-    float Tfin = -1.0f;               // transmittance at termination (valid when >= 0)
-    uint32_t nContrib = count;
+    const float pxf = (float)pxi, pyf = (float)py0;
+    float cx[FPPT], cy[FPPT], cz[FPPT], dep[FPPT], T[FPPT], Ts[FPPT];
+    uint32_t ci[FPPT];
+    bool active[FPPT];
+#pragma unroll
+    for (int r = 0; r < FPPT; ++r) {
+        active[r] = pxi < bm.xmax && py0 + r < bm.ymax;
+        cx[r] = cy[r] = cz[r] = dep[r] = 0.f;
+        T[r] = active[r] ? 1.0f : 0.0f;   // T == 0  <=>  this pixel is finished (terminated or outside)
+        Ts[r] = 0.f;
+        ci[r] = 0u;
+    }
     const uint32_t rec_base = smem_u32(&s_rec[0][0]);
+    bool warp_done = false;
 
-    // one Gaussian: slang/gaussian_tile_global_kernels.slang:437-499 + the termination test :599-603
-    auto blend = [&](uint32_t addr, uint32_t index) {
+    // one Gaussian for the thread's FPPT pixels: slang/gaussian_tile_global_kernels.slang:437-499
+    auto blend = [&](uint32_t addr) {
         const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
-        const float dx = px - a.x, dy = py - a.y;
-        const float t = fmaf(a.w, dy, a.z * dx);
-        const float u = q.x * dy;
-        const float p = fmaf(u, dy, fmaf(dx, t, q.y));
-        const float alpha = fminf(ex2_approx(p), 0.99f);
-        const float contrib = T * alpha;
-        cx = fmaf(contrib, q.z, cx);
-        cy = fmaf(contrib, q.w, cy);
-        cz = fmaf(contrib, c.x, cz);
-        dep = fmaf(contrib, c.z, dep);
-        float Tn = fmaf(-T, alpha, T);
-        if (Tn < 1e-4f && T != 0.0f) {   // terminating Gaussian is included (reference quirk)
-            nContrib = index + 1u;
-            Tfin = Tn;
-            Tn = 0.0f;
-        }
-        T = Tn;
+        const FwdExp e = fwd_exponents(a, q.x, q.y, pxf, pyf);
+        auto px = [&](int r, float alpha) {
+            const float contrib = T[r] * alpha;
+            cx[r] = fmaf(contrib, q.z, cx[r]);
+            cy[r] = fmaf(contrib, q.w, cy[r]);
+            cz[r] = fmaf(contrib, c.x, cz[r]);
+            if (DEPTH) dep[r] = fmaf(contrib, c.z, dep[r]);
+            const float Tn = fmaf(-T[r], alpha, T[r]);
+            T[r] = Tn < 1e-4f ? 0.0f : Tn;   // the terminating Gaussian is included (:599-603)
+        };
+        px(0, fwd_alpha<0>(e));
+        px(1, fwd_alpha<1>(e));
+        px(2, fwd_alpha<2>(e));
+        px(3, fwd_alpha<3>(e));
     };
 
     for (int b = 0; b < nb; ++b) {
-        if (b + 1 < nb) issue(b + 1, idx_next);
-        idx_next = load_idx(b + 2);
+        if (b + 1 < nb) issue(b + 1);
+        load_idx(b + 2);
         mbar_wait(&s_bar[b & 1], (uint32_t)(b >> 1) & 1u);
-        const int n = (int)min((uint32_t)RB_FWD, count - (uint32_t)b * RB_FWD);
-        if (!__all_sync(0xffffffffu, T == 0.0f)) {
+        if (!warp_done) {
+            const int n = (int)min((uint32_t)RB_FWD, count - (uint32_t)b * RB_FWD);
             uint32_t addr = rec_base + (uint32_t)(b & 1) * (RB_FWD * 48u);
-            const uint32_t i0 = (uint32_t)b * RB_FWD;
-            int j = 0;
-            for (; j + 4 <= n; j += 4, addr += 4 * 48u) {
-                blend(addr, i0 + j);
-                blend(addr + 48u, i0 + j + 1);
-                blend(addr + 96u, i0 + j + 2);
-                blend(addr + 144u, i0 + j + 3);
-                if (__all_sync(0xffffffffu, T == 0.0f)) { j = n; break; }
+            uint32_t chunk = (uint32_t)b * (RB_FWD / FCHUNK);
+            for (int j = 0; j < n; j += FCHUNK, addr += FCHUNK * 48u, ++chunk) {
+                // remember where (and with which transmittance) each live pixel entered this chunk
+#pragma unroll
+                for (int r = 0; r < FPPT; ++r) {
+                    const bool live = T[r] != 0.0f;
+                    Ts[r] = live ? T[r] : Ts[r];
+                    ci[r] = live ? chunk : ci[r];
+                }
+#pragma unroll
+                for (int g = 0; g < FCHUNK; ++g) blend(addr + g * 48u);
+                const float tmax = fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3]));
+                if (__all_sync(0xffffffffu, tmax == 0.0f)) { warp_done = true; break; }
             }
-            for (; j < n; ++j, addr += 48u) blend(addr, i0 + j);
         }
         // releases the stage buffer for the copy issued two batches later, and votes on early exit
-        if (__syncthreads_and(T == 0.0f)) {
+        if (__syncthreads_and(warp_done)) {
             if (b + 1 < nb) mbar_wait(&s_bar[(b + 1) & 1], (uint32_t)((b + 1) >> 1) & 1u);  // drain the in-flight copy
             break;
         }
     }
-    if (active) {
-        const float Tend = Tfin >= 0.0f ? Tfin : T;
-        const size_t p = (size_t)pyi * vp.W + pxi;
+    // epilogue: exact lastContrib / transmittance at termination, then the outputs
+#pragma unroll
+    for (int r = 0; r < FPPT; ++r) {
+        if (!active[r]) continue;
+        float Tend = T[r];
+        uint32_t nContrib = count;
+        if (Tend == 0.0f) {
+            float t = Ts[r];
+            uint32_t i = ci[r] * FCHUNK;
+            for (int g = 0; g < FCHUNK && i < count; ++g, ++i) {
+                const float4* src = rec + (size_t)vals[start + i] * 3;
+                const float4 a = __ldg(src), q = __ldg(src + 1);
+                const FwdExp e = fwd_exponents(a, q.x, q.y, pxf, pyf);
+                const float alpha = fwd_alpha_rt(e, r);
+                const float Tn = fmaf(-t, alpha, t);
+                if (Tn < 1e-4f) {
+                    nContrib = i + 1u;
+                    Tend = Tn;
+                    break;
+                }
+                t = Tn;
+            }
+        }
+        const size_t p = (size_t)(py0 + r) * vp.W + pxi;
         const float bg = vp.whiteBg ? Tend : 0.0f;
-        out_color[p * 3 + 0] = cx + bg;
-        out_color[p * 3 + 1] = cy + bg;
-        out_color[p * 3 + 2] = cz + bg;
-        out_depth[p] = dep;
+        out_color[p * 3 + 0] = cx[r] + bg;
+        out_color[p * 3 + 1] = cy[r] + bg;
+        out_color[p * 3 + 2] = cz[r] + bg;
+        if (DEPTH) out_depth[p] = dep[r];
         out_alpha[p] = 1.0f - Tend;
         out_last[p] = nContrib;
     }
@@ -448,9 +529,20 @@ cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint3
                               float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last)
 {
     const int blocks = raster_blocks(vp);
-    if (blocks > 0)
-        k_raster_fwd<<<blocks, RT, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
-                                            d_result_buf, out_color, out_depth, out_alpha, out_last);
+    if (blocks > 0) {
+        static bool carveout_set = false;
+        if (!carveout_set) {
+            cudaFuncSetAttribute(k_raster_fwd<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_raster_fwd<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carveout_set = true;
+        }
+        if (out_depth)
+            k_raster_fwd<true><<<blocks, RT, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
+                                                      d_result_buf, out_color, out_depth, out_alpha, out_last);
+        else
+            k_raster_fwd<false><<<blocks, RT, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
+                                                       d_result_buf, out_color, out_depth, out_alpha, out_last);
+    }
     return cudaGetLastError();
 }
 
