@@ -258,15 +258,30 @@ def run_gsb(args, rank, local_rank, world):
         evals += ctx.last_contrib_sum()
         pairs += ctx.stats()["pairs_last_view"]
 
-    # ---- timed region 1: inputs resident in HBM
+    # ---- timed region 1: inputs resident in HBM (the product configuration: view pipeline on)
     ctx.stats_reset()
-    ctx.enable_stage_timing(True)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     ms_dev = timed(False, False, args.steps, it); it += args.steps
+    launches = ctx.stats()["kernel_launches"]
+    if args.debug_overlap and rank == 0:   # how much each stage stretches when the two streams share the SMs
+        ctx.stats_reset(); ctx.enable_stage_timing(True)
+        ms_dbg = timed(False, False, args.steps, it); it += args.steps
+        sd = ctx.stats(); ctx.enable_stage_timing(False)
+        log(f"[overlap on] {ms_dbg / args.steps:.3f} ms/step; per-launch stage ms: " +
+            ", ".join(f"{k} {sd['stage_ms'][k] / max(sd['stage_calls'][k], 1):.3f}" for k in sd["stage_ms"] if sd["stage_calls"][k]))
+
+    # ---- per-kernel durations: same steps with the view pipeline OFF (every kernel alone on the work stream,
+    #      bracketed by CUDA events on that stream), so a kernel's time is not inflated by the kernels of the next
+    #      view that overlap it in region 1
+    ctx.set_flags(_lib.GSB_FLAG_NO_OVERLAP)
+    ctx.stats_reset()
+    ctx.enable_stage_timing(True)
+    ms_serial = timed(False, False, args.steps, it); it += args.steps
     st = ctx.stats()
     ctx.enable_stage_timing(False)
+    ctx.set_flags(0)
 
     # ---- timed region 2: end to end through the public API (pinned host targets H2D + loss D2H every step)
     step(it, True, True); it += 1
@@ -309,11 +324,11 @@ def run_gsb(args, rank, local_rank, world):
         if bound == "hbm":
             ach = work / (ms * 1e-3) / 1e9
             kernels[name] = {"bound": "hbm", "ms": ms, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": ach / peaks["hbm_gbs"], "share_of_step": st["stage_ms"][name] / (ms_dev) }
+                             "frac": ach / peaks["hbm_gbs"], "share_of_step": st["stage_ms"][name] / ms_serial}
         else:
             ach = work / (ms * 1e-3) / 1e12
             kernels[name] = {"bound": "fp32", "ms": ms, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                             "frac": ach / fp32_peak, "share_of_step": st["stage_ms"][name] / (ms_dev)}
+                             "frac": ach / fp32_peak, "share_of_step": st["stage_ms"][name] / ms_serial}
     dominant = max(kernels, key=lambda k: kernels[k]["share_of_step"]) if kernels else None
     roof = None
     if dominant:
@@ -323,7 +338,10 @@ def run_gsb(args, rank, local_rank, world):
                 "peak_source": (f"{peaks['source']} MEASURED_PEAKS.json hbm_gbs" if d["bound"] == "hbm" else
                                 f"non-tensor FP32 pipe: 148 SM x 128 lanes x 2 flop x sm_max_mhz ({peaks['source']}); "
                                 "no measured FP32 figure exists in MEASURED_PEAKS.json"),
-                "units_per_launch": {"pairs_M": M, "blend_evals_E": E, "gaussians": n, "pixels": P}}
+                "units_per_launch": {"pairs_M": M, "blend_evals_E": E, "gaussians": n, "pixels": P},
+                "timing": "CUDA-event pairs around every launch on the library's work stream, averaged over a second pass of "
+                          "the same steps with the view pipeline disabled (kernels back to back); share_of_step is relative to "
+                          "that pass (ms_per_step_serialized)"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -339,7 +357,8 @@ def run_gsb(args, rank, local_rank, world):
            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                    "h2d_bytes_per_step": img_bytes * len(my_views), "d2h_bytes_per_step": 4,
                    "api": "Context.trainer_accumulate(pinned host targets, want_loss) [+ NCCL all_reduce] + trainer_apply"},
-           "gpu_launches": st["kernel_launches"], "clocks": clk, "roofline": roof, "roofline_kernels": kernels,
+           "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_kernels": kernels,
+           "ms_per_step_serialized": ms_serial / K,
            "cpu_baseline": cpu}
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -356,6 +375,7 @@ def main():
     ap.add_argument("--n", type=int, default=None, help="override the Gaussian count (debugging only)")
     ap.add_argument("--views", type=int, default=None, help="override the views per step (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug-overlap", action="store_true", help="also print per-stage times measured WITH the view pipeline on")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

@@ -16,6 +16,7 @@ LIB_PATH = HERE / "libgsb.so"
 GSB_OK = 0
 GSB_ERR_INVALID, GSB_ERR_CUDA, GSB_ERR_UNSUPPORTED, GSB_ERR_STATE, GSB_ERR_CAPACITY = -1, -2, -3, -4, -5
 GSB_FLAG_SORT_CUB = 1
+GSB_FLAG_NO_OVERLAP = 2
 STAGE_COUNT = 12
 
 
@@ -57,6 +58,7 @@ SIGNATURES = {
     "gsb_last_error": (C.c_char_p, [_P]),
     "gsb_set_stream": (C.c_int, [_P, _P]),
     "gsb_synchronize": (C.c_int, [_P]),
+    "gsb_set_flags": (C.c_int, [_P, C.c_int32]),
     "gsb_activate_fwd": (C.c_int, [_P, _I] + [_P] * 9),
     "gsb_activate_bwd": (C.c_int, [_P, _I] + [_P] * 12),
     "gsb_project_fwd": (C.c_int, [_P, _I] + [_P] * 4 + [C.POINTER(GsbCamera)] + [_P] * 8),

@@ -85,6 +85,11 @@ class Context:
     def synchronize(self):
         self._check(self.lib.gsb_synchronize(self.h))
 
+    def set_flags(self, flags: int):
+        """Replace gsb_config.flags (e.g. GSB_FLAG_NO_OVERLAP for per-kernel timing)."""
+        self._check(self.lib.gsb_set_flags(self.h, int(flags)))
+        self.cfg.flags = int(flags)
+
     # ---- activations ------------------------------------------------------------------------
     def activate_fwd(self, params: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         self._sync_stream()

@@ -28,44 +28,60 @@ struct Ctx {
     std::string err;
     int gridW = 0, gridH = 0, numTiles = 0, tileBits = 1, P = 0;
 
-    // per-Gaussian buffers (capacity capN)
-    int capN = 0;
-    float* rec = nullptr;          // [N,12]
-    float* grad_rec = nullptr;     // [N,12]
-    uint2* tile_rects = nullptr;   // [N]
-    uint32_t* touched = nullptr;   // [N]
-    uint32_t* offsets = nullptr;   // [N] exclusive scan of touched, in DEPTH order
-    uint32_t* dkeys[2] = {nullptr, nullptr};   // [N] asuint(depth) sort keys (ping-pong)
-    uint32_t* dvals[2] = {nullptr, nullptr};   // [N] Gaussian indices in depth order (ping-pong)
-    void* dsort_ws = nullptr;
-    SortPlan dplan;
-    const uint32_t* d_dresult_buf = nullptr;   // which dvals buffer holds the depth order
-    uint32_t* d_nvalue = nullptr;              // device copy of N (count of the depth sort)
-    uint32_t* offsets_ref = nullptr;           // [N] scan in index order (parity API: reference emission order)
-    const float* depth_src = nullptr;          // depth of Gaussian g at depth_src[g * depth_src_stride]
-    int depth_src_stride = 1;
-    void* scan_ws = nullptr;
-    float* act_tmp = nullptr;      // scratch for the reference-layout parity API ([N,12] floats)
+    // Per-view working set.  There are two: while the rasteriser / loss / backward kernels of view v run on the
+    // work stream, the projection + binning of view v+1 run on the (higher-priority) front stream into the
+    // other set (trainer path only; the single-view API always uses set `cur`).
+    struct ViewBufs {
+        // per Gaussian (capacity capN)
+        float* rec = nullptr;          // [N,12]
+        uint2* tile_rects = nullptr;   // [N]
+        uint32_t* touched = nullptr;   // [N]
+        uint32_t* offsets = nullptr;   // [N] exclusive scan of touched, in DEPTH order
+        uint32_t* dkeys[2] = {nullptr, nullptr};   // [N] asuint(depth) sort keys (ping-pong)
+        uint32_t* dvals[2] = {nullptr, nullptr};   // [N] Gaussian indices in depth order (ping-pong)
+        void* dsort_ws = nullptr;
+        const uint32_t* d_dresult_buf = nullptr;   // which dvals buffer holds the depth order
+        uint32_t* d_nvalue = nullptr;              // device copy of N (count of the depth sort)
+        void* scan_ws = nullptr;
+        const float* depth_src = nullptr;          // depth of Gaussian g at depth_src[g * depth_src_stride]
+        int depth_src_stride = 1;
+        // per pair (capacity capM)
+        uint32_t* keys[2] = {nullptr, nullptr};   // tile ids
+        uint32_t* vals[2] = {nullptr, nullptr};   // Gaussian indices
+        void* sort_ws = nullptr;
+        const uint32_t* d_result_buf = nullptr;  // device flag: which ping-pong buffer holds the sorted list
+        // per tile
+        uint32_t* tile_ranges = nullptr;  // [numTiles,2]
+        uint32_t* tile_order = nullptr;   // [numTiles] tile ids, longest list first
+        // control words: [0] = M of the current view, [1] = overflow flag, [2] scratch
+        uint32_t* d_ctl = nullptr;
+        uint32_t* h_ctl = nullptr;        // pinned mirror
+        cudaEvent_t ev_ctl = nullptr;     // fires when h_ctl[0] holds M
+        cudaEvent_t ev_front = nullptr;   // projection + binning of this set finished (front stream)
+        cudaEvent_t ev_back = nullptr;    // the work stream no longer reads this set
+        uint32_t last_M = 0;
+    } vb[2];
+    int cur = 0;                       // set used by the single-view API / holding the saved forward
+    cudaStream_t front_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr;     // work stream -> front stream dependency at the start of a batch
 
-    // per-pair buffers (capacity capM)
+    int capN = 0;
+    SortPlan dplan;
+    float* grad_rec = nullptr;         // [N,12]
+    uint32_t* offsets_ref = nullptr;   // [N] scan in index order (parity API: reference emission order)
+    float* act_tmp = nullptr;          // scratch for the reference-layout parity API ([N,12] floats)
+
     uint32_t capM = 0;
-    uint32_t* keys[2] = {nullptr, nullptr};   // tile ids
-    uint32_t* vals[2] = {nullptr, nullptr};   // Gaussian indices
-    float* staged = nullptr;       // [M,12]
-    void* sort_ws = nullptr;
     SortPlan plan;
     void* cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
     uint64_t* dbg_keys = nullptr;  // unsorted copies for gsb_bin_read
     uint32_t* dbg_vals = nullptr;
     uint32_t dbg_cap = 0;
-    const uint32_t* d_result_buf = nullptr;  // device flag: which ping-pong buffer holds the sorted list
     uint32_t* d_zero = nullptr;              // constant 0 (CUB path result buffer selector = 1 → d_one)
     uint32_t* d_one = nullptr;
 
-    // per-tile / per-pixel
-    uint32_t* tile_ranges = nullptr;  // [numTiles,2]
-    uint32_t* tile_order = nullptr;   // [numTiles] tile ids, longest list first
+    // per pixel
     float* out_color = nullptr;       // saved forward outputs
     float* out_depth = nullptr;
     float* out_alpha = nullptr;
@@ -77,12 +93,6 @@ struct Ctx {
     double* partial = nullptr;        // [2]
     float* loss_accum = nullptr;      // device scalar
     float* h_loss = nullptr;          // pinned
-
-    // control words: [0] = M of the current view, [1] = overflow flag
-    uint32_t* d_ctl = nullptr;
-    uint32_t* h_ctl = nullptr;        // pinned mirror
-    cudaEvent_t ev_ctl = nullptr;
-    uint32_t last_M = 0;
 
     // saved forward (one in flight, like the reference's closure-captured state)
     struct Saved {
@@ -119,6 +129,7 @@ static void resolve_stage_events(Ctx* c)
 {
     if (c->ev_used == 0) return;
     cudaStreamSynchronize(c->stream);
+    if (c->front_stream) cudaStreamSynchronize(c->front_stream);
     for (size_t i = 0; i < c->ev_used; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->ev_pool[i].a, c->ev_pool[i].b) == cudaSuccess) {
@@ -138,8 +149,8 @@ static const char* kStageNames[GSB_STAGE_COUNT] = {"project_fwd", "scan", "keyge
                                                    "loss", "raster_bwd", "project_bwd", "adam", "h2d", "depth_sort"};
 
 struct StageTimer {
-    Ctx* c; int stage; bool on;
-    StageTimer(Ctx* ctx, int s) : c(ctx), stage(s), on(ctx->timing)
+    Ctx* c; int stage; bool on; cudaStream_t st;
+    StageTimer(Ctx* ctx, int s, cudaStream_t stream = nullptr) : c(ctx), stage(s), on(ctx->timing), st(stream ? stream : ctx->stream)
     {
         if (!on) return;
         if (c->ev_used >= 16384) resolve_stage_events(c);
@@ -149,12 +160,12 @@ struct StageTimer {
             c->ev_pool.push_back(e);
         }
         c->ev_pool[c->ev_used].stage = stage;
-        cudaEventRecord(c->ev_pool[c->ev_used].a, c->stream);
+        cudaEventRecord(c->ev_pool[c->ev_used].a, st);
     }
     ~StageTimer()
     {
         if (!on) return;
-        cudaEventRecord(c->ev_pool[c->ev_used].b, c->stream);
+        cudaEventRecord(c->ev_pool[c->ev_used].b, st);
         c->ev_used += 1;
     }
 };
@@ -212,6 +223,12 @@ static ViewParams make_view_nocam(const Ctx* c)
     return make_view(c, &cam);
 }
 
+static void sync_all_streams(Ctx* c)
+{
+    cudaStreamSynchronize(c->stream);
+    if (c->front_stream) cudaStreamSynchronize(c->front_stream);
+}
+
 static int ensure_gaussians(Ctx* c, int N)
 {
     if (N <= c->capN) return GSB_OK;
@@ -219,26 +236,29 @@ static int ensure_gaussians(Ctx* c, int N)
         set_error(c, "N exceeds gsb_config.max_gaussians");
         return GSB_ERR_INVALID;
     }
-    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-    dev_free(c->rec); dev_free(c->grad_rec); dev_free(c->tile_rects); dev_free(c->touched); dev_free(c->offsets);
-    dev_free(c->scan_ws); dev_free(c->act_tmp); dev_free(c->offsets_ref);
-    for (int i = 0; i < 2; ++i) { dev_free(c->dkeys[i]); dev_free(c->dvals[i]); }
-    if (c->dsort_ws) { cudaFree(c->dsort_ws); c->dsort_ws = nullptr; }
+    sync_all_streams(c);
     const int cap = c->cfg.max_gaussians > 0 ? c->cfg.max_gaussians : std::max(N, 1024);
-    GSB_CUDA_CHECK(c, dev_alloc(&c->rec, (size_t)cap * REC_FLOATS));
+    dev_free(c->grad_rec); dev_free(c->act_tmp); dev_free(c->offsets_ref);
     GSB_CUDA_CHECK(c, dev_alloc(&c->grad_rec, (size_t)cap * REC_FLOATS));
-    GSB_CUDA_CHECK(c, dev_alloc(&c->tile_rects, (size_t)cap));
-    GSB_CUDA_CHECK(c, dev_alloc(&c->touched, (size_t)cap));
-    GSB_CUDA_CHECK(c, dev_alloc(&c->offsets, (size_t)cap));
     GSB_CUDA_CHECK(c, dev_alloc(&c->act_tmp, (size_t)cap * REC_FLOATS));
-    GSB_CUDA_CHECK(c, cudaMalloc(&c->scan_ws, scan_ws_bytes(cap)));
     GSB_CUDA_CHECK(c, dev_alloc(&c->offsets_ref, (size_t)cap));
-    for (int i = 0; i < 2; ++i) {
-        GSB_CUDA_CHECK(c, dev_alloc(&c->dkeys[i], (size_t)cap));
-        GSB_CUDA_CHECK(c, dev_alloc(&c->dvals[i], (size_t)cap));
-    }
     c->dplan = sort_plan((uint32_t)cap, 32u);
-    GSB_CUDA_CHECK(c, cudaMalloc(&c->dsort_ws, c->dplan.ws_bytes));
+    for (Ctx::ViewBufs& v : c->vb) {
+        dev_free(v.rec); dev_free(v.tile_rects); dev_free(v.touched); dev_free(v.offsets);
+        for (int i = 0; i < 2; ++i) { dev_free(v.dkeys[i]); dev_free(v.dvals[i]); }
+        if (v.dsort_ws) { cudaFree(v.dsort_ws); v.dsort_ws = nullptr; }
+        if (v.scan_ws) { cudaFree(v.scan_ws); v.scan_ws = nullptr; }
+        GSB_CUDA_CHECK(c, dev_alloc(&v.rec, (size_t)cap * REC_FLOATS));
+        GSB_CUDA_CHECK(c, dev_alloc(&v.tile_rects, (size_t)cap));
+        GSB_CUDA_CHECK(c, dev_alloc(&v.touched, (size_t)cap));
+        GSB_CUDA_CHECK(c, dev_alloc(&v.offsets, (size_t)cap));
+        GSB_CUDA_CHECK(c, cudaMalloc(&v.scan_ws, scan_ws_bytes(cap)));
+        for (int i = 0; i < 2; ++i) {
+            GSB_CUDA_CHECK(c, dev_alloc(&v.dkeys[i], (size_t)cap));
+            GSB_CUDA_CHECK(c, dev_alloc(&v.dvals[i], (size_t)cap));
+        }
+        GSB_CUDA_CHECK(c, cudaMalloc(&v.dsort_ws, c->dplan.ws_bytes));
+    }
     c->capN = cap;
     return GSB_OK;
 }
@@ -250,140 +270,161 @@ static int ensure_pairs(Ctx* c, uint64_t M)
         set_error(c, "intersection list exceeds the 32-bit index range");
         return GSB_ERR_CAPACITY;
     }
-    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < 2; ++i) { dev_free(c->keys[i]); dev_free(c->vals[i]); }
-    dev_free(c->staged);
-    if (c->sort_ws) { cudaFree(c->sort_ws); c->sort_ws = nullptr; }
+    sync_all_streams(c);
     if (c->cub_tmp) { cudaFree(c->cub_tmp); c->cub_tmp = nullptr; c->cub_tmp_bytes = 0; }
     uint64_t cap = std::max<uint64_t>(M + M / 4, 1u << 16);
     cap = (cap + 4095) & ~4095ull;
-    for (int i = 0; i < 2; ++i) {
-        GSB_CUDA_CHECK(c, dev_alloc(&c->keys[i], (size_t)cap));
-        GSB_CUDA_CHECK(c, dev_alloc(&c->vals[i], (size_t)cap));
-    }
     c->plan = sort_plan((uint32_t)cap, (uint32_t)c->tileBits);
-    GSB_CUDA_CHECK(c, cudaMalloc(&c->sort_ws, c->plan.ws_bytes));
+    for (Ctx::ViewBufs& v : c->vb) {
+        for (int i = 0; i < 2; ++i) { dev_free(v.keys[i]); dev_free(v.vals[i]); }
+        if (v.sort_ws) { cudaFree(v.sort_ws); v.sort_ws = nullptr; }
+        for (int i = 0; i < 2; ++i) {
+            GSB_CUDA_CHECK(c, dev_alloc(&v.keys[i], (size_t)cap));
+            GSB_CUDA_CHECK(c, dev_alloc(&v.vals[i], (size_t)cap));
+        }
+        GSB_CUDA_CHECK(c, cudaMalloc(&v.sort_ws, c->plan.ws_bytes));
+    }
     c->capM = (uint32_t)cap;
     c->stats.pair_capacity = cap;
     return GSB_OK;
 }
 
-// depth sort → scan → keys → tile sort → ranges (+ gather when rec != NULL).
-// tile_rects / touched / dkeys[0] must be filled; depth of Gaussian g is depth_ptr[g * depth_stride].
-static int cub_sort32(Ctx* c, uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, uint32_t count, uint32_t end_bit)
+static int cub_sort32(Ctx* c, cudaStream_t st, uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, uint32_t count,
+                      uint32_t end_bit)
 {
     size_t need = 0;
-    GSB_CUDA_CHECK(c, cub_sort_pairs32(c->stream, k0, k1, v0, v1, count, end_bit, nullptr, 0, &need));
+    GSB_CUDA_CHECK(c, cub_sort_pairs32(st, k0, k1, v0, v1, count, end_bit, nullptr, 0, &need));
     if (need > c->cub_tmp_bytes) {
-        GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        sync_all_streams(c);
         if (c->cub_tmp) cudaFree(c->cub_tmp);
         c->cub_tmp = nullptr; c->cub_tmp_bytes = 0;
         GSB_CUDA_CHECK(c, cudaMalloc(&c->cub_tmp, need));
         c->cub_tmp_bytes = need;
     }
-    if (count > 0) GSB_CUDA_CHECK(c, cub_sort_pairs32(c->stream, k0, k1, v0, v1, count, end_bit, c->cub_tmp, c->cub_tmp_bytes, nullptr));
+    if (count > 0) GSB_CUDA_CHECK(c, cub_sort_pairs32(st, k0, k1, v0, v1, count, end_bit, c->cub_tmp, c->cub_tmp_bytes, nullptr));
     return GSB_OK;
 }
 
-static int run_binning(Ctx* c, int N, const ViewParams& vp, const float* depth_ptr, int depth_stride, const float* rec,
-                       bool keep_unsorted)
+// depth sort → scan → keys → tile sort → ranges, enqueued on `st` into view set `v`.
+// v.tile_rects / v.touched / v.dkeys[0] must be filled; depth of Gaussian g is depth_ptr[g * depth_stride].
+// Does not wait for the GPU (except the very first call, which sizes the pair buffers, and the CUB baseline):
+// the pair count M is copied to pinned memory behind v.ev_ctl and checked later by finish_binning.
+static int enqueue_binning(Ctx* c, Ctx::ViewBufs& v, cudaStream_t st, int N, const ViewParams& vp, const float* depth_ptr,
+                           int depth_stride)
 {
     int launches = 0;
     const bool use_cub = (c->cfg.flags & GSB_FLAG_SORT_CUB) != 0;
-    c->depth_src = depth_ptr;
-    c->depth_src_stride = depth_stride;
-    for (int attempt = 0; attempt < 4; ++attempt) {
-        {
-            StageTimer t(c, GSB_STAGE_DEPTH_SORT);
-            // 1. Gaussians into depth order (stable: ties keep index order)
-            const uint32_t n32 = (uint32_t)N;
-            GSB_CUDA_CHECK(c, cudaMemsetAsync(c->d_ctl, 0, 2 * sizeof(uint32_t), c->stream));
-            GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_nvalue, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-            if (use_cub) {
-                GSB_CUDA_CHECK(c, launch_iota(c->stream, n32, c->dvals[0]));
-                int rc = cub_sort32(c, c->dkeys[0], c->dkeys[1], c->dvals[0], c->dvals[1], n32, 32u);
-                if (rc != GSB_OK) return rc;
-                c->d_dresult_buf = N > 0 ? c->d_one : c->d_zero;
-                launches += 2;
-            } else {
-                SortPlan dp = c->dplan;
-                dp.capacity = n32;
-                dp.max_tiles = (uint32_t)cdiv(N > 0 ? N : 1, 4096);
-                GSB_CUDA_CHECK(c, launch_onesweep_sort32(c->stream, dp, c->dkeys[0], c->dkeys[1], c->dvals[0], c->dvals[1], 1,
-                                                         c->d_nvalue, c->dsort_ws, &c->d_dresult_buf, &launches));
-            }
-        }
-        {
-            StageTimer t(c, GSB_STAGE_SCAN);
-            // 2. offsets in depth order, M
-            GSB_CUDA_CHECK(c, launch_exclusive_scan(c->stream, N, c->touched, c->dvals[0], c->dvals[1], c->d_dresult_buf, c->offsets,
-                                                    &c->d_ctl[0], c->scan_ws));
-            ++launches;
-        }
-        GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-        GSB_CUDA_CHECK(c, cudaEventRecord(c->ev_ctl, c->stream));
-        if (c->capM == 0) {  // first use: size the pair buffers from the actual count
-            GSB_CUDA_CHECK(c, cudaEventSynchronize(c->ev_ctl));
-            int rc = ensure_pairs(c, std::max<uint64_t>(c->h_ctl[0], 1));
+    v.depth_src = depth_ptr;
+    v.depth_src_stride = depth_stride;
+    {
+        StageTimer t(c, GSB_STAGE_DEPTH_SORT, st);
+        // 1. Gaussians into depth order (stable: ties keep index order)
+        const uint32_t n32 = (uint32_t)N;
+        GSB_CUDA_CHECK(c, cudaMemsetAsync(v.d_ctl, 0, 2 * sizeof(uint32_t), st));
+        GSB_CUDA_CHECK(c, cudaMemcpyAsync(v.d_nvalue, &n32, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if (use_cub) {
+            GSB_CUDA_CHECK(c, launch_iota(st, n32, v.dvals[0]));
+            int rc = cub_sort32(c, st, v.dkeys[0], v.dkeys[1], v.dvals[0], v.dvals[1], n32, 32u);
             if (rc != GSB_OK) return rc;
-        }
-        {
-            StageTimer t(c, GSB_STAGE_KEYGEN);
-            GSB_CUDA_CHECK(c, launch_generate_keys(c->stream, N, vp, c->tile_rects, c->offsets, c->dvals[0], c->dvals[1],
-                                                   c->d_dresult_buf, c->keys[0], c->vals[0], c->capM, &c->d_ctl[0], &c->d_ctl[1]));
-            ++launches;
-        }
-        {
-            StageTimer t(c, GSB_STAGE_SORT);
-            // 3. stable sort on the tile id alone (the list is already in (depth, index) order)
-            if (use_cub) {
-                GSB_CUDA_CHECK(c, cudaEventSynchronize(c->ev_ctl));   // checked baseline: needs the host-known count
-                const uint32_t M = std::min(c->h_ctl[0], c->capM);
-                int rc = cub_sort32(c, c->keys[0], c->keys[1], c->vals[0], c->vals[1], M, (uint32_t)c->tileBits);
-                if (rc != GSB_OK) return rc;
-                c->d_result_buf = M > 0 ? c->d_one : c->d_zero;
-                launches += 1;
-            } else {
-                GSB_CUDA_CHECK(c, launch_onesweep_sort32(c->stream, c->plan, c->keys[0], c->keys[1], c->vals[0], c->vals[1], 0,
-                                                         &c->d_ctl[0], c->sort_ws, &c->d_result_buf, &launches));
-            }
-        }
-        {
-            StageTimer t(c, GSB_STAGE_RANGES_GATHER);
-            GSB_CUDA_CHECK(c, launch_ranges_gather(c->stream, vp, c->keys[0], c->keys[1], c->vals[0], c->vals[1],
-                                                   c->d_result_buf, &c->d_ctl[0], c->capM, nullptr, c->tile_ranges, nullptr,
-                                                   c->numTiles));
-            (void)rec;
-            GSB_CUDA_CHECK(c, launch_tile_order(c->stream, c->numTiles, c->tile_ranges, c->tile_order));
+            v.d_dresult_buf = N > 0 ? c->d_one : c->d_zero;
             launches += 2;
+        } else {
+            SortPlan dp = c->dplan;
+            dp.capacity = n32;
+            dp.max_tiles = (uint32_t)cdiv(N > 0 ? N : 1, 4096);
+            GSB_CUDA_CHECK(c, launch_onesweep_sort32(st, dp, v.dkeys[0], v.dkeys[1], v.dvals[0], v.dvals[1], 1, v.d_nvalue,
+                                                     v.dsort_ws, &v.d_dresult_buf, &launches));
         }
-        // overflow check: the event fired right after the scan, long before the queue drains
-        GSB_CUDA_CHECK(c, cudaEventSynchronize(c->ev_ctl));
-        const uint32_t M = c->h_ctl[0];
-        if (M <= c->capM) {
-            c->last_M = M;
-            c->stats.kernel_launches += launches;
-            break;
-        }
-        if (attempt == 3) {
-            set_error(c, "intersection buffers kept overflowing");
-            return GSB_ERR_CAPACITY;
-        }
-        int rc = ensure_pairs(c, M);
+    }
+    {
+        StageTimer t(c, GSB_STAGE_SCAN, st);
+        // 2. offsets in depth order, M
+        GSB_CUDA_CHECK(c, launch_exclusive_scan(st, N, v.touched, v.dvals[0], v.dvals[1], v.d_dresult_buf, v.offsets, &v.d_ctl[0],
+                                                v.scan_ws));
+        ++launches;
+    }
+    GSB_CUDA_CHECK(c, cudaMemcpyAsync(v.h_ctl, v.d_ctl, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA_CHECK(c, cudaEventRecord(v.ev_ctl, st));
+    if (c->capM == 0) {  // first use: size the pair buffers from the actual count
+        GSB_CUDA_CHECK(c, cudaEventSynchronize(v.ev_ctl));
+        int rc = ensure_pairs(c, std::max<uint64_t>(v.h_ctl[0], 1));
         if (rc != GSB_OK) return rc;
+    }
+    {
+        StageTimer t(c, GSB_STAGE_KEYGEN, st);
+        GSB_CUDA_CHECK(c, launch_generate_keys(st, N, vp, v.tile_rects, v.offsets, v.dvals[0], v.dvals[1], v.d_dresult_buf, v.keys[0],
+                                               v.vals[0], c->capM, &v.d_ctl[0], &v.d_ctl[1]));
+        ++launches;
+    }
+    {
+        StageTimer t(c, GSB_STAGE_SORT, st);
+        // 3. stable sort on the tile id alone (the list is already in (depth, index) order)
+        if (use_cub) {
+            GSB_CUDA_CHECK(c, cudaEventSynchronize(v.ev_ctl));   // checked baseline: needs the host-known count
+            const uint32_t M = std::min(v.h_ctl[0], c->capM);
+            int rc = cub_sort32(c, st, v.keys[0], v.keys[1], v.vals[0], v.vals[1], M, (uint32_t)c->tileBits);
+            if (rc != GSB_OK) return rc;
+            v.d_result_buf = M > 0 ? c->d_one : c->d_zero;
+            launches += 1;
+        } else {
+            GSB_CUDA_CHECK(c, launch_onesweep_sort32(st, c->plan, v.keys[0], v.keys[1], v.vals[0], v.vals[1], 0, &v.d_ctl[0],
+                                                     v.sort_ws, &v.d_result_buf, &launches));
+        }
+    }
+    {
+        StageTimer t(c, GSB_STAGE_RANGES_GATHER, st);
+        GSB_CUDA_CHECK(c, launch_ranges_gather(st, vp, v.keys[0], v.keys[1], v.vals[0], v.vals[1], v.d_result_buf, &v.d_ctl[0],
+                                               c->capM, nullptr, v.tile_ranges, nullptr, c->numTiles));
+        GSB_CUDA_CHECK(c, launch_tile_order(st, c->numTiles, v.tile_ranges, v.tile_order));
+        launches += 2;
+    }
+    c->stats.kernel_launches += launches;
+    return GSB_OK;
+}
+
+// Waits for the pair count of the binning enqueued on set v (the event fired right after the scan, long
+// before the queue drains).  Returns GSB_OK, or GSB_ERR_CAPACITY when the lists did not fit: the pair
+// buffers have then been regrown and the caller must redo projection + binning of that view.
+static int finish_binning(Ctx* c, Ctx::ViewBufs& v)
+{
+    GSB_CUDA_CHECK(c, cudaEventSynchronize(v.ev_ctl));
+    const uint32_t M = v.h_ctl[0];
+    if (M <= c->capM) {
+        v.last_M = M;
+        return GSB_OK;
+    }
+    int rc = ensure_pairs(c, M);
+    if (rc != GSB_OK) return rc;
+    set_error(c, "intersection buffers regrown");
+    return GSB_ERR_CAPACITY;
+}
+
+// blocking variant on the work stream for the single-view API
+static int run_binning(Ctx* c, Ctx::ViewBufs& v, int N, const ViewParams& vp, const float* depth_ptr, int depth_stride,
+                       bool keep_unsorted)
+{
+    for (int attempt = 0;; ++attempt) {
+        int rc = enqueue_binning(c, v, c->stream, N, vp, depth_ptr, depth_stride);
+        if (rc != GSB_OK) return rc;
+        rc = finish_binning(c, v);
+        if (rc == GSB_OK) break;
+        if (rc != GSB_ERR_CAPACITY || attempt == 3) {
+            if (rc == GSB_ERR_CAPACITY) set_error(c, "intersection buffers kept overflowing");
+            return rc;
+        }
     }
     if (keep_unsorted) {
         // the reference's UNSORTED lists (emission order = Gaussian index order, 64-bit keys): parity API only
         if (c->dbg_cap < c->capM) {
-            GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+            sync_all_streams(c);
             dev_free(c->dbg_keys); dev_free(c->dbg_vals);
             GSB_CUDA_CHECK(c, dev_alloc(&c->dbg_keys, (size_t)c->capM));
             GSB_CUDA_CHECK(c, dev_alloc(&c->dbg_vals, (size_t)c->capM));
             c->dbg_cap = c->capM;
         }
-        GSB_CUDA_CHECK(c, launch_exclusive_scan(c->stream, N, c->touched, nullptr, nullptr, nullptr, c->offsets_ref, &c->d_ctl[2],
-                                                c->scan_ws));
-        GSB_CUDA_CHECK(c, launch_generate_keys_ref(c->stream, N, vp, c->tile_rects, c->offsets_ref, depth_ptr, depth_stride,
+        GSB_CUDA_CHECK(c, launch_exclusive_scan(c->stream, N, v.touched, nullptr, nullptr, nullptr, c->offsets_ref, &v.d_ctl[2],
+                                                v.scan_ws));
+        GSB_CUDA_CHECK(c, launch_generate_keys_ref(c->stream, N, vp, v.tile_rects, c->offsets_ref, depth_ptr, depth_stride,
                                                    c->dbg_keys, c->dbg_vals, c->capM));
         c->stats.kernel_launches += 2;
     }
@@ -406,27 +447,33 @@ static void destroy_ctx(Ctx* c)
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    dev_free(c->rec); dev_free(c->grad_rec); dev_free(c->tile_rects); dev_free(c->touched); dev_free(c->offsets);
-    dev_free(c->act_tmp); dev_free(c->offsets_ref); dev_free(c->d_nvalue);
-    for (int i = 0; i < 2; ++i) { dev_free(c->dkeys[i]); dev_free(c->dvals[i]); }
-    if (c->dsort_ws) cudaFree(c->dsort_ws);
-    if (c->scan_ws) cudaFree(c->scan_ws);
-    for (int i = 0; i < 2; ++i) { dev_free(c->keys[i]); dev_free(c->vals[i]); dev_free(c->t_target[i]); }
-    dev_free(c->staged);
-    if (c->sort_ws) cudaFree(c->sort_ws);
+    if (c->front_stream) cudaStreamSynchronize(c->front_stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    for (Ctx::ViewBufs& v : c->vb) {
+        dev_free(v.rec); dev_free(v.tile_rects); dev_free(v.touched); dev_free(v.offsets); dev_free(v.d_nvalue);
+        for (int i = 0; i < 2; ++i) { dev_free(v.dkeys[i]); dev_free(v.dvals[i]); dev_free(v.keys[i]); dev_free(v.vals[i]); }
+        if (v.dsort_ws) cudaFree(v.dsort_ws);
+        if (v.scan_ws) cudaFree(v.scan_ws);
+        if (v.sort_ws) cudaFree(v.sort_ws);
+        dev_free(v.tile_ranges); dev_free(v.tile_order); dev_free(v.d_ctl);
+        if (v.h_ctl) cudaFreeHost(v.h_ctl);
+        cudaEvent_t* evs[] = {&v.ev_ctl, &v.ev_front, &v.ev_back};
+        for (cudaEvent_t* e : evs) if (*e) cudaEventDestroy(*e);
+    }
+    dev_free(c->grad_rec); dev_free(c->act_tmp); dev_free(c->offsets_ref);
+    for (int i = 0; i < 2; ++i) dev_free(c->t_target[i]);
     if (c->cub_tmp) cudaFree(c->cub_tmp);
     dev_free(c->dbg_keys); dev_free(c->dbg_vals);
-    dev_free(c->tile_ranges); dev_free(c->tile_order); dev_free(c->out_color); dev_free(c->out_depth); dev_free(c->out_alpha); dev_free(c->out_last);
+    dev_free(c->out_color); dev_free(c->out_depth); dev_free(c->out_alpha); dev_free(c->out_last);
     dev_free(c->mapA); dev_free(c->mapB); dev_free(c->mapC); dev_free(c->cot_render); dev_free(c->partial);
-    dev_free(c->loss_accum); dev_free(c->d_ctl); dev_free(c->d_zero);
+    dev_free(c->loss_accum); dev_free(c->d_zero);
     dev_free(c->t_block); dev_free(c->t_accum);
-    if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_loss) cudaFreeHost(c->h_loss);
     for (auto& e : c->ev_pool) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
-    cudaEvent_t* evs[] = {&c->ev_ctl, &c->t_target_ready[0], &c->t_target_ready[1],
-                          &c->t_target_free[0], &c->t_target_free[1]};
+    cudaEvent_t* evs[] = {&c->t_target_ready[0], &c->t_target_ready[1], &c->t_target_free[0], &c->t_target_free[1], &c->ev_fork};
     for (cudaEvent_t* e : evs) if (*e) cudaEventDestroy(*e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->front_stream) cudaStreamDestroy(c->front_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -513,17 +560,28 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
             return GSB_ERR_CUDA;                                                            \
         }                                                                                   \
     } while (0)
+    int prio_lo = 0, prio_hi = 0;
+    CREATE_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // hi = numerically lowest = most urgent
     CREATE_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    CREATE_CHECK(cudaStreamCreateWithPriority(&c->front_stream, cudaStreamNonBlocking, prio_hi));
     CREATE_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CREATE_CHECK(cudaEventCreateWithFlags(&c->ev_ctl, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         CREATE_CHECK(cudaEventCreateWithFlags(&c->t_target_ready[i], cudaEventDisableTiming));
         CREATE_CHECK(cudaEventCreateWithFlags(&c->t_target_free[i], cudaEventDisableTiming));
     }
     const size_t P = (size_t)c->P;
-    CREATE_CHECK(dev_alloc(&c->tile_ranges, (size_t)c->numTiles * 2));
-    CREATE_CHECK(dev_alloc(&c->tile_order, (size_t)c->numTiles));
+    CREATE_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (Ctx::ViewBufs& v : c->vb) {
+        CREATE_CHECK(cudaEventCreateWithFlags(&v.ev_ctl, cudaEventDisableTiming));
+        CREATE_CHECK(cudaEventCreateWithFlags(&v.ev_front, cudaEventDisableTiming));
+        CREATE_CHECK(cudaEventCreateWithFlags(&v.ev_back, cudaEventDisableTiming));
+        CREATE_CHECK(dev_alloc(&v.tile_ranges, (size_t)c->numTiles * 2));
+        CREATE_CHECK(dev_alloc(&v.tile_order, (size_t)c->numTiles));
+        CREATE_CHECK(dev_alloc(&v.d_ctl, 4));
+        CREATE_CHECK(dev_alloc(&v.d_nvalue, 4));
+        CREATE_CHECK(cudaMallocHost(reinterpret_cast<void**>(&v.h_ctl), 4 * sizeof(uint32_t)));
+    }
     CREATE_CHECK(dev_alloc(&c->out_color, P * 3));
     CREATE_CHECK(dev_alloc(&c->out_depth, P));
     CREATE_CHECK(dev_alloc(&c->out_alpha, P));
@@ -534,14 +592,11 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
     CREATE_CHECK(dev_alloc(&c->cot_render, P * 3));
     CREATE_CHECK(dev_alloc(&c->partial, 2));
     CREATE_CHECK(dev_alloc(&c->loss_accum, 4));
-    CREATE_CHECK(dev_alloc(&c->d_ctl, 4));
     CREATE_CHECK(dev_alloc(&c->d_zero, 4));
-    CREATE_CHECK(dev_alloc(&c->d_nvalue, 4));
     c->d_one = c->d_zero + 1;
     const uint32_t zo[4] = {0u, 1u, 0u, 0u};
     CREATE_CHECK(cudaMemcpy(c->d_zero, zo, sizeof(zo), cudaMemcpyHostToDevice));
     CREATE_CHECK(cudaMemset(c->loss_accum, 0, 4 * sizeof(float)));
-    CREATE_CHECK(cudaMallocHost(reinterpret_cast<void**>(&c->h_ctl), 4 * sizeof(uint32_t)));
     CREATE_CHECK(cudaMallocHost(reinterpret_cast<void**>(&c->h_loss), 4 * sizeof(float)));
 #undef CREATE_CHECK
     if (cfg->max_gaussians > 0) {
@@ -557,8 +612,16 @@ void gsb_destroy(gsb_ctx* ctx) { gsb::destroy_ctx(C(ctx)); }
 int gsb_set_stream(gsb_ctx* ctx, void* cuda_stream)
 {
     CTX_PROLOGUE(ctx);
-    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    gsb::sync_all_streams(c);
     c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : cudaStreamLegacy;
+    return GSB_OK;
+}
+
+int gsb_set_flags(gsb_ctx* ctx, int32_t flags)
+{
+    CTX_PROLOGUE(ctx);
+    gsb::sync_all_streams(c);
+    c->cfg.flags = flags;
     return GSB_OK;
 }
 
@@ -566,6 +629,7 @@ int gsb_synchronize(gsb_ctx* ctx)
 {
     CTX_PROLOGUE(ctx);
     GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->front_stream));
     return GSB_OK;
 }
 
@@ -643,26 +707,27 @@ int gsb_bin(gsb_ctx* ctx, int32_t N, const float* rect_min, const float* rect_ma
     int rc = gsb::ensure_gaussians(c, N);
     if (rc != GSB_OK) return rc;
     const gsb::ViewParams vp = gsb::make_view_nocam(c);
+    Ctx::ViewBufs& v = c->vb[c->cur];
     c->saved.valid = false;
     // keep a private copy of the depths: gsb_bin_read rebuilds the reference's sortedKeysLow from them
     if (N > 0) GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->act_tmp, depths, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-    GSB_CUDA_CHECK(c, gsb::launch_count_tiles(c->stream, N, vp, rect_min, rect_max, radii, c->act_tmp, c->tile_rects, c->touched,
-                                              c->dkeys[0]));
+    GSB_CUDA_CHECK(c, gsb::launch_count_tiles(c->stream, N, vp, rect_min, rect_max, radii, c->act_tmp, v.tile_rects, v.touched,
+                                              v.dkeys[0]));
     c->stats.kernel_launches += N > 0;
-    rc = gsb::run_binning(c, N, vp, c->act_tmp, 1, nullptr, true);
+    rc = gsb::run_binning(c, v, N, vp, c->act_tmp, 1, true);
     if (rc != GSB_OK) return rc;
     c->bin_valid = true;
     c->bin_vp = vp;
     if (tiles_touched && N > 0)
-        GSB_CUDA_CHECK(c, cudaMemcpyAsync(tiles_touched, c->touched, (size_t)N * 4, cudaMemcpyDeviceToDevice, c->stream));
+        GSB_CUDA_CHECK(c, cudaMemcpyAsync(tiles_touched, v.touched, (size_t)N * 4, cudaMemcpyDeviceToDevice, c->stream));
     if (tile_ranges)
-        GSB_CUDA_CHECK(c, cudaMemcpyAsync(tile_ranges, c->tile_ranges, (size_t)c->numTiles * 8, cudaMemcpyDeviceToDevice, c->stream));
+        GSB_CUDA_CHECK(c, cudaMemcpyAsync(tile_ranges, v.tile_ranges, (size_t)c->numTiles * 8, cudaMemcpyDeviceToDevice, c->stream));
     if (tile_counts) {
-        GSB_CUDA_CHECK(c, gsb::launch_tile_counts(c->stream, c->numTiles, c->tile_ranges, tile_counts));
+        GSB_CUDA_CHECK(c, gsb::launch_tile_counts(c->stream, c->numTiles, v.tile_ranges, tile_counts));
         c->stats.kernel_launches += 1;
     }
-    if (host_M) *host_M = c->last_M;
-    c->stats.pairs_last_view = c->last_M;
+    if (host_M) *host_M = v.last_M;
+    c->stats.pairs_last_view = v.last_M;
     return GSB_OK;
 }
 
@@ -671,7 +736,8 @@ int gsb_bin_read(gsb_ctx* ctx, uint32_t* keys_high, uint32_t* keys_low, uint32_t
 {
     CTX_PROLOGUE(ctx);
     if (!c->bin_valid && !c->saved.valid) { gsb::set_error(c, "gsb_bin_read: no binning result on this context"); return GSB_ERR_STATE; }
-    const uint32_t M = c->last_M;
+    Ctx::ViewBufs& v = c->vb[c->cur];
+    const uint32_t M = v.last_M;
     if (M == 0) return GSB_OK;
     if (keys_high || keys_low || gauss_idx) {
         if (!c->dbg_keys) { gsb::set_error(c, "gsb_bin_read: unsorted keys are only kept by gsb_bin"); return GSB_ERR_STATE; }
@@ -680,13 +746,13 @@ int gsb_bin_read(gsb_ctx* ctx, uint32_t* keys_high, uint32_t* keys_low, uint32_t
     }
     if (sorted_keys_high || sorted_keys_low || sorted_gauss_idx) {
         uint32_t buf = 0;
-        GSB_CUDA_CHECK(c, cudaMemcpyAsync(&c->h_ctl[2], c->d_result_buf, 4, cudaMemcpyDeviceToHost, c->stream));
+        GSB_CUDA_CHECK(c, cudaMemcpyAsync(&v.h_ctl[2], v.d_result_buf, 4, cudaMemcpyDeviceToHost, c->stream));
         GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-        buf = c->h_ctl[2];
-        GSB_CUDA_CHECK(c, gsb::launch_sorted_keys_out(c->stream, M, c->keys[buf], c->vals[buf], c->depth_src, c->depth_src_stride,
+        buf = v.h_ctl[2];
+        GSB_CUDA_CHECK(c, gsb::launch_sorted_keys_out(c->stream, M, v.keys[buf], v.vals[buf], v.depth_src, v.depth_src_stride,
                                                       sorted_keys_high, sorted_keys_low));
         if (sorted_gauss_idx)
-            GSB_CUDA_CHECK(c, cudaMemcpyAsync(sorted_gauss_idx, c->vals[buf], (size_t)M * 4, cudaMemcpyDeviceToDevice, c->stream));
+            GSB_CUDA_CHECK(c, cudaMemcpyAsync(sorted_gauss_idx, v.vals[buf], (size_t)M * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
     return GSB_OK;
 }
@@ -737,10 +803,10 @@ int gsb_sort_tile_keys(gsb_ctx* ctx, uint32_t M, uint32_t tile_bits, const uint3
             const uint32_t* d_res = nullptr;
             int launches = 0;
             if (e == cudaSuccess) e = gsb::launch_onesweep_sort(c->stream, plan, k[0], k[1], v[0], v[1], d_count, ws, &d_res, &launches);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(&c->h_ctl[2], d_res, 4, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&c->vb[0].h_ctl[2], d_res, 4, cudaMemcpyDeviceToHost, c->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
             if (e != cudaSuccess) { fail(e, "onesweep sort"); break; }
-            buf = c->h_ctl[2];
+            buf = c->vb[0].h_ctl[2];
             c->stats.kernel_launches += launches;
         }
         e = gsb::launch_split_keys(c->stream, M, k[buf], sorted_high, sorted_low);
@@ -761,7 +827,7 @@ static int restage_packed(Ctx* c, int32_t N, const float* packed)
 {
     if (!c->bin_valid && !c->saved.valid) { gsb::set_error(c, "raster: call gsb_bin (or gsb_render_forward) first"); return GSB_ERR_STATE; }
     if (N > c->capN) { gsb::set_error(c, "raster: N larger than the binned scene"); return GSB_ERR_INVALID; }
-    GSB_CUDA_CHECK(c, gsb::launch_packed_to_rec(c->stream, N, packed, c->rec));
+    GSB_CUDA_CHECK(c, gsb::launch_packed_to_rec(c->stream, N, packed, c->vb[c->cur].rec));
     c->stats.kernel_launches += 1;
     return GSB_OK;
 }
@@ -774,9 +840,10 @@ int gsb_raster_fwd(gsb_ctx* ctx, int32_t N, const float* packed, float* out_colo
     if (c->saved.valid) c->bin_vp = c->saved.vp;
     int rc = restage_packed(c, N, packed);
     if (rc != GSB_OK) return rc;
+    Ctx::ViewBufs& v = c->vb[c->cur];
     gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
-    GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, c->bin_vp, c->tile_ranges, c->tile_order, c->rec, c->vals[0], c->vals[1], c->d_result_buf, out_color, out_depth, out_alpha,
-                                             out_last_contrib));
+    GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, c->bin_vp, v.tile_ranges, v.tile_order, v.rec, v.vals[0], v.vals[1], v.d_result_buf, out_color, out_depth, out_alpha,
+                                             out_last_contrib, &v.d_ctl[3]));
     c->stats.kernel_launches += 1;
     return GSB_OK;
 }
@@ -791,11 +858,12 @@ int gsb_raster_bwd(gsb_ctx* ctx, int32_t N, const float* packed, const float* co
     if (c->saved.valid) c->bin_vp = c->saved.vp;
     int rc = restage_packed(c, N, packed);
     if (rc != GSB_OK) return rc;
+    Ctx::ViewBufs& v = c->vb[c->cur];
     GSB_CUDA_CHECK(c, cudaMemsetAsync(c->grad_rec, 0, (size_t)N * gsb::REC_FLOATS * 4, c->stream));
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, c->bin_vp, c->tile_ranges, c->tile_order, c->rec, c->vals[0], c->vals[1], c->d_result_buf, cot_color, cot_depth, cot_alpha,
-                                                 out_color, out_depth, out_alpha, last_contrib, c->grad_rec));
+        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, c->bin_vp, v.tile_ranges, v.tile_order, v.rec, v.vals[0], v.vals[1], v.d_result_buf, cot_color, cot_depth, cot_alpha,
+                                                 out_color, out_depth, out_alpha, last_contrib, c->grad_rec, &v.d_ctl[3]));
     }
     GSB_CUDA_CHECK(c, gsb::launch_rec_to_packed(c->stream, N, c->grad_rec, grad_packed));
     c->stats.kernel_launches += 2;
@@ -833,38 +901,61 @@ int gsb_ssim_bwd(gsb_ctx* ctx, int32_t H, int32_t W, int32_t Cn, const float* gr
 }
 
 // ---- fused renderer ------------------------------------------------------------------------------
-static int render_forward_impl(Ctx* c, int32_t N, const float* xyz, const float* f_dc, const float* f_rest,
-                               const float* scales_log, const float* rot_raw, const float* opacity_logit,
-                               const gsb::ViewParams& vp, float* radii, uint8_t* visibility, bool want_depth)
+struct RawParams {
+    const float *xyz, *f_dc, *f_rest, *scales_log, *rot_raw, *op_logit;
+};
+
+// projection (+ fused activations) and binning of one view into set v, enqueued on st
+static int enqueue_front(Ctx* c, Ctx::ViewBufs& v, cudaStream_t st, int32_t N, const RawParams& p, const gsb::ViewParams& vp,
+                         float* radii, uint8_t* visibility)
+{
+    {
+        gsb::StageTimer t(c, GSB_STAGE_PROJECT_FWD, st);
+        GSB_CUDA_CHECK(c, gsb::launch_project_fused_fwd(st, N, vp, p.xyz, p.f_dc, p.f_rest, p.scales_log, p.rot_raw, p.op_logit, v.rec,
+                                                        v.tile_rects, v.touched, v.dkeys[0], radii, visibility));
+        c->stats.kernel_launches += N > 0;
+    }
+    return gsb::enqueue_binning(c, v, st, N, vp, v.rec + 10, gsb::REC_FLOATS);
+}
+
+// K9 on the work stream from set v; marks the forward of this view as the saved one
+static int enqueue_raster_fwd(Ctx* c, Ctx::ViewBufs& v, int32_t N, const RawParams& p, const gsb::ViewParams& vp, bool want_depth)
+{
+    {
+        gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
+        GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, vp, v.tile_ranges, v.tile_order, v.rec, v.vals[0], v.vals[1], v.d_result_buf,
+                                                 c->out_color, want_depth ? c->out_depth : nullptr, c->out_alpha, c->out_last, &v.d_ctl[3]));
+        c->stats.kernel_launches += 1;
+    }
+    c->cur = (int)(&v - &c->vb[0]);
+    c->saved.valid = true;
+    c->saved.N = N;
+    c->saved.xyz = p.xyz; c->saved.f_dc = p.f_dc; c->saved.f_rest = p.f_rest; c->saved.scales_log = p.scales_log;
+    c->saved.rot_raw = p.rot_raw; c->saved.op_logit = p.op_logit;
+    c->saved.vp = vp;
+    c->bin_vp = vp;
+    c->stats.pairs_last_view = v.last_M;
+    c->stats.pairs_total += v.last_M;
+    c->stats.views += 1;
+    return GSB_OK;
+}
+
+static int render_forward_impl(Ctx* c, int32_t N, const RawParams& p, const gsb::ViewParams& vp, float* radii, uint8_t* visibility,
+                               bool want_depth)
 {
     int rc = gsb::ensure_gaussians(c, N);
     if (rc != GSB_OK) return rc;
     c->saved.valid = false;
     c->bin_valid = false;
-    {
-        gsb::StageTimer t(c, GSB_STAGE_PROJECT_FWD);
-        GSB_CUDA_CHECK(c, gsb::launch_project_fused_fwd(c->stream, N, vp, xyz, f_dc, f_rest, scales_log, rot_raw, opacity_logit,
-                                                        c->rec, c->tile_rects, c->touched, c->dkeys[0], radii, visibility));
-        c->stats.kernel_launches += N > 0;
+    Ctx::ViewBufs& v = c->vb[c->cur];
+    for (int attempt = 0;; ++attempt) {
+        rc = enqueue_front(c, v, c->stream, N, p, vp, radii, visibility);
+        if (rc != GSB_OK) return rc;
+        rc = gsb::finish_binning(c, v);
+        if (rc == GSB_OK) break;
+        if (rc != GSB_ERR_CAPACITY || attempt == 3) return rc;
     }
-    rc = gsb::run_binning(c, N, vp, c->rec + 10, gsb::REC_FLOATS, c->rec, false);
-    if (rc != GSB_OK) return rc;
-    {
-        gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, vp, c->tile_ranges, c->tile_order, c->rec, c->vals[0], c->vals[1], c->d_result_buf, c->out_color,
-                                                 want_depth ? c->out_depth : nullptr, c->out_alpha, c->out_last));
-        c->stats.kernel_launches += 1;
-    }
-    c->saved.valid = true;
-    c->saved.N = N;
-    c->saved.xyz = xyz; c->saved.f_dc = f_dc; c->saved.f_rest = f_rest; c->saved.scales_log = scales_log;
-    c->saved.rot_raw = rot_raw; c->saved.op_logit = opacity_logit;
-    c->saved.vp = vp;
-    c->bin_vp = vp;
-    c->stats.pairs_last_view = c->last_M;
-    c->stats.pairs_total += c->last_M;
-    c->stats.views += 1;
-    return GSB_OK;
+    return enqueue_raster_fwd(c, v, N, p, vp, want_depth);
 }
 
 static int render_backward_impl(Ctx* c, const float* cot_render, const float* cot_depth, const float* cot_alpha, float* g_xyz,
@@ -874,11 +965,12 @@ static int render_backward_impl(Ctx* c, const float* cot_render, const float* co
     if (!c->saved.valid) { gsb::set_error(c, "gsb_render_backward: no forward saved on this context"); return GSB_ERR_STATE; }
     const int N = c->saved.N;
     const gsb::ViewParams& vp = c->saved.vp;
+    Ctx::ViewBufs& v = c->vb[c->cur];
     GSB_CUDA_CHECK(c, cudaMemsetAsync(c->grad_rec, 0, (size_t)N * gsb::REC_FLOATS * 4, c->stream));
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, vp, c->tile_ranges, c->tile_order, c->rec, c->vals[0], c->vals[1], c->d_result_buf, cot_render, cot_depth, cot_alpha,
-                                                 c->out_color, c->out_depth, c->out_alpha, c->out_last, c->grad_rec));
+        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, vp, v.tile_ranges, v.tile_order, v.rec, v.vals[0], v.vals[1], v.d_result_buf, cot_render, cot_depth, cot_alpha,
+                                                 c->out_color, c->out_depth, c->out_alpha, c->out_last, c->grad_rec, &v.d_ctl[3]));
     }
     {
         gsb::StageTimer t(c, GSB_STAGE_PROJECT_BWD);
@@ -899,7 +991,8 @@ int gsb_render_forward(gsb_ctx* ctx, int32_t N, const float* xyz, const float* f
     GSB_REQUIRE(c, N >= 0 && xyz && f_dc && (f_rest || c->cfg.sh_coeffs == 1) && scales_log && rot_raw && opacity_logit && host_cam,
                 "gsb_render_forward: null argument");
     const gsb::ViewParams vp = gsb::make_view(c, host_cam);
-    int rc = render_forward_impl(c, N, xyz, f_dc, f_rest, scales_log, rot_raw, opacity_logit, vp, radii, visibility, depth != nullptr);
+    const RawParams rp{xyz, f_dc, f_rest, scales_log, rot_raw, opacity_logit};
+    int rc = render_forward_impl(c, N, rp, vp, radii, visibility, depth != nullptr);
     if (rc != GSB_OK) return rc;
     const size_t P = (size_t)c->P;
     if (render) GSB_CUDA_CHECK(c, cudaMemcpyAsync(render, c->out_color, P * 12, cudaMemcpyDeviceToDevice, c->stream));
@@ -1053,14 +1146,53 @@ int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
         int rc = prefetch(0);
         if (rc != GSB_OK) return rc;
     }
+    // View pipeline: projection + binning ("front") of view b+1 run on the high-priority front stream into the
+    // other buffer set while the FP32-bound rasteriser / loss / backward kernels ("back") of view b occupy the
+    // work stream.  The front is HBM/latency-bound integer work, so it fills issue slots the back leaves idle.
+    const RawParams rp{c->t_p[0], c->t_p[1], c->t_p[2], c->t_p[3], c->t_p[4], c->t_p[5]};
+    const bool overlap = B >= 2 && !(c->cfg.flags & (GSB_FLAG_SORT_CUB | GSB_FLAG_NO_OVERLAP));
+    c->saved.valid = false;
+    c->bin_valid = false;
+    if (overlap) {   // the front stream must see everything already queued on the work stream (Adam of the last step)
+        GSB_CUDA_CHECK(c, cudaEventRecord(c->ev_fork, c->stream));
+        GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->front_stream, c->ev_fork, 0));
+    }
+    int front_issued = -1;
+    auto issue_front = [&](int b) -> int {
+        Ctx::ViewBufs& v = c->vb[b & 1];
+        const gsb::ViewParams vp = gsb::make_view(c, &host_cams[b]);
+        cudaStream_t st = overlap ? c->front_stream : c->stream;
+        if (overlap) GSB_CUDA_CHECK(c, cudaStreamWaitEvent(st, v.ev_back, 0));   // set free again
+        int rc = enqueue_front(c, v, st, N, rp, vp, nullptr, nullptr);
+        if (rc != GSB_OK) return rc;
+        if (overlap) GSB_CUDA_CHECK(c, cudaEventRecord(v.ev_front, st));
+        front_issued = b;
+        return GSB_OK;
+    };
     for (int b = 0; b < B; ++b) {
         GSB_REQUIRE(c, host_targets[b] != nullptr, "gsb_trainer_accumulate: null target");
         if (targets_on_host && b + 1 < B) {
             int rc = prefetch(b + 1);
             if (rc != GSB_OK) return rc;
         }
+        Ctx::ViewBufs& v = c->vb[b & 1];
+        for (int attempt = 0;; ++attempt) {
+            int rc = GSB_OK;
+            if (front_issued < b) rc = issue_front(b);
+            if (rc == GSB_OK && overlap && b + 1 < B && front_issued < b + 1) rc = issue_front(b + 1);
+            if (rc != GSB_OK) return rc;
+            rc = gsb::finish_binning(c, v);
+            if (rc == GSB_OK) break;
+            if (rc != GSB_ERR_CAPACITY || attempt == 3) return rc;
+            front_issued = b - 1;   // the regrow synchronised and reallocated both sets: redo what was in flight
+            if (overlap) {
+                GSB_CUDA_CHECK(c, cudaEventRecord(c->ev_fork, c->stream));
+                GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->front_stream, c->ev_fork, 0));
+            }
+        }
         const gsb::ViewParams vp = gsb::make_view(c, &host_cams[b]);
-        int rc = render_forward_impl(c, N, c->t_p[0], c->t_p[1], c->t_p[2], c->t_p[3], c->t_p[4], c->t_p[5], vp, nullptr, nullptr, false);
+        if (overlap) GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, v.ev_front, 0));
+        int rc = enqueue_raster_fwd(c, v, N, rp, vp, false);
         if (rc != GSB_OK) return rc;
         const float* target = host_targets[b];
         if (targets_on_host) {
@@ -1074,6 +1206,7 @@ int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
         rc = render_backward_impl(c, c->cot_render, nullptr, nullptr, c->t_g[0], c->t_g[1], c->t_g[2], c->t_g[3], c->t_g[4],
                                   c->t_g[5], accumulate);
         if (rc != GSB_OK) return rc;
+        if (overlap) GSB_CUDA_CHECK(c, cudaEventRecord(v.ev_back, c->stream));
     }
     if (host_loss) {
         GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->h_loss, c->loss_accum, sizeof(float), cudaMemcpyDeviceToHost, c->stream));

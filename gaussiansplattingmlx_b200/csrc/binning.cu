@@ -665,32 +665,37 @@ cudaError_t launch_ranges_gather(cudaStream_t st, const ViewParams& vp, const ui
 // Heavy tiles first: tile ids sorted by descending list length (counting sort over 1024 length buckets,
 // one CTA).  The rasterisers map blockIdx -> order[blockIdx], so the longest lists start in the first
 // wave and the tail of the launch is made of short ones.
-__global__ void __launch_bounds__(1024) k_tile_order(int numTiles, const uint32_t* __restrict__ ranges, uint32_t* __restrict__ order)
+constexpr int TO_THREADS = 256;   // small footprint: this kernel must fit beside the resident rasteriser CTAs of the previous view
+constexpr int TO_BUCKETS = 1024;
+__global__ void __launch_bounds__(TO_THREADS) k_tile_order(int numTiles, const uint32_t* __restrict__ ranges, uint32_t* __restrict__ order)
 {
-    __shared__ uint32_t s_hist[1024];
-    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_hist[TO_BUCKETS];
+    __shared__ uint32_t s_warp[TO_THREADS / 32];
     __shared__ uint32_t s_max;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto count_of = [&](int t) { uint32_t a = ranges[t * 2], b = ranges[t * 2 + 1]; return b > a ? b - a : 0u; };
     uint32_t mx = 0;
-    for (int t = tid; t < numTiles; t += 1024) mx = max(mx, count_of(t));
+    for (int t = tid; t < numTiles; t += TO_THREADS) mx = max(mx, count_of(t));
     mx = __reduce_max_sync(0xffffffffu, mx);
     if (lane == 0) s_warp[warp] = mx;
-    s_hist[tid] = 0;
+    for (int i = tid; i < TO_BUCKETS; i += TO_THREADS) s_hist[i] = 0;
     __syncthreads();
     if (tid == 0) {
         uint32_t m = 0;
-        for (int w = 0; w < 32; ++w) m = max(m, s_warp[w]);
+        for (int w = 0; w < TO_THREADS / 32; ++w) m = max(m, s_warp[w]);
         s_max = m;
     }
     __syncthreads();
     const uint32_t maxc = max(s_max, 1u);
-    auto bucket_of = [&](uint32_t c) { return 1023u - (uint32_t)(((unsigned long long)c * 1023ull) / maxc); };
-    for (int t = tid; t < numTiles; t += 1024) atomicAdd(&s_hist[bucket_of(count_of(t))], 1u);
+    auto bucket_of = [&](uint32_t c) { return (uint32_t)(TO_BUCKETS - 1) - (uint32_t)(((unsigned long long)c * (TO_BUCKETS - 1)) / maxc); };
+    for (int t = tid; t < numTiles; t += TO_THREADS) atomicAdd(&s_hist[bucket_of(count_of(t))], 1u);
     __syncthreads();
-    // exclusive scan of the 1024 buckets
-    const uint32_t v = s_hist[tid];
-    uint32_t inc = v;
+    // exclusive scan of the buckets: thread tid owns buckets [4 tid, 4 tid + 4)
+    constexpr int PER = TO_BUCKETS / TO_THREADS;
+    uint32_t v[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] = s_hist[tid * PER + i]; sum += v[i]; }
+    uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
@@ -699,16 +704,17 @@ __global__ void __launch_bounds__(1024) k_tile_order(int numTiles, const uint32_
     __syncthreads();
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    uint32_t wprefix = 0;
-    for (int w = 0; w < warp; ++w) wprefix += s_warp[w];
-    s_hist[tid] = wprefix + inc - v;
+    uint32_t run = inc - sum;
+    for (int w = 0; w < warp; ++w) run += s_warp[w];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { s_hist[tid * PER + i] = run; run += v[i]; }
     __syncthreads();
-    for (int t = tid; t < numTiles; t += 1024) order[atomicAdd(&s_hist[bucket_of(count_of(t))], 1u)] = (uint32_t)t;
+    for (int t = tid; t < numTiles; t += TO_THREADS) order[atomicAdd(&s_hist[bucket_of(count_of(t))], 1u)] = (uint32_t)t;
 }
 
 cudaError_t launch_tile_order(cudaStream_t st, int numTiles, const uint32_t* tile_ranges, uint32_t* order)
 {
-    if (numTiles > 0) k_tile_order<<<1, 1024, 0, st>>>(numTiles, tile_ranges, order);
+    if (numTiles > 0) k_tile_order<<<1, TO_THREADS, 0, st>>>(numTiles, tile_ranges, order);
     return cudaGetLastError();
 }
 

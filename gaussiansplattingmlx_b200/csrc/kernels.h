@@ -101,13 +101,13 @@ cudaError_t launch_sorted_keys_out(cudaStream_t st, uint32_t M, const uint32_t* 
 cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
                               const uint32_t* tile_order, const float* rec, const uint32_t* vals0, const uint32_t* vals1,
                               const uint32_t* d_result_buf,
-                              float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last);
+                              float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last, uint32_t* work_counter);
 cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
                               const uint32_t* tile_order, const float* rec, const uint32_t* vals0, const uint32_t* vals1,
                               const uint32_t* d_result_buf,
                               const float* cot_color, const float* cot_depth, const float* cot_alpha,
                               const float* out_color, const float* out_depth, const float* out_alpha,
-                              const uint32_t* last_contrib, float* grad_rec);
+                              const uint32_t* last_contrib, float* grad_rec, uint32_t* work_counter);
 
 cudaError_t launch_sum_u32(cudaStream_t st, size_t n, const uint32_t* v, unsigned long long* out);
 

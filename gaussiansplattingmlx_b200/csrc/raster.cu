@@ -19,6 +19,8 @@
 //     of once per 32, and there is no cross-warp reduction at all.  One vector red per (block,
 //     Gaussian, quad) then goes to L2.
 // Work per evaluation: forward 27 flop + 1 ex2; backward ~80 flop + 1 ex2 + 1 rcp.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "kernels.h"
@@ -40,13 +42,13 @@ struct BlockMap {
     int tile, x0, y0;   // pixel origin of the 16x16 block
     int xmax, ymax;     // exclusive pixel bounds of the tile clipped to the image
 };
-__device__ __forceinline__ BlockMap map_block(const ViewParams& vp, const uint32_t* __restrict__ tile_order)
+__device__ __forceinline__ BlockMap map_block(const ViewParams& vp, const uint32_t* __restrict__ tile_order, uint32_t work)
 {
     const int subX = (vp.tileW + 15) >> 4, subY = (vp.tileH + 15) >> 4;
     const int per = subX * subY;
     BlockMap m;
-    const int slot = blockIdx.x / per;
-    const int sb = blockIdx.x - slot * per;
+    const int slot = (int)work / per;
+    const int sb = (int)work - slot * per;
     m.tile = (int)tile_order[slot];   // heavy tiles first (binning.cu k_tile_order)
     const int tileX = m.tile % vp.gridW, tileY = m.tile / vp.gridW;
     m.x0 = tileX * vp.tileW + (sb % subX) * 16;
@@ -103,6 +105,11 @@ __device__ __forceinline__ float fwd_alpha_rt(const FwdExp& e, int r)
     }
 }
 
+// Persistent: the grid is (SM count x resident CTAs per SM); a CTA pulls 16x16 blocks from a device counter in
+// heavy-first order until none is left (dynamic balancing of the tail; 8160 block launches become 1776).
+// The trainer runs the projection/binning kernels of the NEXT view concurrently on a second stream (api.cu);
+// measured on B200, capping the residency below the register limit to leave them room does not pay
+// (tools/sweep_res.sh: 12/16 CTAs per SM beats 9/12), so the defaults fill the SM.
 template <bool DEPTH>
 __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ ViewParams vp,
                                                        const uint32_t* __restrict__ tile_ranges,
@@ -111,154 +118,172 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
                                                        const uint32_t* __restrict__ vals1,
                                                        const uint32_t* __restrict__ d_result_buf, float* __restrict__ out_color,
                                                        float* __restrict__ out_depth, float* __restrict__ out_alpha,
-                                                       uint32_t* __restrict__ out_last)
+                                                       uint32_t* __restrict__ out_last, uint32_t* __restrict__ work_counter,
+                                                       uint32_t total_work)
 {
     __shared__ __align__(128) float4 s_rec[2][RB_FWD * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
-    const BlockMap bm = map_block(vp, tile_order);
+    __shared__ uint32_t s_work;
     const int tid = threadIdx.x;
-    const int pxi = bm.x0 + (tid & 15), py0 = bm.y0 + (tid >> 4) * FPPT;
-    const uint32_t start = tile_ranges[bm.tile * 2], end = tile_ranges[bm.tile * 2 + 1];
-    const uint32_t count = end > start ? end - start : 0u;
-    const int nb = (int)((count + RB_FWD - 1) / RB_FWD);
-
     if (tid == 0) {
         mbar_init(&s_bar[0], RT);
         mbar_init(&s_bar[1], RT);
         mbar_fence_init();
     }
-    __syncthreads();
-    // Gather staging: the tile's list is (tile_ranges, sorted Gaussian indices); every thread pulls RB_FWD / RT
-    // 48-byte records of the next batch from the (L2-resident) record table straight into shared memory with
-    // 16-byte async copies that complete on the batch's mbarrier.  Indices are prefetched two batches ahead.
-    // Slots past the end of the list (up to the next chunk boundary) are filled with a null record
-    // (log2(opacity) = -inf => alpha = +0), so the blend loop always runs whole chunks.
     const uint32_t* __restrict__ vals = (*d_result_buf) ? vals1 : vals0;
-    constexpr int SLOTS = RB_FWD / RT;
-    uint32_t idx_next[SLOTS];
-    auto load_idx = [&](int b) {
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const uint32_t j = (uint32_t)b * RB_FWD + s * RT + tid;
-            idx_next[s] = (b < nb && j < count) ? vals[start + j] : 0xffffffffu;
-        }
-    };
-    auto issue = [&](int b) {
-        uint64_t* bar = &s_bar[b & 1];
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            float4* dst = &s_rec[b & 1][(s * RT + tid) * 3];
-            if (idx_next[s] != 0xffffffffu) {
-                const float4* src = rec + (size_t)idx_next[s] * 3;
-                cp_async16(dst, src);
-                cp_async16(dst + 1, src + 1);
-                cp_async16(dst + 2, src + 2);
-            } else {
-                dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                dst[1] = make_float4(0.f, __int_as_float(0xff800000), 0.f, 0.f);
-                dst[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        cp_async_mbar_arrive_noinc(bar);   // fires when this thread's copies have landed
-    };
-    load_idx(0);
-    if (nb > 0) issue(0);
-    load_idx(1);
-    __syncthreads();   // null-record fills of batch 0 are plain shared stores
-
-    const float pxf = (float)pxi, pyf = (float)py0;
-    float cx[FPPT], cy[FPPT], cz[FPPT], dep[FPPT], T[FPPT], Ts[FPPT];
-    uint32_t ci[FPPT];
-    bool active[FPPT];
-#pragma unroll
-    for (int r = 0; r < FPPT; ++r) {
-        active[r] = pxi < bm.xmax && py0 + r < bm.ymax;
-        cx[r] = cy[r] = cz[r] = dep[r] = 0.f;
-        T[r] = active[r] ? 1.0f : 0.0f;   // T == 0  <=>  this pixel is finished (terminated or outside)
-        Ts[r] = 0.f;
-        ci[r] = 0u;
-    }
     const uint32_t rec_base = smem_u32(&s_rec[0][0]);
-    bool warp_done = false;
+    uint32_t seq = 0;   // batches staged so far by this CTA: stage = seq & 1, mbarrier parity = (seq >> 1) & 1
 
-    // one Gaussian for the thread's FPPT pixels: slang/gaussian_tile_global_kernels.slang:437-499
-    auto blend = [&](uint32_t addr) {
-        const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
-        const FwdExp e = fwd_exponents(a, q.x, q.y, pxf, pyf);
-        auto px = [&](int r, float alpha) {
-            const float contrib = T[r] * alpha;
-            cx[r] = fmaf(contrib, q.z, cx[r]);
-            cy[r] = fmaf(contrib, q.w, cy[r]);
-            cz[r] = fmaf(contrib, c.x, cz[r]);
-            if (DEPTH) dep[r] = fmaf(contrib, c.z, dep[r]);
-            const float Tn = fmaf(-T[r], alpha, T[r]);
-            T[r] = Tn < 1e-4f ? 0.0f : Tn;   // the terminating Gaussian is included (:599-603)
+    for (;;) {
+        __syncthreads();   // previous block fully consumed (also orders the mbarrier init before first use)
+        if (tid == 0) s_work = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t work = s_work;
+        if (work >= total_work) break;
+        const BlockMap bm = map_block(vp, tile_order, work);
+        const int pxi = bm.x0 + (tid & 15), py0 = bm.y0 + (tid >> 4) * FPPT;
+        const uint32_t start = tile_ranges[bm.tile * 2], end = tile_ranges[bm.tile * 2 + 1];
+        const uint32_t count = end > start ? end - start : 0u;
+        const int nb = (int)((count + RB_FWD - 1) / RB_FWD);
+
+        // Gather staging: the tile's list is (tile_ranges, sorted Gaussian indices); every thread pulls RB_FWD / RT
+        // 48-byte records of the next batch from the (L2-resident) record table straight into shared memory with
+        // 16-byte async copies that complete on the batch's mbarrier.  Indices are prefetched two batches ahead.
+        // Slots past the end of the list (up to the next chunk boundary) are filled with a null record
+        // (log2(opacity) = -inf => alpha = +0), so the blend loop always runs whole chunks.
+        constexpr int SLOTS = RB_FWD / RT;
+        uint32_t idx_next[SLOTS];
+        auto load_idx = [&](int b) {
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const uint32_t j = (uint32_t)b * RB_FWD + s * RT + tid;
+                idx_next[s] = (b < nb && j < count) ? vals[start + j] : 0xffffffffu;
+            }
         };
-        px(0, fwd_alpha<0>(e));
-        px(1, fwd_alpha<1>(e));
-        px(2, fwd_alpha<2>(e));
-        px(3, fwd_alpha<3>(e));
-    };
+        auto issue = [&](int b) {
+            const uint32_t sq = seq + (uint32_t)b;
+            uint64_t* bar = &s_bar[sq & 1];
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                float4* dst = &s_rec[sq & 1][(s * RT + tid) * 3];
+                if (idx_next[s] != 0xffffffffu) {
+                    const float4* src = rec + (size_t)idx_next[s] * 3;
+                    cp_async16(dst, src);
+                    cp_async16(dst + 1, src + 1);
+                    cp_async16(dst + 2, src + 2);
+                } else {
+                    dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    dst[1] = make_float4(0.f, __int_as_float(0xff800000), 0.f, 0.f);
+                    dst[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            cp_async_mbar_arrive_noinc(bar);   // fires when this thread's copies have landed
+        };
+        load_idx(0);
+        if (nb > 0) issue(0);
+        load_idx(1);
+        __syncthreads();   // null-record fills of batch 0 are plain shared stores
 
-    for (int b = 0; b < nb; ++b) {
-        if (b + 1 < nb) issue(b + 1);
-        load_idx(b + 2);
-        mbar_wait(&s_bar[b & 1], (uint32_t)(b >> 1) & 1u);
-        if (!warp_done) {
-            const int n = (int)min((uint32_t)RB_FWD, count - (uint32_t)b * RB_FWD);
-            uint32_t addr = rec_base + (uint32_t)(b & 1) * (RB_FWD * 48u);
-            uint32_t chunk = (uint32_t)b * (RB_FWD / FCHUNK);
-            for (int j = 0; j < n; j += FCHUNK, addr += FCHUNK * 48u, ++chunk) {
-                // remember where (and with which transmittance) each live pixel entered this chunk
+        const float pxf = (float)pxi, pyf = (float)py0;
+        float cx[FPPT], cy[FPPT], cz[FPPT], dep[FPPT], T[FPPT], Ts[FPPT];
+        uint32_t ci[FPPT];
+        bool active[FPPT];
 #pragma unroll
-                for (int r = 0; r < FPPT; ++r) {
-                    const bool live = T[r] != 0.0f;
-                    Ts[r] = live ? T[r] : Ts[r];
-                    ci[r] = live ? chunk : ci[r];
+        for (int r = 0; r < FPPT; ++r) {
+            active[r] = pxi < bm.xmax && py0 + r < bm.ymax;
+            cx[r] = cy[r] = cz[r] = dep[r] = 0.f;
+            T[r] = active[r] ? 1.0f : 0.0f;   // T == 0  <=>  this pixel is finished (terminated or outside)
+            Ts[r] = 0.f;
+            ci[r] = 0u;
+        }
+        bool warp_done = false;
+
+        // one Gaussian for the thread's FPPT pixels: slang/gaussian_tile_global_kernels.slang:437-499
+        auto blend = [&](uint32_t addr) {
+            const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
+            const FwdExp e = fwd_exponents(a, q.x, q.y, pxf, pyf);
+            auto px = [&](int r, float alpha) {
+                const float contrib = T[r] * alpha;
+                cx[r] = fmaf(contrib, q.z, cx[r]);
+                cy[r] = fmaf(contrib, q.w, cy[r]);
+                cz[r] = fmaf(contrib, c.x, cz[r]);
+                if (DEPTH) dep[r] = fmaf(contrib, c.z, dep[r]);
+                const float Tn = fmaf(-T[r], alpha, T[r]);
+                T[r] = Tn < 1e-4f ? 0.0f : Tn;   // the terminating Gaussian is included (:599-603)
+            };
+            px(0, fwd_alpha<0>(e));
+            px(1, fwd_alpha<1>(e));
+            px(2, fwd_alpha<2>(e));
+            px(3, fwd_alpha<3>(e));
+        };
+
+        int b = 0;
+        for (; b < nb; ++b) {
+            if (b + 1 < nb) issue(b + 1);
+            load_idx(b + 2);
+            const uint32_t sq = seq + (uint32_t)b;
+            mbar_wait(&s_bar[sq & 1], (sq >> 1) & 1u);
+            if (!warp_done) {
+                const int n = (int)min((uint32_t)RB_FWD, count - (uint32_t)b * RB_FWD);
+                uint32_t addr = rec_base + (sq & 1u) * (RB_FWD * 48u);
+                uint32_t chunk = (uint32_t)b * (RB_FWD / FCHUNK);
+                for (int j = 0; j < n; j += FCHUNK, addr += FCHUNK * 48u, ++chunk) {
+                    // remember where (and with which transmittance) each live pixel entered this chunk
+#pragma unroll
+                    for (int r = 0; r < FPPT; ++r) {
+                        const bool live = T[r] != 0.0f;
+                        Ts[r] = live ? T[r] : Ts[r];
+                        ci[r] = live ? chunk : ci[r];
+                    }
+#pragma unroll
+                    for (int g = 0; g < FCHUNK; ++g) blend(addr + g * 48u);
+                    const float tmax = fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3]));
+                    if (__all_sync(0xffffffffu, tmax == 0.0f)) { warp_done = true; break; }
                 }
-#pragma unroll
-                for (int g = 0; g < FCHUNK; ++g) blend(addr + g * 48u);
-                const float tmax = fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3]));
-                if (__all_sync(0xffffffffu, tmax == 0.0f)) { warp_done = true; break; }
+            }
+            // releases the stage buffer for the copy issued two batches later, and votes on early exit
+            if (__syncthreads_and(warp_done)) {
+                if (b + 1 < nb) {   // drain the in-flight copy
+                    mbar_wait(&s_bar[(sq + 1) & 1], ((sq + 1) >> 1) & 1u);
+                    ++b;
+                }
+                ++b;
+                break;
             }
         }
-        // releases the stage buffer for the copy issued two batches later, and votes on early exit
-        if (__syncthreads_and(warp_done)) {
-            if (b + 1 < nb) mbar_wait(&s_bar[(b + 1) & 1], (uint32_t)((b + 1) >> 1) & 1u);  // drain the in-flight copy
-            break;
-        }
-    }
-    // epilogue: exact lastContrib / transmittance at termination, then the outputs
+        seq += (uint32_t)b;   // batches actually staged (and waited for) in this block
+        // epilogue: exact lastContrib / transmittance at termination, then the outputs
 #pragma unroll
-    for (int r = 0; r < FPPT; ++r) {
-        if (!active[r]) continue;
-        float Tend = T[r];
-        uint32_t nContrib = count;
-        if (Tend == 0.0f) {
-            float t = Ts[r];
-            uint32_t i = ci[r] * FCHUNK;
-            for (int g = 0; g < FCHUNK && i < count; ++g, ++i) {
-                const float4* src = rec + (size_t)vals[start + i] * 3;
-                const float4 a = __ldg(src), q = __ldg(src + 1);
-                const FwdExp e = fwd_exponents(a, q.x, q.y, pxf, pyf);
-                const float alpha = fwd_alpha_rt(e, r);
-                const float Tn = fmaf(-t, alpha, t);
-                if (Tn < 1e-4f) {
-                    nContrib = i + 1u;
-                    Tend = Tn;
-                    break;
+        for (int r = 0; r < FPPT; ++r) {
+            if (!active[r]) continue;
+            float Tend = T[r];
+            uint32_t nContrib = count;
+            if (Tend == 0.0f) {
+                float t = Ts[r];
+                uint32_t i = ci[r] * FCHUNK;
+                for (int g = 0; g < FCHUNK && i < count; ++g, ++i) {
+                    const float4* src = rec + (size_t)vals[start + i] * 3;
+                    const float4 a = __ldg(src), q = __ldg(src + 1);
+                    const FwdExp e = fwd_exponents(a, q.x, q.y, pxf, pyf);
+                    const float alpha = fwd_alpha_rt(e, r);
+                    const float Tn = fmaf(-t, alpha, t);
+                    if (Tn < 1e-4f) {
+                        nContrib = i + 1u;
+                        Tend = Tn;
+                        break;
+                    }
+                    t = Tn;
                 }
-                t = Tn;
             }
+            const size_t p = (size_t)(py0 + r) * vp.W + pxi;
+            const float bg = vp.whiteBg ? Tend : 0.0f;
+            out_color[p * 3 + 0] = cx[r] + bg;
+            out_color[p * 3 + 1] = cy[r] + bg;
+            out_color[p * 3 + 2] = cz[r] + bg;
+            if (DEPTH) out_depth[p] = dep[r];
+            out_alpha[p] = 1.0f - Tend;
+            out_last[p] = nContrib;
         }
-        const size_t p = (size_t)(py0 + r) * vp.W + pxi;
-        const float bg = vp.whiteBg ? Tend : 0.0f;
-        out_color[p * 3 + 0] = cx[r] + bg;
-        out_color[p * 3 + 1] = cy[r] + bg;
-        out_color[p * 3 + 2] = cz[r] + bg;
-        if (DEPTH) out_depth[p] = dep[r];
-        out_alpha[p] = 1.0f - Tend;
-        out_last[p] = nContrib;
     }
 }
 
@@ -310,13 +335,29 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
                                                        const float* __restrict__ cot_color,
                                                        const float* __restrict__ cot_depth, const float* __restrict__ cot_alpha,
                                                        const float* __restrict__ out_alpha,
-                                                       const uint32_t* __restrict__ last_contrib, float* __restrict__ grad_rec)
+                                                       const uint32_t* __restrict__ last_contrib, float* __restrict__ grad_rec,
+                                                       uint32_t* __restrict__ work_counter, uint32_t total_work)
 {
     __shared__ __align__(128) float4 s_rec[2][RB_BWD * 3];
     __shared__ __align__(16) float s_out[RB_BWD][12];   // per-Gaussian sums of this block for one batch
     __shared__ __align__(8) uint64_t s_bar[2];
-    const BlockMap bm = map_block(vp, tile_order);
     const int lane = threadIdx.x;
+    if (lane == 0) {
+        mbar_init(&s_bar[0], GSB_GATHER_TMA ? 1 : 32);
+        mbar_init(&s_bar[1], GSB_GATHER_TMA ? 1 : 32);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const uint32_t* __restrict__ vals = (*d_result_buf) ? vals1 : vals0;
+    uint32_t seq = 0;   // batches staged so far by this CTA: stage = seq & 1, mbarrier parity = (seq >> 1) & 1
+    // persistent: one warp pulls 16x16 blocks (heavy tiles first) from a device counter; see k_raster_fwd
+    for (;;) {
+    __syncwarp();       // every lane is done with the previous block's shared memory
+    uint32_t work = 0;
+    if (lane == 0) work = atomicAdd(work_counter, 1u);
+    work = __shfl_sync(0xffffffffu, work, 0);
+    if (work >= total_work) break;
+    const BlockMap bm = map_block(vp, tile_order, work);
     const uint32_t start = tile_ranges[bm.tile * 2], end = tile_ranges[bm.tile * 2 + 1];
     const uint32_t count = end > start ? end - start : 0u;
 
@@ -349,17 +390,10 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
     // only Gaussians below the block-wide max nContrib can contribute
     const uint32_t used = __reduce_max_sync(0xffffffffu, nmax);
     const int nb = (int)((used + RB_BWD - 1) / RB_BWD);
-    if (nb == 0) return;
-    if (lane == 0) {
-        mbar_init(&s_bar[0], GSB_GATHER_TMA ? 1 : 32);
-        mbar_init(&s_bar[1], GSB_GATHER_TMA ? 1 : 32);
-        mbar_fence_init();
-    }
-    __syncwarp();
+    if (nb == 0) continue;
 
     // batches are visited last -> first; sequence number s = nb-1-b selects stage / parity
     // gather staging as in the forward: each lane pulls two 48-byte records per batch with TMA bulk copies
-    const uint32_t* __restrict__ vals = (*d_result_buf) ? vals1 : vals0;
     uint32_t ia = 0xffffffffu, ib = 0xffffffffu;   // indices of this lane's two slots of the next batch to issue
     auto load_idx = [&](int b) {
         const uint32_t j0 = (uint32_t)b * RB_BWD + lane, j1 = j0 + 32;
@@ -367,7 +401,7 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
         ib = (b >= 0 && j1 < used) ? vals[start + j1] : 0xffffffffu;
     };
     auto issue = [&](int b) {
-        const int s = nb - 1 - b;
+        const uint32_t s = seq + (uint32_t)(nb - 1 - b);
         uint64_t* bar = &s_bar[s & 1];
 #if GSB_GATHER_TMA
         if (lane == 0) mbar_expect_tx(bar, min((uint32_t)RB_BWD, used - (uint32_t)b * RB_BWD) * 48u);
@@ -398,7 +432,7 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
     const bool writer = !(lane & 1) && !(b2 && b1);
 
     for (int b = nb - 1; b >= 0; --b) {
-        const int s = nb - 1 - b;
+        const uint32_t s = seq + (uint32_t)(nb - 1 - b);
         __syncwarp();                               // every lane is done with the stage being refilled
         if (b > 0) issue(b - 1);
         load_idx(b - 2);
@@ -406,10 +440,10 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
             float4* z = reinterpret_cast<float4*>(&s_out[0][0]);
             for (int i = lane; i < RB_BWD * 3; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        mbar_wait(&s_bar[s & 1], (uint32_t)(s >> 1) & 1u);
+        mbar_wait(&s_bar[s & 1], (s >> 1) & 1u);
         __syncwarp();
         const int n = (int)min((uint32_t)RB_BWD, used - (uint32_t)b * RB_BWD);
-        const uint32_t stage_addr = rec_base + (uint32_t)(s & 1) * (RB_BWD * 48u);
+        const uint32_t stage_addr = rec_base + (s & 1u) * (RB_BWD * 48u);
         for (int j = n - 1; j >= 0; --j) {
             const uint32_t i = (uint32_t)(b * RB_BWD + j);
             if (!__any_sync(0xffffffffu, i < nmax)) continue;
@@ -495,6 +529,8 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8), "f"(s0.z), "f"(s1.x), "f"(s0.w), "f"(0.0f) : "memory");
         }
     }
+    seq += (uint32_t)nb;
+    }   // persistent loop
 }
 
 // sum of lastContrib over the image = number of (pixel, Gaussian) blend evaluations (bench statistics)
@@ -523,25 +559,46 @@ static int raster_blocks(const ViewParams& vp)
     return vp.gridW * vp.gridH * subX * subY;
 }
 
+// resident CTAs per SM of the persistent rasterisers (GSB_FWD_RES / GSB_BWD_RES override, for tuning)
+static int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+static int sm_count()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
                               const uint32_t* tile_order, const float* rec, const uint32_t* vals0, const uint32_t* vals1,
                               const uint32_t* d_result_buf,
-                              float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last)
+                              float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last, uint32_t* work_counter)
 {
     const int blocks = raster_blocks(vp);
     if (blocks > 0) {
-        static bool carveout_set = false;
-        if (!carveout_set) {
+        static int res = 0;
+        if (!res) {
             cudaFuncSetAttribute(k_raster_fwd<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_raster_fwd<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            carveout_set = true;
+            res = std::max(1, env_int("GSB_FWD_RES", 12));
         }
+        cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
+        const int grid = std::min(blocks, sm_count() * res);
         if (out_depth)
-            k_raster_fwd<true><<<blocks, RT, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
-                                                      d_result_buf, out_color, out_depth, out_alpha, out_last);
+            k_raster_fwd<true><<<grid, RT, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
+                                                    d_result_buf, out_color, out_depth, out_alpha, out_last, work_counter, (uint32_t)blocks);
         else
-            k_raster_fwd<false><<<blocks, RT, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
-                                                       d_result_buf, out_color, out_depth, out_alpha, out_last);
+            k_raster_fwd<false><<<grid, RT, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
+                                                     d_result_buf, out_color, out_depth, out_alpha, out_last, work_counter, (uint32_t)blocks);
     }
     return cudaGetLastError();
 }
@@ -551,23 +608,28 @@ cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint3
                               const uint32_t* d_result_buf,
                               const float* cot_color, const float* cot_depth, const float* cot_alpha,
                               const float* out_color, const float* out_depth, const float* out_alpha,
-                              const uint32_t* last_contrib, float* grad_rec)
+                              const uint32_t* last_contrib, float* grad_rec, uint32_t* work_counter)
 {
     (void)out_color; (void)out_depth;   // the colour/depth state is not needed by the gradients (see kernel)
     const int blocks = raster_blocks(vp);
     if (blocks > 0) {
-        static bool carveout_set = false;
-        if (!carveout_set) {
+        static int res = 0;
+        if (!res) {
             cudaFuncSetAttribute(k_raster_bwd<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_raster_bwd<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            carveout_set = true;
+            res = std::max(1, env_int("GSB_BWD_RES", 16));
         }
+        cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
+        const int grid = std::min(blocks, sm_count() * res);
         if (cot_depth)
-            k_raster_bwd<true><<<blocks, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
-                                                      d_result_buf, cot_color, cot_depth, cot_alpha, out_alpha, last_contrib, grad_rec);
+            k_raster_bwd<true><<<grid, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
+                                                    d_result_buf, cot_color, cot_depth, cot_alpha, out_alpha, last_contrib, grad_rec,
+                                                    work_counter, (uint32_t)blocks);
         else
-            k_raster_bwd<false><<<blocks, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
-                                                       d_result_buf, cot_color, cot_depth, cot_alpha, out_alpha, last_contrib, grad_rec);
+            k_raster_bwd<false><<<grid, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
+                                                     d_result_buf, cot_color, cot_depth, cot_alpha, out_alpha, last_contrib, grad_rec,
+                                                     work_counter, (uint32_t)blocks);
     }
     return cudaGetLastError();
 }

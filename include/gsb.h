@@ -60,6 +60,7 @@ typedef struct gsb_config {
 } gsb_config;
 
 #define GSB_FLAG_SORT_CUB 1       /* use the CUB baseline instead of the hand-written onesweep (checking only) */
+#define GSB_FLAG_NO_OVERLAP 2     /* trainer: run every view's kernels back to back on one stream (per-kernel timing) */
 
 /* Camera block = the 7 camera arrays of TrainStepInputIndex (GaussianTrainer.swift:254-272),
  * produced exactly as Trainer/CameraUtil.swift:5-102 does (row-vector convention, proj = P^T). */
@@ -82,6 +83,7 @@ GSB_API const char* gsb_last_error(const gsb_ctx* ctx);       /* ctx may be NULL
 GSB_API int gsb_set_stream(gsb_ctx* ctx, void* cuda_stream);  /* cudaStream_t; NULL = the legacy default stream.
                                                               * Before the first call a context uses a private non-blocking stream. */
 GSB_API int gsb_synchronize(gsb_ctx* ctx);
+GSB_API int gsb_set_flags(gsb_ctx* ctx, int32_t flags);      /* replaces gsb_config.flags (GSB_FLAG_*); synchronises */
 
 /* ---- activations: GaussianRenderer.get_*_from (GaussianRenderer.swift:936-963) -------------- */
 /* in : f_dc[N,1,3] f_rest[N,K-1,3] scales_log[N,3] rot_raw[N,4] opacity_logit[N,1]

@@ -304,6 +304,39 @@ def test_train_steps_vs_oracle(gsb, best_oracle):
     assert rel_err(tt["accum"].cpu().numpy(), acc_o) < GRAD_TOL
 
 
+def test_view_pipeline_matches_serial_and_regrows(gsb):
+    """The two-stream view pipeline of gsb_trainer_accumulate (front of view b+1 overlapping the back of view b)
+    must give the same steps as the serial schedule, including when the pair buffers overflow mid-batch."""
+    Context, L = gsb
+    from gaussiansplattingmlx_b200.camera import Camera
+    n, W, H = 40000, 160, 96
+    params = make_gaussians(n, 41, 3)
+    cams = make_cameras(W, H, 5)
+    c2w = np.linalg.inv(cams[0].worldViewTransform.astype(np.float64).T)
+    c2w[:3, 0] *= -1.0; c2w[:3, 2] *= -1.0                                            # look AWAY from the scene:
+    far = Camera(W, H, float(cams[0].focalX), float(cams[0].focalY), c2w)                # everything culled, M = 0
+    targets = make_targets(W, H, 5, 41)
+    out = {}
+    for flags in (0, L.GSB_FLAG_NO_OVERLAP):
+        ctx = Context(W, H, flags=flags)
+        ctx.trainer_init({k: torch.from_numpy(v) for k, v in params.items()})
+        tg = [torch.from_numpy(t).cuda() for t in targets]
+        losses = [ctx.train_step([L.make_camera(far)], tg[:1], 0, 100)]
+        cap0 = ctx.stats()["pair_capacity"]
+        losses += [ctx.train_step([L.make_camera(c) for c in cams], tg, it, 100) for it in (1, 2)]
+        cap1 = ctx.stats()["pair_capacity"]
+        assert cap1 > cap0, "the batch must have outgrown the first sizing (regrow path)"
+        tt = ctx.trainer_tensors()
+        out[flags] = (losses, {k: v.cpu().numpy().copy() for k, v in tt["params"].items()}, tt["accum"].cpu().numpy().copy())
+        ctx.close()
+    (la, pa, aa), (lb, pb, ab) = out[0], out[L.GSB_FLAG_NO_OVERLAP]
+    for x, y in zip(la, lb):
+        assert abs(x - y) < 1e-6
+    for k in pa:   # float atomics make the two runs differ in the last bits only
+        assert rel_err(pa[k] - params[k].reshape(pa[k].shape), pb[k] - params[k].reshape(pb[k].shape)) < 1e-3, k
+    assert rel_err(aa, ab) < 1e-4
+
+
 def test_empty_and_culled_scenes(gsb):
     Context, L = gsb
     cam = make_cameras(32, 32, 1)[0]
