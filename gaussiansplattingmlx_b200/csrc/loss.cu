@@ -48,10 +48,11 @@ __device__ __forceinline__ SsimPoint ssim_point(float mu1, float mu2, float e11,
     const float A = 2.0f * mu1 * mu2 + SSIM_C1, B = 2.0f * s12 + SSIM_C2;
     const float Cc = mu1 * mu1 + mu2 * mu2 + SSIM_C1, D = s1 + s2 + SSIM_C2;
     const float CD = Cc * D;
+    const float inv = 1.0f / CD;       // one IEEE division; the products below differ from (x / CD) by <= 1 ulp
     SsimPoint r;
-    r.ssim = (A * B) / CD;
-    const float gA = B / CD, gB = A / CD;
-    const float gCD = -(A * B) / (CD * CD);
+    r.ssim = (A * B) * inv;
+    const float gA = B * inv, gB = A * inv;
+    const float gCD = -r.ssim * inv;
     const float gC = gCD * D, gD = gCD * Cc;
     r.gs1 = gD;
     r.gs12 = 2.0f * gB;
@@ -62,17 +63,54 @@ __device__ __forceinline__ SsimPoint ssim_point(float mu1, float mu2, float e11,
 // ------------------------------------------------------------------------------------------------
 // Streaming separable convolution.  The HWC image is treated as H rows of W*C floats; a horizontal tap
 // k of the per-channel window sits at element offset (k - 5) * C.  A CTA owns a strip of SW consecutive
-// row elements and a chunk of SROWS output rows and marches down the rows: each input row is loaded once
-// into shared memory (strip + 5*C halo on both sides), filtered horizontally (11 taps) into a ring of
-// the last 11 filtered rows, and one output row is produced from the ring (11 vertical taps).  Compared
-// with 2-D tiles the halo overhead is 10 rows per SROWS-row chunk and 10*C floats per SW-float strip.
+// row elements and a chunk of SROWS output rows and marches down the rows.  Per input row:
+//   * the strip (+ 5*C halo on both sides) is staged in shared memory, one barrier per row (two row
+//     buffers alternate; row r+1 is fetched into registers while row r is filtered);
+//   * each thread filters its element horizontally (11 taps: the only shared-memory reads, 22 per
+//     output instead of the 77 of a shared-memory ring);
+//   * the vertical pass lives entirely in REGISTERS: the filtered row is scattered into the 11 pending
+//     output-row accumulators of the thread's column (acc[(phase + d) % 11] += g[10 - d] * h), the one that
+//     just received its last tap is emitted and recycled.  The row loop is unrolled by 11 so every
+//     accumulator index is a compile-time constant.
 // MODE 0: parity API (writes ssim + optional saved maps)
 // MODE 1: training (writes upstream-scaled A/B/C maps, accumulates sum|d| and sum(ssim))
 // ------------------------------------------------------------------------------------------------
-constexpr int SW = 192;        // strip width in floats = threads per CTA (1080p: 5760 = 30 strips)
-constexpr int SROWS = 60;      // output rows per CTA
+constexpr int SW = 128;        // strip width in floats = threads per CTA (1080p: 5760 = 45 strips)
+constexpr int SROWS = 72;      // output rows per CTA (1080 = 15 chunks)
 constexpr int SMAXC = 4;       // channels supported by the halo buffer
 constexpr int SHALO = SPAD * SMAXC;
+
+// Stages row r of NIMG images: registers -> shared, barrier, prefetch of the next row into registers.
+template <int NIMG>
+struct RowStager {
+    float pre[NIMG][2];
+    const float* img[NIMG];
+    int H, RW, e0, halo, nload, t;
+    __device__ __forceinline__ void fetch(int r)
+    {
+        const bool row_ok = r >= 0 && r < H;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = t + u * SW;
+            const int ee = e0 - halo + i;
+            const bool ok = row_ok && i < nload && ee >= 0 && ee < RW;
+            const size_t si = ok ? (size_t)r * RW + ee : 0;
+#pragma unroll
+            for (int m = 0; m < NIMG; ++m) pre[m][u] = ok ? __ldg(img[m] + si) : 0.f;
+        }
+    }
+    __device__ __forceinline__ void store(float (*row)[SW + 2 * SHALO])
+    {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = t + u * SW;
+            if (i < nload) {
+#pragma unroll
+                for (int m = 0; m < NIMG; ++m) row[m][i] = pre[m][u];
+            }
+        }
+    }
+};
 
 template <int MODE>
 __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int C, const float* __restrict__ img1,
@@ -82,101 +120,89 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int C, const floa
                                                  float* __restrict__ o5, double* __restrict__ partial)
 {
     __shared__ float s_row[4][SW + 2 * SHALO];   // [parity][image]
-    __shared__ float s_ring[SK][5][SW];
     __shared__ double s_red[2][SW / 32];
     const int RW = W * C;                          // floats per image row
     const int e0 = blockIdx.x * SW;                // first row element of the strip
     const int r0 = blockIdx.y * SROWS, r1 = min(r0 + SROWS, H);
     const int t = threadIdx.x;
     const int e = e0 + t;
-    const int halo = SPAD * C;
-    double accL1 = 0.0, accS = 0.0;
-    // row r+1 is fetched into registers while row r is filtered (each thread owns elements t and t + SW of the
-    // haloed strip); zero outside the image
-    const int nload = SW + 2 * halo;
-    float pa[2], pb[2];
-    auto fetch = [&](int r) {
-        const bool row_ok = r >= 0 && r < H;
+    float accL1 = 0.f, accS = 0.f;               // <= SROWS terms each per thread: f32 is ample
+    RowStager<2> st;
+    st.img[0] = img1; st.img[1] = img2;
+    st.H = H; st.RW = RW; st.e0 = e0; st.halo = SPAD * C; st.nload = SW + 2 * SPAD * C; st.t = t;
+    float acc[SK][5];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int i = t + u * SW;
-            const int ee = e0 - halo + i;
-            pa[u] = 0.f; pb[u] = 0.f;
-            if (row_ok && i < nload && ee >= 0 && ee < RW) {
-                const size_t si = (size_t)r * RW + ee;
-                pa[u] = img1[si];
-                pb[u] = img2[si];
-            }
-        }
-    };
-    fetch(r0 - SPAD);
-    for (int r = r0 - SPAD; r < r1 + SPAD; ++r) {
-        float (*row)[SW + 2 * SHALO] = reinterpret_cast<float (*)[SW + 2 * SHALO]>(&s_row[(r & 1) * 2][0]);
+    for (int j = 0; j < SK; ++j)
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int i = t + u * SW;
-            if (i < nload) { row[0][i] = pa[u]; row[1][i] = pb[u]; }
-        }
-        __syncthreads();   // the only barrier per row: the two row buffers alternate
-        if (r + 1 < r1 + SPAD) fetch(r + 1);
-        // ---- horizontal 11 taps -> ring slot of row r
-        {
-            float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+        for (int q = 0; q < 5; ++q) acc[j][q] = 0.f;
+
+    const int rbeg = r0 - SPAD, rend = r1 + SPAD;   // input rows [rbeg, rend)
+    st.fetch(rbeg);
+    for (int rb = rbeg; rb < rend; rb += SK) {
 #pragma unroll
-            for (int k = 0; k < SK; ++k) {
-                const float w = win.g[k];
-                const float a = row[0][t + k * C], b = row[1][t + k * C];
-                m1 = fmaf(w, a, m1);
-                m2 = fmaf(w, b, m2);
-                e11 = fmaf(w, a * a, e11);
-                e22 = fmaf(w, b * b, e22);
-                e12 = fmaf(w, a * b, e12);
-            }
-            const int slot = (r + SK) % SK;
-            s_ring[slot][0][t] = m1; s_ring[slot][1][t] = m2; s_ring[slot][2][t] = e11; s_ring[slot][3][t] = e22;
-            s_ring[slot][4][t] = e12;
-        }
-        // ---- vertical 11 taps -> output row ro = r - 5 (each thread reads only its own ring column)
-        const int ro = r - SPAD;
-        if (ro >= r0 && e < RW) {
-            float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
-            const int base = (ro - SPAD + 2 * SK) % SK;
+        for (int ph = 0; ph < SK; ++ph) {
+            const int r = rb + ph;
+            if (r < rend) {   // uniform across the CTA
+                float (*row)[SW + 2 * SHALO] = reinterpret_cast<float (*)[SW + 2 * SHALO]>(&s_row[((r - rbeg) & 1) * 2][0]);
+                st.store(row);
+                __syncthreads();   // the only barrier per row: the two row buffers alternate
+                if (r + 1 < rend) st.fetch(r + 1);
+                // ---- horizontal 11 taps of input row r
+                float h[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int k = 0; k < SK; ++k) {
-                const float w = win.g[k];
-                int slot = base + k;
-                if (slot >= SK) slot -= SK;
-                m1 = fmaf(w, s_ring[slot][0][t], m1);
-                m2 = fmaf(w, s_ring[slot][1][t], m2);
-                e11 = fmaf(w, s_ring[slot][2][t], e11);
-                e22 = fmaf(w, s_ring[slot][3][t], e22);
-                e12 = fmaf(w, s_ring[slot][4][t], e12);
-            }
-            const SsimPoint sp = ssim_point(m1, m2, e11, e22, e12);
-            const size_t idx = (size_t)ro * RW + e;
-            if (MODE == 0) {
-                o0[idx] = sp.ssim;
-                if (o1) o1[idx] = m1;
-                if (o2) o2[idx] = m2;
-                if (o3) o3[idx] = e11 - m1 * m1;
-                if (o4) o4[idx] = e22 - m2 * m2;
-                if (o5) o5[idx] = e12 - m1 * m2;
-            } else {
-                o0[idx] = upstream * sp.gm1;
-                o1[idx] = upstream * sp.gs1;
-                o2[idx] = upstream * sp.gs12;
-                accS += (double)sp.ssim;
-                accL1 += (double)fabsf(img1[idx] - img2[idx]);
+                for (int k = 0; k < SK; ++k) {
+                    const float w = win.g[k];
+                    const float a = row[0][t + k * C], b = row[1][t + k * C];
+                    h[0] = fmaf(w, a, h[0]);
+                    h[1] = fmaf(w, b, h[1]);
+                    h[2] = fmaf(w, a * a, h[2]);
+                    h[3] = fmaf(w, b * b, h[3]);
+                    h[4] = fmaf(w, a * b, h[4]);
+                }
+                // ---- vertical: input row r feeds output rows r-5 .. r+5; output ro lives in slot (ro - rbeg) % 11
+                //      = (ph + d - 5 + 11) % 11 for ro = r + d - 5, with tap k = r - ro + 5 = 10 - d
+#pragma unroll
+                for (int d = 0; d < SK; ++d) {
+                    const int slot = (ph + d + SK - SPAD) % SK;
+                    const float w = win.g[SK - 1 - d];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) acc[slot][q] = fmaf(w, h[q], acc[slot][q]);
+                }
+                // ---- output row ro = r - 5 just received its last tap (d = 0)
+                const int ro = r - SPAD;
+                const int oslot = (ph + SK - SPAD) % SK;
+                if (ro >= r0 && e < RW) {
+                    const float m1 = acc[oslot][0], m2 = acc[oslot][1], e11 = acc[oslot][2], e22 = acc[oslot][3], e12 = acc[oslot][4];
+                    const SsimPoint sp = ssim_point(m1, m2, e11, e22, e12);
+                    const size_t idx = (size_t)ro * RW + e;
+                    if (MODE == 0) {
+                        o0[idx] = sp.ssim;
+                        if (o1) o1[idx] = m1;
+                        if (o2) o2[idx] = m2;
+                        if (o3) o3[idx] = e11 - m1 * m1;
+                        if (o4) o4[idx] = e22 - m2 * m2;
+                        if (o5) o5[idx] = e12 - m1 * m2;
+                    } else {
+                        o0[idx] = upstream * sp.gm1;
+                        o1[idx] = upstream * sp.gs1;
+                        o2[idx] = upstream * sp.gs12;
+                        accS += sp.ssim;
+                        accL1 += fabsf(__ldg(img1 + idx) - __ldg(img2 + idx));
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 5; ++q) acc[oslot][q] = 0.f;
             }
         }
     }
     if (MODE == 1) {
+        double dL1 = (double)accL1, dS = (double)accS;
         for (int o = 16; o > 0; o >>= 1) {
-            accL1 += __shfl_xor_sync(0xffffffffu, accL1, o);
-            accS += __shfl_xor_sync(0xffffffffu, accS, o);
+            dL1 += __shfl_xor_sync(0xffffffffu, dL1, o);
+            dS += __shfl_xor_sync(0xffffffffu, dS, o);
         }
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (lane == 0) { s_red[0][warp] = accL1; s_red[1][warp] = accS; }
+        if (lane == 0) { s_red[0][warp] = dL1; s_red[1][warp] = dS; }
         __syncthreads();
         if (threadIdx.x == 0 && partial) {
             double a = 0.0, b = 0.0;
@@ -191,6 +217,7 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int C, const floa
 // backward: transposed (flipped-window) separable convolution of the three maps, then the pointwise
 // combination  grad1 = convT(A) + 2 v1 convT(B) + v2 convT(C)  [+ l1_scale * sign(v1 - v2)].
 // Pixel x receives from centre x - (k - 5) with weight g[k]  ->  tap k reads element offset (5 - k) * C.
+// Same streaming structure as the forward (horizontal taps from shared memory, vertical taps in registers).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int C, const float* __restrict__ img1,
                                                  const float* __restrict__ img2, const float* __restrict__ mapA,
@@ -199,74 +226,62 @@ __global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int C, const floa
                                                  float* __restrict__ grad1)
 {
     __shared__ float s_row[6][SW + 2 * SHALO];   // [parity][map]
-    __shared__ float s_ring[SK][3][SW];
     const int RW = W * C;
     const int e0 = blockIdx.x * SW;
     const int r0 = blockIdx.y * SROWS, r1 = min(r0 + SROWS, H);
     const int t = threadIdx.x;
     const int e = e0 + t;
-    const int halo = SPAD * C;
-    const int nload = SW + 2 * halo;
-    float pa[2], pb[2], pc[2];
-    auto fetch = [&](int r) {
-        const bool row_ok = r >= 0 && r < H;
+    RowStager<3> st;
+    st.img[0] = mapA; st.img[1] = mapB; st.img[2] = mapC;
+    st.H = H; st.RW = RW; st.e0 = e0; st.halo = SPAD * C; st.nload = SW + 2 * SPAD * C; st.t = t;
+    float acc[SK][3];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int i = t + u * SW;
-            const int ee = e0 - halo + i;
-            pa[u] = 0.f; pb[u] = 0.f; pc[u] = 0.f;
-            if (row_ok && i < nload && ee >= 0 && ee < RW) {
-                const size_t si = (size_t)r * RW + ee;
-                pa[u] = mapA[si];
-                pb[u] = mapB[si];
-                pc[u] = mapC[si];
-            }
-        }
-    };
-    fetch(r0 - SPAD);
-    for (int r = r0 - SPAD; r < r1 + SPAD; ++r) {
-        float (*row)[SW + 2 * SHALO] = reinterpret_cast<float (*)[SW + 2 * SHALO]>(&s_row[(r & 1) * 3][0]);
+    for (int j = 0; j < SK; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; }
+
+    const int rbeg = r0 - SPAD, rend = r1 + SPAD;
+    st.fetch(rbeg);
+    for (int rb = rbeg; rb < rend; rb += SK) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int i = t + u * SW;
-            if (i < nload) { row[0][i] = pa[u]; row[1][i] = pb[u]; row[2][i] = pc[u]; }
-        }
-        __syncthreads();
-        if (r + 1 < r1 + SPAD) fetch(r + 1);
-        {
-            float a = 0.f, b = 0.f, c = 0.f;
+        for (int ph = 0; ph < SK; ++ph) {
+            const int r = rb + ph;
+            if (r < rend) {
+                float (*row)[SW + 2 * SHALO] = reinterpret_cast<float (*)[SW + 2 * SHALO]>(&s_row[((r - rbeg) & 1) * 3][0]);
+                st.store(row);
+                __syncthreads();
+                if (r + 1 < rend) st.fetch(r + 1);
+                float h[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-            for (int k = 0; k < SK; ++k) {
-                const float w = win.g[k];
-                const int off = t + (2 * SPAD - k) * C;
-                a = fmaf(w, row[0][off], a);
-                b = fmaf(w, row[1][off], b);
-                c = fmaf(w, row[2][off], c);
-            }
-            const int slot = (r + SK) % SK;
-            s_ring[slot][0][t] = a; s_ring[slot][1][t] = b; s_ring[slot][2][t] = c;
-        }
-        const int ro = r - SPAD;
-        if (ro >= r0 && e < RW) {
-            float a = 0.f, b = 0.f, c = 0.f;
-            const int base = (ro + SPAD + SK) % SK;
+                for (int k = 0; k < SK; ++k) {
+                    const float w = win.g[k];
+                    const int off = t + (2 * SPAD - k) * C;
+                    h[0] = fmaf(w, row[0][off], h[0]);
+                    h[1] = fmaf(w, row[1][off], h[1]);
+                    h[2] = fmaf(w, row[2][off], h[2]);
+                }
+                // transposed vertical pass: output row ro receives centre row rc = ro + 5 - k with weight g[k];
+                // centre row r feeds ro = r + d - 5 with k = r - ro + 5 ... flipped: k = d
 #pragma unroll
-            for (int k = 0; k < SK; ++k) {
-                const float w = win.g[k];
-                int slot = base - k;
-                if (slot < 0) slot += SK;
-                a = fmaf(w, s_ring[slot][0][t], a);
-                b = fmaf(w, s_ring[slot][1][t], b);
-                c = fmaf(w, s_ring[slot][2][t], c);
+                for (int d = 0; d < SK; ++d) {
+                    const int slot = (ph + d + SK - SPAD) % SK;
+                    const float w = win.g[d];
+                    acc[slot][0] = fmaf(w, h[0], acc[slot][0]);
+                    acc[slot][1] = fmaf(w, h[1], acc[slot][1]);
+                    acc[slot][2] = fmaf(w, h[2], acc[slot][2]);
+                }
+                const int ro = r - SPAD;
+                const int oslot = (ph + SK - SPAD) % SK;
+                if (ro >= r0 && e < RW) {
+                    const size_t idx = (size_t)ro * RW + e;
+                    const float v1 = __ldg(img1 + idx), v2 = __ldg(img2 + idx);
+                    float g = acc[oslot][0] + 2.0f * v1 * acc[oslot][1] + v2 * acc[oslot][2];
+                    if (l1_scale != 0.0f) {
+                        const float dd = v1 - v2;
+                        g += dd > 0.0f ? l1_scale : (dd < 0.0f ? -l1_scale : 0.0f);
+                    }
+                    grad1[idx] = g;
+                }
+                acc[oslot][0] = 0.f; acc[oslot][1] = 0.f; acc[oslot][2] = 0.f;
             }
-            const size_t idx = (size_t)ro * RW + e;
-            const float v1 = img1[idx], v2 = img2[idx];
-            float g = a + 2.0f * v1 * b + v2 * c;
-            if (l1_scale != 0.0f) {
-                const float d = v1 - v2;
-                g += d > 0.0f ? l1_scale : (d < 0.0f ? -l1_scale : 0.0f);
-            }
-            grad1[idx] = g;
         }
     }
 }
