@@ -81,11 +81,15 @@ constexpr int SMAXC = 4;       // channels supported by the halo buffer
 constexpr int SHALO = SPAD * SMAXC;
 
 // Stages row r of NIMG images: registers -> shared, barrier, prefetch of the next row into registers.
+// Also prefetches, one row ahead, the two image values at the thread's own element of the OUTPUT row r - 5
+// (the pointwise terms of the epilogue), so no global load is consumed in the iteration that issues it.
 template <int NIMG>
 struct RowStager {
     float pre[NIMG][2];
+    float ctr_next[2], ctr[2];
     const float* img[NIMG];
-    int H, RW, e0, halo, nload, t;
+    const float* cimg[2];
+    int H, RW, e0, halo, nload, t, r0;
     __device__ __forceinline__ void fetch(int r)
     {
         const bool row_ok = r >= 0 && r < H;
@@ -98,6 +102,11 @@ struct RowStager {
 #pragma unroll
             for (int m = 0; m < NIMG; ++m) pre[m][u] = ok ? __ldg(img[m] + si) : 0.f;
         }
+        const int ro = r - SPAD;
+        const bool cok = ro >= r0 && ro < H && e0 + t < RW;
+        const size_t ci = cok ? (size_t)ro * RW + e0 + t : 0;
+        ctr_next[0] = cok ? __ldg(cimg[0] + ci) : 0.f;
+        ctr_next[1] = cok ? __ldg(cimg[1] + ci) : 0.f;
     }
     __device__ __forceinline__ void store(float (*row)[SW + 2 * SHALO])
     {
@@ -109,11 +118,14 @@ struct RowStager {
                 for (int m = 0; m < NIMG; ++m) row[m][i] = pre[m][u];
             }
         }
+        ctr[0] = ctr_next[0];
+        ctr[1] = ctr_next[1];
     }
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int C, const float* __restrict__ img1,
+// CT = compile-time channel count (tap offsets become immediates); CT == 0 uses the runtime C.
+template <int MODE, int CT>
+__global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int Crt, const float* __restrict__ img1,
                                                  const float* __restrict__ img2, const __grid_constant__ SsimWindow win,
                                                  float upstream, float* __restrict__ o0, float* __restrict__ o1,
                                                  float* __restrict__ o2, float* __restrict__ o3, float* __restrict__ o4,
@@ -121,6 +133,7 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int C, const floa
 {
     __shared__ float s_row[4][SW + 2 * SHALO];   // [parity][image]
     __shared__ double s_red[2][SW / 32];
+    const int C = CT ? CT : Crt;
     const int RW = W * C;                          // floats per image row
     const int e0 = blockIdx.x * SW;                // first row element of the strip
     const int r0 = blockIdx.y * SROWS, r1 = min(r0 + SROWS, H);
@@ -128,13 +141,15 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int C, const floa
     const int e = e0 + t;
     float accL1 = 0.f, accS = 0.f;               // <= SROWS terms each per thread: f32 is ample
     RowStager<2> st;
-    st.img[0] = img1; st.img[1] = img2;
-    st.H = H; st.RW = RW; st.e0 = e0; st.halo = SPAD * C; st.nload = SW + 2 * SPAD * C; st.t = t;
-    float acc[SK][5];
+    st.img[0] = img1; st.img[1] = img2; st.cimg[0] = img1; st.cimg[1] = img2;
+    st.H = H; st.RW = RW; st.e0 = e0; st.halo = SPAD * C; st.nload = SW + 2 * SPAD * C; st.t = t; st.r0 = r0;
+    // MODE 1 needs sigma1^2 + sigma2^2 only as a SUM, so it filters E[a^2 + b^2] as one map (4 maps, not 5)
+    constexpr int NQ = MODE == 0 ? 5 : 4;
+    float acc[SK][NQ];
 #pragma unroll
     for (int j = 0; j < SK; ++j)
 #pragma unroll
-        for (int q = 0; q < 5; ++q) acc[j][q] = 0.f;
+        for (int q = 0; q < NQ; ++q) acc[j][q] = 0.f;
 
     const int rbeg = r0 - SPAD, rend = r1 + SPAD;   // input rows [rbeg, rend)
     st.fetch(rbeg);
@@ -148,16 +163,23 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int C, const floa
                 __syncthreads();   // the only barrier per row: the two row buffers alternate
                 if (r + 1 < rend) st.fetch(r + 1);
                 // ---- horizontal 11 taps of input row r
-                float h[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                float h[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) h[q] = 0.f;
 #pragma unroll
                 for (int k = 0; k < SK; ++k) {
                     const float w = win.g[k];
                     const float a = row[0][t + k * C], b = row[1][t + k * C];
                     h[0] = fmaf(w, a, h[0]);
                     h[1] = fmaf(w, b, h[1]);
-                    h[2] = fmaf(w, a * a, h[2]);
-                    h[3] = fmaf(w, b * b, h[3]);
-                    h[4] = fmaf(w, a * b, h[4]);
+                    if (MODE == 0) {
+                        h[2] = fmaf(w, a * a, h[2]);
+                        h[3] = fmaf(w, b * b, h[3]);
+                        h[4] = fmaf(w, a * b, h[4]);
+                    } else {
+                        h[2] = fmaf(w, fmaf(b, b, a * a), h[2]);
+                        h[3] = fmaf(w, a * b, h[3]);
+                    }
                 }
                 // ---- vertical: input row r feeds output rows r-5 .. r+5; output ro lives in slot (ro - rbeg) % 11
                 //      = (ph + d - 5 + 11) % 11 for ro = r + d - 5, with tap k = r - ro + 5 = 10 - d
@@ -166,13 +188,15 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int C, const floa
                     const int slot = (ph + d + SK - SPAD) % SK;
                     const float w = win.g[SK - 1 - d];
 #pragma unroll
-                    for (int q = 0; q < 5; ++q) acc[slot][q] = fmaf(w, h[q], acc[slot][q]);
+                    for (int q = 0; q < NQ; ++q) acc[slot][q] = fmaf(w, h[q], acc[slot][q]);
                 }
                 // ---- output row ro = r - 5 just received its last tap (d = 0)
                 const int ro = r - SPAD;
                 const int oslot = (ph + SK - SPAD) % SK;
                 if (ro >= r0 && e < RW) {
-                    const float m1 = acc[oslot][0], m2 = acc[oslot][1], e11 = acc[oslot][2], e22 = acc[oslot][3], e12 = acc[oslot][4];
+                    const float m1 = acc[oslot][0], m2 = acc[oslot][1];
+                    const float e11 = acc[oslot][2], e22 = MODE == 0 ? acc[oslot][3] : 0.f, e12 = acc[oslot][NQ - 1];
+                    // (MODE 1: e11 carries E[a^2 + b^2], e22 = 0: ssim_point only uses their sum)
                     const SsimPoint sp = ssim_point(m1, m2, e11, e22, e12);
                     const size_t idx = (size_t)ro * RW + e;
                     if (MODE == 0) {
@@ -187,11 +211,11 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int C, const floa
                         o1[idx] = upstream * sp.gs1;
                         o2[idx] = upstream * sp.gs12;
                         accS += sp.ssim;
-                        accL1 += fabsf(__ldg(img1 + idx) - __ldg(img2 + idx));
+                        accL1 += fabsf(st.ctr[0] - st.ctr[1]);
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < 5; ++q) acc[oslot][q] = 0.f;
+                for (int q = 0; q < NQ; ++q) acc[oslot][q] = 0.f;
             }
         }
     }
@@ -219,21 +243,23 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int C, const floa
 // Pixel x receives from centre x - (k - 5) with weight g[k]  ->  tap k reads element offset (5 - k) * C.
 // Same streaming structure as the forward (horizontal taps from shared memory, vertical taps in registers).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int C, const float* __restrict__ img1,
+template <int CT>
+__global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int Crt, const float* __restrict__ img1,
                                                  const float* __restrict__ img2, const float* __restrict__ mapA,
                                                  const float* __restrict__ mapB, const float* __restrict__ mapC,
                                                  const __grid_constant__ SsimWindow win, float l1_scale,
                                                  float* __restrict__ grad1)
 {
     __shared__ float s_row[6][SW + 2 * SHALO];   // [parity][map]
+    const int C = CT ? CT : Crt;
     const int RW = W * C;
     const int e0 = blockIdx.x * SW;
     const int r0 = blockIdx.y * SROWS, r1 = min(r0 + SROWS, H);
     const int t = threadIdx.x;
     const int e = e0 + t;
     RowStager<3> st;
-    st.img[0] = mapA; st.img[1] = mapB; st.img[2] = mapC;
-    st.H = H; st.RW = RW; st.e0 = e0; st.halo = SPAD * C; st.nload = SW + 2 * SPAD * C; st.t = t;
+    st.img[0] = mapA; st.img[1] = mapB; st.img[2] = mapC; st.cimg[0] = img1; st.cimg[1] = img2;
+    st.H = H; st.RW = RW; st.e0 = e0; st.halo = SPAD * C; st.nload = SW + 2 * SPAD * C; st.t = t; st.r0 = r0;
     float acc[SK][3];
 #pragma unroll
     for (int j = 0; j < SK; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; }
@@ -272,7 +298,7 @@ __global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int C, const floa
                 const int oslot = (ph + SK - SPAD) % SK;
                 if (ro >= r0 && e < RW) {
                     const size_t idx = (size_t)ro * RW + e;
-                    const float v1 = __ldg(img1 + idx), v2 = __ldg(img2 + idx);
+                    const float v1 = st.ctr[0], v2 = st.ctr[1];
                     float g = acc[oslot][0] + 2.0f * v1 * acc[oslot][1] + v2 * acc[oslot][2];
                     if (l1_scale != 0.0f) {
                         const float dd = v1 - v2;
@@ -320,7 +346,8 @@ cudaError_t launch_ssim_fwd(cudaStream_t st, int H, int W, int C, const float* i
 {
     if (H <= 0 || W <= 0 || C <= 0) return cudaSuccess;
     dim3 grid(cdiv((long long)W * C, SW), cdiv(H, SROWS));
-    k_ssim_fwd<0><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, ssim_map, mu1, mu2, s1, s2, s12, nullptr);
+    if (C == 3) k_ssim_fwd<0, 3><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, ssim_map, mu1, mu2, s1, s2, s12, nullptr);
+    else k_ssim_fwd<0, 0><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, ssim_map, mu1, mu2, s1, s2, s12, nullptr);
     return cudaGetLastError();
 }
 
@@ -331,8 +358,10 @@ cudaError_t launch_loss_fwd(cudaStream_t st, int H, int W, int C, const float* r
     if (e != cudaSuccess) return e;
     if (H <= 0 || W <= 0 || C <= 0) return cudaSuccess;
     dim3 grid(cdiv((long long)W * C, SW), cdiv(H, SROWS));
-    k_ssim_fwd<1><<<grid, SW, 0, st>>>(H, W, C, render, target, window(), upstream, mapA, mapB, mapC, nullptr, nullptr,
-                                        nullptr, partial);
+    if (C == 3) k_ssim_fwd<1, 3><<<grid, SW, 0, st>>>(H, W, C, render, target, window(), upstream, mapA, mapB, mapC, nullptr, nullptr,
+                                                      nullptr, partial);
+    else k_ssim_fwd<1, 0><<<grid, SW, 0, st>>>(H, W, C, render, target, window(), upstream, mapA, mapB, mapC, nullptr, nullptr,
+                                               nullptr, partial);
     return cudaGetLastError();
 }
 
@@ -341,7 +370,8 @@ cudaError_t launch_loss_bwd(cudaStream_t st, int H, int W, int C, const float* r
 {
     if (H <= 0 || W <= 0 || C <= 0) return cudaSuccess;
     dim3 grid(cdiv((long long)W * C, SW), cdiv(H, SROWS));
-    k_ssim_bwd<<<grid, SW, 0, st>>>(H, W, C, render, target, mapA, mapB, mapC, window(), l1_scale, cot_render);
+    if (C == 3) k_ssim_bwd<3><<<grid, SW, 0, st>>>(H, W, C, render, target, mapA, mapB, mapC, window(), l1_scale, cot_render);
+    else k_ssim_bwd<0><<<grid, SW, 0, st>>>(H, W, C, render, target, mapA, mapB, mapC, window(), l1_scale, cot_render);
     return cudaGetLastError();
 }
 
@@ -358,11 +388,12 @@ cudaError_t launch_ssim_bwd_api(cudaStream_t st, int H, int W, int C, const floa
     if (H <= 0 || W <= 0 || C <= 0) return cudaSuccess;
     dim3 grid(cdiv((long long)W * C, SW), cdiv(H, SROWS));
     // maps with unit upstream, then scaled by the caller's per-centre gradient
-    k_ssim_fwd<1><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, mapA, mapB, mapC, nullptr, nullptr, nullptr,
-                                        nullptr);
+    if (C == 3) k_ssim_fwd<1, 3><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, mapA, mapB, mapC, nullptr, nullptr, nullptr, nullptr);
+    else k_ssim_fwd<1, 0><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, mapA, mapB, mapC, nullptr, nullptr, nullptr, nullptr);
     const size_t n = (size_t)H * W * C;
     k_scale_maps<<<cdiv((long long)n, 256), 256, 0, st>>>(n, grad_out, mapA, mapB, mapC);
-    k_ssim_bwd<<<grid, SW, 0, st>>>(H, W, C, img1, img2, mapA, mapB, mapC, window(), 0.0f, grad_img1);
+    if (C == 3) k_ssim_bwd<3><<<grid, SW, 0, st>>>(H, W, C, img1, img2, mapA, mapB, mapC, window(), 0.0f, grad_img1);
+    else k_ssim_bwd<0><<<grid, SW, 0, st>>>(H, W, C, img1, img2, mapA, mapB, mapC, window(), 0.0f, grad_img1);
     return cudaGetLastError();
 }
 
