@@ -204,7 +204,9 @@ def run_gsb(args, rank, local_rank, world):
     my_views = [v for v in range(views) if v % world == rank]
     log(f"[rank {rank}] workload {wl.name}: N={n}, {wl.width}x{wl.height}, views {my_views} of {views}")
 
-    ctx = Context(wl.width, wl.height, tile_w=wl.tile, tile_h=wl.tile, sh_degree=wl.sh_degree, max_gaussians=n, device=local_rank)
+    base_flags = int(os.environ.get("GSB_FLAGS", "0"))   # debugging: 1 = CUB sort baseline, 2 = no view pipeline
+    ctx = Context(wl.width, wl.height, tile_w=wl.tile, tile_h=wl.tile, sh_degree=wl.sh_degree, max_gaussians=n, device=local_rank,
+                  flags=base_flags)
     ctx.trainer_init({k: torch.from_numpy(v) for k, v in params.items()})
     gcams = [_lib.make_camera(cams[v]) for v in my_views]
     host_targets = [torch.from_numpy(targets[v]).pin_memory() for v in my_views]
@@ -275,13 +277,13 @@ def run_gsb(args, rank, local_rank, world):
     # ---- per-kernel durations: same steps with the view pipeline OFF (every kernel alone on the work stream,
     #      bracketed by CUDA events on that stream), so a kernel's time is not inflated by the kernels of the next
     #      view that overlap it in region 1
-    ctx.set_flags(_lib.GSB_FLAG_NO_OVERLAP)
+    ctx.set_flags(base_flags | _lib.GSB_FLAG_NO_OVERLAP)
     ctx.stats_reset()
     ctx.enable_stage_timing(True)
     ms_serial = timed(False, False, args.steps, it); it += args.steps
     st = ctx.stats()
     ctx.enable_stage_timing(False)
-    ctx.set_flags(0)
+    ctx.set_flags(base_flags)
 
     # ---- timed region 2: end to end through the public API (pinned host targets H2D + loss D2H every step)
     step(it, True, True); it += 1

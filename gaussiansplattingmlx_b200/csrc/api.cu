@@ -67,7 +67,11 @@ struct Ctx {
 
     int capN = 0;
     SortPlan dplan;
-    float* grad_rec = nullptr;         // [N,12]
+    float* grad_rec = nullptr;         // [N,12] raster backward -> projection backward
+    float* grad_rec2 = nullptr;        // second buffer (trainer: projection backward of view b overlaps the raster of b+1)
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t ev_rb[2] = {nullptr, nullptr};   // raster backward into gradient-record buffer i finished (work stream)
+    cudaEvent_t ev_pb[2] = {nullptr, nullptr};   // projection backward out of buffer i finished (tail stream)
     uint32_t* offsets_ref = nullptr;   // [N] scan in index order (parity API: reference emission order)
     float* act_tmp = nullptr;          // scratch for the reference-layout parity API ([N,12] floats)
 
@@ -125,11 +129,11 @@ struct Ctx {
     size_t ev_used = 0;
 };
 
+static void sync_all_streams(Ctx* c);
 static void resolve_stage_events(Ctx* c)
 {
     if (c->ev_used == 0) return;
-    cudaStreamSynchronize(c->stream);
-    if (c->front_stream) cudaStreamSynchronize(c->front_stream);
+    sync_all_streams(c);
     for (size_t i = 0; i < c->ev_used; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->ev_pool[i].a, c->ev_pool[i].b) == cudaSuccess) {
@@ -227,6 +231,7 @@ static void sync_all_streams(Ctx* c)
 {
     cudaStreamSynchronize(c->stream);
     if (c->front_stream) cudaStreamSynchronize(c->front_stream);
+    if (c->tail_stream) cudaStreamSynchronize(c->tail_stream);
 }
 
 static int ensure_gaussians(Ctx* c, int N)
@@ -238,8 +243,9 @@ static int ensure_gaussians(Ctx* c, int N)
     }
     sync_all_streams(c);
     const int cap = c->cfg.max_gaussians > 0 ? c->cfg.max_gaussians : std::max(N, 1024);
-    dev_free(c->grad_rec); dev_free(c->act_tmp); dev_free(c->offsets_ref);
+    dev_free(c->grad_rec); dev_free(c->grad_rec2); dev_free(c->act_tmp); dev_free(c->offsets_ref);
     GSB_CUDA_CHECK(c, dev_alloc(&c->grad_rec, (size_t)cap * REC_FLOATS));
+    GSB_CUDA_CHECK(c, dev_alloc(&c->grad_rec2, (size_t)cap * REC_FLOATS));
     GSB_CUDA_CHECK(c, dev_alloc(&c->act_tmp, (size_t)cap * REC_FLOATS));
     GSB_CUDA_CHECK(c, dev_alloc(&c->offsets_ref, (size_t)cap));
     c->dplan = sort_plan((uint32_t)cap, 32u);
@@ -356,11 +362,11 @@ static int enqueue_binning(Ctx* c, Ctx::ViewBufs& v, cudaStream_t st, int N, con
                                                v.vals[0], c->capM, &v.d_ctl[0], &v.d_ctl[1]));
         ++launches;
     }
+    if (use_cub) GSB_CUDA_CHECK(c, cudaStreamSynchronize(st));   // checked baseline: needs the host-known count
     {
         StageTimer t(c, GSB_STAGE_SORT, st);
         // 3. stable sort on the tile id alone (the list is already in (depth, index) order)
         if (use_cub) {
-            GSB_CUDA_CHECK(c, cudaEventSynchronize(v.ev_ctl));   // checked baseline: needs the host-known count
             const uint32_t M = std::min(v.h_ctl[0], c->capM);
             int rc = cub_sort32(c, st, v.keys[0], v.keys[1], v.vals[0], v.vals[1], M, (uint32_t)c->tileBits);
             if (rc != GSB_OK) return rc;
@@ -448,6 +454,7 @@ static void destroy_ctx(Ctx* c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->front_stream) cudaStreamSynchronize(c->front_stream);
+    if (c->tail_stream) cudaStreamSynchronize(c->tail_stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     for (Ctx::ViewBufs& v : c->vb) {
         dev_free(v.rec); dev_free(v.tile_rects); dev_free(v.touched); dev_free(v.offsets); dev_free(v.d_nvalue);
@@ -460,7 +467,7 @@ static void destroy_ctx(Ctx* c)
         cudaEvent_t* evs[] = {&v.ev_ctl, &v.ev_front, &v.ev_back};
         for (cudaEvent_t* e : evs) if (*e) cudaEventDestroy(*e);
     }
-    dev_free(c->grad_rec); dev_free(c->act_tmp); dev_free(c->offsets_ref);
+    dev_free(c->grad_rec); dev_free(c->grad_rec2); dev_free(c->act_tmp); dev_free(c->offsets_ref);
     for (int i = 0; i < 2; ++i) dev_free(c->t_target[i]);
     if (c->cub_tmp) cudaFree(c->cub_tmp);
     dev_free(c->dbg_keys); dev_free(c->dbg_vals);
@@ -470,10 +477,12 @@ static void destroy_ctx(Ctx* c)
     dev_free(c->t_block); dev_free(c->t_accum);
     if (c->h_loss) cudaFreeHost(c->h_loss);
     for (auto& e : c->ev_pool) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
-    cudaEvent_t* evs[] = {&c->t_target_ready[0], &c->t_target_ready[1], &c->t_target_free[0], &c->t_target_free[1], &c->ev_fork};
+    cudaEvent_t* evs[] = {&c->t_target_ready[0], &c->t_target_ready[1], &c->t_target_free[0], &c->t_target_free[1], &c->ev_fork,
+                          &c->ev_rb[0], &c->ev_rb[1], &c->ev_pb[0], &c->ev_pb[1]};
     for (cudaEvent_t* e : evs) if (*e) cudaEventDestroy(*e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->front_stream) cudaStreamDestroy(c->front_stream);
+    if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -565,6 +574,11 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
     CREATE_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CREATE_CHECK(cudaStreamCreateWithPriority(&c->front_stream, cudaStreamNonBlocking, prio_hi));
+    CREATE_CHECK(cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, prio_hi));
+    for (int i = 0; i < 2; ++i) {
+        CREATE_CHECK(cudaEventCreateWithFlags(&c->ev_rb[i], cudaEventDisableTiming));
+        CREATE_CHECK(cudaEventCreateWithFlags(&c->ev_pb[i], cudaEventDisableTiming));
+    }
     CREATE_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         CREATE_CHECK(cudaEventCreateWithFlags(&c->t_target_ready[i], cudaEventDisableTiming));
@@ -628,8 +642,8 @@ int gsb_set_flags(gsb_ctx* ctx, int32_t flags)
 int gsb_synchronize(gsb_ctx* ctx)
 {
     CTX_PROLOGUE(ctx);
-    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->front_stream));
+    gsb::sync_all_streams(c);
+    GSB_CUDA_CHECK(c, cudaGetLastError());
     return GSB_OK;
 }
 
@@ -958,27 +972,39 @@ static int render_forward_impl(Ctx* c, int32_t N, const RawParams& p, const gsb:
     return enqueue_raster_fwd(c, v, N, p, vp, want_depth);
 }
 
+// K10 on the work stream, K2 (+ activation VJPs) either right behind it (gbuf < 0: single-view API, serial
+// trainer) or on the tail stream out of gradient-record buffer gbuf (pipelined trainer).
 static int render_backward_impl(Ctx* c, const float* cot_render, const float* cot_depth, const float* cot_alpha, float* g_xyz,
                                 float* g_f_dc, float* g_f_rest, float* g_scales_log, float* g_rot_raw, float* g_opacity_logit,
-                                int accumulate)
+                                int accumulate, int gbuf = -1)
 {
     if (!c->saved.valid) { gsb::set_error(c, "gsb_render_backward: no forward saved on this context"); return GSB_ERR_STATE; }
     const int N = c->saved.N;
     const gsb::ViewParams& vp = c->saved.vp;
     Ctx::ViewBufs& v = c->vb[c->cur];
-    GSB_CUDA_CHECK(c, cudaMemsetAsync(c->grad_rec, 0, (size_t)N * gsb::REC_FLOATS * 4, c->stream));
+    const bool split = gbuf >= 0;
+    float* grec = (split && gbuf == 1) ? c->grad_rec2 : c->grad_rec;
+    if (split) GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_pb[gbuf], 0));   // previous reader of this buffer
+    GSB_CUDA_CHECK(c, cudaMemsetAsync(grec, 0, (size_t)N * gsb::REC_FLOATS * 4, c->stream));
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
         GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, vp, v.tile_ranges, v.tile_order, v.rec, v.vals[0], v.vals[1], v.d_result_buf, cot_render, cot_depth, cot_alpha,
-                                                 c->out_color, c->out_depth, c->out_alpha, c->out_last, c->grad_rec, &v.d_ctl[3]));
+                                                 c->out_color, c->out_depth, c->out_alpha, c->out_last, grec, &v.d_ctl[3]));
+    }
+    cudaStream_t pst = c->stream;
+    if (split) {
+        GSB_CUDA_CHECK(c, cudaEventRecord(c->ev_rb[gbuf], c->stream));
+        GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->tail_stream, c->ev_rb[gbuf], 0));
+        pst = c->tail_stream;
     }
     {
-        gsb::StageTimer t(c, GSB_STAGE_PROJECT_BWD);
-        GSB_CUDA_CHECK(c, gsb::launch_project_fused_bwd(c->stream, N, vp, c->saved.xyz, c->saved.f_dc, c->saved.f_rest,
-                                                        c->saved.scales_log, c->saved.rot_raw, c->saved.op_logit, c->grad_rec,
+        gsb::StageTimer t(c, GSB_STAGE_PROJECT_BWD, pst);
+        GSB_CUDA_CHECK(c, gsb::launch_project_fused_bwd(pst, N, vp, c->saved.xyz, c->saved.f_dc, c->saved.f_rest,
+                                                        c->saved.scales_log, c->saved.rot_raw, c->saved.op_logit, grec,
                                                         g_xyz, g_f_dc, g_f_rest, g_scales_log, g_rot_raw, g_opacity_logit,
                                                         accumulate));
     }
+    if (split) GSB_CUDA_CHECK(c, cudaEventRecord(c->ev_pb[gbuf], c->tail_stream));
     c->stats.kernel_launches += 1 + (N > 0);
     return GSB_OK;
 }
@@ -1204,10 +1230,12 @@ int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
         if (targets_on_host) GSB_CUDA_CHECK(c, cudaEventRecord(c->t_target_free[b & 1], c->stream));
         const int accumulate = (b > 0 || !zero_grads) ? 1 : 0;
         rc = render_backward_impl(c, c->cot_render, nullptr, nullptr, c->t_g[0], c->t_g[1], c->t_g[2], c->t_g[3], c->t_g[4],
-                                  c->t_g[5], accumulate);
+                                  c->t_g[5], accumulate, overlap ? (b & 1) : -1);
         if (rc != GSB_OK) return rc;
-        if (overlap) GSB_CUDA_CHECK(c, cudaEventRecord(v.ev_back, c->stream));
+        if (overlap) GSB_CUDA_CHECK(c, cudaEventRecord(v.ev_back, c->stream));   // raster backward done: the set is free
     }
+    if (overlap && B > 0)   // the gradients are complete when the last projection backward has run (tail stream is in order)
+        GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_pb[(B - 1) & 1], 0));
     if (host_loss) {
         GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->h_loss, c->loss_accum, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
