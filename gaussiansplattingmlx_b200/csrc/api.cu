@@ -20,6 +20,11 @@ namespace gsb {
 
 static thread_local std::string g_create_error;
 
+// view working sets: with 3 the front of view b+2 can start as soon as the raster backward of view b-1 is done,
+// so the front stream never waits for the view that is being rasterised
+constexpr int GSB_VIEW_SETS = 3;
+constexpr int GSB_FRONT_AHEAD = GSB_VIEW_SETS - 1;
+
 struct Ctx {
     gsb_config cfg{};
     cudaStream_t stream = nullptr;       // work stream (caller's, or own_stream)
@@ -60,7 +65,7 @@ struct Ctx {
         cudaEvent_t ev_front = nullptr;   // projection + binning of this set finished (front stream)
         cudaEvent_t ev_back = nullptr;    // the work stream no longer reads this set
         uint32_t last_M = 0;
-    } vb[2];
+    } vb[GSB_VIEW_SETS];
     int cur = 0;                       // set used by the single-view API / holding the saved forward
     cudaStream_t front_stream = nullptr;
     cudaEvent_t ev_fork = nullptr;     // work stream -> front stream dependency at the start of a batch
@@ -1185,7 +1190,7 @@ int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
     }
     int front_issued = -1;
     auto issue_front = [&](int b) -> int {
-        Ctx::ViewBufs& v = c->vb[b & 1];
+        Ctx::ViewBufs& v = c->vb[b % gsb::GSB_VIEW_SETS];
         const gsb::ViewParams vp = gsb::make_view(c, &host_cams[b]);
         cudaStream_t st = overlap ? c->front_stream : c->stream;
         if (overlap) GSB_CUDA_CHECK(c, cudaStreamWaitEvent(st, v.ev_back, 0));   // set free again
@@ -1201,16 +1206,17 @@ int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
             int rc = prefetch(b + 1);
             if (rc != GSB_OK) return rc;
         }
-        Ctx::ViewBufs& v = c->vb[b & 1];
+        Ctx::ViewBufs& v = c->vb[b % gsb::GSB_VIEW_SETS];
         for (int attempt = 0;; ++attempt) {
             int rc = GSB_OK;
             if (front_issued < b) rc = issue_front(b);
-            if (rc == GSB_OK && overlap && b + 1 < B && front_issued < b + 1) rc = issue_front(b + 1);
+            for (int a = 1; a <= gsb::GSB_FRONT_AHEAD && rc == GSB_OK && overlap; ++a)
+                if (b + a < B && front_issued < b + a) rc = issue_front(b + a);
             if (rc != GSB_OK) return rc;
             rc = gsb::finish_binning(c, v);
             if (rc == GSB_OK) break;
             if (rc != GSB_ERR_CAPACITY || attempt == 3) return rc;
-            front_issued = b - 1;   // the regrow synchronised and reallocated both sets: redo what was in flight
+            front_issued = b - 1;   // the regrow synchronised and reallocated every set: redo what was in flight
             if (overlap) {
                 GSB_CUDA_CHECK(c, cudaEventRecord(c->ev_fork, c->stream));
                 GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->front_stream, c->ev_fork, 0));

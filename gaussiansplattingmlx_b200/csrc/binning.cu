@@ -136,18 +136,18 @@ __global__ void __launch_bounds__(SC_THREADS) k_exclusive_scan(int N, const uint
         if (lane == 0) {
             uint64_t excl = 0;
             if (tile == 0) {
-                st_release_u64(&status[0], SC_FLAG_INCL | block_total);
+                st_relaxed_u64(&status[0], SC_FLAG_INCL | block_total);
             } else {
-                st_release_u64(&status[tile], SC_FLAG_LOCAL | block_total);
+                st_relaxed_u64(&status[tile], SC_FLAG_LOCAL | block_total);
                 int t = (int)tile - 1;
                 while (true) {
-                    uint64_t s = ld_acquire_u64(&status[t]);
+                    uint64_t s = ld_relaxed_u64(&status[t]);
                     if ((s >> 62) == 0) continue;
                     excl += s & SC_VALUE_MASK;
                     if ((s >> 62) == 2) break;
                     --t;
                 }
-                st_release_u64(&status[tile], SC_FLAG_INCL | (excl + block_total));
+                st_relaxed_u64(&status[tile], SC_FLAG_INCL | (excl + block_total));
             }
             s_prefix = (uint32_t)excl;
             if ((long long)(tile + 1) * SC_TILE >= N) *total = (uint32_t)excl + block_total;
@@ -408,7 +408,7 @@ struct OsSmem {
 };
 
 template <typename KeyT>
-__global__ void __launch_bounds__(OS_THREADS) k_os_pass(int pass, uint32_t dmask, SortCtl* ctl, const uint32_t* __restrict__ hist_excl,
+__global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(int pass, uint32_t dmask, SortCtl* ctl, const uint32_t* __restrict__ hist_excl,
                                                         uint32_t* lookback, uint32_t max_tiles, KeyT* keys0, KeyT* keys1,
                                                         uint32_t* vals0, uint32_t* vals1, int iota)
 {
@@ -439,6 +439,13 @@ __global__ void __launch_bounds__(OS_THREADS) k_os_pass(int pass, uint32_t dmask
     for (int i = 0; i < OS_IPT; ++i) {
         uint32_t idx = wbase + i * 32 + lane;
         key[i] = idx < valid ? kin[tile_base + idx] : ~(KeyT)0;
+    }
+    // payloads are fetched now as well, so their latency hides behind the ranking instead of stalling the scatter
+    uint32_t val[OS_IPT];
+#pragma unroll
+    for (int i = 0; i < OS_IPT; ++i) {
+        uint32_t idx = wbase + i * 32 + lane;
+        val[i] = idx < valid ? (synth ? tile_base + idx : vin[tile_base + idx]) : 0u;
     }
     // per-warp stable ranking with match.any
     uint16_t rank[OS_IPT];
@@ -473,18 +480,18 @@ __global__ void __launch_bounds__(OS_THREADS) k_os_pass(int pass, uint32_t dmask
         uint32_t* lb = lookback + ((size_t)pass * max_tiles + tile) * OS_RADIX + d;
         uint32_t excl_prev = 0;
         if (tile == 0) {
-            st_release_u32(lb, OS_FLAG_INCL | total_valid);
+            st_relaxed_u32(lb, OS_FLAG_INCL | total_valid);
         } else {
-            st_release_u32(lb, OS_FLAG_LOCAL | total_valid);
+            st_relaxed_u32(lb, OS_FLAG_LOCAL | total_valid);
             int t = (int)tile - 1;
             while (true) {
-                uint32_t v = ld_acquire_u32(lookback + ((size_t)pass * max_tiles + t) * OS_RADIX + d);
+                uint32_t v = ld_relaxed_u32(lookback + ((size_t)pass * max_tiles + t) * OS_RADIX + d);
                 if ((v >> 30) == 0) continue;
                 excl_prev += v & OS_VALUE_MASK;
                 if ((v >> 30) == 2) break;
                 --t;
             }
-            st_release_u32(lb, OS_FLAG_INCL | (excl_prev + total_valid));
+            st_relaxed_u32(lb, OS_FLAG_INCL | (excl_prev + total_valid));
         }
         // block-exclusive scan of `run` over the 256 digits
         uint32_t inc = run;
@@ -505,11 +512,10 @@ __global__ void __launch_bounds__(OS_THREADS) k_os_pass(int pass, uint32_t dmask
     // scatter into block-sorted order in shared memory
 #pragma unroll
     for (int i = 0; i < OS_IPT; ++i) {
-        uint32_t idx = wbase + i * 32 + lane;
         uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
         uint32_t pos = S.block_excl[d] + S.warp_hist[warp][d] + rank[i];
         S.keys[pos] = key[i];
-        S.vals[pos] = idx < valid ? (synth ? tile_base + idx : vin[tile_base + idx]) : 0u;
+        S.vals[pos] = val[i];
     }
     __syncthreads();
     // coalesced runs out

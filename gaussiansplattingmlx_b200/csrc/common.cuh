@@ -140,6 +140,29 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Look-back status words carry their payload in the same 32/64-bit word as the flag, so polling needs no
+// acquire/release ordering: relaxed gpu-scope accesses avoid the MEMBAR + CCTL.IVALL (L1 invalidate) that
+// ld.acquire.gpu / st.release.gpu cost on every spin iteration (22 % of the onesweep pass's stall samples).
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 // packed-order fields -> raster record quads
 __device__ __forceinline__ void make_raster_record(float mx, float my, float c00, float c01, float c10, float c11, float r,
                                                    float g, float b, float opacity, float depth, uint32_t idx, float4* out)
