@@ -81,6 +81,11 @@ SIGNATURES = {
     "gsb_trainer_accumulate": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), _I, _I, _F, C.POINTER(_F)]),
     "gsb_trainer_apply": (C.c_int, [_P, _I, _I, _I]),
     "gsb_train_step": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), _I, _I, _I, C.POINTER(_F)]),
+    "gsb_densify_classify": (C.c_int, [_P, _I, _P, _F, _P, _P, _F, _F, _F, _I, _P, _P]),
+    "gsb_densify_map": (C.c_int, [_P, _I, _P, _P, _P, _I, _P, _P, C.POINTER(_I)]),
+    "gsb_densify_apply": (C.c_int, [_P, _I, _P, _P, _P, C.c_uint64] + [_P] * 12),
+    "gsb_trainer_densify": (C.c_int, [_P, _F, _F, _F, _I, C.c_uint64, _P, C.POINTER(_I)]),
+    "gsb_trainer_count": (C.c_int, [_P, C.POINTER(_I), C.POINTER(_I)]),
     "gsb_last_contrib_sum": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "gsb_stats_reset": (C.c_int, [_P]),
     "gsb_stats_get": (C.c_int, [_P, C.POINTER(GsbStats)]),

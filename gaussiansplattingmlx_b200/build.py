@@ -27,6 +27,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hi
 SOURCES = {
     "project.cu": ["--fmad=false"],
     "adam.cu": ["--fmad=false"],
+    "densify.cu": ["--fmad=false"],
     "binning.cu": [],
     "raster.cu": [],
     "loss.cu": [],

@@ -319,6 +319,58 @@ class Context:
                                             C.byref(loss) if want_loss else None))
         return float(loss.value) if want_loss else None
 
+    # ---- densification (split_and_prune, GaussianTrainer.swift:766-908) ----------------------
+    def densify_classify(self, grad_accum, denom: float, scales_log, opacity_logit, grad_threshold: float, max_scale: float,
+                         min_opacity: float, allow_densify: bool):
+        self._sync_stream()
+        n = grad_accum.shape[0]
+        actions, counts = self._new(n, dtype=torch.int32), self._new(n, dtype=torch.int32)
+        self._check(self.lib.gsb_densify_classify(self.h, n, _ptr(_f32(grad_accum)), C.c_float(denom), _ptr(_f32(scales_log)),
+                                                  _ptr(_f32(opacity_logit)), C.c_float(grad_threshold), C.c_float(max_scale),
+                                                  C.c_float(min_opacity), int(bool(allow_densify)), _ptr(actions), _ptr(counts)))
+        return actions, counts
+
+    def densify_map(self, actions, counts):
+        """cumsum + build_densify_output_map; returns (offsets[N], gather[N'], noise_mode[N'])."""
+        self._sync_stream()
+        n = actions.shape[0]
+        cap = 2 * n
+        offsets = self._new(n, dtype=torch.int32)
+        gather, mode = self._new(max(cap, 1), dtype=torch.int32), self._new(max(cap, 1), dtype=torch.int32)
+        total = C.c_int32(0)
+        self._check(self.lib.gsb_densify_map(self.h, n, _ptr(actions), _ptr(counts), _ptr(offsets), cap, _ptr(gather), _ptr(mode),
+                                             C.byref(total)))
+        t = int(total.value)
+        return offsets, gather[:t], mode[:t]
+
+    def densify_apply(self, params: Dict[str, torch.Tensor], gather, noise_mode, base_noise=None, seed: int = 0):
+        self._sync_stream()
+        nout = gather.shape[0]
+        K = self.K
+        out = {"_xyz": self._new(nout, 3), "_features_dc": self._new(nout, 1, 3), "_features_rest": self._new(nout, K - 1, 3),
+               "_scales": self._new(nout, 3), "_rotation": self._new(nout, 4), "_opacity": self._new(nout, 1)}
+        self._check(self.lib.gsb_densify_apply(self.h, nout, _ptr(gather.contiguous()), _ptr(noise_mode.contiguous()),
+                                               _ptr(base_noise), C.c_uint64(seed), *[_ptr(_f32(params[k])) for k in PARAM_NAMES],
+                                               *[_ptr(out[k]) for k in PARAM_NAMES]))
+        return out
+
+    def trainer_densify(self, grad_threshold: float = 0.0002, max_scale: float = 0.01, min_opacity: float = 0.005,
+                        max_gaussians: int = 1_000_000, seed: int = 0, base_noise=None) -> Dict[str, int]:
+        """split_and_prune on the context-owned tensors; returns keep/split/clone/prune/total and the new count."""
+        self._sync_stream()
+        counts = (C.c_int32 * 5)()
+        self._check(self.lib.gsb_trainer_densify(self.h, C.c_float(grad_threshold), C.c_float(max_scale), C.c_float(min_opacity),
+                                                 int(max_gaussians), C.c_uint64(seed), _ptr(base_noise), counts))
+        n, steps = C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.gsb_trainer_count(self.h, C.byref(n), C.byref(steps)))
+        self.tN = int(n.value)
+        return {"keep": counts[0], "split": counts[1], "clone": counts[2], "prune": counts[3], "total": counts[4], "n": self.tN}
+
+    def trainer_count(self):
+        n, steps = C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.gsb_trainer_count(self.h, C.byref(n), C.byref(steps)))
+        return int(n.value), int(steps.value)
+
     # ---- stats ------------------------------------------------------------------------------
     def stats(self) -> Dict:
         st = GsbStats()

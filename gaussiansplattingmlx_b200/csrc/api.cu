@@ -116,6 +116,7 @@ struct Ctx {
 
     // trainer state
     int tN = 0;
+    int t_accum_steps = 0;           // iterations accumulated into t_accum since the last reset (denomGradAccumulation)
     float* t_block = nullptr;         // params | grads | m | v, each 6 tensors, 16-byte aligned segments
     float* t_p[6]{}; float* t_g[6]{}; float* t_m[6]{}; float* t_v[6]{};
     long long t_count[6]{};
@@ -247,7 +248,8 @@ static int ensure_gaussians(Ctx* c, int N)
         return GSB_ERR_INVALID;
     }
     sync_all_streams(c);
-    const int cap = c->cfg.max_gaussians > 0 ? c->cfg.max_gaussians : std::max(N, 1024);
+    // max_gaussians == 0: grow on demand, geometrically (densification raises N every 100 iterations)
+    const int cap = c->cfg.max_gaussians > 0 ? c->cfg.max_gaussians : std::max(std::max(N, 1024), c->capN + c->capN / 2);
     dev_free(c->grad_rec); dev_free(c->grad_rec2); dev_free(c->act_tmp); dev_free(c->offsets_ref);
     GSB_CUDA_CHECK(c, dev_alloc(&c->grad_rec, (size_t)cap * REC_FLOATS));
     GSB_CUDA_CHECK(c, dev_alloc(&c->grad_rec2, (size_t)cap * REC_FLOATS));
@@ -1091,6 +1093,41 @@ int gsb_adam_step(gsb_ctx* ctx, int32_t N, float* const* host_params, const floa
 }
 
 // ---- trainer -------------------------------------------------------------------------------------
+// Layout of one trainer block: params | grads | m | v, each the six tensors in 128-byte aligned segments.
+struct TrainerLayout {
+    long long cnt[6];
+    size_t off[7];
+    size_t floats;
+};
+static TrainerLayout trainer_layout(int N, int K)
+{
+    TrainerLayout L;
+    const long long cnt[6] = {(long long)N * 3, (long long)N * 3, (long long)N * (K - 1) * 3, (long long)N * 3, (long long)N * 4, (long long)N};
+    L.off[0] = 0;
+    for (int k = 0; k < 6; ++k) {
+        L.cnt[k] = cnt[k];
+        L.off[k + 1] = L.off[k] + (((size_t)cnt[k] + 31) & ~(size_t)31);
+    }
+    L.floats = L.off[6];
+    return L;
+}
+// adopts `block` (zeroed grads/m/v expected) and `accum` as the trainer state for N Gaussians
+static void trainer_adopt(Ctx* c, int N, const TrainerLayout& L, float* block, float* accum)
+{
+    c->t_block = block;
+    c->t_accum = accum;
+    c->t_floats = L.floats;
+    for (int k = 0; k < 6; ++k) {
+        c->t_count[k] = L.cnt[k];
+        c->t_p[k] = block + L.off[k];
+        c->t_g[k] = block + L.floats + L.off[k];
+        c->t_m[k] = block + 2 * L.floats + L.off[k];
+        c->t_v[k] = block + 3 * L.floats + L.off[k];
+    }
+    c->tN = N;
+    c->t_accum_steps = 0;
+}
+
 int gsb_trainer_init(gsb_ctx* ctx, int32_t N, const float* host_xyz, const float* host_f_dc, const float* host_f_rest,
                      const float* host_scales_log, const float* host_rot_raw, const float* host_opacity_logit)
 {
@@ -1100,33 +1137,24 @@ int gsb_trainer_init(gsb_ctx* ctx, int32_t N, const float* host_xyz, const float
                 "gsb_trainer_init: null argument");
     int rc = gsb::ensure_gaussians(c, N);
     if (rc != GSB_OK) return rc;
-    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    gsb::sync_all_streams(c);
     gsb::dev_free(c->t_block); gsb::dev_free(c->t_accum);
-    const long long cnt[6] = {(long long)N * 3, (long long)N * 3, (long long)N * (K - 1) * 3, (long long)N * 3, (long long)N * 4, (long long)N};
-    size_t off[7];
-    off[0] = 0;
-    for (int k = 0; k < 6; ++k) {
-        c->t_count[k] = cnt[k];
-        off[k + 1] = off[k] + (((size_t)cnt[k] + 31) & ~(size_t)31);   // 128-byte aligned segments
-    }
-    c->t_floats = off[6];
-    GSB_CUDA_CHECK(c, gsb::dev_alloc(&c->t_block, c->t_floats * 4));
-    GSB_CUDA_CHECK(c, gsb::dev_alloc(&c->t_accum, (size_t)N));
+    c->tN = 0;
+    const TrainerLayout L = trainer_layout(N, K);
+    float *block = nullptr, *accum = nullptr;
+    GSB_CUDA_CHECK(c, gsb::dev_alloc(&block, L.floats * 4));
+    cudaError_t e = gsb::dev_alloc(&accum, (size_t)N);
+    if (e != cudaSuccess) { cudaFree(block); GSB_CUDA_CHECK(c, e); }
+    trainer_adopt(c, N, L, block, accum);
     GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block, 0, c->t_floats * 4 * sizeof(float), c->stream));
     GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_accum, 0, (size_t)N * sizeof(float), c->stream));
     const float* src[6] = {host_xyz, host_f_dc, host_f_rest, host_scales_log, host_rot_raw, host_opacity_logit};
-    for (int k = 0; k < 6; ++k) {
-        c->t_p[k] = c->t_block + off[k];
-        c->t_g[k] = c->t_block + c->t_floats + off[k];
-        c->t_m[k] = c->t_block + 2 * c->t_floats + off[k];
-        c->t_v[k] = c->t_block + 3 * c->t_floats + off[k];
-        if (cnt[k] > 0)
-            GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->t_p[k], src[k], (size_t)cnt[k] * 4, cudaMemcpyDefault, c->stream));
-    }
+    for (int k = 0; k < 6; ++k)
+        if (L.cnt[k] > 0)
+            GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->t_p[k], src[k], (size_t)L.cnt[k] * 4, cudaMemcpyDefault, c->stream));
     for (int i = 0; i < 2; ++i)
         if (!c->t_target[i]) GSB_CUDA_CHECK(c, gsb::dev_alloc(&c->t_target[i], (size_t)c->P * 3));
     GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-    c->tN = N;
     return GSB_OK;
 }
 
@@ -1276,6 +1304,7 @@ int gsb_trainer_apply(gsb_ctx* ctx, int32_t iteration, int32_t total_iterations,
     GSB_CUDA_CHECK(c, gsb::launch_adam(c->stream, t, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, c->tN,
                                        c->t_accum, nullptr, &launches));
     c->stats.kernel_launches += launches;
+    c->t_accum_steps += 1;   // addGradientAccumulation (GaussianTrainer.swift:724-742)
     return GSB_OK;
 }
 
@@ -1286,6 +1315,138 @@ int gsb_train_step(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams, const f
     int rc = gsb_trainer_accumulate(ctx, B, host_cams, host_targets, targets_on_host, 1, 1.0f / (float)B, host_loss);
     if (rc != GSB_OK) return rc;
     return gsb_trainer_apply(ctx, iteration, total_iterations, 0);
+}
+
+// ---- densification -------------------------------------------------------------------------------
+int gsb_densify_classify(gsb_ctx* ctx, int32_t N, const float* grad_accum, float denom, const float* scales_log,
+                         const float* opacity_logit, float grad_threshold, float max_scale, float min_opacity,
+                         int32_t allow_densify, int32_t* actions, int32_t* output_counts)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, N >= 0 && grad_accum && scales_log && opacity_logit && actions && output_counts, "gsb_densify_classify: null argument");
+    GSB_CUDA_CHECK(c, gsb::launch_densify_classify(c->stream, N, grad_accum, denom, scales_log, opacity_logit, grad_threshold, max_scale,
+                                                   min_opacity, allow_densify, actions, output_counts, nullptr));
+    c->stats.kernel_launches += N > 0;
+    return GSB_OK;
+}
+
+int gsb_densify_map(gsb_ctx* ctx, int32_t N, const int32_t* actions, const int32_t* output_counts, int32_t* offsets, int32_t capacity,
+                    int32_t* gather_indices, int32_t* noise_mode, int32_t* host_total)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, N >= 0 && capacity >= 0 && actions && output_counts && gather_indices && noise_mode, "gsb_densify_map: null argument");
+    uint32_t* off = reinterpret_cast<uint32_t*>(offsets);
+    uint32_t* tmp = nullptr;
+    void* ws = nullptr;
+    if (!off) { GSB_CUDA_CHECK(c, gsb::dev_alloc(&tmp, (size_t)N)); off = tmp; }
+    cudaError_t e = cudaMalloc(&ws, gsb::scan_ws_bytes(N));
+    Ctx::ViewBufs& v = c->vb[c->cur];
+    if (e == cudaSuccess) e = gsb::launch_exclusive_scan(c->stream, N, reinterpret_cast<const uint32_t*>(output_counts), nullptr, nullptr, nullptr,
+                                                         off, &v.d_ctl[2], ws);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&v.h_ctl[2], &v.d_ctl[2], 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = gsb::launch_densify_map(c->stream, N, actions, off, (uint32_t)capacity, gather_indices, noise_mode);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (tmp) cudaFree(tmp);
+    if (ws) cudaFree(ws);
+    GSB_CUDA_CHECK(c, e);
+    if (host_total) *host_total = (int32_t)v.h_ctl[2];
+    c->stats.kernel_launches += 2;
+    if ((int64_t)v.h_ctl[2] > capacity) { gsb::set_error(c, "gsb_densify_map: output map larger than capacity"); return GSB_ERR_CAPACITY; }
+    return GSB_OK;
+}
+
+int gsb_densify_apply(gsb_ctx* ctx, int32_t N_out, const int32_t* gather_indices, const int32_t* noise_mode, const float* base_noise,
+                      uint64_t seed, const float* xyz, const float* f_dc, const float* f_rest, const float* scales_log,
+                      const float* rot_raw, const float* opacity_logit, float* o_xyz, float* o_f_dc, float* o_f_rest, float* o_scales_log,
+                      float* o_rot_raw, float* o_opacity_logit)
+{
+    CTX_PROLOGUE(ctx);
+    const int K = c->cfg.sh_coeffs;
+    GSB_REQUIRE(c, N_out >= 0 && gather_indices && noise_mode && xyz && f_dc && (f_rest || K == 1) && scales_log && rot_raw &&
+                       opacity_logit && o_xyz && o_f_dc && (o_f_rest || K == 1) && o_scales_log && o_rot_raw && o_opacity_logit,
+                "gsb_densify_apply: null argument");
+    const float* in6[6] = {xyz, f_dc, f_rest, scales_log, rot_raw, opacity_logit};
+    float* out6[6] = {o_xyz, o_f_dc, o_f_rest, o_scales_log, o_rot_raw, o_opacity_logit};
+    GSB_CUDA_CHECK(c, gsb::launch_densify_apply(c->stream, N_out, K, gather_indices, noise_mode, base_noise, seed, in6, out6));
+    c->stats.kernel_launches += N_out > 0;
+    return GSB_OK;
+}
+
+int gsb_trainer_count(gsb_ctx* ctx, int32_t* host_N, int32_t* host_accum_steps)
+{
+    CTX_PROLOGUE(ctx);
+    if (host_N) *host_N = c->tN;
+    if (host_accum_steps) *host_accum_steps = c->t_accum_steps;
+    return GSB_OK;
+}
+
+int gsb_trainer_densify(gsb_ctx* ctx, float grad_threshold, float max_scale, float min_opacity, int32_t max_gaussians, uint64_t seed,
+                        const float* base_noise, int32_t* host_counts5)
+{
+    CTX_PROLOGUE(ctx);
+    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    const int N = c->tN, K = c->cfg.sh_coeffs;
+    gsb::sync_all_streams(c);
+    // scratch: actions | counts | offsets in the [capN,12] float parity buffer (capN >= N)
+    int* actions = reinterpret_cast<int*>(c->act_tmp);
+    int* counts = actions + N;
+    uint32_t* offsets = reinterpret_cast<uint32_t*>(counts + N);
+    Ctx::ViewBufs& v = c->vb[0];
+    uint32_t* d_stats = reinterpret_cast<uint32_t*>(c->loss_accum);   // 4 words of scratch
+    const int allow = N < max_gaussians ? 1 : 0;   // GaussianTrainer.swift:785
+    GSB_CUDA_CHECK(c, gsb::launch_densify_classify(c->stream, N, c->t_accum, (float)c->t_accum_steps, c->t_p[3], c->t_p[5], grad_threshold,
+                                                   max_scale, min_opacity, allow, actions, counts, d_stats));
+    GSB_CUDA_CHECK(c, gsb::launch_exclusive_scan(c->stream, N, reinterpret_cast<const uint32_t*>(counts), nullptr, nullptr, nullptr, offsets,
+                                                 &v.d_ctl[2], v.scan_ws));
+    uint32_t h[5] = {0, 0, 0, 0, 0};
+    GSB_CUDA_CHECK(c, cudaMemcpyAsync(h, d_stats, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    GSB_CUDA_CHECK(c, cudaMemcpyAsync(&h[4], &v.d_ctl[2], sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    GSB_CUDA_CHECK(c, cudaMemsetAsync(c->loss_accum, 0, 4 * sizeof(float), c->stream));
+    c->stats.kernel_launches += 2;
+    if (host_counts5) for (int i = 0; i < 5; ++i) host_counts5[i] = (int32_t)h[i];
+    const uint32_t total = h[4];
+    const bool unchanged = total == 0 || (h[1] == 0 && h[2] == 0 && h[3] == 0);   // :820-838
+    if (unchanged) {   // resetGradientAccumulation on every exit path
+        GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_accum, 0, (size_t)N * sizeof(float), c->stream));
+        c->t_accum_steps = 0;
+        return GSB_OK;
+    }
+    const int Nout = (int)total;
+    if (c->cfg.max_gaussians > 0 && Nout > c->cfg.max_gaussians) {
+        gsb::set_error(c, "gsb_trainer_densify: output count exceeds gsb_config.max_gaussians (use 0 = grow on demand)");
+        return GSB_ERR_CAPACITY;
+    }
+    int* gather = nullptr; int* mode = nullptr; float* block = nullptr; float* accum = nullptr;
+    const TrainerLayout L = trainer_layout(Nout, K);
+    cudaError_t e = gsb::dev_alloc(&gather, (size_t)Nout);
+    if (e == cudaSuccess) e = gsb::dev_alloc(&mode, (size_t)Nout);
+    if (e == cudaSuccess) e = gsb::dev_alloc(&block, L.floats * 4);
+    if (e == cudaSuccess) e = gsb::dev_alloc(&accum, (size_t)Nout);
+    if (e == cudaSuccess) e = cudaMemsetAsync(block, 0, L.floats * 4 * sizeof(float), c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(accum, 0, (size_t)Nout * sizeof(float), c->stream);
+    if (e == cudaSuccess) e = gsb::launch_densify_map(c->stream, N, actions, offsets, (uint32_t)Nout, gather, mode);
+    if (e == cudaSuccess) {
+        const float* in6[6] = {c->t_p[0], c->t_p[1], c->t_p[2], c->t_p[3], c->t_p[4], c->t_p[5]};
+        float* out6[6];
+        for (int k = 0; k < 6; ++k) out6[k] = block + L.off[k];
+        e = gsb::launch_densify_apply(c->stream, Nout, K, gather, mode, base_noise, seed, in6, out6);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (gather) cudaFree(gather);
+    if (mode) cudaFree(mode);
+    if (e != cudaSuccess) {
+        if (block) cudaFree(block);
+        if (accum) cudaFree(accum);
+        GSB_CUDA_CHECK(c, e);
+    }
+    c->stats.kernel_launches += 2;
+    // commit (GaussianTrainer.swift:899-907) + fresh optimiser state (:1104-1109)
+    gsb::dev_free(c->t_block); gsb::dev_free(c->t_accum);
+    trainer_adopt(c, Nout, L, block, accum);
+    c->saved.valid = false;
+    c->bin_valid = false;
+    return gsb::ensure_gaussians(c, Nout);
 }
 
 // ---- stats ---------------------------------------------------------------------------------------

@@ -142,4 +142,13 @@ struct AdamTensors {
 cudaError_t launch_adam(cudaStream_t st, const AdamTensors& t, float beta1, float beta2, float eps, float gscale, int N,
                         float* grad_norm_accum, const uint32_t* skip_flag, int* launches);
 
+// ---- densify.cu --------------------------------------------------------------------------------
+cudaError_t launch_densify_classify(cudaStream_t st, int N, const float* grad_accum, float denom, const float* scales_log,
+                                    const float* opacity_logit, float grad_threshold, float max_scale, float min_opacity,
+                                    int allow_densify, int* actions, int* counts, uint32_t* stats4);
+cudaError_t launch_densify_map(cudaStream_t st, int N, const int* actions, const uint32_t* offsets, uint32_t capacity, int* gather,
+                               int* noise_mode);
+cudaError_t launch_densify_apply(cudaStream_t st, int Nout, int K, const int* gather, const int* noise_mode, const float* base_noise,
+                                 uint64_t seed, const float* const* in6, float* const* out6);
+
 }  // namespace gsb

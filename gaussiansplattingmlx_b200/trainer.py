@@ -3,8 +3,8 @@
 
 One iteration = ``gsb_trainer_accumulate`` (per view: render → loss → backward, gradients summed with
 weight 1/B) → optional view-parallel all-reduce → ``gsb_trainer_apply`` (Adam + D1 grad-norm accumulation).
-With ``views_per_step == 1`` and one rank this is the reference iteration; densification (D2/D3) is a
-"next" row and is not run here — only the optimiser-state reset cadence is kept.
+With ``views_per_step == 1`` and one rank this is the reference iteration, including ``split_and_prune`` every
+``split_and_prune_per_iteration`` iterations (``gsb_trainer_densify``) and the optimiser-state reset cadence.
 """
 from __future__ import annotations
 
@@ -40,6 +40,14 @@ class GaussianTrainer:
     lambda_dssim = 0.2
     lambda_depth = 0.0
     optimizer_reset_interval = 100
+    # split and prune parameters (GaussianTrainer.swift:281, 293-300)
+    split_and_prune_per_iteration = 100
+    gradientThreshold = 0.0002
+    minOpacity = 0.005
+    maxScale = 0.01
+    densifyFromIter = 500
+    densifyUntilIter = 15000
+    maxGaussians = 1_000_000
 
     def __init__(self, model: GaussModel, data: TrainData, gaussRender: GaussianRenderer, iterationCount: int,
                  views_per_step: int = 1, parallel: Optional[ViewParallel] = None, seed: Optional[int] = None,
@@ -49,6 +57,9 @@ class GaussianTrainer:
         self.views_per_step = views_per_step
         self.parallel = parallel or ViewParallel()
         self.reset_optimizer_state = reset_optimizer_state
+        self.densify = True
+        self.densify_seed = 0 if seed is None else int(seed)
+        self.densify_log: List[Dict[str, int]] = []
         self.forceStop = False
         self.delegate: Optional[Callable[[float, int], None]] = None   # pushLoss(loss, iteration)
         self._rng = random.Random(seed)
@@ -85,10 +96,25 @@ class GaussianTrainer:
         # (GaussianTrainer.swift:1098-1109); zeroing before the next update is the same thing
         ctx.trainer_apply(iteration, self.iterationCount, reset_state=False)
         if reset:
+            if self.densify:
+                self.split_and_prune(iteration)
             tt = ctx.trainer_tensors()
             for k in PARAM_ORDER:
                 tt["m"][k].zero_(); tt["v"][k].zero_()
         return loss
+
+    def split_and_prune(self, iteration: int):
+        """``GaussianTrainer.split_and_prune`` (``GaussianTrainer.swift:766-908``): iteration guard on the host, the rest in
+        ``gsb_trainer_densify``.  The noise is drawn from a counter-based generator keyed by (seed, iteration) so that every
+        view-parallel replica produces identical tensors."""
+        if not (self.densifyFromIter <= iteration <= self.densifyUntilIter):
+            return None
+        info = self.gaussRender.ctx.trainer_densify(self.gradientThreshold, self.maxScale, self.minOpacity, self.maxGaussians,
+                                                    seed=(self.densify_seed << 32) ^ iteration)
+        self.densify_log.append(dict(info, iteration=iteration))
+        if self.parallel.world > 1:
+            self._grad_block = self.gaussRender.ctx.trainer_grad_block()
+        return info
 
     def startTrain(self, earlyStoppingThreshold: float = 1e-4):
         for iteration in range(self.iterationCount):
@@ -108,4 +134,4 @@ class GaussianTrainer:
         """Copy the trained parameters back into the host-side ``GaussModel``."""
         tt = self.gaussRender.ctx.trainer_tensors()
         for k in PARAM_ORDER:
-            setattr(self.model, k, tt["params"][k].cpu().numpy().reshape(getattr(self.model, k).shape))
+            setattr(self.model, k, tt["params"][k].cpu().numpy().copy())

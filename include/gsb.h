@@ -208,6 +208,33 @@ GSB_API int gsb_trainer_apply(gsb_ctx*, int32_t iteration, int32_t total_iterati
 GSB_API int gsb_train_step(gsb_ctx*, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
                    int32_t targets_on_host, int32_t iteration, int32_t total_iterations, float* host_loss);
 
+/* ---- densification: split_and_prune (Trainer/GaussianTrainer.swift:766-908) ------------------
+ * D2 classify_gaussians (:344-392): actions i32[N] = 0 keep / 1 split / 2 clone / 3 prune and the per-Gaussian
+ * output count 1 / 2 / 2 / 0.  denom = denomGradAccumulation (iterations accumulated into grad_accum). */
+GSB_API int gsb_densify_classify(gsb_ctx*, int32_t N, const float* grad_accum, float denom, const float* scales_log,
+                         const float* opacity_logit, float grad_threshold, float max_scale, float min_opacity,
+                         int32_t allow_densify, int32_t* actions, int32_t* output_counts);
+/* cumsum -> offsets (:813-817) + D3 build_densify_output_map (:397-427).  offsets i32[N] may be NULL.
+ * gather_indices / noise_mode have `capacity` slots (2N always suffices); *host_total = total output count
+ * (synchronises).  noise_mode: 0 none, 1 split first, 2 split second, 3 clone copy. */
+GSB_API int gsb_densify_map(gsb_ctx*, int32_t N, const int32_t* actions, const int32_t* output_counts, int32_t* offsets,
+                    int32_t capacity, int32_t* gather_indices, int32_t* noise_mode, int32_t* host_total);
+/* Phases 4-5 (:866-897): gather the six raw tensors into N_out slots; split children get scale / 1.6 and
+ * +-0.1*mean(exp(scale))*noise, clone copies 0.01*noise.  base_noise f32[N_out,3] stands for
+ * MLXRandom.normal([totalOutput,3]); NULL draws it from a counter-based generator keyed by (seed, slot). */
+GSB_API int gsb_densify_apply(gsb_ctx*, int32_t N_out, const int32_t* gather_indices, const int32_t* noise_mode,
+                      const float* base_noise, uint64_t seed, const float* xyz, const float* f_dc, const float* f_rest,
+                      const float* scales_log, const float* rot_raw, const float* opacity_logit, float* o_xyz, float* o_f_dc,
+                      float* o_f_rest, float* o_scales_log, float* o_rot_raw, float* o_opacity_logit);
+/* split_and_prune on the trainer's own tensors: classify with the accumulated gradient norms, rebuild parameters
+ * (new Gaussian count), re-create the Adam state and reset the accumulation (GaussianTrainer.swift:1098-1109).
+ * max_gaussians: densification is allowed while N < max_gaussians (:785).  base_noise: device f32[>= 2N,3] or NULL.
+ * host_counts5 (may be NULL) = {keep, split, clone, prune, total}.  Synchronises. */
+GSB_API int gsb_trainer_densify(gsb_ctx*, float grad_threshold, float max_scale, float min_opacity, int32_t max_gaussians,
+                        uint64_t seed, const float* base_noise, int32_t* host_counts5);
+/* current Gaussian count of the trainer and the number of iterations accumulated since the last reset */
+GSB_API int gsb_trainer_count(gsb_ctx*, int32_t* host_N, int32_t* host_accum_steps);
+
 /* ---- introspection for bench.py / profiles ------------------------------------------------- */
 typedef struct gsb_stats {
     uint64_t kernel_launches;   /* CUDA kernels launched by this library since the last reset */

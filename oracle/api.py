@@ -192,6 +192,35 @@ class Port(_Base):
     def accum_grad_norm(self, xyz_grad, accum):
         self.lib.gso_accum_grad_norm(xyz_grad.shape[0], _p(_f(xyz_grad)), _p(accum))
 
+    # ---- densification (D2, D3, gather + noise) ----------------------------------------------
+    def classify_gaussians(self, accum, denom, scales_log, opacity_logit, grad_threshold, max_scale, min_opacity, allow_densify):
+        n = accum.shape[0]
+        actions = np.zeros(n, np.int32); counts = np.zeros(n, np.int32)
+        self.lib.gso_classify_gaussians(n, _p(_f(accum)), C.c_float(denom), _p(_f(scales_log)), _p(_f(opacity_logit).reshape(-1)),
+                                        C.c_float(grad_threshold), C.c_float(max_scale), C.c_float(min_opacity),
+                                        int(bool(allow_densify)), _p(actions), _p(counts))
+        return actions, counts
+
+    def build_densify_output_map(self, actions, offsets, total):
+        gather = np.zeros(total, np.int32); mode = np.zeros(total, np.int32)
+        self.lib.gso_build_densify_output_map(actions.shape[0], _p(np.ascontiguousarray(actions, np.int32)),
+                                              _p(np.ascontiguousarray(offsets, np.int32)), _p(gather), _p(mode))
+        return gather, mode
+
+    def densify_apply(self, params, gather, noise_mode, base_noise):
+        """Phases 4-5 of split_and_prune; returns the new parameter dict."""
+        nout = gather.shape[0]
+        K = params["_features_rest"].shape[1] + 1
+        out = {"_xyz": np.zeros((nout, 3), f32), "_features_dc": np.zeros((nout, 1, 3), f32),
+               "_features_rest": np.zeros((nout, K - 1, 3), f32), "_scales": np.zeros((nout, 3), f32),
+               "_rotation": np.zeros((nout, 4), f32), "_opacity": np.zeros((nout, 1), f32)}
+        self.lib.gso_densify_apply(nout, K, _p(np.ascontiguousarray(gather, np.int32)), _p(np.ascontiguousarray(noise_mode, np.int32)),
+                                   _p(_f(base_noise)), _p(_f(params["_xyz"])), _p(_f(params["_features_dc"])),
+                                   _p(_f(params["_features_rest"])), _p(_f(params["_scales"])), _p(_f(params["_rotation"])),
+                                   _p(_f(params["_opacity"])), _p(out["_xyz"]), _p(out["_features_dc"]), _p(out["_features_rest"]),
+                                   _p(out["_scales"]), _p(out["_rotation"]), _p(out["_opacity"]))
+        return out
+
 
 class Ref(_Base):
     """The reference's own kernels (JSON MSL → g++).  Buffer order = each JSON's buffer_parameters."""
@@ -324,5 +353,29 @@ class Ref(_Base):
     def adam(self, *a, **k):
         return self._port().adam(*a, **k)
 
-    def accum_grad_norm(self, *a, **k):
-        return self._port().accum_grad_norm(*a, **k)
+    def accum_grad_norm(self, xyz_grad, accum):
+        """D1 through the reference's own inline Metal kernel (GaussianTrainer.swift:321-339); in place."""
+        n = accum.shape[0]
+        out = np.zeros(n, f32)
+        self._run("accum_grad_norm", n, 1, [_f(xyz_grad).reshape(-1), accum, np.array([n], np.int32), out])
+        accum[:] = out
+
+    def classify_gaussians(self, accum, denom, scales_log, opacity_logit, grad_threshold, max_scale, min_opacity, allow_densify):
+        n = accum.shape[0]
+        actions = np.zeros(n, np.int32); counts = np.zeros(n, np.int32)
+        sl = _f(scales_log)
+        self._run("classify_gaussians", n, 1, [
+            _f(accum), np.array([n], np.int32), np.full(n, denom, f32), sl, np.array(sl.shape, np.int32), _f(opacity_logit).reshape(-1),
+            np.array([grad_threshold], f32), np.array([max_scale], f32), np.array([min_opacity], f32),
+            np.array([1 if allow_densify else 0], np.int32), actions, counts])
+        return actions, counts
+
+    def build_densify_output_map(self, actions, offsets, total):
+        gather = np.zeros(total, np.int32); mode = np.zeros(total, np.int32)
+        a = np.ascontiguousarray(actions, np.int32)
+        self._run("build_densify_output_map", a.shape[0], 1, [a, np.array([a.shape[0]], np.int32),
+                                                              np.ascontiguousarray(offsets, np.int32), gather, mode])
+        return gather, mode
+
+    def densify_apply(self, *a, **k):   # MLX gather + arithmetic in the reference (no kernel): the port's restatement
+        return self._port().densify_apply(*a, **k)

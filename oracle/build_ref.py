@@ -43,7 +43,9 @@ import tempfile
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-REF_SLANG_DIR = Path(os.environ.get("GSB_REFERENCE_ROOT", "/root/reference")) / "GaussianSplattingMlx" / "Slang"
+REF_ROOT = Path(os.environ.get("GSB_REFERENCE_ROOT", "/root/reference"))
+REF_SLANG_DIR = REF_ROOT / "GaussianSplattingMlx" / "Slang"
+REF_TRAINER_SWIFT = REF_ROOT / "GaussianSplattingMlx" / "Trainer" / "GaussianTrainer.swift"
 OUT_DIR = HERE / "_ref"
 OUT_SO = OUT_DIR / "libgsref.so"
 
@@ -206,6 +208,56 @@ extern "C" void ref_stable_sort_tile_keys(
 """
 
 
+# ------------------------------------------------------------------------------------------------
+# The three densification kernels are NOT shipped as JSON: they are inline Metal strings handed to
+# MLXFast.metalKernel(name:inputNames:outputNames:source:) in Trainer/GaussianTrainer.swift:321-427.
+# Their bodies are extracted from the Swift file where it lies and wrapped with the buffer signature MLX
+# generates for them (pointer per array input/output, `<name>_shape` int arrays, scalars by reference).
+# ------------------------------------------------------------------------------------------------
+INLINE_KERNELS = {
+    # name: (signature, call expression) — b[] is the void* buffer table handed to ref_<name>()
+    "accum_grad_norm": (
+        "const float* xyz_grad, const float* accum_in, const int* accum_in_shape, float* accum_out",
+        "(const float*)b[0], (const float*)b[1], (const int*)b[2], (float*)b[3]"),
+    "classify_gaussians": (
+        "const float* grad_accum, const int* grad_accum_shape, const float* denom_accum, const float* scales, "
+        "const int* scales_shape, const float* opacity, const float& grad_threshold, const float& max_scale_thresh, "
+        "const float& min_opacity_thresh, const int& allow_densify, int* actions, int* output_counts",
+        "(const float*)b[0], (const int*)b[1], (const float*)b[2], (const float*)b[3], (const int*)b[4], (const float*)b[5], "
+        "*(const float*)b[6], *(const float*)b[7], *(const float*)b[8], *(const int*)b[9], (int*)b[10], (int*)b[11]"),
+    "build_densify_output_map": (
+        "const int* actions, const int* actions_shape, const int* offsets, int* gather_indices, int* noise_mode",
+        "(const int*)b[0], (const int*)b[1], (const int*)b[2], (int*)b[3], (int*)b[4]"),
+}
+
+
+def _inline_kernel_source(swift: str, name: str) -> str:
+    m = re.search(r'name:\s*"' + re.escape(name) + r'".*?source:\s*"""(.*?)"""', swift, flags=re.S)
+    if not m:
+        raise RuntimeError(f"inline Metal kernel {name} not found in {REF_TRAINER_SWIFT}")
+    return m.group(1)
+
+
+def _emit_inline(name: str, body: str) -> str:
+    sig, call = INLINE_KERNELS[name]
+    return f"""
+namespace k_{name} {{
+static inline float fmax(float a, float b) {{ return a > b ? a : b; }}
+static inline void body(uint3 thread_position_in_grid, {sig})
+{{
+{body}
+}}
+}}  // namespace
+extern "C" void ref_{name}(unsigned gx, unsigned gy, void** b)
+{{
+    const long total = (long)gx * (long)gy;
+    #pragma omp parallel for schedule(static)
+    for (long i = 0; i < total; ++i)
+        k_{name}::body(uint3((unsigned)(i % gx), (unsigned)(i / gx), 0u), {call});
+}}
+"""
+
+
 def generate_source() -> str:
     parts = [
         "// GENERATED in a temporary directory by oracle/build_ref.py — never committed.\n",
@@ -218,7 +270,10 @@ def generate_source() -> str:
     parts.append("namespace k_gaussian_tile_global_backward {\n" + _strip_includes(bwd["header"]) + "\n}\n")
     parts.append(RASTER_BWD_DRIVER)
     parts.append(STABLE_SORT)
-    parts.append('extern "C" int ref_abi_version() { return 1; }\n')
+    swift = REF_TRAINER_SWIFT.read_text()
+    for name in INLINE_KERNELS:
+        parts.append(_emit_inline(name, _inline_kernel_source(swift, name)))
+    parts.append('extern "C" int ref_abi_version() { return 2; }\n')
     return "".join(parts)
 
 

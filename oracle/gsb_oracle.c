@@ -895,3 +895,78 @@ GSO_API void gso_accum_grad_norm(int N, const float* xyzGrad, float* accum)
         accum[i] = accum[i] + sqrtf(gx * gx + gy * gy + gz * gz);
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Densification.  D2 classify_gaussians (Trainer/GaussianTrainer.swift:344-392):
+ *   avg_grad = denom > 0 ? accum/denom : 0;  max_scale = max(exp(s0), exp(s1), exp(s2));
+ *   op = 1/(1+exp(-raw));  prune (3, count 0) if op < min_opacity; else if allow_densify and
+ *   avg_grad > grad_threshold: split (1, count 2) if max_scale > max_scale_thresh else clone (2, count 2);
+ *   else keep (0, count 1).
+ * ---------------------------------------------------------------------------------------- */
+GSO_API void gso_classify_gaussians(int N, const float* grad_accum, float denom, const float* scales_log,
+                                    const float* opacity_logit, float grad_threshold, float max_scale_thresh,
+                                    float min_opacity_thresh, int allow_densify, int* actions, int* output_counts)
+{
+    #pragma omp parallel for
+    for (int i = 0; i < N; ++i) {
+        float g = grad_accum[i];
+        float avg = denom > 0.0f ? g / denom : 0.0f;
+        float s0 = expf(scales_log[i * 3]), s1 = expf(scales_log[i * 3 + 1]), s2 = expf(scales_log[i * 3 + 2]);
+        float mx = fmaxf_(fmaxf_(s0, s1), s2);
+        float op = 1.0f / (1.0f + expf(-opacity_logit[i]));
+        int action, cnt;
+        if (op < min_opacity_thresh) { action = 3; cnt = 0; }
+        else if (allow_densify && avg > grad_threshold) {
+            if (mx > max_scale_thresh) { action = 1; cnt = 2; } else { action = 2; cnt = 2; }
+        } else { action = 0; cnt = 1; }
+        actions[i] = action;
+        output_counts[i] = cnt;
+    }
+}
+
+/* D3 build_densify_output_map (Trainer/GaussianTrainer.swift:397-427): offsets = exclusive scan of counts.
+ * noise_mode: 0 none (keep / clone original), 1 split first, 2 split second, 3 clone copy. */
+GSO_API void gso_build_densify_output_map(int N, const int* actions, const int* offsets, int* gather, int* noise_mode)
+{
+    #pragma omp parallel for
+    for (int i = 0; i < N; ++i) {
+        int a = actions[i], o = offsets[i];
+        if (a == 0) { gather[o] = i; noise_mode[o] = 0; }
+        else if (a == 1) { gather[o] = i; noise_mode[o] = 1; gather[o + 1] = i; noise_mode[o + 1] = 2; }
+        else if (a == 2) { gather[o] = i; noise_mode[o] = 0; gather[o + 1] = i; noise_mode[o + 1] = 3; }
+    }
+}
+
+/* Phases 4-5 of split_and_prune (Trainer/GaussianTrainer.swift:866-897): gather the six tensors; split
+ * children get scales + Float(-log(1.6)) and position offset sign * mean(exp(source scales)) * 0.1 * noise
+ * (sign +1 first / -1 second), clone copies get 0.01 * noise.  The MLX expression is evaluated left to right in
+ * f32: ((sign * mean) * 0.1) * n, (flag * 0.01) * n, (xyz + split) + clone; mean over 3 = sum / 3
+ * (MLX mean: parity unpinned).  base_noise[Nout,3] stands for MLXRandom.normal([totalOutput,3]). */
+GSO_API void gso_densify_apply(int Nout, int K, const int* gather, const int* noise_mode, const float* base_noise,
+                               const float* xyz, const float* f_dc, const float* f_rest, const float* scales_log,
+                               const float* rot, const float* opacity, float* o_xyz, float* o_f_dc, float* o_f_rest,
+                               float* o_scales_log, float* o_rot, float* o_opacity)
+{
+    const float red = (float)(-log(1.6));
+    const int R = (K - 1) * 3;
+    #pragma omp parallel for
+    for (int j = 0; j < Nout; ++j) {
+        const int s = gather[j], mode = noise_mode[j];
+        for (int c = 0; c < 3; ++c) o_f_dc[(size_t)j * 3 + c] = f_dc[(size_t)s * 3 + c];
+        for (int c = 0; c < R; ++c) o_f_rest[(size_t)j * R + c] = f_rest[(size_t)s * R + c];
+        for (int c = 0; c < 4; ++c) o_rot[(size_t)j * 4 + c] = rot[(size_t)s * 4 + c];
+        o_opacity[j] = opacity[s];
+        const float isSplit = (mode == 1 || mode == 2) ? 1.0f : 0.0f;
+        for (int c = 0; c < 3; ++c) o_scales_log[(size_t)j * 3 + c] = scales_log[(size_t)s * 3 + c] + isSplit * red;
+        const float e0 = expf(scales_log[(size_t)s * 3]), e1 = expf(scales_log[(size_t)s * 3 + 1]), e2 = expf(scales_log[(size_t)s * 3 + 2]);
+        const float mean = ((e0 + e1) + e2) / 3.0f;
+        const float sign = (mode == 1 ? 1.0f : 0.0f) - (mode == 2 ? 1.0f : 0.0f);
+        const float isClone = mode == 3 ? 1.0f : 0.0f;
+        for (int c = 0; c < 3; ++c) {
+            const float n = base_noise[(size_t)j * 3 + c];
+            const float splitNoise = ((sign * mean) * 0.1f) * n;
+            const float cloneNoise = (isClone * 0.01f) * n;
+            o_xyz[(size_t)j * 3 + c] = (xyz[(size_t)s * 3 + c] + splitNoise) + cloneNoise;
+        }
+    }
+}

@@ -106,3 +106,41 @@ def train_steps(o, params, cams, targets, degree, iterations, total_iterations, 
             o.adam(params[k], grads[k], m[k], v_[k], lrs[i])
         losses.append(loss)
     return params, m, v_, accum, losses
+
+
+# densification defaults (Trainer/GaussianTrainer.swift:293-300)
+DENSIFY_DEFAULTS = dict(gradientThreshold=0.0002, maxScale=0.01, minOpacity=0.005, densifyFromIter=500, densifyUntilIter=15000,
+                        maxGaussians=1_000_000)
+
+
+def split_and_prune(o, params, accum, denom, iteration, base_noise, **kw):
+    """Restatement of ``split_and_prune`` (Trainer/GaussianTrainer.swift:766-908).
+
+    ``base_noise[>=totalOutput,3]`` stands for ``MLXRandom.normal([totalOutput,3])`` (:881), which cannot be
+    reproduced outside MLX.  Returns ``(new_params | None, info)``; ``None`` = the model is unchanged (guards
+    :767, :777-780, :820-838).  The caller resets the gradient accumulation whenever this function is entered
+    past the iteration guard, like the reference does on every exit path.
+    """
+    cfg = dict(DENSIFY_DEFAULTS); cfg.update(kw)
+    info = {"ran": False}
+    if not (cfg["densifyFromIter"] <= iteration <= cfg["densifyUntilIter"]):
+        return None, info
+    n = params["_xyz"].shape[0]
+    info["ran"] = True
+    if n == 0:
+        return None, info
+    allow = n < cfg["maxGaussians"]
+    actions, counts = o.classify_gaussians(accum, float(denom), params["_scales"], params["_opacity"], cfg["gradientThreshold"],
+                                           cfg["maxScale"], cfg["minOpacity"], allow)
+    inclusive = np.cumsum(counts, dtype=np.int64).astype(np.int32)
+    offsets = inclusive - counts
+    total = int(inclusive[-1])
+    num_split, num_clone, num_prune = int((actions == 1).sum()), int((actions == 2).sum()), int((actions == 3).sum())
+    info.update(keep=n - num_split - num_clone - num_prune, split=num_split, clone=num_clone, prune=num_prune, total=total,
+                actions=actions, counts=counts, offsets=offsets)
+    if total == 0 or (num_split == 0 and num_clone == 0 and num_prune == 0):
+        return None, info
+    gather, mode = o.build_densify_output_map(actions, offsets, total)
+    info.update(gather=gather, noise_mode=mode)
+    new = o.densify_apply(params, gather, mode, np.ascontiguousarray(base_noise[:total], np.float32))
+    return new, info
