@@ -51,13 +51,17 @@ class GaussianTrainer:
 
     def __init__(self, model: GaussModel, data: TrainData, gaussRender: GaussianRenderer, iterationCount: int,
                  views_per_step: int = 1, parallel: Optional[ViewParallel] = None, seed: Optional[int] = None,
-                 reset_optimizer_state: bool = True):
+                 reset_optimizer_state: bool = True, outputDirectoryURL: Optional[str] = None,
+                 save_snapshot_per_iteration: int = 100):
         self.model, self.data, self.gaussRender = model, data, gaussRender
         self.iterationCount = iterationCount
         self.views_per_step = views_per_step
         self.parallel = parallel or ViewParallel()
         self.reset_optimizer_state = reset_optimizer_state
         self.densify = True
+        self.outputDirectoryURL = outputDirectoryURL
+        self.save_snapshot_per_iteration = save_snapshot_per_iteration
+        self.snapshots: List[str] = []
         self.densify_seed = 0 if seed is None else int(seed)
         self.densify_log: List[Dict[str, int]] = []
         self.forceStop = False
@@ -95,6 +99,8 @@ class GaussianTrainer:
         # the reference re-creates the Adam state AFTER the update of every 100th iteration
         # (GaussianTrainer.swift:1098-1109); zeroing before the next update is the same thing
         ctx.trainer_apply(iteration, self.iterationCount, reset_state=False)
+        if self.outputDirectoryURL and iteration % self.save_snapshot_per_iteration == 0:
+            self.save_snapshot(iteration)                     # GaussianTrainer.swift:1092 (before split_and_prune)
         if reset:
             if self.densify:
                 self.split_and_prune(iteration)
@@ -115,6 +121,18 @@ class GaussianTrainer:
         if self.parallel.world > 1:
             self._grad_block = self.gaussRender.ctx.trainer_grad_block()
         return info
+
+    def save_snapshot(self, iteration: int):
+        """``GaussianTrainer.save_snapshot`` (``GaussianTrainer.swift:909-929``) + the resume sidecar the reference lacks."""
+        from .ply import save_snapshot, save_resume
+        ctx = self.gaussRender.ctx
+        tt = ctx.trainer_tensors()
+        host = lambda d: {k: v.cpu().numpy() for k, v in d.items()}
+        out = save_snapshot(host(tt["params"]), self.outputDirectoryURL, iteration)
+        save_resume(str(out)[:-4] + ".resume.npz", iteration, host(tt["m"]), host(tt["v"]), tt["accum"].cpu().numpy(),
+                    ctx.trainer_count()[1])
+        self.snapshots.append(str(out))
+        return out
 
     def startTrain(self, earlyStoppingThreshold: float = 1e-4):
         for iteration in range(self.iterationCount):
