@@ -117,7 +117,13 @@ struct Ctx {
     // trainer state
     int tN = 0;
     int t_accum_steps = 0;           // iterations accumulated into t_accum since the last reset (denomGradAccumulation)
-    float* t_block = nullptr;         // params | grads | m | v, each 6 tensors, 16-byte aligned segments
+    float* t_block = nullptr;         // params | grads | m | v, each 6 tensors, 128-byte aligned segments (= t_slab[t_cur])
+    // Two capacity-sized slabs (block + accumulator): densification gathers from the current one into the other, so a
+    // clone/split/prune every 100 iterations costs no cudaMalloc/cudaFree unless the capacity itself has to grow.
+    float* t_slab[2] = {nullptr, nullptr};
+    float* t_accum_slab[2] = {nullptr, nullptr};
+    int t_cur = 0;
+    int t_cap = 0;                    // Gaussians each slab can hold
     float* t_p[6]{}; float* t_g[6]{}; float* t_m[6]{}; float* t_v[6]{};
     long long t_count[6]{};
     size_t t_floats = 0;              // padded floats of one copy of the six tensors
@@ -481,7 +487,7 @@ static void destroy_ctx(Ctx* c)
     dev_free(c->out_color); dev_free(c->out_depth); dev_free(c->out_alpha); dev_free(c->out_last);
     dev_free(c->mapA); dev_free(c->mapB); dev_free(c->mapC); dev_free(c->cot_render); dev_free(c->partial);
     dev_free(c->loss_accum); dev_free(c->d_zero);
-    dev_free(c->t_block); dev_free(c->t_accum);
+    for (int i = 0; i < 2; ++i) { dev_free(c->t_slab[i]); dev_free(c->t_accum_slab[i]); }
     if (c->h_loss) cudaFreeHost(c->h_loss);
     for (auto& e : c->ev_pool) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
     cudaEvent_t* evs[] = {&c->t_target_ready[0], &c->t_target_ready[1], &c->t_target_free[0], &c->t_target_free[1], &c->ev_fork,
@@ -1111,11 +1117,13 @@ static TrainerLayout trainer_layout(int N, int K)
     L.floats = L.off[6];
     return L;
 }
-// adopts `block` (zeroed grads/m/v expected) and `accum` as the trainer state for N Gaussians
-static void trainer_adopt(Ctx* c, int N, const TrainerLayout& L, float* block, float* accum)
+// makes slab `which` (params already in place, grads/m/v/accum zeroed) the trainer state for N Gaussians
+static void trainer_adopt(Ctx* c, int N, const TrainerLayout& L, int which)
 {
+    float* block = c->t_slab[which];
+    c->t_cur = which;
     c->t_block = block;
-    c->t_accum = accum;
+    c->t_accum = c->t_accum_slab[which];
     c->t_floats = L.floats;
     for (int k = 0; k < 6; ++k) {
         c->t_count[k] = L.cnt[k];
@@ -1126,6 +1134,14 @@ static void trainer_adopt(Ctx* c, int N, const TrainerLayout& L, float* block, f
     }
     c->tN = N;
     c->t_accum_steps = 0;
+}
+static cudaError_t trainer_alloc_slab(Ctx* c, int which, int cap)
+{
+    const TrainerLayout L = trainer_layout(cap, c->cfg.sh_coeffs);
+    gsb::dev_free(c->t_slab[which]); gsb::dev_free(c->t_accum_slab[which]);
+    cudaError_t e = gsb::dev_alloc(&c->t_slab[which], L.floats * 4);
+    if (e == cudaSuccess) e = gsb::dev_alloc(&c->t_accum_slab[which], (size_t)cap);
+    return e;
 }
 
 int gsb_trainer_init(gsb_ctx* ctx, int32_t N, const float* host_xyz, const float* host_f_dc, const float* host_f_rest,
@@ -1138,14 +1154,13 @@ int gsb_trainer_init(gsb_ctx* ctx, int32_t N, const float* host_xyz, const float
     int rc = gsb::ensure_gaussians(c, N);
     if (rc != GSB_OK) return rc;
     gsb::sync_all_streams(c);
-    gsb::dev_free(c->t_block); gsb::dev_free(c->t_accum);
     c->tN = 0;
+    for (int i = 0; i < 2; ++i) { gsb::dev_free(c->t_slab[i]); gsb::dev_free(c->t_accum_slab[i]); }
+    c->t_block = nullptr; c->t_accum = nullptr;
+    c->t_cap = N;
+    GSB_CUDA_CHECK(c, trainer_alloc_slab(c, 0, c->t_cap));
     const TrainerLayout L = trainer_layout(N, K);
-    float *block = nullptr, *accum = nullptr;
-    GSB_CUDA_CHECK(c, gsb::dev_alloc(&block, L.floats * 4));
-    cudaError_t e = gsb::dev_alloc(&accum, (size_t)N);
-    if (e != cudaSuccess) { cudaFree(block); GSB_CUDA_CHECK(c, e); }
-    trainer_adopt(c, N, L, block, accum);
+    trainer_adopt(c, N, L, 0);
     GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block, 0, c->t_floats * 4 * sizeof(float), c->stream));
     GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_accum, 0, (size_t)N * sizeof(float), c->stream));
     const float* src[6] = {host_xyz, host_f_dc, host_f_rest, host_scales_log, host_rot_raw, host_opacity_logit};
@@ -1417,33 +1432,38 @@ int gsb_trainer_densify(gsb_ctx* ctx, float grad_threshold, float max_scale, flo
         gsb::set_error(c, "gsb_trainer_densify: output count exceeds gsb_config.max_gaussians (use 0 = grow on demand)");
         return GSB_ERR_CAPACITY;
     }
-    int* gather = nullptr; int* mode = nullptr; float* block = nullptr; float* accum = nullptr;
+    // destination slab: the other one; (re)allocated only when it does not exist yet or the capacity has to grow
+    const int dst = c->t_cur ^ 1;
     const TrainerLayout L = trainer_layout(Nout, K);
-    cudaError_t e = gsb::dev_alloc(&gather, (size_t)Nout);
-    if (e == cudaSuccess) e = gsb::dev_alloc(&mode, (size_t)Nout);
-    if (e == cudaSuccess) e = gsb::dev_alloc(&block, L.floats * 4);
-    if (e == cudaSuccess) e = gsb::dev_alloc(&accum, (size_t)Nout);
-    if (e == cudaSuccess) e = cudaMemsetAsync(block, 0, L.floats * 4 * sizeof(float), c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(accum, 0, (size_t)Nout * sizeof(float), c->stream);
-    if (e == cudaSuccess) e = gsb::launch_densify_map(c->stream, N, actions, offsets, (uint32_t)Nout, gather, mode);
-    if (e == cudaSuccess) {
+    bool grew = false;
+    if (Nout > c->t_cap) {
+        c->t_cap = std::max(Nout, c->t_cap + c->t_cap / 2);
+        grew = true;
+    }
+    if (grew || !c->t_slab[dst]) GSB_CUDA_CHECK(c, trainer_alloc_slab(c, dst, c->t_cap));
+    float* block = c->t_slab[dst];
+    float* accum = c->t_accum_slab[dst];
+    // gather map in the destination's (still unused) Adam-state region: 2 * Nout ints << 2 * L.floats floats
+    int* gather = reinterpret_cast<int*>(block + 2 * L.floats);
+    int* mode = gather + Nout;
+    GSB_CUDA_CHECK(c, cudaMemsetAsync(block + L.floats, 0, L.floats * sizeof(float), c->stream));   // grads
+    GSB_CUDA_CHECK(c, cudaMemsetAsync(accum, 0, (size_t)Nout * sizeof(float), c->stream));
+    GSB_CUDA_CHECK(c, gsb::launch_densify_map(c->stream, N, actions, offsets, (uint32_t)Nout, gather, mode));
+    {
         const float* in6[6] = {c->t_p[0], c->t_p[1], c->t_p[2], c->t_p[3], c->t_p[4], c->t_p[5]};
         float* out6[6];
         for (int k = 0; k < 6; ++k) out6[k] = block + L.off[k];
-        e = gsb::launch_densify_apply(c->stream, Nout, K, gather, mode, base_noise, seed, in6, out6);
+        GSB_CUDA_CHECK(c, gsb::launch_densify_apply(c->stream, Nout, K, gather, mode, base_noise, seed, in6, out6));
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (gather) cudaFree(gather);
-    if (mode) cudaFree(mode);
-    if (e != cudaSuccess) {
-        if (block) cudaFree(block);
-        if (accum) cudaFree(accum);
-        GSB_CUDA_CHECK(c, e);
-    }
+    GSB_CUDA_CHECK(c, cudaMemsetAsync(block + 2 * L.floats, 0, 2 * L.floats * sizeof(float), c->stream));   // m, v (after the map is consumed)
     c->stats.kernel_launches += 2;
     // commit (GaussianTrainer.swift:899-907) + fresh optimiser state (:1104-1109)
-    gsb::dev_free(c->t_block); gsb::dev_free(c->t_accum);
-    trainer_adopt(c, Nout, L, block, accum);
+    const int old = c->t_cur;
+    trainer_adopt(c, Nout, L, dst);
+    if (grew) {   // the old slab is too small to ever be a destination again
+        GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        gsb::dev_free(c->t_slab[old]); gsb::dev_free(c->t_accum_slab[old]);
+    }
     c->saved.valid = false;
     c->bin_valid = false;
     return gsb::ensure_gaussians(c, Nout);

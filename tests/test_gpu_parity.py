@@ -444,3 +444,58 @@ def test_full_size_properties(gsb, wl_name, n):
     assert all(bool(torch.isfinite(v).all()) for v in g1.values())
     if wl_name == "C3":
         assert abs(M - 12_031_308) <= 200     # SURVEY.md 8d-workload (reference kernels on CPU), view 0
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs 4 and 5 at full size: size-independent properties
+# ------------------------------------------------------------------------------------------------
+def test_c5_forward_only_render_3m(gsb):
+    """Forward-only render (GaussianRenderer.forward, GaussianRenderer.swift:882-934) of 3 M Gaussians at 1080p."""
+    Context, L = gsb
+    n, W, H = 3_000_000, 1920, 1080
+    params = make_gaussians(n, 5, 3)
+    ctx = Context(W, H, max_gaussians=n)
+    dp = {k: dev(v) for k, v in params.items()}
+    cam = L.make_camera(make_cameras(W, H, 8)[0])
+    render, depth, alpha, vis, radii = ctx.render_forward(dp, cam)
+    M = ctx.stats()["pairs_last_view"]
+    assert M > 10 * n // 4 and bool(torch.isfinite(render).all()) and float(alpha.min()) >= 0.0 and float(alpha.max()) <= 1.0
+    lists = ctx.bin_read()
+    key = (lists["sortedKeysHigh"].to(torch.int64) << 32) | (lists["sortedKeysLow"].to(torch.int64) & 0xffffffff)
+    assert key.numel() == M and bool((key[1:] >= key[:-1]).all())
+    eq = key[1:] == key[:-1]
+    sv = lists["sortedGaussIdx"]
+    assert bool((sv[1:][eq] > sv[:-1][eq]).all())
+    del key, eq, lists
+    render2, *_ = ctx.render_forward(dp, cam)
+    assert torch.equal(render, render2)
+    assert ctx.last_contrib_sum() <= M * 256
+    ctx.close()
+
+
+def test_c4_densification_stress_6m_4k(gsb):
+    """6 M Gaussians at 3840x2160: train, clone/split/prune on the accumulated gradient norms, train on the new count."""
+    Context, L = gsb
+    wl, params, cams, targets = make_workload("C4")
+    n = params["_xyz"].shape[0]
+    ctx = Context(wl.width, wl.height, sh_degree=wl.sh_degree)           # max_gaussians = 0: buffers grow with the model
+    ctx.trainer_init({k: torch.from_numpy(v) for k, v in params.items()})
+    gc = [L.make_camera(c) for c in cams]
+    tg = [torch.from_numpy(t).cuda() for t in targets]
+    losses = [ctx.train_step(gc, tg, it, 30000) for it in range(2)]
+    assert all(np.isfinite(l) for l in losses) and ctx.trainer_count() == (n, 2)
+    acc = ctx.trainer_tensors()["accum"]
+    thr = float(torch.quantile(acc[::8], 0.95)) / 2.0                        # ~5 % of the Gaussians densify
+    op = ctx.trainer_tensors()["params"]["_opacity"]
+    pruned_expected = int((torch.sigmoid(op[:, 0]) < 0.005).sum())
+    info = ctx.trainer_densify(thr, 0.01, 0.005, 8_000_000, seed=7)
+    assert info["prune"] == pruned_expected
+    assert info["keep"] + info["split"] + info["clone"] + info["prune"] == n
+    assert info["n"] == info["keep"] + 2 * (info["split"] + info["clone"]) == info["total"]
+    assert 0.03 * n < info["split"] + info["clone"] < 0.07 * n
+    tt = ctx.trainer_tensors()
+    assert tt["params"]["_xyz"].shape[0] == info["n"] and float(tt["m"]["_xyz"].abs().max()) == 0.0
+    assert bool(torch.isfinite(tt["params"]["_xyz"]).all())
+    l2 = ctx.train_step(gc, tg, 2, 30000)
+    assert np.isfinite(l2) and ctx.trainer_count() == (info["n"], 1)
+    ctx.close()
