@@ -9,9 +9,11 @@ raster backward → projection backward (gradients accumulated), then [DP all-re
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo (libgsb.so)
     python bench.py --impl reference ...                            # the reference's kernels on host cores
 
-N > 1 is launched by torchrun (one rank per GPU); the 8 views are split round-robin over the ranks
-(strong scaling: the batch is fixed) and the per-Gaussian gradient block is all-reduced with NCCL.
-Prints ONE JSON line on rank 0.
+N > 1 is launched by torchrun (one rank per GPU).  Default = WEAK scaling (view-batched training):
+every rank renders its own batch of 8 views of a ring of 8 N cameras (global batch 8 N views, gradient scale
+1/(8 N)), the per-Gaussian gradient block is all-reduced with NCCL over NVLink and every replica runs the same Adam.
+`value` counts 8-view steps: all ranks' views / 8 / time.  `--scaling strong` keeps the batch at 8 views in total
+(split round-robin over the ranks).  Prints ONE JSON line on rank 0 (library chatter on stdout is sent to stderr).
 """
 from __future__ import annotations
 
@@ -162,7 +164,7 @@ def run_reference(args, rank, world):
               f"compiled for the host ({kind}); step time = {views} x mean view time ({t_view:.2f} s) + Adam ({t_adam:.3f} s); "
               f"{len(times)} timed samples (requested {args.steps}, wall budget {budget:.0f} s), OpenMP on {cores} threads")
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-           "warmup": done_warm, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "warmup": done_warm, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": workload_config(wl, params, views, world=1),
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
@@ -171,11 +173,13 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
-def workload_config(wl, params, views, world):
+def workload_config(wl, params, views, world, global_views=None):
     n = params["_xyz"].shape[0]
-    return {"workload": f"{wl.name}: {n} Gaussians, SH deg {wl.sh_degree}, {wl.width}x{wl.height}, batch of {views} views, "
-                        f"L1+SSIM loss, Adam; seed {wl.seed} (SURVEY.md 8d generator)",
-            "gaussians": n, "width": wl.width, "height": wl.height, "views_per_step": views, "tile": wl.tile,
+    global_views = global_views or views
+    return {"workload": f"{wl.name}: {n} Gaussians, SH deg {wl.sh_degree}, {wl.width}x{wl.height}, batch of {views} views per step"
+                        f"{' per GPU' if global_views != views else ''}, L1+SSIM loss, Adam; seed {wl.seed} (SURVEY.md 8d generator)",
+            "gaussians": n, "width": wl.width, "height": wl.height, "views_per_step": views, "global_views_per_step": global_views,
+            "tile": wl.tile,
             "parallelism": f"view-parallel dp{world}" if world > 1 else "single GPU",
             "l2_policy": "inputs larger than L2 (per step: 236 MB params + 236 MB grads + 472 MB Adam state + per-view "
                          "key/record streams > 126 MB L2); no explicit flush"}
@@ -191,18 +195,30 @@ def run_gsb(args, rank, local_rank, world):
     from gaussiansplattingmlx_b200.context import Context
     from gaussiansplattingmlx_b200.scene import make_workload
 
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: NCCL prints its version banner there
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    from gaussiansplattingmlx_b200.scene import make_cameras, make_targets
     wl, params, cams, targets = make_workload(args.workload, n_override=args.n, views_override=args.views)
-    views = len(cams)
+    per_step = len(cams)                                   # views of one "step" of the metric (8)
     n = params["_xyz"].shape[0]
-    my_views = [v for v in range(views) if v % world == rank]
-    log(f"[rank {rank}] workload {wl.name}: N={n}, {wl.width}x{wl.height}, views {my_views} of {views}")
+    weak = args.scaling == "weak" and world > 1
+    if weak:   # ring of 8 N cameras, rank r takes views r, r + N, ...; targets drawn in view order from the same seed
+        views = per_step * world
+        cams = make_cameras(wl.width, wl.height, views)
+        my_views = [v for v in range(views) if v % world == rank]
+        all_targets = make_targets(wl.width, wl.height, views, wl.seed)
+        targets = {v: all_targets[v] for v in my_views}
+        del all_targets
+    else:
+        views = per_step
+        my_views = [v for v in range(views) if v % world == rank]
+    log(f"[rank {rank}] workload {wl.name}: N={n}, {wl.width}x{wl.height}, views {my_views} of {views} ({args.scaling} scaling)")
 
     base_flags = int(os.environ.get("GSB_FLAGS", "0"))   # debugging: 1 = CUB sort baseline, 2 = no view pipeline
     ctx = Context(wl.width, wl.height, tile_w=wl.tile, tile_h=wl.tile, sh_degree=wl.sh_degree, max_gaussians=n, device=local_rank,
@@ -296,8 +312,9 @@ def run_gsb(args, rank, local_rank, world):
         return
 
     K = args.steps
-    value = K / (ms_dev * 1e-3)
-    e2e_value = K / (ms_e2e * 1e-3)
+    unit_steps = views / per_step                        # 8-view steps processed per global step (N for weak scaling, else 1)
+    value = K * unit_steps / (ms_dev * 1e-3)
+    e2e_value = K * unit_steps / (ms_e2e * 1e-3)
     img_bytes = wl.width * wl.height * 3 * 4
     peaks = measured_peaks()
     fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12   # TFLOP/s, non-tensor FP32 pipe at max clock
@@ -353,16 +370,17 @@ def run_gsb(args, rank, local_rank, world):
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-           "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "config": workload_config(wl, params, views, world),
-           "views_per_s": value * views,
+           "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak" if (weak or world == 1 and args.scaling == "weak") else "strong",
+           "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": workload_config(wl, params, per_step, world, views),
+           "views_per_s": value * per_step,
            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
-                   "h2d_bytes_per_step": img_bytes * len(my_views), "d2h_bytes_per_step": 4,
+                   "h2d_bytes_per_step": img_bytes * views, "d2h_bytes_per_step": 4 * world,
                    "api": "Context.trainer_accumulate(pinned host targets, want_loss) [+ NCCL all_reduce] + trainer_apply"},
            "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_kernels": kernels,
            "ms_per_step_serialized": ms_serial / K,
            "cpu_baseline": cpu}
-    print(json.dumps(out), flush=True)
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
@@ -376,6 +394,8 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--n", type=int, default=None, help="override the Gaussian count (debugging only)")
     ap.add_argument("--views", type=int, default=None, help="override the views per step (debugging only)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = 8 views per GPU per step (default); strong = 8 views in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--debug-overlap", action="store_true", help="also print per-stage times measured WITH the view pipeline on")
     args = ap.parse_args()
