@@ -262,8 +262,12 @@ def run_gsb(args, rank, local_rank, world):
             ms = float(t.item())
         return ms
 
-    # ---- warm-up (also sizes the intersection buffers)
+    # ---- set-up steps (size the intersection buffers, fault in every allocation, let clocks settle), then the W warm-up steps
     it = 0
+    for _ in range(8):
+        step(it, False, False); it += 1
+    step(it, True, True); it += 1
+    barrier()
     for _ in range(args.warmup):
         step(it, False, False); it += 1
     barrier()
