@@ -356,8 +356,15 @@ def run_gsb(args, rank, local_rank, world):
     roof = None
     if dominant:
         d = kernels[dominant]
+        # DRAM bytes per launch of that kernel from the committed ncu --set full capture (tools/ncu_summary.py --traffic)
+        traffic, traffic_src = None, None
+        tfile = ROOT / "profiles" / "traffic.json"
+        if tfile.exists():
+            t = json.loads(tfile.read_text()).get("k_" + dominant)
+            if t:
+                traffic, traffic_src = t["dram_bytes_per_launch"], f"profiles/traffic.json ({t['source']})"
         roof = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
-                "frac": d["frac"], "traffic": None,
+                "frac": d["frac"], "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
                 "peak_source": (f"{peaks['source']} MEASURED_PEAKS.json hbm_gbs" if d["bound"] == "hbm" else
                                 f"non-tensor FP32 pipe: 148 SM x 128 lanes x 2 flop x sm_max_mhz ({peaks['source']}); "
                                 "no measured FP32 figure exists in MEASURED_PEAKS.json"),

@@ -29,7 +29,36 @@ WANT = [
     ("smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "stall_membar"),
 ]
 
+def traffic_json(reps, out_path):
+    """--traffic OUT.json rep...: average DRAM bytes (read + write) per launch of every kernel captured."""
+    import json
+    acc = {}
+    for rep in reps:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("gsb::", "").split("<")[0]
+            b = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+            t = float(r[hdr.index("gpu__time_duration.sum")])
+            acc.setdefault(name, []).append((b, t, units[hdr.index("gpu__time_duration.sum")], r[hdr.index("Grid Size")]))
+    res = {}
+    for name, v in acc.items():
+        big = max(x[0] for x in v)
+        sel = [x for x in v if x[0] >= 0.5 * big]          # ignore the tiny launches of a multi-size kernel (sort passes)
+        res[name] = {"dram_bytes_per_launch": sum(x[0] for x in sel) / len(sel), "launches_averaged": len(sel),
+                     "source": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum"}
+    json.dump(res, open(out_path, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--traffic":
+        return traffic_json(sys.argv[3:], sys.argv[2])
     for rep in sys.argv[1:]:
         out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(out)))
