@@ -275,10 +275,12 @@ def run_gsb(args, rank, local_rank, world):
     # blend evaluations per step on this rank (for the raster rooflines), from lastContrib of each view
     evals = 0
     pairs = 0
+    l1_pairs = 0
     for cam in gcams:
         ctx.render_forward(ctx.trainer_tensors()["params"], cam, want_outputs=False)
         evals += ctx.last_contrib_sum()
         pairs += ctx.stats()["pairs_last_view"]
+        l1_pairs += ctx.stats()["sb_pairs_last_view"]
 
     # ---- timed region 1: inputs resident in HBM (the product configuration: view pipeline on)
     ctx.stats_reset()
@@ -326,15 +328,17 @@ def run_gsb(args, rank, local_rank, world):
     # per-stage averages on rank 0 (CUDA-event pairs recorded on the work stream during timed region 1)
     nv = max(len(my_views), 1)
     P = wl.width * wl.height
-    passes = -(-max(1, (ctx.num_tiles - 1).bit_length()) // 8)
+    num_sb = -(-ctx.grid_w // 4) * -(-ctx.grid_h // 2)        # superblocks of 4 x 2 tiles (tilelists.cu)
+    passes = -(-max(1, (num_sb - 1).bit_length()) // 8)
+    L1 = l1_pairs / max(len(my_views), 1)
     M = pairs / nv
     E = evals / nv
     alg = {  # algorithmic bytes / flops per LAUNCH, per view unless noted
         "project_fwd": ("hbm", 284.0 * n), "project_bwd": ("hbm", 516.0 * n), "scan": ("hbm", 8.0 * n),
         "depth_sort": ("hbm", n * (4.0 + 16.0 * 4)),          # 32-bit key + index, 4 onesweep passes (r+w) + histogram read
-        "keygen": ("hbm", 16.0 * n + 8.0 * M),              # perm, offset, rect in; (tile id, index) out
-        "sort": ("hbm", M * (4.0 + 16.0 * passes)),          # 8-byte pairs, `passes` onesweep passes on the tile id
-        "ranges_gather": ("hbm", M * 4.0 + 16.0 * ctx.num_tiles),   # sorted tile ids in, ranges + launch order out
+        "keygen": ("hbm", 16.0 * n + 8.0 * L1),             # perm, offset, rect in; (superblock id, index) out
+        "sort": ("hbm", L1 * (4.0 + 16.0 * passes)),         # 8-byte pairs, `passes` onesweep passes on the superblock id
+        "tile_lists": ("hbm", 2 * 12.0 * L1 + 4.0 * L1 + 4.0 * M + 16.0 * ctx.num_tiles),   # 2 walks (index + rect), ranges, M list entries out
         "raster_fwd": ("fp32", 27.0 * E), "raster_bwd": ("fp32", 80.0 * E),
         "loss": ("fp32", (225.0 + 170.0) * P * 3), "adam": ("hbm", 28.0 * 59 * n + 12.0 * n),
     }
@@ -368,7 +372,7 @@ def run_gsb(args, rank, local_rank, world):
                 "peak_source": (f"{peaks['source']} MEASURED_PEAKS.json hbm_gbs" if d["bound"] == "hbm" else
                                 f"non-tensor FP32 pipe: 148 SM x 128 lanes x 2 flop x sm_max_mhz ({peaks['source']}); "
                                 "no measured FP32 figure exists in MEASURED_PEAKS.json"),
-                "units_per_launch": {"pairs_M": M, "blend_evals_E": E, "gaussians": n, "pixels": P},
+                "units_per_launch": {"pairs_M": M, "superblock_pairs_L1": L1, "blend_evals_E": E, "gaussians": n, "pixels": P},
                 "timing": "CUDA-event pairs around every launch on the library's work stream, averaged over a second pass of "
                           "the same steps with the view pipeline disabled (kernels back to back); share_of_step is relative to "
                           "that pass (ms_per_step_serialized)"}

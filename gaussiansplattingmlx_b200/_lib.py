@@ -36,7 +36,7 @@ class GsbCamera(C.Structure):
 class GsbStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pairs_last_view", C.c_uint64), ("pairs_total", C.c_uint64),
                 ("views", C.c_uint64), ("pair_capacity", C.c_uint64), ("stage_ms", C.c_double * 16),
-                ("stage_calls", C.c_uint64 * 16)]
+                ("stage_calls", C.c_uint64 * 16), ("sb_pairs_last_view", C.c_uint64)]
 
 
 class GsbError(RuntimeError):

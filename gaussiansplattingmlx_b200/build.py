@@ -29,6 +29,7 @@ SOURCES = {
     "adam.cu": ["--fmad=false"],
     "densify.cu": ["--fmad=false"],
     "binning.cu": [],
+    "tilelists.cu": [],
     "raster.cu": [],
     "loss.cu": [],
     "api.cu": [],

@@ -378,6 +378,7 @@ class Context:
         names = [self.lib.gsb_stage_name(i).decode() for i in range(_lib.STAGE_COUNT)]
         return {"kernel_launches": int(st.kernel_launches), "pairs_last_view": int(st.pairs_last_view),
                 "pairs_total": int(st.pairs_total), "views": int(st.views), "pair_capacity": int(st.pair_capacity),
+                "sb_pairs_last_view": int(st.sb_pairs_last_view),
                 "stage_ms": {n: float(st.stage_ms[i]) for i, n in enumerate(names)},
                 "stage_calls": {n: int(st.stage_calls[i]) for i, n in enumerate(names)}}
 

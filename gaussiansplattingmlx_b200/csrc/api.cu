@@ -32,6 +32,7 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;  // H2D of targets
     std::string err;
     int gridW = 0, gridH = 0, numTiles = 0, tileBits = 1, P = 0;
+    int sbGridW = 0, sbGridH = 0, numSB = 0, sbBits = 1;   // superblocks of SBW x SBH tiles (tilelists.cu)
 
     // Per-view working set.  There are two: while the rasteriser / loss / backward kernels of view v run on the
     // work stream, the projection + binning of view v+1 run on the (higher-priority) front stream into the
@@ -50,21 +51,29 @@ struct Ctx {
         void* scan_ws = nullptr;
         const float* depth_src = nullptr;          // depth of Gaussian g at depth_src[g * depth_src_stride]
         int depth_src_stride = 1;
-        // per pair (capacity capM)
-        uint32_t* keys[2] = {nullptr, nullptr};   // tile ids
-        uint32_t* vals[2] = {nullptr, nullptr};   // Gaussian indices
+        uint32_t* sbcnt = nullptr;     // [N] superblocks touched, in DEPTH order (input of the level-1 scan)
+        // level 1: (superblock id, Gaussian) pairs (capacity capL1), ping-pong for the sort
+        uint32_t* keys[2] = {nullptr, nullptr};
+        uint32_t* vals[2] = {nullptr, nullptr};
         void* sort_ws = nullptr;
-        const uint32_t* d_result_buf = nullptr;  // device flag: which ping-pong buffer holds the sorted list
-        // per tile
-        uint32_t* tile_ranges = nullptr;  // [numTiles,2]
+        const uint32_t* d_result_buf = nullptr;  // device flag: which ping-pong buffer holds the sorted level-1 list
+        // level 2 / per tile
+        uint32_t* list = nullptr;         // [capM] Gaussian indices in (tile, depth, index) order = the tile lists
+        uint32_t* sb_ranges = nullptr;    // [numSB,2] slice of every superblock in the sorted level-1 list
+        uint32_t* slice_counts = nullptr; // [numSB,8 warps,8 tiles]
+        uint32_t* slice_base = nullptr;   // [numSB,8 warps,8 tiles]
+        uint32_t* tile_starts = nullptr;  // [numTiles+1] monotone CSR offsets
+        uint32_t* tile_ranges = nullptr;  // [numTiles,2] (reference convention: (0,0) for an empty tile)
         uint32_t* tile_order = nullptr;   // [numTiles] tile ids, longest list first
-        // control words: [0] = M of the current view, [1] = overflow flag, [2] scratch
+        // control words: [0] = M of the current view, [1] = overflow flag, [2] scratch, [3] raster work counter,
+        //                [4] = level-1 pair count, [5] = list total after the tile scan
         uint32_t* d_ctl = nullptr;
         uint32_t* h_ctl = nullptr;        // pinned mirror
         cudaEvent_t ev_ctl = nullptr;     // fires when h_ctl[0] holds M
         cudaEvent_t ev_front = nullptr;   // projection + binning of this set finished (front stream)
         cudaEvent_t ev_back = nullptr;    // the work stream no longer reads this set
         uint32_t last_M = 0;
+        uint32_t last_L1 = 0;
     } vb[GSB_VIEW_SETS];
     int cur = 0;                       // set used by the single-view API / holding the saved forward
     cudaStream_t front_stream = nullptr;
@@ -80,7 +89,8 @@ struct Ctx {
     uint32_t* offsets_ref = nullptr;   // [N] scan in index order (parity API: reference emission order)
     float* act_tmp = nullptr;          // scratch for the reference-layout parity API ([N,12] floats)
 
-    uint32_t capM = 0;
+    uint32_t capM = 0;                 // capacity of the tile lists (pairs)
+    uint32_t capL1 = 0;                // capacity of the level-1 (superblock) pair buffers
     SortPlan plan;
     void* cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
@@ -161,7 +171,7 @@ void set_error(Ctx* ctx, const std::string& msg)
     if (ctx) ctx->err = msg; else g_create_error = msg;
 }
 
-static const char* kStageNames[GSB_STAGE_COUNT] = {"project_fwd", "scan", "keygen", "sort", "ranges_gather", "raster_fwd",
+static const char* kStageNames[GSB_STAGE_COUNT] = {"project_fwd", "scan", "keygen", "sort", "tile_lists", "raster_fwd",
                                                    "loss", "raster_bwd", "project_bwd", "adam", "h2d", "depth_sort"};
 
 struct StageTimer {
@@ -263,7 +273,7 @@ static int ensure_gaussians(Ctx* c, int N)
     GSB_CUDA_CHECK(c, dev_alloc(&c->offsets_ref, (size_t)cap));
     c->dplan = sort_plan((uint32_t)cap, 32u);
     for (Ctx::ViewBufs& v : c->vb) {
-        dev_free(v.rec); dev_free(v.tile_rects); dev_free(v.touched); dev_free(v.offsets);
+        dev_free(v.rec); dev_free(v.tile_rects); dev_free(v.touched); dev_free(v.offsets); dev_free(v.sbcnt);
         for (int i = 0; i < 2; ++i) { dev_free(v.dkeys[i]); dev_free(v.dvals[i]); }
         if (v.dsort_ws) { cudaFree(v.dsort_ws); v.dsort_ws = nullptr; }
         if (v.scan_ws) { cudaFree(v.scan_ws); v.scan_ws = nullptr; }
@@ -271,6 +281,7 @@ static int ensure_gaussians(Ctx* c, int N)
         GSB_CUDA_CHECK(c, dev_alloc(&v.tile_rects, (size_t)cap));
         GSB_CUDA_CHECK(c, dev_alloc(&v.touched, (size_t)cap));
         GSB_CUDA_CHECK(c, dev_alloc(&v.offsets, (size_t)cap));
+        GSB_CUDA_CHECK(c, dev_alloc(&v.sbcnt, (size_t)cap));
         GSB_CUDA_CHECK(c, cudaMalloc(&v.scan_ws, scan_ws_bytes(cap)));
         for (int i = 0; i < 2; ++i) {
             GSB_CUDA_CHECK(c, dev_alloc(&v.dkeys[i], (size_t)cap));
@@ -282,29 +293,39 @@ static int ensure_gaussians(Ctx* c, int N)
     return GSB_OK;
 }
 
-static int ensure_pairs(Ctx* c, uint64_t M)
+static int ensure_pairs(Ctx* c, uint64_t M, uint64_t L1)
 {
-    if (M <= c->capM) return GSB_OK;
+    if (M <= c->capM && L1 <= c->capL1) return GSB_OK;
     if (M > 0xfffffff0ull / 3ull) {  // u32 offsets (the reference's cumsum is u32 too)
         set_error(c, "intersection list exceeds the 32-bit index range");
         return GSB_ERR_CAPACITY;
     }
     sync_all_streams(c);
     if (c->cub_tmp) { cudaFree(c->cub_tmp); c->cub_tmp = nullptr; c->cub_tmp_bytes = 0; }
-    uint64_t cap = std::max<uint64_t>(M + M / 4, 1u << 16);
-    cap = (cap + 4095) & ~4095ull;
-    c->plan = sort_plan((uint32_t)cap, (uint32_t)c->tileBits);
-    for (Ctx::ViewBufs& v : c->vb) {
-        for (int i = 0; i < 2; ++i) { dev_free(v.keys[i]); dev_free(v.vals[i]); }
-        if (v.sort_ws) { cudaFree(v.sort_ws); v.sort_ws = nullptr; }
-        for (int i = 0; i < 2; ++i) {
-            GSB_CUDA_CHECK(c, dev_alloc(&v.keys[i], (size_t)cap));
-            GSB_CUDA_CHECK(c, dev_alloc(&v.vals[i], (size_t)cap));
+    auto grow = [](uint64_t need) { uint64_t cap = std::max<uint64_t>(need + need / 4, 1u << 16); return (cap + 4095) & ~4095ull; };
+    if (M > c->capM) {
+        const uint64_t cap = grow(M);
+        for (Ctx::ViewBufs& v : c->vb) {
+            dev_free(v.list);
+            GSB_CUDA_CHECK(c, dev_alloc(&v.list, (size_t)cap));
         }
-        GSB_CUDA_CHECK(c, cudaMalloc(&v.sort_ws, c->plan.ws_bytes));
+        c->capM = (uint32_t)cap;
+        c->stats.pair_capacity = cap;
     }
-    c->capM = (uint32_t)cap;
-    c->stats.pair_capacity = cap;
+    if (L1 > c->capL1) {
+        const uint64_t cap = grow(L1);
+        c->plan = sort_plan((uint32_t)cap, (uint32_t)c->sbBits);
+        for (Ctx::ViewBufs& v : c->vb) {
+            for (int i = 0; i < 2; ++i) { dev_free(v.keys[i]); dev_free(v.vals[i]); }
+            if (v.sort_ws) { cudaFree(v.sort_ws); v.sort_ws = nullptr; }
+            for (int i = 0; i < 2; ++i) {
+                GSB_CUDA_CHECK(c, dev_alloc(&v.keys[i], (size_t)cap));
+                GSB_CUDA_CHECK(c, dev_alloc(&v.vals[i], (size_t)cap));
+            }
+            GSB_CUDA_CHECK(c, cudaMalloc(&v.sort_ws, c->plan.ws_bytes));
+        }
+        c->capL1 = (uint32_t)cap;
+    }
     return GSB_OK;
 }
 
@@ -357,45 +378,52 @@ static int enqueue_binning(Ctx* c, Ctx::ViewBufs& v, cudaStream_t st, int N, con
     }
     {
         StageTimer t(c, GSB_STAGE_SCAN, st);
-        // 2. offsets in depth order, M
-        GSB_CUDA_CHECK(c, launch_exclusive_scan(st, N, v.touched, v.dvals[0], v.dvals[1], v.d_dresult_buf, v.offsets, &v.d_ctl[0],
-                                                v.scan_ws));
-        ++launches;
+        // 2. superblocks touched per Gaussian in depth order (+ M = sum of tiles touched), offsets of the level-1 pairs
+        GSB_CUDA_CHECK(c, launch_sb_counts(st, N, v.tile_rects, v.touched, v.dvals[0], v.dvals[1], v.d_dresult_buf, v.sbcnt, &v.d_ctl[0]));
+        GSB_CUDA_CHECK(c, launch_exclusive_scan(st, N, v.sbcnt, nullptr, nullptr, nullptr, v.offsets, &v.d_ctl[4], v.scan_ws));
+        launches += 2;
     }
-    GSB_CUDA_CHECK(c, cudaMemcpyAsync(v.h_ctl, v.d_ctl, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA_CHECK(c, cudaMemcpyAsync(v.h_ctl, v.d_ctl, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     GSB_CUDA_CHECK(c, cudaEventRecord(v.ev_ctl, st));
-    if (c->capM == 0) {  // first use: size the pair buffers from the actual count
+    if (c->capM == 0 || c->capL1 == 0) {  // first use: size the pair buffers from the actual counts
         GSB_CUDA_CHECK(c, cudaEventSynchronize(v.ev_ctl));
-        int rc = ensure_pairs(c, std::max<uint64_t>(v.h_ctl[0], 1));
+        int rc = ensure_pairs(c, std::max<uint64_t>(v.h_ctl[0], 1), std::max<uint64_t>(v.h_ctl[4], 1));
         if (rc != GSB_OK) return rc;
     }
     {
         StageTimer t(c, GSB_STAGE_KEYGEN, st);
-        GSB_CUDA_CHECK(c, launch_generate_keys(st, N, vp, v.tile_rects, v.offsets, v.dvals[0], v.dvals[1], v.d_dresult_buf, v.keys[0],
-                                               v.vals[0], c->capM, &v.d_ctl[0], &v.d_ctl[1]));
+        // 3. level-1 pairs (superblock id, Gaussian) in depth order
+        GSB_CUDA_CHECK(c, launch_generate_keys(st, N, c->sbGridW, SBW, SBH, v.tile_rects, v.offsets, v.dvals[0], v.dvals[1],
+                                               v.d_dresult_buf, v.keys[0], v.vals[0], c->capL1, &v.d_ctl[4], &v.d_ctl[1]));
         ++launches;
     }
     if (use_cub) GSB_CUDA_CHECK(c, cudaStreamSynchronize(st));   // checked baseline: needs the host-known count
     {
         StageTimer t(c, GSB_STAGE_SORT, st);
-        // 3. stable sort on the tile id alone (the list is already in (depth, index) order)
+        // 4. stable sort on the superblock id alone (the pairs are already in (depth, index) order)
         if (use_cub) {
-            const uint32_t M = std::min(v.h_ctl[0], c->capM);
-            int rc = cub_sort32(c, st, v.keys[0], v.keys[1], v.vals[0], v.vals[1], M, (uint32_t)c->tileBits);
+            const uint32_t L1 = std::min(v.h_ctl[4], c->capL1);
+            int rc = cub_sort32(c, st, v.keys[0], v.keys[1], v.vals[0], v.vals[1], L1, (uint32_t)c->sbBits);
             if (rc != GSB_OK) return rc;
-            v.d_result_buf = M > 0 ? c->d_one : c->d_zero;
+            v.d_result_buf = L1 > 0 ? c->d_one : c->d_zero;
             launches += 1;
         } else {
-            GSB_CUDA_CHECK(c, launch_onesweep_sort32(st, c->plan, v.keys[0], v.keys[1], v.vals[0], v.vals[1], 0, &v.d_ctl[0],
+            GSB_CUDA_CHECK(c, launch_onesweep_sort32(st, c->plan, v.keys[0], v.keys[1], v.vals[0], v.vals[1], 0, &v.d_ctl[4],
                                                      v.sort_ws, &v.d_result_buf, &launches));
         }
     }
     {
-        StageTimer t(c, GSB_STAGE_RANGES_GATHER, st);
-        GSB_CUDA_CHECK(c, launch_ranges_gather(st, vp, v.keys[0], v.keys[1], v.vals[0], v.vals[1], v.d_result_buf, &v.d_ctl[0],
-                                               c->capM, nullptr, v.tile_ranges, nullptr, c->numTiles));
-        GSB_CUDA_CHECK(c, launch_tile_order(st, c->numTiles, v.tile_ranges, v.tile_order));
-        launches += 2;
+        StageTimer t(c, GSB_STAGE_TILE_LISTS, st);
+        // 5. superblock slices -> per-tile counts -> CSR ranges + heavy-first order -> the tile lists (tilelists.cu)
+        GSB_CUDA_CHECK(c, launch_ranges_gather(st, vp, v.keys[0], v.keys[1], v.vals[0], v.vals[1], v.d_result_buf, &v.d_ctl[4],
+                                               c->capL1, nullptr, v.sb_ranges, nullptr, c->numSB));
+        GSB_CUDA_CHECK(c, launch_l2_count(st, c->numSB, c->sbGridW, v.sb_ranges, v.vals[0], v.vals[1], v.d_result_buf, v.tile_rects,
+                                          v.slice_counts));
+        GSB_CUDA_CHECK(c, launch_tile_scan_order(st, c->gridW, c->gridH, c->sbGridW, v.slice_counts, v.slice_base, v.tile_ranges,
+                                                 v.tile_starts, v.tile_order, &v.d_ctl[5]));
+        GSB_CUDA_CHECK(c, launch_l2_fill(st, c->numSB, c->sbGridW, v.sb_ranges, v.vals[0], v.vals[1], v.d_result_buf, v.tile_rects,
+                                         v.slice_base, v.list, c->capM));
+        launches += 4;
     }
     c->stats.kernel_launches += launches;
     return GSB_OK;
@@ -407,12 +435,13 @@ static int enqueue_binning(Ctx* c, Ctx::ViewBufs& v, cudaStream_t st, int N, con
 static int finish_binning(Ctx* c, Ctx::ViewBufs& v)
 {
     GSB_CUDA_CHECK(c, cudaEventSynchronize(v.ev_ctl));
-    const uint32_t M = v.h_ctl[0];
-    if (M <= c->capM) {
+    const uint32_t M = v.h_ctl[0], L1 = v.h_ctl[4];
+    if (M <= c->capM && L1 <= c->capL1) {
         v.last_M = M;
+        v.last_L1 = L1;
         return GSB_OK;
     }
-    int rc = ensure_pairs(c, M);
+    int rc = ensure_pairs(c, M, L1);
     if (rc != GSB_OK) return rc;
     set_error(c, "intersection buffers regrown");
     return GSB_ERR_CAPACITY;
@@ -475,7 +504,8 @@ static void destroy_ctx(Ctx* c)
         if (v.dsort_ws) cudaFree(v.dsort_ws);
         if (v.scan_ws) cudaFree(v.scan_ws);
         if (v.sort_ws) cudaFree(v.sort_ws);
-        dev_free(v.tile_ranges); dev_free(v.tile_order); dev_free(v.d_ctl);
+        dev_free(v.tile_ranges); dev_free(v.tile_order); dev_free(v.d_ctl); dev_free(v.sbcnt); dev_free(v.list);
+        dev_free(v.sb_ranges); dev_free(v.slice_counts); dev_free(v.slice_base); dev_free(v.tile_starts);
         if (v.h_ctl) cudaFreeHost(v.h_ctl);
         cudaEvent_t* evs[] = {&v.ev_ctl, &v.ev_front, &v.ev_back};
         for (cudaEvent_t* e : evs) if (*e) cudaEventDestroy(*e);
@@ -572,6 +602,10 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
     if (c->gridW > 65535 || c->gridH > 65535) { delete h; set_error(nullptr, "tile grid too large"); return GSB_ERR_UNSUPPORTED; }
     c->numTiles = c->gridW * c->gridH;
     c->tileBits = tile_bit_count(c->numTiles);
+    c->sbGridW = (c->gridW + gsb::SBW - 1) / gsb::SBW;
+    c->sbGridH = (c->gridH + gsb::SBH - 1) / gsb::SBH;
+    c->numSB = c->sbGridW * c->sbGridH;
+    c->sbBits = tile_bit_count(c->numSB);
     c->P = cfg->width * cfg->height;
 #define CREATE_CHECK(expr)                                                                  \
     do {                                                                                    \
@@ -605,9 +639,13 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
         CREATE_CHECK(cudaEventCreateWithFlags(&v.ev_back, cudaEventDisableTiming));
         CREATE_CHECK(dev_alloc(&v.tile_ranges, (size_t)c->numTiles * 2));
         CREATE_CHECK(dev_alloc(&v.tile_order, (size_t)c->numTiles));
-        CREATE_CHECK(dev_alloc(&v.d_ctl, 4));
+        CREATE_CHECK(dev_alloc(&v.tile_starts, (size_t)c->numTiles + 1));
+        CREATE_CHECK(dev_alloc(&v.sb_ranges, (size_t)c->numSB * 2));
+        CREATE_CHECK(dev_alloc(&v.slice_counts, (size_t)c->numSB * 64));
+        CREATE_CHECK(dev_alloc(&v.slice_base, (size_t)c->numSB * 64));
+        CREATE_CHECK(dev_alloc(&v.d_ctl, 8));
         CREATE_CHECK(dev_alloc(&v.d_nvalue, 4));
-        CREATE_CHECK(cudaMallocHost(reinterpret_cast<void**>(&v.h_ctl), 4 * sizeof(uint32_t)));
+        CREATE_CHECK(cudaMallocHost(reinterpret_cast<void**>(&v.h_ctl), 8 * sizeof(uint32_t)));
     }
     CREATE_CHECK(dev_alloc(&c->out_color, P * 3));
     CREATE_CHECK(dev_alloc(&c->out_depth, P));
@@ -772,14 +810,11 @@ int gsb_bin_read(gsb_ctx* ctx, uint32_t* keys_high, uint32_t* keys_low, uint32_t
         if (gauss_idx) GSB_CUDA_CHECK(c, cudaMemcpyAsync(gauss_idx, c->dbg_vals, (size_t)M * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
     if (sorted_keys_high || sorted_keys_low || sorted_gauss_idx) {
-        uint32_t buf = 0;
-        GSB_CUDA_CHECK(c, cudaMemcpyAsync(&v.h_ctl[2], v.d_result_buf, 4, cudaMemcpyDeviceToHost, c->stream));
-        GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-        buf = v.h_ctl[2];
-        GSB_CUDA_CHECK(c, gsb::launch_sorted_keys_out(c->stream, M, v.keys[buf], v.vals[buf], v.depth_src, v.depth_src_stride,
-                                                      sorted_keys_high, sorted_keys_low));
+        // the lists are stored without keys: tile id = position in the CSR offsets, depth bits = the listed Gaussian's depth
+        GSB_CUDA_CHECK(c, gsb::launch_expand_sorted_keys(c->stream, M, c->numTiles, v.tile_starts, v.list, v.depth_src, v.depth_src_stride,
+                                                         sorted_keys_high, sorted_keys_low));
         if (sorted_gauss_idx)
-            GSB_CUDA_CHECK(c, cudaMemcpyAsync(sorted_gauss_idx, v.vals[buf], (size_t)M * 4, cudaMemcpyDeviceToDevice, c->stream));
+            GSB_CUDA_CHECK(c, cudaMemcpyAsync(sorted_gauss_idx, v.list, (size_t)M * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
     return GSB_OK;
 }
@@ -869,7 +904,7 @@ int gsb_raster_fwd(gsb_ctx* ctx, int32_t N, const float* packed, float* out_colo
     if (rc != GSB_OK) return rc;
     Ctx::ViewBufs& v = c->vb[c->cur];
     gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
-    GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, c->bin_vp, v.tile_ranges, v.tile_order, v.rec, v.vals[0], v.vals[1], v.d_result_buf, out_color, out_depth, out_alpha,
+    GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, c->bin_vp, v.tile_ranges, v.tile_order, v.rec, v.list, v.list, c->d_zero, out_color, out_depth, out_alpha,
                                              out_last_contrib, &v.d_ctl[3]));
     c->stats.kernel_launches += 1;
     return GSB_OK;
@@ -889,7 +924,7 @@ int gsb_raster_bwd(gsb_ctx* ctx, int32_t N, const float* packed, const float* co
     GSB_CUDA_CHECK(c, cudaMemsetAsync(c->grad_rec, 0, (size_t)N * gsb::REC_FLOATS * 4, c->stream));
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, c->bin_vp, v.tile_ranges, v.tile_order, v.rec, v.vals[0], v.vals[1], v.d_result_buf, cot_color, cot_depth, cot_alpha,
+        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, c->bin_vp, v.tile_ranges, v.tile_order, v.rec, v.list, v.list, c->d_zero, cot_color, cot_depth, cot_alpha,
                                                  out_color, out_depth, out_alpha, last_contrib, c->grad_rec, &v.d_ctl[3]));
     }
     GSB_CUDA_CHECK(c, gsb::launch_rec_to_packed(c->stream, N, c->grad_rec, grad_packed));
@@ -950,7 +985,7 @@ static int enqueue_raster_fwd(Ctx* c, Ctx::ViewBufs& v, int32_t N, const RawPara
 {
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, vp, v.tile_ranges, v.tile_order, v.rec, v.vals[0], v.vals[1], v.d_result_buf,
+        GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, vp, v.tile_ranges, v.tile_order, v.rec, v.list, v.list, c->d_zero,
                                                  c->out_color, want_depth ? c->out_depth : nullptr, c->out_alpha, c->out_last, &v.d_ctl[3]));
         c->stats.kernel_launches += 1;
     }
@@ -962,6 +997,7 @@ static int enqueue_raster_fwd(Ctx* c, Ctx::ViewBufs& v, int32_t N, const RawPara
     c->saved.vp = vp;
     c->bin_vp = vp;
     c->stats.pairs_last_view = v.last_M;
+    c->stats.sb_pairs_last_view = v.last_L1;
     c->stats.pairs_total += v.last_M;
     c->stats.views += 1;
     return GSB_OK;
@@ -1001,7 +1037,7 @@ static int render_backward_impl(Ctx* c, const float* cot_render, const float* co
     GSB_CUDA_CHECK(c, cudaMemsetAsync(grec, 0, (size_t)N * gsb::REC_FLOATS * 4, c->stream));
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
-        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, vp, v.tile_ranges, v.tile_order, v.rec, v.vals[0], v.vals[1], v.d_result_buf, cot_render, cot_depth, cot_alpha,
+        GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, vp, v.tile_ranges, v.tile_order, v.rec, v.list, v.list, c->d_zero, cot_render, cot_depth, cot_alpha,
                                                  c->out_color, c->out_depth, c->out_alpha, c->out_last, grec, &v.d_ctl[3]));
     }
     cudaStream_t pst = c->stream;

@@ -213,7 +213,7 @@ cudaError_t launch_generate_keys_ref(cudaStream_t st, int N, const ViewParams& v
 
 constexpr int KG_THREADS = 256;
 
-__global__ void __launch_bounds__(KG_THREADS) k_generate_keys(int N, int gridW, const uint2* __restrict__ tile_rects,
+__global__ void __launch_bounds__(KG_THREADS) k_generate_keys(int N, int gridW, int cw, int ch, const uint2* __restrict__ tile_rects,
                                                               const uint32_t* __restrict__ offsets,
                                                               const uint32_t* __restrict__ perm0,
                                                               const uint32_t* __restrict__ perm1,
@@ -233,7 +233,13 @@ __global__ void __launch_bounds__(KG_THREADS) k_generate_keys(int N, int gridW, 
     if (i < N) {
         const uint32_t g = perm[i];
         s_g[threadIdx.x] = g;
-        s_rect[threadIdx.x] = tile_rects[g];
+        uint2 r = tile_rects[g];
+        if (cw != 1 || ch != 1) {   // tile rect -> rect of cw x ch cells
+            const uint32_t x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
+            if (x1 > x0 && y1 > y0)
+                r = make_uint2((x0 / cw) | ((y0 / ch) << 16), ((x1 - 1) / cw + 1) | (((y1 - 1) / ch + 1) << 16));
+        }
+        s_rect[threadIdx.x] = r;
         s_off[threadIdx.x] = offsets[i];
     } else {
         s_off[threadIdx.x] = M;
@@ -263,14 +269,14 @@ __global__ void __launch_bounds__(KG_THREADS) k_generate_keys(int N, int gridW, 
     }
 }
 
-cudaError_t launch_generate_keys(cudaStream_t st, int N, const ViewParams& vp, const uint2* tile_rects,
+cudaError_t launch_generate_keys(cudaStream_t st, int N, int cellGridW, int cw, int ch, const uint2* tile_rects,
                                  const uint32_t* offsets, const uint32_t* perm0, const uint32_t* perm1,
                                  const uint32_t* perm_sel, uint32_t* keys, uint32_t* vals, uint32_t capacity,
                                  const uint32_t* total, uint32_t* overflow_flag)
 {
     if (N > 0)
-        k_generate_keys<<<cdiv(N, KG_THREADS), KG_THREADS, 0, st>>>(N, vp.gridW, tile_rects, offsets, perm0, perm1, perm_sel, keys,
-                                                                    vals, capacity, total, overflow_flag);
+        k_generate_keys<<<cdiv(N, KG_THREADS), KG_THREADS, 0, st>>>(N, cellGridW, cw, ch, tile_rects, offsets, perm0, perm1, perm_sel,
+                                                                    keys, vals, capacity, total, overflow_flag);
     return cudaGetLastError();
 }
 

@@ -4,6 +4,8 @@
 
 namespace gsb {
 
+constexpr int SBW = 4, SBH = 2;   // superblock = SBW x SBH tiles (tilelists.cu)
+
 // ---- project.cu --------------------------------------------------------------------------------
 cudaError_t launch_activate_fwd(cudaStream_t st, int N, int K, const float* f_dc, const float* f_rest,
                                 const float* scales_log, const float* rot_raw, const float* op_logit, float* shs,
@@ -41,8 +43,9 @@ cudaError_t launch_count_tiles(cudaStream_t st, int N, const ViewParams& vp, con
 size_t scan_ws_bytes(int N);
 cudaError_t launch_exclusive_scan(cudaStream_t st, int N, const uint32_t* in, const uint32_t* perm0, const uint32_t* perm1,
                                   const uint32_t* perm_sel, uint32_t* offsets, uint32_t* total, void* scan_ws);
-// K4 in depth order: tile-id keys + Gaussian indices, one thread per output pair (coalesced).
-cudaError_t launch_generate_keys(cudaStream_t st, int N, const ViewParams& vp, const uint2* tile_rects,
+// K4 in depth order: cell-id keys + Gaussian indices, one thread per output pair (coalesced).  A cell is cw x ch
+// tiles (1 x 1 = the reference's tiles, SBW x SBH = the superblocks of tilelists.cu); cellGridW = cells per row.
+cudaError_t launch_generate_keys(cudaStream_t st, int N, int cellGridW, int cw, int ch, const uint2* tile_rects,
                                  const uint32_t* offsets, const uint32_t* perm0, const uint32_t* perm1,
                                  const uint32_t* perm_sel, uint32_t* keys, uint32_t* vals, uint32_t capacity,
                                  const uint32_t* total, uint32_t* overflow_flag);
@@ -95,6 +98,19 @@ cudaError_t launch_merge_keys(cudaStream_t st, uint32_t M, const uint32_t* hi, c
                               uint64_t* keys);
 cudaError_t launch_sorted_keys_out(cudaStream_t st, uint32_t M, const uint32_t* tile_keys, const uint32_t* vals,
                                    const float* depth_ptr, int depth_stride, uint32_t* hi, uint32_t* lo);
+
+// ---- tilelists.cu ------------------------------------------------------------------------------
+cudaError_t launch_sb_counts(cudaStream_t st, int N, const uint2* tile_rects, const uint32_t* touched, const uint32_t* perm0,
+                             const uint32_t* perm1, const uint32_t* perm_sel, uint32_t* sb_counts, uint32_t* total_pairs);
+cudaError_t launch_l2_count(cudaStream_t st, int numSB, int sbGridW, const uint32_t* sb_ranges, const uint32_t* vals0,
+                            const uint32_t* vals1, const uint32_t* d_result_buf, const uint2* tile_rects, uint32_t* slice_counts);
+cudaError_t launch_l2_fill(cudaStream_t st, int numSB, int sbGridW, const uint32_t* sb_ranges, const uint32_t* vals0,
+                           const uint32_t* vals1, const uint32_t* d_result_buf, const uint2* tile_rects, const uint32_t* slice_base,
+                           uint32_t* list, uint32_t capacity);
+cudaError_t launch_tile_scan_order(cudaStream_t st, int gridW, int gridH, int sbGridW, const uint32_t* slice_counts, uint32_t* slice_base,
+                                   uint32_t* tile_ranges, uint32_t* tile_starts, uint32_t* order, uint32_t* total_out);
+cudaError_t launch_expand_sorted_keys(cudaStream_t st, uint32_t M, int numTiles, const uint32_t* tile_starts, const uint32_t* list,
+                                      const float* depth_ptr, int depth_stride, uint32_t* hi, uint32_t* lo);
 
 // ---- raster.cu ---------------------------------------------------------------------------------
 // rec = record table [N,12]; (vals0|vals1 selected by *d_result_buf) = Gaussian indices in (tile, depth) order

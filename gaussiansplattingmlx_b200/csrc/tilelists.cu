@@ -1,0 +1,300 @@
+// tilelists.cu — per-tile Gaussian lists by a two-level stable partition (sm_100a).
+//
+// Reference semantics (slang/gaussian_tile_global_kernels.slang:73-404, Trainer/GaussianRenderer.swift:333-490):
+// tile t's list = the Gaussians whose clamped rect covers t, ascending asuint(depth), ties by Gaussian index.
+// The Gaussians arrive already in that order (depth pre-sort, binning.cu), so a tile's list is a FILTER of the
+// depth-ordered sequence.  Sorting M = 12 M (Gaussian, tile) pairs by tile id moves 36 B/pair through HBM; this
+// file builds the same lists while only ever sorting the ~3.5x fewer (Gaussian, superblock) pairs:
+//
+//   level 1   superblock = SBW x SBH = 4 x 2 tiles.  Emit one (superblock id, Gaussian) pair per superblock a rect
+//             touches, in depth order (k_generate_keys of binning.cu with a superblock grid), stable radix sort on
+//             the superblock id (the onesweep of binning.cu): every superblock now owns a depth-ordered slice.
+//   level 2   a CTA per superblock, its slice cut into 8 contiguous warp slices.  COUNT: each warp walks its slice
+//             32 entries at a time, rebuilds the 8-bit "which of my 8 tiles does this rect cover" mask from the
+//             packed tile rect and counts per tile with ballots.  One small single-CTA kernel turns the
+//             (superblock, warp slice, tile) counts into tile ranges (CSR), slice bases and the heavy-first tile
+//             order.  FILL: the same walk again; lane ranks from the ballots give every (Gaussian, tile) pair its
+//             final slot — stable by construction, no atomics, writes coalesced per tile.
+//
+// HBM traffic per view at C3: ~3.4 M pairs x (8 B keygen + 36 B sort) + 2 x (3.4 M x 12 B) walks + 48 MB of list
+// writes = ~280 MB instead of ~580 MB, and the result is bit-identical (tests/test_gpu_parity.py).
+#include "kernels.h"
+
+namespace gsb {
+
+// packed tile rect (binning.cu / project.cu): x = x0 | y0 << 16, y = x1 | y1 << 16, exclusive upper bounds, 0 = empty
+__device__ __forceinline__ uint32_t sb_tile_mask(uint2 r, int tx0, int ty0)
+{
+    const int x0 = (int)(r.x & 0xffff) - tx0, y0 = (int)(r.x >> 16) - ty0;
+    const int x1 = (int)(r.y & 0xffff) - tx0, y1 = (int)(r.y >> 16) - ty0;
+    const int lx = max(x0, 0), hx = min(x1, SBW), ly = max(y0, 0), hy = min(y1, SBH);
+    if (hx <= lx || hy <= ly) return 0u;
+    const uint32_t xm = ((1u << hx) - 1u) & ~((1u << lx) - 1u);          // SBW-bit row mask
+    uint32_t m = 0u;
+#pragma unroll
+    for (int y = 0; y < SBH; ++y)
+        if (y >= ly && y < hy) m |= xm << (y * SBW);
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// superblock counts in depth order (input of the level-1 scan) + M = sum of tiles-touched
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sb_counts(int N, const uint2* __restrict__ tile_rects, const uint32_t* __restrict__ touched,
+                                                   const uint32_t* __restrict__ perm0, const uint32_t* __restrict__ perm1,
+                                                   const uint32_t* __restrict__ perm_sel, uint32_t* __restrict__ sb_counts,
+                                                   uint32_t* __restrict__ total_pairs)
+{
+    const uint32_t* perm = (perm_sel && *perm_sel) ? perm1 : perm0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t t = 0;
+    if (i < N) {
+        const uint32_t g = perm ? perm[i] : (uint32_t)i;
+        const uint2 r = tile_rects[g];
+        const int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
+        uint32_t c = 0;
+        if (x1 > x0 && y1 > y0) c = (uint32_t)((((x1 - 1) / SBW) - (x0 / SBW) + 1) * (((y1 - 1) / SBH) - (y0 / SBH) + 1));
+        sb_counts[i] = c;
+        t = touched[g];
+    }
+    t = __reduce_add_sync(0xffffffffu, t);
+    __shared__ uint32_t s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(&s_sum, t);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_sum) atomicAdd(total_pairs, s_sum);
+}
+
+cudaError_t launch_sb_counts(cudaStream_t st, int N, const uint2* tile_rects, const uint32_t* touched, const uint32_t* perm0,
+                             const uint32_t* perm1, const uint32_t* perm_sel, uint32_t* sb_counts, uint32_t* total_pairs)
+{
+    cudaError_t e = cudaMemsetAsync(total_pairs, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    if (N > 0) k_sb_counts<<<cdiv(N, 256), 256, 0, st>>>(N, tile_rects, touched, perm0, perm1, perm_sel, sb_counts, total_pairs);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// level 2: count / fill.  One CTA (8 warps) per superblock, warp w owns slice w of the superblock's depth-ordered
+// list.  counts / bases are indexed [superblock][warp][tile-in-superblock].
+// ------------------------------------------------------------------------------------------------
+constexpr int L2_WARPS = 8;
+constexpr int SB_TILES = SBW * SBH;
+
+template <bool FILL>
+__global__ void __launch_bounds__(L2_WARPS * 32) k_l2_walk(int sbGridW, const uint32_t* __restrict__ sb_ranges,
+                                                           const uint32_t* __restrict__ vals0, const uint32_t* __restrict__ vals1,
+                                                           const uint32_t* __restrict__ d_result_buf,
+                                                           const uint2* __restrict__ tile_rects, uint32_t* __restrict__ slice_counts,
+                                                           const uint32_t* __restrict__ slice_base, uint32_t* __restrict__ list,
+                                                           uint32_t capacity)
+{
+    const int s = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t begin = sb_ranges[s * 2], end = sb_ranges[s * 2 + 1];
+    const uint32_t n = end > begin ? end - begin : 0u;
+    const uint32_t per = (n + L2_WARPS - 1) / L2_WARPS;
+    const uint32_t w0 = min(begin + warp * per, end), w1 = min(w0 + per, end);
+    const uint32_t* __restrict__ vals = (d_result_buf && *d_result_buf) ? vals1 : vals0;
+    const int tx0 = (s % sbGridW) * SBW, ty0 = (s / sbGridW) * SBH;
+    const uint32_t lt = (1u << lane) - 1u;
+    const size_t slot = ((size_t)s * L2_WARPS + warp) * SB_TILES;
+    uint32_t run[SB_TILES];
+#pragma unroll
+    for (int t = 0; t < SB_TILES; ++t) run[t] = FILL ? slice_base[slot + t] : 0u;
+    // software pipeline: the Gaussian index of step k+1 and its rect are in flight while step k is balloted
+    uint32_t g_next = (w0 + lane < w1) ? vals[w0 + lane] : 0xffffffffu;
+    uint2 r_next = g_next != 0xffffffffu ? tile_rects[g_next] : make_uint2(0u, 0u);
+    for (uint32_t j = w0; j < w1; j += 32) {
+        const uint32_t g = g_next;
+        const uint2 r = r_next;
+        const uint32_t jn = j + 32 + lane;
+        g_next = jn < w1 ? vals[jn] : 0xffffffffu;
+        r_next = g_next != 0xffffffffu ? tile_rects[g_next] : make_uint2(0u, 0u);
+        const uint32_t mask = g != 0xffffffffu ? sb_tile_mask(r, tx0, ty0) : 0u;
+#pragma unroll
+        for (int t = 0; t < SB_TILES; ++t) {
+            const uint32_t b = __ballot_sync(0xffffffffu, (mask >> t) & 1u);
+            if (FILL) {
+                if ((mask >> t) & 1u) {
+                    const uint32_t dst = run[t] + __popc(b & lt);
+                    if (dst < capacity) list[dst] = g;
+                }
+            }
+            run[t] += __popc(b);
+        }
+    }
+    if (!FILL && lane == 0) {
+#pragma unroll
+        for (int t = 0; t < SB_TILES; ++t) slice_counts[slot + t] = run[t];
+    }
+}
+
+cudaError_t launch_l2_count(cudaStream_t st, int numSB, int sbGridW, const uint32_t* sb_ranges, const uint32_t* vals0,
+                            const uint32_t* vals1, const uint32_t* d_result_buf, const uint2* tile_rects, uint32_t* slice_counts)
+{
+    if (numSB > 0)
+        k_l2_walk<false><<<numSB, L2_WARPS * 32, 0, st>>>(sbGridW, sb_ranges, vals0, vals1, d_result_buf, tile_rects, slice_counts, nullptr,
+                                                          nullptr, 0u);
+    return cudaGetLastError();
+}
+cudaError_t launch_l2_fill(cudaStream_t st, int numSB, int sbGridW, const uint32_t* sb_ranges, const uint32_t* vals0,
+                           const uint32_t* vals1, const uint32_t* d_result_buf, const uint2* tile_rects, const uint32_t* slice_base,
+                           uint32_t* list, uint32_t capacity)
+{
+    if (numSB > 0)
+        k_l2_walk<true><<<numSB, L2_WARPS * 32, 0, st>>>(sbGridW, sb_ranges, vals0, vals1, d_result_buf, tile_rects, nullptr, slice_base,
+                                                         list, capacity);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// One CTA: slice counts -> tile counts -> exclusive scan -> tile ranges (reference convention: (0,0) for an empty
+// tile), monotone tile starts (numTiles + 1), slice bases, total, and the heavy-first tile order (counting sort
+// over 1024 length buckets; the rasterisers map work item -> order[item]).
+// ------------------------------------------------------------------------------------------------
+constexpr int TS_THREADS = 256;
+constexpr int TS_BUCKETS = 1024;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* s_warp, uint32_t* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < TS_THREADS / 32; ++w) {
+        const uint32_t x = s_warp[w];
+        if (w < warp) pre += x;
+        tot += x;
+    }
+    *total = tot;
+    return pre + inc - v;
+}
+
+__global__ void __launch_bounds__(TS_THREADS) k_tile_scan_order(int gridW, int gridH, int sbGridW, const uint32_t* __restrict__ slice_counts,
+                                                                uint32_t* __restrict__ slice_base, uint32_t* __restrict__ tile_ranges,
+                                                                uint32_t* __restrict__ tile_starts, uint32_t* __restrict__ order,
+                                                                uint32_t* __restrict__ total_out)
+{
+    __shared__ uint32_t s_warp[TS_THREADS / 32];
+    __shared__ uint32_t s_hist[TS_BUCKETS];
+    __shared__ uint32_t s_max;
+    const int numTiles = gridW * gridH;
+    const int tid = threadIdx.x;
+    const int per = (numTiles + TS_THREADS - 1) / TS_THREADS;        // consecutive tiles per thread
+    const int t0 = tid * per, t1 = min(t0 + per, numTiles);
+    auto slot_of = [&](int t) -> size_t {
+        const int tx = t % gridW, ty = t / gridW;
+        const int s = (ty / SBH) * sbGridW + tx / SBW;
+        return (size_t)s * L2_WARPS * SB_TILES + (size_t)((ty % SBH) * SBW + tx % SBW);
+    };
+    auto count_of = [&](int t) -> uint32_t {
+        const size_t sl = slot_of(t);
+        uint32_t c = 0;
+#pragma unroll
+        for (int w = 0; w < L2_WARPS; ++w) c += slice_counts[sl + (size_t)w * SB_TILES];
+        return c;
+    };
+    uint32_t mine = 0, mx = 0;
+    for (int t = t0; t < t1; ++t) {
+        const uint32_t c = count_of(t);
+        mine += c;
+        mx = max(mx, c);
+    }
+    uint32_t total = 0;
+    uint32_t run = block_exclusive_scan_256(mine, s_warp, &total);
+    for (int t = t0; t < t1; ++t) {
+        const size_t sl = slot_of(t);
+        uint32_t c = 0, b = run;
+#pragma unroll
+        for (int w = 0; w < L2_WARPS; ++w) {
+            const uint32_t x = slice_counts[sl + (size_t)w * SB_TILES];
+            slice_base[sl + (size_t)w * SB_TILES] = b;
+            b += x;
+            c += x;
+        }
+        tile_starts[t] = run;
+        tile_ranges[t * 2 + 0] = c ? run : 0u;       // compute_tile_ranges leaves (0,0) for tiles nobody touches
+        tile_ranges[t * 2 + 1] = c ? run + c : 0u;
+        run += c;
+    }
+    if (tid == 0) {
+        tile_starts[numTiles] = total;
+        if (total_out) *total_out = total;
+    }
+    // ---- heavy-first order
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    __syncthreads();
+    if ((tid & 31) == 0) s_warp[tid >> 5] = mx;
+    for (int i = tid; i < TS_BUCKETS; i += TS_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t m = 0;
+        for (int w = 0; w < TS_THREADS / 32; ++w) m = max(m, s_warp[w]);
+        s_max = m;
+    }
+    __syncthreads();
+    const uint32_t maxc = max(s_max, 1u);
+    auto bucket_of = [&](uint32_t c) { return (uint32_t)(TS_BUCKETS - 1) - (uint32_t)(((unsigned long long)c * (TS_BUCKETS - 1)) / maxc); };
+    auto cnt_final = [&](int t) { return tile_ranges[t * 2 + 1] - tile_ranges[t * 2]; };
+    __syncthreads();
+    for (int t = t0; t < t1; ++t) atomicAdd(&s_hist[bucket_of(cnt_final(t))], 1u);
+    __syncthreads();
+    constexpr int PER = TS_BUCKETS / TS_THREADS;
+    uint32_t v[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] = s_hist[tid * PER + i]; sum += v[i]; }
+    uint32_t dummy;
+    uint32_t pre = block_exclusive_scan_256(sum, s_warp, &dummy);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { s_hist[tid * PER + i] = pre; pre += v[i]; }
+    __syncthreads();
+    for (int t = t0; t < t1; ++t) order[atomicAdd(&s_hist[bucket_of(cnt_final(t))], 1u)] = (uint32_t)t;
+}
+
+cudaError_t launch_tile_scan_order(cudaStream_t st, int gridW, int gridH, int sbGridW, const uint32_t* slice_counts, uint32_t* slice_base,
+                                   uint32_t* tile_ranges, uint32_t* tile_starts, uint32_t* order, uint32_t* total_out)
+{
+    if (gridW * gridH > 0)
+        k_tile_scan_order<<<1, TS_THREADS, 0, st>>>(gridW, gridH, sbGridW, slice_counts, slice_base, tile_ranges, tile_starts, order, total_out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity API: the reference's sortedKeysHigh / sortedKeysLow for list position j
+// (tile id by binary search in the monotone tile starts, depth bits of the listed Gaussian)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_expand_sorted_keys(uint32_t M, int numTiles, const uint32_t* __restrict__ tile_starts, const uint32_t* __restrict__ list,
+                                     const float* __restrict__ depth_ptr, int depth_stride, uint32_t* __restrict__ hi,
+                                     uint32_t* __restrict__ lo)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    if (hi) {
+        int a = 0, b = numTiles;       // invariant: tile_starts[a] <= j < tile_starts[b]
+        while (b - a > 1) {
+            const int m = (a + b) >> 1;
+            if (tile_starts[m] <= j) a = m; else b = m;
+        }
+        hi[j] = (uint32_t)a;
+    }
+    if (lo) lo[j] = __float_as_uint(depth_ptr[(size_t)list[j] * depth_stride]);
+}
+
+cudaError_t launch_expand_sorted_keys(cudaStream_t st, uint32_t M, int numTiles, const uint32_t* tile_starts, const uint32_t* list,
+                                      const float* depth_ptr, int depth_stride, uint32_t* hi, uint32_t* lo)
+{
+    if (M > 0) k_expand_sorted_keys<<<cdiv(M, 256), 256, 0, st>>>(M, numTiles, tile_starts, list, depth_ptr, depth_stride, hi, lo);
+    return cudaGetLastError();
+}
+
+}  // namespace gsb

@@ -244,8 +244,9 @@ typedef struct gsb_stats {
     uint64_t pair_capacity;     /* current capacity of the intersection buffers */
     double   stage_ms[16];      /* accumulated CUDA-event time per stage when timing is enabled */
     uint64_t stage_calls[16];
+    uint64_t sb_pairs_last_view; /* (Gaussian, superblock) pairs of the last view: the only list that is radix-sorted */
 } gsb_stats;
-enum { GSB_STAGE_PROJECT_FWD = 0, GSB_STAGE_SCAN, GSB_STAGE_KEYGEN, GSB_STAGE_SORT, GSB_STAGE_RANGES_GATHER,
+enum { GSB_STAGE_PROJECT_FWD = 0, GSB_STAGE_SCAN, GSB_STAGE_KEYGEN, GSB_STAGE_SORT, GSB_STAGE_TILE_LISTS,
        GSB_STAGE_RASTER_FWD, GSB_STAGE_LOSS, GSB_STAGE_RASTER_BWD, GSB_STAGE_PROJECT_BWD, GSB_STAGE_ADAM,
        GSB_STAGE_H2D, GSB_STAGE_DEPTH_SORT, GSB_STAGE_COUNT };
 /* Sum of lastContrib over the image of the last gsb_render_forward = number of (pixel, Gaussian)

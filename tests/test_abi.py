@@ -40,7 +40,7 @@ def test_struct_layouts_match_header(lib):
     from gaussiansplattingmlx_b200 import _lib
     assert C.sizeof(_lib.GsbConfig) == 14 * 4
     assert C.sizeof(_lib.GsbCamera) == 39 * 4
-    assert C.sizeof(_lib.GsbStats) == 5 * 8 + 16 * 8 + 16 * 8
+    assert C.sizeof(_lib.GsbStats) == 5 * 8 + 16 * 8 + 16 * 8 + 8
     assert lib.gsb_abi_version() == 1
     cfg = _lib.GsbConfig()
     lib.gsb_default_config(C.byref(cfg))
