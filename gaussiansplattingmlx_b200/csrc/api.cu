@@ -63,6 +63,8 @@ struct Ctx {
         uint32_t* slice_counts = nullptr; // [numSB,8 warps,8 tiles]
         uint32_t* slice_base = nullptr;   // [numSB,8 warps,8 tiles]
         uint32_t* tile_starts = nullptr;  // [numTiles+1] monotone CSR offsets
+        uint32_t* tile_counts = nullptr;  // [numTiles]
+        void* tile_scan_ws = nullptr;
         uint32_t* tile_ranges = nullptr;  // [numTiles,2] (reference convention: (0,0) for an empty tile)
         uint32_t* tile_order = nullptr;   // [numTiles] tile ids, longest list first
         // control words: [0] = M of the current view, [1] = overflow flag, [2] scratch, [3] raster work counter,
@@ -417,10 +419,14 @@ static int enqueue_binning(Ctx* c, Ctx::ViewBufs& v, cudaStream_t st, int N, con
         // 5. superblock slices -> per-tile counts -> CSR ranges + heavy-first order -> the tile lists (tilelists.cu)
         GSB_CUDA_CHECK(c, launch_ranges_gather(st, vp, v.keys[0], v.keys[1], v.vals[0], v.vals[1], v.d_result_buf, &v.d_ctl[4],
                                                c->capL1, nullptr, v.sb_ranges, nullptr, c->numSB));
-        GSB_CUDA_CHECK(c, launch_l2_count(st, c->numSB, c->sbGridW, v.sb_ranges, v.vals[0], v.vals[1], v.d_result_buf, v.tile_rects,
-                                          v.slice_counts));
-        GSB_CUDA_CHECK(c, launch_tile_scan_order(st, c->gridW, c->gridH, c->sbGridW, v.slice_counts, v.slice_base, v.tile_ranges,
-                                                 v.tile_starts, v.tile_order, &v.d_ctl[5]));
+        GSB_CUDA_CHECK(c, launch_l2_count(st, c->numSB, c->sbGridW, c->gridW, c->gridH, v.sb_ranges, v.vals[0], v.vals[1], v.d_result_buf,
+                                          v.tile_rects, v.slice_counts, v.tile_counts));
+        GSB_CUDA_CHECK(c, launch_exclusive_scan(st, c->numTiles, v.tile_counts, nullptr, nullptr, nullptr, v.tile_starts, &v.d_ctl[5],
+                                                v.tile_scan_ws));
+        GSB_CUDA_CHECK(c, launch_tile_bases(st, c->gridW, c->gridH, c->sbGridW, v.tile_counts, v.tile_starts, v.slice_counts, v.slice_base,
+                                            v.tile_ranges));
+        GSB_CUDA_CHECK(c, launch_tile_order(st, c->numTiles, v.tile_ranges, v.tile_order));
+        launches += 2;
         GSB_CUDA_CHECK(c, launch_l2_fill(st, c->numSB, c->sbGridW, v.sb_ranges, v.vals[0], v.vals[1], v.d_result_buf, v.tile_rects,
                                          v.slice_base, v.list, c->capM));
         launches += 4;
@@ -505,7 +511,8 @@ static void destroy_ctx(Ctx* c)
         if (v.scan_ws) cudaFree(v.scan_ws);
         if (v.sort_ws) cudaFree(v.sort_ws);
         dev_free(v.tile_ranges); dev_free(v.tile_order); dev_free(v.d_ctl); dev_free(v.sbcnt); dev_free(v.list);
-        dev_free(v.sb_ranges); dev_free(v.slice_counts); dev_free(v.slice_base); dev_free(v.tile_starts);
+        dev_free(v.sb_ranges); dev_free(v.slice_counts); dev_free(v.slice_base); dev_free(v.tile_starts); dev_free(v.tile_counts);
+        if (v.tile_scan_ws) cudaFree(v.tile_scan_ws);
         if (v.h_ctl) cudaFreeHost(v.h_ctl);
         cudaEvent_t* evs[] = {&v.ev_ctl, &v.ev_front, &v.ev_back};
         for (cudaEvent_t* e : evs) if (*e) cudaEventDestroy(*e);
@@ -640,6 +647,8 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
         CREATE_CHECK(dev_alloc(&v.tile_ranges, (size_t)c->numTiles * 2));
         CREATE_CHECK(dev_alloc(&v.tile_order, (size_t)c->numTiles));
         CREATE_CHECK(dev_alloc(&v.tile_starts, (size_t)c->numTiles + 1));
+        CREATE_CHECK(dev_alloc(&v.tile_counts, (size_t)c->numTiles));
+        CREATE_CHECK(cudaMalloc(&v.tile_scan_ws, scan_ws_bytes(c->numTiles)));
         CREATE_CHECK(dev_alloc(&v.sb_ranges, (size_t)c->numSB * 2));
         CREATE_CHECK(dev_alloc(&v.slice_counts, (size_t)c->numSB * 64));
         CREATE_CHECK(dev_alloc(&v.slice_base, (size_t)c->numSB * 64));

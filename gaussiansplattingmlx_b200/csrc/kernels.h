@@ -102,13 +102,14 @@ cudaError_t launch_sorted_keys_out(cudaStream_t st, uint32_t M, const uint32_t* 
 // ---- tilelists.cu ------------------------------------------------------------------------------
 cudaError_t launch_sb_counts(cudaStream_t st, int N, const uint2* tile_rects, const uint32_t* touched, const uint32_t* perm0,
                              const uint32_t* perm1, const uint32_t* perm_sel, uint32_t* sb_counts, uint32_t* total_pairs);
-cudaError_t launch_l2_count(cudaStream_t st, int numSB, int sbGridW, const uint32_t* sb_ranges, const uint32_t* vals0,
-                            const uint32_t* vals1, const uint32_t* d_result_buf, const uint2* tile_rects, uint32_t* slice_counts);
+cudaError_t launch_l2_count(cudaStream_t st, int numSB, int sbGridW, int gridW, int gridH, const uint32_t* sb_ranges, const uint32_t* vals0,
+                            const uint32_t* vals1, const uint32_t* d_result_buf, const uint2* tile_rects, uint32_t* slice_counts,
+                            uint32_t* tile_counts);
 cudaError_t launch_l2_fill(cudaStream_t st, int numSB, int sbGridW, const uint32_t* sb_ranges, const uint32_t* vals0,
                            const uint32_t* vals1, const uint32_t* d_result_buf, const uint2* tile_rects, const uint32_t* slice_base,
                            uint32_t* list, uint32_t capacity);
-cudaError_t launch_tile_scan_order(cudaStream_t st, int gridW, int gridH, int sbGridW, const uint32_t* slice_counts, uint32_t* slice_base,
-                                   uint32_t* tile_ranges, uint32_t* tile_starts, uint32_t* order, uint32_t* total_out);
+cudaError_t launch_tile_bases(cudaStream_t st, int gridW, int gridH, int sbGridW, const uint32_t* tile_counts, const uint32_t* tile_starts,
+                              const uint32_t* slice_counts, uint32_t* slice_base, uint32_t* tile_ranges);
 cudaError_t launch_expand_sorted_keys(cudaStream_t st, uint32_t M, int numTiles, const uint32_t* tile_starts, const uint32_t* list,
                                       const float* depth_ptr, int depth_stride, uint32_t* hi, uint32_t* lo);
 

@@ -11,9 +11,9 @@
 //             the superblock id (the onesweep of binning.cu): every superblock now owns a depth-ordered slice.
 //   level 2   a CTA per superblock, its slice cut into 8 contiguous warp slices.  COUNT: each warp walks its slice
 //             32 entries at a time, rebuilds the 8-bit "which of my 8 tiles does this rect cover" mask from the
-//             packed tile rect and counts per tile with ballots.  One small single-CTA kernel turns the
-//             (superblock, warp slice, tile) counts into tile ranges (CSR), slice bases and the heavy-first tile
-//             order.  FILL: the same walk again; lane ranks from the ballots give every (Gaussian, tile) pair its
+//             packed tile rect and counts per tile with ballots.  The per-tile totals are scanned
+//             (binning.cu), k_tile_bases turns them into CSR ranges and (superblock, warp slice, tile) bases, and
+//             k_tile_order (binning.cu) gives the heavy-first launch order.  FILL: the same walk again; lane ranks from the ballots give every (Gaussian, tile) pair its
 //             final slot — stable by construction, no atomics, writes coalesced per tile.
 //
 // HBM traffic per view at C3: ~3.4 M pairs x (8 B keygen + 36 B sort) + 2 x (3.4 M x 12 B) walks + 48 MB of list
@@ -88,8 +88,9 @@ __global__ void __launch_bounds__(L2_WARPS * 32) k_l2_walk(int sbGridW, const ui
                                                            const uint32_t* __restrict__ d_result_buf,
                                                            const uint2* __restrict__ tile_rects, uint32_t* __restrict__ slice_counts,
                                                            const uint32_t* __restrict__ slice_base, uint32_t* __restrict__ list,
-                                                           uint32_t capacity)
+                                                           uint32_t capacity, uint32_t* __restrict__ tile_counts, int gridW, int gridH)
 {
+    __shared__ uint32_t s_cnt[L2_WARPS][SB_TILES];
     const int s = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t begin = sb_ranges[s * 2], end = sb_ranges[s * 2 + 1];
@@ -103,15 +104,18 @@ __global__ void __launch_bounds__(L2_WARPS * 32) k_l2_walk(int sbGridW, const ui
     uint32_t run[SB_TILES];
 #pragma unroll
     for (int t = 0; t < SB_TILES; ++t) run[t] = FILL ? slice_base[slot + t] : 0u;
-    // software pipeline: the Gaussian index of step k+1 and its rect are in flight while step k is balloted
-    uint32_t g_next = (w0 + lane < w1) ? vals[w0 + lane] : 0xffffffffu;
-    uint2 r_next = g_next != 0xffffffffu ? tile_rects[g_next] : make_uint2(0u, 0u);
+    // software pipeline over the dependent gather (index -> rect): the index of step k+2 and the rect of step k+1 are
+    // in flight while step k is balloted, so no load is consumed in the iteration that issues it
+    auto ld_idx = [&](uint32_t j) { return j < w1 ? vals[j] : 0xffffffffu; };
+    auto ld_rect = [&](uint32_t g) { return g != 0xffffffffu ? tile_rects[g] : make_uint2(0u, 0u); };
+    uint32_t g1 = ld_idx(w0 + lane), g2 = ld_idx(w0 + 32 + lane);
+    uint2 r1 = ld_rect(g1);
     for (uint32_t j = w0; j < w1; j += 32) {
-        const uint32_t g = g_next;
-        const uint2 r = r_next;
-        const uint32_t jn = j + 32 + lane;
-        g_next = jn < w1 ? vals[jn] : 0xffffffffu;
-        r_next = g_next != 0xffffffffu ? tile_rects[g_next] : make_uint2(0u, 0u);
+        const uint32_t g = g1;
+        const uint2 r = r1;
+        g1 = g2;
+        g2 = ld_idx(j + 64 + lane);
+        r1 = ld_rect(g1);
         const uint32_t mask = g != 0xffffffffu ? sb_tile_mask(r, tx0, ty0) : 0u;
 #pragma unroll
         for (int t = 0; t < SB_TILES; ++t) {
@@ -125,18 +129,35 @@ __global__ void __launch_bounds__(L2_WARPS * 32) k_l2_walk(int sbGridW, const ui
             run[t] += __popc(b);
         }
     }
-    if (!FILL && lane == 0) {
+    if (!FILL) {
+        if (lane == 0) {
 #pragma unroll
-        for (int t = 0; t < SB_TILES; ++t) slice_counts[slot + t] = run[t];
+            for (int t = 0; t < SB_TILES; ++t) {
+                slice_counts[slot + t] = run[t];
+                s_cnt[warp][t] = run[t];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < SB_TILES) {   // tile totals of this superblock (each tile belongs to exactly one superblock)
+            const int t = threadIdx.x;
+            const int tx = tx0 + t % SBW, ty = ty0 + t / SBW;
+            if (tx < gridW && ty < gridH) {
+                uint32_t c = 0;
+#pragma unroll
+                for (int w = 0; w < L2_WARPS; ++w) c += s_cnt[w][t];
+                tile_counts[ty * gridW + tx] = c;
+            }
+        }
     }
 }
 
-cudaError_t launch_l2_count(cudaStream_t st, int numSB, int sbGridW, const uint32_t* sb_ranges, const uint32_t* vals0,
-                            const uint32_t* vals1, const uint32_t* d_result_buf, const uint2* tile_rects, uint32_t* slice_counts)
+cudaError_t launch_l2_count(cudaStream_t st, int numSB, int sbGridW, int gridW, int gridH, const uint32_t* sb_ranges, const uint32_t* vals0,
+                            const uint32_t* vals1, const uint32_t* d_result_buf, const uint2* tile_rects, uint32_t* slice_counts,
+                            uint32_t* tile_counts)
 {
     if (numSB > 0)
         k_l2_walk<false><<<numSB, L2_WARPS * 32, 0, st>>>(sbGridW, sb_ranges, vals0, vals1, d_result_buf, tile_rects, slice_counts, nullptr,
-                                                          nullptr, 0u);
+                                                          nullptr, 0u, tile_counts, gridW, gridH);
     return cudaGetLastError();
 }
 cudaError_t launch_l2_fill(cudaStream_t st, int numSB, int sbGridW, const uint32_t* sb_ranges, const uint32_t* vals0,
@@ -145,127 +166,40 @@ cudaError_t launch_l2_fill(cudaStream_t st, int numSB, int sbGridW, const uint32
 {
     if (numSB > 0)
         k_l2_walk<true><<<numSB, L2_WARPS * 32, 0, st>>>(sbGridW, sb_ranges, vals0, vals1, d_result_buf, tile_rects, nullptr, slice_base,
-                                                         list, capacity);
+                                                         list, capacity, nullptr, 0, 0);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
-// One CTA: slice counts -> tile counts -> exclusive scan -> tile ranges (reference convention: (0,0) for an empty
-// tile), monotone tile starts (numTiles + 1), slice bases, total, and the heavy-first tile order (counting sort
-// over 1024 length buckets; the rasterisers map work item -> order[item]).
+// tile counts (written by the count walk) -> exclusive scan (binning.cu, decoupled look-back) -> this kernel:
+// tile ranges in the reference convention ((0,0) for an empty tile) and the base of every (superblock, warp
+// slice, tile) run.  One thread per tile.
 // ------------------------------------------------------------------------------------------------
-constexpr int TS_THREADS = 256;
-constexpr int TS_BUCKETS = 1024;
-
-__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* s_warp, uint32_t* total)
+__global__ void __launch_bounds__(256) k_tile_bases(int gridW, int gridH, int sbGridW, const uint32_t* __restrict__ tile_counts,
+                                                    const uint32_t* __restrict__ tile_starts, const uint32_t* __restrict__ slice_counts,
+                                                    uint32_t* __restrict__ slice_base, uint32_t* __restrict__ tile_ranges)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = v;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= gridW * gridH) return;
+    const int tx = t % gridW, ty = t / gridW;
+    const int s = (ty / SBH) * sbGridW + tx / SBW;
+    const size_t sl = (size_t)s * L2_WARPS * SB_TILES + (size_t)((ty % SBH) * SBW + tx % SBW);
+    const uint32_t start = tile_starts[t], c = tile_counts[t];
+    uint32_t b = start;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += n;
+    for (int w = 0; w < L2_WARPS; ++w) {
+        slice_base[sl + (size_t)w * SB_TILES] = b;
+        b += slice_counts[sl + (size_t)w * SB_TILES];
     }
-    __syncthreads();
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    uint32_t pre = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < TS_THREADS / 32; ++w) {
-        const uint32_t x = s_warp[w];
-        if (w < warp) pre += x;
-        tot += x;
-    }
-    *total = tot;
-    return pre + inc - v;
+    tile_ranges[t * 2 + 0] = c ? start : 0u;       // compute_tile_ranges leaves (0,0) for tiles nobody touches
+    tile_ranges[t * 2 + 1] = c ? start + c : 0u;
 }
 
-__global__ void __launch_bounds__(TS_THREADS) k_tile_scan_order(int gridW, int gridH, int sbGridW, const uint32_t* __restrict__ slice_counts,
-                                                                uint32_t* __restrict__ slice_base, uint32_t* __restrict__ tile_ranges,
-                                                                uint32_t* __restrict__ tile_starts, uint32_t* __restrict__ order,
-                                                                uint32_t* __restrict__ total_out)
+cudaError_t launch_tile_bases(cudaStream_t st, int gridW, int gridH, int sbGridW, const uint32_t* tile_counts, const uint32_t* tile_starts,
+                              const uint32_t* slice_counts, uint32_t* slice_base, uint32_t* tile_ranges)
 {
-    __shared__ uint32_t s_warp[TS_THREADS / 32];
-    __shared__ uint32_t s_hist[TS_BUCKETS];
-    __shared__ uint32_t s_max;
-    const int numTiles = gridW * gridH;
-    const int tid = threadIdx.x;
-    const int per = (numTiles + TS_THREADS - 1) / TS_THREADS;        // consecutive tiles per thread
-    const int t0 = tid * per, t1 = min(t0 + per, numTiles);
-    auto slot_of = [&](int t) -> size_t {
-        const int tx = t % gridW, ty = t / gridW;
-        const int s = (ty / SBH) * sbGridW + tx / SBW;
-        return (size_t)s * L2_WARPS * SB_TILES + (size_t)((ty % SBH) * SBW + tx % SBW);
-    };
-    auto count_of = [&](int t) -> uint32_t {
-        const size_t sl = slot_of(t);
-        uint32_t c = 0;
-#pragma unroll
-        for (int w = 0; w < L2_WARPS; ++w) c += slice_counts[sl + (size_t)w * SB_TILES];
-        return c;
-    };
-    uint32_t mine = 0, mx = 0;
-    for (int t = t0; t < t1; ++t) {
-        const uint32_t c = count_of(t);
-        mine += c;
-        mx = max(mx, c);
-    }
-    uint32_t total = 0;
-    uint32_t run = block_exclusive_scan_256(mine, s_warp, &total);
-    for (int t = t0; t < t1; ++t) {
-        const size_t sl = slot_of(t);
-        uint32_t c = 0, b = run;
-#pragma unroll
-        for (int w = 0; w < L2_WARPS; ++w) {
-            const uint32_t x = slice_counts[sl + (size_t)w * SB_TILES];
-            slice_base[sl + (size_t)w * SB_TILES] = b;
-            b += x;
-            c += x;
-        }
-        tile_starts[t] = run;
-        tile_ranges[t * 2 + 0] = c ? run : 0u;       // compute_tile_ranges leaves (0,0) for tiles nobody touches
-        tile_ranges[t * 2 + 1] = c ? run + c : 0u;
-        run += c;
-    }
-    if (tid == 0) {
-        tile_starts[numTiles] = total;
-        if (total_out) *total_out = total;
-    }
-    // ---- heavy-first order
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    __syncthreads();
-    if ((tid & 31) == 0) s_warp[tid >> 5] = mx;
-    for (int i = tid; i < TS_BUCKETS; i += TS_THREADS) s_hist[i] = 0;
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t m = 0;
-        for (int w = 0; w < TS_THREADS / 32; ++w) m = max(m, s_warp[w]);
-        s_max = m;
-    }
-    __syncthreads();
-    const uint32_t maxc = max(s_max, 1u);
-    auto bucket_of = [&](uint32_t c) { return (uint32_t)(TS_BUCKETS - 1) - (uint32_t)(((unsigned long long)c * (TS_BUCKETS - 1)) / maxc); };
-    auto cnt_final = [&](int t) { return tile_ranges[t * 2 + 1] - tile_ranges[t * 2]; };
-    __syncthreads();
-    for (int t = t0; t < t1; ++t) atomicAdd(&s_hist[bucket_of(cnt_final(t))], 1u);
-    __syncthreads();
-    constexpr int PER = TS_BUCKETS / TS_THREADS;
-    uint32_t v[PER], sum = 0;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) { v[i] = s_hist[tid * PER + i]; sum += v[i]; }
-    uint32_t dummy;
-    uint32_t pre = block_exclusive_scan_256(sum, s_warp, &dummy);
-#pragma unroll
-    for (int i = 0; i < PER; ++i) { s_hist[tid * PER + i] = pre; pre += v[i]; }
-    __syncthreads();
-    for (int t = t0; t < t1; ++t) order[atomicAdd(&s_hist[bucket_of(cnt_final(t))], 1u)] = (uint32_t)t;
-}
-
-cudaError_t launch_tile_scan_order(cudaStream_t st, int gridW, int gridH, int sbGridW, const uint32_t* slice_counts, uint32_t* slice_base,
-                                   uint32_t* tile_ranges, uint32_t* tile_starts, uint32_t* order, uint32_t* total_out)
-{
-    if (gridW * gridH > 0)
-        k_tile_scan_order<<<1, TS_THREADS, 0, st>>>(gridW, gridH, sbGridW, slice_counts, slice_base, tile_ranges, tile_starts, order, total_out);
+    const int n = gridW * gridH;
+    if (n > 0) k_tile_bases<<<cdiv(n, 256), 256, 0, st>>>(gridW, gridH, sbGridW, tile_counts, tile_starts, slice_counts, slice_base, tile_ranges);
     return cudaGetLastError();
 }
 
