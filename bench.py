@@ -64,7 +64,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+                                          "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -181,6 +181,8 @@ def workload_config(wl, params, views, world, global_views=None):
             "gaussians": n, "width": wl.width, "height": wl.height, "views_per_step": views, "global_views_per_step": global_views,
             "tile": wl.tile,
             "parallelism": f"view-parallel dp{world}" if world > 1 else "single GPU",
+            "state_policy": "every timed region starts from the freshly initialised model (W warm-up + K timed steps of the same "
+                            "trajectory): training on random targets inflates the Gaussians, so later steps are heavier",
             "l2_policy": "inputs larger than L2 (per step: 236 MB params + 236 MB grads + 472 MB Adam state + per-view "
                          "key/record streams > 126 MB L2); no explicit flush"}
 
@@ -227,19 +229,39 @@ def run_gsb(args, rank, local_rank, world):
     gcams = [_lib.make_camera(cams[v]) for v in my_views]
     host_targets = [torch.from_numpy(targets[v]).pin_memory() for v in my_views]
     dev_targets = [t.to(dev, non_blocking=True) for t in host_targets]
-    grad_block = ctx.trainer_grad_block() if world > 1 else None
+    dp_state = {"grad_block": ctx.trainer_grad_block() if world > 1 else None}
     total_iters = 30000
     gscale = 1.0 / views
 
+    # end-to-end mode: pinned host targets go H2D every step and every step's loss comes back D2H into a pinned slot
+    # (asynchronously, GSB_FLAG_ASYNC_LOSS); the value of step i is read after step i+1 has been enqueued, so the
+    # view pipeline never drains.  Every loss is read inside the timed region.
+    loss_slots = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_events = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"pending": None, "losses": []}
+
+    def drain_loss():
+        if e2e_state["pending"] is not None:
+            s_ = e2e_state["pending"]
+            loss_events[s_].synchronize()
+            e2e_state["losses"].append(float(loss_slots[s_][0]))
+            e2e_state["pending"] = None
+
     def step(it, host: bool, want_loss: bool):
         tg = host_targets if host else dev_targets
-        loss = None
         if my_views:
-            loss = ctx.trainer_accumulate(gcams, tg, zero_grads=True, grad_scale=gscale, want_loss=want_loss)
+            if want_loss:
+                slot = it & 1
+                ctx.trainer_accumulate(gcams, tg, zero_grads=True, grad_scale=gscale, loss_out=loss_slots[slot])
+                loss_events[slot].record()
+            else:
+                ctx.trainer_accumulate(gcams, tg, zero_grads=True, grad_scale=gscale, want_loss=False)
         if world > 1:
-            dist.all_reduce(grad_block)
+            dist.all_reduce(dp_state["grad_block"])
         ctx.trainer_apply(it, total_iters, reset_state=False)
-        return loss
+        if want_loss and my_views:
+            drain_loss()                       # the PREVIOUS step's loss: its copy finished long ago
+            e2e_state["pending"] = it & 1
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -253,6 +275,8 @@ def run_gsb(args, rank, local_rank, world):
         e0.record()
         for i in range(k):
             step(it0 + i, host, want_loss)
+        if want_loss:
+            drain_loss()                       # the last step's loss is read inside the timed region too
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -262,17 +286,34 @@ def run_gsb(args, rank, local_rank, world):
             ms = float(t.item())
         return ms
 
-    # ---- set-up steps (size the intersection buffers, fault in every allocation, let clocks settle), then the W warm-up steps
-    it = 0
-    for _ in range(8):
-        step(it, False, False); it += 1
-    step(it, True, True); it += 1
-    barrier()
-    for _ in range(args.warmup):
-        step(it, False, False); it += 1
+    # Training on synthetic random targets moves the Gaussians (pairs and blend evaluations per view grow step after
+    # step), so every timed region starts from the SAME state: parameters re-initialised, optimiser state zeroed, then
+    # the W warm-up steps, then the K timed steps — region to region the work is identical.
+    host_params = {k: torch.from_numpy(v) for k, v in params.items()}
+
+    def fresh_region(host: bool, want_loss: bool):
+        barrier()
+        ctx.trainer_init(host_params)
+        if world > 1:
+            dp_state["grad_block"] = ctx.trainer_grad_block()
+        for i in range(args.warmup):
+            step(i, host, want_loss)
+        if want_loss:
+            drain_loss()
+        barrier()
+        return args.warmup
+
+    # ---- set-up steps (size the intersection buffers, fault in every allocation, let clocks settle)
+    for i in range(6):
+        step(i, False, False)
+    step(6, True, False)
     barrier()
 
-    # blend evaluations per step on this rank (for the raster rooflines), from lastContrib of each view
+    # blend evaluations per step on this rank (for the raster rooflines), from lastContrib of each view, measured on the
+    # state in the middle of a timed region
+    fresh_region(False, False)
+    for i in range(args.steps // 2):
+        step(args.warmup + i, False, False)
     evals = 0
     pairs = 0
     l1_pairs = 0
@@ -283,15 +324,17 @@ def run_gsb(args, rank, local_rank, world):
         l1_pairs += ctx.stats()["sb_pairs_last_view"]
 
     # ---- timed region 1: inputs resident in HBM (the product configuration: view pipeline on)
+    it = fresh_region(False, False)
     ctx.stats_reset()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ms_dev = timed(False, False, args.steps, it); it += args.steps
+    ms_dev = timed(False, False, args.steps, it)
     launches = ctx.stats()["kernel_launches"]
     if args.debug_overlap and rank == 0:   # how much each stage stretches when the two streams share the SMs
+        it = fresh_region(False, False)
         ctx.stats_reset(); ctx.enable_stage_timing(True)
-        ms_dbg = timed(False, False, args.steps, it); it += args.steps
+        ms_dbg = timed(False, False, args.steps, it)
         sd = ctx.stats(); ctx.enable_stage_timing(False)
         log(f"[overlap on] {ms_dbg / args.steps:.3f} ms/step; per-launch stage ms: " +
             ", ".join(f"{k} {sd['stage_ms'][k] / max(sd['stage_calls'][k], 1):.3f}" for k in sd["stage_ms"] if sd["stage_calls"][k]))
@@ -300,16 +343,20 @@ def run_gsb(args, rank, local_rank, world):
     #      bracketed by CUDA events on that stream), so a kernel's time is not inflated by the kernels of the next
     #      view that overlap it in region 1
     ctx.set_flags(base_flags | _lib.GSB_FLAG_NO_OVERLAP)
+    it = fresh_region(False, False)
     ctx.stats_reset()
     ctx.enable_stage_timing(True)
-    ms_serial = timed(False, False, args.steps, it); it += args.steps
+    ms_serial = timed(False, False, args.steps, it)
     st = ctx.stats()
     ctx.enable_stage_timing(False)
     ctx.set_flags(base_flags)
 
     # ---- timed region 2: end to end through the public API (pinned host targets H2D + loss D2H every step)
-    step(it, True, True); it += 1
-    ms_e2e = timed(True, True, args.steps, it); it += args.steps
+    ctx.set_flags(base_flags | _lib.GSB_FLAG_ASYNC_LOSS)
+    it = fresh_region(True, True)
+    e2e_state["losses"].clear()
+    ms_e2e = timed(True, True, args.steps, it)
+    assert len(e2e_state["losses"]) >= args.steps and all(np.isfinite(l) for l in e2e_state["losses"])
     clk = clocks.stop() if rank == 0 else None
 
     if rank != 0:
@@ -391,7 +438,8 @@ def run_gsb(args, rank, local_rank, world):
            "views_per_s": value * per_step,
            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                    "h2d_bytes_per_step": img_bytes * views, "d2h_bytes_per_step": 4 * world,
-                   "api": "Context.trainer_accumulate(pinned host targets, want_loss) [+ NCCL all_reduce] + trainer_apply"},
+                   "api": "Context.trainer_accumulate(pinned host targets, pinned loss slot) [+ NCCL all_reduce] + trainer_apply; "
+                          "every step's loss is copied D2H asynchronously and read on the host one step later"},
            "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_kernels": kernels,
            "ms_per_step_serialized": ms_serial / K,
            "cpu_baseline": cpu}
@@ -403,7 +451,7 @@ def run_gsb(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gsb", choices=["gsb", "reference"])
     ap.add_argument("--workload", default="C3")

@@ -17,6 +17,7 @@ GSB_OK = 0
 GSB_ERR_INVALID, GSB_ERR_CUDA, GSB_ERR_UNSUPPORTED, GSB_ERR_STATE, GSB_ERR_CAPACITY = -1, -2, -3, -4, -5
 GSB_FLAG_SORT_CUB = 1
 GSB_FLAG_NO_OVERLAP = 2
+GSB_FLAG_ASYNC_LOSS = 4
 STAGE_COUNT = 12
 
 
@@ -78,7 +79,7 @@ SIGNATURES = {
     "gsb_trainer_init": (C.c_int, [_P, _I] + [_P] * 6),
     "gsb_trainer_param_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "gsb_trainer_grad_block": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
-    "gsb_trainer_accumulate": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), _I, _I, _F, C.POINTER(_F)]),
+    "gsb_trainer_accumulate": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), _I, _I, _F, _P]),
     "gsb_trainer_apply": (C.c_int, [_P, _I, _I, _I]),
     "gsb_train_step": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), _I, _I, _I, C.POINTER(_F)]),
     "gsb_densify_classify": (C.c_int, [_P, _I, _P, _F, _P, _P, _F, _F, _F, _I, _P, _P]),

@@ -298,13 +298,21 @@ class Context:
         return B, cam_arr, tp, int(on_host)
 
     def trainer_accumulate(self, cams, targets, zero_grads: bool = True, grad_scale: Optional[float] = None,
-                           want_loss: bool = True) -> Optional[float]:
+                           want_loss: bool = True, loss_out: Optional[torch.Tensor] = None) -> Optional[float]:
+        """``loss_out``: a pinned 1-element f32 CPU tensor; with GSB_FLAG_ASYNC_LOSS set the mean loss is copied into it
+        asynchronously (no synchronisation; read it after an event/stream sync) and the return value is None."""
         self._sync_stream()
         B, cam_arr, tp, on_host = self._cams_targets(cams, targets)
-        loss = C.c_float(0.0)
         scale = (1.0 / B) if grad_scale is None else grad_scale
+        if loss_out is not None:
+            assert self.cfg.flags & _lib.GSB_FLAG_ASYNC_LOSS and loss_out.is_pinned() and loss_out.dtype == torch.float32
+            self._check(self.lib.gsb_trainer_accumulate(self.h, B, cam_arr, tp, on_host, int(zero_grads), C.c_float(scale),
+                                                        C.c_void_p(loss_out.data_ptr())))
+            return None
+        assert not (want_loss and self.cfg.flags & _lib.GSB_FLAG_ASYNC_LOSS), "async-loss contexts need loss_out"
+        loss = C.c_float(0.0)
         self._check(self.lib.gsb_trainer_accumulate(self.h, B, cam_arr, tp, on_host, int(zero_grads), C.c_float(scale),
-                                                    C.byref(loss) if want_loss else None))
+                                                    C.cast(C.pointer(loss), C.c_void_p) if want_loss else None))
         return float(loss.value) if want_loss else None
 
     def trainer_apply(self, iteration: int, total_iterations: int, reset_state: bool = False):

@@ -1200,10 +1200,12 @@ int gsb_trainer_init(gsb_ctx* ctx, int32_t N, const float* host_xyz, const float
     if (rc != GSB_OK) return rc;
     gsb::sync_all_streams(c);
     c->tN = 0;
-    for (int i = 0; i < 2; ++i) { gsb::dev_free(c->t_slab[i]); gsb::dev_free(c->t_accum_slab[i]); }
     c->t_block = nullptr; c->t_accum = nullptr;
-    c->t_cap = N;
-    GSB_CUDA_CHECK(c, trainer_alloc_slab(c, 0, c->t_cap));
+    if (!c->t_slab[0] || N > c->t_cap) {   // re-initialisation within the capacity keeps the slabs (and their addresses)
+        for (int i = 0; i < 2; ++i) { gsb::dev_free(c->t_slab[i]); gsb::dev_free(c->t_accum_slab[i]); }
+        c->t_cap = N;
+        GSB_CUDA_CHECK(c, trainer_alloc_slab(c, 0, c->t_cap));
+    }
     const TrainerLayout L = trainer_layout(N, K);
     trainer_adopt(c, N, L, 0);
     GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block, 0, c->t_floats * 4 * sizeof(float), c->stream));
@@ -1331,9 +1333,13 @@ int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
     if (overlap && B > 0)   // the gradients are complete when the last projection backward has run (tail stream is in order)
         GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_pb[(B - 1) & 1], 0));
     if (host_loss) {
-        GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->h_loss, c->loss_accum, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-        *host_loss = c->h_loss[0];
+        if (c->cfg.flags & GSB_FLAG_ASYNC_LOSS) {   // pinned destination, the caller synchronises when it wants the value
+            GSB_CUDA_CHECK(c, cudaMemcpyAsync(host_loss, c->loss_accum, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->h_loss, c->loss_accum, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+            *host_loss = c->h_loss[0];
+        }
     }
     return GSB_OK;
 }

@@ -61,6 +61,8 @@ typedef struct gsb_config {
 
 #define GSB_FLAG_SORT_CUB 1       /* use the CUB baseline instead of the hand-written onesweep (checking only) */
 #define GSB_FLAG_NO_OVERLAP 2     /* trainer: run every view's kernels back to back on one stream (per-kernel timing) */
+#define GSB_FLAG_ASYNC_LOSS 4     /* gsb_trainer_accumulate / gsb_train_step: host_loss is PINNED host memory; the loss is copied
+                                   * into it asynchronously on the work stream and the call does not synchronise */
 
 /* Camera block = the 7 camera arrays of TrainStepInputIndex (GaussianTrainer.swift:254-272),
  * produced exactly as Trainer/CameraUtil.swift:5-102 does (row-vector convention, proj = P^T). */
@@ -198,7 +200,7 @@ GSB_API int gsb_trainer_param_ptrs(gsb_ctx*, float** host_params6, float** host_
  * collective between gsb_trainer_accumulate and gsb_trainer_apply. */
 GSB_API int gsb_trainer_grad_block(gsb_ctx*, float** grad_block, int64_t* floats);
 /* Forward+loss+backward for B views into the context's gradient buffers (no optimiser step).
- * host_loss (may be NULL) receives the mean loss and makes the call synchronise. */
+ * host_loss (may be NULL) receives the mean loss and makes the call synchronise (unless GSB_FLAG_ASYNC_LOSS). */
 GSB_API int gsb_trainer_accumulate(gsb_ctx*, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
                            int32_t targets_on_host, int32_t zero_grads, float grad_scale, float* host_loss);
 /* Adam + D1 on the context's buffers; learning rates from (iteration, total_iterations)
