@@ -337,6 +337,38 @@ def test_view_pipeline_matches_serial_and_regrows(gsb):
     assert rel_err(aa, ab) < 1e-4
 
 
+@pytest.mark.parametrize("W,H,tw,th", [(128, 96, 32, 24), (100, 70, 25, 18), (64, 64, 8, 8)])
+def test_app_default_tile_sizes(gsb, best_oracle, W, H, tw, th):
+    """The reference app renders with TILE_SIZE = W/4 x H/4 (UI/TrainView.swift:158-163), not 16 x 16: tile lists,
+    forward and backward must match the oracle for tiles larger (covered by several 16 x 16 blocks) and smaller
+    than the raster block."""
+    Context, L = gsb
+    o = best_oracle
+    n, degree = 900, 3
+    params = make_gaussians(n, 71, degree)
+    cam = make_cameras(W, H, 3)[2]
+    target = make_targets(W, H, 1, 71)[0]
+    fr, lo, bw = pl.loss_and_grads(o, params, cam, target, degree, 0.2, tw, th)
+    ctx = Context(W, H, tile_w=tw, tile_h=th, sh_degree=degree)
+    gcam = L.make_camera(cam)
+    # tile lists on the oracle's projection: bit-exact
+    bins_o = fr["bins"]
+    bins_g = ctx.bin({k: dev(v) for k, v in fr["proj"].items()})
+    assert bins_g["M"] == bins_o["M"]
+    for k in ("tilesTouched", "sortedKeysHigh", "sortedKeysLow", "sortedGaussIdx", "tileCounts"):
+        assert np.array_equal(u32(bins_g[k]), bins_o[k]), k
+    # fused path
+    render, depth, alpha, vis, radii = ctx.render_forward({k: dev(v) for k, v in params.items()}, gcam)
+    assert np.abs(render.cpu().numpy() - fr["render"]).max() <= PIX_TOL
+    assert np.abs(alpha.cpu().numpy() - fr["alpha"]).max() <= PIX_TOL
+    loss, cot = ctx.loss_fwd_bwd(render, dev(target), 1.0)
+    assert abs(float(loss.item()) - lo["loss"]) < 2e-5
+    grads = ctx.render_backward(cot)
+    for k, g in grads.items():
+        assert rel_err(g.cpu().numpy().reshape(bw["grads"][k].shape), bw["grads"][k]) < GRAD_TOL, k
+    ctx.close()
+
+
 def test_empty_and_culled_scenes(gsb):
     Context, L = gsb
     cam = make_cameras(32, 32, 1)[0]
