@@ -8,19 +8,19 @@
 // (Gaussian index ascending).  It is produced here WITHOUT ever sorting 64-bit keys over the M pairs:
 //
 //   1. sort the N Gaussians by asuint(depth) (stable, 32-bit keys, payload = Gaussian index);
-//   2. exclusive scan of tiles-touched in that order (single pass, decoupled look-back);
-//   3. emit the (tile id, Gaussian) pairs in that order — the pair list is then already sorted by
-//      (depth, index) — with one thread per OUTPUT pair (binary search in shared memory), so the
-//      writes are fully coalesced;
-//   4. one STABLE radix sort of the M pairs on the tile id alone: ceil(tileBits/8) = 2 onesweep
-//      passes over 8-byte pairs instead of 6 passes over 12-byte pairs;
-//   5. tile ranges from the sorted tile ids + gather of the 48-byte records into tile/depth order.
+//   2. exclusive scan, in that order, of the SUPERBLOCKS (4 x 2 tiles) each rect touches (single pass, decoupled
+//      look-back);
+//   3. emit the (superblock id, Gaussian) pairs in that order — the pair list is then already sorted by
+//      (depth, index) — with one thread per OUTPUT pair (binary search in shared memory), fully coalesced;
+//   4. one STABLE radix sort of those ~3.4 M pairs on the superblock id alone (10 bits at 1080p: 2 onesweep passes
+//      over 8-byte pairs; the reference sorts 12 M twelve-byte triples in 12 passes);
+//   5. tilelists.cu turns every superblock's depth-ordered slice into its 8 tile lists (ballot-ranked count / fill).
 //
-// Nothing synchronises with the host: every kernel reads the pair count M from device memory and is
-// launched for the buffer capacity.  All of this is HBM-bound integer work; the figure of merit is
-// bytes moved per pair.  The hand-written onesweep (8-bit digits, chained-scan look-back, stable) is
-// also exposed stand-alone on 64-bit keys (gsb_sort_tile_keys = the reference's K5), with
-// cub::DeviceRadixSort as the checked baseline.
+// Nothing synchronises with the host: every kernel reads its element count from device memory and is launched for
+// the buffer capacity.  All of this is HBM/latency-bound integer work; the figure of merit is bytes moved per pair.
+// The hand-written onesweep (8-bit digits, chained-scan look-back with relaxed status words, stable) is also exposed
+// stand-alone on 64-bit keys (gsb_sort_tile_keys = the reference's K5), with cub::DeviceRadixSort as the checked
+// baseline.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>

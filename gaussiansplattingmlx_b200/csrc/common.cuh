@@ -164,13 +164,19 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v)
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // packed-order fields -> raster record quads
+// Bit 31 of the index word = "alpha may reach the 0.99 clamp (or the conic is not negative definite in log2 form)":
+// when it is clear, exponent <= 0 everywhere and opacity <= 0.98, so min(0.99, .) is the identity and the backward
+// takes a path without the clamp logic.  Gaussian indices stay below 2^31.
+constexpr uint32_t REC_MAYCLAMP = 0x80000000u;
 __device__ __forceinline__ void make_raster_record(float mx, float my, float c00, float c01, float c10, float c11, float r,
                                                    float g, float b, float opacity, float depth, uint32_t idx, float4* out)
 {
     const float s = -0.5f * LOG2E_F;
-    out[0] = make_float4(mx, my, s * c00, s * (c01 + c10));
-    out[1] = make_float4(s * c11, log2f(opacity), r, g);
-    out[2] = make_float4(b, opacity, depth, __uint_as_float(idx));
+    const float A = s * c00, B = s * (c01 + c10), C = s * c11;
+    const bool safe = opacity <= 0.98f && A <= 0.0f && C <= 0.0f && B * B <= 4.0f * A * C;   // false for NaNs
+    out[0] = make_float4(mx, my, A, B);
+    out[1] = make_float4(C, log2f(opacity), r, g);
+    out[2] = make_float4(b, opacity, depth, __uint_as_float(idx | (safe ? 0u : REC_MAYCLAMP)));
 }
 __device__ __forceinline__ float ex2_approx(float x)
 {

@@ -3,21 +3,22 @@
 // Reference: slang/gaussian_tile_global_kernels.slang:437-614 (forward), :501-521 + :648-881
 // (backward), call sites Trainer/GaussianRenderer.swift:124-147,187-226.
 //
-// Both kernels are FP32-issue bound (ncu: issue slots ~90 % busy), so the design goal is the fewest
+// Both kernels are FP32-issue bound (ncu: issue slots ~82 % busy), so the design goal is the fewest
 // instructions per (pixel, Gaussian) evaluation:
-//   * the tile's depth-ordered 48-byte records are contiguous in the `staged` stream (binning.cu);
-//     batches are pulled into shared memory by TMA 1-D bulk copies (cp.async.bulk -> SASS UBLKCP)
-//     signalled through mbarriers, double-buffered against the blend loop;
+//   * a tile's list is (tile_ranges, Gaussian indices in depth order) from tilelists.cu; the 48-byte records are
+//     gathered from the L2-resident record table straight into shared memory by 16-byte async copies (LDGSTS; the
+//     backward also has per-record TMA bulk copies, GSB_GATHER_TMA=1) completing on mbarriers, double-buffered;
 //   * records carry the conic/opacity pre-folded into log2 units (common.cuh), so
-//     alpha = min(0.99, ex2(A dx^2 + B dx dy + C dy^2 + lo)): 5 FMA-pipe ops + 1 MUFU;
-//   * forward: one pixel per thread, 256 threads = one 16x16 block; a terminated pixel keeps running
-//     with T = 0 (adds exact zeros) so the loop body has no per-lane predicate, and the warp votes
-//     only every 4 Gaussians;
-//   * backward: ONE WARP per 16x16 block, 8 pixels per thread.  The 11 per-Gaussian gradient sums are
-//     first accumulated over the thread's 8 pixels in registers (the accumulation is the FMA that
-//     produces the term), so the 13-shuffle warp butterfly is paid once per 256 evaluations instead
-//     of once per 32, and there is no cross-warp reduction at all.  One vector red per (block,
-//     Gaussian, quad) then goes to L2.
+//     alpha = min(0.99, ex2(A dx^2 + B dx dy + C dy^2 + lo));
+//   * a thread owns a COLUMN of pixels (forward 4, backward 8): the record is read once per column and the exponent
+//     is a quadratic in the compile-time row offset, 2 FFMA per pixel;
+//   * forward: 64 threads per 16x16 block; a terminated pixel keeps running with T = 0 (adds exact zeros), the
+//     termination bookkeeping is a per-pixel replay in the epilogue: 15 instructions per evaluation;
+//   * backward: ONE WARP per 16x16 block.  The per-Gaussian gradient sums are first accumulated over the thread's 8
+//     pixels in registers (geometry as three moments of h), parked in shared memory and summed across lanes by
+//     column reads every 3 Gaussians; one vector red per (block, Gaussian, quad) then goes to L2.  Records flagged
+//     "cannot reach the alpha clamp" take a path without the clamp logic;
+//   * both kernels are persistent: CTAs pull blocks heavy-first from a device counter.
 // Work per evaluation: forward 27 flop + 1 ex2; backward ~80 flop + 1 ex2 + 1 rcp.
 #include <stdlib.h>
 
@@ -292,41 +293,6 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-// Sums 12 per-lane values across the warp with a halving butterfly (13 shuffles instead of 60):
-// afterwards lane L holds the warp total of component comp(L) = 6*b4 + 3*b3 + (b2 ? 2 : b1)
-// (invalid when b2 && b1); lanes differing only in bit 0 hold duplicates.
-__device__ __forceinline__ float warp_reduce12(float (&v)[12], int lane)
-{
-    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const float send = u16 ? v[k] : v[k + 6];
-        const float keep = u16 ? v[k + 6] : v[k];
-        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float send = u8 ? v[k] : v[k + 3];
-        const float keep = u8 ? v[k + 3] : v[k];
-        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    {
-        const float send0 = u4 ? v[0] : v[2];
-        const float keep0 = u4 ? v[2] : v[0];
-        const float send1 = u4 ? v[1] : 0.0f;
-        const float keep1 = u4 ? 0.0f : v[1];
-        v[0] = keep0 + __shfl_xor_sync(0xffffffffu, send0, 4);
-        v[1] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 4);
-    }
-    {
-        const float send = u2 ? v[0] : v[1];
-        const float keep = u2 ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-    return v[0];
-}
-
 template <bool DEPTH>
 __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ ViewParams vp,
                                                        const uint32_t* __restrict__ tile_ranges,
@@ -450,9 +416,6 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
 
     const float pxf = (float)pxi, pyf = (float)py0;
     const uint32_t rec_base = smem_u32(&s_rec[0][0]);
-    const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
-    const int comp = 6 * b4 + 3 * b3 + (b2 ? 2 : b1);
-    const bool writer = !(lane & 1) && !(b2 && b1);
 
     for (int b = nb - 1; b >= 0; --b) {
         const uint32_t s = seq + (uint32_t)(nb - 1 - b);
@@ -480,45 +443,56 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
             // per-thread partial sums over the 8 pixels: colour/depth terms and the moments of
             // h = dL/d(opacity-free alpha) in the row offset: H0 = sum h, H1 = sum p h, H2 = sum p^2 h
             float Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f, H0 = 0.f, H1 = 0.f, H2 = 0.f;
-            // one pixel of this thread.  MASKED = false when every pixel of the block is known to be active.
-            // Neither variant branches, so the compiler interleaves the 8 dependent chains; in the masked
-            // variant an inactive pixel (i >= nContrib) computes and discards (selects keep its state).
-            auto pixel = [&](int p, bool masked) {
-                const bool act = !masked || (i < nC[p]);
+            // one pixel of this thread.  masked = false when every pixel of the block is known to be active; clamp =
+            // false when the record says alpha cannot reach 0.99 (REC_MAYCLAMP clear).  No variant branches, so the
+            // compiler interleaves the 8 dependent chains.  An inactive pixel (i >= nContrib) of the masked variant
+            // sees ex = 0: alpha = 0, contrib = 0, kT unchanged, h = 0 — only its transmittance needs a select.
+            auto pixel = [&](int p, bool masked, bool clamp) {
                 const float pf = (float)p;
-                const float ex = ex2_approx(fmaf(pf, fmaf(pf, q.x, E1), E0));    // :437-483
+                float ex = ex2_approx(fmaf(pf, fmaf(pf, q.x, E1), E0));    // :437-483
+                const bool act = !masked || (i < nC[p]);
+                if (masked) ex = act ? ex : 0.0f;
                 const float raw = ex * c.y;
-                const bool keep = act && !(raw > 0.99f);   // the alpha clamp branch has zero gradient
-                const float alpha = fminf(raw, 0.99f);
+                const float alpha = clamp ? fminf(raw, 0.99f) : raw;
                 // undoTileGlobalPixelState (:501-521): only the transmittance matters for the gradients;
                 // max(1 - alpha, 1e-6) == 1 - alpha because alpha <= 0.99
                 const float prevT = sT[p] * rcp_approx(1.0f - alpha);
-                const float contrib = act ? prevT * alpha : 0.0f;
+                const float contrib = prevT * alpha;
                 sT[p] = act ? prevT : sT[p];
                 // VJP of updateTileGlobalPixelState (:485-499)
                 float dotc = fmaf(kZ[p], c.x, fmaf(kY[p], q.w, kX[p] * q.z));
                 if (DEPTH) dotc = fmaf(kD[p], c.z, dotc);
                 const float d = dotc - kT[p];
                 const float g_alpha = prevT * d;
-                kT[p] = act ? fmaf(alpha, d, kT[p]) : kT[p];
+                kT[p] = fmaf(alpha, d, kT[p]);
                 Cr = fmaf(contrib, kX[p], Cr);
                 Cg = fmaf(contrib, kY[p], Cg);
                 Cb = fmaf(contrib, kZ[p], Cb);
                 if (DEPTH) Cd = fmaf(contrib, kD[p], Cd);
-                // VJP of evaluateTileGlobalSample: everything geometric is a moment of h
-                const float h = keep ? g_alpha * ex : 0.0f;
+                // VJP of evaluateTileGlobalSample: everything geometric is a moment of h; the alpha clamp branch has
+                // zero gradient
+                float h = g_alpha * ex;
+                if (clamp) h = raw > 0.99f ? 0.0f : h;
                 H0 += h;
                 if (p > 0) {
                     H1 = fmaf(h, pf, H1);
                     H2 = fmaf(h, pf * pf, H2);
                 }
             };
-            if (__all_sync(0xffffffffu, i < nmin)) {
+            const bool mayclamp = (__float_as_uint(c.w) & REC_MAYCLAMP) != 0u;   // warp-uniform
+            const bool all_active = __all_sync(0xffffffffu, i < nmin);
+            if (all_active && !mayclamp) {
 #pragma unroll
-                for (int p = 0; p < BPPT; ++p) pixel(p, false);
+                for (int p = 0; p < BPPT; ++p) pixel(p, false, false);
+            } else if (all_active) {
+#pragma unroll
+                for (int p = 0; p < BPPT; ++p) pixel(p, false, true);
+            } else if (!mayclamp) {
+#pragma unroll
+                for (int p = 0; p < BPPT; ++p) pixel(p, true, false);
             } else {
 #pragma unroll
-                for (int p = 0; p < BPPT; ++p) pixel(p, true);
+                for (int p = 0; p < BPPT; ++p) pixel(p, true, true);
             }
             // moments in (dx, dy) of this thread's pixels: sum h dy = dyb H0 + H1, sum h dy^2 = dyb^2 H0 + 2 dyb H1 + H2
             const float Sy = fmaf(dyb, H0, H1);
@@ -560,7 +534,7 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
             const float g_mx = km * fmaf(a.z + a.z, s1.y, a.w * s1.z);
             const float g_my = km * fmaf(q.x + q.x, s1.z, a.w * s1.y);
             const float g_c00 = kc * s1.w, g_c01 = kc * s2.x, g_c11 = kc * s2.y;
-            float* dst = grad_rec + (size_t)__float_as_uint(c.w) * REC_FLOATS;
+            float* dst = grad_rec + (size_t)(__float_as_uint(c.w) & ~REC_MAYCLAMP) * REC_FLOATS;
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g_mx), "f"(g_my), "f"(g_c00), "f"(g_c01) : "memory");
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(g_c01), "f"(g_c11), "f"(s0.x), "f"(s0.y) : "memory");
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8), "f"(s0.z), "f"(s1.x), "f"(s0.w), "f"(0.0f) : "memory");
