@@ -531,3 +531,24 @@ def test_c4_densification_stress_6m_4k(gsb):
     l2 = ctx.train_step(gc, tg, 2, 30000)
     assert np.isfinite(l2) and ctx.trainer_count() == (info["n"], 1)
     ctx.close()
+
+
+def test_async_loss_flag_matches_synchronous_loss(gsb):
+    """GSB_FLAG_ASYNC_LOSS: the loss lands in the caller's pinned slot without a synchronisation inside the call."""
+    Context, L = gsb
+    n, W, H = 800, 64, 48
+    params = make_gaussians(n, 81, 3)
+    cams = [L.make_camera(c) for c in make_cameras(W, H, 2)]
+    tg = [torch.from_numpy(t).cuda() for t in make_targets(W, H, 2, 81)]
+    ref = Context(W, H)
+    ref.trainer_init({k: torch.from_numpy(v) for k, v in params.items()})
+    want = [ref.train_step(cams, tg, it, 100) for it in range(2)]
+    ctx = Context(W, H, flags=L.GSB_FLAG_ASYNC_LOSS)
+    ctx.trainer_init({k: torch.from_numpy(v) for k, v in params.items()})
+    slots = [torch.full((1,), -1.0).pin_memory() for _ in range(2)]
+    for it in range(2):
+        ctx.trainer_accumulate(cams, tg, loss_out=slots[it])
+        ctx.trainer_apply(it, 100)
+    torch.cuda.synchronize()
+    for it in range(2):
+        assert abs(float(slots[it][0]) - want[it]) < 1e-6
