@@ -375,8 +375,7 @@ def run_gsb(args, rank, local_rank, world):
     # per-stage averages on rank 0 (CUDA-event pairs recorded on the work stream during timed region 1)
     nv = max(len(my_views), 1)
     P = wl.width * wl.height
-    num_sb = -(-ctx.grid_w // 4) * -(-ctx.grid_h // 2)        # superblocks of 4 x 2 tiles (tilelists.cu)
-    passes = -(-max(1, (num_sb - 1).bit_length()) // 8)
+    passes = ctx.tile_list_info()["sort_passes"]               # onesweep passes over the (superblock id, Gaussian) pairs
     L1 = l1_pairs / max(len(my_views), 1)
     M = pairs / nv
     E = evals / nv

@@ -8,6 +8,7 @@ loudly.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
@@ -88,6 +89,7 @@ SIGNATURES = {
     "gsb_trainer_densify": (C.c_int, [_P, _F, _F, _F, _I, C.c_uint64, _P, C.POINTER(_I)]),
     "gsb_trainer_count": (C.c_int, [_P, C.POINTER(_I), C.POINTER(_I)]),
     "gsb_last_contrib_sum": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "gsb_tile_list_info": (C.c_int, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "gsb_stats_reset": (C.c_int, [_P]),
     "gsb_stats_get": (C.c_int, [_P, C.POINTER(GsbStats)]),
     "gsb_enable_stage_timing": (C.c_int, [_P, _I]),
@@ -101,10 +103,11 @@ def load() -> C.CDLL:
     """Load ``libgsb.so`` (built in-tree by ``gaussiansplattingmlx_b200.build``).  No fallback."""
     global _lib
     if _lib is None:
-        if not LIB_PATH.exists():
+        lib_path = Path(os.environ.get("GSB_LIB", str(LIB_PATH)))   # GSB_LIB: tuning builds (tools/)
+        if not lib_path.exists():
             raise FileNotFoundError(
-                f"{LIB_PATH} is missing: run `python -m gaussiansplattingmlx_b200.build` (there is no CPU fallback)")
-        lib = C.CDLL(str(LIB_PATH))
+                f"{lib_path} is missing: run `python -m gaussiansplattingmlx_b200.build` (there is no CPU fallback)")
+        lib = C.CDLL(str(lib_path))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = res

@@ -390,6 +390,11 @@ class Context:
                 "stage_ms": {n: float(st.stage_ms[i]) for i, n in enumerate(names)},
                 "stage_calls": {n: int(st.stage_calls[i]) for i, n in enumerate(names)}}
 
+    def tile_list_info(self) -> Dict[str, int]:
+        a, b, n, p = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self.lib.gsb_tile_list_info(self.h, C.byref(a), C.byref(b), C.byref(n), C.byref(p)))
+        return {"sb_w": a.value, "sb_h": b.value, "num_superblocks": n.value, "sort_passes": p.value}
+
     def last_contrib_sum(self) -> int:
         v = C.c_uint64(0)
         self._check(self.lib.gsb_last_contrib_sum(self.h, C.byref(v)))

@@ -417,8 +417,7 @@ static int enqueue_binning(Ctx* c, Ctx::ViewBufs& v, cudaStream_t st, int N, con
     {
         StageTimer t(c, GSB_STAGE_TILE_LISTS, st);
         // 5. superblock slices -> per-tile counts -> CSR ranges + heavy-first order -> the tile lists (tilelists.cu)
-        GSB_CUDA_CHECK(c, launch_ranges_gather(st, vp, v.keys[0], v.keys[1], v.vals[0], v.vals[1], v.d_result_buf, &v.d_ctl[4],
-                                               c->capL1, nullptr, v.sb_ranges, nullptr, c->numSB));
+        GSB_CUDA_CHECK(c, launch_key_ranges(st, v.keys[0], v.keys[1], v.d_result_buf, &v.d_ctl[4], c->capL1, v.sb_ranges, c->numSB));
         GSB_CUDA_CHECK(c, launch_l2_count(st, c->numSB, c->sbGridW, c->gridW, c->gridH, v.sb_ranges, v.vals[0], v.vals[1], v.d_result_buf,
                                           v.tile_rects, v.slice_counts, v.tile_counts));
         GSB_CUDA_CHECK(c, launch_exclusive_scan(st, c->numTiles, v.tile_counts, nullptr, nullptr, nullptr, v.tile_starts, &v.d_ctl[5],
@@ -650,8 +649,8 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
         CREATE_CHECK(dev_alloc(&v.tile_counts, (size_t)c->numTiles));
         CREATE_CHECK(cudaMalloc(&v.tile_scan_ws, scan_ws_bytes(c->numTiles)));
         CREATE_CHECK(dev_alloc(&v.sb_ranges, (size_t)c->numSB * 2));
-        CREATE_CHECK(dev_alloc(&v.slice_counts, (size_t)c->numSB * 64));
-        CREATE_CHECK(dev_alloc(&v.slice_base, (size_t)c->numSB * 64));
+        CREATE_CHECK(dev_alloc(&v.slice_counts, (size_t)c->numSB * gsb::L2_WARPS * gsb::SB_TILES));
+        CREATE_CHECK(dev_alloc(&v.slice_base, (size_t)c->numSB * gsb::L2_WARPS * gsb::SB_TILES));
         CREATE_CHECK(dev_alloc(&v.d_ctl, 8));
         CREATE_CHECK(dev_alloc(&v.d_nvalue, 4));
         CREATE_CHECK(cudaMallocHost(reinterpret_cast<void**>(&v.h_ctl), 8 * sizeof(uint32_t)));
@@ -1533,6 +1532,16 @@ int gsb_last_contrib_sum(gsb_ctx* ctx, uint64_t* host_out)
     GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     *host_out = h;
     c->stats.kernel_launches += 1;
+    return GSB_OK;
+}
+
+int gsb_tile_list_info(gsb_ctx* ctx, int32_t* sb_w, int32_t* sb_h, int32_t* num_superblocks, int32_t* sort_passes)
+{
+    CTX_PROLOGUE(ctx);
+    if (sb_w) *sb_w = gsb::SBW;
+    if (sb_h) *sb_h = gsb::SBH;
+    if (num_superblocks) *num_superblocks = c->numSB;
+    if (sort_passes) *sort_passes = (c->sbBits + 7) / 8;
     return GSB_OK;
 }
 

@@ -622,55 +622,38 @@ cudaError_t launch_iota(cudaStream_t st, uint32_t n, uint32_t* v)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K6/K7 (slang/gaussian_tile_global_kernels.slang:314-367) + gather of records into tile/depth order.
-// Three threads per pair: each moves one 16-byte third of the 48-byte record (coalesced stores);
-// the first of the three also does the tile-boundary detection.
+// K6 compute_tile_ranges (slang/gaussian_tile_global_kernels.slang:314-344) on a sorted key list: boundary
+// detection -> ranges[key] = (first, last + 1).  Used on the sorted superblock ids of the level-1 list.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ranges_gather(const uint32_t* __restrict__ keys0, const uint32_t* __restrict__ keys1,
-                                                       const uint32_t* __restrict__ vals0, const uint32_t* __restrict__ vals1,
-                                                       const uint32_t* __restrict__ d_result_buf,
-                                                       const uint32_t* __restrict__ d_count, uint32_t capacity,
-                                                       const float4* __restrict__ rec, uint32_t* __restrict__ tile_ranges,
-                                                       float4* __restrict__ staged)
+__global__ void __launch_bounds__(256) k_key_ranges(const uint32_t* __restrict__ keys0, const uint32_t* __restrict__ keys1,
+                                                    const uint32_t* __restrict__ d_result_buf, const uint32_t* __restrict__ d_count,
+                                                    uint32_t capacity, uint32_t* __restrict__ ranges)
 {
     const uint32_t M = min(*d_count, capacity);
-    const uint32_t buf = d_result_buf ? *d_result_buf : 0u;
-    const uint32_t* keys = buf ? keys1 : keys0;
-    const uint32_t* vals = buf ? vals1 : vals0;
-    const uint32_t per = rec ? 3u : 1u;   // threads per pair (3 x 16 bytes when the records are gathered too)
-    const uint64_t total = (uint64_t)M * per;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t j = (uint32_t)(g / per), part = (uint32_t)(g - (uint64_t)j * per);
-        if (rec) staged[(size_t)j * 3 + part] = rec[(size_t)vals[j] * 3 + part];
-        if (part == 0) {
-            uint32_t cur = keys[j];
-            if (j == 0) {
-                tile_ranges[cur * 2 + 0] = 0;
-            } else {
-                uint32_t prev = keys[j - 1];
-                if (cur != prev) {
-                    tile_ranges[prev * 2 + 1] = j;
-                    tile_ranges[cur * 2 + 0] = j;
-                }
+    const uint32_t* keys = (d_result_buf && *d_result_buf) ? keys1 : keys0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+        const uint32_t cur = keys[j];
+        if (j == 0) {
+            ranges[cur * 2 + 0] = 0;
+        } else {
+            const uint32_t prev = keys[j - 1];
+            if (cur != prev) {
+                ranges[prev * 2 + 1] = j;
+                ranges[cur * 2 + 0] = j;
             }
-            if (j == M - 1) tile_ranges[cur * 2 + 1] = M;
         }
+        if (j == M - 1) ranges[cur * 2 + 1] = M;
     }
 }
 
-cudaError_t launch_ranges_gather(cudaStream_t st, const ViewParams& vp, const uint32_t* keys0, const uint32_t* keys1,
-                                 const uint32_t* vals0, const uint32_t* vals1, const uint32_t* d_result_buf,
-                                 const uint32_t* d_count, uint32_t capacity, const float* rec, uint32_t* tile_ranges,
-                                 float* staged, int numTiles)
+cudaError_t launch_key_ranges(cudaStream_t st, const uint32_t* keys0, const uint32_t* keys1, const uint32_t* d_result_buf,
+                              const uint32_t* d_count, uint32_t capacity, uint32_t* ranges, int numKeys)
 {
-    (void)vp;
-    cudaError_t e = cudaMemsetAsync(tile_ranges, 0, (size_t)numTiles * 2 * sizeof(uint32_t), st);
+    cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)numKeys * 2 * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     if (capacity == 0) return cudaSuccess;
-    int blocks = (int)std::min<uint64_t>(((uint64_t)capacity * 3 + 255) / 256, 148ull * 16ull);
-    k_ranges_gather<<<blocks, 256, 0, st>>>(keys0, keys1, vals0, vals1, d_result_buf, d_count, capacity,
-                                            reinterpret_cast<const float4*>(rec), tile_ranges,
-                                            reinterpret_cast<float4*>(staged));
+    const int blocks = (int)std::min<uint64_t>(((uint64_t)capacity + 255) / 256, 148ull * 16ull);
+    k_key_ranges<<<blocks, 256, 0, st>>>(keys0, keys1, d_result_buf, d_count, capacity, ranges);
     return cudaGetLastError();
 }
 
@@ -788,16 +771,6 @@ __global__ void k_merge_keys(uint32_t M, const uint32_t* __restrict__ hi, const 
     if (i >= M) return;
     keys[i] = ((uint64_t)(hi[i] & hi_mask) << 32) | lo[i];
 }
-// sorted (tile id, Gaussian) lists -> the reference's sortedKeysHigh / sortedKeysLow (= asuint(depth of the Gaussian))
-__global__ void k_sorted_keys_out(uint32_t M, const uint32_t* __restrict__ tile_keys, const uint32_t* __restrict__ vals,
-                                  const float* __restrict__ depth_ptr, int depth_stride, uint32_t* __restrict__ hi,
-                                  uint32_t* __restrict__ lo)
-{
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M) return;
-    if (hi) hi[i] = tile_keys[i];
-    if (lo) lo[i] = __float_as_uint(depth_ptr[(size_t)vals[i] * depth_stride]);
-}
 cudaError_t launch_split_keys(cudaStream_t st, uint32_t M, const uint64_t* keys, uint32_t* hi, uint32_t* lo)
 {
     if (M > 0) k_split_keys<<<cdiv(M, 256), 256, 0, st>>>(M, keys, hi, lo);
@@ -809,11 +782,4 @@ cudaError_t launch_merge_keys(cudaStream_t st, uint32_t M, const uint32_t* hi, c
     if (M > 0) k_merge_keys<<<cdiv(M, 256), 256, 0, st>>>(M, hi, lo, hi_mask, keys);
     return cudaGetLastError();
 }
-cudaError_t launch_sorted_keys_out(cudaStream_t st, uint32_t M, const uint32_t* tile_keys, const uint32_t* vals,
-                                   const float* depth_ptr, int depth_stride, uint32_t* hi, uint32_t* lo)
-{
-    if (M > 0) k_sorted_keys_out<<<cdiv(M, 256), 256, 0, st>>>(M, tile_keys, vals, depth_ptr, depth_stride, hi, lo);
-    return cudaGetLastError();
-}
-
 }  // namespace gsb

@@ -4,7 +4,18 @@
 
 namespace gsb {
 
-constexpr int SBW = 4, SBH = 2;   // superblock = SBW x SBH tiles (tilelists.cu)
+// superblock = SBW x SBH tiles, walked by L2_WARPS warps (tilelists.cu); SBW * SBH <= 32 (one ballot mask)
+#ifndef GSB_SBW
+#define GSB_SBW 4
+#endif
+#ifndef GSB_SBH
+#define GSB_SBH 2
+#endif
+#ifndef GSB_L2_WARPS
+#define GSB_L2_WARPS 8
+#endif
+constexpr int SBW = GSB_SBW, SBH = GSB_SBH, L2_WARPS = GSB_L2_WARPS, SB_TILES = SBW * SBH;
+static_assert(SB_TILES <= 32 && L2_WARPS * 32 <= 1024, "superblock geometry");
 
 // ---- project.cu --------------------------------------------------------------------------------
 cudaError_t launch_activate_fwd(cudaStream_t st, int N, int K, const float* f_dc, const float* f_rest,
@@ -80,12 +91,9 @@ cudaError_t cub_sort_pairs32(cudaStream_t st, uint32_t* keys0, uint32_t* keys1, 
                              uint32_t count, uint32_t end_bit, void* tmp, size_t tmp_bytes, size_t* tmp_needed);
 cudaError_t launch_iota(cudaStream_t st, uint32_t n, uint32_t* v);
 
-// K6/K7 + record gather: tile ranges/counts from the sorted tile ids, and the depth-ordered contiguous
-// record stream staged[j] = rec[sorted_val[j]] that the rasteriser bulk-copies (rec == NULL: ranges only).
-cudaError_t launch_ranges_gather(cudaStream_t st, const ViewParams& vp, const uint32_t* keys0, const uint32_t* keys1,
-                                 const uint32_t* vals0, const uint32_t* vals1, const uint32_t* d_result_buf,
-                                 const uint32_t* d_count, uint32_t capacity, const float* rec, uint32_t* tile_ranges,
-                                 float* staged, int numTiles);
+// K6 on a sorted key list: ranges[key] = (first, last + 1), (0, 0) for absent keys
+cudaError_t launch_key_ranges(cudaStream_t st, const uint32_t* keys0, const uint32_t* keys1, const uint32_t* d_result_buf,
+                              const uint32_t* d_count, uint32_t capacity, uint32_t* ranges, int numKeys);
 // tile ids by descending list length (raster launch order)
 cudaError_t launch_tile_order(cudaStream_t st, int numTiles, const uint32_t* tile_ranges, uint32_t* order);
 cudaError_t launch_tile_counts(cudaStream_t st, int numTiles, const uint32_t* tile_ranges, uint32_t* tile_counts);
@@ -96,8 +104,6 @@ cudaError_t launch_rec_to_packed(cudaStream_t st, int N, const float* rec, float
 cudaError_t launch_split_keys(cudaStream_t st, uint32_t M, const uint64_t* keys, uint32_t* hi, uint32_t* lo);
 cudaError_t launch_merge_keys(cudaStream_t st, uint32_t M, const uint32_t* hi, const uint32_t* lo, uint32_t hi_mask,
                               uint64_t* keys);
-cudaError_t launch_sorted_keys_out(cudaStream_t st, uint32_t M, const uint32_t* tile_keys, const uint32_t* vals,
-                                   const float* depth_ptr, int depth_stride, uint32_t* hi, uint32_t* lo);
 
 // ---- tilelists.cu ------------------------------------------------------------------------------
 cudaError_t launch_sb_counts(cudaStream_t st, int N, const uint2* tile_rects, const uint32_t* touched, const uint32_t* perm0,

@@ -79,8 +79,6 @@ cudaError_t launch_sb_counts(cudaStream_t st, int N, const uint2* tile_rects, co
 // level 2: count / fill.  One CTA (8 warps) per superblock, warp w owns slice w of the superblock's depth-ordered
 // list.  counts / bases are indexed [superblock][warp][tile-in-superblock].
 // ------------------------------------------------------------------------------------------------
-constexpr int L2_WARPS = 8;
-constexpr int SB_TILES = SBW * SBH;
 
 template <bool FILL>
 __global__ void __launch_bounds__(L2_WARPS * 32) k_l2_walk(int sbGridW, const uint32_t* __restrict__ sb_ranges,

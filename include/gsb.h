@@ -254,6 +254,8 @@ enum { GSB_STAGE_PROJECT_FWD = 0, GSB_STAGE_SCAN, GSB_STAGE_KEYGEN, GSB_STAGE_SO
 /* Sum of lastContrib over the image of the last gsb_render_forward = number of (pixel, Gaussian)
  * blend evaluations E of that view (the unit of the raster rooflines).  Synchronises. */
 GSB_API int gsb_last_contrib_sum(gsb_ctx*, uint64_t* host_out);
+/* geometry of the two-level tile lists: superblock size in tiles, superblock count, onesweep passes of the level-1 sort */
+GSB_API int gsb_tile_list_info(gsb_ctx*, int32_t* sb_w, int32_t* sb_h, int32_t* num_superblocks, int32_t* sort_passes);
 GSB_API int gsb_stats_reset(gsb_ctx*);
 GSB_API int gsb_stats_get(gsb_ctx*, gsb_stats* host_out);
 GSB_API int gsb_enable_stage_timing(gsb_ctx*, int32_t on);   /* brackets every stage with CUDA-event pairs; no syncs until stats are read */
