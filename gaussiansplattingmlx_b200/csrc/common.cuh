@@ -164,10 +164,12 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v)
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // packed-order fields -> raster record quads
-// Bit 31 of the index word = "alpha may reach the 0.99 clamp (or the conic is not negative definite in log2 form)":
+// Bits 31/30 of the index word are flags.  Bit 31 = "alpha may reach the 0.99 clamp (or the conic is not negative definite in log2 form)":
 // when it is clear, exponent <= 0 everywhere and opacity <= 0.98, so min(0.99, .) is the identity and the backward
-// takes a path without the clamp logic.  Gaussian indices stay below 2^31.
+// takes a path without the clamp logic.
 constexpr uint32_t REC_MAYCLAMP = 0x80000000u;
+// Bit 30 is reserved; Gaussian indices stay below 2^30.
+constexpr uint32_t REC_IDX_MASK = 0x3fffffffu;
 __device__ __forceinline__ void make_raster_record(float mx, float my, float c00, float c01, float c10, float c11, float r,
                                                    float g, float b, float opacity, float depth, uint32_t idx, float4* out)
 {
@@ -189,6 +191,56 @@ __device__ __forceinline__ float rcp_approx(float x)
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// Packed FP32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): one issue slot for two IEEE-rn operations, each half bit-identical
+// to the scalar fmaf / __fmul_rn / __fadd_rn.  Measured on B200 (tools/microbench/f32x2_rate.cu): same FMA rate as scalar
+// FFMA (123 of 128 fma/clk/SM) at half the issue slots when one source is a broadcast scalar; the rasterisers are
+// issue-bound, not pipe-bound, so pairs of vertically adjacent pixels are evaluated as one f32x2 lane.
+struct f32x2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f32x2 f2_make(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_bc(float x) { return f2_make(x, x); }
+__device__ __forceinline__ float f2_lo(f32x2 a)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+    return lo;
+}
+__device__ __forceinline__ float f2_hi(f32x2 a)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+    return hi;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
 }
 __device__ __forceinline__ float4 lds128(uint32_t addr)
 {

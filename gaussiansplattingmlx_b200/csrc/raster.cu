@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "kernels.h"
 
@@ -94,8 +95,9 @@ __device__ __forceinline__ FwdExp fwd_exponents(const float4& a, float C, float 
 template <int R>
 __device__ __forceinline__ float fwd_alpha(const FwdExp& e)
 {
+    // same two roundings per row as the packed f32x2 evaluation in the blend loop (row 0 included: fma(0, x, E0) = E0)
     const float rf = (float)R;
-    const float p = R == 0 ? e.E0 : fmaf(rf, fmaf(rf, e.C, e.E1), e.E0);
+    const float p = fmaf(rf, fmaf(rf, e.C, e.E1), e.E0);
     return fminf(ex2_approx(p), 0.99f);
 }
 __device__ __forceinline__ float fwd_alpha_rt(const FwdExp& e, int r)
@@ -188,16 +190,25 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
         __syncthreads();   // null-record fills of batch 0 are plain shared stores
 
         const float pxf = (float)pxi, pyf = (float)py0;
-        float cx[FPPT], cy[FPPT], cz[FPPT], dep[FPPT], T[FPPT], Ts[FPPT];
+        // Rows (2k, 2k+1) of the thread's column form one f32x2 lane pair.  The colour/depth accumulators hold the
+        // NEGATED sums and the blend works with -alpha, so that T - T*alpha is a single packed FMA with no operand
+        // negation (f32x2 instructions have none); every half is bit-identical to the scalar fmaf sequence.
+        constexpr int FPAIRS = FPPT / 2;
+        f32x2 T2[FPAIRS], ncx[FPAIRS], ncy[FPAIRS], ncz[FPAIRS], ndep[FPAIRS];
+        float Ts[FPPT];
         uint32_t ci[FPPT];
         bool active[FPPT];
 #pragma unroll
         for (int r = 0; r < FPPT; ++r) {
             active[r] = pxi < bm.xmax && py0 + r < bm.ymax;
-            cx[r] = cy[r] = cz[r] = dep[r] = 0.f;
-            T[r] = active[r] ? 1.0f : 0.0f;   // T == 0  <=>  this pixel is finished (terminated or outside)
             Ts[r] = 0.f;
             ci[r] = 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < FPAIRS; ++k) {
+            // T == 0  <=>  this pixel is finished (terminated or outside)
+            T2[k] = f2_make(active[2 * k] ? 1.0f : 0.0f, active[2 * k + 1] ? 1.0f : 0.0f);
+            ncx[k] = ncy[k] = ncz[k] = ndep[k] = f2_bc(0.0f);
         }
         bool warp_done = false;
 
@@ -205,20 +216,25 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
         auto blend = [&](uint32_t addr) {
             const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
             const FwdExp e = fwd_exponents(a, q.x, q.y, pxf, pyf);
-            auto px = [&](int r, float alpha) {
-                const float contrib = T[r] * alpha;
-                cx[r] = fmaf(contrib, q.z, cx[r]);
-                cy[r] = fmaf(contrib, q.w, cy[r]);
-                cz[r] = fmaf(contrib, c.x, cz[r]);
-                if (DEPTH) dep[r] = fmaf(contrib, c.z, dep[r]);
-                const float Tn = fmaf(-T[r], alpha, T[r]);
-                T[r] = Tn < 1e-4f ? 0.0f : Tn;   // the terminating Gaussian is included (:599-603)
-            };
-            px(0, fwd_alpha<0>(e));
-            px(1, fwd_alpha<1>(e));
-            px(2, fwd_alpha<2>(e));
-            px(3, fwd_alpha<3>(e));
+            const f32x2 E0b = f2_bc(e.E0), E1b = f2_bc(e.E1), Cb = f2_bc(e.C);
+            const f32x2 colR = f2_bc(q.z), colG = f2_bc(q.w), colB = f2_bc(c.x), colD = f2_bc(c.z);
+#pragma unroll
+            for (int k = 0; k < FPAIRS; ++k) {
+                const f32x2 rf = f2_make((float)(2 * k), (float)(2 * k + 1));
+                const f32x2 p = f2_fma(rf, f2_fma(rf, Cb, E1b), E0b);
+                const f32x2 na = f2_make(fmaxf(-ex2_approx(f2_lo(p)), -0.99f), fmaxf(-ex2_approx(f2_hi(p)), -0.99f));
+                const f32x2 nc = f2_mul(T2[k], na);   // -T * alpha
+                ncx[k] = f2_fma(nc, colR, ncx[k]);
+                ncy[k] = f2_fma(nc, colG, ncy[k]);
+                ncz[k] = f2_fma(nc, colB, ncz[k]);
+                if (DEPTH) ndep[k] = f2_fma(nc, colD, ndep[k]);
+                const f32x2 Tn = f2_fma(T2[k], na, T2[k]);
+                const float t0 = f2_lo(Tn), t1 = f2_hi(Tn);
+                // the terminating Gaussian is included (:599-603)
+                T2[k] = f2_make(t0 < 1e-4f ? 0.0f : t0, t1 < 1e-4f ? 0.0f : t1);
+            }
         };
+        auto Trow = [&](int r) { return (r & 1) ? f2_hi(T2[r >> 1]) : f2_lo(T2[r >> 1]); };
 
         int b = 0;
         for (; b < nb; ++b) {
@@ -234,13 +250,16 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
                     // remember where (and with which transmittance) each live pixel entered this chunk
 #pragma unroll
                     for (int r = 0; r < FPPT; ++r) {
-                        const bool live = T[r] != 0.0f;
-                        Ts[r] = live ? T[r] : Ts[r];
+                        const float t = Trow(r);
+                        const bool live = t != 0.0f;
+                        Ts[r] = live ? t : Ts[r];
                         ci[r] = live ? chunk : ci[r];
                     }
 #pragma unroll
                     for (int g = 0; g < FCHUNK; ++g) blend(addr + g * 48u);
-                    const float tmax = fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3]));
+                    float tmax = Trow(0);
+#pragma unroll
+                    for (int r = 1; r < FPPT; ++r) tmax = fmaxf(tmax, Trow(r));
                     if (__all_sync(0xffffffffu, tmax == 0.0f)) { warp_done = true; break; }
                 }
             }
@@ -259,7 +278,7 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
 #pragma unroll
         for (int r = 0; r < FPPT; ++r) {
             if (!active[r]) continue;
-            float Tend = T[r];
+            float Tend = Trow(r);
             uint32_t nContrib = count;
             if (Tend == 0.0f) {
                 float t = Ts[r];
@@ -280,10 +299,11 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
             }
             const size_t p = (size_t)(py0 + r) * vp.W + pxi;
             const float bg = vp.whiteBg ? Tend : 0.0f;
-            out_color[p * 3 + 0] = cx[r] + bg;
-            out_color[p * 3 + 1] = cy[r] + bg;
-            out_color[p * 3 + 2] = cz[r] + bg;
-            if (DEPTH) out_depth[p] = dep[r];
+            auto row = [&](const f32x2* v) { return -((r & 1) ? f2_hi(v[r >> 1]) : f2_lo(v[r >> 1])); };
+            out_color[p * 3 + 0] = row(ncx) + bg;
+            out_color[p * 3 + 1] = row(ncy) + bg;
+            out_color[p * 3 + 2] = row(ncz) + bg;
+            if (DEPTH) out_depth[p] = row(ndep);
             out_alpha[p] = 1.0f - Tend;
             out_last[p] = nContrib;
         }
@@ -353,31 +373,46 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
     // thread = column (lane & 15) x 8 consecutive rows starting at (lane >> 4) * 8
     const int pxi = bm.x0 + (lane & 15);
     const int py0 = bm.y0 + (lane >> 4) * BPPT;
-    float sT[BPPT], kX[BPPT], kY[BPPT], kZ[BPPT], kD[BPPT], kT[BPPT];
+    // rows (2k, 2k+1) of the thread's column form one f32x2 lane pair (see the forward)
+    constexpr int BPAIRS = BPPT / 2;
+    f32x2 sT2[BPAIRS], kX2[BPAIRS], kY2[BPAIRS], kZ2[BPAIRS], kD2[BPAIRS], kT2[BPAIRS];
     uint32_t nC[BPPT];
     uint32_t nmax = 0, nmin = 0xffffffffu;
+    {
+        float sT[BPPT], kX[BPPT], kY[BPPT], kZ[BPPT], kD[BPPT], kT[BPPT];
 #pragma unroll
-    for (int p = 0; p < BPPT; ++p) {
-        const int pyi = py0 + p;
-        sT[p] = 0.f; kX[p] = 0.f; kY[p] = 0.f; kZ[p] = 0.f; kD[p] = 0.f; kT[p] = 0.f;
-        nC[p] = 0;
-        if (pxi < bm.xmax && pyi < bm.ymax) {
-            // slang/gaussian_tile_global_kernels.slang:696-723
-            const size_t pix = (size_t)pyi * vp.W + pxi;
-            kX[p] = cot_color[pix * 3];
-            kY[p] = cot_color[pix * 3 + 1];
-            kZ[p] = cot_color[pix * 3 + 2];
-            kD[p] = cot_depth ? cot_depth[pix] : 0.0f;
-            const float cotA = cot_alpha ? cot_alpha[pix] : 0.0f;
-            sT[p] = 1.0f - out_alpha[pix];
-            kT[p] = -cotA + (vp.whiteBg ? (kX[p] + kY[p] + kZ[p]) : 0.0f);
-            nC[p] = min(last_contrib[pix], count);
+        for (int p = 0; p < BPPT; ++p) {
+            const int pyi = py0 + p;
+            sT[p] = 0.f; kX[p] = 0.f; kY[p] = 0.f; kZ[p] = 0.f; kD[p] = 0.f; kT[p] = 0.f;
+            nC[p] = 0;
+            if (pxi < bm.xmax && pyi < bm.ymax) {
+                // slang/gaussian_tile_global_kernels.slang:696-723
+                const size_t pix = (size_t)pyi * vp.W + pxi;
+                kX[p] = cot_color[pix * 3];
+                kY[p] = cot_color[pix * 3 + 1];
+                kZ[p] = cot_color[pix * 3 + 2];
+                kD[p] = cot_depth ? cot_depth[pix] : 0.0f;
+                const float cotA = cot_alpha ? cot_alpha[pix] : 0.0f;
+                sT[p] = 1.0f - out_alpha[pix];
+                kT[p] = -cotA + (vp.whiteBg ? (kX[p] + kY[p] + kZ[p]) : 0.0f);
+                nC[p] = min(last_contrib[pix], count);
+            }
+            nmax = max(nmax, nC[p]);
+            nmin = min(nmin, nC[p]);
         }
-        nmax = max(nmax, nC[p]);
-        nmin = min(nmin, nC[p]);
+#pragma unroll
+        for (int k = 0; k < BPAIRS; ++k) {
+            sT2[k] = f2_make(sT[2 * k], sT[2 * k + 1]);
+            kX2[k] = f2_make(kX[2 * k], kX[2 * k + 1]);
+            kY2[k] = f2_make(kY[2 * k], kY[2 * k + 1]);
+            kZ2[k] = f2_make(kZ[2 * k], kZ[2 * k + 1]);
+            kD2[k] = f2_make(kD[2 * k], kD[2 * k + 1]);
+            kT2[k] = f2_make(kT[2 * k], kT[2 * k + 1]);
+        }
     }
     // only Gaussians below the block-wide max nContrib can contribute
     const uint32_t used = __reduce_max_sync(0xffffffffu, nmax);
+    const uint32_t nmin_block = __reduce_min_sync(0xffffffffu, nmin);
     const int nb = (int)((used + RB_BWD - 1) / RB_BWD);
     if (nb == 0) continue;
 
@@ -430,86 +465,105 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
         __syncwarp();
         const int n = (int)min((uint32_t)RB_BWD, used - (uint32_t)b * RB_BWD);
         const uint32_t stage_addr = rec_base + (s & 1u) * (RB_BWD * 48u);
-        for (int j = n - 1; j >= 0; --j) {
+        // One Gaussian for the thread's 8 pixels.  MASKED = false when every pixel of the block is known to be active
+        // (i < block-wide min nContrib); CLAMP = false when the record says alpha cannot reach 0.99 (REC_MAYCLAMP clear).
+        // The four variants are whole loop bodies (no join inside an iteration), so the pixel state is updated in
+        // place, and no variant branches, so the compiler interleaves the 4 dependent pair chains.  An inactive pixel
+        // (i >= nContrib) of the masked variant sees alpha = 0: contrib = 0, kT unchanged, h = 0 - only its
+        // transmittance needs a select.
+        auto gaussian = [&](int j, const float4& a, const float4& q, const float4& c, auto masked_c, auto clamp_c) {
+            constexpr bool MASKED = decltype(masked_c)::value, CLAMP = decltype(clamp_c)::value;
             const uint32_t i = (uint32_t)(b * RB_BWD + j);
-            if (!__any_sync(0xffffffffu, i < nmax)) continue;
-            const uint32_t addr = stage_addr + (uint32_t)j * 48u;
-            const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
             const float dx = pxf - a.x, dyb = pyf - a.y;
             // The thread's 8 pixels share dx and have dy = dyb + p, so the exponent is a quadratic in the
-            // compile-time row offset p:  e(p) = E0 + p*E1 + p^2*C  (log2 units, opacity not included)
-            const float E0 = fmaf(dx, fmaf(a.z, dx, a.w * dyb), q.x * dyb * dyb);
+            // compile-time row offset p:  e(p) = E0 + p*E1 + p^2*C  (log2 units).  log2(opacity) is folded in, so
+            // ex2 yields alpha itself and h = dL/d(ln of the opacity-free alpha) = contrib * d; the opacity gradient
+            // is H0 / opacity (flush).
+            const float E0 = fmaf(dx, fmaf(a.z, dx, a.w * dyb), fmaf(q.x * dyb, dyb, q.y));
             const float E1 = fmaf(a.w, dx, 2.0f * q.x * dyb);
-            // per-thread partial sums over the 8 pixels: colour/depth terms and the moments of
-            // h = dL/d(opacity-free alpha) in the row offset: H0 = sum h, H1 = sum p h, H2 = sum p^2 h
-            float Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f, H0 = 0.f, H1 = 0.f, H2 = 0.f;
-            // one pixel of this thread.  masked = false when every pixel of the block is known to be active; clamp =
-            // false when the record says alpha cannot reach 0.99 (REC_MAYCLAMP clear).  No variant branches, so the
-            // compiler interleaves the 8 dependent chains.  An inactive pixel (i >= nContrib) of the masked variant
-            // sees ex = 0: alpha = 0, contrib = 0, kT unchanged, h = 0 — only its transmittance needs a select.
-            auto pixel = [&](int p, bool masked, bool clamp) {
-                const float pf = (float)p;
-                float ex = ex2_approx(fmaf(pf, fmaf(pf, q.x, E1), E0));    // :437-483
-                const bool act = !masked || (i < nC[p]);
-                if (masked) ex = act ? ex : 0.0f;
-                const float raw = ex * c.y;
-                const float alpha = clamp ? fminf(raw, 0.99f) : raw;
+            const f32x2 E0b = f2_bc(E0), E1b = f2_bc(E1), Cqb = f2_bc(q.x);
+            const f32x2 colR = f2_bc(q.z), colG = f2_bc(q.w), colB = f2_bc(c.x), colD = f2_bc(c.z);
+            f32x2 Cr2 = f2_bc(0.f), Cg2 = f2_bc(0.f), Cb2 = f2_bc(0.f), Cd2 = f2_bc(0.f);
+            f32x2 h[BPAIRS];
+#pragma unroll
+            for (int k = 0; k < BPAIRS; ++k) {
+                const f32x2 rf = f2_make((float)(2 * k), (float)(2 * k + 1));
+                const f32x2 e = f2_fma(rf, f2_fma(rf, Cqb, E1b), E0b);    // :437-483
+                float a0 = ex2_approx(f2_lo(e)), a1 = ex2_approx(f2_hi(e));
+                const bool act0 = !MASKED || (i < nC[2 * k]), act1 = !MASKED || (i < nC[2 * k + 1]);
+                if (MASKED) {
+                    a0 = act0 ? a0 : 0.0f;
+                    a1 = act1 ? a1 : 0.0f;
+                }
+                const float raw0 = a0, raw1 = a1;
+                if (CLAMP) {
+                    a0 = fminf(a0, 0.99f);
+                    a1 = fminf(a1, 0.99f);
+                }
+                const f32x2 al = f2_make(a0, a1);
                 // undoTileGlobalPixelState (:501-521): only the transmittance matters for the gradients;
                 // max(1 - alpha, 1e-6) == 1 - alpha because alpha <= 0.99
-                const float prevT = sT[p] * rcp_approx(1.0f - alpha);
-                const float contrib = prevT * alpha;
-                sT[p] = act ? prevT : sT[p];
+                const f32x2 om = f2_fma(al, f2_bc(-1.0f), f2_bc(1.0f));
+                const f32x2 prevT = f2_mul(sT2[k], f2_make(rcp_approx(f2_lo(om)), rcp_approx(f2_hi(om))));
+                const f32x2 contrib = f2_mul(prevT, al);
+                sT2[k] = MASKED ? f2_make(act0 ? f2_lo(prevT) : f2_lo(sT2[k]), act1 ? f2_hi(prevT) : f2_hi(sT2[k])) : prevT;
                 // VJP of updateTileGlobalPixelState (:485-499)
-                float dotc = fmaf(kZ[p], c.x, fmaf(kY[p], q.w, kX[p] * q.z));
-                if (DEPTH) dotc = fmaf(kD[p], c.z, dotc);
-                const float d = dotc - kT[p];
-                const float g_alpha = prevT * d;
-                kT[p] = fmaf(alpha, d, kT[p]);
-                Cr = fmaf(contrib, kX[p], Cr);
-                Cg = fmaf(contrib, kY[p], Cg);
-                Cb = fmaf(contrib, kZ[p], Cb);
-                if (DEPTH) Cd = fmaf(contrib, kD[p], Cd);
+                f32x2 dotc = f2_fma(kZ2[k], colB, f2_fma(kY2[k], colG, f2_mul(kX2[k], colR)));
+                if (DEPTH) dotc = f2_fma(kD2[k], colD, dotc);
+                const f32x2 d = f2_sub(dotc, kT2[k]);
+                kT2[k] = f2_fma(al, d, kT2[k]);
+                Cr2 = f2_fma(contrib, kX2[k], Cr2);
+                Cg2 = f2_fma(contrib, kY2[k], Cg2);
+                Cb2 = f2_fma(contrib, kZ2[k], Cb2);
+                if (DEPTH) Cd2 = f2_fma(contrib, kD2[k], Cd2);
                 // VJP of evaluateTileGlobalSample: everything geometric is a moment of h; the alpha clamp branch has
                 // zero gradient
-                float h = g_alpha * ex;
-                if (clamp) h = raw > 0.99f ? 0.0f : h;
-                H0 += h;
-                if (p > 0) {
-                    H1 = fmaf(h, pf, H1);
-                    H2 = fmaf(h, pf * pf, H2);
-                }
-            };
-            const bool mayclamp = (__float_as_uint(c.w) & REC_MAYCLAMP) != 0u;   // warp-uniform
-            const bool all_active = __all_sync(0xffffffffu, i < nmin);
-            if (all_active && !mayclamp) {
-#pragma unroll
-                for (int p = 0; p < BPPT; ++p) pixel(p, false, false);
-            } else if (all_active) {
-#pragma unroll
-                for (int p = 0; p < BPPT; ++p) pixel(p, false, true);
-            } else if (!mayclamp) {
-#pragma unroll
-                for (int p = 0; p < BPPT; ++p) pixel(p, true, false);
-            } else {
-#pragma unroll
-                for (int p = 0; p < BPPT; ++p) pixel(p, true, true);
+                f32x2 hh = f2_mul(contrib, d);
+                if (CLAMP) hh = f2_make(raw0 > 0.99f ? 0.0f : f2_lo(hh), raw1 > 0.99f ? 0.0f : f2_hi(hh));
+                h[k] = hh;
             }
+            // per-thread sums over the 8 pixels: colour/depth terms and the moments of h in the row offset
+            // p = 2k + (0 | 1):  H0 = sum h,  H1 = sum p h = 2 sum k (he + ho) + sum ho,
+            //                    H2 = sum p^2 h = 4 sum k^2 (he + ho) + 4 sum k ho + sum ho
+            static_assert(BPAIRS == 4, "moment recombination below is written for 4 pairs");
+            const f32x2 S = f2_add(f2_add(h[0], h[1]), f2_add(h[2], h[3]));
+            const f32x2 M1 = f2_fma(h[3], f2_bc(3.0f), f2_fma(h[2], f2_bc(2.0f), h[1]));
+            const f32x2 M2 = f2_fma(h[3], f2_bc(9.0f), f2_fma(h[2], f2_bc(4.0f), h[1]));
+            const float So = f2_hi(S);
+            const float H0 = f2_lo(S) + So;
+            const float H1 = fmaf(2.0f, f2_lo(M1) + f2_hi(M1), So);
+            const float H2 = fmaf(4.0f, (f2_lo(M2) + f2_hi(M2)) + f2_hi(M1), So);
             // moments in (dx, dy) of this thread's pixels: sum h dy = dyb H0 + H1, sum h dy^2 = dyb^2 H0 + 2 dyb H1 + H2
             const float Sy = fmaf(dyb, H0, H1);
             const float Syy = fmaf(dyb, fmaf(dyb, H0, H1 + H1), H2);
             const float Sx = dx * H0;
-            // park this lane's 10 partial sums; every BGRP Gaussians the warp sums the parked columns (below)
-            {
-                float* dst = &s_part[gcnt][0][lane];
-                dst[0 * BPAD] = Cr; dst[1 * BPAD] = Cg; dst[2 * BPAD] = Cb; dst[3 * BPAD] = Cd; dst[4 * BPAD] = H0;
-                dst[5 * BPAD] = Sx; dst[6 * BPAD] = Sy; dst[7 * BPAD] = dx * Sx; dst[8 * BPAD] = dx * Sy; dst[9 * BPAD] = Syy;
-                jpack |= (uint32_t)j << (8 * gcnt);
-                if (++gcnt == BGRP) {
-                    reduce_group(BGRP);
-                    gcnt = 0;
-                    jpack = 0u;
-                }
+            // park this lane's 10 partial sums; every BGRP Gaussians the warp sums the parked columns (reduce_group)
+            float* dst = &s_part[gcnt][0][lane];
+            dst[0 * BPAD] = f2_lo(Cr2) + f2_hi(Cr2); dst[1 * BPAD] = f2_lo(Cg2) + f2_hi(Cg2); dst[2 * BPAD] = f2_lo(Cb2) + f2_hi(Cb2);
+            dst[3 * BPAD] = DEPTH ? f2_lo(Cd2) + f2_hi(Cd2) : 0.0f; dst[4 * BPAD] = H0;
+            dst[5 * BPAD] = Sx; dst[6 * BPAD] = Sy; dst[7 * BPAD] = dx * Sx; dst[8 * BPAD] = dx * Sy; dst[9 * BPAD] = Syy;
+            jpack |= (uint32_t)j << (8 * gcnt);
+            if (++gcnt == BGRP) {
+                reduce_group(BGRP);
+                gcnt = 0;
+                jpack = 0u;
             }
+        };
+        // back to front: the Gaussians at or beyond the block-wide min nContrib come first (masked), the rest have
+        // every pixel of the block active
+        const int jsplit = (int)min((uint32_t)n, max(nmin_block, (uint32_t)b * RB_BWD) - (uint32_t)b * RB_BWD);
+        int j = n - 1;
+        for (; j >= jsplit; --j) {
+            const uint32_t addr = stage_addr + (uint32_t)j * 48u;
+            const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
+            if (__float_as_uint(c.w) & REC_MAYCLAMP) gaussian(j, a, q, c, std::true_type{}, std::true_type{});   // warp-uniform
+            else gaussian(j, a, q, c, std::true_type{}, std::false_type{});
+        }
+        for (; j >= 0; --j) {
+            const uint32_t addr = stage_addr + (uint32_t)j * 48u;
+            const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
+            if (__float_as_uint(c.w) & REC_MAYCLAMP) gaussian(j, a, q, c, std::false_type{}, std::true_type{});
+            else gaussian(j, a, q, c, std::false_type{}, std::false_type{});
         }
         if (gcnt) {
             reduce_group(gcnt);
@@ -528,16 +582,18 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
             if (!any) continue;
             const uint32_t addr = stage_addr + (uint32_t)j * 48u;
             const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
-            const float op = c.y;
-            const float kc = -0.5f * op;                 // d(natural exponent)/d conic = -0.5 * (dx^2, dx dy, dy^2)
-            const float km = -op * (1.0f / LOG2E_F);     // d(natural exponent)/d mean = -(2a dx + b dy, ...), (a,b,c) = (A,B,C)/log2 e
+            // h carries the opacity factor (alpha-weighted): the opacity gradient is H0 / opacity.  opacity == 0
+            // (sigmoid underflow) gives 0; the activation VJP multiplies it by opacity (1 - opacity) = 0 anyway
+            const float g_op = c.y > 0.0f ? s1.x / c.y : 0.0f;
+            const float kc = -0.5f;                      // d(natural exponent)/d conic = -0.5 * (dx^2, dx dy, dy^2)
+            const float km = -(1.0f / LOG2E_F);          // d(natural exponent)/d mean = -(2a dx + b dy, ...), (a,b,c) = (A,B,C)/log2 e
             const float g_mx = km * fmaf(a.z + a.z, s1.y, a.w * s1.z);
             const float g_my = km * fmaf(q.x + q.x, s1.z, a.w * s1.y);
             const float g_c00 = kc * s1.w, g_c01 = kc * s2.x, g_c11 = kc * s2.y;
-            float* dst = grad_rec + (size_t)(__float_as_uint(c.w) & ~REC_MAYCLAMP) * REC_FLOATS;
+            float* dst = grad_rec + (size_t)(__float_as_uint(c.w) & REC_IDX_MASK) * REC_FLOATS;
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g_mx), "f"(g_my), "f"(g_c00), "f"(g_c01) : "memory");
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(g_c01), "f"(g_c11), "f"(s0.x), "f"(s0.y) : "memory");
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8), "f"(s0.z), "f"(s1.x), "f"(s0.w), "f"(0.0f) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8), "f"(s0.z), "f"(g_op), "f"(s0.w), "f"(0.0f) : "memory");
         }
     }
     seq += (uint32_t)nb;
