@@ -19,6 +19,7 @@ GSB_ERR_INVALID, GSB_ERR_CUDA, GSB_ERR_UNSUPPORTED, GSB_ERR_STATE, GSB_ERR_CAPAC
 GSB_FLAG_SORT_CUB = 1
 GSB_FLAG_NO_OVERLAP = 2
 GSB_FLAG_ASYNC_LOSS = 4
+GSB_FLAG_NO_SEGMENTS = 8
 STAGE_COUNT = 12
 
 

@@ -107,6 +107,9 @@ struct Ctx {
     float* out_depth = nullptr;
     float* out_alpha = nullptr;
     uint32_t* out_last = nullptr;
+    gsb::RasterCkpt ck;               // forward blend-state checkpoints for the segmented raster backward (raster.cu)
+    bool ck_has_depth = false;        // the last fused forward also checkpointed the depth prefix
+    bool ck_valid = false;            // the last fused forward wrote checkpoints at all (GSB_FLAG_NO_SEGMENTS clear)
     float* mapA = nullptr;            // SSIM backward maps, [P*3] each
     float* mapB = nullptr;
     float* mapC = nullptr;
@@ -521,6 +524,9 @@ static void destroy_ctx(Ctx* c)
     if (c->cub_tmp) cudaFree(c->cub_tmp);
     dev_free(c->dbg_keys); dev_free(c->dbg_vals);
     dev_free(c->out_color); dev_free(c->out_depth); dev_free(c->out_alpha); dev_free(c->out_last);
+    if (c->ck.state) cudaFree(c->ck.state);
+    if (c->ck.header) cudaFree(c->ck.header);
+    dev_free(c->ck.depth); dev_free(c->ck.count); dev_free(c->ck.written); dev_free(c->ck.table);
     dev_free(c->mapA); dev_free(c->mapB); dev_free(c->mapC); dev_free(c->cot_render); dev_free(c->partial);
     dev_free(c->loss_accum); dev_free(c->d_zero);
     for (int i = 0; i < 2; ++i) { dev_free(c->t_slab[i]); dev_free(c->t_accum_slab[i]); }
@@ -659,6 +665,20 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
     CREATE_CHECK(dev_alloc(&c->out_depth, P));
     CREATE_CHECK(dev_alloc(&c->out_alpha, P));
     CREATE_CHECK(dev_alloc(&c->out_last, P));
+    {
+        // checkpoint pool: ~1.1 slots per block at C3 (lists are cut short by early termination); 4 per block leaves
+        // room for translucent scenes, and an exhausted pool only costs load balance (5 KB per slot)
+        const int blocks = gsb::raster_block_count(make_view_nocam(c));
+        c->ck.capacity = (uint32_t)std::max(4096, 4 * blocks);
+        CREATE_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->ck.state), (size_t)c->ck.capacity * 256 * sizeof(float4)));
+        CREATE_CHECK(dev_alloc(&c->ck.depth, (size_t)c->ck.capacity * 256));
+        CREATE_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->ck.header), (size_t)c->ck.capacity * sizeof(uint2)));
+        CREATE_CHECK(dev_alloc(&c->ck.count, 4));
+        CREATE_CHECK(dev_alloc(&c->ck.written, (size_t)std::max(blocks, 1)));
+        CREATE_CHECK(dev_alloc(&c->ck.table, (size_t)std::max(blocks, 1) * 17));
+        CREATE_CHECK(cudaMemset(c->ck.count, 0, 4 * sizeof(uint32_t)));
+        CREATE_CHECK(cudaMemset(c->ck.written, 0, (size_t)std::max(blocks, 1) * sizeof(uint32_t)));
+    }
     CREATE_CHECK(dev_alloc(&c->mapA, P * 3));
     CREATE_CHECK(dev_alloc(&c->mapB, P * 3));
     CREATE_CHECK(dev_alloc(&c->mapC, P * 3));
@@ -912,8 +932,9 @@ int gsb_raster_fwd(gsb_ctx* ctx, int32_t N, const float* packed, float* out_colo
     if (rc != GSB_OK) return rc;
     Ctx::ViewBufs& v = c->vb[c->cur];
     gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
+    // kernel-level mirror of K9/K10: the caller owns the saved outputs, so no checkpoints are kept for them
     GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, c->bin_vp, v.tile_ranges, v.tile_order, v.rec, v.list, v.list, c->d_zero, out_color, out_depth, out_alpha,
-                                             out_last_contrib, &v.d_ctl[3]));
+                                             out_last_contrib, &v.d_ctl[3], gsb::RasterCkpt{}));
     c->stats.kernel_launches += 1;
     return GSB_OK;
 }
@@ -933,7 +954,7 @@ int gsb_raster_bwd(gsb_ctx* ctx, int32_t N, const float* packed, const float* co
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
         GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, c->bin_vp, v.tile_ranges, v.tile_order, v.rec, v.list, v.list, c->d_zero, cot_color, cot_depth, cot_alpha,
-                                                 out_color, out_depth, out_alpha, last_contrib, c->grad_rec, &v.d_ctl[3]));
+                                                 out_color, out_depth, out_alpha, last_contrib, c->grad_rec, &v.d_ctl[3], gsb::RasterCkpt{}));
     }
     GSB_CUDA_CHECK(c, gsb::launch_rec_to_packed(c->stream, N, c->grad_rec, grad_packed));
     c->stats.kernel_launches += 2;
@@ -994,7 +1015,10 @@ static int enqueue_raster_fwd(Ctx* c, Ctx::ViewBufs& v, int32_t N, const RawPara
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_FWD);
         GSB_CUDA_CHECK(c, gsb::launch_raster_fwd(c->stream, vp, v.tile_ranges, v.tile_order, v.rec, v.list, v.list, c->d_zero,
-                                                 c->out_color, want_depth ? c->out_depth : nullptr, c->out_alpha, c->out_last, &v.d_ctl[3]));
+                                                 c->out_color, want_depth ? c->out_depth : nullptr, c->out_alpha, c->out_last, &v.d_ctl[3],
+                                                 (c->cfg.flags & GSB_FLAG_NO_SEGMENTS) ? gsb::RasterCkpt{} : c->ck));
+        c->ck_has_depth = want_depth;
+        c->ck_valid = !(c->cfg.flags & GSB_FLAG_NO_SEGMENTS);
         c->stats.kernel_launches += 1;
     }
     c->cur = (int)(&v - &c->vb[0]);
@@ -1046,7 +1070,8 @@ static int render_backward_impl(Ctx* c, const float* cot_render, const float* co
     {
         gsb::StageTimer t(c, GSB_STAGE_RASTER_BWD);
         GSB_CUDA_CHECK(c, gsb::launch_raster_bwd(c->stream, vp, v.tile_ranges, v.tile_order, v.rec, v.list, v.list, c->d_zero, cot_render, cot_depth, cot_alpha,
-                                                 c->out_color, c->out_depth, c->out_alpha, c->out_last, grec, &v.d_ctl[3]));
+                                                 c->out_color, c->out_depth, c->out_alpha, c->out_last, grec, &v.d_ctl[3],
+                                                 (!c->ck_valid || (cot_depth && !c->ck_has_depth)) ? gsb::RasterCkpt{} : c->ck));
     }
     cudaStream_t pst = c->stream;
     if (split) {

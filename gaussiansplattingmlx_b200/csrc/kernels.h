@@ -120,17 +120,32 @@ cudaError_t launch_expand_sorted_keys(cudaStream_t st, uint32_t M, int numTiles,
                                       const float* depth_ptr, int depth_stride, uint32_t* hi, uint32_t* lo);
 
 // ---- raster.cu ---------------------------------------------------------------------------------
+// Blend-state checkpoints written by the forward every 256 Gaussians of a 16x16 block that is still running, so that
+// the backward can differentiate the segments of a long list as independent, bounded work items.  A pool of slots
+// handed out by a device counter; a null `state` disables checkpointing (forward-only rendering) and an empty or
+// exhausted pool only makes the backward fall back to longer items.
+struct RasterCkpt {
+    float4* state = nullptr;      // [capacity][256] colour summed over one segment + transmittance at its end, 16x16 pixels
+    float* depth = nullptr;       // [capacity][256] depth summed over one segment (written only when depth is requested)
+    uint2* header = nullptr;      // [capacity] (block work id, checkpoint index | 0xffffffff = final partial segment sums)
+    uint32_t* table = nullptr;    // [blocks][17] slot of checkpoint c (c < written), [16] = slot of the final segment sums
+    uint32_t* count = nullptr;    // slots requested by the last forward (may exceed capacity)
+    uint32_t* written = nullptr;  // [blocks] checkpoints each block managed to write
+    uint32_t capacity = 0;
+};
+int raster_block_count(const ViewParams& vp);
 // rec = record table [N,12]; (vals0|vals1 selected by *d_result_buf) = Gaussian indices in (tile, depth) order
 cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
                               const uint32_t* tile_order, const float* rec, const uint32_t* vals0, const uint32_t* vals1,
                               const uint32_t* d_result_buf,
-                              float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last, uint32_t* work_counter);
+                              float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last, uint32_t* work_counter,
+                              const RasterCkpt& ck);
 cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
                               const uint32_t* tile_order, const float* rec, const uint32_t* vals0, const uint32_t* vals1,
                               const uint32_t* d_result_buf,
                               const float* cot_color, const float* cot_depth, const float* cot_alpha,
                               const float* out_color, const float* out_depth, const float* out_alpha,
-                              const uint32_t* last_contrib, float* grad_rec, uint32_t* work_counter);
+                              const uint32_t* last_contrib, float* grad_rec, uint32_t* work_counter, const RasterCkpt& ck);
 
 cudaError_t launch_sum_u32(cudaStream_t st, size_t n, const uint32_t* v, unsigned long long* out);
 

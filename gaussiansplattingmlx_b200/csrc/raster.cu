@@ -34,6 +34,8 @@ constexpr int RB_FWD = 128;      // records per forward batch (6 KB)
 constexpr int RB_BWD = 64;       // records per backward batch
 constexpr int BPPT = 8;          // backward: pixels per thread (rows)
 constexpr int BGRP = 3;          // backward: Gaussians per shared-memory reduction round (3 x 10 sums <= 32 lanes)
+constexpr int CK = 256;          // Gaussians between transmittance/colour checkpoints (forward) = backward segment length
+constexpr int CK_MAX = 16;       // checkpoints per block (a longer list ends in one long backward item)
 constexpr int BPAD = 36;         // padded column length (floats): 144-byte stride keeps the LDS.128 of 8 lanes on distinct banks
 // Gather staging engine for the 48-byte records: 1 = one TMA bulk copy per record (cp.async.bulk, UBLKCP),
 // 0 = three 16-byte cp.async (LDGSTS) per record.  Both complete on the batch's mbarrier.
@@ -77,6 +79,7 @@ __device__ __forceinline__ BlockMap map_block(const ViewParams& vp, const uint32
 constexpr int FPPT = 4;          // forward: pixels (rows) per thread
 constexpr int FCHUNK = 4;        // Gaussians between termination bookkeeping / warp votes
 static_assert(RB_FWD % FCHUNK == 0, "batch must be a whole number of chunks");
+static_assert(CK % RB_FWD == 0 && CK % RB_BWD == 0, "checkpoints sit on batch boundaries");
 
 struct FwdExp {
     float E0, E1, C;
@@ -124,11 +127,11 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
                                                        const uint32_t* __restrict__ d_result_buf, float* __restrict__ out_color,
                                                        float* __restrict__ out_depth, float* __restrict__ out_alpha,
                                                        uint32_t* __restrict__ out_last, uint32_t* __restrict__ work_counter,
-                                                       uint32_t total_work)
+                                                       uint32_t total_work, const RasterCkpt ck)
 {
     __shared__ __align__(128) float4 s_rec[2][RB_FWD * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_work;
+    __shared__ uint32_t s_work, s_slot, s_slots[CK_MAX + 1];
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(&s_bar[0], RT);
@@ -211,6 +214,8 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
             ncx[k] = ncy[k] = ncz[k] = ndep[k] = f2_bc(0.0f);
         }
         bool warp_done = false;
+        bool ck_ok = ck.state != nullptr;
+        uint32_t ck_written = 0;
 
         // one Gaussian for the thread's FPPT pixels: slang/gaussian_tile_global_kernels.slang:437-499
         auto blend = [&](uint32_t addr) {
@@ -235,6 +240,19 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
             }
         };
         auto Trow = [&](int r) { return (r & 1) ? f2_hi(T2[r >> 1]) : f2_lo(T2[r >> 1]); };
+
+        // this thread's FPPT pixels of checkpoint slot `slot`: (sum r, sum g, sum b, T) [+ depth plane]
+        auto store_sums = [&](uint32_t slot) {
+#pragma unroll
+            for (int r = 0; r < FPPT; ++r) {
+                const int k = r >> 1;
+                const bool hi = (r & 1) != 0;
+                const size_t o = (size_t)slot * 256 + (size_t)(((tid >> 4) * FPPT + r) * 16 + (tid & 15));
+                ck.state[o] = make_float4(-(hi ? f2_hi(ncx[k]) : f2_lo(ncx[k])), -(hi ? f2_hi(ncy[k]) : f2_lo(ncy[k])),
+                                          -(hi ? f2_hi(ncz[k]) : f2_lo(ncz[k])), Trow(r));
+                if (DEPTH) ck.depth[o] = -(hi ? f2_hi(ndep[k]) : f2_lo(ndep[k]));
+            }
+        };
 
         int b = 0;
         for (; b < nb; ++b) {
@@ -272,8 +290,66 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
                 ++b;
                 break;
             }
+            // The block goes on past a multiple of CK Gaussians: checkpoint the blend state of its 256 pixels for the
+            // segmented backward (RasterCkpt) - the colour/depth summed SINCE THE PREVIOUS CHECKPOINT and the
+            // transmittance - and restart the sums, so a late segment's small terms keep their relative precision
+            // (the backward needs sum_{j >= e} w_j c_j; as C_final - C_prefix(e) it would lose it to cancellation).
+            // A terminated pixel stores T = 0 and is never read back.
+            const uint32_t done = (uint32_t)(b + 1) * RB_FWD;
+            if (ck_ok && done % CK == 0u && done < count) {
+                if (tid == 0) {
+                    // the first checkpoint also reserves the slot of the block's final (partial) segment sums
+                    const uint32_t want = ck_written == 0u ? 2u : 1u;
+                    uint32_t slot = 0xffffffffu;
+                    if (ck_written < (uint32_t)CK_MAX) {
+                        slot = atomicAdd(ck.count, want);
+                        if (slot + want > ck.capacity) {   // pool exhausted; every slot below min(count, capacity) keeps a valid header
+                            if (slot < ck.capacity) ck.header[slot] = make_uint2(work, 0xffffffffu);
+                            slot = 0xffffffffu;
+                        }
+                    }
+                    if (slot != 0xffffffffu) {
+                        if (want == 2u) {
+                            ck.header[slot] = make_uint2(work, 0xffffffffu);   // not a work item
+                            s_slots[CK_MAX] = slot++;
+                        }
+                        ck.header[slot] = make_uint2(work, ck_written);
+                        s_slots[ck_written] = slot;
+                    }
+                    s_slot = slot;
+                }
+                __syncthreads();
+                const uint32_t slot = s_slot;
+                if (slot != 0xffffffffu) {
+                    store_sums(slot);
+#pragma unroll
+                    for (int k = 0; k < FPAIRS; ++k) ncx[k] = ncy[k] = ncz[k] = ndep[k] = f2_bc(0.0f);
+                    ++ck_written;
+                } else {
+                    ck_ok = false;   // pool exhausted: the backward handles the rest of this block as one item
+                }
+            }
         }
         seq += (uint32_t)b;   // batches actually staged (and waited for) in this block
+        // Segment sums -> totals.  The block's final (partial) segment sums go to the slot reserved with the first
+        // checkpoint; the per-block slot table lets a backward item find the sums of all later segments.
+        float tot[FPPT][4];
+#pragma unroll
+        for (int r = 0; r < FPPT; ++r) tot[r][0] = tot[r][1] = tot[r][2] = tot[r][3] = 0.0f;
+        if (ck_written) {   // CTA-uniform
+            if (tid <= CK_MAX) ck.table[(size_t)work * (CK_MAX + 1) + tid] = s_slots[tid < (int)ck_written || tid == CK_MAX ? tid : CK_MAX];
+            for (uint32_t c = 0; c < ck_written; ++c) {   // this thread re-reads its own stores
+                const uint32_t slot = s_slots[c];
+#pragma unroll
+                for (int r = 0; r < FPPT; ++r) {
+                    const size_t o = (size_t)slot * 256 + (size_t)(((tid >> 4) * FPPT + r) * 16 + (tid & 15));
+                    const float4 v = ck.state[o];
+                    tot[r][0] += v.x; tot[r][1] += v.y; tot[r][2] += v.z;
+                    if (DEPTH) tot[r][3] += ck.depth[o];
+                }
+            }
+        }
+        if (tid == 0 && ck.written) ck.written[work] = ck_written;
         // epilogue: exact lastContrib / transmittance at termination, then the outputs
 #pragma unroll
         for (int r = 0; r < FPPT; ++r) {
@@ -300,10 +376,16 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
             const size_t p = (size_t)(py0 + r) * vp.W + pxi;
             const float bg = vp.whiteBg ? Tend : 0.0f;
             auto row = [&](const f32x2* v) { return -((r & 1) ? f2_hi(v[r >> 1]) : f2_lo(v[r >> 1])); };
-            out_color[p * 3 + 0] = row(ncx) + bg;
-            out_color[p * 3 + 1] = row(ncy) + bg;
-            out_color[p * 3 + 2] = row(ncz) + bg;
-            if (DEPTH) out_depth[p] = row(ndep);
+            if (ck_written) {
+                // final (partial) segment sums + the exact final transmittance (out_alpha = 1 - T loses its low bits)
+                const size_t o = (size_t)s_slots[CK_MAX] * 256 + (size_t)(((tid >> 4) * FPPT + r) * 16 + (tid & 15));
+                ck.state[o] = make_float4(row(ncx), row(ncy), row(ncz), Tend);
+                if (DEPTH) ck.depth[o] = row(ndep);
+            }
+            out_color[p * 3 + 0] = (tot[r][0] + row(ncx)) + bg;
+            out_color[p * 3 + 1] = (tot[r][1] + row(ncy)) + bg;
+            out_color[p * 3 + 2] = (tot[r][2] + row(ncz)) + bg;
+            if (DEPTH) out_depth[p] = tot[r][3] + row(ndep);
             out_alpha[p] = 1.0f - Tend;
             out_last[p] = nContrib;
         }
@@ -314,7 +396,7 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
 // backward
 // ------------------------------------------------------------------------------------------------
 template <bool DEPTH>
-__global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ ViewParams vp,
+__global__ void __launch_bounds__(32, 16) k_raster_bwd(const __grid_constant__ ViewParams vp,
                                                        const uint32_t* __restrict__ tile_ranges,
                                                        const uint32_t* __restrict__ tile_order,
                                                        const float4* __restrict__ rec, const uint32_t* __restrict__ vals0,
@@ -322,9 +404,10 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
                                                        const uint32_t* __restrict__ d_result_buf,
                                                        const float* __restrict__ cot_color,
                                                        const float* __restrict__ cot_depth, const float* __restrict__ cot_alpha,
+                                                       const float* __restrict__ out_color, const float* __restrict__ out_depth,
                                                        const float* __restrict__ out_alpha,
                                                        const uint32_t* __restrict__ last_contrib, float* __restrict__ grad_rec,
-                                                       uint32_t* __restrict__ work_counter, uint32_t total_work)
+                                                       uint32_t* __restrict__ work_counter, uint32_t num_blocks, const RasterCkpt ck)
 {
     __shared__ __align__(128) float4 s_rec[2][RB_BWD * 3];
     __shared__ __align__(16) float s_out[RB_BWD][12];   // per-Gaussian sums of this block for one batch
@@ -359,16 +442,38 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
     __syncwarp();
     const uint32_t* __restrict__ vals = (*d_result_buf) ? vals1 : vals0;
     uint32_t seq = 0;   // batches staged so far by this CTA: stage = seq & 1, mbarrier parity = (seq >> 1) & 1
-    // persistent: one warp pulls 16x16 blocks (heavy tiles first) from a device counter; see k_raster_fwd
+    // Persistent: one warp pulls work items from a device counter.  A work item is a SEGMENT of a 16x16 block's list:
+    // the forward saved the per-pixel blend state every CK Gaussians (RasterCkpt), so the Gaussians
+    // [c CK, (c+1) CK) of a block can be differentiated on their own, starting from the checkpointed state at (c+1) CK:
+    // the items are bounded by CK Gaussians and the warps of the grid finish together (a whole-block item is up to
+    // ~7x the mean, longer than the ideal makespan at 16 warps per SM).  Items: first one per checkpoint slot (all
+    // full segments), then one per block for the remainder past the block's last checkpoint, heavy tiles first.
+    const uint32_t num_slots = ck.count ? min(*ck.count, ck.capacity) : 0u;
+    const uint32_t total_work = num_slots + num_blocks;
     for (;;) {
     __syncwarp();       // every lane is done with the previous block's shared memory
     uint32_t work = 0;
     if (lane == 0) work = atomicAdd(work_counter, 1u);
     work = __shfl_sync(0xffffffffu, work, 0);
     if (work >= total_work) break;
-    const BlockMap bm = map_block(vp, tile_order, work);
+    const bool interior = work < num_slots;
+    uint32_t block_id, seg_begin;
+    uint32_t ck_index = 0, ck_written = 0;
+    if (interior) {
+        const uint2 h = ck.header[work];   // (block work id, checkpoint index)
+        if (h.y == 0xffffffffu) continue;  // the slot holding a block's final segment sums is not a work item
+        block_id = h.x;
+        ck_index = h.y;
+        ck_written = ck.written[block_id];
+        seg_begin = h.y * (uint32_t)CK;
+    } else {
+        block_id = work - num_slots;
+        seg_begin = ck.written ? ck.written[block_id] * (uint32_t)CK : 0u;
+    }
+    const BlockMap bm = map_block(vp, tile_order, block_id);
     const uint32_t start = tile_ranges[bm.tile * 2], end = tile_ranges[bm.tile * 2 + 1];
     const uint32_t count = end > start ? end - start : 0u;
+    const uint32_t seg_limit = interior ? seg_begin + (uint32_t)CK : count;   // Gaussians >= seg_limit belong to later items
 
     // thread = column (lane & 15) x 8 consecutive rows starting at (lane >> 4) * 8
     const int pxi = bm.x0 + (lane & 15);
@@ -393,9 +498,33 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
                 kZ[p] = cot_color[pix * 3 + 2];
                 kD[p] = cot_depth ? cot_depth[pix] : 0.0f;
                 const float cotA = cot_alpha ? cot_alpha[pix] : 0.0f;
-                sT[p] = 1.0f - out_alpha[pix];
+                const float Tfin = 1.0f - out_alpha[pix];
+                sT[p] = Tfin;
                 kT[p] = -cotA + (vp.whiteBg ? (kX[p] + kY[p] + kZ[p]) : 0.0f);
-                nC[p] = min(last_contrib[pix], count);
+                const uint32_t nc = min(last_contrib[pix], count);
+                nC[p] = min(nc, seg_limit);
+                if (nc > seg_limit) {
+                    // The pixel is still live at the end of this segment: start from the forward's checkpoint there.
+                    // The back-to-front recursion kT <- (1 - alpha) kT + alpha (cot . colour) has the closed form
+                    //   kT_e = (cot . sum_{j >= e} w_j c_j + T_final kT_init) / T(e),
+                    // and the sum is the forward's segment sums of all later segments (+ the final partial one)
+                    const int pi = (p + (lane >> 4) * BPPT) * 16 + (lane & 15);
+                    const uint32_t* tab = ck.table + (size_t)block_id * (CK_MAX + 1);
+                    float acc = 0.0f, Tend = Tfin;
+                    for (uint32_t t = ck_index + 1; t <= ck_written; ++t) {
+                        const size_t o = (size_t)tab[t < ck_written ? t : (uint32_t)CK_MAX] * 256 + pi;
+                        const float4 s4 = ck.state[o];
+                        acc = fmaf(kX[p], s4.x, fmaf(kY[p], s4.y, fmaf(kZ[p], s4.z, acc)));
+                        if (DEPTH) acc = fmaf(kD[p], ck.depth[o], acc);
+                        Tend = s4.w;   // the last slot read holds the exact final transmittance
+                    }
+                    const float Te = ck.state[(size_t)work * 256 + pi].w;   // T after seg_limit Gaussians
+                    kT[p] = fmaf(kT[p], Tend, acc) / Te;
+                    // The reference starts its undo chain from T = 1 - out_alpha (tile_global.slang:696-723), whose
+                    // rounding (up to 1e-3 relative for a saturated pixel) scales every transmittance of the chain:
+                    // apply the same factor to the checkpoint so that segmented and whole-list gradients agree
+                    sT[p] = Te * (Tfin / Tend);
+                }
             }
             nmax = max(nmax, nC[p]);
             nmin = min(nmin, nC[p]);
@@ -410,19 +539,21 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
             kT2[k] = f2_make(kT[2 * k], kT[2 * k + 1]);
         }
     }
-    // only Gaussians below the block-wide max nContrib can contribute
-    const uint32_t used = __reduce_max_sync(0xffffffffu, nmax);
+    // only Gaussians below the block-wide max nContrib (capped at the segment end) can contribute
+    const uint32_t used_abs = __reduce_max_sync(0xffffffffu, nmax);
     const uint32_t nmin_block = __reduce_min_sync(0xffffffffu, nmin);
+    const uint32_t used = used_abs > seg_begin ? used_abs - seg_begin : 0u;   // Gaussians of this item
     const int nb = (int)((used + RB_BWD - 1) / RB_BWD);
     if (nb == 0) continue;
+    const uint32_t lstart = start + seg_begin;   // list position of the item's first Gaussian
 
     // batches are visited last -> first; sequence number s = nb-1-b selects stage / parity
     // gather staging as in the forward: each lane pulls two 48-byte records per batch with TMA bulk copies
     uint32_t ia = 0xffffffffu, ib = 0xffffffffu;   // indices of this lane's two slots of the next batch to issue
     auto load_idx = [&](int b) {
         const uint32_t j0 = (uint32_t)b * RB_BWD + lane, j1 = j0 + 32;
-        ia = (b >= 0 && j0 < used) ? vals[start + j0] : 0xffffffffu;
-        ib = (b >= 0 && j1 < used) ? vals[start + j1] : 0xffffffffu;
+        ia = (b >= 0 && j0 < used) ? vals[lstart + j0] : 0xffffffffu;
+        ib = (b >= 0 && j1 < used) ? vals[lstart + j1] : 0xffffffffu;
     };
     auto issue = [&](int b) {
         const uint32_t s = seq + (uint32_t)(nb - 1 - b);
@@ -473,7 +604,7 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
         // transmittance needs a select.
         auto gaussian = [&](int j, const float4& a, const float4& q, const float4& c, auto masked_c, auto clamp_c) {
             constexpr bool MASKED = decltype(masked_c)::value, CLAMP = decltype(clamp_c)::value;
-            const uint32_t i = (uint32_t)(b * RB_BWD + j);
+            const uint32_t i = seg_begin + (uint32_t)(b * RB_BWD + j);
             const float dx = pxf - a.x, dyb = pyf - a.y;
             // The thread's 8 pixels share dx and have dy = dyb + p, so the exponent is a quadratic in the
             // compile-time row offset p:  e(p) = E0 + p*E1 + p^2*C  (log2 units).  log2(opacity) is folded in, so
@@ -551,7 +682,8 @@ __global__ void __launch_bounds__(32, 12) k_raster_bwd(const __grid_constant__ V
         };
         // back to front: the Gaussians at or beyond the block-wide min nContrib come first (masked), the rest have
         // every pixel of the block active
-        const int jsplit = (int)min((uint32_t)n, max(nmin_block, (uint32_t)b * RB_BWD) - (uint32_t)b * RB_BWD);
+        const uint32_t bstart = seg_begin + (uint32_t)b * RB_BWD;   // absolute index of the batch's first Gaussian
+        const int jsplit = (int)min((uint32_t)n, max(nmin_block, bstart) - bstart);
         int j = n - 1;
         for (; j >= jsplit; --j) {
             const uint32_t addr = stage_addr + (uint32_t)j * 48u;
@@ -625,6 +757,7 @@ static int raster_blocks(const ViewParams& vp)
     const int subX = (vp.tileW + 15) / 16, subY = (vp.tileH + 15) / 16;
     return vp.gridW * vp.gridH * subX * subY;
 }
+int raster_block_count(const ViewParams& vp) { return raster_blocks(vp); }
 
 // resident CTAs per SM of the persistent rasterisers (GSB_FWD_RES / GSB_BWD_RES override, for tuning)
 static int env_int(const char* name, int dflt)
@@ -647,7 +780,8 @@ static int sm_count()
 cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint32_t* tile_ranges,
                               const uint32_t* tile_order, const float* rec, const uint32_t* vals0, const uint32_t* vals1,
                               const uint32_t* d_result_buf,
-                              float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last, uint32_t* work_counter)
+                              float* out_color, float* out_depth, float* out_alpha, uint32_t* out_last, uint32_t* work_counter,
+                              const RasterCkpt& ck)
 {
     const int blocks = raster_blocks(vp);
     if (blocks > 0) {
@@ -659,13 +793,17 @@ cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint3
         }
         cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
         if (e != cudaSuccess) return e;
+        if (ck.state) {
+            e = cudaMemsetAsync(ck.count, 0, sizeof(uint32_t), st);
+            if (e != cudaSuccess) return e;
+        }
         const int grid = std::min(blocks, sm_count() * res);
         if (out_depth)
             k_raster_fwd<true><<<grid, RT, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
-                                                    d_result_buf, out_color, out_depth, out_alpha, out_last, work_counter, (uint32_t)blocks);
+                                                    d_result_buf, out_color, out_depth, out_alpha, out_last, work_counter, (uint32_t)blocks, ck);
         else
             k_raster_fwd<false><<<grid, RT, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
-                                                     d_result_buf, out_color, out_depth, out_alpha, out_last, work_counter, (uint32_t)blocks);
+                                                     d_result_buf, out_color, out_depth, out_alpha, out_last, work_counter, (uint32_t)blocks, ck);
     }
     return cudaGetLastError();
 }
@@ -675,9 +813,9 @@ cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint3
                               const uint32_t* d_result_buf,
                               const float* cot_color, const float* cot_depth, const float* cot_alpha,
                               const float* out_color, const float* out_depth, const float* out_alpha,
-                              const uint32_t* last_contrib, float* grad_rec, uint32_t* work_counter)
+                              const uint32_t* last_contrib, float* grad_rec, uint32_t* work_counter, const RasterCkpt& ck)
 {
-    (void)out_color; (void)out_depth;   // the colour/depth state is not needed by the gradients (see kernel)
+    // out_color / out_depth are only read where a work item starts from a forward checkpoint (see kernel)
     const int blocks = raster_blocks(vp);
     if (blocks > 0) {
         static int res = 0;
@@ -688,15 +826,15 @@ cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint3
         }
         cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
         if (e != cudaSuccess) return e;
-        const int grid = std::min(blocks, sm_count() * res);
+        const int grid = sm_count() * res;   // the item count (checkpoint slots + blocks) is only known on the device
         if (cot_depth)
             k_raster_bwd<true><<<grid, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
-                                                    d_result_buf, cot_color, cot_depth, cot_alpha, out_alpha, last_contrib, grad_rec,
-                                                    work_counter, (uint32_t)blocks);
+                                                    d_result_buf, cot_color, cot_depth, cot_alpha, out_color, out_depth, out_alpha,
+                                                    last_contrib, grad_rec, work_counter, (uint32_t)blocks, ck);
         else
             k_raster_bwd<false><<<grid, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
-                                                     d_result_buf, cot_color, cot_depth, cot_alpha, out_alpha, last_contrib, grad_rec,
-                                                     work_counter, (uint32_t)blocks);
+                                                     d_result_buf, cot_color, cot_depth, cot_alpha, out_color, out_depth, out_alpha,
+                                                     last_contrib, grad_rec, work_counter, (uint32_t)blocks, ck);
     }
     return cudaGetLastError();
 }

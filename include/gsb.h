@@ -63,6 +63,8 @@ typedef struct gsb_config {
 #define GSB_FLAG_NO_OVERLAP 2     /* trainer: run every view's kernels back to back on one stream (per-kernel timing) */
 #define GSB_FLAG_ASYNC_LOSS 4     /* gsb_trainer_accumulate / gsb_train_step: host_loss is PINNED host memory; the loss is copied
                                    * into it asynchronously on the work stream and the call does not synchronise */
+#define GSB_FLAG_NO_SEGMENTS 8    /* raster backward: one work item per 16x16 block instead of checkpointed 256-Gaussian segments
+                                   * (checking only: same gradients up to rounding, worse load balance) */
 
 /* Camera block = the 7 camera arrays of TrainStepInputIndex (GaussianTrainer.swift:254-272),
  * produced exactly as Trainer/CameraUtil.swift:5-102 does (row-vector convention, proj = P^T). */

@@ -278,6 +278,41 @@ def test_fused_render_and_backward_vs_oracle(gsb, best_oracle, name):
         assert rel_err(grads2[k].cpu().numpy(), 2.0 * grads[k].cpu().numpy()) < 1e-5, k
 
 
+@pytest.mark.parametrize("white,depth_cot", [(False, False), (True, True)])
+def test_segmented_backward_long_lists_vs_oracle(gsb, best_oracle, white, depth_cot):
+    """Lists of ~1500 translucent Gaussians per tile: most blocks cross several 256-Gaussian checkpoints, pixels
+    terminate inside, at and past segment boundaries.  Fused forward + segmented backward against the oracle, and
+    against the whole-block backward (GSB_FLAG_NO_SEGMENTS)."""
+    Context, L = gsb
+    o = best_oracle
+    n, W, H, degree = 6000, 48, 40, 1
+    params = make_gaussians(n, 21, degree)
+    params["_scales"] = params["_scales"] + np.float32(1.1)        # big footprints: every tile sees most Gaussians
+    params["_opacity"] = params["_opacity"] - np.float32(2.0)      # translucent: long lists before T < 1e-4
+    cam = make_cameras(W, H, 3)[2]
+    rng = np.random.default_rng(5)
+    cot = rng.standard_normal((H, W, 3)).astype(np.float32)
+    cot_depth = rng.standard_normal((H, W, 1)).astype(np.float32) if depth_cot else None
+    cot_alpha = rng.standard_normal((H, W, 1)).astype(np.float32) if depth_cot else None
+    fr = pl.render_forward(o, params, cam, degree, white_bg=white)
+    last = fr["fwd"]["lastContrib"].reshape(-1)
+    assert last.max() > 8 * 256 and last.min() < 2 * 256 and (last % 256 == 0).any()   # incl. termination AT a checkpoint
+    bw = pl.backward(o, params, cam, degree, fr, cot, cot_depth, cot_alpha, white_bg=white)
+    ctx = Context(W, H, sh_degree=degree, white_background=white)
+    dparams = {k: dev(v) for k, v in params.items()}
+    render, depth, alpha, vis, radii = ctx.render_forward(dparams, L.make_camera(cam))
+    assert np.abs(render.cpu().numpy() - fr["render"]).max() <= PIX_TOL
+    kw = dict(cot_depth=dev(cot_depth), cot_alpha=dev(cot_alpha)) if depth_cot else {}
+    g = {k: v.clone() for k, v in ctx.render_backward(dev(cot), **kw).items()}
+    for k in g:
+        assert rel_err(g[k].cpu().numpy().reshape(bw["grads"][k].shape), bw["grads"][k]) < GRAD_TOL, k
+    ctx.set_flags(L.GSB_FLAG_NO_SEGMENTS)
+    ctx.render_forward(dparams, L.make_camera(cam))
+    g0 = ctx.render_backward(dev(cot), **kw)
+    for k in g:
+        assert rel_err(g[k].cpu().numpy(), g0[k].cpu().numpy()) < 1e-4, k
+
+
 def test_train_steps_vs_oracle(gsb, best_oracle):
     """Three batched train steps (B = 2 views) through gsb_train_step vs the oracle loop."""
     Context, L = gsb
@@ -332,8 +367,12 @@ def test_view_pipeline_matches_serial_and_regrows(gsb):
     (la, pa, aa), (lb, pb, ab) = out[0], out[L.GSB_FLAG_NO_OVERLAP]
     for x, y in zip(la, lb):
         assert abs(x - y) < 1e-6
-    for k in pa:   # float atomics make the two runs differ in the last bits only
-        assert rel_err(pa[k] - params[k].reshape(pa[k].shape), pb[k] - params[k].reshape(pb[k].shape)) < 1e-3, k
+    # Float atomics make two runs of the SAME schedule differ in the last bits of the gradients, and Adam without bias
+    # correction turns a first-step gradient into a step of ~3.2 lr * sign(g): measured run-to-run noise of the
+    # parameter deltas is up to 2e-2 of the largest delta (tools/dbg/pipeline_noise.py); a schedule bug (a view
+    # dropped, a stale buffer) shows up at O(1)
+    for k in pa:
+        assert rel_err(pa[k] - params[k].reshape(pa[k].shape), pb[k] - params[k].reshape(pb[k].shape)) < 5e-2, k
     assert rel_err(aa, ab) < 1e-4
 
 
@@ -474,6 +513,14 @@ def test_full_size_properties(gsb, wl_name, n):
     for k in g1:
         assert rel_err(g2[k].cpu().numpy(), 2.0 * g1[k].cpu().numpy()) < 1e-4, k
     assert all(bool(torch.isfinite(v).all()) for v in g1.values())
+    # the segmented backward (forward checkpoints every 256 Gaussians) against whole-block work items
+    ctx.set_flags(L.GSB_FLAG_NO_SEGMENTS)
+    render3, *_ = ctx.render_forward(dparams, gcam)
+    assert float((render - render3).abs().max()) < 1e-5     # per-segment colour sums vs one running sum
+    g3 = ctx.render_backward(cot)
+    ctx.set_flags(0)
+    for k in g1:
+        assert rel_err(g1[k].cpu().numpy(), g3[k].cpu().numpy()) < 1e-4, k
     if wl_name == "C3":
         assert abs(M - 12_031_308) <= 200     # SURVEY.md 8d-workload (reference kernels on CPU), view 0
 
