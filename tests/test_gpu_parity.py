@@ -278,8 +278,8 @@ def test_fused_render_and_backward_vs_oracle(gsb, best_oracle, name):
         assert rel_err(grads2[k].cpu().numpy(), 2.0 * grads[k].cpu().numpy()) < 1e-5, k
 
 
-@pytest.mark.parametrize("white,depth_cot", [(False, False), (True, True)])
-def test_segmented_backward_long_lists_vs_oracle(gsb, best_oracle, white, depth_cot):
+@pytest.mark.parametrize("white,depth_cot,tile", [(False, False, (16, 16)), (True, True, (16, 16)), (False, True, (24, 20))])
+def test_segmented_backward_long_lists_vs_oracle(gsb, best_oracle, white, depth_cot, tile):
     """Lists of ~1500 translucent Gaussians per tile: most blocks cross several 256-Gaussian checkpoints, pixels
     terminate inside, at and past segment boundaries.  Fused forward + segmented backward against the oracle, and
     against the whole-block backward (GSB_FLAG_NO_SEGMENTS)."""
@@ -294,11 +294,14 @@ def test_segmented_backward_long_lists_vs_oracle(gsb, best_oracle, white, depth_
     cot = rng.standard_normal((H, W, 3)).astype(np.float32)
     cot_depth = rng.standard_normal((H, W, 1)).astype(np.float32) if depth_cot else None
     cot_alpha = rng.standard_normal((H, W, 1)).astype(np.float32) if depth_cot else None
-    fr = pl.render_forward(o, params, cam, degree, white_bg=white)
+    tw, th = tile
+    fr = pl.render_forward(o, params, cam, degree, tileW=tw, tileH=th, white_bg=white)
     last = fr["fwd"]["lastContrib"].reshape(-1)
-    assert last.max() > 8 * 256 and last.min() < 2 * 256 and (last % 256 == 0).any()   # incl. termination AT a checkpoint
-    bw = pl.backward(o, params, cam, degree, fr, cot, cot_depth, cot_alpha, white_bg=white)
-    ctx = Context(W, H, sh_degree=degree, white_background=white)
+    assert last.max() > 8 * 256
+    if tile == (16, 16):
+        assert last.min() < 2 * 256 and (last % 256 == 0).any()   # incl. termination AT a checkpoint
+    bw = pl.backward(o, params, cam, degree, fr, cot, cot_depth, cot_alpha, tileW=tw, tileH=th, white_bg=white)
+    ctx = Context(W, H, tile_w=tw, tile_h=th, sh_degree=degree, white_background=white)
     dparams = {k: dev(v) for k, v in params.items()}
     render, depth, alpha, vis, radii = ctx.render_forward(dparams, L.make_camera(cam))
     assert np.abs(render.cpu().numpy() - fr["render"]).max() <= PIX_TOL
