@@ -675,6 +675,7 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
         // room for translucent scenes, and an exhausted pool only costs load balance (5 KB per slot)
         const int blocks = gsb::raster_block_count(make_view_nocam(c));
         c->ck.capacity = (uint32_t)std::max(4096, 4 * blocks);
+        if (const char* e = getenv("GSB_CKPT_SLOTS")) c->ck.capacity = (uint32_t)std::max(1, atoi(e));   // tests: force exhaustion
         CREATE_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->ck.state), (size_t)c->ck.capacity * 256 * sizeof(float4)));
         CREATE_CHECK(dev_alloc(&c->ck.depth, (size_t)c->ck.capacity * 256));
         CREATE_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->ck.header), (size_t)c->ck.capacity * sizeof(uint2)));

@@ -316,6 +316,33 @@ def test_segmented_backward_long_lists_vs_oracle(gsb, best_oracle, white, depth_
         assert rel_err(g[k].cpu().numpy(), g0[k].cpu().numpy()) < 1e-4, k
 
 
+def test_segmented_backward_checkpoint_pool_exhausted(gsb, monkeypatch):
+    """With a pool of 7 slots most blocks cannot checkpoint (or stop half way, or get a slot for one of the two a
+    first checkpoint needs): the backward must fall back to longer items and give the same gradients."""
+    Context, L = gsb
+    n, W, H, degree = 6000, 48, 40, 1
+    params = make_gaussians(n, 21, degree)
+    params["_scales"] = params["_scales"] + np.float32(1.1)
+    params["_opacity"] = params["_opacity"] - np.float32(2.0)
+    cam = L.make_camera(make_cameras(W, H, 3)[2])
+    cot = dev(np.random.default_rng(5).standard_normal((H, W, 3)).astype(np.float32))
+    dparams = {k: dev(v) for k, v in params.items()}
+    grads = {}
+    for slots in (None, "7", "2", "1"):
+        if slots is None:
+            monkeypatch.delenv("GSB_CKPT_SLOTS", raising=False)
+        else:
+            monkeypatch.setenv("GSB_CKPT_SLOTS", slots)
+        ctx = Context(W, H, sh_degree=degree)
+        render, *_ = ctx.render_forward(dparams, cam)
+        grads[slots] = ({k: v.clone() for k, v in ctx.render_backward(cot).items()}, render.clone())
+        ctx.close()
+    for slots in ("7", "2", "1"):
+        assert float((grads[slots][1] - grads[None][1]).abs().max()) < 1e-5
+        for k in grads[None][0]:
+            assert rel_err(grads[slots][0][k].cpu().numpy(), grads[None][0][k].cpu().numpy()) < 1e-4, (slots, k)
+
+
 def test_train_steps_vs_oracle(gsb, best_oracle):
     """Three batched train steps (B = 2 views) through gsb_train_step vs the oracle loop."""
     Context, L = gsb
