@@ -143,13 +143,20 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int Crt, const fl
     RowStager<2> st;
     st.img[0] = img1; st.img[1] = img2; st.cimg[0] = img1; st.cimg[1] = img2;
     st.H = H; st.RW = RW; st.e0 = e0; st.halo = SPAD * C; st.nload = SW + 2 * SPAD * C; st.t = t; st.r0 = r0;
-    // MODE 1 needs sigma1^2 + sigma2^2 only as a SUM, so it filters E[a^2 + b^2] as one map (4 maps, not 5)
+    // MODE 1 needs sigma1^2 + sigma2^2 only as a SUM, so it filters E[a^2 + b^2] as one map (4 maps, not 5) - and
+    // keeps the 4 maps as two packed f32x2 pairs (mu1, mu2), (E[a^2 + b^2], E[ab]): one FFMA2 per pair and tap, each
+    // half bit-identical to the scalar fmaf (the kernel is issue-bound)
     constexpr int NQ = MODE == 0 ? 5 : 4;
-    float acc[SK][NQ];
+    constexpr int NP = MODE == 0 ? 1 : 2;   // packed pairs (MODE 1 only)
+    float acc[SK][MODE == 0 ? NQ : 1];
+    f32x2 accp[SK][NP];
 #pragma unroll
-    for (int j = 0; j < SK; ++j)
+    for (int j = 0; j < SK; ++j) {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) acc[j][q] = 0.f;
+        for (int q = 0; q < (MODE == 0 ? NQ : 1); ++q) acc[j][q] = 0.f;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) accp[j][q] = f2_bc(0.f);
+    }
 
     const int rbeg = r0 - SPAD, rend = r1 + SPAD;   // input rows [rbeg, rend)
     st.fetch(rbeg);
@@ -164,21 +171,26 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int Crt, const fl
                 if (r + 1 < rend) st.fetch(r + 1);
                 // ---- horizontal 11 taps of input row r
                 float h[NQ];
+                f32x2 hp[NP];
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) h[q] = 0.f;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) hp[q] = f2_bc(0.f);
 #pragma unroll
                 for (int k = 0; k < SK; ++k) {
                     const float w = win.g[k];
                     const float a = row[0][t + k * C], b = row[1][t + k * C];
-                    h[0] = fmaf(w, a, h[0]);
-                    h[1] = fmaf(w, b, h[1]);
                     if (MODE == 0) {
+                        h[0] = fmaf(w, a, h[0]);
+                        h[1] = fmaf(w, b, h[1]);
                         h[2] = fmaf(w, a * a, h[2]);
                         h[3] = fmaf(w, b * b, h[3]);
                         h[4] = fmaf(w, a * b, h[4]);
                     } else {
-                        h[2] = fmaf(w, fmaf(b, b, a * a), h[2]);
-                        h[3] = fmaf(w, a * b, h[3]);
+                        const f32x2 wb = f2_bc(w), ab = f2_make(a, b);
+                        hp[0] = f2_fma(wb, ab, hp[0]);                            // (mu1, mu2)
+                        const f32x2 pr = f2_mul(ab, f2_bc(a));                     // (a*a, a*b)
+                        hp[1] = f2_fma(wb, f2_make(fmaf(b, b, f2_lo(pr)), f2_hi(pr)), hp[1]);   // (E[a^2 + b^2], E[ab])
                     }
                 }
                 // ---- vertical: input row r feeds output rows r-5 .. r+5; output ro lives in slot (ro - rbeg) % 11
@@ -187,15 +199,23 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int Crt, const fl
                 for (int d = 0; d < SK; ++d) {
                     const int slot = (ph + d + SK - SPAD) % SK;
                     const float w = win.g[SK - 1 - d];
+                    if (MODE == 0) {
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) acc[slot][q] = fmaf(w, h[q], acc[slot][q]);
+                        for (int q = 0; q < NQ; ++q) acc[slot][q] = fmaf(w, h[q], acc[slot][q]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) accp[slot][q] = f2_fma(f2_bc(w), hp[q], accp[slot][q]);
+                    }
                 }
                 // ---- output row ro = r - 5 just received its last tap (d = 0)
                 const int ro = r - SPAD;
                 const int oslot = (ph + SK - SPAD) % SK;
                 if (ro >= r0 && e < RW) {
-                    const float m1 = acc[oslot][0], m2 = acc[oslot][1];
-                    const float e11 = acc[oslot][2], e22 = MODE == 0 ? acc[oslot][3] : 0.f, e12 = acc[oslot][NQ - 1];
+                    const float m1 = MODE == 0 ? acc[oslot][0] : f2_lo(accp[oslot][0]);
+                    const float m2 = MODE == 0 ? acc[oslot][MODE == 0 ? 1 : 0] : f2_hi(accp[oslot][0]);
+                    const float e11 = MODE == 0 ? acc[oslot][MODE == 0 ? 2 : 0] : f2_lo(accp[oslot][NP - 1]);
+                    const float e22 = MODE == 0 ? acc[oslot][MODE == 0 ? 3 : 0] : 0.f;
+                    const float e12 = MODE == 0 ? acc[oslot][MODE == 0 ? 4 : 0] : f2_hi(accp[oslot][NP - 1]);
                     // (MODE 1: e11 carries E[a^2 + b^2], e22 = 0: ssim_point only uses their sum)
                     const SsimPoint sp = ssim_point(m1, m2, e11, e22, e12);
                     const size_t idx = (size_t)ro * RW + e;
@@ -215,7 +235,9 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int Crt, const fl
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) acc[oslot][q] = 0.f;
+                for (int q = 0; q < (MODE == 0 ? NQ : 1); ++q) acc[oslot][q] = 0.f;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) accp[oslot][q] = f2_bc(0.f);
             }
         }
     }
@@ -260,9 +282,11 @@ __global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int Crt, const fl
     RowStager<3> st;
     st.img[0] = mapA; st.img[1] = mapB; st.img[2] = mapC; st.cimg[0] = img1; st.cimg[1] = img2;
     st.H = H; st.RW = RW; st.e0 = e0; st.halo = SPAD * C; st.nload = SW + 2 * SPAD * C; st.t = t; st.r0 = r0;
-    float acc[SK][3];
+    // maps A and B travel as one packed f32x2 pair, C as a scalar
+    f32x2 accp[SK];
+    float acc2[SK];
 #pragma unroll
-    for (int j = 0; j < SK; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; }
+    for (int j = 0; j < SK; ++j) { accp[j] = f2_bc(0.f); acc2[j] = 0.f; }
 
     const int rbeg = r0 - SPAD, rend = r1 + SPAD;
     st.fetch(rbeg);
@@ -275,14 +299,14 @@ __global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int Crt, const fl
                 st.store(row);
                 __syncthreads();
                 if (r + 1 < rend) st.fetch(r + 1);
-                float h[3] = {0.f, 0.f, 0.f};
+                f32x2 hp = f2_bc(0.f);
+                float h2 = 0.f;
 #pragma unroll
                 for (int k = 0; k < SK; ++k) {
                     const float w = win.g[k];
                     const int off = t + (2 * SPAD - k) * C;
-                    h[0] = fmaf(w, row[0][off], h[0]);
-                    h[1] = fmaf(w, row[1][off], h[1]);
-                    h[2] = fmaf(w, row[2][off], h[2]);
+                    hp = f2_fma(f2_bc(w), f2_make(row[0][off], row[1][off]), hp);
+                    h2 = fmaf(w, row[2][off], h2);
                 }
                 // transposed vertical pass: output row ro receives centre row rc = ro + 5 - k with weight g[k];
                 // centre row r feeds ro = r + d - 5 with k = r - ro + 5 ... flipped: k = d
@@ -290,23 +314,22 @@ __global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int Crt, const fl
                 for (int d = 0; d < SK; ++d) {
                     const int slot = (ph + d + SK - SPAD) % SK;
                     const float w = win.g[d];
-                    acc[slot][0] = fmaf(w, h[0], acc[slot][0]);
-                    acc[slot][1] = fmaf(w, h[1], acc[slot][1]);
-                    acc[slot][2] = fmaf(w, h[2], acc[slot][2]);
+                    accp[slot] = f2_fma(f2_bc(w), hp, accp[slot]);
+                    acc2[slot] = fmaf(w, h2, acc2[slot]);
                 }
                 const int ro = r - SPAD;
                 const int oslot = (ph + SK - SPAD) % SK;
                 if (ro >= r0 && e < RW) {
                     const size_t idx = (size_t)ro * RW + e;
                     const float v1 = st.ctr[0], v2 = st.ctr[1];
-                    float g = acc[oslot][0] + 2.0f * v1 * acc[oslot][1] + v2 * acc[oslot][2];
+                    float g = f2_lo(accp[oslot]) + 2.0f * v1 * f2_hi(accp[oslot]) + v2 * acc2[oslot];
                     if (l1_scale != 0.0f) {
                         const float dd = v1 - v2;
                         g += dd > 0.0f ? l1_scale : (dd < 0.0f ? -l1_scale : 0.0f);
                     }
                     grad1[idx] = g;
                 }
-                acc[oslot][0] = 0.f; acc[oslot][1] = 0.f; acc[oslot][2] = 0.f;
+                accp[oslot] = f2_bc(0.f); acc2[oslot] = 0.f;
             }
         }
     }
