@@ -36,6 +36,16 @@ def test_binding_covers_header_both_ways():
     assert set(_lib.SIGNATURES) == set(header_functions())
 
 
+def test_flag_constants_match_header():
+    from gaussiansplattingmlx_b200 import _lib
+    text = (ROOT / "include" / "gsb.h").read_text()
+    flags = dict(re.findall(r"^#define\s+(GSB_FLAG_[A-Z_]+)\s+(\d+)", text, flags=re.M))
+    assert len(flags) >= 4
+    for name, value in flags.items():
+        assert getattr(_lib, name) == int(value), name
+    assert len({int(v) for v in flags.values()}) == len(flags) and all(int(v) & (int(v) - 1) == 0 for v in flags.values())
+
+
 def test_struct_layouts_match_header(lib):
     from gaussiansplattingmlx_b200 import _lib
     assert C.sizeof(_lib.GsbConfig) == 14 * 4
