@@ -31,7 +31,14 @@ namespace gsb {
 
 constexpr int RT = 64;           // forward: threads per CTA (16x16 pixels, 4 per thread)
 constexpr int RB_FWD = 128;      // records per forward batch (6 KB)
-constexpr int RB_BWD = 64;       // records per backward batch
+#ifndef GSB_RB_BWD
+#define GSB_RB_BWD 64
+#endif
+#ifndef GSB_BWD_WARPS
+#define GSB_BWD_WARPS 16
+#endif
+constexpr int RB_BWD = GSB_RB_BWD;   // records per backward batch
+constexpr int BWD_WARPS = GSB_BWD_WARPS;   // resident one-warp CTAs per SM the backward is compiled for (register budget)
 constexpr int BPPT = 8;          // backward: pixels per thread (rows)
 constexpr int BGRP = 3;          // backward: Gaussians per shared-memory reduction round (3 x 10 sums <= 32 lanes)
 constexpr int CK = 256;          // Gaussians between transmittance/colour checkpoints (forward) = backward segment length
@@ -80,6 +87,7 @@ constexpr int FPPT = 4;          // forward: pixels (rows) per thread
 constexpr int FCHUNK = 4;        // Gaussians between termination bookkeeping / warp votes
 static_assert(RB_FWD % FCHUNK == 0, "batch must be a whole number of chunks");
 static_assert(CK % RB_FWD == 0 && CK % RB_BWD == 0, "checkpoints sit on batch boundaries");
+static_assert(RB_BWD == 32 || RB_BWD == 64, "a lane stages one or two records per backward batch");
 
 struct FwdExp {
     float E0, E1, C;
@@ -396,7 +404,7 @@ __global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ V
 // backward
 // ------------------------------------------------------------------------------------------------
 template <bool DEPTH>
-__global__ void __launch_bounds__(32, 16) k_raster_bwd(const __grid_constant__ ViewParams vp,
+__global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_constant__ ViewParams vp,
                                                        const uint32_t* __restrict__ tile_ranges,
                                                        const uint32_t* __restrict__ tile_order,
                                                        const float4* __restrict__ rec, const uint32_t* __restrict__ vals0,
@@ -553,7 +561,7 @@ __global__ void __launch_bounds__(32, 16) k_raster_bwd(const __grid_constant__ V
     auto load_idx = [&](int b) {
         const uint32_t j0 = (uint32_t)b * RB_BWD + lane, j1 = j0 + 32;
         ia = (b >= 0 && j0 < used) ? vals[lstart + j0] : 0xffffffffu;
-        ib = (b >= 0 && j1 < used) ? vals[lstart + j1] : 0xffffffffu;
+        ib = (RB_BWD > 32 && b >= 0 && j1 < used) ? vals[lstart + j1] : 0xffffffffu;
     };
     auto issue = [&](int b) {
         const uint32_t s = seq + (uint32_t)(nb - 1 - b);
@@ -822,7 +830,7 @@ cudaError_t launch_raster_bwd(cudaStream_t st, const ViewParams& vp, const uint3
         if (!res) {
             cudaFuncSetAttribute(k_raster_bwd<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_raster_bwd<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            res = std::max(1, env_int("GSB_BWD_RES", 16));
+            res = std::max(1, env_int("GSB_BWD_RES", BWD_WARPS));
         }
         cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
         if (e != cudaSuccess) return e;
