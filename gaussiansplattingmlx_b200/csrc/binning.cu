@@ -56,7 +56,10 @@ __global__ void k_count_tiles(int N, const __grid_constant__ ViewParams vp, cons
     if (cnt == 0) { x0 = y0 = x1 = y1 = 0; }
     tile_rects[i] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
     touched[i] = cnt;
-    depth_keys[i] = cnt ? __float_as_uint(depths[i]) : 0xffffffffu;   // Gaussians without tiles sort last
+    // Gaussians without tiles emit no pairs, so their place in the depth order is irrelevant: they keep a key in the
+    // range of the others (|depth| clamped to the near plane) instead of 0xffffffff, which would make the top digit
+    // place non-trivial and cost the depth sort a fourth pass
+    depth_keys[i] = __float_as_uint(cnt ? depths[i] : fminf(fmaxf(fabsf(depths[i]), 0.2f), 3.0e38f));
 }
 
 cudaError_t launch_count_tiles(cudaStream_t st, int N, const ViewParams& vp, const float* rectMin, const float* rectMax,

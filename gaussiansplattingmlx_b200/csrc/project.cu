@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(PB) k_project_fused_fwd(int N, const float* __
         if (cnt == 0) { x0 = y0 = x1 = y1 = 0; }
         tile_rects[p] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
         touched[p] = cnt;
-        depth_keys[p] = cnt ? __float_as_uint(o.depth) : 0xffffffffu;   // Gaussians without tiles sort last
+        // Gaussians without tiles emit no pairs, so their place in the depth order is irrelevant: they keep a key in the
+        // range of the others (|depth| clamped to the near plane) instead of 0xffffffff, which would make the top digit
+        // place non-trivial and cost the depth sort a fourth pass
+        depth_keys[p] = __float_as_uint(cnt ? o.depth : fminf(fmaxf(fabsf(o.depth), 0.2f), 3.0e38f));
         if (radii_out) radii_out[p] = o.radius;
         if (vis_out) vis_out[p] = o.radius > 0.0f ? 1 : 0;
     }
