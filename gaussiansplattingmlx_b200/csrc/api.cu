@@ -380,7 +380,7 @@ static int enqueue_binning(Ctx* c, Ctx::ViewBufs& v, cudaStream_t st, int N, con
         } else {
             SortPlan dp = c->dplan;
             dp.capacity = n32;
-            dp.max_tiles = (uint32_t)cdiv(N > 0 ? N : 1, 4096);
+            dp.max_tiles = (uint32_t)cdiv(N > 0 ? N : 1, sort_tile_items());
             GSB_CUDA_CHECK(c, launch_onesweep_sort32(st, dp, v.dkeys[0], v.dkeys[1], v.dvals[0], v.dvals[1], 1, v.d_nvalue,
                                                      v.dsort_ws, &v.d_dresult_buf, &launches));
         }

@@ -136,22 +136,37 @@ __global__ void __launch_bounds__(SC_THREADS) k_exclusive_scan(int N, const uint
         }
         if (lane < SC_THREADS / 32) s_warp[lane] = winc - w;  // exclusive warp prefix
         uint32_t block_total = __shfl_sync(0xffffffffu, winc, SC_THREADS / 32 - 1);
-        if (lane == 0) {
-            uint64_t excl = 0;
-            if (tile == 0) {
-                st_relaxed_u64(&status[0], SC_FLAG_INCL | block_total);
-            } else {
-                st_relaxed_u64(&status[tile], SC_FLAG_LOCAL | block_total);
-                int t = (int)tile - 1;
-                while (true) {
-                    uint64_t s = ld_relaxed_u64(&status[t]);
-                    if ((s >> 62) == 0) continue;
-                    excl += s & SC_VALUE_MASK;
-                    if ((s >> 62) == 2) break;
-                    --t;
-                }
-                st_relaxed_u64(&status[tile], SC_FLAG_INCL | (excl + block_total));
+        // Decoupled look-back, one warp wide: lane i inspects predecessor t - i, so a chain of LOCAL aggregates is
+        // consumed 32 tiles per L2 round trip (a one-thread walk made the scan of 489 tiles a ~50-hop serial chain:
+        // all tiles publish LOCAL at the same time and the INCLUSIVE frontier meets the walkers half way).
+        uint64_t excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st_relaxed_u64(&status[0], SC_FLAG_INCL | block_total);
+        } else {
+            if (lane == 0) st_relaxed_u64(&status[tile], SC_FLAG_LOCAL | block_total);
+            int t = (int)tile - 1;
+            while (true) {
+                const int tt = t - lane;
+                const uint64_t s = tt >= 0 ? ld_relaxed_u64(&status[tt]) : SC_FLAG_INCL;   // virtual tile -1: inclusive 0
+                const uint32_t flag = (uint32_t)(s >> 62);
+                const uint32_t not_ready = __ballot_sync(0xffffffffu, flag == 0);
+                const uint32_t incl = __ballot_sync(0xffffffffu, flag == 2);
+                // lanes [0, stop) can be consumed: up to and including the nearest INCLUSIVE, or up to the first tile
+                // that has not published yet
+                const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
+                const int first_in = incl ? __ffs(incl) - 1 : 32;
+                const bool done = first_in < first_nr;
+                const int stop = done ? first_in + 1 : first_nr;
+                uint64_t part = lane < stop ? (s & SC_VALUE_MASK) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                excl += part;
+                if (done) break;
+                t -= stop;
             }
+            if (lane == 0) st_relaxed_u64(&status[tile], SC_FLAG_INCL | (excl + block_total));
+        }
+        if (lane == 0) {
             s_prefix = (uint32_t)excl;
             if ((long long)(tile + 1) * SC_TILE >= N) *total = (uint32_t)excl + block_total;
         }
@@ -293,10 +308,14 @@ cudaError_t launch_generate_keys(cudaStream_t st, int N, int cellGridW, int cw, 
 // ------------------------------------------------------------------------------------------------
 constexpr int OS_THREADS = 256;
 constexpr int OS_WARPS = OS_THREADS / 32;
-constexpr int OS_IPT = 16;
+#ifndef GSB_OS_IPT
+#define GSB_OS_IPT 16
+#endif
+constexpr int OS_IPT = GSB_OS_IPT;
 constexpr int OS_TILE = OS_THREADS * OS_IPT;  // 4096 pairs per CTA
 constexpr int OS_RADIX = 256;
 constexpr int OS_MAX_PASSES = 8;
+constexpr int OS_LB = 8;           // look-back: predecessors fetched per round trip
 constexpr uint32_t OS_FLAG_LOCAL = 1u << 30;
 constexpr uint32_t OS_FLAG_INCL = 2u << 30;
 constexpr uint32_t OS_VALUE_MASK = (1u << 30) - 1;
@@ -318,6 +337,8 @@ struct SortCtl {
     uint32_t pad[4];
 };
 static_assert(sizeof(SortCtl) == 128, "SortCtl layout");
+
+uint32_t sort_tile_items() { return (uint32_t)OS_TILE; }
 
 SortPlan sort_plan(uint32_t capacity, uint32_t end_bit)
 {
@@ -492,13 +513,32 @@ __global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(int pass, uint32_t dm
             st_relaxed_u32(lb, OS_FLAG_INCL | total_valid);
         } else {
             st_relaxed_u32(lb, OS_FLAG_LOCAL | total_valid);
+            // Decoupled look-back with OS_LB predecessors in flight per round trip: every tile publishes LOCAL at about
+            // the same time, so a one-at-a-time walk is a serial chain of ~tiles/2 L2 latencies (it was most of a
+            // 1 M-key pass); the status rows of a tile are 1 KB apart, one coalesced row per predecessor.
             int t = (int)tile - 1;
-            while (true) {
-                uint32_t v = ld_relaxed_u32(lookback + ((size_t)pass * max_tiles + t) * OS_RADIX + d);
-                if ((v >> 30) == 0) continue;
-                excl_prev += v & OS_VALUE_MASK;
-                if ((v >> 30) == 2) break;
-                --t;
+            const uint32_t* row = lookback + (size_t)pass * max_tiles * OS_RADIX + d;
+            for (bool done = false; !done;) {
+                uint32_t v[OS_LB];
+#pragma unroll
+                for (int k = 0; k < OS_LB; ++k)
+                    v[k] = t - k >= 0 ? ld_relaxed_u32(row + (size_t)(t - k) * OS_RADIX) : OS_FLAG_INCL;   // virtual tile -1
+                int consumed = 0, state = 0;   // 0 consuming, 1 blocked on a tile that has not published, 2 done
+#pragma unroll
+                for (int k = 0; k < OS_LB; ++k) {
+                    const uint32_t f = v[k] >> 30;
+                    if (state == 0) {
+                        if (f == 0) {
+                            state = 1;
+                        } else {
+                            excl_prev += v[k] & OS_VALUE_MASK;
+                            ++consumed;
+                            if (f == 2) state = 2;
+                        }
+                    }
+                }
+                t -= consumed;
+                done = state == 2;
             }
             st_relaxed_u32(lb, OS_FLAG_INCL | (excl_prev + total_valid));
         }

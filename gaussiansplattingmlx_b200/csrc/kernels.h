@@ -74,6 +74,7 @@ struct SortPlan {
     size_t ws_bytes = 0;        // workspace: histograms, look-back state, counters, control block
 };
 SortPlan sort_plan(uint32_t capacity, uint32_t end_bit);
+uint32_t sort_tile_items();   // pairs per onesweep CTA
 // keys/vals double buffers; count read from device *d_count (clamped to capacity).  On return the
 // sorted data sits in buffer index *d_result_buf (device u32 inside the workspace control block,
 // pointer returned via result_buf_ptr).  sort32: iota != 0 synthesises the payload (= element index).
