@@ -308,6 +308,9 @@ cudaError_t launch_generate_keys(cudaStream_t st, int N, int cellGridW, int cw, 
 // ------------------------------------------------------------------------------------------------
 constexpr int OS_THREADS = 256;
 constexpr int OS_WARPS = OS_THREADS / 32;
+#ifndef GSB_OS_HIST_MULT
+#define GSB_OS_HIST_MULT 2
+#endif
 #ifndef GSB_OS_IPT
 #define GSB_OS_IPT 16
 #endif
@@ -595,7 +598,8 @@ static cudaError_t onesweep_impl(cudaStream_t st, const SortPlan& plan, KeyT* ke
     if (result_buf_ptr) *result_buf_ptr = &ctl->result_buf;
     cudaError_t e = cudaMemsetAsync(ws, 0, plan.ws_bytes, st);
     if (e != cudaSuccess) return e;
-    int hist_blocks = (int)std::min<uint32_t>(plan.max_tiles, 148u * 8u);
+    // the histogram is latency-bound (load -> shared atomics per key): a few keys per thread, up to one full wave of CTAs
+    int hist_blocks = (int)std::min<uint32_t>(plan.max_tiles * (uint32_t)GSB_OS_HIST_MULT, 148u * 8u);
     k_os_histogram<KeyT><<<hist_blocks, 256, 0, st>>>(keys0, d_count, plan.capacity, (int)plan.passes, (int)plan.end_bit, hist);
     k_os_scan<<<1, OS_RADIX, 0, st>>>(ctl, hist, d_count, plan.capacity, (int)plan.passes);
     static bool attr_set = false;
