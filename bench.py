@@ -417,7 +417,10 @@ def run_gsb(args, rank, local_rank, world):
                 "frac": d["frac"], "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
                 "peak_source": (f"{peaks['source']} MEASURED_PEAKS.json hbm_gbs" if d["bound"] == "hbm" else
                                 f"non-tensor FP32 pipe: 148 SM x 128 lanes x 2 flop x sm_max_mhz ({peaks['source']}); "
-                                "no measured FP32 figure exists in MEASURED_PEAKS.json"),
+                                "no measured FP32 figure exists in MEASURED_PEAKS.json; tools/microbench/f32x2_rate.cu "
+                                "measured 71.5 TFLOP/s (123 of 128 fma/clk/SM) on this pool (profiles/f32x2_rate.txt)"),
+                "peak_measured": 71.54 if d["bound"] == "fp32" else None,
+                "frac_of_measured": (d["achieved"] / 71.54) if d["bound"] == "fp32" else None,
                 "units_per_launch": {"pairs_M": M, "superblock_pairs_L1": L1, "blend_evals_E": E, "gaussians": n, "pixels": P},
                 "timing": "CUDA-event pairs around every launch on the library's work stream, averaged over a second pass of "
                           "the same steps with the view pipeline disabled (kernels back to back); share_of_step is relative to "
