@@ -715,8 +715,11 @@ __global__ void __launch_bounds__(TO_THREADS) k_tile_order(int numTiles, const u
     __shared__ uint32_t s_warp[TO_THREADS / 32];
     __shared__ uint32_t s_max;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    auto count_of = [&](int t) { uint32_t a = ranges[t * 2], b = ranges[t * 2 + 1]; return b > a ? b - a : 0u; };
+    // one 8-byte load per tile, four tiles in flight per thread: the kernel is a chain of dependent L2 round trips
+    const uint2* __restrict__ ranges2 = reinterpret_cast<const uint2*>(ranges);
+    auto count_of = [&](int t) { const uint2 r = __ldg(ranges2 + t); return r.y > r.x ? r.y - r.x : 0u; };
     uint32_t mx = 0;
+#pragma unroll 4
     for (int t = tid; t < numTiles; t += TO_THREADS) mx = max(mx, count_of(t));
     mx = __reduce_max_sync(0xffffffffu, mx);
     if (lane == 0) s_warp[warp] = mx;
@@ -730,6 +733,7 @@ __global__ void __launch_bounds__(TO_THREADS) k_tile_order(int numTiles, const u
     __syncthreads();
     const uint32_t maxc = max(s_max, 1u);
     auto bucket_of = [&](uint32_t c) { return (uint32_t)(TO_BUCKETS - 1) - (uint32_t)(((unsigned long long)c * (TO_BUCKETS - 1)) / maxc); };
+#pragma unroll 4
     for (int t = tid; t < numTiles; t += TO_THREADS) atomicAdd(&s_hist[bucket_of(count_of(t))], 1u);
     __syncthreads();
     // exclusive scan of the buckets: thread tid owns buckets [4 tid, 4 tid + 4)
@@ -751,6 +755,7 @@ __global__ void __launch_bounds__(TO_THREADS) k_tile_order(int numTiles, const u
 #pragma unroll
     for (int i = 0; i < PER; ++i) { s_hist[tid * PER + i] = run; run += v[i]; }
     __syncthreads();
+#pragma unroll 4
     for (int t = tid; t < numTiles; t += TO_THREADS) order[atomicAdd(&s_hist[bucket_of(count_of(t))], 1u)] = (uint32_t)t;
 }
 
