@@ -31,6 +31,9 @@ namespace gsb {
 
 constexpr int RT = 64;           // forward: threads per CTA (16x16 pixels, 4 per thread)
 constexpr int RB_FWD = 128;      // records per forward batch (6 KB)
+#ifndef GSB_FWD_CTAS
+#define GSB_FWD_CTAS 12
+#endif
 #ifndef GSB_RB_BWD
 #define GSB_RB_BWD 64
 #endif
@@ -127,7 +130,7 @@ __device__ __forceinline__ float fwd_alpha_rt(const FwdExp& e, int r)
 // measured on B200, capping the residency below the register limit to leave them room does not pay
 // (tools/sweep_res.sh: 12/16 CTAs per SM beats 9/12), so the defaults fill the SM.
 template <bool DEPTH>
-__global__ void __launch_bounds__(RT, 12) k_raster_fwd(const __grid_constant__ ViewParams vp,
+__global__ void __launch_bounds__(RT, GSB_FWD_CTAS) k_raster_fwd(const __grid_constant__ ViewParams vp,
                                                        const uint32_t* __restrict__ tile_ranges,
                                                        const uint32_t* __restrict__ tile_order,
                                                        const float4* __restrict__ rec, const uint32_t* __restrict__ vals0,
@@ -797,7 +800,7 @@ cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint3
         if (!res) {
             cudaFuncSetAttribute(k_raster_fwd<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_raster_fwd<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            res = std::max(1, env_int("GSB_FWD_RES", 12));
+            res = std::max(1, env_int("GSB_FWD_RES", GSB_FWD_CTAS));   // resident 64-thread CTAs per SM the forward is compiled for
         }
         cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
         if (e != cudaSuccess) return e;
