@@ -12,6 +12,8 @@
 //     grad1(p) = convT(A)(p) + 2*v1(p)*convT(B)(p) + v2(p)*convT(C)(p)
 // which is exactly what the reference's gather (ssim_kernels.slang:214-262) sums.
 // FP32-pipe work: ~225 flop (fwd) / ~170 flop (bwd) per pixel-channel; HWC f32 images.
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace gsb {
@@ -63,7 +65,7 @@ __device__ __forceinline__ SsimPoint ssim_point(float mu1, float mu2, float e11,
 // ------------------------------------------------------------------------------------------------
 // Streaming separable convolution.  The HWC image is treated as H rows of W*C floats; a horizontal tap
 // k of the per-channel window sits at element offset (k - 5) * C.  A CTA owns a strip of SW consecutive
-// row elements and a chunk of SROWS output rows and marches down the rows.  Per input row:
+// row elements and a chunk of `srows` output rows (chosen by the launcher so that the grid is one full wave) and marches down the rows.  Per input row:
 //   * the strip (+ 5*C halo on both sides) is staged in shared memory, one barrier per row (two row
 //     buffers alternate; row r+1 is fetched into registers while row r is filtered);
 //   * each thread filters its element horizontally (11 taps: the only shared-memory reads, 22 per
@@ -76,7 +78,7 @@ __device__ __forceinline__ SsimPoint ssim_point(float mu1, float mu2, float e11,
 // MODE 1: training (writes upstream-scaled A/B/C maps, accumulates sum|d| and sum(ssim))
 // ------------------------------------------------------------------------------------------------
 constexpr int SW = 128;        // strip width in floats = threads per CTA (1080p: 5760 = 45 strips)
-constexpr int SROWS = 72;      // output rows per CTA (1080 = 15 chunks)
+constexpr int SROWS_MIN = 24;  // fewest output rows per CTA (10 halo rows are filtered on top of them)
 constexpr int SMAXC = 4;       // channels supported by the halo buffer
 constexpr int SHALO = SPAD * SMAXC;
 
@@ -129,17 +131,17 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int Crt, const fl
                                                  const float* __restrict__ img2, const __grid_constant__ SsimWindow win,
                                                  float upstream, float* __restrict__ o0, float* __restrict__ o1,
                                                  float* __restrict__ o2, float* __restrict__ o3, float* __restrict__ o4,
-                                                 float* __restrict__ o5, double* __restrict__ partial)
+                                                 float* __restrict__ o5, double* __restrict__ partial, int srows)
 {
     __shared__ float s_row[4][SW + 2 * SHALO];   // [parity][image]
     __shared__ double s_red[2][SW / 32];
     const int C = CT ? CT : Crt;
     const int RW = W * C;                          // floats per image row
     const int e0 = blockIdx.x * SW;                // first row element of the strip
-    const int r0 = blockIdx.y * SROWS, r1 = min(r0 + SROWS, H);
+    const int r0 = blockIdx.y * srows, r1 = min(r0 + srows, H);
     const int t = threadIdx.x;
     const int e = e0 + t;
-    float accL1 = 0.f, accS = 0.f;               // <= SROWS terms each per thread: f32 is ample
+    float accL1 = 0.f, accS = 0.f;               // <= srows terms each per thread: f32 is ample
     RowStager<2> st;
     st.img[0] = img1; st.img[1] = img2; st.cimg[0] = img1; st.cimg[1] = img2;
     st.H = H; st.RW = RW; st.e0 = e0; st.halo = SPAD * C; st.nload = SW + 2 * SPAD * C; st.t = t; st.r0 = r0;
@@ -270,13 +272,13 @@ __global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int Crt, const fl
                                                  const float* __restrict__ img2, const float* __restrict__ mapA,
                                                  const float* __restrict__ mapB, const float* __restrict__ mapC,
                                                  const __grid_constant__ SsimWindow win, float l1_scale,
-                                                 float* __restrict__ grad1)
+                                                 float* __restrict__ grad1, int srows)
 {
     __shared__ float s_row[6][SW + 2 * SHALO];   // [parity][map]
     const int C = CT ? CT : Crt;
     const int RW = W * C;
     const int e0 = blockIdx.x * SW;
-    const int r0 = blockIdx.y * SROWS, r1 = min(r0 + SROWS, H);
+    const int r0 = blockIdx.y * srows, r1 = min(r0 + srows, H);
     const int t = threadIdx.x;
     const int e = e0 + t;
     RowStager<3> st;
@@ -364,13 +366,29 @@ static const SsimWindow& window()
     return w;
 }
 
+// Output rows per CTA: every CTA walks its rows serially, so the kernel lasts as long as one CTA; the image is cut into
+// as many row chunks as fit in ONE wave of resident CTAs (occupancy x SM count / strips), but not below SROWS_MIN rows
+// (each chunk filters 10 halo rows on top of its own).
+template <typename K>
+static int rows_per_cta(K kernel, int H, int strips)
+{
+    int dev = 0, sms = 148, per_sm = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SW, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    const int chunks = std::max(1, (sms * per_sm) / std::max(strips, 1));
+    return std::max(SROWS_MIN, cdiv(H, chunks));
+}
+
 cudaError_t launch_ssim_fwd(cudaStream_t st, int H, int W, int C, const float* img1, const float* img2, float* ssim_map,
                             float* mu1, float* mu2, float* s1, float* s2, float* s12)
 {
     if (H <= 0 || W <= 0 || C <= 0) return cudaSuccess;
-    dim3 grid(cdiv((long long)W * C, SW), cdiv(H, SROWS));
-    if (C == 3) k_ssim_fwd<0, 3><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, ssim_map, mu1, mu2, s1, s2, s12, nullptr);
-    else k_ssim_fwd<0, 0><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, ssim_map, mu1, mu2, s1, s2, s12, nullptr);
+    const int strips = cdiv((long long)W * C, SW);
+    const int srows = C == 3 ? rows_per_cta(k_ssim_fwd<0, 3>, H, strips) : rows_per_cta(k_ssim_fwd<0, 0>, H, strips);
+    dim3 grid(strips, cdiv(H, srows));
+    if (C == 3) k_ssim_fwd<0, 3><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, ssim_map, mu1, mu2, s1, s2, s12, nullptr, srows);
+    else k_ssim_fwd<0, 0><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, ssim_map, mu1, mu2, s1, s2, s12, nullptr, srows);
     return cudaGetLastError();
 }
 
@@ -380,11 +398,13 @@ cudaError_t launch_loss_fwd(cudaStream_t st, int H, int W, int C, const float* r
     cudaError_t e = cudaMemsetAsync(partial, 0, 2 * sizeof(double), st);
     if (e != cudaSuccess) return e;
     if (H <= 0 || W <= 0 || C <= 0) return cudaSuccess;
-    dim3 grid(cdiv((long long)W * C, SW), cdiv(H, SROWS));
+    const int strips = cdiv((long long)W * C, SW);
+    const int srows = C == 3 ? rows_per_cta(k_ssim_fwd<1, 3>, H, strips) : rows_per_cta(k_ssim_fwd<1, 0>, H, strips);
+    dim3 grid(strips, cdiv(H, srows));
     if (C == 3) k_ssim_fwd<1, 3><<<grid, SW, 0, st>>>(H, W, C, render, target, window(), upstream, mapA, mapB, mapC, nullptr, nullptr,
-                                                      nullptr, partial);
+                                                      nullptr, partial, srows);
     else k_ssim_fwd<1, 0><<<grid, SW, 0, st>>>(H, W, C, render, target, window(), upstream, mapA, mapB, mapC, nullptr, nullptr,
-                                               nullptr, partial);
+                                               nullptr, partial, srows);
     return cudaGetLastError();
 }
 
@@ -392,9 +412,11 @@ cudaError_t launch_loss_bwd(cudaStream_t st, int H, int W, int C, const float* r
                             const float* mapA, const float* mapB, const float* mapC, float l1_scale, float* cot_render)
 {
     if (H <= 0 || W <= 0 || C <= 0) return cudaSuccess;
-    dim3 grid(cdiv((long long)W * C, SW), cdiv(H, SROWS));
-    if (C == 3) k_ssim_bwd<3><<<grid, SW, 0, st>>>(H, W, C, render, target, mapA, mapB, mapC, window(), l1_scale, cot_render);
-    else k_ssim_bwd<0><<<grid, SW, 0, st>>>(H, W, C, render, target, mapA, mapB, mapC, window(), l1_scale, cot_render);
+    const int strips = cdiv((long long)W * C, SW);
+    const int srows = C == 3 ? rows_per_cta(k_ssim_bwd<3>, H, strips) : rows_per_cta(k_ssim_bwd<0>, H, strips);
+    dim3 grid(strips, cdiv(H, srows));
+    if (C == 3) k_ssim_bwd<3><<<grid, SW, 0, st>>>(H, W, C, render, target, mapA, mapB, mapC, window(), l1_scale, cot_render, srows);
+    else k_ssim_bwd<0><<<grid, SW, 0, st>>>(H, W, C, render, target, mapA, mapB, mapC, window(), l1_scale, cot_render, srows);
     return cudaGetLastError();
 }
 
@@ -409,14 +431,18 @@ cudaError_t launch_ssim_bwd_api(cudaStream_t st, int H, int W, int C, const floa
                                 const float* img2, float* mapA, float* mapB, float* mapC, float* grad_img1)
 {
     if (H <= 0 || W <= 0 || C <= 0) return cudaSuccess;
-    dim3 grid(cdiv((long long)W * C, SW), cdiv(H, SROWS));
+    const int strips = cdiv((long long)W * C, SW);
+    const int srows = C == 3 ? rows_per_cta(k_ssim_fwd<1, 3>, H, strips) : rows_per_cta(k_ssim_fwd<1, 0>, H, strips);
+    dim3 grid(strips, cdiv(H, srows));
     // maps with unit upstream, then scaled by the caller's per-centre gradient
-    if (C == 3) k_ssim_fwd<1, 3><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, mapA, mapB, mapC, nullptr, nullptr, nullptr, nullptr);
-    else k_ssim_fwd<1, 0><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, mapA, mapB, mapC, nullptr, nullptr, nullptr, nullptr);
+    if (C == 3) k_ssim_fwd<1, 3><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, mapA, mapB, mapC, nullptr, nullptr, nullptr, nullptr, srows);
+    else k_ssim_fwd<1, 0><<<grid, SW, 0, st>>>(H, W, C, img1, img2, window(), 1.0f, mapA, mapB, mapC, nullptr, nullptr, nullptr, nullptr, srows);
     const size_t n = (size_t)H * W * C;
     k_scale_maps<<<cdiv((long long)n, 256), 256, 0, st>>>(n, grad_out, mapA, mapB, mapC);
-    if (C == 3) k_ssim_bwd<3><<<grid, SW, 0, st>>>(H, W, C, img1, img2, mapA, mapB, mapC, window(), 0.0f, grad_img1);
-    else k_ssim_bwd<0><<<grid, SW, 0, st>>>(H, W, C, img1, img2, mapA, mapB, mapC, window(), 0.0f, grad_img1);
+    const int srows_b = C == 3 ? rows_per_cta(k_ssim_bwd<3>, H, strips) : rows_per_cta(k_ssim_bwd<0>, H, strips);
+    dim3 grid_b(strips, cdiv(H, srows_b));
+    if (C == 3) k_ssim_bwd<3><<<grid_b, SW, 0, st>>>(H, W, C, img1, img2, mapA, mapB, mapC, window(), 0.0f, grad_img1, srows_b);
+    else k_ssim_bwd<0><<<grid_b, SW, 0, st>>>(H, W, C, img1, img2, mapA, mapB, mapC, window(), 0.0f, grad_img1, srows_b);
     return cudaGetLastError();
 }
 
