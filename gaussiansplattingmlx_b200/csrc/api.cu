@@ -268,6 +268,10 @@ static void sync_all_streams(Ctx* c)
 static int ensure_gaussians(Ctx* c, int N)
 {
     if (N <= c->capN) return GSB_OK;
+    if ((uint32_t)N > gsb::REC_IDX_MASK) {   // the two top bits of a record's index word are flags (common.cuh)
+        set_error(c, "more than 2^30 Gaussians are not supported");
+        return GSB_ERR_INVALID;
+    }
     if (c->cfg.max_gaussians > 0 && N > c->cfg.max_gaussians) {
         set_error(c, "N exceeds gsb_config.max_gaussians");
         return GSB_ERR_INVALID;
