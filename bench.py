@@ -229,7 +229,22 @@ def run_gsb(args, rank, local_rank, world):
     gcams = [_lib.make_camera(cams[v]) for v in my_views]
     host_targets = [torch.from_numpy(targets[v]).pin_memory() for v in my_views]
     dev_targets = [t.to(dev, non_blocking=True) for t in host_targets]
-    dp_state = {"grad_block": ctx.trainer_grad_block() if world > 1 else None}
+    dp_state = {"grad_block": ctx.trainer_grad_block() if world > 1 else None, "peers": False}
+    vp_dp = None
+    if world > 1:
+        # the data-parallel step fused with its collective over NVLink peer memory (GSB_DP=nccl: all-reduce + Adam)
+        from gaussiansplattingmlx_b200.dp import ViewParallel
+        vp_dp = ViewParallel(rank, world)
+        # GSB_DP = peers (default: one kernel over NVLink peer memory) | multicast (NVLS through torch symmetric memory;
+        # measured slower: 0.86 vs 0.72 ms per step at 8 GPUs) | nccl (all-reduce + Adam on every replica)
+        want = os.environ.get("GSB_DP", "peers")
+        dp_state["mode"] = "nccl"
+        if want == "multicast" and vp_dp.enable_multicast(ctx):
+            dp_state["mode"] = "multicast"
+        elif want in ("multicast", "peers") and vp_dp.enable_peers(ctx):
+            dp_state["mode"] = "peers"
+        dp_state["peers"] = dp_state["mode"] != "nccl"
+        log(f"[rank {rank}] data-parallel step: {dp_state['mode']}")
     total_iters = 30000
     gscale = 1.0 / views
 
@@ -256,9 +271,14 @@ def run_gsb(args, rank, local_rank, world):
                 loss_events[slot].record()
             else:
                 ctx.trainer_accumulate(gcams, tg, zero_grads=True, grad_scale=gscale, want_loss=False)
-        if world > 1:
-            dist.all_reduce(dp_state["grad_block"])
-        ctx.trainer_apply(it, total_iters, reset_state=False)
+        if dp_state.get("mode") == "multicast":
+            vp_dp.multicast_step(ctx, it, total_iters)
+        elif dp_state.get("mode") == "peers":
+            vp_dp.peer_step(ctx, it, total_iters)
+        else:
+            if world > 1:
+                dist.all_reduce(dp_state["grad_block"])
+            ctx.trainer_apply(it, total_iters, reset_state=False)
         if want_loss and my_views:
             drain_loss()                       # the PREVIOUS step's loss: its copy finished long ago
             e2e_state["pending"] = it & 1
@@ -295,6 +315,8 @@ def run_gsb(args, rank, local_rank, world):
         barrier()
         ctx.trainer_init(host_params)
         if world > 1:
+            if dp_state.get("mode") == "multicast":
+                assert vp_dp.enable_multicast(ctx)      # trainer_init moved the parameters back into the slab: re-attach
             dp_state["grad_block"] = ctx.trainer_grad_block()
         for i in range(args.warmup):
             step(i, host, want_loss)
@@ -436,11 +458,20 @@ def run_gsb(args, rank, local_rank, world):
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak" if (weak or world == 1 and args.scaling == "weak") else "strong",
            "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "config": workload_config(wl, params, per_step, world, views),
+           "data": "synthetic", "config": dict(workload_config(wl, params, per_step, world, views),
+                                               **({"dp_step": {"multicast": "one kernel through the NVSwitch (symmetric memory): multimem.ld_reduce of the "
+                                                                           "owned gradient slice + Adam + multimem.st of the new parameters, "
+                                                                           "between two 4-byte NCCL barriers",
+                                                              "peers": "one kernel over NVLink peer memory: reduce the gradient slices of all "
+                                                                       "replicas + Adam + store the parameters into every replica, between two "
+                                                                       "4-byte NCCL barriers",
+                                                              "nccl": "NCCL all-reduce of the 236 MB gradient block + Adam on every replica"}[
+                                                       dp_state.get("mode", "nccl")]}
+                                                  if world > 1 else {})),
            "views_per_s": value * per_step,
            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                    "h2d_bytes_per_step": img_bytes * views, "d2h_bytes_per_step": 4 * world,
-                   "api": "Context.trainer_accumulate(pinned host targets, pinned loss slot) [+ NCCL all_reduce] + trainer_apply; "
+                   "api": "Context.trainer_accumulate(pinned host targets, pinned loss slot) + trainer_apply [N > 1: dp.ViewParallel.peer_step]; "
                           "every step's loss is copied D2H asynchronously and read on the host one step later"},
            "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_kernels": kernels,
            "ms_per_step_serialized": ms_serial / K,

@@ -20,6 +20,7 @@ GSB_FLAG_SORT_CUB = 1
 GSB_FLAG_NO_OVERLAP = 2
 GSB_FLAG_ASYNC_LOSS = 4
 GSB_FLAG_NO_SEGMENTS = 8
+GSB_PEER_BLOB_BYTES = 256
 STAGE_COUNT = 12
 
 
@@ -83,6 +84,11 @@ SIGNATURES = {
     "gsb_trainer_grad_block": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "gsb_trainer_accumulate": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), _I, _I, _F, _P]),
     "gsb_trainer_apply": (C.c_int, [_P, _I, _I, _I]),
+    "gsb_trainer_peers_export": (C.c_int, [_P, _P, C.c_int64]),
+    "gsb_trainer_peers_import": (C.c_int, [_P, _I, _I, _P, C.c_int64]),
+    "gsb_trainer_apply_peers": (C.c_int, [_P, _I, _I, _I]),
+    "gsb_trainer_attach_symmetric": (C.c_int, [_P, _I, _I, _P, _P, _P, _P, C.c_int64]),
+    "gsb_trainer_apply_multicast": (C.c_int, [_P, _I, _I, _I]),
     "gsb_train_step": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), _I, _I, _I, C.POINTER(_F)]),
     "gsb_densify_classify": (C.c_int, [_P, _I, _P, _F, _P, _P, _F, _F, _F, _I, _P, _P]),
     "gsb_densify_map": (C.c_int, [_P, _I, _P, _P, _P, _I, _P, _P, C.POINTER(_I)]),

@@ -319,6 +319,35 @@ class Context:
         self._sync_stream()
         self._check(self.lib.gsb_trainer_apply(self.h, iteration, total_iterations, int(reset_state)))
 
+    # ---- peer-memory data parallelism (gsb.h: gsb_trainer_peers_*) -------------------------------
+    def trainer_peers_export(self) -> bytes:
+        """This replica's IPC blob (trainer slab handles + layout); exchange the blobs of all ranks, in rank order."""
+        buf = C.create_string_buffer(_lib.GSB_PEER_BLOB_BYTES)
+        self._check(self.lib.gsb_trainer_peers_export(self.h, C.cast(buf, C.c_void_p), _lib.GSB_PEER_BLOB_BYTES))
+        return buf.raw
+
+    def trainer_peers_import(self, world: int, rank: int, blobs: Sequence[bytes]):
+        assert len(blobs) == world and all(len(b) == _lib.GSB_PEER_BLOB_BYTES for b in blobs)
+        buf = C.create_string_buffer(b"".join(blobs), world * _lib.GSB_PEER_BLOB_BYTES)
+        self._check(self.lib.gsb_trainer_peers_import(self.h, world, rank, C.cast(buf, C.c_void_p), _lib.GSB_PEER_BLOB_BYTES))
+
+    def trainer_apply_peers(self, iteration: int, total_iterations: int, reset_state: bool = False):
+        """Fused gradient reduction + Adam + parameter broadcast over NVLink peer memory; the caller brackets it with
+        two stream-ordered barriers (see dp.ViewParallel.peer_step)."""
+        self._sync_stream()
+        self._check(self.lib.gsb_trainer_apply_peers(self.h, iteration, total_iterations, int(reset_state)))
+
+    def trainer_attach_symmetric(self, world: int, rank: int, params_local: int, grads_local: int, params_mc: int, grads_mc: int,
+                                 floats: int):
+        """Device addresses (ints) of this replica's symmetric parameter / gradient buffers and of their multicast mappings."""
+        self._sync_stream()
+        self._check(self.lib.gsb_trainer_attach_symmetric(self.h, world, rank, C.c_void_p(params_local), C.c_void_p(grads_local),
+                                                          C.c_void_p(params_mc), C.c_void_p(grads_mc), int(floats)))
+
+    def trainer_apply_multicast(self, iteration: int, total_iterations: int, reset_state: bool = False):
+        self._sync_stream()
+        self._check(self.lib.gsb_trainer_apply_multicast(self.h, iteration, total_iterations, int(reset_state)))
+
     def train_step(self, cams, targets, iteration: int, total_iterations: int, want_loss: bool = True) -> Optional[float]:
         self._sync_stream()
         B, cam_arr, tp, on_host = self._cams_targets(cams, targets)

@@ -7,6 +7,8 @@
 // and accum_grad_norm (GaussianTrainer.swift:321-339): accum[i] += ||grad_xyz_i||_2.
 // HBM-bound: 28 B per parameter float (read p,g,m,v; write p,m,v).  Compiled with --fmad=false so
 // the update rounds exactly like the CPU oracle (bit-exact Adam parity).
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace gsb {
@@ -75,6 +77,226 @@ __global__ void __launch_bounds__(AD_THREADS) k_adam(const __grid_constant__ Ada
             grad_norm_accum[i] = grad_norm_accum[i] + sqrtf(a * a + b * b + c * c);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Data-parallel step fused with its collective: gradient reduction + Adam + parameter broadcast in ONE
+// kernel over NVLink peer memory.  Rank r owns the Gaussians [g0, g1) of every tensor: it sums that slice of the gradient
+// blocks of ALL ranks (peer loads, fixed rank order, so the sum has one owner and no replica can diverge), applies Adam
+// with its local m / v / p, and stores the new parameters into every rank's replica (peer stores).  Per rank and step
+// this moves (world - 1) / world of the gradient block in and of the parameter block out over NVLink - what a
+// reduce-scatter + all-gather moves - and 1 / world of Adam's HBM traffic, with no staging buffers and no second pass.
+// The caller brackets the launch with two stream-ordered barriers (all gradients complete / all replicas written).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AD_THREADS, 4) k_adam_peers(const __grid_constant__ AdamTensors t, const __grid_constant__ AdamPeers pr,
+                                                           const __grid_constant__ AdamSeg seg, float b1, float b2, float eps,
+                                                           float gscale)
+{
+    const long long total = seg.vec_begin[6];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // chunk i of the owned slice -> tensor k, float offset inside the tensor / inside one copy of the six tensors
+    auto locate = [&](long long i, int& k, long long& base, long long& off) {
+        k = 0;
+#pragma unroll
+        for (int j = 1; j < 6; ++j) k += (i >= seg.vec_begin[j]) ? 1 : 0;
+        base = pr.first[k] + (i - seg.vec_begin[k]) * 4;   // the slice starts on a multiple of 4 floats
+        off = pr.tensor_off[k] + base;
+    };
+    // Software pipeline: the peer loads of chunk i + stride are in flight while chunk i is updated and stored to every
+    // replica, so NVLink carries gradients in and parameters out at the same time (a load-all / store-all loop
+    // alternates the two directions: 0.73 ms instead of 0.5 ms per step at 8 GPUs).
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 gn[GSB_MAX_PEERS];
+    bool vec_n = false;
+    auto prefetch = [&](long long ii) {
+        int k; long long base, off;
+        locate(ii, k, base, off);
+        vec_n = base + 4 <= pr.first[k] + t.count[k];
+        if (vec_n) {
+#pragma unroll
+            for (int r = 0; r < GSB_MAX_PEERS; ++r)
+                if (r < pr.world) gn[r] = __ldcg(reinterpret_cast<const float4*>(pr.grads[r] + off));
+        }
+    };
+    if (i < total) prefetch(i);
+    while (i < total) {
+        int k; long long base, off;
+        locate(i, k, base, off);
+        const long long end = pr.first[k] + t.count[k];   // t.count = floats of the slice
+        const float lr = t.lr[k];
+        float* m = t.m[k] + base;
+        float* v = t.v[k] + base;
+        const bool vec = vec_n;
+        float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec) {
+#pragma unroll
+            for (int r = 0; r < GSB_MAX_PEERS; ++r)
+                if (r < pr.world) { G.x += gn[r].x; G.y += gn[r].y; G.z += gn[r].z; G.w += gn[r].w; }
+        }
+        const long long inext = i + stride;
+        if (inext < total) prefetch(inext);
+        if (vec) {
+            float4 P = *reinterpret_cast<const float4*>(t.p[k] + base);
+            float4 M = *reinterpret_cast<float4*>(m);
+            float4 V = *reinterpret_cast<float4*>(v);
+            G.x = G.x * gscale; G.y = G.y * gscale; G.z = G.z * gscale; G.w = G.w * gscale;
+            adam1(P.x, G.x, M.x, V.x, lr, b1, b2, eps);
+            adam1(P.y, G.y, M.y, V.y, lr, b1, b2, eps);
+            adam1(P.z, G.z, M.z, V.z, lr, b1, b2, eps);
+            adam1(P.w, G.w, M.w, V.w, lr, b1, b2, eps);
+            *reinterpret_cast<float4*>(m) = M;
+            *reinterpret_cast<float4*>(v) = V;
+            for (int r = 0; r < pr.world; ++r) *reinterpret_cast<float4*>(pr.params[r] + off) = P;
+        } else {
+            for (long long e = 0; base + e < end; ++e) {
+                float g = 0.f;
+                for (int r = 0; r < pr.world; ++r) g += __ldcg(pr.grads[r] + off + e);
+                float pp = t.p[k][base + e], mm = m[e], vv = v[e];
+                adam1(pp, g * gscale, mm, vv, lr, b1, b2, eps);
+                m[e] = mm; v[e] = vv;
+                for (int r = 0; r < pr.world; ++r) pr.params[r][off + e] = pp;
+            }
+        }
+        i = inext;
+    }
+    // D1 for the owned Gaussians: the norm of the SUMMED position gradient, written to every replica's accumulator
+    if (pr.accum[0]) {
+        for (long long i = pr.g0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pr.g1; i += stride) {
+            float a = 0.f, b = 0.f, c = 0.f;
+            for (int r = 0; r < pr.world; ++r) {
+                const float* gx = pr.grads[r] + pr.tensor_off[0] + i * 3;
+                a += __ldcg(gx); b += __ldcg(gx + 1); c += __ldcg(gx + 2);
+            }
+            a *= gscale; b *= gscale; c *= gscale;
+            const float acc = pr.accum[pr.rank][i] + sqrtf(a * a + b * b + c * c);
+            for (int r = 0; r < pr.world; ++r) pr.accum[r][i] = acc;
+        }
+    }
+}
+
+cudaError_t launch_adam_peers(cudaStream_t st, const AdamTensors& t, const AdamPeers& pr, float beta1, float beta2, float eps,
+                              float gscale, int* launches)
+{
+    AdamSeg seg;
+    seg.vec_begin[0] = 0;
+    for (int k = 0; k < 6; ++k) seg.vec_begin[k + 1] = seg.vec_begin[k] + (t.count[k] + 3) / 4;
+    const long long total = seg.vec_begin[6];
+    if (total == 0 && pr.g1 <= pr.g0) return cudaSuccess;
+    long long blocks = (std::max<long long>(total, 1) + AD_THREADS - 1) / AD_THREADS;
+    const long long cap = 148LL * 4;   // persistent: one resident wave (4 CTAs per SM), every thread pipelines its chunks
+    if (blocks > cap) blocks = cap;
+    k_adam_peers<<<(int)blocks, AD_THREADS, 0, st>>>(t, pr, seg, beta1, beta2, eps, gscale);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same step through the NVSwitch (NVLS): the gradient and parameter blocks of all replicas are bound to ONE multicast
+// address range (symmetric memory).  multimem.ld_reduce returns the SUM over all replicas of a 16-byte chunk - the switch
+// adds, one read crosses this GPU's links - and multimem.st writes a chunk into every replica.  Rank r still owns slice r:
+// per step it pulls 1 / world of the gradient block (already reduced) and pushes 1 / world of the parameter block, instead
+// of (world - 1) / world each with plain peer loads / stores.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 mc_ld_reduce_v4(const float* mc)
+{
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ float mc_ld_reduce(const float* mc)
+{
+    float v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st_v4(float* mc, const float4& v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mc_st(float* mc, float v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(AD_THREADS) k_adam_multicast(const __grid_constant__ AdamTensors t, const __grid_constant__ AdamPeers pr,
+                                                               const __grid_constant__ AdamSeg seg, const float* __restrict__ mc_grads,
+                                                               float* __restrict__ mc_params, float b1, float b2, float eps, float gscale,
+                                                               int N)
+{
+    const long long total = seg.vec_begin[6];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int k = 0;
+#pragma unroll
+        for (int j = 1; j < 6; ++j) k += (i >= seg.vec_begin[j]) ? 1 : 0;
+        const long long base = pr.first[k] + (i - seg.vec_begin[k]) * 4;
+        const long long end = pr.first[k] + t.count[k];
+        const long long off = pr.tensor_off[k] + base;
+        const float lr = t.lr[k];
+        float* m = t.m[k] + base;
+        float* v = t.v[k] + base;
+        if (base + 4 <= end) {
+            float4 G = mc_ld_reduce_v4(mc_grads + off);
+            float4 P = *reinterpret_cast<const float4*>(t.p[k] + base);
+            float4 M = *reinterpret_cast<float4*>(m);
+            float4 V = *reinterpret_cast<float4*>(v);
+            G.x = G.x * gscale; G.y = G.y * gscale; G.z = G.z * gscale; G.w = G.w * gscale;
+            adam1(P.x, G.x, M.x, V.x, lr, b1, b2, eps);
+            adam1(P.y, G.y, M.y, V.y, lr, b1, b2, eps);
+            adam1(P.z, G.z, M.z, V.z, lr, b1, b2, eps);
+            adam1(P.w, G.w, M.w, V.w, lr, b1, b2, eps);
+            *reinterpret_cast<float4*>(m) = M;
+            *reinterpret_cast<float4*>(v) = V;
+            mc_st_v4(mc_params + off, P);
+        } else {
+            for (long long e = 0; base + e < end; ++e) {
+                const float g = mc_ld_reduce(mc_grads + off + e);
+                float pp = t.p[k][base + e], mm = m[e], vv = v[e];
+                adam1(pp, g * gscale, mm, vv, lr, b1, b2, eps);
+                m[e] = mm; v[e] = vv;
+                mc_st(mc_params + off + e, pp);
+            }
+        }
+    }
+    // D1 on every replica for ALL Gaussians (12 bytes each through the switch): the accumulator stays local and every
+    // replica computes the identical value from the identical switch-reduced gradient
+    if (pr.accum[pr.rank]) {
+        float* accum = pr.accum[pr.rank];
+        const float* gx = mc_grads + pr.tensor_off[0];
+        const long long quads = N / 4;
+        for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < quads; j += stride) {
+            const float4 a = mc_ld_reduce_v4(gx + j * 12), b = mc_ld_reduce_v4(gx + j * 12 + 4), c = mc_ld_reduce_v4(gx + j * 12 + 8);
+            const float g[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+            float4 acc = *reinterpret_cast<float4*>(accum + j * 4);
+            float* ap = &acc.x;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float x = g[3 * q] * gscale, y = g[3 * q + 1] * gscale, z = g[3 * q + 2] * gscale;
+                ap[q] = ap[q] + sqrtf(x * x + y * y + z * z);
+            }
+            *reinterpret_cast<float4*>(accum + j * 4) = acc;
+        }
+        for (long long i = quads * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+            const float x = mc_ld_reduce(gx + i * 3) * gscale, y = mc_ld_reduce(gx + i * 3 + 1) * gscale, z = mc_ld_reduce(gx + i * 3 + 2) * gscale;
+            accum[i] = accum[i] + sqrtf(x * x + y * y + z * z);
+        }
+    }
+}
+
+cudaError_t launch_adam_multicast(cudaStream_t st, const AdamTensors& t, const AdamPeers& pr, const float* mc_grads, float* mc_params,
+                                  float beta1, float beta2, float eps, float gscale, int N, int* launches)
+{
+    AdamSeg seg;
+    seg.vec_begin[0] = 0;
+    for (int k = 0; k < 6; ++k) seg.vec_begin[k + 1] = seg.vec_begin[k] + (t.count[k] + 3) / 4;
+    const long long total = std::max<long long>(seg.vec_begin[6], (N + 3) / 4);
+    long long blocks = (std::max<long long>(total, 1) + AD_THREADS - 1) / AD_THREADS;
+    const long long cap = 148LL * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    k_adam_multicast<<<(int)blocks, AD_THREADS, 0, st>>>(t, pr, seg, mc_grads, mc_params, beta1, beta2, eps, gscale, N);
+    if (launches) ++*launches;
+    return cudaGetLastError();
 }
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

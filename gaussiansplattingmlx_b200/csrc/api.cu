@@ -147,6 +147,16 @@ struct Ctx {
     long long t_count[6]{};
     size_t t_floats = 0;              // padded floats of one copy of the six tensors
     float* t_accum = nullptr;         // D1 accumulator [N]
+    // peer-memory data parallelism (gsb_trainer_peers_*): the other replicas' slab / accumulator mapped through CUDA IPC
+    int peer_world = 0, peer_rank = 0;
+    float* peer_block[gsb::GSB_MAX_PEERS] = {};    // base of replica r's trainer slab (own pointer at [peer_rank])
+    float* peer_accum[gsb::GSB_MAX_PEERS] = {};
+    bool peer_opened[gsb::GSB_MAX_PEERS] = {};
+    // symmetric-memory / NVLS variant (gsb_trainer_attach_symmetric): parameters and gradients live in caller-owned
+    // symmetric buffers, mc_* are the multicast addresses of the same buffers on all replicas
+    bool sym = false;
+    int sym_world = 0, sym_rank = 0;
+    float* sym_params = nullptr; float* sym_grads = nullptr; float* mc_params = nullptr; float* mc_grads = nullptr;
     float* t_target[2] = {nullptr, nullptr};
     cudaEvent_t t_target_ready[2] = {nullptr, nullptr};
     cudaEvent_t t_target_free[2] = {nullptr, nullptr};
@@ -506,6 +516,20 @@ static int check_ctx(Ctx* c)
     return GSB_OK;
 }
 
+// unmap the other replicas' trainer slabs (peer-memory data parallelism, gsb_trainer_peers_import)
+static void peers_close(Ctx* c)
+{
+    for (int r = 0; r < gsb::GSB_MAX_PEERS; ++r) {
+        if (c->peer_opened[r]) {
+            if (c->peer_block[r]) cudaIpcCloseMemHandle(c->peer_block[r]);
+            if (c->peer_accum[r]) cudaIpcCloseMemHandle(c->peer_accum[r]);
+        }
+        c->peer_block[r] = nullptr; c->peer_accum[r] = nullptr; c->peer_opened[r] = false;
+    }
+    c->peer_world = 0;
+}
+
+
 static void destroy_ctx(Ctx* c)
 {
     if (!c) return;
@@ -537,6 +561,7 @@ static void destroy_ctx(Ctx* c)
     dev_free(c->ck.depth); dev_free(c->ck.count); dev_free(c->ck.written); dev_free(c->ck.table);
     dev_free(c->mapA); dev_free(c->mapB); dev_free(c->mapC); dev_free(c->cot_render); dev_free(c->partial);
     dev_free(c->loss_accum); dev_free(c->d_zero);
+    peers_close(c);
     for (int i = 0; i < 2; ++i) { dev_free(c->t_slab[i]); dev_free(c->t_accum_slab[i]); }
     if (c->h_loss) cudaFreeHost(c->h_loss);
     for (auto& e : c->ev_pool) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
@@ -1213,6 +1238,7 @@ static void trainer_adopt(Ctx* c, int N, const TrainerLayout& L, int which)
     }
     c->tN = N;
     c->t_accum_steps = 0;
+    c->sym = false;   // parameters / gradients are back in the slab: a symmetric attachment has to be renewed
 }
 static cudaError_t trainer_alloc_slab(Ctx* c, int which, int cap)
 {
@@ -1233,9 +1259,11 @@ int gsb_trainer_init(gsb_ctx* ctx, int32_t N, const float* host_xyz, const float
     int rc = gsb::ensure_gaussians(c, N);
     if (rc != GSB_OK) return rc;
     gsb::sync_all_streams(c);
+    if (N != c->tN) gsb::peers_close(c);   // a different layout invalidates what the other replicas mapped
     c->tN = 0;
     c->t_block = nullptr; c->t_accum = nullptr;
     if (!c->t_slab[0] || N > c->t_cap) {   // re-initialisation within the capacity keeps the slabs (and their addresses)
+        gsb::peers_close(c);                 // ... and the peers' mappings of them
         for (int i = 0; i < 2; ++i) { gsb::dev_free(c->t_slab[i]); gsb::dev_free(c->t_accum_slab[i]); }
         c->t_cap = N;
         GSB_CUDA_CHECK(c, trainer_alloc_slab(c, 0, c->t_cap));
@@ -1273,7 +1301,7 @@ int gsb_trainer_grad_block(gsb_ctx* ctx, float** grad_block, int64_t* floats)
 {
     CTX_PROLOGUE(ctx);
     if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
-    if (grad_block) *grad_block = c->t_block + c->t_floats;
+    if (grad_block) *grad_block = c->t_g[0];   // base of the gradient copy (slab, or the attached symmetric buffer)
     if (floats) *floats = (int64_t)c->t_floats;
     return GSB_OK;
 }
@@ -1287,7 +1315,7 @@ int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
     const int N = c->tN;
     const size_t img_bytes = (size_t)c->P * 3 * sizeof(float);
     if (host_loss) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->loss_accum, 0, sizeof(float), c->stream));
-    if (zero_grads && B == 0) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + c->t_floats, 0, c->t_floats * 4, c->stream));
+    if (zero_grads && B == 0) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_g[0], 0, c->t_floats * 4, c->stream));
     // prefetch of view 0's target
     auto prefetch = [&](int b) -> int {
         const int s = b & 1;
@@ -1407,6 +1435,160 @@ int gsb_trainer_apply(gsb_ctx* ctx, int32_t iteration, int32_t total_iterations,
                                        c->t_accum, nullptr, &launches));
     c->stats.kernel_launches += launches;
     c->t_accum_steps += 1;   // addGradientAccumulation (GaussianTrainer.swift:724-742)
+    return GSB_OK;
+}
+
+// ---- peer-memory data parallelism ----------------------------------------------------------------
+struct PeerExport {                 // what one replica publishes: 2 IPC handles + the layout the others must share
+    cudaIpcMemHandle_t block, accum;
+    int64_t n, floats, cap;
+};
+int gsb_trainer_peers_export(gsb_ctx* ctx, void* host_blob, int64_t blob_bytes)
+{
+    CTX_PROLOGUE(ctx);
+    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    GSB_REQUIRE(c, host_blob && blob_bytes >= (int64_t)sizeof(PeerExport), "gsb_trainer_peers_export: blob too small");
+    PeerExport e{};
+    GSB_CUDA_CHECK(c, cudaIpcGetMemHandle(&e.block, c->t_block));
+    GSB_CUDA_CHECK(c, cudaIpcGetMemHandle(&e.accum, c->t_accum));
+    e.n = c->tN; e.floats = (int64_t)c->t_floats; e.cap = c->t_cap;
+    memset(host_blob, 0, (size_t)blob_bytes);
+    memcpy(host_blob, &e, sizeof(e));
+    return GSB_OK;
+}
+
+int gsb_trainer_peers_import(gsb_ctx* ctx, int32_t world, int32_t rank, const void* host_blobs, int64_t blob_bytes)
+{
+    CTX_PROLOGUE(ctx);
+    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    GSB_REQUIRE(c, world >= 1 && world <= gsb::GSB_MAX_PEERS && rank >= 0 && rank < world && host_blobs &&
+                       blob_bytes >= (int64_t)sizeof(PeerExport),
+                "gsb_trainer_peers_import: bad arguments (at most 8 replicas)");
+    gsb::sync_all_streams(c);
+    gsb::peers_close(c);
+    for (int r = 0; r < world; ++r) {
+        PeerExport e;
+        memcpy(&e, static_cast<const char*>(host_blobs) + (size_t)r * (size_t)blob_bytes, sizeof(e));
+        if (e.n != c->tN || e.floats != (int64_t)c->t_floats) {
+            gsb::peers_close(c);
+            gsb::set_error(c, "gsb_trainer_peers_import: replica layouts differ");
+            return GSB_ERR_INVALID;
+        }
+        if (r == rank) {
+            c->peer_block[r] = c->t_block; c->peer_accum[r] = c->t_accum;
+            continue;
+        }
+        void* pb = nullptr; void* pa = nullptr;
+        cudaError_t err = cudaIpcOpenMemHandle(&pb, e.block, cudaIpcMemLazyEnablePeerAccess);
+        if (err == cudaSuccess) err = cudaIpcOpenMemHandle(&pa, e.accum, cudaIpcMemLazyEnablePeerAccess);
+        if (err != cudaSuccess) {
+            if (pb) cudaIpcCloseMemHandle(pb);
+            gsb::peers_close(c);
+            gsb::set_error(c, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(err));
+            cudaGetLastError();
+            return GSB_ERR_CUDA;
+        }
+        c->peer_block[r] = static_cast<float*>(pb); c->peer_accum[r] = static_cast<float*>(pa); c->peer_opened[r] = true;
+    }
+    c->peer_world = world; c->peer_rank = rank;
+    return GSB_OK;
+}
+
+int gsb_trainer_apply_peers(gsb_ctx* ctx, int32_t iteration, int32_t total_iterations, int32_t reset_state)
+{
+    CTX_PROLOGUE(ctx);
+    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    GSB_REQUIRE(c, total_iterations > 0, "gsb_trainer_apply_peers: total_iterations must be positive");
+    if (c->peer_world < 1 || c->peer_block[c->peer_rank] != c->t_block) {
+        gsb::set_error(c, "gsb_trainer_apply_peers: peers not imported for the current trainer state");
+        return GSB_ERR_STATE;
+    }
+    if (reset_state) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + 2 * c->t_floats, 0, 2 * c->t_floats * sizeof(float), c->stream));
+    const int W = c->peer_world, R = c->peer_rank;
+    // owned Gaussians: equal slices on multiples of 4 (every tensor slice then starts 16-byte aligned)
+    const long long per = (((long long)c->tN + W - 1) / W + 3) & ~3LL;
+    const long long g0 = std::min<long long>((long long)R * per, c->tN), g1 = std::min<long long>(g0 + per, c->tN);
+    gsb::AdamTensors t{};
+    gsb::AdamPeers pr{};
+    learning_rates(iteration, total_iterations, t.lr);
+    const int K = c->cfg.sh_coeffs;
+    const long long row[6] = {3, 3, (long long)(K - 1) * 3, 3, 4, 1};
+    for (int k = 0; k < 6; ++k) {
+        t.p[k] = c->t_p[k]; t.g[k] = c->t_g[k]; t.m[k] = c->t_m[k]; t.v[k] = c->t_v[k];
+        t.count[k] = (g1 - g0) * row[k];
+        pr.first[k] = g0 * row[k];
+        pr.tensor_off[k] = (long long)(c->t_p[k] - c->t_block);
+    }
+    for (int r = 0; r < W; ++r) {
+        pr.params[r] = c->peer_block[r];
+        pr.grads[r] = c->peer_block[r] + c->t_floats;
+        pr.accum[r] = c->peer_accum[r];
+    }
+    pr.g0 = g0; pr.g1 = g1; pr.world = W; pr.rank = R;
+    gsb::StageTimer tm(c, GSB_STAGE_ADAM);
+    int launches = 0;
+    GSB_CUDA_CHECK(c, gsb::launch_adam_peers(c->stream, t, pr, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, &launches));
+    c->stats.kernel_launches += launches;
+    c->t_accum_steps += 1;
+    return GSB_OK;
+}
+
+int gsb_trainer_attach_symmetric(gsb_ctx* ctx, int32_t world, int32_t rank, float* params_local, float* grads_local,
+                                 float* params_mc, float* grads_mc, int64_t floats)
+{
+    CTX_PROLOGUE(ctx);
+    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    GSB_REQUIRE(c, world >= 1 && world <= gsb::GSB_MAX_PEERS && rank >= 0 && rank < world && params_local && grads_local &&
+                       params_mc && grads_mc && floats >= (int64_t)c->t_floats,
+                "gsb_trainer_attach_symmetric: bad arguments (buffers must hold gsb_trainer_grad_block's float count)");
+    GSB_REQUIRE(c, ((reinterpret_cast<uintptr_t>(params_local) | reinterpret_cast<uintptr_t>(grads_local) |
+                     reinterpret_cast<uintptr_t>(params_mc) | reinterpret_cast<uintptr_t>(grads_mc)) & 127u) == 0,
+                "gsb_trainer_attach_symmetric: buffers must be 128-byte aligned");
+    gsb::sync_all_streams(c);
+    const float* cur_params = c->t_p[0];   // off[0] == 0: base of the current parameter copy
+    if (cur_params != params_local)
+        GSB_CUDA_CHECK(c, cudaMemcpyAsync(params_local, cur_params, c->t_floats * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    GSB_CUDA_CHECK(c, cudaMemsetAsync(grads_local, 0, c->t_floats * sizeof(float), c->stream));
+    for (int k = 0; k < 6; ++k) {
+        const ptrdiff_t off = c->t_m[k] - (c->t_block + 2 * c->t_floats);   // segment offset inside one copy
+        c->t_p[k] = params_local + off;
+        c->t_g[k] = grads_local + off;
+    }
+    c->sym = true; c->sym_world = world; c->sym_rank = rank;
+    c->sym_params = params_local; c->sym_grads = grads_local; c->mc_params = params_mc; c->mc_grads = grads_mc;
+    GSB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return GSB_OK;
+}
+
+int gsb_trainer_apply_multicast(gsb_ctx* ctx, int32_t iteration, int32_t total_iterations, int32_t reset_state)
+{
+    CTX_PROLOGUE(ctx);
+    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    GSB_REQUIRE(c, total_iterations > 0, "gsb_trainer_apply_multicast: total_iterations must be positive");
+    if (!c->sym) { gsb::set_error(c, "gsb_trainer_apply_multicast: no symmetric buffers attached to the current trainer state"); return GSB_ERR_STATE; }
+    if (reset_state) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + 2 * c->t_floats, 0, 2 * c->t_floats * sizeof(float), c->stream));
+    const int W = c->sym_world, R = c->sym_rank;
+    const long long per = (((long long)c->tN + W - 1) / W + 3) & ~3LL;
+    const long long g0 = std::min<long long>((long long)R * per, c->tN), g1 = std::min<long long>(g0 + per, c->tN);
+    gsb::AdamTensors t{};
+    gsb::AdamPeers pr{};
+    learning_rates(iteration, total_iterations, t.lr);
+    const int K = c->cfg.sh_coeffs;
+    const long long row[6] = {3, 3, (long long)(K - 1) * 3, 3, 4, 1};
+    for (int k = 0; k < 6; ++k) {
+        t.p[k] = c->t_p[k]; t.g[k] = c->t_g[k]; t.m[k] = c->t_m[k]; t.v[k] = c->t_v[k];
+        t.count[k] = (g1 - g0) * row[k];
+        pr.first[k] = g0 * row[k];
+        pr.tensor_off[k] = (long long)(c->t_p[k] - c->sym_params);
+    }
+    pr.accum[R] = c->t_accum;
+    pr.g0 = g0; pr.g1 = g1; pr.world = W; pr.rank = R;
+    gsb::StageTimer tm(c, GSB_STAGE_ADAM);
+    int launches = 0;
+    GSB_CUDA_CHECK(c, gsb::launch_adam_multicast(c->stream, t, pr, c->mc_grads, c->mc_params, c->cfg.adam_beta1, c->cfg.adam_beta2,
+                                                 c->cfg.adam_eps, 1.0f, c->tN, &launches));
+    c->stats.kernel_launches += launches;
+    c->t_accum_steps += 1;
     return GSB_OK;
 }
 

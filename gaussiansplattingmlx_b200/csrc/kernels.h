@@ -176,6 +176,25 @@ struct AdamTensors {
     long long count[6];
     float lr[6];
 };
+// Peer-memory data parallelism (adam.cu k_adam_peers): replica r's gradient / parameter copies and D1 accumulator, and the
+// slice of Gaussians [g0, g1) this rank owns.  AdamTensors passed with it holds the LOCAL p / m / v base pointers of the
+// six tensors and count[k] = floats of the owned slice of tensor k.
+constexpr int GSB_MAX_PEERS = 8;
+struct AdamPeers {
+    const float* grads[GSB_MAX_PEERS];   // base of the gradient copy (six tensors, padded) of every replica
+    float* params[GSB_MAX_PEERS];        // base of the parameter copy of every replica
+    float* accum[GSB_MAX_PEERS];         // D1 accumulators (accum[0] == nullptr: skip D1)
+    long long tensor_off[6];             // float offset of tensor k inside one copy
+    long long first[6];                  // first float of the owned slice inside tensor k (multiple of 4)
+    long long g0, g1;                    // owned Gaussians
+    int world, rank;
+};
+cudaError_t launch_adam_peers(cudaStream_t st, const AdamTensors& t, const AdamPeers& pr, float beta1, float beta2, float eps,
+                              float gscale, int* launches);
+// NVLS variant: mc_grads / mc_params = multicast addresses of the replicas' gradient / parameter blocks (symmetric memory);
+// pr supplies the owned slice, the tensor offsets and (accum[rank]) the local D1 accumulator.
+cudaError_t launch_adam_multicast(cudaStream_t st, const AdamTensors& t, const AdamPeers& pr, const float* mc_grads, float* mc_params,
+                                  float beta1, float beta2, float eps, float gscale, int N, int* launches);
 // gscale multiplies every gradient before use (1.0 on the training path); launches (may be NULL) is
 // incremented by the number of kernels launched.
 cudaError_t launch_adam(cudaStream_t st, const AdamTensors& t, float beta1, float beta2, float eps, float gscale, int N,

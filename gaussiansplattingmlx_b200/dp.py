@@ -46,6 +46,82 @@ class ViewParallel:
             dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
         return tensor
 
+    # ---- step fused with its collective over NVLink peer memory (include/gsb.h: gsb_trainer_peers_*) ----------
+    def enable_peers(self, ctx) -> bool:
+        """Exchange the replicas' CUDA-IPC blobs and map every replica's trainer slab into ``ctx``.  Returns False (and
+        leaves the all-reduce path in charge) for world 1, non-NCCL backends or more than 8 ranks."""
+        if self.world == 1 or self.world > 8:
+            return False
+        import torch
+        import torch.distributed as dist
+        if dist.get_backend(self.group) != "nccl":
+            return False
+        blob = ctx.trainer_peers_export()
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(ctx.device)
+        everyone = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=ctx.device)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        raw = bytes(everyone.cpu().numpy().tobytes())
+        n = len(blob)
+        ok = 1
+        try:
+            ctx.trainer_peers_import(self.world, self.rank, [raw[i * n:(i + 1) * n] for i in range(self.world)])
+        except Exception:   # no peer access between these devices (IPC refused): every rank falls back together
+            ok = 0
+        self._token = torch.zeros(1, dtype=torch.float32, device=ctx.device)
+        agreed = torch.tensor([ok], dtype=torch.int32, device=ctx.device)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=self.group)   # also: nobody launches before everyone has mapped
+        return bool(agreed.item())
+
+    # ---- the same step through the NVSwitch: symmetric memory + multicast (gsb_trainer_attach_symmetric) -----------
+    def enable_multicast(self, ctx) -> bool:
+        """Put the replicas' parameter and gradient blocks into torch symmetric memory (one multicast range per block) and
+        attach them to ``ctx``.  Call again after every ``ctx.trainer_init`` / densification (the buffers are kept).
+        Returns False when the box has no NVLS multicast (or world 1 / non-NCCL / > 8 ranks)."""
+        if self.world == 1 or self.world > 8:
+            return False
+        import torch
+        import torch.distributed as dist
+        if dist.get_backend(self.group) != "nccl":
+            return False
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            floats = int(ctx.trainer_grad_block().numel())
+            if getattr(self, "_sym_floats", 0) < floats:
+                self._symP = symm_mem.empty(floats, dtype=torch.float32, device=ctx.device)
+                self._symG = symm_mem.empty(floats, dtype=torch.float32, device=ctx.device)
+                grp = self.group if self.group is not None else dist.group.WORLD
+                self._hP = symm_mem.rendezvous(self._symP, grp)
+                self._hG = symm_mem.rendezvous(self._symG, grp)
+                self._sym_floats = floats
+            if not (self._hP.multicast_ptr and self._hG.multicast_ptr):
+                ok = 0
+            else:
+                ctx.trainer_attach_symmetric(self.world, self.rank, self._symP.data_ptr(), self._symG.data_ptr(),
+                                             self._hP.multicast_ptr, self._hG.multicast_ptr, self._sym_floats)
+        except Exception:
+            ok = 0
+        self._token = torch.zeros(1, dtype=torch.float32, device=ctx.device)
+        agreed = torch.tensor([ok], dtype=torch.int32, device=ctx.device)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(agreed.item())
+
+    def multicast_step(self, ctx, iteration: int, total_iterations: int, reset_state: bool = False):
+        self.stream_barrier()            # every replica's gradients are complete
+        ctx.trainer_apply_multicast(iteration, total_iterations, reset_state)
+        self.stream_barrier()            # every replica's parameters are written
+
+    def stream_barrier(self):
+        """Stream-ordered barrier: a 4-byte all-reduce enqueued behind the work already on the current stream."""
+        import torch.distributed as dist
+        dist.all_reduce(self._token, group=self.group)
+
+    def peer_step(self, ctx, iteration: int, total_iterations: int, reset_state: bool = False):
+        """What replaces ``all_reduce_sum(grad_block); ctx.trainer_apply(...)`` once ``enable_peers`` succeeded."""
+        self.stream_barrier()            # every replica's gradients are complete
+        ctx.trainer_apply_peers(iteration, total_iterations, reset_state)
+        self.stream_barrier()            # every replica's parameters (and D1 accumulators) are written
+
     def all_reduce_max(self, value: float, device=None) -> float:
         if self.world == 1:
             return value

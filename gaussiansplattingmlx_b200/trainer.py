@@ -2,7 +2,8 @@
 (``Trainer/GaussianTrainer.swift:448-477`` init, ``:934-1114`` startTrain) over the fused CUDA step.
 
 One iteration = ``gsb_trainer_accumulate`` (per view: render → loss → backward, gradients summed with
-weight 1/B) → optional view-parallel all-reduce → ``gsb_trainer_apply`` (Adam + D1 grad-norm accumulation).
+weight 1/B) → ``gsb_trainer_apply`` (Adam + D1 grad-norm accumulation); view-parallel: the step fused with its
+collective over NVLink peer memory (``dp.ViewParallel.peer_step``), or all-reduce + apply on non-NCCL backends.
 With ``views_per_step == 1`` and one rank this is the reference iteration, including ``split_and_prune`` every
 ``split_and_prune_per_iteration`` iterations (``gsb_trainer_densify``) and the optimiser-state reset cadence.
 """
@@ -72,6 +73,9 @@ class GaussianTrainer:
         self._gcams = [_lib.make_camera(c) for c in data.cameras]
         self._targets = [torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)).pin_memory() for t in data.rgbArray]
         self._grad_block = ctx.trainer_grad_block() if self.parallel.world > 1 else None
+        # one process per GPU over NCCL: the step is fused with its collective over NVLink peer memory (dp.peer_step);
+        # otherwise (gloo, a single rank) all-reduce + gsb_trainer_apply
+        self._peers = self.parallel.world > 1 and self.parallel.enable_peers(ctx)
         self.losses: List[float] = []
 
     def stopTrain(self):
@@ -93,12 +97,15 @@ class GaussianTrainer:
                                           grad_scale=1.0 / B, want_loss=want_loss)
         elif self.parallel.world > 1:
             self._grad_block.zero_()
-        if self.parallel.world > 1:
-            self.parallel.all_reduce_sum(self._grad_block)
         reset = self.reset_optimizer_state and iteration % self.optimizer_reset_interval == 0
         # the reference re-creates the Adam state AFTER the update of every 100th iteration
         # (GaussianTrainer.swift:1098-1109); zeroing before the next update is the same thing
-        ctx.trainer_apply(iteration, self.iterationCount, reset_state=False)
+        if self._peers:
+            self.parallel.peer_step(ctx, iteration, self.iterationCount, reset_state=False)
+        else:
+            if self.parallel.world > 1:
+                self.parallel.all_reduce_sum(self._grad_block)
+            ctx.trainer_apply(iteration, self.iterationCount, reset_state=False)
         if self.outputDirectoryURL and iteration % self.save_snapshot_per_iteration == 0:
             self.save_snapshot(iteration)                     # GaussianTrainer.swift:1092 (before split_and_prune)
         if reset:
@@ -120,6 +127,8 @@ class GaussianTrainer:
         self.densify_log.append(dict(info, iteration=iteration))
         if self.parallel.world > 1:
             self._grad_block = self.gaussRender.ctx.trainer_grad_block()
+            if self._peers:   # the slabs swapped: map the replicas' new ones
+                self._peers = self.parallel.enable_peers(self.gaussRender.ctx)
         return info
 
     def save_snapshot(self, iteration: int):

@@ -208,6 +208,30 @@ GSB_API int gsb_trainer_accumulate(gsb_ctx*, int32_t B, const gsb_camera* host_c
 /* Adam + D1 on the context's buffers; learning rates from (iteration, total_iterations)
  * (GaussianModel.swift:56-65).  reset_state != 0 re-zeroes m/v first (GaussianTrainer.swift:1104-1109). */
 GSB_API int gsb_trainer_apply(gsb_ctx*, int32_t iteration, int32_t total_iterations, int32_t reset_state);
+/* Data-parallel step fused with its collective, over NVLink peer memory (one process per GPU on one node, <= 8):
+ *   every replica calls gsb_trainer_peers_export (GSB_PEER_BLOB_BYTES of host memory: CUDA IPC handles of its trainer
+ *   slab + layout), the host exchanges the blobs (any transport) and hands all of them, in rank order, to
+ *   gsb_trainer_peers_import.  Per step, INSTEAD of "all-reduce the gradient block; gsb_trainer_apply":
+ *       barrier (stream-ordered: every replica's gsb_trainer_accumulate is complete)
+ *       gsb_trainer_apply_peers   -- rank r sums slice r of ALL replicas' gradients (peer loads), applies Adam + D1 with
+ *                                    its local m / v, stores the new parameters into EVERY replica (peer stores)
+ *       barrier (every replica's parameters are written)
+ * The mapping survives gsb_trainer_init with the same N; it is dropped by a different N, by densification (the slabs
+ * swap: export / import again) and by gsb_destroy.  gsb_trainer_apply_peers fails with GSB_ERR_STATE without it. */
+#define GSB_PEER_BLOB_BYTES 256
+GSB_API int gsb_trainer_peers_export(gsb_ctx*, void* host_blob, int64_t blob_bytes);
+GSB_API int gsb_trainer_peers_import(gsb_ctx*, int32_t world, int32_t rank, const void* host_blobs, int64_t blob_bytes);
+GSB_API int gsb_trainer_apply_peers(gsb_ctx*, int32_t iteration, int32_t total_iterations, int32_t reset_state);
+/* The same step through the NVSwitch (NVLS).  The host allocates, per replica, two SYMMETRIC buffers of at least
+ * gsb_trainer_grad_block's float count (same size on every replica, bound to one multicast range - e.g.
+ * torch.distributed._symmetric_memory) and attaches them: the parameters move into params_local, gradients are
+ * accumulated into grads_local; params_mc / grads_mc are the multicast addresses of those buffers.
+ * gsb_trainer_apply_multicast (between the same two barriers as above) then reads slice r of the gradient ALREADY SUMMED
+ * by the switch (multimem.ld_reduce), applies Adam + D1 and multicasts the new parameters (multimem.st): 1/world of
+ * the two blocks crosses this GPU's links instead of (world-1)/world.  gsb_trainer_init and densification detach. */
+GSB_API int gsb_trainer_attach_symmetric(gsb_ctx*, int32_t world, int32_t rank, float* params_local, float* grads_local,
+                                 float* params_mc, float* grads_mc, int64_t floats);
+GSB_API int gsb_trainer_apply_multicast(gsb_ctx*, int32_t iteration, int32_t total_iterations, int32_t reset_state);
 /* accumulate (zero_grads=1, scale 1/B) followed by apply. */
 GSB_API int gsb_train_step(gsb_ctx*, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
                    int32_t targets_on_host, int32_t iteration, int32_t total_iterations, float* host_loss);
