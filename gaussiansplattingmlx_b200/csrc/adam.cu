@@ -7,6 +7,8 @@
 // and accum_grad_norm (GaussianTrainer.swift:321-339): accum[i] += ||grad_xyz_i||_2.
 // HBM-bound: 28 B per parameter float (read p,g,m,v; write p,m,v).  Compiled with --fmad=false so
 // the update rounds exactly like the CPU oracle (bit-exact Adam parity).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "kernels.h"
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(AD_THREADS) k_adam(const __grid_constant__ Ada
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(AD_THREADS, 4) k_adam_peers(const __grid_constant__ AdamTensors t, const __grid_constant__ AdamPeers pr,
                                                            const __grid_constant__ AdamSeg seg, float b1, float b2, float eps,
-                                                           float gscale)
+                                                           float gscale, int diag)
 {
     const long long total = seg.vec_begin[6];
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -115,7 +117,8 @@ __global__ void __launch_bounds__(AD_THREADS, 4) k_adam_peers(const __grid_const
         if (vec_n) {
 #pragma unroll
             for (int r = 0; r < GSB_MAX_PEERS; ++r)
-                if (r < pr.world) gn[r] = __ldcg(reinterpret_cast<const float4*>(pr.grads[r] + off));
+                if (r < pr.world && (!(diag & 2) || r == pr.rank)) gn[r] = __ldcg(reinterpret_cast<const float4*>(pr.grads[r] + off));
+                else if (r < pr.world) gn[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     if (i < total) prefetch(i);
@@ -146,7 +149,8 @@ __global__ void __launch_bounds__(AD_THREADS, 4) k_adam_peers(const __grid_const
             adam1(P.w, G.w, M.w, V.w, lr, b1, b2, eps);
             *reinterpret_cast<float4*>(m) = M;
             *reinterpret_cast<float4*>(v) = V;
-            for (int r = 0; r < pr.world; ++r) *reinterpret_cast<float4*>(pr.params[r] + off) = P;
+            for (int r = 0; r < pr.world; ++r)
+                if (!(diag & 1) || r == pr.rank) *reinterpret_cast<float4*>(pr.params[r] + off) = P;
         } else {
             for (long long e = 0; base + e < end; ++e) {
                 float g = 0.f;
@@ -183,9 +187,13 @@ cudaError_t launch_adam_peers(cudaStream_t st, const AdamTensors& t, const AdamP
     const long long total = seg.vec_begin[6];
     if (total == 0 && pr.g1 <= pr.g0) return cudaSuccess;
     long long blocks = (std::max<long long>(total, 1) + AD_THREADS - 1) / AD_THREADS;
-    const long long cap = 148LL * 4;   // persistent: one resident wave (4 CTAs per SM), every thread pipelines its chunks
+    long long cap = 148LL * 4;   // persistent: one resident wave (4 CTAs per SM), every thread pipelines its chunks
+    // tuning / diagnosis knobs, never set in production (DESIGN.md section 5 quotes what they measured)
+    static const int env_blocks = getenv("GSB_PEER_BLOCKS") ? atoi(getenv("GSB_PEER_BLOCKS")) : 0;
+    static const int diag = getenv("GSB_PEER_DIAG") ? atoi(getenv("GSB_PEER_DIAG")) : 0;             // 1: no remote stores, 2: no remote loads (WRONG results)
+    if (env_blocks > 0) cap = env_blocks;
     if (blocks > cap) blocks = cap;
-    k_adam_peers<<<(int)blocks, AD_THREADS, 0, st>>>(t, pr, seg, beta1, beta2, eps, gscale);
+    k_adam_peers<<<(int)blocks, AD_THREADS, 0, st>>>(t, pr, seg, beta1, beta2, eps, gscale, diag);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
