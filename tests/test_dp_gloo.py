@@ -40,8 +40,24 @@ def _worker(rank, world, port, out_dir):
     vp.all_reduce_sum(block)
     t_max = vp.all_reduce_max(float(rank + 1))
     assert t_max == float(world)
+    # the peer-memory / multicast steps need NCCL on one NVLink box: on gloo both report "not available" (without touching
+    # the context) and the caller stays on all-reduce + apply
+    assert vp.enable_peers(None) is False and vp.enable_multicast(None) is False
     np.save(Path(out_dir) / f"block_{rank}.npy", block.numpy())
     dist.destroy_process_group()
+
+
+def test_owned_slices_cover_every_gaussian_once():
+    """The slicing rule of gsb_trainer_apply_peers / _multicast (api.cu): equal slices on multiples of 4 Gaussians."""
+    for n in (1, 3, 4, 5, 50001, 1_000_000, 6_000_003):
+        for world in (1, 2, 3, 4, 8):
+            per = (((n + world - 1) // world) + 3) & ~3
+            covered = 0
+            for r in range(world):
+                g0 = min(r * per, n); g1 = min(g0 + per, n)
+                assert g0 == covered and g0 % 4 == 0 or g0 == n
+                covered = g1
+            assert covered == n
 
 
 def test_view_parallel_gradient_equals_batch_gradient(tmp_path):
