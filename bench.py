@@ -380,6 +380,8 @@ def run_gsb(args, rank, local_rank, world):
     ms_e2e = timed(True, True, args.steps, it)
     assert len(e2e_state["losses"]) >= args.steps and all(np.isfinite(l) for l in e2e_state["losses"])
     clk = clocks.stop() if rank == 0 else None
+    if world > 1 and dp_state.get("mode") == "peers":
+        vp_dp.disable_peers(ctx)   # unmap the replicas' slabs on every rank before any context is destroyed
 
     if rank != 0:
         if world > 1:

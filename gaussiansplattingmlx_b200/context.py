@@ -331,6 +331,9 @@ class Context:
         buf = C.create_string_buffer(b"".join(blobs), world * _lib.GSB_PEER_BLOB_BYTES)
         self._check(self.lib.gsb_trainer_peers_import(self.h, world, rank, C.cast(buf, C.c_void_p), _lib.GSB_PEER_BLOB_BYTES))
 
+    def trainer_peers_close(self):
+        self._check(self.lib.gsb_trainer_peers_close(self.h))
+
     def trainer_apply_peers(self, iteration: int, total_iterations: int, reset_state: bool = False):
         """Fused gradient reduction + Adam + parameter broadcast over NVLink peer memory; the caller brackets it with
         two stream-ordered barriers (see dp.ViewParallel.peer_step)."""

@@ -1494,6 +1494,14 @@ int gsb_trainer_peers_import(gsb_ctx* ctx, int32_t world, int32_t rank, const vo
     return GSB_OK;
 }
 
+int gsb_trainer_peers_close(gsb_ctx* ctx)
+{
+    CTX_PROLOGUE(ctx);
+    gsb::sync_all_streams(c);
+    gsb::peers_close(c);
+    return GSB_OK;
+}
+
 int gsb_trainer_apply_peers(gsb_ctx* ctx, int32_t iteration, int32_t total_iterations, int32_t reset_state)
 {
     CTX_PROLOGUE(ctx);

@@ -111,6 +111,14 @@ class ViewParallel:
         ctx.trainer_apply_multicast(iteration, total_iterations, reset_state)
         self.stream_barrier()            # every replica's parameters are written
 
+    def disable_peers(self, ctx):
+        """Unmap the other replicas' slabs on every rank, then synchronise: call before the contexts are destroyed
+        (memory exported through CUDA IPC must not be freed while another process still has it open)."""
+        if self.world > 1:
+            import torch.distributed as dist
+            ctx.trainer_peers_close()
+            dist.barrier(group=self.group)
+
     def stream_barrier(self):
         """Stream-ordered barrier: a 4-byte all-reduce enqueued behind the work already on the current stream."""
         import torch.distributed as dist

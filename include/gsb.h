@@ -222,6 +222,9 @@ GSB_API int gsb_trainer_apply(gsb_ctx*, int32_t iteration, int32_t total_iterati
 GSB_API int gsb_trainer_peers_export(gsb_ctx*, void* host_blob, int64_t blob_bytes);
 GSB_API int gsb_trainer_peers_import(gsb_ctx*, int32_t world, int32_t rank, const void* host_blobs, int64_t blob_bytes);
 GSB_API int gsb_trainer_apply_peers(gsb_ctx*, int32_t iteration, int32_t total_iterations, int32_t reset_state);
+/* Unmaps the other replicas' slabs.  Call it on every replica (and synchronise the replicas) BEFORE any of them destroys
+ * its context: memory exported through CUDA IPC must not be freed while another process still has it open. */
+GSB_API int gsb_trainer_peers_close(gsb_ctx*);
 /* The same step through the NVSwitch (NVLS).  The host allocates, per replica, two SYMMETRIC buffers of at least
  * gsb_trainer_grad_block's float count (same size on every replica, bound to one multicast range - e.g.
  * torch.distributed._symmetric_memory) and attaches them: the parameters move into params_local, gradients are
