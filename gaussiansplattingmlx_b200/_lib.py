@@ -77,12 +77,15 @@ SIGNATURES = {
     "gsb_render_forward": (C.c_int, [_P, _I] + [_P] * 6 + [C.POINTER(GsbCamera)] + [_P] * 5),
     "gsb_render_backward": (C.c_int, [_P] + [_P] * 9 + [_I]),
     "gsb_loss_fwd_bwd": (C.c_int, [_P, _P, _P, _F, _P, _P]),
+    "gsb_loss_fwd_bwd_depth": (C.c_int, [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P]),
     "gsb_adam_step": (C.c_int, [_P, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
                                 C.POINTER(C.c_int64), C.POINTER(_F), _P]),
     "gsb_trainer_init": (C.c_int, [_P, _I] + [_P] * 6),
     "gsb_trainer_param_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "gsb_trainer_grad_block": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "gsb_trainer_accumulate": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), _I, _I, _F, _P]),
+    "gsb_trainer_accumulate_depth": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _F, _I, _I,
+                                               _F, _P]),
     "gsb_trainer_apply": (C.c_int, [_P, _I, _I, _I]),
     "gsb_trainer_peers_export": (C.c_int, [_P, _P, C.c_int64]),
     "gsb_trainer_peers_import": (C.c_int, [_P, _I, _I, _P, C.c_int64]),

@@ -2,7 +2,7 @@
 
     python -m gaussiansplattingmlx_b200.build [--force]
 
-nvcc cross-compiles without a GPU.  ``project.cu`` and ``adam.cu`` are compiled with
+nvcc cross-compiles without a GPU.  ``project.cu`` (forward only) and ``adam.cu`` are compiled with
 ``--fmad=false`` so that their arithmetic rounds exactly like the ``-ffp-contract=off`` CPU oracle
 (bit-exact projection geometry → bit-exact tile lists; bit-exact Adam); both are HBM-bound, the
 lost FMA contraction is not on their critical path.  Everything else is compiled with FMA.
@@ -26,6 +26,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hi
           "-Xptxas", "-v"]
 SOURCES = {
     "project.cu": ["--fmad=false"],
+    "project_bwd.cu": [],
     "adam.cu": ["--fmad=false"],
     "densify.cu": ["--fmad=false"],
     "binning.cu": [],

@@ -237,14 +237,23 @@ class Context:
                                                  *[_ptr(grads[k]) for k in PARAM_NAMES], int(accumulate)))
         return grads
 
-    def loss_fwd_bwd(self, render, target, grad_scale: float = 1.0):
-        """Returns (loss tensor [1] on device, cot_render[H,W,3])."""
+    def loss_fwd_bwd(self, render, target, grad_scale: float = 1.0, depth=None, depth_mask=None, target_depth=None,
+                     lambda_depth: float = 0.0):
+        """Returns (loss tensor [1] on device, cot_render[H,W,3]); with depth supervision (``depth`` = the renderer's depth
+        output, ``depth_mask`` bool/uint8 [H,W], ``target_depth`` f32 [H,W]) also cot_depth[H,W,1] as a third value."""
         self._sync_stream()
         cot = torch.empty_like(render)
         loss = torch.zeros(1, dtype=torch.float32, device=self.device)
-        self._check(self.lib.gsb_loss_fwd_bwd(self.h, _ptr(_f32(render)), _ptr(_f32(target)), C.c_float(grad_scale), _ptr(cot),
-                                              _ptr(loss)))
-        return loss, cot
+        if depth is None:
+            self._check(self.lib.gsb_loss_fwd_bwd(self.h, _ptr(_f32(render)), _ptr(_f32(target)), C.c_float(grad_scale), _ptr(cot),
+                                                  _ptr(loss)))
+            return loss, cot
+        mask = depth_mask.to(torch.uint8).contiguous()
+        cot_depth = torch.empty_like(depth)
+        self._check(self.lib.gsb_loss_fwd_bwd_depth(self.h, _ptr(_f32(render)), _ptr(_f32(depth)), _ptr(_f32(target)), _ptr(mask),
+                                                    _ptr(_f32(target_depth)), C.c_float(lambda_depth), C.c_float(grad_scale),
+                                                    _ptr(cot), _ptr(cot_depth), _ptr(loss)))
+        return loss, cot, cot_depth
 
     # ---- Adam -------------------------------------------------------------------------------
     def adam_step(self, params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], m: Sequence[torch.Tensor],
@@ -298,21 +307,35 @@ class Context:
         return B, cam_arr, tp, int(on_host)
 
     def trainer_accumulate(self, cams, targets, zero_grads: bool = True, grad_scale: Optional[float] = None,
-                           want_loss: bool = True, loss_out: Optional[torch.Tensor] = None) -> Optional[float]:
+                           want_loss: bool = True, loss_out: Optional[torch.Tensor] = None,
+                           target_depths: Optional[Sequence[torch.Tensor]] = None,
+                           depth_masks: Optional[Sequence[torch.Tensor]] = None, lambda_depth: float = 0.0) -> Optional[float]:
         """``loss_out``: a pinned 1-element f32 CPU tensor; with GSB_FLAG_ASYNC_LOSS set the mean loss is copied into it
-        asynchronously (no synchronisation; read it after an event/stream sync) and the return value is None."""
+        asynchronously (no synchronisation; read it after an event/stream sync) and the return value is None.
+        ``target_depths`` (f32 [H,W]) + ``depth_masks`` (uint8 [H,W]), living where the targets live, switch on the
+        depth-supervision term with weight ``lambda_depth``."""
         self._sync_stream()
         B, cam_arr, tp, on_host = self._cams_targets(cams, targets)
         scale = (1.0 / B) if grad_scale is None else grad_scale
+        if target_depths is not None:
+            assert depth_masks is not None and len(target_depths) == B and len(depth_masks) == B
+            for d, m in zip(target_depths, depth_masks):
+                assert d.dtype == torch.float32 and m.dtype == torch.uint8 and d.is_contiguous() and m.is_contiguous()
+                assert d.is_cuda != bool(on_host) and m.is_cuda != bool(on_host) and d.numel() == self.P and m.numel() == self.P
+            dp = (C.c_void_p * B)(*[t.data_ptr() for t in target_depths])
+            mp = (C.c_void_p * B)(*[t.data_ptr() for t in depth_masks])
+            call = lambda loss_ptr: self.lib.gsb_trainer_accumulate_depth(self.h, B, cam_arr, tp, dp, mp, C.c_float(lambda_depth), on_host,
+                                                                          int(zero_grads), C.c_float(scale), loss_ptr)
+        else:
+            call = lambda loss_ptr: self.lib.gsb_trainer_accumulate(self.h, B, cam_arr, tp, on_host, int(zero_grads), C.c_float(scale),
+                                                                    loss_ptr)
         if loss_out is not None:
             assert self.cfg.flags & _lib.GSB_FLAG_ASYNC_LOSS and loss_out.is_pinned() and loss_out.dtype == torch.float32
-            self._check(self.lib.gsb_trainer_accumulate(self.h, B, cam_arr, tp, on_host, int(zero_grads), C.c_float(scale),
-                                                        C.c_void_p(loss_out.data_ptr())))
+            self._check(call(C.c_void_p(loss_out.data_ptr())))
             return None
         assert not (want_loss and self.cfg.flags & _lib.GSB_FLAG_ASYNC_LOSS), "async-loss contexts need loss_out"
         loss = C.c_float(0.0)
-        self._check(self.lib.gsb_trainer_accumulate(self.h, B, cam_arr, tp, on_host, int(zero_grads), C.c_float(scale),
-                                                    C.cast(C.pointer(loss), C.c_void_p) if want_loss else None))
+        self._check(call(C.cast(C.pointer(loss), C.c_void_p) if want_loss else None))
         return float(loss.value) if want_loss else None
 
     def trainer_apply(self, iteration: int, total_iterations: int, reset_state: bool = False):

@@ -118,7 +118,8 @@ struct Ctx {
     float* mapB = nullptr;
     float* mapC = nullptr;
     float* cot_render = nullptr;      // [P*3]
-    double* partial = nullptr;        // [2]
+    float* cot_depth = nullptr;       // [P] depth-supervision cotangent (allocated on first use)
+    double* partial = nullptr;        // [4]: L1 / SSIM sums, depth-loss sums
     float* loss_accum = nullptr;      // device scalar
     float* h_loss = nullptr;          // pinned
 
@@ -158,6 +159,8 @@ struct Ctx {
     int sym_world = 0, sym_rank = 0;
     float* sym_params = nullptr; float* sym_grads = nullptr; float* mc_params = nullptr; float* mc_grads = nullptr;
     float* t_target[2] = {nullptr, nullptr};
+    float* t_dtarget[2] = {nullptr, nullptr};     // depth targets / masks of host-resident depth supervision (first use)
+    uint8_t* t_dmask[2] = {nullptr, nullptr};
     cudaEvent_t t_target_ready[2] = {nullptr, nullptr};
     cudaEvent_t t_target_free[2] = {nullptr, nullptr};
 
@@ -552,7 +555,8 @@ static void destroy_ctx(Ctx* c)
         for (cudaEvent_t* e : evs) if (*e) cudaEventDestroy(*e);
     }
     dev_free(c->grad_rec); dev_free(c->grad_rec2); dev_free(c->act_tmp); dev_free(c->offsets_ref);
-    for (int i = 0; i < 2; ++i) dev_free(c->t_target[i]);
+    for (int i = 0; i < 2; ++i) { dev_free(c->t_target[i]); dev_free(c->t_dtarget[i]); dev_free(c->t_dmask[i]); }
+    dev_free(c->cot_depth);
     if (c->cub_tmp) cudaFree(c->cub_tmp);
     dev_free(c->dbg_keys); dev_free(c->dbg_vals);
     dev_free(c->out_color); dev_free(c->out_depth); dev_free(c->out_alpha); dev_free(c->out_last);
@@ -718,7 +722,7 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
     CREATE_CHECK(dev_alloc(&c->mapB, P * 3));
     CREATE_CHECK(dev_alloc(&c->mapC, P * 3));
     CREATE_CHECK(dev_alloc(&c->cot_render, P * 3));
-    CREATE_CHECK(dev_alloc(&c->partial, 2));
+    CREATE_CHECK(dev_alloc(&c->partial, 4));
     CREATE_CHECK(dev_alloc(&c->loss_accum, 4));
     CREATE_CHECK(dev_alloc(&c->d_zero, 4));
     c->d_one = c->d_zero + 1;
@@ -1156,7 +1160,17 @@ int gsb_render_backward(gsb_ctx* ctx, const float* cot_render, const float* cot_
 }
 
 // ---- loss ----------------------------------------------------------------------------------------
-static int loss_impl(Ctx* c, const float* render, const float* target, float grad_scale, float* cot_render, float* loss_accum)
+// Optional depth supervision of one view (GaussianTrainer.swift:693-699): rendered depth, target, mask, weight.
+struct DepthTerm {
+    const float* depth = nullptr;
+    const float* target = nullptr;
+    const uint8_t* mask = nullptr;
+    float lambda = 0.0f;
+    float* cot = nullptr;
+};
+
+static int loss_impl(Ctx* c, const float* render, const float* target, float grad_scale, float* cot_render, float* loss_accum,
+                     const DepthTerm* dt = nullptr)
 {
     gsb::StageTimer t(c, GSB_STAGE_LOSS);
     const int H = c->cfg.height, W = c->cfg.width;
@@ -1169,6 +1183,11 @@ static int loss_impl(Ctx* c, const float* render, const float* target, float gra
     if (loss_accum) GSB_CUDA_CHECK(c, gsb::launch_loss_finalize(c->stream, c->partial, 1.0 / n, lambda, grad_scale, loss_accum));
     GSB_CUDA_CHECK(c, gsb::launch_loss_bwd(c->stream, H, W, 3, render, target, c->mapA, c->mapB, c->mapC, l1_scale, cot_render));
     c->stats.kernel_launches += 2 + (loss_accum != nullptr);
+    if (dt) {
+        GSB_CUDA_CHECK(c, gsb::launch_depth_loss(c->stream, (size_t)c->P, dt->depth, dt->target, dt->mask, dt->lambda, grad_scale, dt->cot,
+                                                 c->partial + 2, loss_accum));
+        c->stats.kernel_launches += 2;
+    }
     return GSB_OK;
 }
 
@@ -1178,6 +1197,18 @@ int gsb_loss_fwd_bwd(gsb_ctx* ctx, const float* render, const float* target_rgb,
     CTX_PROLOGUE(ctx);
     GSB_REQUIRE(c, render && target_rgb && cot_render, "gsb_loss_fwd_bwd: null argument");
     return loss_impl(c, render, target_rgb, grad_scale, cot_render, loss_accum);
+}
+
+int gsb_loss_fwd_bwd_depth(gsb_ctx* ctx, const float* render, const float* depth, const float* target_rgb,
+                           const uint8_t* depth_mask, const float* target_depth, float lambda_depth, float grad_scale,
+                           float* cot_render, float* cot_depth, float* loss_accum)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, render && depth && target_rgb && depth_mask && target_depth && cot_render && cot_depth,
+                "gsb_loss_fwd_bwd_depth: null argument");
+    DepthTerm dt;
+    dt.depth = depth; dt.target = target_depth; dt.mask = depth_mask; dt.lambda = lambda_depth; dt.cot = cot_depth;
+    return loss_impl(c, render, target_rgb, grad_scale, cot_render, loss_accum, &dt);
 }
 
 // ---- Adam ----------------------------------------------------------------------------------------
@@ -1306,14 +1337,25 @@ int gsb_trainer_grad_block(gsb_ctx* ctx, float** grad_block, int64_t* floats)
     return GSB_OK;
 }
 
-int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
-                           int32_t targets_on_host, int32_t zero_grads, float grad_scale, float* host_loss)
+// One batch of views into the context's gradient buffers.  host_depths / host_masks (both or neither) switch on the
+// depth-supervision term with weight lambda_depth (GaussianTrainer.swift:693-714,949).
+static int trainer_accumulate_impl(Ctx* c, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
+                                   const float* const* host_depths, const uint8_t* const* host_masks, float lambda_depth,
+                                   int32_t targets_on_host, int32_t zero_grads, float grad_scale, float* host_loss)
 {
-    CTX_PROLOGUE(ctx);
     if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
     GSB_REQUIRE(c, B >= 0 && (B == 0 || (host_cams && host_targets)), "gsb_trainer_accumulate: null argument");
+    GSB_REQUIRE(c, (host_depths == nullptr) == (host_masks == nullptr), "gsb_trainer_accumulate_depth: depth targets and masks go together");
+    const bool with_depth = host_depths != nullptr && B > 0;
     const int N = c->tN;
     const size_t img_bytes = (size_t)c->P * 3 * sizeof(float);
+    if (with_depth) {
+        if (!c->cot_depth) GSB_CUDA_CHECK(c, gsb::dev_alloc(&c->cot_depth, (size_t)c->P));
+        for (int i = 0; i < 2 && targets_on_host; ++i) {
+            if (!c->t_dtarget[i]) GSB_CUDA_CHECK(c, gsb::dev_alloc(&c->t_dtarget[i], (size_t)c->P));
+            if (!c->t_dmask[i]) GSB_CUDA_CHECK(c, gsb::dev_alloc(&c->t_dmask[i], (size_t)c->P));
+        }
+    }
     if (host_loss) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->loss_accum, 0, sizeof(float), c->stream));
     if (zero_grads && B == 0) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_g[0], 0, c->t_floats * 4, c->stream));
     // prefetch of view 0's target
@@ -1321,6 +1363,11 @@ int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
         const int s = b & 1;
         GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->copy_stream, c->t_target_free[s], 0));
         GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->t_target[s], host_targets[b], img_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        if (with_depth) {
+            GSB_REQUIRE(c, host_depths[b] && host_masks[b], "gsb_trainer_accumulate_depth: null depth target / mask");
+            GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->t_dtarget[s], host_depths[b], (size_t)c->P * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+            GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->t_dmask[s], host_masks[b], (size_t)c->P, cudaMemcpyHostToDevice, c->copy_stream));
+        }
         GSB_CUDA_CHECK(c, cudaEventRecord(c->t_target_ready[s], c->copy_stream));
         c->stats.stage_calls[GSB_STAGE_H2D] += 1;
         return GSB_OK;
@@ -1378,18 +1425,24 @@ int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
         }
         const gsb::ViewParams vp = gsb::make_view(c, &host_cams[b]);
         if (overlap) GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, v.ev_front, 0));
-        int rc = enqueue_raster_fwd(c, v, N, rp, vp, false);
+        int rc = enqueue_raster_fwd(c, v, N, rp, vp, with_depth);
         if (rc != GSB_OK) return rc;
         const float* target = host_targets[b];
+        DepthTerm dt;
+        if (with_depth) {
+            GSB_REQUIRE(c, host_depths[b] && host_masks[b], "gsb_trainer_accumulate_depth: null depth target / mask");
+            dt.depth = c->out_depth; dt.target = host_depths[b]; dt.mask = host_masks[b]; dt.lambda = lambda_depth; dt.cot = c->cot_depth;
+        }
         if (targets_on_host) {
             GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->t_target_ready[b & 1], 0));
             target = c->t_target[b & 1];
+            dt.target = c->t_dtarget[b & 1]; dt.mask = c->t_dmask[b & 1];
         }
-        rc = loss_impl(c, c->out_color, target, grad_scale, c->cot_render, host_loss ? c->loss_accum : nullptr);
+        rc = loss_impl(c, c->out_color, target, grad_scale, c->cot_render, host_loss ? c->loss_accum : nullptr, with_depth ? &dt : nullptr);
         if (rc != GSB_OK) return rc;
         if (targets_on_host) GSB_CUDA_CHECK(c, cudaEventRecord(c->t_target_free[b & 1], c->stream));
         const int accumulate = (b > 0 || !zero_grads) ? 1 : 0;
-        rc = render_backward_impl(c, c->cot_render, nullptr, nullptr, c->t_g[0], c->t_g[1], c->t_g[2], c->t_g[3], c->t_g[4],
+        rc = render_backward_impl(c, c->cot_render, with_depth ? c->cot_depth : nullptr, nullptr, c->t_g[0], c->t_g[1], c->t_g[2], c->t_g[3], c->t_g[4],
                                   c->t_g[5], accumulate, overlap ? (b & 1) : -1);
         if (rc != GSB_OK) return rc;
         if (overlap) GSB_CUDA_CHECK(c, cudaEventRecord(v.ev_back, c->stream));   // raster backward done: the set is free
@@ -1406,6 +1459,23 @@ int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
         }
     }
     return GSB_OK;
+}
+
+int gsb_trainer_accumulate(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
+                           int32_t targets_on_host, int32_t zero_grads, float grad_scale, float* host_loss)
+{
+    CTX_PROLOGUE(ctx);
+    return trainer_accumulate_impl(c, B, host_cams, host_targets, nullptr, nullptr, 0.0f, targets_on_host, zero_grads, grad_scale, host_loss);
+}
+
+int gsb_trainer_accumulate_depth(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
+                                 const float* const* host_target_depths, const uint8_t* const* host_depth_masks, float lambda_depth,
+                                 int32_t targets_on_host, int32_t zero_grads, float grad_scale, float* host_loss)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, B == 0 || (host_target_depths && host_depth_masks), "gsb_trainer_accumulate_depth: null argument");
+    return trainer_accumulate_impl(c, B, host_cams, host_targets, host_target_depths, host_depth_masks, lambda_depth, targets_on_host,
+                                   zero_grads, grad_scale, host_loss);
 }
 
 static void learning_rates(int iteration, int total, float* lrs)
@@ -1678,6 +1748,13 @@ int gsb_trainer_densify(gsb_ctx* ctx, float grad_threshold, float max_scale, flo
     CTX_PROLOGUE(ctx);
     if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
     const int N = c->tN, K = c->cfg.sh_coeffs;
+    if (c->peer_world > 0) {
+        // densification swaps - and, when the capacity grows, frees - the slab the other replicas have mapped through CUDA
+        // IPC (freeing exported memory that an importer still has open is undefined behaviour)
+        gsb::set_error(c, "gsb_trainer_densify: peer mappings are open - every replica must call gsb_trainer_peers_close and pass a "
+                          "barrier first, and exchange the new slabs (export / import) afterwards");
+        return GSB_ERR_STATE;
+    }
     gsb::sync_all_streams(c);
     // scratch: actions | counts | offsets in the [capN,12] float parity buffer (capN >= N)
     int* actions = reinterpret_cast<int*>(c->act_tmp);

@@ -180,6 +180,31 @@ __device__ __forceinline__ void make_raster_record(float mx, float my, float c00
     out[1] = make_float4(C, log2f(opacity), r, g);
     out[2] = make_float4(b, opacity, depth, __uint_as_float(idx | (safe ? 0u : REC_MAYCLAMP)));
 }
+// Activation exponential, pinned by convention (the CPU checker restates the same sequence of
+// IEEE-754 f32 operations): the reference's MLX.exp / MLX.sigmoid (Trainer/GaussianRenderer.swift:936-963) cannot be reproduced
+// bit for bit off-device, and a 1-ulp difference in exp(scale) moves ceil() in the radius of a few Gaussians, i.e. the
+// tile lists.  Cephes-style: k = rint(x log2 e), two-step Cody-Waite reduction, degree-5 polynomial, 2^k applied in two
+// multiplies; explicit _rn intrinsics so that no translation unit contracts them into FMAs.  <= 1 ulp.
+__device__ __forceinline__ float gsb_expf(float x)
+{
+    if (x != x) return x;
+    if (x > 88.8f) return __int_as_float(0x7f800000);
+    if (x < -104.0f) return 0.0f;
+    const float kf = rintf(__fmul_rn(x, 1.44269504088896341f));
+    float r = __fsub_rn(x, __fmul_rn(kf, 0.693359375f));
+    r = __fsub_rn(r, __fmul_rn(kf, -2.12194440e-4f));
+    float p = 1.9875691500e-4f;
+    p = __fadd_rn(__fmul_rn(p, r), 1.3981999507e-3f);
+    p = __fadd_rn(__fmul_rn(p, r), 8.3334519073e-3f);
+    p = __fadd_rn(__fmul_rn(p, r), 4.1665795894e-2f);
+    p = __fadd_rn(__fmul_rn(p, r), 1.6666665459e-1f);
+    p = __fadd_rn(__fmul_rn(p, r), 5.0000001201e-1f);
+    float y = __fadd_rn(__fmul_rn(p, __fmul_rn(r, r)), r);
+    y = __fadd_rn(y, 1.0f);
+    const int k = (int)kf;
+    const int k1 = k / 2, k2 = k - k1;
+    return __fmul_rn(__fmul_rn(y, __int_as_float((k1 + 127) << 23)), __int_as_float((k2 + 127) << 23));
+}
 __device__ __forceinline__ float ex2_approx(float x)
 {
     float y;

@@ -163,6 +163,10 @@ cudaError_t launch_loss_bwd(cudaStream_t st, int H, int W, int C, const float* r
                             const float* mapA, const float* mapB, const float* mapC, float l1_scale, float* cot_render);
 cudaError_t launch_loss_finalize(cudaStream_t st, const double* partial, double inv_count, float lambda, float scale,
                                  float* loss_accum);
+// masked-L1 depth supervision: cot_depth[P] = lambda * scale * mask * sign(depth - target) / max(sum mask, 1e-6) and
+// loss_accum += lambda * scale * masked mean; partial2 = two doubles of scratch
+cudaError_t launch_depth_loss(cudaStream_t st, size_t P, const float* depth, const float* target_depth, const uint8_t* mask,
+                              float lambda_depth, float scale, float* cot_depth, double* partial2, float* loss_accum);
 // generic ssim backward for the parity API (upstream map given)
 cudaError_t launch_ssim_bwd_api(cudaStream_t st, int H, int W, int C, const float* grad_out, const float* img1,
                                 const float* img2, float* mapA, float* mapB, float* mapC, float* grad_img1);

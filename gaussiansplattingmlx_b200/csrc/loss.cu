@@ -358,6 +358,64 @@ __global__ void k_loss_finalize(const double* __restrict__ partial, double inv_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Depth supervision (Trainer/GaussianTrainer.swift:693-699,710-714; enabled when the dataset carries depth, :949):
+//     depthLoss = sum(|depth - target| * mask) / max(sum(mask), 1e-6),   total += lambda_depth * depthLoss
+// mask = target alpha > 0.5 as bytes (MLX bool array).  Two small HBM-bound passes: the reduction (sum of the masked
+// differences and of the mask, doubles), then the cotangent  lambda * scale * mask * sign(depth - target) / weight
+// (MLX abs has derivative 0 at 0) and the contribution to the loss scalar.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_depth_loss_reduce(size_t P, const float* __restrict__ depth, const float* __restrict__ target,
+                                                           const uint8_t* __restrict__ mask, double* __restrict__ partial)
+{
+    double a = 0.0, w = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x) {
+        const float m = mask[i] ? 1.0f : 0.0f;
+        a += (double)(fabsf(depth[i] - target[i]) * m);
+        w += (double)m;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        w += __shfl_xor_sync(0xffffffffu, w, o);
+    }
+    __shared__ double s_a[8], s_w[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_a[warp] = a; s_w[warp] = w; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0.0, tw = 0.0;
+        for (int i = 0; i < 8; ++i) { ta += s_a[i]; tw += s_w[i]; }
+        atomicAdd(&partial[0], ta);
+        atomicAdd(&partial[1], tw);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_depth_loss_bwd(size_t P, const float* __restrict__ depth, const float* __restrict__ target,
+                                                        const uint8_t* __restrict__ mask, const double* __restrict__ partial,
+                                                        float lambda_depth, float scale, float* __restrict__ cot_depth,
+                                                        float* __restrict__ loss_accum)
+{
+    const float weight = fmaxf((float)partial[1], 1e-6f);   // safeDepthWeight
+    const float g = lambda_depth * scale / weight;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x) {
+        const float d = depth[i] - target[i];
+        cot_depth[i] = mask[i] ? (d > 0.0f ? g : (d < 0.0f ? -g : 0.0f)) : 0.0f;
+    }
+    if (loss_accum && blockIdx.x == 0 && threadIdx.x == 0)
+        loss_accum[0] += (float)((double)lambda_depth * (partial[0] / (double)weight) * (double)scale);
+}
+
+cudaError_t launch_depth_loss(cudaStream_t st, size_t P, const float* depth, const float* target_depth, const uint8_t* mask,
+                              float lambda_depth, float scale, float* cot_depth, double* partial2, float* loss_accum)
+{
+    cudaError_t e = cudaMemsetAsync(partial2, 0, 2 * sizeof(double), st);
+    if (e != cudaSuccess || P == 0) return e;
+    const int blocks = (int)std::min<size_t>((P + 255) / 256, 148 * 8);
+    k_depth_loss_reduce<<<blocks, 256, 0, st>>>(P, depth, target_depth, mask, partial2);
+    k_depth_loss_bwd<<<blocks, 256, 0, st>>>(P, depth, target_depth, mask, partial2, lambda_depth, scale, cot_depth, loss_accum);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 static const SsimWindow& window()

@@ -130,6 +130,18 @@ class ViewParallel:
         ctx.trainer_apply_peers(iteration, total_iterations, reset_state)
         self.stream_barrier()            # every replica's parameters (and D1 accumulators) are written
 
+    def all_reduce_scalar_sum(self, value: float, device=None) -> float:
+        """SUM over ranks of a host scalar (the reported batch loss: every rank holds the part of its own views)."""
+        if self.world == 1:
+            return value
+        import torch
+        import torch.distributed as dist
+        if dist.get_backend(self.group) != "nccl":
+            device = None
+        t = torch.tensor([value], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return float(t.item())
+
     def all_reduce_max(self, value: float, device=None) -> float:
         if self.world == 1:
             return value

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GSB_ABI_VERSION 1
+#define GSB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GSB_API __attribute__((visibility("default")))
@@ -178,6 +178,15 @@ GSB_API int gsb_render_backward(gsb_ctx*, const float* cot_render, const float* 
  * grad_scale*total into *loss_accum (device scalar). */
 GSB_API int gsb_loss_fwd_bwd(gsb_ctx*, const float* render, const float* target_rgb, float grad_scale,
                      float* cot_render, float* loss_accum);
+/* The same with the depth-supervision term of lossFn (GaussianTrainer.swift:693-699,710-714; the trainer enables it
+ * whenever the dataset carries depth, :949):
+ *   total += lambda_depth * sum(|depth - target_depth| * mask) / max(sum(mask), 1e-6)
+ * depth[H,W,1] = the renderer's depth output, target_depth[H,W] f32, depth_mask[H,W] one byte per pixel (the MLX bool
+ * array `alpha > 0.5`, GaussianTrainer.swift:492).  Also writes cot_depth[H,W,1] = d total / d depth (scaled by grad_scale),
+ * to be handed to gsb_render_backward. */
+GSB_API int gsb_loss_fwd_bwd_depth(gsb_ctx*, const float* render, const float* depth, const float* target_rgb,
+                           const uint8_t* depth_mask, const float* target_depth, float lambda_depth, float grad_scale,
+                           float* cot_render, float* cot_depth, float* loss_accum);
 
 /* ---- Adam (MLXOptimizers.Adam.applySingle x6, GaussianTrainer.swift:1066-1079) + D1
  *      accum_grad_norm (GaussianTrainer.swift:321-339), one launch.  No bias correction.
@@ -205,6 +214,13 @@ GSB_API int gsb_trainer_grad_block(gsb_ctx*, float** grad_block, int64_t* floats
  * host_loss (may be NULL) receives the mean loss and makes the call synchronise (unless GSB_FLAG_ASYNC_LOSS). */
 GSB_API int gsb_trainer_accumulate(gsb_ctx*, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
                            int32_t targets_on_host, int32_t zero_grads, float grad_scale, float* host_loss);
+/* gsb_trainer_accumulate with depth supervision (GaussianTrainer.swift:949: effectiveLambdaDepth = lambda_depth when the
+ * dataset has depth): host_target_depths[b] -> f32[H,W], host_depth_masks[b] -> one byte per pixel; both live where the
+ * RGB targets live (device, or pinned host memory when targets_on_host != 0). */
+GSB_API int gsb_trainer_accumulate_depth(gsb_ctx*, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
+                                 const float* const* host_target_depths, const uint8_t* const* host_depth_masks,
+                                 float lambda_depth, int32_t targets_on_host, int32_t zero_grads, float grad_scale,
+                                 float* host_loss);
 /* Adam + D1 on the context's buffers; learning rates from (iteration, total_iterations)
  * (GaussianModel.swift:56-65).  reset_state != 0 re-zeroes m/v first (GaussianTrainer.swift:1104-1109). */
 GSB_API int gsb_trainer_apply(gsb_ctx*, int32_t iteration, int32_t total_iterations, int32_t reset_state);
@@ -216,8 +232,11 @@ GSB_API int gsb_trainer_apply(gsb_ctx*, int32_t iteration, int32_t total_iterati
  *       gsb_trainer_apply_peers   -- rank r sums slice r of ALL replicas' gradients (peer loads), applies Adam + D1 with
  *                                    its local m / v, stores the new parameters into EVERY replica (peer stores)
  *       barrier (every replica's parameters are written)
- * The mapping survives gsb_trainer_init with the same N; it is dropped by a different N, by densification (the slabs
- * swap: export / import again) and by gsb_destroy.  gsb_trainer_apply_peers fails with GSB_ERR_STATE without it. */
+ * The mapping survives gsb_trainer_init with the same N; it is dropped by a different N and by gsb_destroy.
+ * gsb_trainer_apply_peers fails with GSB_ERR_STATE without it.  Densification swaps (and may free) the slab the other
+ * replicas have mapped: EVERY replica must call gsb_trainer_peers_close and pass a host barrier before
+ * gsb_trainer_densify (which otherwise fails with GSB_ERR_STATE), then export / import the new slabs; the same close +
+ * barrier is required before any replica's gsb_destroy. */
 #define GSB_PEER_BLOB_BYTES 256
 GSB_API int gsb_trainer_peers_export(gsb_ctx*, void* host_blob, int64_t blob_bytes);
 GSB_API int gsb_trainer_peers_import(gsb_ctx*, int32_t world, int32_t rank, const void* host_blobs, int64_t blob_bytes);
@@ -260,7 +279,8 @@ GSB_API int gsb_densify_apply(gsb_ctx*, int32_t N_out, const int32_t* gather_ind
 /* split_and_prune on the trainer's own tensors: classify with the accumulated gradient norms, rebuild parameters
  * (new Gaussian count), re-create the Adam state and reset the accumulation (GaussianTrainer.swift:1098-1109).
  * max_gaussians: densification is allowed while N < max_gaussians (:785).  base_noise: device f32[>= 2N,3] or NULL.
- * host_counts5 (may be NULL) = {keep, split, clone, prune, total}.  Synchronises. */
+ * host_counts5 (may be NULL) = {keep, split, clone, prune, total}.  Synchronises.  GSB_ERR_STATE while peer mappings
+ * (gsb_trainer_peers_import) are open. */
 GSB_API int gsb_trainer_densify(gsb_ctx*, float grad_threshold, float max_scale, float min_opacity, int32_t max_gaussians,
                         uint64_t seed, const float* base_noise, int32_t* host_counts5);
 /* current Gaussian count of the trainer and the number of iterations accumulated since the last reset */

@@ -25,6 +25,48 @@ static inline float clampf_(float x, float lo, float hi) { return fminf_(fmaxf_(
 GSO_API int gso_abi_version(void) { return 1; }
 
 /* ------------------------------------------------------------------------------------------
+ * Activation exponential, PINNED BY CONVENTION.  The reference computes exp / sigmoid with MLX ops
+ * (Trainer/GaussianRenderer.swift:936-963: MLX.exp, MLX.sigmoid) whose Metal fast-math bits cannot be
+ * reproduced off-device ("parity unpinned").  A 1-ulp difference in exp(scale) flips
+ * ceil() in the radius of a handful of Gaussians, so the tile lists of the fused path would only
+ * match "almost".  The arithmetic is therefore fixed here and restated op for op in the CUDA library
+ * (csrc/common.cuh gsb_expf): Cephes-style range reduction k = rint(x log2 e), r = x - k ln2 (two-step
+ * Cody-Waite), degree-5 polynomial, every operation a single IEEE-754 f32 rounding (no FMA), scaling
+ * by 2^k in two exact-or-once-rounded multiplies.  <= 1 ulp from the exact value
+ * (tests/test_oracle_pinning.py), identical bits on CPU and GPU.
+ * ---------------------------------------------------------------------------------------- */
+static inline float gso_pow2i(int k)   /* 2^k for -126 <= k <= 127 */
+{
+    union { unsigned u; float f; } c;
+    c.u = (unsigned)(k + 127) << 23;
+    return c.f;
+}
+GSO_API float gso_expf(float x)
+{
+    if (x != x) return x;
+    if (x > 88.8f) return INFINITY;
+    if (x < -104.0f) return 0.0f;
+    const float kf = rintf(x * 1.44269504088896341f);
+    float r = x - kf * 0.693359375f;
+    r = r - kf * -2.12194440e-4f;
+    float p = 1.9875691500e-4f;
+    p = p * r + 1.3981999507e-3f;
+    p = p * r + 8.3334519073e-3f;
+    p = p * r + 4.1665795894e-2f;
+    p = p * r + 1.6666665459e-1f;
+    p = p * r + 5.0000001201e-1f;
+    float y = p * (r * r) + r;
+    y = y + 1.0f;
+    const int k = (int)kf;
+    const int k1 = k / 2, k2 = k - k1;
+    return (y * gso_pow2i(k1)) * gso_pow2i(k2);
+}
+GSO_API void gso_expf_array(int n, const float* x, float* y)
+{
+    for (int i = 0; i < n; ++i) y[i] = gso_expf(x[i]);
+}
+
+/* ------------------------------------------------------------------------------------------
  * Activations.  Trainer/GaussianRenderer.swift:936-963 (get_*_from), called from
  * Trainer/GaussianTrainer.swift:652-666.
  *   means3d = xyz; opacity = sigmoid(o); scales = exp(s); rotations = q/(||q||+1e-8);
@@ -38,12 +80,12 @@ GSO_API void gso_activate_fwd(int N, int K, const float* f_dc, const float* f_re
     for (int p = 0; p < N; ++p) {
         for (int c = 0; c < 3; ++c) shs[(size_t)p * K * 3 + c] = f_dc[(size_t)p * 3 + c];
         for (int j = 0; j < (K - 1) * 3; ++j) shs[(size_t)p * K * 3 + 3 + j] = f_rest[(size_t)p * (K - 1) * 3 + j];
-        for (int c = 0; c < 3; ++c) scales[p * 3 + c] = expf(scales_log[p * 3 + c]);
+        for (int c = 0; c < 3; ++c) scales[p * 3 + c] = gso_expf(scales_log[p * 3 + c]);
         const float* q = rot_raw + (size_t)p * 4;
         float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
         float d = n + 1e-8f;
         for (int c = 0; c < 4; ++c) rotations[p * 4 + c] = q[c] / d;
-        opacity[p] = 1.0f / (1.0f + expf(-opacity_logit[p]));
+        opacity[p] = 1.0f / (1.0f + gso_expf(-opacity_logit[p]));
     }
 }
 
@@ -57,7 +99,7 @@ GSO_API void gso_activate_bwd(int N, int K, const float* scales_log, const float
     for (int p = 0; p < N; ++p) {
         for (int c = 0; c < 3; ++c) g_f_dc[(size_t)p * 3 + c] = g_shs[(size_t)p * K * 3 + c];
         for (int j = 0; j < (K - 1) * 3; ++j) g_f_rest[(size_t)p * (K - 1) * 3 + j] = g_shs[(size_t)p * K * 3 + 3 + j];
-        for (int c = 0; c < 3; ++c) g_scales_log[p * 3 + c] = g_scales[p * 3 + c] * expf(scales_log[p * 3 + c]);
+        for (int c = 0; c < 3; ++c) g_scales_log[p * 3 + c] = g_scales[p * 3 + c] * gso_expf(scales_log[p * 3 + c]);
         const float* q = rot_raw + (size_t)p * 4;
         const float* gq = g_rotations + (size_t)p * 4;
         float n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
@@ -67,7 +109,7 @@ GSO_API void gso_activate_bwd(int N, int K, const float* scales_log, const float
         float dot = gq[0] * q[0] + gq[1] * q[1] + gq[2] * q[2] + gq[3] * q[3];
         float gd = -dot / (d * d);
         for (int c = 0; c < 4; ++c) g_rot_raw[p * 4 + c] = gq[c] / d + (n > 0.0f ? gd * q[c] / n : 0.0f);
-        float s = 1.0f / (1.0f + expf(-opacity_logit[p]));
+        float s = 1.0f / (1.0f + gso_expf(-opacity_logit[p]));
         g_opacity_logit[p] = g_opacity[p] * s * (1.0f - s);
     }
 }

@@ -56,6 +56,18 @@ def loss_forward_backward(o, render, target, lambda_dssim=0.2):
             "cot_render": (g_l1 + g_ssim).astype(f32)}
 
 
+def depth_loss_forward_backward(depth, target_depth, depth_mask, lambda_depth):
+    """Depth supervision of lossFn: ``GaussianTrainer.swift:492`` (depthMask = alpha > 0.5, passed in here as a bool
+    array), ``:693-699`` (sum(|depth[...,0] - trainDepth| * mask) / max(sum(mask), 1e-6)), ``:710-714`` (weight
+    lambdaDepth).  Returns the weighted loss term and d total / d depth [H,W,1] (MLX abs: derivative 0 at 0)."""
+    m = np.asarray(depth_mask).astype(f32)
+    diff = depth[..., 0].astype(f32) - np.asarray(target_depth, f32)
+    weight = max(f32(m.sum(dtype=np.float64)), f32(1e-6))
+    term = float((np.abs(diff) * m).sum(dtype=np.float64) / float(weight))
+    cot = (f32(lambda_depth) * m * np.sign(diff) / weight).astype(f32)
+    return {"depth_loss": term, "weighted": float(lambda_depth) * term, "cot_depth": cot[..., None]}
+
+
 def backward(o, params, cam, degree, fr, cot_render, cot_depth=None, cot_alpha=None, tileW=16, tileH=16,
              white_bg=False):
     W, H = cam.imageWidth, cam.imageHeight
@@ -76,10 +88,16 @@ def backward(o, params, cam, degree, fr, cot_render, cot_depth=None, cot_alpha=N
             "grad_camera_center": gproj["cameraCenterPoint"].sum(axis=0, dtype=np.float64)}
 
 
-def loss_and_grads(o, params, cam, target, degree, lambda_dssim=0.2, tileW=16, tileH=16, white_bg=False):
+def loss_and_grads(o, params, cam, target, degree, lambda_dssim=0.2, tileW=16, tileH=16, white_bg=False,
+                   target_depth=None, depth_mask=None, lambda_depth=0.0):
     fr = render_forward(o, params, cam, degree, tileW, tileH, white_bg)
     lo = loss_forward_backward(o, fr["render"], target, lambda_dssim)
-    bw = backward(o, params, cam, degree, fr, lo["cot_render"], tileW=tileW, tileH=tileH, white_bg=white_bg)
+    cot_depth = None
+    if target_depth is not None:
+        dl = depth_loss_forward_backward(fr["depth"], target_depth, depth_mask, lambda_depth)
+        lo = dict(lo, loss=lo["loss"] + dl["weighted"], depth_loss=dl["depth_loss"], cot_depth=dl["cot_depth"])
+        cot_depth = dl["cot_depth"]
+    bw = backward(o, params, cam, degree, fr, lo["cot_render"], cot_depth=cot_depth, tileW=tileW, tileH=tileH, white_bg=white_bg)
     return fr, lo, bw
 
 

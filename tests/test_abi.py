@@ -51,7 +51,7 @@ def test_struct_layouts_match_header(lib):
     assert C.sizeof(_lib.GsbConfig) == 14 * 4
     assert C.sizeof(_lib.GsbCamera) == 39 * 4
     assert C.sizeof(_lib.GsbStats) == 5 * 8 + 16 * 8 + 16 * 8 + 8
-    assert lib.gsb_abi_version() == 1
+    assert lib.gsb_abi_version() == 2
     cfg = _lib.GsbConfig()
     lib.gsb_default_config(C.byref(cfg))
     assert (cfg.tile_w, cfg.tile_h, cfg.sh_degree, cfg.sh_coeffs) == (16, 16, 3, 16)

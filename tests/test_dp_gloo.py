@@ -78,3 +78,68 @@ def test_view_parallel_gradient_equals_batch_gradient(tmp_path):
         _, _, bw = pl.loss_and_grads(o, params, cams[v], targets[v], 2)
         ref += np.concatenate([bw["grads"][k].reshape(-1) for k in params]).astype(np.float64) / B
     assert np.abs(b0 - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+# ------------------------------------------------------------------------------------------------
+# host logic of GaussianTrainer.startTrain on two ranks: the early-stopping decision must be taken from the
+# batch loss summed over ranks (a rank-local loss would let one rank leave the loop while the other blocks in
+# the next collective) and before the optimiser update, like the reference (GaussianTrainer.swift:1003-1058)
+# ------------------------------------------------------------------------------------------------
+class _FakeCtx:
+    """Duck-typed stand-in for context.Context: records the calls the trainer makes, no GPU."""
+    device = None
+
+    def __init__(self, losses):
+        self.losses, self.applied, self.accumulated = list(losses), [], []
+        self.block = torch.zeros(8)
+
+    def trainer_init(self, params): pass
+    def trainer_grad_block(self): return self.block
+    def trainer_tensors(self):
+        z = {k: torch.zeros(1) for k in ("_xyz", "_features_dc", "_features_rest", "_scales", "_rotation", "_opacity")}
+        return {"params": z, "m": z, "v": z}
+
+    def trainer_accumulate(self, cams, targets, zero_grads=True, grad_scale=None, want_loss=True, **kw):
+        self.accumulated.append(len(cams))
+        return self.losses.pop(0) if want_loss else None
+
+    def trainer_apply(self, iteration, total, reset_state=False): self.applied.append(iteration)
+    def trainer_densify(self, *a, **k): raise AssertionError("densification is outside [500, 15000] in this test")
+
+
+def _trainer_worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    from types import SimpleNamespace
+    from gaussiansplattingmlx_b200.dp import ViewParallel
+    from gaussiansplattingmlx_b200.model import GaussModel
+    from gaussiansplattingmlx_b200.scene import make_cameras, make_gaussians
+    from gaussiansplattingmlx_b200.trainer import GaussianTrainer, TrainData
+    from gaussiansplattingmlx_b200 import _lib
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    _lib.make_camera = lambda c: c                       # no ctypes camera needed by the fake context
+    cams = make_cameras(16, 16, 3)
+    data = TrainData(cams, [np.zeros((16, 16, 3), np.float32)] * 3)
+    # one view per step: rank 0 renders it, rank 1 has no view and contributes 0 to the batch loss.
+    # loss read-backs happen on iterations 0, 9, 19, 20: 0.5, 0.25, then 5e-5 < 1e-4 on iteration 19
+    ctx = _FakeCtx([0.5, 0.25, 5e-5] if rank == 0 else [])
+    params = make_gaussians(10, 1, 1)
+    model = GaussModel.__new__(GaussModel)
+    for k, v in params.items():
+        setattr(model, k, v)
+    tr = GaussianTrainer(model, data, SimpleNamespace(ctx=ctx), iterationCount=100, views_per_step=1,
+                         parallel=ViewParallel.from_env(), seed=0)
+    assert tr._peers is False                            # gloo: all-reduce + apply
+    tr.startTrain(earlyStoppingThreshold=1e-4)
+    np.save(Path(out_dir) / f"trainer_{rank}.npy", np.array([len(ctx.applied), int(tr.stopped_early), len(tr.losses),
+                                                              len(ctx.accumulated)] + [round(l, 9) for l in tr.losses]))
+    dist.destroy_process_group()
+
+
+def test_trainer_early_stop_is_a_collective_decision(tmp_path):
+    world = 2
+    mp.spawn(_trainer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0 = np.load(tmp_path / "trainer_0.npy"); r1 = np.load(tmp_path / "trainer_1.npy")
+    # both ranks applied iterations 0..18 and stopped on iteration 19 before its update, with the same reported losses
+    assert r0[0] == r1[0] == 19 and r0[1] == r1[1] == 1 and r0[2] == r1[2] == 3
+    assert np.array_equal(r0[4:], r1[4:]) and abs(r0[-1] - 5e-5) < 1e-12
+    assert r0[3] == 20 and r1[3] == 0                    # only rank 0 rendered

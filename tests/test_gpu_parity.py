@@ -223,6 +223,55 @@ def test_loss_fwd_bwd_parity(gsb, best_oracle):
     assert rel_err(cot.cpu().numpy(), lo["cot_render"]) < GRAD_TOL
 
 
+def test_depth_supervised_loss_and_training_path(gsb, best_oracle):
+    """lossFn's depth term (GaussianTrainer.swift:693-714, on whenever the dataset has depth, :949): masked L1 with the
+    safe weight, its cotangent through the raster / projection backward, and the trainer entry point with depth targets
+    on the device and in pinned host memory - against the oracle's restatement."""
+    Context, L = gsb
+    o = best_oracle
+    n, W, H, degree, lam = 900, 80, 56, 3, 0.35
+    params = make_gaussians(n, 91, degree)
+    cam = make_cameras(W, H, 3)[1]
+    target = make_targets(W, H, 1, 91)[0]
+    rng = np.random.default_rng(92)
+    tdepth = (rng.random((H, W), dtype=np.float32) * 6.0).astype(np.float32)
+    mask = rng.random((H, W)) > 0.4
+    fr, lo, bw = pl.loss_and_grads(o, params, cam, target, degree, target_depth=tdepth, depth_mask=mask, lambda_depth=lam)
+    ctx = Context(W, H, sh_degree=degree)
+    gcam = L.make_camera(cam)
+    dparams = {k: dev(v) for k, v in params.items()}
+    render, depth, alpha, vis, radii = ctx.render_forward(dparams, gcam)
+    dmask = dev(mask.astype(np.uint8))
+    loss, cot, cot_depth = ctx.loss_fwd_bwd(render, dev(target), 1.0, depth=depth, depth_mask=dmask, target_depth=dev(tdepth),
+                                            lambda_depth=lam)
+    assert abs(float(loss.item()) - lo["loss"]) < 3e-5 and lo["depth_loss"] > 0.1
+    # sign(depth - target) can flip where the two differ by less than the raster tolerance
+    near = np.abs(fr["depth"][..., 0] - tdepth) < 1e-3
+    d = np.abs(cot_depth.cpu().numpy() - lo["cot_depth"])[..., 0]
+    assert d[~near].max() <= 1e-6 * np.abs(lo["cot_depth"]).max() and near.mean() < 0.01
+    grads = ctx.render_backward(cot, cot_depth=cot_depth)
+    for k, g in grads.items():
+        assert rel_err(g.cpu().numpy().reshape(bw["grads"][k].shape), bw["grads"][k]) < GRAD_TOL, k
+    # an all-false mask: weight = max(0, 1e-6), zero loss term, zero cotangent
+    l0, _, cd0 = ctx.loss_fwd_bwd(render, dev(target), 1.0, depth=depth, depth_mask=torch.zeros_like(dmask), target_depth=dev(tdepth),
+                                  lambda_depth=lam)
+    l_rgb, _ = ctx.loss_fwd_bwd(render, dev(target), 1.0)
+    assert float(cd0.abs().max()) == 0.0 and abs(float(l0.item()) - float(l_rgb.item())) < 1e-7
+    # trainer path: device-resident and pinned-host depth targets give the oracle's loss and gradient block
+    for on_host in (False, True):
+        tctx = Context(W, H, sh_degree=degree)
+        tctx.trainer_init({k: torch.from_numpy(v) for k, v in params.items()})
+        put = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()) if on_host else dev
+        l = tctx.trainer_accumulate([gcam], [put(target)], grad_scale=1.0, target_depths=[put(tdepth)],
+                                    depth_masks=[put(mask.astype(np.uint8))], lambda_depth=lam)
+        assert abs(l - lo["loss"]) < 3e-5
+        tg = tctx.trainer_tensors()["grads"]
+        for k in params:
+            assert rel_err(tg[k].cpu().numpy().reshape(bw["grads"][k].shape), bw["grads"][k]) < GRAD_TOL, (on_host, k)
+        tctx.close()
+    ctx.close()
+
+
 def test_adam_bit_exact(gsb, port):
     Context, _ = gsb
     ctx = Context(64, 64)
@@ -263,10 +312,14 @@ def test_fused_render_and_backward_vs_oracle(gsb, best_oracle, name):
     assert np.abs(alpha.cpu().numpy() - fr["alpha"]).max() <= PIX_TOL
     assert np.abs(depth.cpu().numpy() - fr["depth"]).max() <= PIX_TOL * 10
     assert (vis.cpu().numpy() == fr["visibility_filter"]).all()
-    # device expf differs from libm by <= 1 ulp in the scale activation: radii may flip for a handful
-    assert (radii.cpu().numpy() != fr["radii"]).mean() < 1e-3
+    # the activation exponential is pinned by convention (common.cuh gsb_expf == the oracle's gso_expf, bit for bit), so
+    # the fused path's geometry - radii, pair count, tile lists - equals the oracle's exactly
+    assert np.array_equal(radii.cpu().numpy(), fr["radii"])
     st = ctx.stats()
-    assert abs(st["pairs_last_view"] - fr["bins"]["M"]) <= max(4, fr["bins"]["M"] // 1000)
+    assert st["pairs_last_view"] == fr["bins"]["M"]
+    lists = ctx.bin_read()
+    for k in ("sortedKeysHigh", "sortedKeysLow", "sortedGaussIdx"):
+        assert np.array_equal(u32(lists[k]), fr["bins"][k]), k
     loss, cot = ctx.loss_fwd_bwd(render, dev(target), 1.0)
     assert abs(float(loss.item()) - lo["loss"]) < 2e-5
     grads = ctx.render_backward(cot)
@@ -343,30 +396,56 @@ def test_segmented_backward_checkpoint_pool_exhausted(gsb, monkeypatch):
             assert rel_err(grads[slots][0][k].cpu().numpy(), grads[None][0][k].cpu().numpy()) < 1e-4, (slots, k)
 
 
-def test_train_steps_vs_oracle(gsb, best_oracle):
-    """Three batched train steps (B = 2 views) through gsb_train_step vs the oracle loop."""
+def test_train_steps_vs_oracle(gsb, best_oracle, port):
+    """Three batched train steps (B = 2 views).  Every iteration is checked in two tight halves instead of through
+    parameter deltas (Adam without bias correction turns a first-step gradient into ~3.2 lr sign(g), which amplifies
+    last-bit noise of near-zero gradients to O(lr)):
+      * the PRE-ADAM gradient block of gsb_trainer_accumulate against the oracle's batch-mean gradient at the SAME
+        parameters (<= 1e-3 relative per tensor), and the loss;
+      * gsb_trainer_apply against the C port's Adam + accum_grad_norm fed with that very gradient block: bit-exact
+        parameters, m, v and D1 accumulator."""
     Context, L = gsb
     o = best_oracle
     n, W, H = 600, 64, 48
     params = make_gaussians(n, 21, 3)
     cams = make_cameras(W, H, 2)
     targets = make_targets(W, H, 2, 21)
-    p_o, m_o, v_o, acc_o, losses_o = pl.train_steps(o, params, cams, targets, 3, 3, 100)
     ctx = Context(W, H)
     ctx.trainer_init({k: torch.from_numpy(v) for k, v in params.items()})
     gcams = [L.make_camera(c) for c in cams]
-    for host in (True,):
-        tg = [torch.from_numpy(t).pin_memory() for t in targets]
-        losses = [ctx.train_step(gcams, tg, it, 100) for it in range(3)]
-    tt = ctx.trainer_tensors()
-    for a, b in zip(losses, losses_o):
-        assert abs(a - b) < 5e-5
-    # Adam normalises the step to ~lr regardless of gradient scale: compare the parameter DELTAS
-    for k in params:
-        d_g = tt["params"][k].cpu().numpy().reshape(params[k].shape) - params[k]
-        d_o = p_o[k] - params[k]
-        assert rel_err(d_g, d_o) < 2e-2, k
-    assert rel_err(tt["accum"].cpu().numpy(), acc_o) < GRAD_TOL
+    tg = [torch.from_numpy(t).pin_memory() for t in targets]
+    worst = 0.0
+    for it in range(3):
+        tt = ctx.trainer_tensors()
+        host = {k: tt["params"][k].cpu().numpy().reshape(params[k].shape).copy() for k in params}
+        m_h = {k: tt["m"][k].cpu().numpy().copy() for k in params}
+        v_h = {k: tt["v"][k].cpu().numpy().copy() for k in params}
+        acc_h = tt["accum"].cpu().numpy().copy()
+        loss = ctx.trainer_accumulate(gcams, tg, zero_grads=True, grad_scale=0.5)
+        g_dev = {k: tt["grads"][k].cpu().numpy().copy() for k in params}
+        gsum = {k: np.zeros(params[k].shape, np.float64) for k in params}
+        loss_o = 0.0
+        for b in range(2):
+            _, lo, bw = pl.loss_and_grads(o, host, cams[b], targets[b], 3)
+            loss_o += lo["loss"] / 2
+            for k in gsum:
+                gsum[k] += bw["grads"][k].reshape(gsum[k].shape).astype(np.float64) / 2
+        assert abs(loss - loss_o) < 5e-5
+        for k in params:
+            e = rel_err(g_dev[k].reshape(gsum[k].shape), gsum[k])
+            worst = max(worst, e)
+            assert e < GRAD_TOL, (it, k, e)
+        ctx.trainer_apply(it, 100)
+        lrs = pl.learning_rates(it, 100)
+        port.accum_grad_norm(np.ascontiguousarray(g_dev["_xyz"].reshape(n, 3)), acc_h)
+        for i, k in enumerate(pl.PARAM_ORDER):
+            p_h = np.ascontiguousarray(host[k].reshape(g_dev[k].shape))
+            port.adam(p_h, np.ascontiguousarray(g_dev[k]), m_h[k], v_h[k], lrs[i])
+            assert np.array_equal(tt["params"][k].cpu().numpy().view(np.uint32), p_h.view(np.uint32)), (it, k)
+            assert np.array_equal(tt["m"][k].cpu().numpy().view(np.uint32), m_h[k].view(np.uint32)), (it, k)
+            assert np.array_equal(tt["v"][k].cpu().numpy().view(np.uint32), v_h[k].view(np.uint32)), (it, k)
+        assert np.array_equal(tt["accum"].cpu().numpy().view(np.uint32), acc_h.view(np.uint32)), it
+    print(f"train steps: worst pre-Adam gradient error {worst:.2e} relative")
 
 
 def test_view_pipeline_matches_serial_and_regrows(gsb):
@@ -495,6 +574,69 @@ def test_cuda_path_vs_reference_golden(gsb, port, name):
 
 
 # ------------------------------------------------------------------------------------------------
+# BASELINE.json's own sizes against the reference-kernel oracle (one view each: ~3 s / ~9 s of CPU on the GPU box)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wl_name", ["C2", "C3"])
+def test_baseline_sizes_vs_reference_oracle(gsb, best_oracle, wl_name):
+    """C2 (300 k Gaussians, 800x800) and C3 (1 M Gaussians, 1080p), seed / view 0 of SURVEY.md 8d, through the oracle
+    (the reference's shipped kernels compiled for the host when oracle/_ref is present):
+      * stage API on the oracle's projection: M, tiles-touched, tile counts, sorted (tile, depth) keys and Gaussian
+        lists BIT-EXACT (slang/gaussian_tile_global_kernels.slang:17-404);
+      * fused product path (raw tensors in): the same M, radii and sorted lists bit-exact (activation exp pinned by
+        convention), pixels <= 1e-4 max-abs (:523-614), loss, and all six gradient tensors <= 1e-3 relative (:648-881,
+        gaussian_projection_kernels.slang:205-398).
+    The measured errors are printed (pytest -s / the GPU test log)."""
+    Context, L = gsb
+    o = best_oracle
+    wl, params, cams, targets = make_workload(wl_name, views_override=1)
+    N = params["_xyz"].shape[0]
+    W, H, degree = wl.width, wl.height, wl.sh_degree
+    fr, lo, bw = pl.loss_and_grads(o, params, cams[0], targets[0], degree, 0.2, wl.tile, wl.tile)
+    bo = fr["bins"]
+    ctx = Context(W, H, tile_w=wl.tile, tile_h=wl.tile, sh_degree=degree, max_gaussians=N)
+    gcam = L.make_camera(cams[0])
+    # --- stage API on the oracle's projection
+    bg = ctx.bin({k: dev(v) for k, v in fr["proj"].items()})
+    assert bg["M"] == bo["M"]
+    for k in ("tilesTouched", "tileCounts", "sortedKeysHigh", "sortedKeysLow", "sortedGaussIdx"):
+        assert np.array_equal(u32(bg[k]), bo[k]), f"stage API {k}"
+    del bg
+    # --- fused product path
+    dparams = {k: dev(v) for k, v in params.items()}
+    render, depth, alpha, vis, radii = ctx.render_forward(dparams, gcam)
+    M = ctx.stats()["pairs_last_view"]
+    flips = int((radii.cpu().numpy() != fr["radii"]).sum())
+    assert M == bo["M"] and flips == 0, f"fused path: M {M} vs {bo['M']}, {flips} radius flips"
+    lists = ctx.bin_read()
+    for k in ("sortedKeysHigh", "sortedKeysLow", "sortedGaussIdx"):
+        assert np.array_equal(u32(lists[k]), bo[k]), f"fused path {k}"
+    del lists
+    e_pix = float(np.abs(render.cpu().numpy() - fr["render"]).max())
+    e_alpha = float(np.abs(alpha.cpu().numpy() - fr["alpha"]).max())
+    e_depth = float(np.abs(depth.cpu().numpy() - fr["depth"]).max())
+    assert e_pix <= PIX_TOL and e_alpha <= PIX_TOL and e_depth <= PIX_TOL * 10
+    assert (vis.cpu().numpy() == fr["visibility_filter"]).all()
+    loss, cot = ctx.loss_fwd_bwd(render, dev(targets[0]), 1.0)
+    e_loss = abs(float(loss.item()) - lo["loss"])
+    assert e_loss < 2e-5
+    e_cot = rel_err(cot.cpu().numpy(), lo["cot_render"])
+    assert e_cot < GRAD_TOL
+    grads = ctx.render_backward(cot)
+    errs = {k: rel_err(g.cpu().numpy().reshape(bw["grads"][k].shape), bw["grads"][k]) for k, g in grads.items()}
+    print(f"\n[{wl_name} vs {o.kind} oracle] N={N} M={M} (bit-exact lists) pixels {e_pix:.2e} alpha {e_alpha:.2e} depth {e_depth:.2e} "
+          f"loss {e_loss:.2e} cot {e_cot:.2e} grads " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v < GRAD_TOL, (k, v)
+    # the whole-block backward (no forward checkpoints) meets the same bound
+    ctx.set_flags(L.GSB_FLAG_NO_SEGMENTS)
+    ctx.render_forward(dparams, gcam)
+    g0 = ctx.render_backward(cot)
+    for k in g0:
+        assert rel_err(g0[k].cpu().numpy().reshape(bw["grads"][k].shape), bw["grads"][k]) < GRAD_TOL, ("no segments", k)
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------
 # BASELINE.json full sizes: size-independent properties (the oracle would take minutes here)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("wl_name,n", [("C2", None), ("C3", None)])
@@ -517,12 +659,11 @@ def test_full_size_properties(gsb, wl_name, n):
     cnt = torch.bincount(sv.long(), minlength=N)
     assert bool((vis | (cnt == 0)).all()), "only visible Gaussians are listed"
     assert int((cnt > 0).sum()) > 0.9 * int(vis.sum())
-    # the API path on the API projection must produce the same number of pairs (geometry is activation independent
-    # except for radii, which may flip by one step for a handful of Gaussians)
+    # the stage API on the stage API's projection produces the same pairs as the fused path (same pinned activations)
     act = ctx.activate_fwd(dparams)
     proj = ctx.project_fwd(act, gcam)
     bins = ctx.bin(proj, read_lists=False)
-    assert abs(bins["M"] - M) <= max(8, M // 100000)
+    assert bins["M"] == M
     tc = bins["tileCounts"].long()
     assert int(tc.sum()) == bins["M"] == int(bins["tilesTouched"].long().sum())
     rg = bins["tileRanges"].long()
@@ -552,7 +693,9 @@ def test_full_size_properties(gsb, wl_name, n):
     for k in g1:
         assert rel_err(g1[k].cpu().numpy(), g3[k].cpu().numpy()) < 1e-4, k
     if wl_name == "C3":
-        assert abs(M - 12_031_308) <= 200     # SURVEY.md 8d-workload (reference kernels on CPU), view 0
+        # SURVEY.md 8d-workload quotes 12 031 308 for libm expf activations; with the pinned activation exponential the
+        # reference kernels give the count asserted exactly in test_baseline_sizes_vs_reference_oracle
+        assert abs(M - 12_031_308) <= 200
 
 
 # ------------------------------------------------------------------------------------------------

@@ -203,3 +203,26 @@ def test_oracle_gradients_match_finite_differences(port):
             fd = (l1 - l2) / (2 * eps)
             an = float(bw["grads"][key][idx])
             assert abs(fd - an) < 5e-2 * max(abs(an), abs(fd)) + 2e-6, (key, idx, fd, an)
+
+
+def test_activation_exp_convention_is_within_one_ulp(port):
+    """The activation exponential is pinned by convention (oracle gso_expf == csrc/common.cuh gsb_expf, op for op): it
+    must stay within 1 ulp of the exact value over the range of log-scales / opacity logits, saturate and flush like
+    expf, and pass NaN through."""
+    import ctypes as C
+    x = np.concatenate([np.linspace(-104.5, 89.0, 1_000_001), np.random.default_rng(0).normal(0, 3, 500_000),
+                        [np.inf, -np.inf, 0.0, -0.0, 88.9, -200.0]]).astype(np.float32)
+    y = np.empty_like(x)
+    port.lib.gso_expf_array(len(x), x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p))
+    exact = np.exp(x.astype(np.float64))
+    with np.errstate(over="ignore"):
+        r32 = exact.astype(np.float32)
+    normal = np.isfinite(r32) & (r32 > 1.2e-38)
+    ulp = np.abs(y[normal].astype(np.float64) - exact[normal]) / np.spacing(r32[normal]).astype(np.float64)
+    assert ulp.max() < 1.0
+    assert np.all(y[np.isposinf(r32)] == np.inf) and np.all(y[x < -104.0] == 0.0)
+    tiny = np.isfinite(r32) & ~normal
+    assert np.abs(y[tiny].astype(np.float64) - exact[tiny]).max() <= 1.5e-45      # one subnormal step
+    nan = np.array([np.nan], np.float32); out = np.empty(1, np.float32)
+    port.lib.gso_expf_array(1, nan.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert np.isnan(out[0])
