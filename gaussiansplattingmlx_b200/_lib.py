@@ -20,6 +20,7 @@ GSB_FLAG_SORT_CUB = 1
 GSB_FLAG_NO_OVERLAP = 2
 GSB_FLAG_ASYNC_LOSS = 4
 GSB_FLAG_NO_SEGMENTS = 8
+GSB_FLAG_NVTX = 16
 GSB_PEER_BLOB_BYTES = 256
 STAGE_COUNT = 12
 
@@ -105,6 +106,8 @@ SIGNATURES = {
     "gsb_stats_get": (C.c_int, [_P, C.POINTER(GsbStats)]),
     "gsb_enable_stage_timing": (C.c_int, [_P, _I]),
     "gsb_stage_name": (C.c_char_p, [_I]),
+    "gsb_stage_section": (C.c_char_p, [_I]),
+    "gsb_bin_generation": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

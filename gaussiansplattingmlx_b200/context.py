@@ -455,6 +455,15 @@ class Context:
         self._check(self.lib.gsb_last_contrib_sum(self.h, C.byref(v)))
         return int(v.value)
 
+    def bin_generation(self) -> int:
+        v = C.c_uint64(0)
+        self._check(self.lib.gsb_bin_generation(self.h, C.byref(v)))
+        return int(v.value)
+
+    def stage_sections(self) -> Dict[str, str]:
+        """stage name -> section of the reference's profiler report (GaussianTrainer.swift:122-241)."""
+        return {self.lib.gsb_stage_name(i).decode(): self.lib.gsb_stage_section(i).decode() for i in range(_lib.STAGE_COUNT)}
+
     def stats_reset(self):
         self._check(self.lib.gsb_stats_reset(self.h))
 

@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges are no-ops unless a profiler injects itself
+
 #include "kernels.h"
 
 namespace gsb {
@@ -131,6 +133,7 @@ struct Ctx {
                     *op_logit = nullptr;
         ViewParams vp{};
     } saved;
+    uint64_t bin_gen = 0;             // bumped whenever the tile lists of the single-view API are rebuilt (gsb_bin_generation)
     bool bin_valid = false;           // gsb_bin ran (parity API)
     ViewParams bin_vp{};
 
@@ -195,11 +198,24 @@ void set_error(Ctx* ctx, const std::string& msg)
 
 static const char* kStageNames[GSB_STAGE_COUNT] = {"project_fwd", "scan", "keygen", "sort", "tile_lists", "raster_fwd",
                                                    "loss", "raster_bwd", "project_bwd", "adam", "h2d", "depth_sort"};
+// The section of the reference's IntervalProfiler report (GaussianTrainer.swift:122-241; names at :652-716,1060-1086 and
+// GaussianRenderer.swift:187-226,605-701) each stage belongs to, so that a trace of a Swift shim over this library lines
+// up with the reference's own "[Profile]" report.  The L1 term ("train.loss.l1") is fused into the SSIM kernels.
+static const char* kStageSections[GSB_STAGE_COUNT] = {"train.forward", "train.forward", "train.forward", "train.forward", "train.forward",
+                                                      "train.forward", "train.loss.ssim", "bwd.globalTileComposite",
+                                                      "bwd.projectionScreenFused", "train.optimizer.applySingle",
+                                                      "train.makeTrainStepInputs", "train.forward"};
+static const char* kStageNvtx[GSB_STAGE_COUNT] = {
+    "train.forward/project_fwd", "train.forward/scan", "train.forward/keygen", "train.forward/sort", "train.forward/tile_lists",
+    "train.forward/raster_fwd", "train.loss.ssim/loss", "bwd.globalTileComposite/raster_bwd", "bwd.projectionScreenFused/project_bwd",
+    "train.optimizer.applySingle/adam", "train.makeTrainStepInputs/h2d", "train.forward/depth_sort"};
 
 struct StageTimer {
-    Ctx* c; int stage; bool on; cudaStream_t st;
-    StageTimer(Ctx* ctx, int s, cudaStream_t stream = nullptr) : c(ctx), stage(s), on(ctx->timing), st(stream ? stream : ctx->stream)
+    Ctx* c; int stage; bool on; cudaStream_t st; bool nvtx;
+    StageTimer(Ctx* ctx, int s, cudaStream_t stream = nullptr)
+        : c(ctx), stage(s), on(ctx->timing), st(stream ? stream : ctx->stream), nvtx((ctx->cfg.flags & GSB_FLAG_NVTX) != 0)
     {
+        if (nvtx) nvtxRangePushA(kStageNvtx[stage]);   // host range around the enqueue; profilers project it onto the kernels
         if (!on) return;
         if (c->ev_used >= 16384) resolve_stage_events(c);
         if (c->ev_used == c->ev_pool.size()) {
@@ -212,9 +228,11 @@ struct StageTimer {
     }
     ~StageTimer()
     {
-        if (!on) return;
-        cudaEventRecord(c->ev_pool[c->ev_used].b, st);
-        c->ev_used += 1;
+        if (on) {
+            cudaEventRecord(c->ev_pool[c->ev_used].b, st);
+            c->ev_used += 1;
+        }
+        if (nvtx) nvtxRangePop();
     }
 };
 
@@ -841,6 +859,7 @@ int gsb_bin(gsb_ctx* ctx, int32_t N, const float* rect_min, const float* rect_ma
     const gsb::ViewParams vp = gsb::make_view_nocam(c);
     Ctx::ViewBufs& v = c->vb[c->cur];
     c->saved.valid = false;
+    c->bin_gen += 1;
     // keep a private copy of the depths: gsb_bin_read rebuilds the reference's sortedKeysLow from them
     if (N > 0) GSB_CUDA_CHECK(c, cudaMemcpyAsync(c->act_tmp, depths, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
     GSB_CUDA_CHECK(c, gsb::launch_count_tiles(c->stream, N, vp, rect_min, rect_max, radii, c->act_tmp, v.tile_rects, v.touched,
@@ -1081,6 +1100,7 @@ static int render_forward_impl(Ctx* c, int32_t N, const RawParams& p, const gsb:
     if (rc != GSB_OK) return rc;
     c->saved.valid = false;
     c->bin_valid = false;
+    c->bin_gen += 1;
     Ctx::ViewBufs& v = c->vb[c->cur];
     for (int attempt = 0;; ++attempt) {
         rc = enqueue_front(c, v, c->stream, N, p, vp, radii, visibility);
@@ -1385,6 +1405,7 @@ static int trainer_accumulate_impl(Ctx* c, int32_t B, const gsb_camera* host_cam
     const bool overlap = B >= 2 && !(c->cfg.flags & (GSB_FLAG_SORT_CUB | GSB_FLAG_NO_OVERLAP));
     c->saved.valid = false;
     c->bin_valid = false;
+    c->bin_gen += 1;
     if (overlap) {   // the front stream must see everything already queued on the work stream (Adam of the last step)
         GSB_CUDA_CHECK(c, cudaEventRecord(c->ev_fork, c->stream));
         for (cudaStream_t fs : c->front_streams) GSB_CUDA_CHECK(c, cudaStreamWaitEvent(fs, c->ev_fork, 0));
@@ -1876,6 +1897,18 @@ int gsb_enable_stage_timing(gsb_ctx* ctx, int32_t on)
 const char* gsb_stage_name(int32_t stage)
 {
     return (stage >= 0 && stage < GSB_STAGE_COUNT) ? gsb::kStageNames[stage] : "";
+}
+const char* gsb_stage_section(int32_t stage)
+{
+    return (stage >= 0 && stage < GSB_STAGE_COUNT) ? gsb::kStageSections[stage] : "";
+}
+
+int gsb_bin_generation(gsb_ctx* ctx, uint64_t* host_out)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, host_out, "gsb_bin_generation: null argument");
+    *host_out = c->bin_gen;
+    return GSB_OK;
 }
 
 }  // extern "C"

@@ -52,6 +52,7 @@ class _CompositeFn(torch.autograd.Function):
         packed = packed.contiguous()
         o = ctx.raster_fwd(packed)
         fn.gsb = ctx
+        fn.bin_generation = ctx.bin_generation()     # the reference's closure captures the slice info per call (:119-122)
         fn.save_for_backward(packed, o["color"], o["depth"], o["alpha"], o["lastContrib"])
         fn.mark_non_differentiable(o["lastContrib"])
         return o["color"], o["depth"], o["alpha"], o["lastContrib"]
@@ -59,6 +60,9 @@ class _CompositeFn(torch.autograd.Function):
     @staticmethod
     def backward(fn, g_color, g_depth, g_alpha, _):
         packed, color, depth, alpha, last = fn.saved_tensors
+        if fn.gsb.bin_generation() != fn.bin_generation:
+            raise RuntimeError("GaussianRenderer: the context's tile lists were rebuilt (another forward / bin call) between this "
+                               "render's forward and its backward; render and differentiate one view at a time per renderer")
         P = color.shape[0]
         z = lambda g, *shape: torch.zeros(*shape, device=packed.device) if g is None else g.contiguous()
         cot = {"color": z(g_color, P, 3), "depth": z(g_depth, P, 1), "alpha": z(g_alpha, P, 1)}

@@ -61,7 +61,7 @@ class GaussianTrainer:
     def __init__(self, model: GaussModel, data: TrainData, gaussRender: GaussianRenderer, iterationCount: int,
                  views_per_step: int = 1, parallel: Optional[ViewParallel] = None, seed: Optional[int] = None,
                  reset_optimizer_state: bool = True, outputDirectoryURL: Optional[str] = None,
-                 save_snapshot_per_iteration: int = 100):
+                 save_snapshot_per_iteration: int = 100, step_log_path: Optional[str] = None):
         self.model, self.data, self.gaussRender = model, data, gaussRender
         self.iterationCount = iterationCount
         self.views_per_step = views_per_step
@@ -75,6 +75,9 @@ class GaussianTrainer:
         self.densify_log: List[Dict[str, int]] = []
         self.forceStop = False
         self.stopped_early = False
+        # JSONL step log (one line per loss read-back: iteration, loss, Gaussian count, pairs of the last view, wall ms):
+        # the machine-readable counterpart of the reference's "[Profile] iter=..." report lines
+        self.step_log_path = step_log_path
         self.delegate: Optional[Callable[[float, int], None]] = None   # pushLoss(loss, iteration)
         self._rng = random.Random(seed)
         ctx = gaussRender.ctx
@@ -199,6 +202,13 @@ class GaussianTrainer:
                 self.losses.append(loss)
                 if self.delegate:
                     self.delegate(loss, iteration)
+                if self.step_log_path and self.parallel.rank == 0:
+                    import json, time
+                    st = self.gaussRender.ctx.stats()
+                    with open(self.step_log_path, "a") as f:
+                        f.write(json.dumps({"iteration": iteration, "loss": loss, "gaussians": self.gaussRender.ctx.trainer_count()[0],
+                                            "pairs_last_view": st["pairs_last_view"], "kernel_launches": st["kernel_launches"],
+                                            "t": time.time()}) + "\n")
             if self.stopped_early:
                 break
         self.sync_model()

@@ -63,6 +63,8 @@ typedef struct gsb_config {
 #define GSB_FLAG_NO_OVERLAP 2     /* trainer: run every view's kernels back to back on one stream (per-kernel timing) */
 #define GSB_FLAG_ASYNC_LOSS 4     /* gsb_trainer_accumulate / gsb_train_step: host_loss is PINNED host memory; the loss is copied
                                    * into it asynchronously on the work stream and the call does not synchronise */
+#define GSB_FLAG_NVTX 16          /* wrap every stage in an NVTX range named "<reference profiler section>/<stage>", e.g.
+                                   * "bwd.globalTileComposite/raster_bwd" (sections of GaussianTrainer.swift:122-241) */
 #define GSB_FLAG_NO_SEGMENTS 8    /* raster backward: one work item per 16x16 block instead of checkpointed 256-Gaussian segments
                                    * (checking only: same gradients up to rounding, worse load balance) */
 
@@ -309,6 +311,15 @@ GSB_API int gsb_stats_reset(gsb_ctx*);
 GSB_API int gsb_stats_get(gsb_ctx*, gsb_stats* host_out);
 GSB_API int gsb_enable_stage_timing(gsb_ctx*, int32_t on);   /* brackets every stage with CUDA-event pairs; no syncs until stats are read */
 GSB_API const char* gsb_stage_name(int32_t stage);
+/* the section of the reference's IntervalProfiler report (GaussianTrainer.swift:122-241) the stage belongs to:
+ * "train.forward", "train.loss.ssim", "bwd.globalTileComposite", "bwd.projectionScreenFused",
+ * "train.optimizer.applySingle", "train.makeTrainStepInputs" */
+GSB_API const char* gsb_stage_section(int32_t stage);
+/* Counter bumped whenever the context's tile lists are rebuilt (gsb_bin, gsb_render_forward, the trainer).  A caller
+ * that differentiates gsb_raster_fwd later (autograd node, the reference's CustomFunction closure,
+ * GaussianRenderer.swift:119-122,150-184) stamps it at forward time and must find it unchanged at backward time:
+ * gsb_raster_bwd differentiates with the binning the context holds NOW. */
+GSB_API int gsb_bin_generation(gsb_ctx*, uint64_t* host_out);
 
 #ifdef __cplusplus
 }

@@ -223,6 +223,57 @@ def test_loss_fwd_bwd_parity(gsb, best_oracle):
     assert rel_err(cot.cpu().numpy(), lo["cot_render"]) < GRAD_TOL
 
 
+def test_autograd_through_reference_shaped_renderer(gsb, best_oracle):
+    """``GaussianRenderer.forward`` (GaussianRenderer.swift:882-934) is differentiable through two custom functions
+    standing where the reference has its CustomFunction{Forward; VJP} pairs (:150-184 tile composite, :576-602 fused
+    projection).  torch.autograd through that path (activations as torch ops, like the reference's MLX ops) must give
+    the oracle's gradients w.r.t. the activated AND the raw tensors, and agree with the fused ``forward_raw`` path."""
+    Context, L = gsb
+    from gaussiansplattingmlx_b200.renderer import GaussianRenderer
+    o = best_oracle
+    s, params, cam, target = scene("deg4")
+    W, H, degree = s["W"], s["H"], s["degree"]
+    fr, lo, bw = pl.loss_and_grads(o, params, cam, target, degree)
+    r = GaussianRenderer(degree, W, H)
+    raw = {k: dev(v).requires_grad_(True) for k, v in params.items()}
+    act = {"means3d": r.get_xyz_from(raw["_xyz"]), "shs": r.get_features_from(raw["_features_dc"], raw["_features_rest"]),
+           "opacity": r.get_opacity_from(raw["_opacity"]), "scales": r.get_scales_from(raw["_scales"]),
+           "rotations": r.get_rotation_from(raw["_rotation"])}
+    for v in act.values():
+        v.retain_grad()
+    render, depth, alpha, vis, radii = r.forward(cam, act["means3d"], act["shs"], act["opacity"], act["scales"], act["rotations"])
+    assert np.abs(render.detach().cpu().numpy() - fr["render"]).max() <= PIX_TOL
+    assert (vis.cpu().numpy() == fr["visibility_filter"]).all()
+    (render * dev(lo["cot_render"])).sum().backward()          # VJP with the loss cotangent
+    for k in ("means3d", "shs", "scales", "rotations", "opacity"):
+        assert rel_err(act[k].grad.cpu().numpy().reshape(bw["g_act"][k].shape), bw["g_act"][k]) < GRAD_TOL, k
+    for k in params:
+        assert rel_err(raw[k].grad.cpu().numpy().reshape(bw["grads"][k].shape), bw["grads"][k]) < GRAD_TOL, k
+    # the fused path on the same cotangent
+    ctx = r.ctx
+    ctx.render_forward({k: v.detach() for k, v in raw.items()}, L.make_camera(cam))
+    gf = ctx.render_backward(dev(lo["cot_render"]))
+    for k in params:
+        assert rel_err(raw[k].grad.cpu().numpy(), gf[k].cpu().numpy()) < GRAD_TOL, k
+    # depth / alpha outputs are differentiable too (cotDepth / cotAlpha of the composite VJP, :187-226)
+    rng = np.random.default_rng(3)
+    cd, ca = rng.standard_normal((H, W, 1)).astype(np.float32), rng.standard_normal((H, W, 1)).astype(np.float32)
+    bw2 = pl.backward(o, params, cam, degree, fr, lo["cot_render"], cd, ca)
+    act2 = {k: v.detach().clone().requires_grad_(True) for k, v in act.items()}
+    render2, depth2, alpha2, _, _ = r.forward(cam, act2["means3d"], act2["shs"], act2["opacity"], act2["scales"], act2["rotations"])
+    ((render2 * dev(lo["cot_render"])).sum() + (depth2 * dev(cd)).sum() + (alpha2 * dev(ca)).sum()).backward()
+    for k in act2:
+        assert rel_err(act2[k].grad.cpu().numpy().reshape(bw2["g_act"][k].shape), bw2["g_act"][k]) < GRAD_TOL, ("depth/alpha", k)
+    # one saved forward per renderer, like the reference's closure-captured state: a second forward invalidates the first
+    act3 = {k: v.detach().clone().requires_grad_(True) for k, v in act.items()}
+    ra, *_ = r.forward(cam, act3["means3d"], act3["shs"], act3["opacity"], act3["scales"], act3["rotations"])
+    other = make_cameras(W, H, 3)[2]
+    r.forward(other, act3["means3d"].detach(), act3["shs"].detach(), act3["opacity"].detach(), act3["scales"].detach(),
+              act3["rotations"].detach())
+    with pytest.raises(RuntimeError, match="tile lists were rebuilt"):
+        ra.sum().backward()
+
+
 def test_depth_supervised_loss_and_training_path(gsb, best_oracle):
     """lossFn's depth term (GaussianTrainer.swift:693-714, on whenever the dataset has depth, :949): masked L1 with the
     safe weight, its cotangent through the raster / projection backward, and the trainer entry point with depth targets
