@@ -48,7 +48,6 @@ class GaussianTrainer:
     # reference defaults (GaussianTrainer.swift:277-300)
     lambda_dssim = 0.2
     lambda_depth = 0.0
-    optimizer_reset_interval = 100
     # split and prune parameters (GaussianTrainer.swift:281, 293-300)
     split_and_prune_per_iteration = 100
     gradientThreshold = 0.0002

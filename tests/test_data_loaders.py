@@ -199,6 +199,6 @@ def test_colmap_dataset_to_training_end_to_end(tmp_path):
     tr = GaussianTrainer(model, data, r, iterationCount=30, seed=1)
     before = model._xyz.copy()
     tr.startTrain(earlyStoppingThreshold=-1.0)
-    assert len(tr.losses) == 3 and all(np.isfinite(l) for l in tr.losses)
+    assert len(tr.losses) == 5 and all(np.isfinite(l) for l in tr.losses)
     assert tr.losses[-1] < tr.losses[0], "30 Adam iterations on 4 views must lower the loss"
     assert model._xyz.shape == before.shape and not np.array_equal(model._xyz, before)

@@ -207,7 +207,7 @@ def test_python_trainer_runs_split_and_prune_on_cadence(gsb):
     model = GaussModel.from_arrays(params, 3)
     r = GaussianRenderer(active_sh_degree=3, W=W, H=H, TILE_SIZE=(16, 16), whiteBackground=False)
     tr = GaussianTrainer(model, TrainData(cams, targets), r, iterationCount=12, views_per_step=2, seed=3)
-    tr.optimizer_reset_interval = 5
+    tr.split_and_prune_per_iteration = 5      # GaussianTrainer.swift:1098: this cadence alone drives densify + state reset
     tr.densifyFromIter, tr.densifyUntilIter = 5, 10
     tr.gradientThreshold, tr.maxScale = 1e-7, 0.05
     tr.startTrain(earlyStoppingThreshold=-1.0)
