@@ -363,6 +363,28 @@ class Context:
         self._sync_stream()
         self._check(self.lib.gsb_trainer_apply_peers(self.h, iteration, total_iterations, int(reset_state)))
 
+    def trainer_step_peers(self, cams, targets, grad_scale: float, iteration: int, total_iterations: int, reset_state: bool = False,
+                           want_loss: bool = False, loss_out: Optional[torch.Tensor] = None) -> Optional[float]:
+        """The whole data-parallel step with device-side synchronisation (gsb.h: gsb_trainer_step_peers); ``cams`` may be empty
+        on a replica without views.  Loss semantics as in ``trainer_accumulate``."""
+        self._sync_stream()
+        if len(cams):
+            B, cam_arr, tp, on_host = self._cams_targets(cams, targets)
+        else:
+            B, cam_arr, tp, on_host = 0, None, None, 0
+        if loss_out is not None:
+            assert self.cfg.flags & _lib.GSB_FLAG_ASYNC_LOSS and loss_out.is_pinned() and loss_out.dtype == torch.float32
+            self._check(self.lib.gsb_trainer_step_peers(self.h, B, cam_arr, tp, on_host, C.c_float(grad_scale), iteration, total_iterations,
+                                                        int(reset_state), C.c_void_p(loss_out.data_ptr())))
+            return None
+        loss = C.c_float(0.0)
+        self._check(self.lib.gsb_trainer_step_peers(self.h, B, cam_arr, tp, on_host, C.c_float(grad_scale), iteration, total_iterations,
+                                                    int(reset_state), C.cast(C.pointer(loss), C.c_void_p) if want_loss else None))
+        return float(loss.value) if want_loss else None
+
+    def trainer_peers_check(self):
+        self._check(self.lib.gsb_trainer_peers_check(self.h))
+
     def trainer_attach_symmetric(self, world: int, rank: int, params_local: int, grads_local: int, params_mc: int, grads_mc: int,
                                  floats: int):
         """Device addresses (ints) of this replica's symmetric parameter / gradient buffers and of their multicast mappings."""

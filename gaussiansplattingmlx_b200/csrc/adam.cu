@@ -82,18 +82,102 @@ __global__ void __launch_bounds__(AD_THREADS) k_adam(const __grid_constant__ Ada
 }
 
 // ------------------------------------------------------------------------------------------------
+// Device-side synchronisation between the replicas (one process per GPU, flags in peer-mapped memory; PeerSync in
+// kernels.h).  A flag holds the id of the last step for which its event happened; ids are compared modulo 2^32.
+// Every wait is bounded (2 s of %globaltimer): a replica that never arrives sets the local error word instead of
+// hanging the GPU.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t value, uint32_t* error)
+{
+    if ((int32_t)(ld_acquire_sys_u32(flag) - value) >= 0) return;
+    const unsigned long long t0 = global_timer_ns();
+    while ((int32_t)(ld_acquire_sys_u32(flag) - value) < 0) {
+        __nanosleep(200);
+        if (global_timer_ns() - t0 > 2000000000ull) {
+            if (error) *error = 1u;
+            return;
+        }
+    }
+}
+// all threads of the CTA: returns when every replica's flag has reached sy.step
+__device__ __forceinline__ void peer_wait_cta(const PeerStepSync& sy, int world)
+{
+    if (sy.wait_flags) {
+        if ((int)threadIdx.x < world) spin_until(sy.wait_flags + threadIdx.x, sy.step, sy.error);
+        __syncthreads();
+    }
+}
+// all threads of the CTA, after their last peer store: the last CTA of the grid announces sy.step to every replica
+__device__ __forceinline__ void peer_announce_cta(const PeerStepSync& sy, int world)
+{
+    if (!sy.done) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(sy.done, 1u);
+        if (prev == gridDim.x - 1) {
+            *sy.done = 0u;
+            __threadfence_system();
+            for (int r = 0; r < world; ++r) st_release_sys_u32(sy.announce[r], sy.step);
+        }
+    }
+}
+
+__global__ void k_peer_signal(const __grid_constant__ PeerFlagList flags, uint32_t value)
+{
+    __threadfence_system();
+    if ((int)threadIdx.x < flags.n) st_release_sys_u32(flags.dst[threadIdx.x], value);
+}
+__global__ void k_peer_wait(const uint32_t* flags, int rows, int cols, int row_stride, uint32_t value, uint32_t* error)
+{
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) spin_until(flags + (i / cols) * row_stride + (i % cols), value, error);
+}
+cudaError_t launch_peer_signal(cudaStream_t st, const PeerFlagList& flags, uint32_t value)
+{
+    if (flags.n > 0) k_peer_signal<<<1, 32, 0, st>>>(flags, value);
+    return cudaGetLastError();
+}
+cudaError_t launch_peer_wait(cudaStream_t st, const uint32_t* flags, int rows, int cols, int row_stride, uint32_t value, uint32_t* error)
+{
+    if (rows * cols > 0) k_peer_wait<<<1, 64, 0, st>>>(flags, rows, cols, row_stride, value, error);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Data-parallel step fused with its collective: gradient reduction + Adam + parameter broadcast in ONE
 // kernel over NVLink peer memory.  Rank r owns the Gaussians [g0, g1) of every tensor: it sums that slice of the gradient
 // blocks of ALL ranks (peer loads, fixed rank order, so the sum has one owner and no replica can diverge), applies Adam
 // with its local m / v / p, and stores the new parameters into every rank's replica (peer stores).  Per rank and step
 // this moves (world - 1) / world of the gradient block in and of the parameter block out over NVLink - what a
 // reduce-scatter + all-gather moves - and 1 / world of Adam's HBM traffic, with no staging buffers and no second pass.
-// The caller brackets the launch with two stream-ordered barriers (all gradients complete / all replicas written).
+// Link traffic per GPU and DIRECTION is twice that (206 MB at 8 GPUs and C3): its own pulls / pushes plus the pulls /
+// pushes of the 7 other owners that target it - 412 MB, i.e. 0.72 ms = 570 GB/s per direction.
+// Synchronisation: either the caller brackets the launch with two stream-ordered barriers (sync.wait_flags == nullptr,
+// gsb_trainer_apply_peers), or the kernel itself waits for the replicas' "gradients complete" flags and its last CTA
+// raises "parameters written" in every replica (gsb_trainer_step_peers: one launch per Gaussian chunk, so the exchange
+// of chunk c overlaps the projection backward of chunk c + 1).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(AD_THREADS, 4) k_adam_peers(const __grid_constant__ AdamTensors t, const __grid_constant__ AdamPeers pr,
-                                                           const __grid_constant__ AdamSeg seg, float b1, float b2, float eps,
-                                                           float gscale, int diag)
+                                                           const __grid_constant__ AdamSeg seg, const __grid_constant__ PeerStepSync sy,
+                                                           float b1, float b2, float eps, float gscale)
 {
+    peer_wait_cta(sy, pr.world);
     const long long total = seg.vec_begin[6];
     const long long stride = (long long)gridDim.x * blockDim.x;
     // chunk i of the owned slice -> tensor k, float offset inside the tensor / inside one copy of the six tensors
@@ -105,8 +189,7 @@ __global__ void __launch_bounds__(AD_THREADS, 4) k_adam_peers(const __grid_const
         off = pr.tensor_off[k] + base;
     };
     // Software pipeline: the peer loads of chunk i + stride are in flight while chunk i is updated and stored to every
-    // replica, so NVLink carries gradients in and parameters out at the same time (a load-all / store-all loop
-    // alternates the two directions: 0.73 ms instead of 0.5 ms per step at 8 GPUs).
+    // replica, so NVLink carries gradients in and parameters out at the same time.
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float4 gn[GSB_MAX_PEERS];
     bool vec_n = false;
@@ -117,8 +200,7 @@ __global__ void __launch_bounds__(AD_THREADS, 4) k_adam_peers(const __grid_const
         if (vec_n) {
 #pragma unroll
             for (int r = 0; r < GSB_MAX_PEERS; ++r)
-                if (r < pr.world && (!(diag & 2) || r == pr.rank)) gn[r] = __ldcg(reinterpret_cast<const float4*>(pr.grads[r] + off));
-                else if (r < pr.world) gn[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < pr.world) gn[r] = __ldcg(reinterpret_cast<const float4*>(pr.grads[r] + off));
         }
     };
     if (i < total) prefetch(i);
@@ -149,8 +231,7 @@ __global__ void __launch_bounds__(AD_THREADS, 4) k_adam_peers(const __grid_const
             adam1(P.w, G.w, M.w, V.w, lr, b1, b2, eps);
             *reinterpret_cast<float4*>(m) = M;
             *reinterpret_cast<float4*>(v) = V;
-            for (int r = 0; r < pr.world; ++r)
-                if (!(diag & 1) || r == pr.rank) *reinterpret_cast<float4*>(pr.params[r] + off) = P;
+            for (int r = 0; r < pr.world; ++r) *reinterpret_cast<float4*>(pr.params[r] + off) = P;
         } else {
             for (long long e = 0; base + e < end; ++e) {
                 float g = 0.f;
@@ -176,24 +257,28 @@ __global__ void __launch_bounds__(AD_THREADS, 4) k_adam_peers(const __grid_const
             for (int r = 0; r < pr.world; ++r) pr.accum[r][i] = acc;
         }
     }
+    peer_announce_cta(sy, pr.world);
 }
 
 cudaError_t launch_adam_peers(cudaStream_t st, const AdamTensors& t, const AdamPeers& pr, float beta1, float beta2, float eps,
-                              float gscale, int* launches)
+                              float gscale, const PeerStepSync* sync, int* launches)
 {
     AdamSeg seg;
     seg.vec_begin[0] = 0;
     for (int k = 0; k < 6; ++k) seg.vec_begin[k + 1] = seg.vec_begin[k] + (t.count[k] + 3) / 4;
     const long long total = seg.vec_begin[6];
-    if (total == 0 && pr.g1 <= pr.g0) return cudaSuccess;
+    if (!sync && total == 0 && pr.g1 <= pr.g0) return cudaSuccess;   // with sync even an empty slice must announce itself
     long long blocks = (std::max<long long>(total, 1) + AD_THREADS - 1) / AD_THREADS;
-    long long cap = 148LL * 4;   // persistent: one resident wave (4 CTAs per SM), every thread pipelines its chunks
-    // tuning / diagnosis knobs, never set in production (DESIGN.md section 5 quotes what they measured)
-    static const int env_blocks = getenv("GSB_PEER_BLOCKS") ? atoi(getenv("GSB_PEER_BLOCKS")) : 0;
-    static const int diag = getenv("GSB_PEER_DIAG") ? atoi(getenv("GSB_PEER_DIAG")) : 0;             // 1: no remote stores, 2: no remote loads (WRONG results)
+    // persistent: every thread pipelines its chunks.  One resident wave of 4 CTAs per SM when the launch is alone on the GPU;
+    // 2 per SM under the step protocol, where the projection backward of the next Gaussian chunk must fit beside it (the
+    // kernel is NVLink-bound: 296 CTAs keep ~10 MB of peer loads in flight)
+    long long cap = sync ? 148LL * 2 : 148LL * 4;
+    static const int env_blocks = getenv("GSB_PEER_BLOCKS") ? atoi(getenv("GSB_PEER_BLOCKS")) : 0;   // tuning only
     if (env_blocks > 0) cap = env_blocks;
     if (blocks > cap) blocks = cap;
-    k_adam_peers<<<(int)blocks, AD_THREADS, 0, st>>>(t, pr, seg, beta1, beta2, eps, gscale, diag);
+    PeerStepSync sy{};
+    if (sync) sy = *sync;
+    k_adam_peers<<<(int)blocks, AD_THREADS, 0, st>>>(t, pr, seg, sy, beta1, beta2, eps, gscale);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
@@ -203,7 +288,10 @@ cudaError_t launch_adam_peers(cudaStream_t st, const AdamTensors& t, const AdamP
 // address range (symmetric memory).  multimem.ld_reduce returns the SUM over all replicas of a 16-byte chunk - the switch
 // adds, one read crosses this GPU's links - and multimem.st writes a chunk into every replica.  Rank r still owns slice r:
 // per step it pulls 1 / world of the gradient block (already reduced) and pushes 1 / world of the parameter block, instead
-// of (world - 1) / world each with plain peer loads / stores.
+// of (world - 1) / world each with plain peer loads / stores: ~265 MB per direction and GPU instead of 412 MB at 8 GPUs.
+// Four 16-byte reductions are in flight per thread before the first is consumed (the switch round trip is several
+// microseconds).  D1 is computed for the owned Gaussians only and stored into every replica's accumulator through peer
+// memory (one owner per value: replicas cannot diverge by the summation order of the switch).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 mc_ld_reduce_v4(const float* mc)
 {
@@ -227,82 +315,106 @@ __device__ __forceinline__ void mc_st(float* mc, float v)
     asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
 }
 
+constexpr int MC_UNROLL = 4;
+
 __global__ void __launch_bounds__(AD_THREADS) k_adam_multicast(const __grid_constant__ AdamTensors t, const __grid_constant__ AdamPeers pr,
-                                                               const __grid_constant__ AdamSeg seg, const float* __restrict__ mc_grads,
-                                                               float* __restrict__ mc_params, float b1, float b2, float eps, float gscale,
-                                                               int N)
+                                                               const __grid_constant__ AdamSeg seg, const __grid_constant__ PeerStepSync sy,
+                                                               const float* __restrict__ mc_grads, float* __restrict__ mc_params, float b1,
+                                                               float b2, float eps, float gscale, int N)
 {
+    peer_wait_cta(sy, pr.world);
     const long long total = seg.vec_begin[6];
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        int k = 0;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * MC_UNROLL) {
+        int kk[MC_UNROLL];
+        long long bb[MC_UNROLL], oo[MC_UNROLL];
+        bool vec[MC_UNROLL], live[MC_UNROLL];
+        float4 G[MC_UNROLL];
 #pragma unroll
-        for (int j = 1; j < 6; ++j) k += (i >= seg.vec_begin[j]) ? 1 : 0;
-        const long long base = pr.first[k] + (i - seg.vec_begin[k]) * 4;
-        const long long end = pr.first[k] + t.count[k];
-        const long long off = pr.tensor_off[k] + base;
-        const float lr = t.lr[k];
-        float* m = t.m[k] + base;
-        float* v = t.v[k] + base;
-        if (base + 4 <= end) {
-            float4 G = mc_ld_reduce_v4(mc_grads + off);
-            float4 P = *reinterpret_cast<const float4*>(t.p[k] + base);
-            float4 M = *reinterpret_cast<float4*>(m);
-            float4 V = *reinterpret_cast<float4*>(v);
-            G.x = G.x * gscale; G.y = G.y * gscale; G.z = G.z * gscale; G.w = G.w * gscale;
-            adam1(P.x, G.x, M.x, V.x, lr, b1, b2, eps);
-            adam1(P.y, G.y, M.y, V.y, lr, b1, b2, eps);
-            adam1(P.z, G.z, M.z, V.z, lr, b1, b2, eps);
-            adam1(P.w, G.w, M.w, V.w, lr, b1, b2, eps);
-            *reinterpret_cast<float4*>(m) = M;
-            *reinterpret_cast<float4*>(v) = V;
-            mc_st_v4(mc_params + off, P);
-        } else {
-            for (long long e = 0; base + e < end; ++e) {
-                const float g = mc_ld_reduce(mc_grads + off + e);
-                float pp = t.p[k][base + e], mm = m[e], vv = v[e];
-                adam1(pp, g * gscale, mm, vv, lr, b1, b2, eps);
-                m[e] = mm; v[e] = vv;
-                mc_st(mc_params + off + e, pp);
+        for (int u = 0; u < MC_UNROLL; ++u) {
+            const long long i = i0 + (long long)u * stride;
+            live[u] = i < total;
+            vec[u] = false;
+            if (live[u]) {
+                int k = 0;
+#pragma unroll
+                for (int j = 1; j < 6; ++j) k += (i >= seg.vec_begin[j]) ? 1 : 0;
+                kk[u] = k;
+                bb[u] = pr.first[k] + (i - seg.vec_begin[k]) * 4;
+                oo[u] = pr.tensor_off[k] + bb[u];
+                vec[u] = bb[u] + 4 <= pr.first[k] + t.count[k];
+                if (vec[u]) G[u] = mc_ld_reduce_v4(mc_grads + oo[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < MC_UNROLL; ++u) {
+            if (!live[u]) continue;
+            const int k = kk[u];
+            const long long base = bb[u], off = oo[u];
+            const float lr = t.lr[k];
+            float* m = t.m[k] + base;
+            float* v = t.v[k] + base;
+            if (vec[u]) {
+                float4 Gu = G[u];
+                float4 P = *reinterpret_cast<const float4*>(t.p[k] + base);
+                float4 M = *reinterpret_cast<float4*>(m);
+                float4 V = *reinterpret_cast<float4*>(v);
+                Gu.x = Gu.x * gscale; Gu.y = Gu.y * gscale; Gu.z = Gu.z * gscale; Gu.w = Gu.w * gscale;
+                adam1(P.x, Gu.x, M.x, V.x, lr, b1, b2, eps);
+                adam1(P.y, Gu.y, M.y, V.y, lr, b1, b2, eps);
+                adam1(P.z, Gu.z, M.z, V.z, lr, b1, b2, eps);
+                adam1(P.w, Gu.w, M.w, V.w, lr, b1, b2, eps);
+                *reinterpret_cast<float4*>(m) = M;
+                *reinterpret_cast<float4*>(v) = V;
+                mc_st_v4(mc_params + off, P);
+            } else {
+                const long long end = pr.first[k] + t.count[k];
+                for (long long e = 0; base + e < end; ++e) {
+                    const float g = mc_ld_reduce(mc_grads + off + e);
+                    float pp = t.p[k][base + e], mm = m[e], vv = v[e];
+                    adam1(pp, g * gscale, mm, vv, lr, b1, b2, eps);
+                    m[e] = mm; v[e] = vv;
+                    mc_st(mc_params + off + e, pp);
+                }
             }
         }
     }
-    // D1 on every replica for ALL Gaussians (12 bytes each through the switch): the accumulator stays local and every
-    // replica computes the identical value from the identical switch-reduced gradient
-    if (pr.accum[pr.rank]) {
-        float* accum = pr.accum[pr.rank];
-        const float* gx = mc_grads + pr.tensor_off[0];
-        const long long quads = N / 4;
-        for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < quads; j += stride) {
-            const float4 a = mc_ld_reduce_v4(gx + j * 12), b = mc_ld_reduce_v4(gx + j * 12 + 4), c = mc_ld_reduce_v4(gx + j * 12 + 8);
-            const float g[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-            float4 acc = *reinterpret_cast<float4*>(accum + j * 4);
-            float* ap = &acc.x;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float x = g[3 * q] * gscale, y = g[3 * q + 1] * gscale, z = g[3 * q + 2] * gscale;
-                ap[q] = ap[q] + sqrtf(x * x + y * y + z * z);
-            }
-            *reinterpret_cast<float4*>(accum + j * 4) = acc;
+    const float* gx = mc_grads + pr.tensor_off[0];
+    if (pr.accum[pr.rank] && pr.accum_all) {
+        // the replicas' accumulators are peer-mapped: D1 of the owned Gaussians, one owner per value
+        for (long long i = pr.g0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pr.g1; i += stride) {
+            const float a = mc_ld_reduce(gx + i * 3) * gscale, b = mc_ld_reduce(gx + i * 3 + 1) * gscale, c = mc_ld_reduce(gx + i * 3 + 2) * gscale;
+            const float acc = pr.accum[pr.rank][i] + sqrtf(a * a + b * b + c * c);
+            for (int r = 0; r < pr.world; ++r) pr.accum[r][i] = acc;
         }
-        for (long long i = quads * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    } else if (pr.accum[pr.rank]) {
+        // no peer mapping of the accumulators: every replica computes all of D1 from the switch-reduced gradient
+        float* accum = pr.accum[pr.rank];
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
             const float x = mc_ld_reduce(gx + i * 3) * gscale, y = mc_ld_reduce(gx + i * 3 + 1) * gscale, z = mc_ld_reduce(gx + i * 3 + 2) * gscale;
             accum[i] = accum[i] + sqrtf(x * x + y * y + z * z);
         }
     }
+    peer_announce_cta(sy, pr.world);
 }
 
 cudaError_t launch_adam_multicast(cudaStream_t st, const AdamTensors& t, const AdamPeers& pr, const float* mc_grads, float* mc_params,
-                                  float beta1, float beta2, float eps, float gscale, int N, int* launches)
+                                  float beta1, float beta2, float eps, float gscale, int N, const PeerStepSync* sync, int* launches)
 {
     AdamSeg seg;
     seg.vec_begin[0] = 0;
     for (int k = 0; k < 6; ++k) seg.vec_begin[k + 1] = seg.vec_begin[k] + (t.count[k] + 3) / 4;
-    const long long total = std::max<long long>(seg.vec_begin[6], (N + 3) / 4);
-    long long blocks = (std::max<long long>(total, 1) + AD_THREADS - 1) / AD_THREADS;
-    const long long cap = 148LL * 8 * 4;
+    const bool own_d1 = pr.accum[pr.rank] && pr.accum_all;
+    const long long d1 = pr.accum[pr.rank] ? (own_d1 ? pr.g1 - pr.g0 : N) : 0;
+    const long long total = std::max<long long>(seg.vec_begin[6], d1);
+    long long blocks = (std::max<long long>((total + MC_UNROLL - 1) / MC_UNROLL, 1) + AD_THREADS - 1) / AD_THREADS;
+    long long cap = 148LL * 8;
+    static const int env_blocks = getenv("GSB_MC_BLOCKS") ? atoi(getenv("GSB_MC_BLOCKS")) : 0;   // tuning only
+    if (env_blocks > 0) cap = env_blocks;
     if (blocks > cap) blocks = cap;
-    k_adam_multicast<<<(int)blocks, AD_THREADS, 0, st>>>(t, pr, seg, mc_grads, mc_params, beta1, beta2, eps, gscale, N);
+    PeerStepSync sy{};
+    if (sync) sy = *sync;
+    k_adam_multicast<<<(int)blocks, AD_THREADS, 0, st>>>(t, pr, seg, sy, mc_grads, mc_params, beta1, beta2, eps, gscale, N);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

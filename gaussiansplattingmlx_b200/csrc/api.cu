@@ -156,6 +156,16 @@ struct Ctx {
     float* peer_block[gsb::GSB_MAX_PEERS] = {};    // base of replica r's trainer slab (own pointer at [peer_rank])
     float* peer_accum[gsb::GSB_MAX_PEERS] = {};
     bool peer_opened[gsb::GSB_MAX_PEERS] = {};
+    // device-side step protocol (gsb_trainer_step_peers): this replica's flag block (written by the others), the others'
+    // blocks, the id of the last step and the events "projection backward of Gaussian chunk c is done"
+    gsb::PeerSync* t_sync = nullptr;
+    gsb::PeerSync* peer_sync[gsb::GSB_MAX_PEERS] = {};
+    uint32_t peer_step_id = 0;
+    uint32_t peer_wait_step = 0;        // != 0: the next batch must first wait for this step's "parameters written" flags
+    int peer_wait_chunks = 0;
+    int peer_chunks = 4;
+    cudaEvent_t ev_chunk[gsb::GSB_MAX_CHUNKS] = {};
+    uint32_t* h_peer_error = nullptr;   // pinned mirror of t_sync->error
     // symmetric-memory / NVLS variant (gsb_trainer_attach_symmetric): parameters and gradients live in caller-owned
     // symmetric buffers, mc_* are the multicast addresses of the same buffers on all replicas
     bool sym = false;
@@ -544,12 +554,26 @@ static void peers_close(Ctx* c)
         if (c->peer_opened[r]) {
             if (c->peer_block[r]) cudaIpcCloseMemHandle(c->peer_block[r]);
             if (c->peer_accum[r]) cudaIpcCloseMemHandle(c->peer_accum[r]);
+            if (c->peer_sync[r]) cudaIpcCloseMemHandle(c->peer_sync[r]);
         }
-        c->peer_block[r] = nullptr; c->peer_accum[r] = nullptr; c->peer_opened[r] = false;
+        c->peer_block[r] = nullptr; c->peer_accum[r] = nullptr; c->peer_sync[r] = nullptr; c->peer_opened[r] = false;
     }
     c->peer_world = 0;
 }
 
+
+// After a gsb_trainer_step_peers the other replicas may still be storing parameters into this replica (and reading its
+// gradients): anything that reads the trainer state from the stream, or overwrites the gradients, first waits for their
+// "parameters written" flags of that step.
+static cudaError_t drain_peer_step(Ctx* c)
+{
+    if (!c->peer_wait_step || !c->t_sync || c->peer_world < 1) return cudaSuccess;
+    cudaError_t e = launch_peer_wait(c->stream, &c->t_sync->params_ready[0][0], c->peer_wait_chunks, c->peer_world, GSB_MAX_PEERS,
+                                     c->peer_wait_step, &c->t_sync->error);
+    c->stats.kernel_launches += 1;
+    c->peer_wait_step = 0;
+    return e;
+}
 
 static void destroy_ctx(Ctx* c)
 {
@@ -584,6 +608,9 @@ static void destroy_ctx(Ctx* c)
     dev_free(c->mapA); dev_free(c->mapB); dev_free(c->mapC); dev_free(c->cot_render); dev_free(c->partial);
     dev_free(c->loss_accum); dev_free(c->d_zero);
     peers_close(c);
+    if (c->t_sync) cudaFree(c->t_sync);
+    if (c->h_peer_error) cudaFreeHost(c->h_peer_error);
+    for (cudaEvent_t& e : c->ev_chunk) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { dev_free(c->t_slab[i]); dev_free(c->t_accum_slab[i]); }
     if (c->h_loss) cudaFreeHost(c->h_loss);
     for (auto& e : c->ev_pool) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
@@ -778,6 +805,7 @@ int gsb_set_flags(gsb_ctx* ctx, int32_t flags)
 int gsb_synchronize(gsb_ctx* ctx)
 {
     CTX_PROLOGUE(ctx);
+    GSB_CUDA_CHECK(c, gsb::drain_peer_step(c));
     gsb::sync_all_streams(c);
     GSB_CUDA_CHECK(c, cudaGetLastError());
     return GSB_OK;
@@ -1114,9 +1142,27 @@ static int render_forward_impl(Ctx* c, int32_t N, const RawParams& p, const gsb:
 
 // K10 on the work stream, K2 (+ activation VJPs) either right behind it (gbuf < 0: single-view API, serial
 // trainer) or on the tail stream out of gradient-record buffer gbuf (pipelined trainer).
+// Peer step protocol: the projection backward of the step's LAST view runs as one launch per Gaussian chunk; after
+// chunk k the replica raises grads_ready[k][rank] in every replica and records ev_chunk[k].
+struct ChunkSignal {
+    uint32_t step = 0;
+    int chunks = 0;
+    long long begin[gsb::GSB_MAX_CHUNKS + 1] = {};
+};
+static int signal_chunk(Ctx* c, cudaStream_t st, const ChunkSignal& sig, int k)
+{
+    gsb::PeerFlagList fl;
+    fl.n = c->peer_world;
+    for (int r = 0; r < c->peer_world; ++r) fl.dst[r] = &c->peer_sync[r]->grads_ready[k][c->peer_rank];
+    GSB_CUDA_CHECK(c, gsb::launch_peer_signal(st, fl, sig.step));
+    GSB_CUDA_CHECK(c, cudaEventRecord(c->ev_chunk[k], st));
+    c->stats.kernel_launches += 1;
+    return GSB_OK;
+}
+
 static int render_backward_impl(Ctx* c, const float* cot_render, const float* cot_depth, const float* cot_alpha, float* g_xyz,
                                 float* g_f_dc, float* g_f_rest, float* g_scales_log, float* g_rot_raw, float* g_opacity_logit,
-                                int accumulate, int gbuf = -1)
+                                int accumulate, int gbuf = -1, const ChunkSignal* sig = nullptr)
 {
     if (!c->saved.valid) { gsb::set_error(c, "gsb_render_backward: no forward saved on this context"); return GSB_ERR_STATE; }
     const int N = c->saved.N;
@@ -1138,15 +1184,32 @@ static int render_backward_impl(Ctx* c, const float* cot_render, const float* co
         GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->tail_stream, c->ev_rb[gbuf], 0));
         pst = c->tail_stream;
     }
-    {
+    if (!sig) {
         gsb::StageTimer t(c, GSB_STAGE_PROJECT_BWD, pst);
         GSB_CUDA_CHECK(c, gsb::launch_project_fused_bwd(pst, N, vp, c->saved.xyz, c->saved.f_dc, c->saved.f_rest,
                                                         c->saved.scales_log, c->saved.rot_raw, c->saved.op_logit, grec,
                                                         g_xyz, g_f_dc, g_f_rest, g_scales_log, g_rot_raw, g_opacity_logit,
                                                         accumulate));
+        c->stats.kernel_launches += N > 0;
+    } else {
+        const long long rest = (long long)(c->cfg.sh_coeffs - 1) * 3;
+        for (int k = 0; k < sig->chunks; ++k) {
+            const long long n0 = sig->begin[k], n1 = sig->begin[k + 1];
+            if (n1 > n0) {
+                gsb::StageTimer t(c, GSB_STAGE_PROJECT_BWD, pst);
+                GSB_CUDA_CHECK(c, gsb::launch_project_fused_bwd(
+                    pst, (int)(n1 - n0), vp, c->saved.xyz + n0 * 3, c->saved.f_dc + n0 * 3, c->saved.f_rest ? c->saved.f_rest + n0 * rest : nullptr,
+                    c->saved.scales_log + n0 * 3, c->saved.rot_raw + n0 * 4, c->saved.op_logit + n0, grec + n0 * gsb::REC_FLOATS,
+                    g_xyz + n0 * 3, g_f_dc + n0 * 3, g_f_rest ? g_f_rest + n0 * rest : nullptr, g_scales_log + n0 * 3, g_rot_raw + n0 * 4,
+                    g_opacity_logit + n0, accumulate));
+                c->stats.kernel_launches += 1;
+            }
+            int rc = signal_chunk(c, pst, *sig, k);
+            if (rc != GSB_OK) return rc;
+        }
     }
     if (split) GSB_CUDA_CHECK(c, cudaEventRecord(c->ev_pb[gbuf], c->tail_stream));
-    c->stats.kernel_launches += 1 + (N > 0);
+    c->stats.kernel_launches += 1;
     return GSB_OK;
 }
 
@@ -1338,6 +1401,7 @@ int gsb_trainer_param_ptrs(gsb_ctx* ctx, float** host_params6, float** host_grad
 {
     CTX_PROLOGUE(ctx);
     if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    GSB_CUDA_CHECK(c, gsb::drain_peer_step(c));   // reads of the returned buffers queued behind this call see the finished step
     for (int k = 0; k < 6; ++k) {
         if (host_params6) host_params6[k] = c->t_p[k];
         if (host_grads6) host_grads6[k] = c->t_g[k];
@@ -1361,7 +1425,8 @@ int gsb_trainer_grad_block(gsb_ctx* ctx, float** grad_block, int64_t* floats)
 // depth-supervision term with weight lambda_depth (GaussianTrainer.swift:693-714,949).
 static int trainer_accumulate_impl(Ctx* c, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
                                    const float* const* host_depths, const uint8_t* const* host_masks, float lambda_depth,
-                                   int32_t targets_on_host, int32_t zero_grads, float grad_scale, float* host_loss)
+                                   int32_t targets_on_host, int32_t zero_grads, float grad_scale, float* host_loss,
+                                   const ChunkSignal* sig = nullptr)
 {
     if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
     GSB_REQUIRE(c, B >= 0 && (B == 0 || (host_cams && host_targets)), "gsb_trainer_accumulate: null argument");
@@ -1376,8 +1441,17 @@ static int trainer_accumulate_impl(Ctx* c, int32_t B, const gsb_camera* host_cam
             if (!c->t_dmask[i]) GSB_CUDA_CHECK(c, gsb::dev_alloc(&c->t_dmask[i], (size_t)c->P));
         }
     }
+    // the previous step may have ended without a barrier (gsb_trainer_step_peers): before this replica reads its parameters
+    // or overwrites its gradients, every owner must have announced "my stores into your replica are done" - which also
+    // means it no longer reads this replica's gradients
+    GSB_CUDA_CHECK(c, gsb::drain_peer_step(c));
     if (host_loss) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->loss_accum, 0, sizeof(float), c->stream));
     if (zero_grads && B == 0) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_g[0], 0, c->t_floats * 4, c->stream));
+    if (sig && B == 0)   // a replica without views this step: its (zero) gradients are complete right away
+        for (int k = 0; k < sig->chunks; ++k) {
+            int rc = signal_chunk(c, c->stream, *sig, k);
+            if (rc != GSB_OK) return rc;
+        }
     // prefetch of view 0's target
     auto prefetch = [&](int b) -> int {
         const int s = b & 1;
@@ -1463,13 +1537,17 @@ static int trainer_accumulate_impl(Ctx* c, int32_t B, const gsb_camera* host_cam
         if (rc != GSB_OK) return rc;
         if (targets_on_host) GSB_CUDA_CHECK(c, cudaEventRecord(c->t_target_free[b & 1], c->stream));
         const int accumulate = (b > 0 || !zero_grads) ? 1 : 0;
+        // peer step protocol: the last view's projection backward always goes to the tail stream, chunk by chunk, so that
+        // the exchange of chunk k (work stream) overlaps the projection backward of chunk k + 1
+        const bool last_sig = sig && b == B - 1;
+        const bool split = overlap || (last_sig && !(c->cfg.flags & (GSB_FLAG_SORT_CUB | GSB_FLAG_NO_OVERLAP)));
         rc = render_backward_impl(c, c->cot_render, with_depth ? c->cot_depth : nullptr, nullptr, c->t_g[0], c->t_g[1], c->t_g[2], c->t_g[3], c->t_g[4],
-                                  c->t_g[5], accumulate, overlap ? (b & 1) : -1);
+                                  c->t_g[5], accumulate, split ? (b & 1) : -1, last_sig ? sig : nullptr);
         if (rc != GSB_OK) return rc;
         if (overlap) GSB_CUDA_CHECK(c, cudaEventRecord(v.ev_back, c->stream));   // raster backward done: the set is free
     }
-    if (overlap && B > 0)   // the gradients are complete when the last projection backward has run (tail stream is in order)
-        GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_pb[(B - 1) & 1], 0));
+    if (overlap && B > 0 && !sig)   // the gradients are complete when the last projection backward has run (tail stream is in order)
+        GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_pb[(B - 1) & 1], 0));   // (peer step protocol: per-chunk events instead)
     if (host_loss) {
         if (c->cfg.flags & GSB_FLAG_ASYNC_LOSS) {   // pinned destination, the caller synchronises when it wants the value
             GSB_CUDA_CHECK(c, cudaMemcpyAsync(host_loss, c->loss_accum, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1516,6 +1594,7 @@ int gsb_trainer_apply(gsb_ctx* ctx, int32_t iteration, int32_t total_iterations,
     CTX_PROLOGUE(ctx);
     if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
     GSB_REQUIRE(c, total_iterations > 0, "gsb_trainer_apply: total_iterations must be positive");
+    GSB_CUDA_CHECK(c, gsb::drain_peer_step(c));
     if (reset_state) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + 2 * c->t_floats, 0, 2 * c->t_floats * sizeof(float), c->stream));
     gsb::AdamTensors t{};
     learning_rates(iteration, total_iterations, t.lr);
@@ -1530,18 +1609,28 @@ int gsb_trainer_apply(gsb_ctx* ctx, int32_t iteration, int32_t total_iterations,
 }
 
 // ---- peer-memory data parallelism ----------------------------------------------------------------
-struct PeerExport {                 // what one replica publishes: 2 IPC handles + the layout the others must share
-    cudaIpcMemHandle_t block, accum;
+struct PeerExport {                 // what one replica publishes: 3 IPC handles + the layout the others must share
+    cudaIpcMemHandle_t block, accum, sync;
     int64_t n, floats, cap;
 };
+static_assert(sizeof(PeerExport) <= GSB_PEER_BLOB_BYTES, "GSB_PEER_BLOB_BYTES too small");
 int gsb_trainer_peers_export(gsb_ctx* ctx, void* host_blob, int64_t blob_bytes)
 {
     CTX_PROLOGUE(ctx);
     if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
     GSB_REQUIRE(c, host_blob && blob_bytes >= (int64_t)sizeof(PeerExport), "gsb_trainer_peers_export: blob too small");
     PeerExport e{};
+    if (!c->t_sync) {   // allocated once per context: survives densification (the slabs do not)
+        GSB_CUDA_CHECK(c, cudaMalloc(reinterpret_cast<void**>(&c->t_sync), sizeof(gsb::PeerSync)));
+        GSB_CUDA_CHECK(c, cudaMemset(c->t_sync, 0, sizeof(gsb::PeerSync)));
+        GSB_CUDA_CHECK(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_peer_error), sizeof(uint32_t)));
+        *c->h_peer_error = 0;
+        for (cudaEvent_t& ev : c->ev_chunk) GSB_CUDA_CHECK(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        if (const char* env = getenv("GSB_PEER_CHUNKS")) c->peer_chunks = std::max(1, std::min(gsb::GSB_MAX_CHUNKS, atoi(env)));
+    }
     GSB_CUDA_CHECK(c, cudaIpcGetMemHandle(&e.block, c->t_block));
     GSB_CUDA_CHECK(c, cudaIpcGetMemHandle(&e.accum, c->t_accum));
+    GSB_CUDA_CHECK(c, cudaIpcGetMemHandle(&e.sync, c->t_sync));
     e.n = c->tN; e.floats = (int64_t)c->t_floats; e.cap = c->t_cap;
     memset(host_blob, 0, (size_t)blob_bytes);
     memcpy(host_blob, &e, sizeof(e));
@@ -1566,49 +1655,51 @@ int gsb_trainer_peers_import(gsb_ctx* ctx, int32_t world, int32_t rank, const vo
             return GSB_ERR_INVALID;
         }
         if (r == rank) {
-            c->peer_block[r] = c->t_block; c->peer_accum[r] = c->t_accum;
+            if (!c->t_sync) { gsb::peers_close(c); gsb::set_error(c, "gsb_trainer_peers_import: call gsb_trainer_peers_export first"); return GSB_ERR_STATE; }
+            c->peer_block[r] = c->t_block; c->peer_accum[r] = c->t_accum; c->peer_sync[r] = c->t_sync;
             continue;
         }
-        void* pb = nullptr; void* pa = nullptr;
+        void* pb = nullptr; void* pa = nullptr; void* ps = nullptr;
         cudaError_t err = cudaIpcOpenMemHandle(&pb, e.block, cudaIpcMemLazyEnablePeerAccess);
         if (err == cudaSuccess) err = cudaIpcOpenMemHandle(&pa, e.accum, cudaIpcMemLazyEnablePeerAccess);
+        if (err == cudaSuccess) err = cudaIpcOpenMemHandle(&ps, e.sync, cudaIpcMemLazyEnablePeerAccess);
         if (err != cudaSuccess) {
             if (pb) cudaIpcCloseMemHandle(pb);
+            if (pa) cudaIpcCloseMemHandle(pa);
             gsb::peers_close(c);
             gsb::set_error(c, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(err));
             cudaGetLastError();
             return GSB_ERR_CUDA;
         }
-        c->peer_block[r] = static_cast<float*>(pb); c->peer_accum[r] = static_cast<float*>(pa); c->peer_opened[r] = true;
+        c->peer_block[r] = static_cast<float*>(pb); c->peer_accum[r] = static_cast<float*>(pa);
+        c->peer_sync[r] = static_cast<gsb::PeerSync*>(ps); c->peer_opened[r] = true;
     }
     c->peer_world = world; c->peer_rank = rank;
+    // A new generation of the step protocol: nobody writes into this block any more (every replica closed its mappings
+    // and passed a barrier before exporting again) and nobody starts a step before all replicas have imported.
+    GSB_CUDA_CHECK(c, cudaMemset(c->t_sync, 0, sizeof(gsb::PeerSync)));
+    c->peer_step_id = 0;
+    c->peer_wait_step = 0;
     return GSB_OK;
 }
 
 int gsb_trainer_peers_close(gsb_ctx* ctx)
 {
     CTX_PROLOGUE(ctx);
+    GSB_CUDA_CHECK(c, gsb::drain_peer_step(c));
     gsb::sync_all_streams(c);
     gsb::peers_close(c);
     return GSB_OK;
 }
 
-int gsb_trainer_apply_peers(gsb_ctx* ctx, int32_t iteration, int32_t total_iterations, int32_t reset_state)
+// Owned slice of the Gaussians [n0, n1) for replica R of W: equal parts on multiples of 4 Gaussians (every tensor slice then
+// starts 16-byte aligned).  Fills the per-launch descriptors of the exchange kernels (adam.cu).
+static void fill_exchange(Ctx* c, int W, int R, long long n0, long long n1, int iteration, int total_iterations, const float* param_base,
+                          gsb::AdamTensors& t, gsb::AdamPeers& pr)
 {
-    CTX_PROLOGUE(ctx);
-    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
-    GSB_REQUIRE(c, total_iterations > 0, "gsb_trainer_apply_peers: total_iterations must be positive");
-    if (c->peer_world < 1 || c->peer_block[c->peer_rank] != c->t_block) {
-        gsb::set_error(c, "gsb_trainer_apply_peers: peers not imported for the current trainer state");
-        return GSB_ERR_STATE;
-    }
-    if (reset_state) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + 2 * c->t_floats, 0, 2 * c->t_floats * sizeof(float), c->stream));
-    const int W = c->peer_world, R = c->peer_rank;
-    // owned Gaussians: equal slices on multiples of 4 (every tensor slice then starts 16-byte aligned)
-    const long long per = (((long long)c->tN + W - 1) / W + 3) & ~3LL;
-    const long long g0 = std::min<long long>((long long)R * per, c->tN), g1 = std::min<long long>(g0 + per, c->tN);
-    gsb::AdamTensors t{};
-    gsb::AdamPeers pr{};
+    const long long n = n1 - n0;
+    const long long per = ((n + W - 1) / W + 3) & ~3LL;
+    const long long g0 = n0 + std::min<long long>((long long)R * per, n), g1 = n0 + std::min<long long>((long long)R * per + per, n);
     learning_rates(iteration, total_iterations, t.lr);
     const int K = c->cfg.sh_coeffs;
     const long long row[6] = {3, 3, (long long)(K - 1) * 3, 3, 4, 1};
@@ -1616,19 +1707,111 @@ int gsb_trainer_apply_peers(gsb_ctx* ctx, int32_t iteration, int32_t total_itera
         t.p[k] = c->t_p[k]; t.g[k] = c->t_g[k]; t.m[k] = c->t_m[k]; t.v[k] = c->t_v[k];
         t.count[k] = (g1 - g0) * row[k];
         pr.first[k] = g0 * row[k];
-        pr.tensor_off[k] = (long long)(c->t_p[k] - c->t_block);
-    }
-    for (int r = 0; r < W; ++r) {
-        pr.params[r] = c->peer_block[r];
-        pr.grads[r] = c->peer_block[r] + c->t_floats;
-        pr.accum[r] = c->peer_accum[r];
+        pr.tensor_off[k] = (long long)(c->t_p[k] - param_base);
     }
     pr.g0 = g0; pr.g1 = g1; pr.world = W; pr.rank = R;
+    pr.accum_all = 0;
+    if (c->peer_world == W && c->peer_accum[R] == c->t_accum) {   // the replicas' slabs are peer-mapped
+        for (int r = 0; r < W; ++r) {
+            pr.params[r] = c->peer_block[r];
+            pr.grads[r] = c->peer_block[r] + c->t_floats;
+            pr.accum[r] = c->peer_accum[r];
+        }
+        pr.accum_all = 1;
+    } else {
+        pr.accum[R] = c->t_accum;
+    }
+}
+
+int gsb_trainer_apply_peers(gsb_ctx* ctx, int32_t iteration, int32_t total_iterations, int32_t reset_state)
+{
+    CTX_PROLOGUE(ctx);
+    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    GSB_REQUIRE(c, total_iterations > 0, "gsb_trainer_apply_peers: total_iterations must be positive");
+    if (c->peer_world < 1 || c->peer_block[c->peer_rank] != c->t_block || c->sym) {
+        gsb::set_error(c, "gsb_trainer_apply_peers: peers not imported for the current trainer state");
+        return GSB_ERR_STATE;
+    }
+    if (reset_state) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + 2 * c->t_floats, 0, 2 * c->t_floats * sizeof(float), c->stream));
+    gsb::AdamTensors t{};
+    gsb::AdamPeers pr{};
+    fill_exchange(c, c->peer_world, c->peer_rank, 0, c->tN, iteration, total_iterations, c->t_block, t, pr);
     gsb::StageTimer tm(c, GSB_STAGE_ADAM);
     int launches = 0;
-    GSB_CUDA_CHECK(c, gsb::launch_adam_peers(c->stream, t, pr, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, &launches));
+    GSB_CUDA_CHECK(c, gsb::launch_adam_peers(c->stream, t, pr, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, nullptr, &launches));
     c->stats.kernel_launches += launches;
     c->t_accum_steps += 1;
+    return GSB_OK;
+}
+
+// ---- the whole data-parallel step with device-side synchronisation ---------------------------------
+// wait (previous step's parameter stores have landed, every owner is done with my gradients)
+//   -> views (the last view's projection backward chunk by chunk, each chunk announced to every replica)
+//   -> per chunk: exchange kernel (waits for every replica's announcement, reduces + Adam + stores, announces back)
+// No host barrier and no NCCL call on the step: the replicas only meet in the flags.
+int gsb_trainer_step_peers(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
+                           int32_t targets_on_host, float grad_scale, int32_t iteration, int32_t total_iterations, int32_t reset_state,
+                           float* host_loss)
+{
+    CTX_PROLOGUE(ctx);
+    if (c->tN == 0) { gsb::set_error(c, "trainer not initialised"); return GSB_ERR_STATE; }
+    GSB_REQUIRE(c, total_iterations > 0 && B >= 0, "gsb_trainer_step_peers: bad arguments");
+    const int W = c->peer_world, R = c->peer_rank;
+    if (W < 1 || c->peer_block[R] != c->t_block || !c->t_sync) {
+        gsb::set_error(c, "gsb_trainer_step_peers: peers not imported for the current trainer state");
+        return GSB_ERR_STATE;
+    }
+    const uint32_t step = ++c->peer_step_id;
+    ChunkSignal sig;
+    sig.step = step;
+    sig.chunks = std::max(1, std::min(c->peer_chunks, gsb::GSB_MAX_CHUNKS));
+    {   // chunk boundaries on multiples of 128 Gaussians (one projection CTA, 16-byte aligned tensor rows)
+        const long long per = (((long long)c->tN + sig.chunks - 1) / sig.chunks + 127) & ~127LL;
+        for (int k = 0; k <= sig.chunks; ++k) sig.begin[k] = std::min<long long>((long long)k * per, c->tN);
+    }
+    int rc = trainer_accumulate_impl(c, B, host_cams, host_targets, nullptr, nullptr, 0.0f, targets_on_host, 1, grad_scale, host_loss, &sig);
+    if (rc != GSB_OK) return rc;
+    if (reset_state) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + 2 * c->t_floats, 0, 2 * c->t_floats * sizeof(float), c->stream));
+    const float* param_base = c->sym ? c->sym_params : c->t_block;
+    for (int k = 0; k < sig.chunks; ++k) {
+        GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_chunk[k], 0));   // my own chunk k is done (other stream)
+        gsb::AdamTensors t{};
+        gsb::AdamPeers pr{};
+        fill_exchange(c, W, R, sig.begin[k], sig.begin[k + 1], iteration, total_iterations, param_base, t, pr);
+        gsb::PeerStepSync sy;
+        sy.wait_flags = &c->t_sync->grads_ready[k][0];
+        sy.done = &c->t_sync->done[k];
+        for (int r = 0; r < W; ++r) sy.announce[r] = &c->peer_sync[r]->params_ready[k][R];
+        sy.error = &c->t_sync->error;
+        sy.step = step;
+        gsb::StageTimer tm(c, GSB_STAGE_ADAM);
+        int launches = 0;
+        if (c->sym)
+            GSB_CUDA_CHECK(c, gsb::launch_adam_multicast(c->stream, t, pr, c->mc_grads, c->mc_params, c->cfg.adam_beta1, c->cfg.adam_beta2,
+                                                         c->cfg.adam_eps, 1.0f, c->tN, &sy, &launches));
+        else
+            GSB_CUDA_CHECK(c, gsb::launch_adam_peers(c->stream, t, pr, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, &sy, &launches));
+        c->stats.kernel_launches += launches;
+    }
+    c->t_accum_steps += 1;
+    c->peer_wait_step = step;        // the next batch (fused or not) starts by waiting for every replica's stores of this step
+    c->peer_wait_chunks = sig.chunks;
+    return GSB_OK;
+}
+
+// A bounded wait of the step protocol ran out on this replica (a replica died or the replicas disagree about the step
+// count): the results since then are invalid.  Reads one word; synchronises the context.
+int gsb_trainer_peers_check(gsb_ctx* ctx)
+{
+    CTX_PROLOGUE(ctx);
+    if (!c->t_sync) return GSB_OK;
+    GSB_CUDA_CHECK(c, gsb::drain_peer_step(c));
+    gsb::sync_all_streams(c);
+    GSB_CUDA_CHECK(c, cudaMemcpy(c->h_peer_error, &c->t_sync->error, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (*c->h_peer_error) {
+        gsb::set_error(c, "gsb_trainer_step_peers: a wait for another replica timed out (2 s); the step results are invalid");
+        return GSB_ERR_STATE;
+    }
     return GSB_OK;
 }
 
@@ -1666,26 +1849,13 @@ int gsb_trainer_apply_multicast(gsb_ctx* ctx, int32_t iteration, int32_t total_i
     GSB_REQUIRE(c, total_iterations > 0, "gsb_trainer_apply_multicast: total_iterations must be positive");
     if (!c->sym) { gsb::set_error(c, "gsb_trainer_apply_multicast: no symmetric buffers attached to the current trainer state"); return GSB_ERR_STATE; }
     if (reset_state) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + 2 * c->t_floats, 0, 2 * c->t_floats * sizeof(float), c->stream));
-    const int W = c->sym_world, R = c->sym_rank;
-    const long long per = (((long long)c->tN + W - 1) / W + 3) & ~3LL;
-    const long long g0 = std::min<long long>((long long)R * per, c->tN), g1 = std::min<long long>(g0 + per, c->tN);
     gsb::AdamTensors t{};
     gsb::AdamPeers pr{};
-    learning_rates(iteration, total_iterations, t.lr);
-    const int K = c->cfg.sh_coeffs;
-    const long long row[6] = {3, 3, (long long)(K - 1) * 3, 3, 4, 1};
-    for (int k = 0; k < 6; ++k) {
-        t.p[k] = c->t_p[k]; t.g[k] = c->t_g[k]; t.m[k] = c->t_m[k]; t.v[k] = c->t_v[k];
-        t.count[k] = (g1 - g0) * row[k];
-        pr.first[k] = g0 * row[k];
-        pr.tensor_off[k] = (long long)(c->t_p[k] - c->sym_params);
-    }
-    pr.accum[R] = c->t_accum;
-    pr.g0 = g0; pr.g1 = g1; pr.world = W; pr.rank = R;
+    fill_exchange(c, c->sym_world, c->sym_rank, 0, c->tN, iteration, total_iterations, c->sym_params, t, pr);
     gsb::StageTimer tm(c, GSB_STAGE_ADAM);
     int launches = 0;
     GSB_CUDA_CHECK(c, gsb::launch_adam_multicast(c->stream, t, pr, c->mc_grads, c->mc_params, c->cfg.adam_beta1, c->cfg.adam_beta2,
-                                                 c->cfg.adam_eps, 1.0f, c->tN, &launches));
+                                                 c->cfg.adam_eps, 1.0f, c->tN, nullptr, &launches));
     c->stats.kernel_launches += launches;
     c->t_accum_steps += 1;
     return GSB_OK;

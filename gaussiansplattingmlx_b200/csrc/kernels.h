@@ -184,6 +184,23 @@ struct AdamTensors {
 // slice of Gaussians [g0, g1) this rank owns.  AdamTensors passed with it holds the LOCAL p / m / v base pointers of the
 // six tensors and count[k] = floats of the owned slice of tensor k.
 constexpr int GSB_MAX_PEERS = 8;
+constexpr int GSB_MAX_CHUNKS = 8;
+// Flags of the device-side step protocol (gsb_trainer_step_peers), one block per replica, written by the OTHER replicas
+// through peer memory.  Every word holds the id of the last step for which the event happened (monotone, compared >=).
+struct PeerSync {
+    uint32_t grads_ready[GSB_MAX_CHUNKS][GSB_MAX_PEERS];    // [c][r]: replica r's gradients of Gaussian chunk c are complete
+    uint32_t params_ready[GSB_MAX_CHUNKS][GSB_MAX_PEERS];   // [c][r]: owner r has written its part of chunk c into THIS replica
+    uint32_t done[GSB_MAX_CHUNKS];                          // local: finished CTAs of the exchange kernel of chunk c
+    uint32_t error;                                         // local: a bounded wait ran out (the step's results are invalid)
+    uint32_t pad[7];
+};
+struct PeerStepSync {                      // what one exchange kernel launch waits for and announces
+    const uint32_t* wait_flags = nullptr;  // local grads_ready[c][0..world): all must reach `step` before any gradient is read
+    uint32_t* done = nullptr;              // local CTA completion counter (self-resetting)
+    uint32_t* announce[GSB_MAX_PEERS] = {};   // params_ready[c][rank] of every replica: set to `step` by the last CTA
+    uint32_t* error = nullptr;
+    uint32_t step = 0;
+};
 struct AdamPeers {
     const float* grads[GSB_MAX_PEERS];   // base of the gradient copy (six tensors, padded) of every replica
     float* params[GSB_MAX_PEERS];        // base of the parameter copy of every replica
@@ -192,13 +209,26 @@ struct AdamPeers {
     long long first[6];                  // first float of the owned slice inside tensor k (multiple of 4)
     long long g0, g1;                    // owned Gaussians
     int world, rank;
+    int accum_all;                       // accum[r] is valid for EVERY replica (peer-mapped), not only for accum[rank]
 };
+// sync == nullptr: the caller brackets the launch with two barriers (gsb_trainer_apply_peers); otherwise the kernel
+// itself waits for the replicas' gradients and announces its parameter stores (gsb_trainer_step_peers)
 cudaError_t launch_adam_peers(cudaStream_t st, const AdamTensors& t, const AdamPeers& pr, float beta1, float beta2, float eps,
-                              float gscale, int* launches);
+                              float gscale, const PeerStepSync* sync, int* launches);
 // NVLS variant: mc_grads / mc_params = multicast addresses of the replicas' gradient / parameter blocks (symmetric memory);
-// pr supplies the owned slice, the tensor offsets and (accum[rank]) the local D1 accumulator.
+// pr supplies the owned slice, the tensor offsets and the D1 accumulators (accum[r] of every replica when the slabs are
+// peer-mapped: D1 is then computed for the owned slice only and stored to every replica; otherwise accum[rank] alone and
+// every replica computes all of D1 from the switch-reduced gradient).
 cudaError_t launch_adam_multicast(cudaStream_t st, const AdamTensors& t, const AdamPeers& pr, const float* mc_grads, float* mc_params,
-                                  float beta1, float beta2, float eps, float gscale, int N, int* launches);
+                                  float beta1, float beta2, float eps, float gscale, int N, const PeerStepSync* sync, int* launches);
+// system-scope release of `value` into up to GSB_MAX_PEERS flag words (after everything queued before it on the stream)
+struct PeerFlagList {
+    uint32_t* dst[GSB_MAX_PEERS] = {};
+    int n = 0;
+};
+cudaError_t launch_peer_signal(cudaStream_t st, const PeerFlagList& flags, uint32_t value);
+// bounded wait until the rows x cols words flags[row * row_stride + col] have all reached `value` (ids modulo 2^32)
+cudaError_t launch_peer_wait(cudaStream_t st, const uint32_t* flags, int rows, int cols, int row_stride, uint32_t value, uint32_t* error);
 // gscale multiplies every gradient before use (1.0 on the training path); launches (may be NULL) is
 // incremented by the number of kernels launched.
 cudaError_t launch_adam(cudaStream_t st, const AdamTensors& t, float beta1, float beta2, float eps, float gscale, int N,

@@ -130,6 +130,14 @@ class ViewParallel:
         ctx.trainer_apply_peers(iteration, total_iterations, reset_state)
         self.stream_barrier()            # every replica's parameters (and D1 accumulators) are written
 
+    def fused_step(self, ctx, cams, targets, grad_scale: float, iteration: int, total_iterations: int, reset_state: bool = False,
+                   want_loss: bool = False, loss_out=None):
+        """The whole data-parallel step in the library, replicas synchronised by flags in peer memory - no NCCL call, no host
+        barrier (``gsb_trainer_step_peers``): views -> chunked projection backward of the last view -> per-chunk exchange
+        (peer loads / stores, or NVLS multimem when ``enable_multicast`` attached symmetric buffers) overlapping it.  Needs
+        ``enable_peers``.  ``cams`` / ``targets`` may be empty on a rank without views; returns this rank's part of the loss."""
+        return ctx.trainer_step_peers(cams, targets, grad_scale, iteration, total_iterations, reset_state, want_loss, loss_out)
+
     def all_reduce_scalar_sum(self, value: float, device=None) -> float:
         """SUM over ranks of a host scalar (the reported batch loss: every rank holds the part of its own views)."""
         if self.world == 1:

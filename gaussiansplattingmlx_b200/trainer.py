@@ -113,6 +113,16 @@ class GaussianTrainer:
         B = len(views)
         mine = [views[i] for i in self.parallel.my_views(B)]
         loss = None
+        fused = self._peers and self._depths is None and not (want_loss and early_stopping_threshold is not None)
+        if fused:
+            # the whole step in the library, replicas synchronised by flags in peer memory (no NCCL call on the step); used
+            # whenever no early-stopping decision has to be taken between the backward and the update
+            loss = self.parallel.fused_step(ctx, [self._gcams[v] for v in mine], [self._targets[v] for v in mine], 1.0 / B, iteration,
+                                            self.iterationCount, want_loss=want_loss and bool(mine))
+            if want_loss and self.parallel.world > 1:
+                loss = self.parallel.all_reduce_scalar_sum(loss or 0.0, ctx.device)
+            self._after_update(iteration)
+            return loss
         if mine:
             kw = {}
             if self._depths is not None:
@@ -135,6 +145,11 @@ class GaussianTrainer:
             if self.parallel.world > 1:
                 self.parallel.all_reduce_sum(self._grad_block)
             ctx.trainer_apply(iteration, self.iterationCount, reset_state=False)
+        self._after_update(iteration)
+        return loss
+
+    def _after_update(self, iteration: int):
+        ctx = self.gaussRender.ctx
         if self.outputDirectoryURL and iteration % self.save_snapshot_per_iteration == 0:
             self.save_snapshot(iteration)                     # GaussianTrainer.swift:1092 (before split_and_prune)
         if iteration % self.split_and_prune_per_iteration == 0:   # :1098-1114, independent of the optimiser policy
@@ -145,7 +160,6 @@ class GaussianTrainer:
                 tt = ctx.trainer_tensors()
                 for k in PARAM_ORDER:
                     tt["m"][k].zero_(); tt["v"][k].zero_()
-        return loss
 
     def split_and_prune(self, iteration: int):
         """``GaussianTrainer.split_and_prune`` (``GaussianTrainer.swift:766-908``): iteration guard on the host, the rest in

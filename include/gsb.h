@@ -239,10 +239,23 @@ GSB_API int gsb_trainer_apply(gsb_ctx*, int32_t iteration, int32_t total_iterati
  * replicas have mapped: EVERY replica must call gsb_trainer_peers_close and pass a host barrier before
  * gsb_trainer_densify (which otherwise fails with GSB_ERR_STATE), then export / import the new slabs; the same close +
  * barrier is required before any replica's gsb_destroy. */
+/* gsb_trainer_step_peers: the WHOLE data-parallel step with device-side synchronisation - no host barrier, no NCCL call.
+ *   = gsb_trainer_accumulate(B views, zero_grads, grad_scale) + the exchange, where the replicas meet only in flag words
+ *   kept in peer-mapped memory: the projection backward of the step's last view runs in Gaussian chunks, each chunk is
+ *   announced to every replica, and the exchange kernel of chunk k (reduce the owned slice over all replicas + Adam + D1 +
+ *   store the parameters into every replica; NVLS multimem variant when symmetric buffers are attached) starts as soon as
+ *   all replicas have announced chunk k - so it overlaps the projection backward of chunk k+1 - and announces its stores
+ *   back.  The next batch on any replica begins by waiting for those announcements.  Every replica must call it the same
+ *   number of times (B may be 0 on a replica without views).  Waits are bounded (2 s): gsb_trainer_peers_check reports a
+ *   replica that never arrived.  May be mixed with the barrier-bracketed gsb_trainer_apply_peers form. */
 #define GSB_PEER_BLOB_BYTES 256
 GSB_API int gsb_trainer_peers_export(gsb_ctx*, void* host_blob, int64_t blob_bytes);
 GSB_API int gsb_trainer_peers_import(gsb_ctx*, int32_t world, int32_t rank, const void* host_blobs, int64_t blob_bytes);
 GSB_API int gsb_trainer_apply_peers(gsb_ctx*, int32_t iteration, int32_t total_iterations, int32_t reset_state);
+GSB_API int gsb_trainer_step_peers(gsb_ctx*, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
+                           int32_t targets_on_host, float grad_scale, int32_t iteration, int32_t total_iterations,
+                           int32_t reset_state, float* host_loss);
+GSB_API int gsb_trainer_peers_check(gsb_ctx*);   /* GSB_ERR_STATE when a bounded wait of the step protocol ran out; synchronises */
 /* Unmaps the other replicas' slabs.  Call it on every replica (and synchronise the replicas) BEFORE any of them destroys
  * its context: memory exported through CUDA IPC must not be freed while another process still has it open. */
 GSB_API int gsb_trainer_peers_close(gsb_ctx*);
