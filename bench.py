@@ -240,8 +240,9 @@ def run_gsb(args, rank, local_rank, world):
     total_iters = 30000
 
     # ---- data-parallel step variant (N > 1)
-    #   fused     (default) gsb_trainer_step_peers: flags in peer memory, chunked projection backward overlapping the exchange
-    #   fused_mc  the same with the NVLS multimem exchange kernel (torch symmetric memory)
+    #   fused_mc  (default) gsb_trainer_step_peers: flags in peer memory, chunked projection backward overlapping the exchange,
+    #             NVLS multimem exchange kernel (torch symmetric memory); falls back to `fused` without multicast
+    #   fused     the same with plain peer loads / stores
     #   peers / multicast   barrier + one exchange kernel + barrier (two 4-byte NCCL all-reduces per step)
     #   nccl      NCCL all-reduce of the gradient block + Adam on every replica
     dp = {"mode": "single", "check": None}
@@ -253,7 +254,7 @@ def run_gsb(args, rank, local_rank, world):
             from tools.dp_check import run_dp_check
             dp["check"] = run_dp_check(rank, world, local_rank, n=20001, W=256, H=160)
             log(f"[rank {rank}] dp_check: {json.dumps(dp['check'])}")
-        want = os.environ.get("GSB_DP", "fused")
+        want = os.environ.get("GSB_DP", "fused_mc")   # the NVLS exchange where the box has multicast, else peer loads / stores
         dp["mode"] = "nccl"
         if want != "nccl" and vp_dp.enable_peers(ctx):
             dp["mode"] = "peers"
@@ -261,6 +262,9 @@ def run_gsb(args, rank, local_rank, world):
                 dp["mode"] = "fused"
             if want in ("multicast", "fused_mc") and vp_dp.enable_multicast(ctx):
                 dp["mode"] = "fused_mc" if want == "fused_mc" else "multicast"
+            tune = [int(os.environ.get(k, "0")) for k in ("GSB_PEER_CHUNKS", "GSB_PEER_BLOCKS", "GSB_MC_BLOCKS")]
+            if any(tune):
+                ctx.trainer_peers_tune(*tune)
         log(f"[rank {rank}] data-parallel step: {dp['mode']}")
 
     def reattach():
@@ -483,7 +487,7 @@ def run_gsb(args, rank, local_rank, world):
         calls = st["stage_calls"].get(name, 0)
         if not calls:
             continue
-        ms = st["stage_ms"][name] / (K if name in per_step_stages else calls)
+        ms = st["stage_ms"][name] / (K if name in per_step_stages else K * nv)   # per step / per view (a stage may be several launches)
         if bound == "hbm":
             ach = work / (ms * 1e-3) / 1e9
             kernels[name] = {"bound": "hbm", "ms": ms, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",

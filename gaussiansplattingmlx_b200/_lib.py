@@ -94,6 +94,7 @@ SIGNATURES = {
     "gsb_trainer_peers_close": (C.c_int, [_P]),
     "gsb_trainer_step_peers": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), _I, _F, _I, _I, _I, _P]),
     "gsb_trainer_peers_check": (C.c_int, [_P]),
+    "gsb_trainer_peers_tune": (C.c_int, [_P, _I, _I, _I]),
     "gsb_trainer_attach_symmetric": (C.c_int, [_P, _I, _I, _P, _P, _P, _P, C.c_int64]),
     "gsb_trainer_apply_multicast": (C.c_int, [_P, _I, _I, _I]),
     "gsb_train_step": (C.c_int, [_P, _I, C.POINTER(GsbCamera), C.POINTER(_P), _I, _I, _I, C.POINTER(_F)]),

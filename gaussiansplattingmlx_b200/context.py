@@ -382,6 +382,9 @@ class Context:
                                                     int(reset_state), C.cast(C.pointer(loss), C.c_void_p) if want_loss else None))
         return float(loss.value) if want_loss else None
 
+    def trainer_peers_tune(self, chunks: int = 0, peer_blocks: int = 0, multicast_blocks: int = 0):
+        self._check(self.lib.gsb_trainer_peers_tune(self.h, int(chunks), int(peer_blocks), int(multicast_blocks)))
+
     def trainer_peers_check(self):
         self._check(self.lib.gsb_trainer_peers_check(self.h))
 

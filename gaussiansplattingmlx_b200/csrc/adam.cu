@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(AD_THREADS, 4) k_adam_peers(const __grid_const
 }
 
 cudaError_t launch_adam_peers(cudaStream_t st, const AdamTensors& t, const AdamPeers& pr, float beta1, float beta2, float eps,
-                              float gscale, const PeerStepSync* sync, int* launches)
+                              float gscale, const PeerStepSync* sync, int blocks_override, int* launches)
 {
     AdamSeg seg;
     seg.vec_begin[0] = 0;
@@ -273,8 +273,7 @@ cudaError_t launch_adam_peers(cudaStream_t st, const AdamTensors& t, const AdamP
     // 2 per SM under the step protocol, where the projection backward of the next Gaussian chunk must fit beside it (the
     // kernel is NVLink-bound: 296 CTAs keep ~10 MB of peer loads in flight)
     long long cap = sync ? 148LL * 2 : 148LL * 4;
-    static const int env_blocks = getenv("GSB_PEER_BLOCKS") ? atoi(getenv("GSB_PEER_BLOCKS")) : 0;   // tuning only
-    if (env_blocks > 0) cap = env_blocks;
+    if (blocks_override > 0) cap = blocks_override;   // gsb_trainer_peers_tune
     if (blocks > cap) blocks = cap;
     PeerStepSync sy{};
     if (sync) sy = *sync;
@@ -399,7 +398,8 @@ __global__ void __launch_bounds__(AD_THREADS) k_adam_multicast(const __grid_cons
 }
 
 cudaError_t launch_adam_multicast(cudaStream_t st, const AdamTensors& t, const AdamPeers& pr, const float* mc_grads, float* mc_params,
-                                  float beta1, float beta2, float eps, float gscale, int N, const PeerStepSync* sync, int* launches)
+                                  float beta1, float beta2, float eps, float gscale, int N, const PeerStepSync* sync, int blocks_override,
+                                  int* launches)
 {
     AdamSeg seg;
     seg.vec_begin[0] = 0;
@@ -408,9 +408,10 @@ cudaError_t launch_adam_multicast(cudaStream_t st, const AdamTensors& t, const A
     const long long d1 = pr.accum[pr.rank] ? (own_d1 ? pr.g1 - pr.g0 : N) : 0;
     const long long total = std::max<long long>(seg.vec_begin[6], d1);
     long long blocks = (std::max<long long>((total + MC_UNROLL - 1) / MC_UNROLL, 1) + AD_THREADS - 1) / AD_THREADS;
-    long long cap = 148LL * 8;
-    static const int env_blocks = getenv("GSB_MC_BLOCKS") ? atoi(getenv("GSB_MC_BLOCKS")) : 0;   // tuning only
-    if (env_blocks > 0) cap = env_blocks;
+    // one CTA per SM: measured at 8 GPUs (profiles/r2/r2e_exchange_8gpu.jsonl) 148 CTAs 0.65 ms, 296 0.66 ms, 1184 0.70 ms per
+    // step - the switch, not the SMs, sets the pace, and fewer requesters keep it streaming
+    long long cap = 148LL;
+    if (blocks_override > 0) cap = blocks_override;   // gsb_trainer_peers_tune
     if (blocks > cap) blocks = cap;
     PeerStepSync sy{};
     if (sync) sy = *sync;

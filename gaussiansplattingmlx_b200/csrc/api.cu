@@ -163,7 +163,8 @@ struct Ctx {
     uint32_t peer_step_id = 0;
     uint32_t peer_wait_step = 0;        // != 0: the next batch must first wait for this step's "parameters written" flags
     int peer_wait_chunks = 0;
-    int peer_chunks = 4;
+    int peer_chunks = 2;
+    int peer_blocks = 0, mc_blocks = 0;   // CTAs of the exchange kernels (0 = default), gsb_trainer_peers_tune
     cudaEvent_t ev_chunk[gsb::GSB_MAX_CHUNKS] = {};
     uint32_t* h_peer_error = nullptr;   // pinned mirror of t_sync->error
     // symmetric-memory / NVLS variant (gsb_trainer_attach_symmetric): parameters and gradients live in caller-owned
@@ -1738,7 +1739,7 @@ int gsb_trainer_apply_peers(gsb_ctx* ctx, int32_t iteration, int32_t total_itera
     fill_exchange(c, c->peer_world, c->peer_rank, 0, c->tN, iteration, total_iterations, c->t_block, t, pr);
     gsb::StageTimer tm(c, GSB_STAGE_ADAM);
     int launches = 0;
-    GSB_CUDA_CHECK(c, gsb::launch_adam_peers(c->stream, t, pr, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, nullptr, &launches));
+    GSB_CUDA_CHECK(c, gsb::launch_adam_peers(c->stream, t, pr, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, nullptr, c->peer_blocks, &launches));
     c->stats.kernel_launches += launches;
     c->t_accum_steps += 1;
     return GSB_OK;
@@ -1788,14 +1789,26 @@ int gsb_trainer_step_peers(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
         int launches = 0;
         if (c->sym)
             GSB_CUDA_CHECK(c, gsb::launch_adam_multicast(c->stream, t, pr, c->mc_grads, c->mc_params, c->cfg.adam_beta1, c->cfg.adam_beta2,
-                                                         c->cfg.adam_eps, 1.0f, c->tN, &sy, &launches));
+                                                         c->cfg.adam_eps, 1.0f, c->tN, &sy, c->mc_blocks, &launches));
         else
-            GSB_CUDA_CHECK(c, gsb::launch_adam_peers(c->stream, t, pr, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, &sy, &launches));
+            GSB_CUDA_CHECK(c, gsb::launch_adam_peers(c->stream, t, pr, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, &sy, c->peer_blocks, &launches));
         c->stats.kernel_launches += launches;
     }
     c->t_accum_steps += 1;
     c->peer_wait_step = step;        // the next batch (fused or not) starts by waiting for every replica's stores of this step
     c->peer_wait_chunks = sig.chunks;
+    return GSB_OK;
+}
+
+int gsb_trainer_peers_tune(gsb_ctx* ctx, int32_t chunks, int32_t peer_blocks, int32_t multicast_blocks)
+{
+    CTX_PROLOGUE(ctx);
+    GSB_REQUIRE(c, chunks >= 0 && chunks <= gsb::GSB_MAX_CHUNKS && peer_blocks >= 0 && multicast_blocks >= 0, "gsb_trainer_peers_tune: bad arguments");
+    GSB_CUDA_CHECK(c, gsb::drain_peer_step(c));
+    gsb::sync_all_streams(c);
+    if (chunks > 0) c->peer_chunks = chunks;
+    c->peer_blocks = peer_blocks;
+    c->mc_blocks = multicast_blocks;
     return GSB_OK;
 }
 
@@ -1855,7 +1868,7 @@ int gsb_trainer_apply_multicast(gsb_ctx* ctx, int32_t iteration, int32_t total_i
     gsb::StageTimer tm(c, GSB_STAGE_ADAM);
     int launches = 0;
     GSB_CUDA_CHECK(c, gsb::launch_adam_multicast(c->stream, t, pr, c->mc_grads, c->mc_params, c->cfg.adam_beta1, c->cfg.adam_beta2,
-                                                 c->cfg.adam_eps, 1.0f, c->tN, nullptr, &launches));
+                                                 c->cfg.adam_eps, 1.0f, c->tN, nullptr, c->mc_blocks, &launches));
     c->stats.kernel_launches += launches;
     c->t_accum_steps += 1;
     return GSB_OK;

@@ -214,13 +214,13 @@ struct AdamPeers {
 // sync == nullptr: the caller brackets the launch with two barriers (gsb_trainer_apply_peers); otherwise the kernel
 // itself waits for the replicas' gradients and announces its parameter stores (gsb_trainer_step_peers)
 cudaError_t launch_adam_peers(cudaStream_t st, const AdamTensors& t, const AdamPeers& pr, float beta1, float beta2, float eps,
-                              float gscale, const PeerStepSync* sync, int* launches);
+                              float gscale, const PeerStepSync* sync, int blocks, int* launches);
 // NVLS variant: mc_grads / mc_params = multicast addresses of the replicas' gradient / parameter blocks (symmetric memory);
 // pr supplies the owned slice, the tensor offsets and the D1 accumulators (accum[r] of every replica when the slabs are
 // peer-mapped: D1 is then computed for the owned slice only and stored to every replica; otherwise accum[rank] alone and
 // every replica computes all of D1 from the switch-reduced gradient).
 cudaError_t launch_adam_multicast(cudaStream_t st, const AdamTensors& t, const AdamPeers& pr, const float* mc_grads, float* mc_params,
-                                  float beta1, float beta2, float eps, float gscale, int N, const PeerStepSync* sync, int* launches);
+                                  float beta1, float beta2, float eps, float gscale, int N, const PeerStepSync* sync, int blocks, int* launches);
 // system-scope release of `value` into up to GSB_MAX_PEERS flag words (after everything queued before it on the stream)
 struct PeerFlagList {
     uint32_t* dst[GSB_MAX_PEERS] = {};

@@ -255,6 +255,9 @@ GSB_API int gsb_trainer_apply_peers(gsb_ctx*, int32_t iteration, int32_t total_i
 GSB_API int gsb_trainer_step_peers(gsb_ctx*, int32_t B, const gsb_camera* host_cams, const float* const* host_targets,
                            int32_t targets_on_host, float grad_scale, int32_t iteration, int32_t total_iterations,
                            int32_t reset_state, float* host_loss);
+/* tuning of the step protocol: Gaussian chunks per step (1..8, 0 = keep; default 2) and CTAs of the peer / multicast
+ * exchange kernels (0 = default: 2 per SM beside the projection backward, 1 per SM for the NVLS kernel) */
+GSB_API int gsb_trainer_peers_tune(gsb_ctx*, int32_t chunks, int32_t peer_blocks, int32_t multicast_blocks);
 GSB_API int gsb_trainer_peers_check(gsb_ctx*);   /* GSB_ERR_STATE when a bounded wait of the step protocol ran out; synchronises */
 /* Unmaps the other replicas' slabs.  Call it on every replica (and synchronise the replicas) BEFORE any of them destroys
  * its context: memory exported through CUDA IPC must not be freed while another process still has it open. */
