@@ -93,6 +93,9 @@ class GaussianTrainer:
         # one process per GPU over NCCL: the step is fused with its collective over NVLink peer memory (dp.peer_step);
         # otherwise (gloo, a single rank) all-reduce + gsb_trainer_apply
         self._peers = self.parallel.world > 1 and self.parallel.enable_peers(ctx)
+        # ... and through the NVSwitch (NVLS multimem exchange kernel) where the box has multicast: measured 0.65 ms against
+        # 0.81 ms per step at 8 GPUs (profiles/r2/r2e_exchange_8gpu.jsonl)
+        self._multicast = self._peers and self.parallel.enable_multicast(ctx)
         self.losses: List[float] = []
 
     def stopTrain(self):
@@ -140,7 +143,7 @@ class GaussianTrainer:
             self.stopped_early = True
             return loss
         if self._peers:
-            self.parallel.peer_step(ctx, iteration, self.iterationCount, reset_state=False)
+            (self.parallel.multicast_step if self._multicast else self.parallel.peer_step)(ctx, iteration, self.iterationCount, reset_state=False)
         else:
             if self.parallel.world > 1:
                 self.parallel.all_reduce_sum(self._grad_block)
@@ -182,6 +185,7 @@ class GaussianTrainer:
             self._grad_block = ctx.trainer_grad_block()
             if had_peers:
                 self._peers = self.parallel.enable_peers(ctx)
+                self._multicast = self._peers and self._multicast and self.parallel.enable_multicast(ctx)
         return info
 
     def close(self):
