@@ -1497,6 +1497,24 @@ static int trainer_accumulate_impl(Ctx* c, int32_t B, const gsb_camera* host_cam
         front_issued = b;
         return GSB_OK;
     };
+    // measurement aid (GSB_DBG_FRONT_ALL=1, needs a build with GSB_VIEW_SETS_N >= B): every front of the batch is issued
+    // first, each on its own stream, the work stream waits for all of them and the span is printed (synchronises)
+    static const bool dbg_front_all = getenv("GSB_DBG_FRONT_ALL") != nullptr;
+    if (dbg_front_all && overlap && B <= gsb::GSB_VIEW_SETS) {
+        static cudaEvent_t ea = nullptr, eb = nullptr;
+        if (!ea) { cudaEventCreate(&ea); cudaEventCreate(&eb); }
+        cudaEventRecord(ea, c->stream);
+        for (int b = 0; b < B; ++b) {
+            int rc = issue_front(b);
+            if (rc != GSB_OK) return rc;
+        }
+        for (int b = 0; b < B; ++b) GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->vb[b % gsb::GSB_VIEW_SETS].ev_front, 0));
+        cudaEventRecord(eb, c->stream);
+        cudaEventSynchronize(eb);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ea, eb);
+        fprintf(stderr, "[GSB_DBG_FRONT_ALL] %d fronts on %d streams, alone on the GPU: %.3f ms\n", B, gsb::GSB_VIEW_SETS, ms);
+    }
     for (int b = 0; b < B; ++b) {
         GSB_REQUIRE(c, host_targets[b] != nullptr, "gsb_trainer_accumulate: null target");
         if (targets_on_host && b + 1 < B) {

@@ -6,8 +6,8 @@
 // Both kernels are FP32-issue bound (ncu: issue slots ~82 % busy), so the design goal is the fewest
 // instructions per (pixel, Gaussian) evaluation:
 //   * a tile's list is (tile_ranges, Gaussian indices in depth order) from tilelists.cu; the 48-byte records are
-//     gathered from the L2-resident record table straight into shared memory by 16-byte async copies (LDGSTS; the
-//     backward also has per-record TMA bulk copies, GSB_GATHER_TMA=1) completing on mbarriers, double-buffered;
+//     gathered from the L2-resident record table straight into shared memory by 16-byte async copies (LDGSTS)
+//     completing on mbarriers, double-buffered;
 //   * records carry the conic/opacity pre-folded into log2 units (common.cuh), so
 //     alpha = min(0.99, ex2(A dx^2 + B dx dy + C dy^2 + lo));
 //   * a thread owns a COLUMN of pixels (forward 4, backward 8): the record is read once per column and the exponent
@@ -47,11 +47,11 @@ constexpr int BGRP = 3;          // backward: Gaussians per shared-memory reduct
 constexpr int CK = 256;          // Gaussians between transmittance/colour checkpoints (forward) = backward segment length
 constexpr int CK_MAX = 16;       // checkpoints per block (a longer list ends in one long backward item)
 constexpr int BPAD = 36;         // padded column length (floats): 144-byte stride keeps the LDS.128 of 8 lanes on distinct banks
-// Gather staging engine for the 48-byte records: 1 = one TMA bulk copy per record (cp.async.bulk, UBLKCP),
-// 0 = three 16-byte cp.async (LDGSTS) per record.  Both complete on the batch's mbarrier.
-#ifndef GSB_GATHER_TMA
-#define GSB_GATHER_TMA 0
-#endif
+// Gather staging of the 48-byte records: three 16-byte cp.async (LDGSTS) per record completing on the batch's mbarrier.
+// One TMA bulk copy per record (cp.async.bulk, 48 bytes, UBLKCP) was measured and removed: a list is a GATHER of
+// scattered records, so TMA can only move 48 bytes per instruction and its per-copy issue cost loses to LDGSTS - forward
+// 0.452 vs 0.430 ms, backward 0.793 vs 0.764 ms on the same box (profiles/r2/r2h_forward_variants_and_tma_gather.txt).
+// TMA is used where the bytes are contiguous: the projection kernels stage 128 Gaussians per CTA with bulk copies.
 
 // (tile, 16x16 sub-block) of this CTA; tiles larger than 16x16 are covered by several CTAs
 struct BlockMap {
@@ -87,7 +87,10 @@ __device__ __forceinline__ BlockMap map_block(const ViewParams& vp, const uint32
 // epilogue by replaying the (at most FCHUNK) Gaussians of the chunk in which the pixel died, starting
 // from the transmittance saved at that chunk's start, with bit-identical arithmetic (fwd_exponents).
 constexpr int FPPT = 4;          // forward: pixels (rows) per thread
-constexpr int FCHUNK = 4;        // Gaussians between termination bookkeeping / warp votes
+#ifndef GSB_FCHUNK
+#define GSB_FCHUNK 8
+#endif
+constexpr int FCHUNK = GSB_FCHUNK;   // Gaussians between termination cuts / warp votes
 static_assert(RB_FWD % FCHUNK == 0, "batch must be a whole number of chunks");
 static_assert(CK % RB_FWD == 0 && CK % RB_BWD == 0, "checkpoints sit on batch boundaries");
 static_assert(RB_BWD == 32 || RB_BWD == 64, "a lane stages one or two records per backward batch");
@@ -244,10 +247,12 @@ __global__ void __launch_bounds__(RT, GSB_FWD_CTAS) k_raster_fwd(const __grid_co
                 ncy[k] = f2_fma(nc, colG, ncy[k]);
                 ncz[k] = f2_fma(nc, colB, ncz[k]);
                 if (DEPTH) ndep[k] = f2_fma(nc, colD, ndep[k]);
-                const f32x2 Tn = f2_fma(T2[k], na, T2[k]);
-                const float t0 = f2_lo(Tn), t1 = f2_hi(Tn);
-                // the terminating Gaussian is included (:599-603)
-                T2[k] = f2_make(t0 < 1e-4f ? 0.0f : t0, t1 < 1e-4f ? 0.0f : t1);
+                // The T < 1e-4 cut (:599-603) is NOT applied per Gaussian: it costs a compare + select per pixel and
+                // Gaussian on an issue-bound loop.  It is applied once per chunk of FCHUNK Gaussians (below); a pixel that
+                // crossed the threshold inside the chunk has blended up to FCHUNK - 1 Gaussians too many, with weights
+                // below 1e-4 - the epilogue replays that one chunk per pixel, finds the exact terminating Gaussian and
+                // takes the surplus terms out again (of the pixel and of the checkpoint sums the backward reads).
+                T2[k] = f2_fma(T2[k], na, T2[k]);
             }
         };
         auto Trow = [&](int r) { return (r & 1) ? f2_hi(T2[r >> 1]) : f2_lo(T2[r >> 1]); };
@@ -286,9 +291,16 @@ __global__ void __launch_bounds__(RT, GSB_FWD_CTAS) k_raster_fwd(const __grid_co
                     }
 #pragma unroll
                     for (int g = 0; g < FCHUNK; ++g) blend(addr + g * 48u);
-                    float tmax = Trow(0);
+                    // the termination cut, once per chunk: a finished pixel continues with T = 0 (adds exact zeros)
+                    float tmax = 0.0f;
 #pragma unroll
-                    for (int r = 1; r < FPPT; ++r) tmax = fmaxf(tmax, Trow(r));
+                    for (int k = 0; k < FPAIRS; ++k) {
+                        float t0 = f2_lo(T2[k]), t1 = f2_hi(T2[k]);
+                        t0 = t0 < 1e-4f ? 0.0f : t0;
+                        t1 = t1 < 1e-4f ? 0.0f : t1;
+                        T2[k] = f2_make(t0, t1);
+                        tmax = fmaxf(tmax, fmaxf(t0, t1));
+                    }
                     if (__all_sync(0xffffffffu, tmax == 0.0f)) { warp_done = true; break; }
                 }
             }
@@ -367,36 +379,62 @@ __global__ void __launch_bounds__(RT, GSB_FWD_CTAS) k_raster_fwd(const __grid_co
             if (!active[r]) continue;
             float Tend = Trow(r);
             uint32_t nContrib = count;
+            auto row = [&](const f32x2* v) { return -((r & 1) ? f2_hi(v[r >> 1]) : f2_lo(v[r >> 1])); };
+            float cur[4] = {row(ncx), row(ncy), row(ncz), DEPTH ? row(ndep) : 0.0f};   // sums since the last checkpoint
+            const size_t po = (size_t)(((tid >> 4) * FPPT + r) * 16 + (tid & 15));      // pixel inside a checkpoint slot
             if (Tend == 0.0f) {
+                // The pixel finished inside chunk ci[r], which it entered with transmittance Ts[r]: replay that chunk with
+                // the blend loop's own bits, find the terminating Gaussian (included, :599-603) and collect what the loop
+                // blended beyond it (the loop only cuts at chunk ends)
                 float t = Ts[r];
                 uint32_t i = ci[r] * FCHUNK;
+                float sur[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                bool found = false;
                 for (int g = 0; g < FCHUNK && i < count; ++g, ++i) {
                     const float4* src = rec + (size_t)vals[start + i] * 3;
                     const float4 a = __ldg(src), q = __ldg(src + 1);
                     const FwdExp e = fwd_exponents(a, q.x, q.y, pxf, pyf);
                     const float alpha = fwd_alpha_rt(e, r);
+                    if (found) {
+                        const float4 c = __ldg(src + 2);
+                        const float w = t * alpha;
+                        sur[0] = fmaf(w, q.z, sur[0]); sur[1] = fmaf(w, q.w, sur[1]); sur[2] = fmaf(w, c.x, sur[2]);
+                        if (DEPTH) sur[3] = fmaf(w, c.z, sur[3]);
+                    }
                     const float Tn = fmaf(-t, alpha, t);
-                    if (Tn < 1e-4f) {
+                    if (!found && Tn < 1e-4f) {
                         nContrib = i + 1u;
                         Tend = Tn;
-                        break;
+                        found = true;
                     }
                     t = Tn;
+                }
+                const uint32_t seg = ci[r] * FCHUNK / (uint32_t)CK;   // the segment (between checkpoints) the surplus went into
+                if (seg < ck_written) {
+                    const size_t o = (size_t)s_slots[seg] * 256 + po;
+                    float4 v = ck.state[o];
+                    v.x -= sur[0]; v.y -= sur[1]; v.z -= sur[2];
+                    ck.state[o] = v;
+                    if (DEPTH) ck.depth[o] -= sur[3];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tot[r][q] -= sur[q];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cur[q] -= sur[q];
                 }
             }
             const size_t p = (size_t)(py0 + r) * vp.W + pxi;
             const float bg = vp.whiteBg ? Tend : 0.0f;
-            auto row = [&](const f32x2* v) { return -((r & 1) ? f2_hi(v[r >> 1]) : f2_lo(v[r >> 1])); };
             if (ck_written) {
                 // final (partial) segment sums + the exact final transmittance (out_alpha = 1 - T loses its low bits)
-                const size_t o = (size_t)s_slots[CK_MAX] * 256 + (size_t)(((tid >> 4) * FPPT + r) * 16 + (tid & 15));
-                ck.state[o] = make_float4(row(ncx), row(ncy), row(ncz), Tend);
-                if (DEPTH) ck.depth[o] = row(ndep);
+                const size_t o = (size_t)s_slots[CK_MAX] * 256 + po;
+                ck.state[o] = make_float4(cur[0], cur[1], cur[2], Tend);
+                if (DEPTH) ck.depth[o] = cur[3];
             }
-            out_color[p * 3 + 0] = (tot[r][0] + row(ncx)) + bg;
-            out_color[p * 3 + 1] = (tot[r][1] + row(ncy)) + bg;
-            out_color[p * 3 + 2] = (tot[r][2] + row(ncz)) + bg;
-            if (DEPTH) out_depth[p] = tot[r][3] + row(ndep);
+            out_color[p * 3 + 0] = (tot[r][0] + cur[0]) + bg;
+            out_color[p * 3 + 1] = (tot[r][1] + cur[1]) + bg;
+            out_color[p * 3 + 2] = (tot[r][2] + cur[2]) + bg;
+            if (DEPTH) out_depth[p] = tot[r][3] + cur[3];
             out_alpha[p] = 1.0f - Tend;
             out_last[p] = nContrib;
         }
@@ -446,8 +484,8 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
         __syncwarp();
     };
     if (lane == 0) {
-        mbar_init(&s_bar[0], GSB_GATHER_TMA ? 1 : 32);
-        mbar_init(&s_bar[1], GSB_GATHER_TMA ? 1 : 32);
+        mbar_init(&s_bar[0], 32);
+        mbar_init(&s_bar[1], 32);
         mbar_fence_init();
     }
     __syncwarp();
@@ -559,7 +597,7 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
     const uint32_t lstart = start + seg_begin;   // list position of the item's first Gaussian
 
     // batches are visited last -> first; sequence number s = nb-1-b selects stage / parity
-    // gather staging as in the forward: each lane pulls two 48-byte records per batch with TMA bulk copies
+    // gather staging as in the forward: each lane pulls two 48-byte records per batch
     uint32_t ia = 0xffffffffu, ib = 0xffffffffu;   // indices of this lane's two slots of the next batch to issue
     auto load_idx = [&](int b) {
         const uint32_t j0 = (uint32_t)b * RB_BWD + lane, j1 = j0 + 32;
@@ -569,11 +607,6 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
     auto issue = [&](int b) {
         const uint32_t s = seq + (uint32_t)(nb - 1 - b);
         uint64_t* bar = &s_bar[s & 1];
-#if GSB_GATHER_TMA
-        if (lane == 0) mbar_expect_tx(bar, min((uint32_t)RB_BWD, used - (uint32_t)b * RB_BWD) * 48u);
-        if (ia != 0xffffffffu) bulk_g2s(&s_rec[s & 1][lane * 3], rec + (size_t)ia * 3, 48u, bar);
-        if (ib != 0xffffffffu) bulk_g2s(&s_rec[s & 1][(lane + 32) * 3], rec + (size_t)ib * 3, 48u, bar);
-#else
         if (ia != 0xffffffffu) {
             float4* dst = &s_rec[s & 1][lane * 3];
             const float4* src = rec + (size_t)ia * 3;
@@ -585,7 +618,6 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
             cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
         }
         cp_async_mbar_arrive_noinc(bar);   // fires when this lane's copies have landed (immediately if it has none)
-#endif
     };
     load_idx(nb - 1);
     issue(nb - 1);

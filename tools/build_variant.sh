@@ -8,7 +8,7 @@ out=build_variants/$name; mkdir -p $out
 csrc=gaussiansplattingmlx_b200/csrc
 common="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr $defs"
 for f in project adam densify; do nvcc $common --fmad=false -c $csrc/$f.cu -o $out/$f.o & done
-for f in binning tilelists raster loss api; do nvcc $common -c $csrc/$f.cu -o $out/$f.o & done
+for f in binning tilelists raster loss api project_bwd; do nvcc $common -c $csrc/$f.cu -o $out/$f.o & done
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o build_variants/$name.so $out/*.o
 rm -rf $out
