@@ -75,7 +75,10 @@ cudaError_t launch_count_tiles(cudaStream_t st, int N, const ViewParams& vp, con
 // single pass, decoupled look-back; 2048 items per CTA; optional gather through a permutation
 // ------------------------------------------------------------------------------------------------
 constexpr int SC_THREADS = 256;
-constexpr int SC_IPT = 8;
+#ifndef GSB_SC_IPT
+#define GSB_SC_IPT 8
+#endif
+constexpr int SC_IPT = GSB_SC_IPT;
 constexpr int SC_TILE = SC_THREADS * SC_IPT;
 constexpr uint64_t SC_FLAG_LOCAL = 1ull << 62;
 constexpr uint64_t SC_FLAG_INCL = 2ull << 62;
@@ -318,7 +321,10 @@ constexpr int OS_IPT = GSB_OS_IPT;
 constexpr int OS_TILE = OS_THREADS * OS_IPT;  // 4096 pairs per CTA
 constexpr int OS_RADIX = 256;
 constexpr int OS_MAX_PASSES = 8;
-constexpr int OS_LB = 8;           // look-back: predecessors fetched per round trip
+#ifndef GSB_OS_LB
+#define GSB_OS_LB 8
+#endif
+constexpr int OS_LB = GSB_OS_LB;   // look-back: predecessors fetched per round trip
 constexpr uint32_t OS_FLAG_LOCAL = 1u << 30;
 constexpr uint32_t OS_FLAG_INCL = 2u << 30;
 constexpr uint32_t OS_VALUE_MASK = (1u << 30) - 1;
