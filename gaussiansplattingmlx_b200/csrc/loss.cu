@@ -18,6 +18,13 @@
 
 namespace gsb {
 
+__device__ __forceinline__ f32x2 lds64_pair(uint32_t addr)
+{
+    f32x2 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v.v) : "r"(addr));
+    return v;
+}
+
 constexpr int SPAD = 5;           // window radius (K/2)
 constexpr int SK = 11;
 constexpr float SSIM_C1 = 0.0001f, SSIM_C2 = 0.0009f;
@@ -92,23 +99,38 @@ struct RowStager {
     const float* img[NIMG];
     const float* cimg[2];
     int H, RW, e0, halo, nload, t, r0;
+    // column validity and element offsets are row-invariant: set once (begin), advanced by one image row per fetch -
+    // recomputing r * RW + e with its 64-bit selects cost ~100 of the ~260 instructions of a row
+    bool colok[2], cok_col;
+    long long off[2], coff;
+    __device__ __forceinline__ void begin(int r)
+    {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = t + u * SW;
+            const int ee = e0 - halo + i;
+            colok[u] = i < nload && ee >= 0 && ee < RW;
+            off[u] = (long long)r * RW + ee;
+        }
+        cok_col = e0 + t < RW;
+        coff = (long long)(r - SPAD) * RW + e0 + t;
+    }
+    // rows must be fetched in order: begin(r), fetch(r), fetch(r + 1), ...
     __device__ __forceinline__ void fetch(int r)
     {
         const bool row_ok = r >= 0 && r < H;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const int i = t + u * SW;
-            const int ee = e0 - halo + i;
-            const bool ok = row_ok && i < nload && ee >= 0 && ee < RW;
-            const size_t si = ok ? (size_t)r * RW + ee : 0;
+            const bool ok = row_ok && colok[u];
 #pragma unroll
-            for (int m = 0; m < NIMG; ++m) pre[m][u] = ok ? __ldg(img[m] + si) : 0.f;
+            for (int m = 0; m < NIMG; ++m) pre[m][u] = ok ? __ldg(img[m] + off[u]) : 0.f;
+            off[u] += RW;
         }
         const int ro = r - SPAD;
-        const bool cok = ro >= r0 && ro < H && e0 + t < RW;
-        const size_t ci = cok ? (size_t)ro * RW + e0 + t : 0;
-        ctr_next[0] = cok ? __ldg(cimg[0] + ci) : 0.f;
-        ctr_next[1] = cok ? __ldg(cimg[1] + ci) : 0.f;
+        const bool cok = ro >= r0 && ro < H && cok_col;
+        ctr_next[0] = cok ? __ldg(cimg[0] + coff) : 0.f;
+        ctr_next[1] = cok ? __ldg(cimg[1] + coff) : 0.f;
+        coff += RW;
     }
     __device__ __forceinline__ void store(float (*row)[SW + 2 * SHALO])
     {
@@ -118,6 +140,37 @@ struct RowStager {
             if (i < nload) {
 #pragma unroll
                 for (int m = 0; m < NIMG; ++m) row[m][i] = pre[m][u];
+            }
+        }
+        ctr[0] = ctr_next[0];
+        ctr[1] = ctr_next[1];
+    }
+    // Training forward (NIMG == 2): every staged element is stored ONCE as two packed pairs - (a, b) and the products
+    // (a^2 + b^2, a b) - so that a horizontal tap is two 64-bit shared loads feeding two FFMA2 (the products were
+    // recomputed by each of the 11 threads whose window covers the element: 8 instructions per tap instead of 4)
+    __device__ __forceinline__ void store_pairs(float2* ab, float2* pp)
+    {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = t + u * SW;
+            if (i < nload) {
+                const float a = pre[0][u], b = pre[1][u];
+                ab[i] = make_float2(a, b);
+                pp[i] = make_float2(fmaf(b, b, a * a), a * b);
+            }
+        }
+        ctr[0] = ctr_next[0];
+        ctr[1] = ctr_next[1];
+    }
+    // Backward (NIMG == 3): maps A and B as one packed pair, C on its own
+    __device__ __forceinline__ void store_ab_c(float2* ab, float* cc)
+    {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = t + u * SW;
+            if (i < nload) {
+                ab[i] = make_float2(pre[0][u], pre[1][u]);
+                cc[i] = pre[2][u];
             }
         }
         ctr[0] = ctr_next[0];
@@ -133,7 +186,9 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int Crt, const fl
                                                  float* __restrict__ o2, float* __restrict__ o3, float* __restrict__ o4,
                                                  float* __restrict__ o5, double* __restrict__ partial, int srows)
 {
-    __shared__ float s_row[4][SW + 2 * SHALO];   // [parity][image]
+    __shared__ __align__(16) float s_row[MODE == 0 ? 4 : 1][SW + 2 * SHALO];   // MODE 0: [parity][image]
+    __shared__ __align__(16) float2 s_ab[MODE == 1 ? 2 : 1][SW + 2 * SHALO];   // MODE 1: [parity] (a, b)
+    __shared__ __align__(16) float2 s_pp[MODE == 1 ? 2 : 1][SW + 2 * SHALO];   //         [parity] (a^2 + b^2, a b)
     __shared__ double s_red[2][SW / 32];
     const int C = CT ? CT : Crt;
     const int RW = W * C;                          // floats per image row
@@ -161,16 +216,21 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int Crt, const fl
     }
 
     const int rbeg = r0 - SPAD, rend = r1 + SPAD;   // input rows [rbeg, rend)
+    long long oidx = (long long)(rbeg - SPAD) * RW + e;   // element index of output row r - 5, advanced by one row per iteration
+    st.begin(rbeg);
     st.fetch(rbeg);
     for (int rb = rbeg; rb < rend; rb += SK) {
 #pragma unroll
         for (int ph = 0; ph < SK; ++ph) {
             const int r = rb + ph;
             if (r < rend) {   // uniform across the CTA
-                float (*row)[SW + 2 * SHALO] = reinterpret_cast<float (*)[SW + 2 * SHALO]>(&s_row[((r - rbeg) & 1) * 2][0]);
-                st.store(row);
+                const int par = (r - rbeg) & 1;
+                float (*row)[SW + 2 * SHALO] = reinterpret_cast<float (*)[SW + 2 * SHALO]>(&s_row[MODE == 0 ? par * 2 : 0][0]);
+                if (MODE == 0) st.store(row);
+                else st.store_pairs(&s_ab[par][0], &s_pp[par][0]);
                 __syncthreads();   // the only barrier per row: the two row buffers alternate
                 if (r + 1 < rend) st.fetch(r + 1);
+                const uint32_t ab_addr = smem_u32(&s_ab[MODE == 1 ? par : 0][t]), pp_addr = smem_u32(&s_pp[MODE == 1 ? par : 0][t]);
                 // ---- horizontal 11 taps of input row r
                 float h[NQ];
                 f32x2 hp[NP];
@@ -181,18 +241,17 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int Crt, const fl
 #pragma unroll
                 for (int k = 0; k < SK; ++k) {
                     const float w = win.g[k];
-                    const float a = row[0][t + k * C], b = row[1][t + k * C];
                     if (MODE == 0) {
+                        const float a = row[0][t + k * C], b = row[1][t + k * C];
                         h[0] = fmaf(w, a, h[0]);
                         h[1] = fmaf(w, b, h[1]);
                         h[2] = fmaf(w, a * a, h[2]);
                         h[3] = fmaf(w, b * b, h[3]);
                         h[4] = fmaf(w, a * b, h[4]);
                     } else {
-                        const f32x2 wb = f2_bc(w), ab = f2_make(a, b);
-                        hp[0] = f2_fma(wb, ab, hp[0]);                            // (mu1, mu2)
-                        const f32x2 pr = f2_mul(ab, f2_bc(a));                     // (a*a, a*b)
-                        hp[1] = f2_fma(wb, f2_make(fmaf(b, b, f2_lo(pr)), f2_hi(pr)), hp[1]);   // (E[a^2 + b^2], E[ab])
+                        const f32x2 wb = f2_bc(w);
+                        hp[0] = f2_fma(wb, lds64_pair(ab_addr + (uint32_t)(k * C) * 8u), hp[0]);   // (mu1, mu2)
+                        hp[1] = f2_fma(wb, lds64_pair(pp_addr + (uint32_t)(k * C) * 8u), hp[1]);   // (E[a^2 + b^2], E[ab])
                     }
                 }
                 // ---- vertical: input row r feeds output rows r-5 .. r+5; output ro lives in slot (ro - rbeg) % 11
@@ -220,7 +279,7 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int Crt, const fl
                     const float e12 = MODE == 0 ? acc[oslot][MODE == 0 ? 4 : 0] : f2_hi(accp[oslot][NP - 1]);
                     // (MODE 1: e11 carries E[a^2 + b^2], e22 = 0: ssim_point only uses their sum)
                     const SsimPoint sp = ssim_point(m1, m2, e11, e22, e12);
-                    const size_t idx = (size_t)ro * RW + e;
+                    const long long idx = oidx;
                     if (MODE == 0) {
                         o0[idx] = sp.ssim;
                         if (o1) o1[idx] = m1;
@@ -240,6 +299,7 @@ __global__ void __launch_bounds__(SW) k_ssim_fwd(int H, int W, int Crt, const fl
                 for (int q = 0; q < (MODE == 0 ? NQ : 1); ++q) acc[oslot][q] = 0.f;
 #pragma unroll
                 for (int q = 0; q < NP; ++q) accp[oslot][q] = f2_bc(0.f);
+                oidx += RW;
             }
         }
     }
@@ -274,7 +334,8 @@ __global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int Crt, const fl
                                                  const __grid_constant__ SsimWindow win, float l1_scale,
                                                  float* __restrict__ grad1, int srows)
 {
-    __shared__ float s_row[6][SW + 2 * SHALO];   // [parity][map]
+    __shared__ __align__(16) float2 s_ab[2][SW + 2 * SHALO];   // [parity] maps (A, B) as one packed pair
+    __shared__ __align__(16) float s_c[2][SW + 2 * SHALO];     // [parity] map C
     const int C = CT ? CT : Crt;
     const int RW = W * C;
     const int e0 = blockIdx.x * SW;
@@ -291,24 +352,27 @@ __global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int Crt, const fl
     for (int j = 0; j < SK; ++j) { accp[j] = f2_bc(0.f); acc2[j] = 0.f; }
 
     const int rbeg = r0 - SPAD, rend = r1 + SPAD;
+    long long oidx = (long long)(rbeg - SPAD) * RW + e;
+    st.begin(rbeg);
     st.fetch(rbeg);
     for (int rb = rbeg; rb < rend; rb += SK) {
 #pragma unroll
         for (int ph = 0; ph < SK; ++ph) {
             const int r = rb + ph;
             if (r < rend) {
-                float (*row)[SW + 2 * SHALO] = reinterpret_cast<float (*)[SW + 2 * SHALO]>(&s_row[((r - rbeg) & 1) * 3][0]);
-                st.store(row);
+                const int par = (r - rbeg) & 1;
+                st.store_ab_c(&s_ab[par][0], &s_c[par][0]);
                 __syncthreads();
                 if (r + 1 < rend) st.fetch(r + 1);
                 f32x2 hp = f2_bc(0.f);
                 float h2 = 0.f;
+                const uint32_t ab_addr = smem_u32(&s_ab[par][t]);
 #pragma unroll
                 for (int k = 0; k < SK; ++k) {
                     const float w = win.g[k];
-                    const int off = t + (2 * SPAD - k) * C;
-                    hp = f2_fma(f2_bc(w), f2_make(row[0][off], row[1][off]), hp);
-                    h2 = fmaf(w, row[2][off], h2);
+                    const int off = (2 * SPAD - k) * C;
+                    hp = f2_fma(f2_bc(w), lds64_pair(ab_addr + (uint32_t)off * 8u), hp);
+                    h2 = fmaf(w, s_c[par][t + off], h2);
                 }
                 // transposed vertical pass: output row ro receives centre row rc = ro + 5 - k with weight g[k];
                 // centre row r feeds ro = r + d - 5 with k = r - ro + 5 ... flipped: k = d
@@ -322,7 +386,7 @@ __global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int Crt, const fl
                 const int ro = r - SPAD;
                 const int oslot = (ph + SK - SPAD) % SK;
                 if (ro >= r0 && e < RW) {
-                    const size_t idx = (size_t)ro * RW + e;
+                    const long long idx = oidx;
                     const float v1 = st.ctr[0], v2 = st.ctr[1];
                     float g = f2_lo(accp[oslot]) + 2.0f * v1 * f2_hi(accp[oslot]) + v2 * acc2[oslot];
                     if (l1_scale != 0.0f) {
@@ -332,6 +396,7 @@ __global__ void __launch_bounds__(SW) k_ssim_bwd(int H, int W, int Crt, const fl
                     grad1[idx] = g;
                 }
                 accp[oslot] = f2_bc(0.f); acc2[oslot] = 0.f;
+                oidx += RW;
             }
         }
     }
