@@ -162,7 +162,10 @@ struct Ctx {
     gsb::PeerSync* peer_sync[gsb::GSB_MAX_PEERS] = {};
     uint32_t peer_step_id = 0;
     uint32_t peer_wait_step = 0;        // != 0: the next batch must first wait for this step's "parameters written" flags
-    int peer_wait_chunks = 0;
+    int peer_wait_chunks = 0;           // flag rows of that step: chunks, or 2 x chunks (geometry rows, then SH rows) when phased
+    bool peer_wait_phased = false;
+    int peer_phased = 1;                // exchange the geometry tensors first, the SH tensors behind the next step's binning
+    cudaEvent_t ev_sh = nullptr;        // the SH rows of the previous step have been announced (recorded on the tail stream)
     int peer_chunks = 2;
     int peer_blocks = 0, mc_blocks = 0;   // CTAs of the exchange kernels (0 = default), gsb_trainer_peers_tune
     cudaEvent_t ev_chunk[gsb::GSB_MAX_CHUNKS] = {};
@@ -612,6 +615,7 @@ static void destroy_ctx(Ctx* c)
     if (c->t_sync) cudaFree(c->t_sync);
     if (c->h_peer_error) cudaFreeHost(c->h_peer_error);
     for (cudaEvent_t& e : c->ev_chunk) if (e) cudaEventDestroy(e);
+    if (c->ev_sh) cudaEventDestroy(c->ev_sh);
     for (int i = 0; i < 2; ++i) { dev_free(c->t_slab[i]); dev_free(c->t_accum_slab[i]); }
     if (c->h_loss) cudaFreeHost(c->h_loss);
     for (auto& e : c->ev_pool) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
@@ -1084,16 +1088,27 @@ struct RawParams {
 };
 
 // projection (+ fused activations) and binning of one view into set v, enqueued on st
+// color_after != nullptr: the projection runs without the SH colour (geometry only), and the colour kernel follows the
+// binning once that event has fired (data-parallel step: the SH parameters of the previous exchange arrive last)
 static int enqueue_front(Ctx* c, Ctx::ViewBufs& v, cudaStream_t st, int32_t N, const RawParams& p, const gsb::ViewParams& vp,
-                         float* radii, uint8_t* visibility)
+                         float* radii, uint8_t* visibility, cudaEvent_t color_after = nullptr)
 {
     {
         gsb::StageTimer t(c, GSB_STAGE_PROJECT_FWD, st);
         GSB_CUDA_CHECK(c, gsb::launch_project_fused_fwd(st, N, vp, p.xyz, p.f_dc, p.f_rest, p.scales_log, p.rot_raw, p.op_logit, v.rec,
-                                                        v.tile_rects, v.touched, v.dkeys[0], radii, visibility));
+                                                        v.tile_rects, v.touched, v.dkeys[0], radii, visibility, color_after ? 1 : 3));
         c->stats.kernel_launches += N > 0;
     }
-    return gsb::enqueue_binning(c, v, st, N, vp, v.rec + 10, gsb::REC_FLOATS);
+    int rc = gsb::enqueue_binning(c, v, st, N, vp, v.rec + 10, gsb::REC_FLOATS);
+    if (rc != GSB_OK || !color_after) return rc;
+    GSB_CUDA_CHECK(c, cudaStreamWaitEvent(st, color_after, 0));
+    {
+        gsb::StageTimer t(c, GSB_STAGE_PROJECT_FWD, st);
+        GSB_CUDA_CHECK(c, gsb::launch_project_fused_fwd(st, N, vp, p.xyz, p.f_dc, p.f_rest, p.scales_log, p.rot_raw, p.op_logit, v.rec,
+                                                        v.tile_rects, v.touched, v.dkeys[0], nullptr, nullptr, 2));
+        c->stats.kernel_launches += N > 0;
+    }
+    return GSB_OK;
 }
 
 // K9 on the work stream from set v; marks the forward of this view as the saved one
@@ -1445,6 +1460,23 @@ static int trainer_accumulate_impl(Ctx* c, int32_t B, const gsb_camera* host_cam
     // the previous step may have ended without a barrier (gsb_trainer_step_peers): before this replica reads its parameters
     // or overwrites its gradients, every owner must have announced "my stores into your replica are done" - which also
     // means it no longer reads this replica's gradients
+    cudaEvent_t sh_event = nullptr;
+    if (sig && c->peer_wait_step && c->peer_wait_phased && c->t_sync && B > 0) {
+        // Phased exchange of the previous step: its geometry rows gate this batch (work stream, the fronts fork from it),
+        // its SH rows only gate the colour kernels (waited for on the tail stream, idle at this point) - the binning of
+        // the first view runs while the SH parameters are still crossing the links.  The SH rows also tell that every
+        // owner is done with this replica's gradients: the first projection backward that overwrites them comes after a
+        // rasteriser, i.e. after a colour kernel.
+        const int rows = c->peer_wait_chunks / 2;
+        GSB_CUDA_CHECK(c, gsb::launch_peer_wait(c->stream, &c->t_sync->params_ready[0][0], rows, c->peer_world, gsb::GSB_MAX_PEERS,
+                                                c->peer_wait_step, &c->t_sync->error));
+        GSB_CUDA_CHECK(c, gsb::launch_peer_wait(c->tail_stream, &c->t_sync->params_ready[rows][0], rows, c->peer_world, gsb::GSB_MAX_PEERS,
+                                                c->peer_wait_step, &c->t_sync->error));
+        GSB_CUDA_CHECK(c, cudaEventRecord(c->ev_sh, c->tail_stream));
+        c->stats.kernel_launches += 2;
+        c->peer_wait_step = 0;
+        sh_event = c->ev_sh;
+    }
     GSB_CUDA_CHECK(c, gsb::drain_peer_step(c));
     if (host_loss) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->loss_accum, 0, sizeof(float), c->stream));
     if (zero_grads && B == 0) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_g[0], 0, c->t_floats * 4, c->stream));
@@ -1491,7 +1523,7 @@ static int trainer_accumulate_impl(Ctx* c, int32_t B, const gsb_camera* host_cam
         const gsb::ViewParams vp = gsb::make_view(c, &host_cams[b]);
         cudaStream_t st = overlap ? c->front_streams[b % gsb::GSB_VIEW_SETS] : c->stream;
         if (overlap) GSB_CUDA_CHECK(c, cudaStreamWaitEvent(st, v.ev_back, 0));   // set free again
-        int rc = enqueue_front(c, v, st, N, rp, vp, nullptr, nullptr);
+        int rc = enqueue_front(c, v, st, N, rp, vp, nullptr, nullptr, sh_event);
         if (rc != GSB_OK) return rc;
         if (overlap) GSB_CUDA_CHECK(c, cudaEventRecord(v.ev_front, st));
         front_issued = b;
@@ -1645,7 +1677,9 @@ int gsb_trainer_peers_export(gsb_ctx* ctx, void* host_blob, int64_t blob_bytes)
         GSB_CUDA_CHECK(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_peer_error), sizeof(uint32_t)));
         *c->h_peer_error = 0;
         for (cudaEvent_t& ev : c->ev_chunk) GSB_CUDA_CHECK(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        GSB_CUDA_CHECK(c, cudaEventCreateWithFlags(&c->ev_sh, cudaEventDisableTiming));
         if (const char* env = getenv("GSB_PEER_CHUNKS")) c->peer_chunks = std::max(1, std::min(gsb::GSB_MAX_CHUNKS, atoi(env)));
+        if (const char* env = getenv("GSB_PEER_PHASED")) c->peer_phased = atoi(env);
     }
     GSB_CUDA_CHECK(c, cudaIpcGetMemHandle(&e.block, c->t_block));
     GSB_CUDA_CHECK(c, cudaIpcGetMemHandle(&e.accum, c->t_accum));
@@ -1713,8 +1747,10 @@ int gsb_trainer_peers_close(gsb_ctx* ctx)
 
 // Owned slice of the Gaussians [n0, n1) for replica R of W: equal parts on multiples of 4 Gaussians (every tensor slice then
 // starts 16-byte aligned).  Fills the per-launch descriptors of the exchange kernels (adam.cu).
+// tensor_mask: bit k = tensor k of (xyz, f_dc, f_rest, scales, rotation, opacity) takes part; D1 goes with xyz (bit 0)
+constexpr int TENSORS_ALL = 0x3f, TENSORS_GEOMETRY = 0x39, TENSORS_SH = 0x06;
 static void fill_exchange(Ctx* c, int W, int R, long long n0, long long n1, int iteration, int total_iterations, const float* param_base,
-                          gsb::AdamTensors& t, gsb::AdamPeers& pr)
+                          gsb::AdamTensors& t, gsb::AdamPeers& pr, int tensor_mask = TENSORS_ALL)
 {
     const long long n = n1 - n0;
     const long long per = ((n + W - 1) / W + 3) & ~3LL;
@@ -1724,21 +1760,23 @@ static void fill_exchange(Ctx* c, int W, int R, long long n0, long long n1, int 
     const long long row[6] = {3, 3, (long long)(K - 1) * 3, 3, 4, 1};
     for (int k = 0; k < 6; ++k) {
         t.p[k] = c->t_p[k]; t.g[k] = c->t_g[k]; t.m[k] = c->t_m[k]; t.v[k] = c->t_v[k];
-        t.count[k] = (g1 - g0) * row[k];
+        t.count[k] = ((tensor_mask >> k) & 1) ? (g1 - g0) * row[k] : 0;
         pr.first[k] = g0 * row[k];
         pr.tensor_off[k] = (long long)(c->t_p[k] - param_base);
     }
     pr.g0 = g0; pr.g1 = g1; pr.world = W; pr.rank = R;
     pr.accum_all = 0;
+    const bool d1 = (tensor_mask & 1) != 0;
+    if (!d1) pr.g1 = pr.g0;   // no D1 in this launch
     if (c->peer_world == W && c->peer_accum[R] == c->t_accum) {   // the replicas' slabs are peer-mapped
         for (int r = 0; r < W; ++r) {
             pr.params[r] = c->peer_block[r];
             pr.grads[r] = c->peer_block[r] + c->t_floats;
-            pr.accum[r] = c->peer_accum[r];
+            pr.accum[r] = d1 ? c->peer_accum[r] : nullptr;
         }
         pr.accum_all = 1;
     } else {
-        pr.accum[R] = c->t_accum;
+        pr.accum[R] = d1 ? c->t_accum : nullptr;
     }
 }
 
@@ -1792,29 +1830,38 @@ int gsb_trainer_step_peers(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
     if (rc != GSB_OK) return rc;
     if (reset_state) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + 2 * c->t_floats, 0, 2 * c->t_floats * sizeof(float), c->stream));
     const float* param_base = c->sym ? c->sym_params : c->t_block;
-    for (int k = 0; k < sig.chunks; ++k) {
-        GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_chunk[k], 0));   // my own chunk k is done (other stream)
-        gsb::AdamTensors t{};
-        gsb::AdamPeers pr{};
-        fill_exchange(c, W, R, sig.begin[k], sig.begin[k + 1], iteration, total_iterations, param_base, t, pr);
-        gsb::PeerStepSync sy;
-        sy.wait_flags = &c->t_sync->grads_ready[k][0];
-        sy.done = &c->t_sync->done[k];
-        for (int r = 0; r < W; ++r) sy.announce[r] = &c->peer_sync[r]->params_ready[k][R];
-        sy.error = &c->t_sync->error;
-        sy.step = step;
-        gsb::StageTimer tm(c, GSB_STAGE_ADAM);
-        int launches = 0;
-        if (c->sym)
-            GSB_CUDA_CHECK(c, gsb::launch_adam_multicast(c->stream, t, pr, c->mc_grads, c->mc_params, c->cfg.adam_beta1, c->cfg.adam_beta2,
-                                                         c->cfg.adam_eps, 1.0f, c->tN, &sy, c->mc_blocks, &launches));
-        else
-            GSB_CUDA_CHECK(c, gsb::launch_adam_peers(c->stream, t, pr, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, &sy, c->peer_blocks, &launches));
-        c->stats.kernel_launches += launches;
+    // Phased: the geometry tensors (19 % of the bytes) of every chunk first, then the SH tensors - the next step's
+    // projection + binning only need the former (enqueue_front), so most of the exchange hides behind them.
+    const bool phased = c->peer_phased != 0 && 2 * sig.chunks <= gsb::GSB_MAX_CHUNKS;
+    for (int phase = 0; phase < (phased ? 2 : 1); ++phase) {
+        for (int k = 0; k < sig.chunks; ++k) {
+            GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_chunk[k], 0));   // my own chunk k is done (other stream)
+            gsb::AdamTensors t{};
+            gsb::AdamPeers pr{};
+            fill_exchange(c, W, R, sig.begin[k], sig.begin[k + 1], iteration, total_iterations, param_base, t, pr,
+                          phased ? (phase == 0 ? TENSORS_GEOMETRY : TENSORS_SH) : TENSORS_ALL);
+            const int row = phase * sig.chunks + k;
+            gsb::PeerStepSync sy;
+            sy.wait_flags = &c->t_sync->grads_ready[k][0];
+            sy.done = &c->t_sync->done[row];
+            for (int r = 0; r < W; ++r) sy.announce[r] = &c->peer_sync[r]->params_ready[row][R];
+            sy.error = &c->t_sync->error;
+            sy.step = step;
+            gsb::StageTimer tm(c, GSB_STAGE_ADAM);
+            int launches = 0;
+            if (c->sym)
+                GSB_CUDA_CHECK(c, gsb::launch_adam_multicast(c->stream, t, pr, c->mc_grads, c->mc_params, c->cfg.adam_beta1, c->cfg.adam_beta2,
+                                                             c->cfg.adam_eps, 1.0f, c->tN, &sy, c->mc_blocks, &launches));
+            else
+                GSB_CUDA_CHECK(c, gsb::launch_adam_peers(c->stream, t, pr, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, &sy,
+                                                         c->peer_blocks, &launches));
+            c->stats.kernel_launches += launches;
+        }
     }
     c->t_accum_steps += 1;
     c->peer_wait_step = step;        // the next batch (fused or not) starts by waiting for every replica's stores of this step
-    c->peer_wait_chunks = sig.chunks;
+    c->peer_wait_chunks = phased ? 2 * sig.chunks : sig.chunks;
+    c->peer_wait_phased = phased;
     return GSB_OK;
 }
 
@@ -1825,6 +1872,7 @@ int gsb_trainer_peers_tune(gsb_ctx* ctx, int32_t chunks, int32_t peer_blocks, in
     GSB_CUDA_CHECK(c, gsb::drain_peer_step(c));
     gsb::sync_all_streams(c);
     if (chunks > 0) c->peer_chunks = chunks;
+    if (const char* e = getenv("GSB_PEER_PHASED")) c->peer_phased = atoi(e);   // 0: one exchange kernel per chunk for all six tensors
     c->peer_blocks = peer_blocks;
     c->mc_blocks = multicast_blocks;
     return GSB_OK;

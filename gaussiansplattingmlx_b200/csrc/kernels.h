@@ -37,7 +37,7 @@ cudaError_t launch_project_bwd_api(cudaStream_t st, int N, const ViewParams& vp,
 cudaError_t launch_project_fused_fwd(cudaStream_t st, int N, const ViewParams& vp, const float* xyz, const float* f_dc,
                                      const float* f_rest, const float* scales_log, const float* rot_raw,
                                      const float* op_logit, float* rec, uint2* tile_rects, uint32_t* touched,
-                                     uint32_t* depth_keys, float* radii_out, uint8_t* vis_out);
+                                     uint32_t* depth_keys, float* radii_out, uint8_t* vis_out, int part = 3);   // 1 geometry, 2 colour, 3 both
 size_t project_fused_smem_bytes(int K);
 cudaError_t launch_project_fused_bwd(cudaStream_t st, int N, const ViewParams& vp, const float* xyz, const float* f_dc,
                                      const float* f_rest, const float* scales_log, const float* rot_raw,

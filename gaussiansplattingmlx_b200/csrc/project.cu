@@ -66,7 +66,11 @@ __global__ void __launch_bounds__(128) k_project_fwd_api(int N, const float* __r
 // ------------------------------------------------------------------------------------------------
 // fused training-path kernels (staging helpers: project_stage.cuh)
 // ------------------------------------------------------------------------------------------------
-template <int MAXK>
+// PART 3: the whole forward.  PART 1: geometry only (positions, scales, rotations, opacities in; record with a zero colour,
+// tile rect, tiles-touched, depth key out).  PART 2: colour only (positions + SH coefficients in; the three colour floats of
+// the record out).  The data-parallel step (api.cu gsb_trainer_step_peers) runs 1, the binning, then 2: the SH parameters
+// - 81 % of the bytes of the previous step's parameter exchange - are only needed by 2.
+template <int MAXK, int PART>
 __global__ void __launch_bounds__(PB) k_project_fused_fwd(int N, const float* __restrict__ xyz,
                                                           const float* __restrict__ f_dc, const float* __restrict__ f_rest,
                                                           const float* __restrict__ scales_log,
@@ -84,9 +88,22 @@ __global__ void __launch_bounds__(PB) k_project_fused_fwd(int N, const float* __
     const int base = blockIdx.x * PB;
     const int count = min(PB, N - base);
     const bool tma = tma_ok && count == PB;
-    stage_inputs(sm, L, base, count, K, tma, xyz, f_dc, f_rest, scales_log, rot_raw, op_logit, nullptr, 0);
+    stage_inputs(sm, L, base, count, K, tma, xyz, f_dc, f_rest, scales_log, rot_raw, op_logit, nullptr, 0,
+                 STAGE_XYZ | ((PART & 1) ? STAGE_GEO : 0) | ((PART & 2) ? STAGE_SH : 0));
 
     const int t = threadIdx.x;
+    if (PART == 2) {
+        if (t < count) {
+            const float* dc = sm + L.fdc + t * 3;
+            const float* rest = sm + L.frest + t * (K - 1) * 3;
+            float col[3];
+            project_color<MAXK>(sm[L.xyz + t * 3], sm[L.xyz + t * 3 + 1], sm[L.xyz + t * 3 + 2],
+                                [&](int k, int c) { return k == 0 ? dc[c] : rest[(k - 1) * 3 + c]; }, vp, col);
+            float* r = rec + (size_t)(base + t) * REC_FLOATS;   // record floats 6, 7, 8 = r, g, b (common.cuh)
+            r[6] = col[0]; r[7] = col[1]; r[8] = col[2];
+        }
+        return;
+    }
     if (t < count) {
         const int p = base + t;
         float s0 = gsb_expf(sm[L.scales + t * 3]), s1 = gsb_expf(sm[L.scales + t * 3 + 1]), s2 = gsb_expf(sm[L.scales + t * 3 + 2]);
@@ -97,8 +114,9 @@ __global__ void __launch_bounds__(PB) k_project_fused_fwd(int N, const float* __
         const float* dc = sm + L.fdc + t * 3;
         const float* rest = sm + L.frest + t * (K - 1) * 3;
         ProjOut o;
-        project_forward<MAXK>(sm[L.xyz + t * 3], sm[L.xyz + t * 3 + 1], sm[L.xyz + t * 3 + 2], s0, s1, s2, rw, rx, ry, rz,
-                              [&](int k, int c) { return k == 0 ? dc[c] : rest[(k - 1) * 3 + c]; }, vp, o);
+        o.color[0] = o.color[1] = o.color[2] = 0.0f;
+        project_forward<MAXK, PART>(sm[L.xyz + t * 3], sm[L.xyz + t * 3 + 1], sm[L.xyz + t * 3 + 2], s0, s1, s2, rw, rx, ry, rz,
+                                    [&](int k, int c) { return k == 0 ? dc[c] : rest[(k - 1) * 3 + c]; }, vp, o);
         float4* r4 = reinterpret_cast<float4*>(sm + L.rec + t * REC_FLOATS);
         make_raster_record(o.sx, o.sy, o.conic[0], o.conic[1], o.conic[2], o.conic[3], o.color[0], o.color[1], o.color[2],
                            opac, o.depth, (uint32_t)p, r4);
@@ -155,26 +173,36 @@ cudaError_t launch_project_fwd_api(cudaStream_t st, int N, const ViewParams& vp,
 
 size_t project_fused_smem_bytes(int K) { return (size_t)fused_layout(K).total * sizeof(float); }
 
+template <int MAXK, int PART>
+static cudaError_t launch_fused_fwd_t(cudaStream_t st, int N, const ViewParams& vp, const float* xyz, const float* f_dc, const float* f_rest,
+                                      const float* scales_log, const float* rot_raw, const float* op_logit, int tma_ok, size_t smem, float* rec,
+                                      uint2* tile_rects, uint32_t* touched, uint32_t* depth_keys, float* radii_out, uint8_t* vis_out)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_project_fused_fwd<MAXK, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_project_fused_fwd<MAXK, PART><<<cdiv(N, PB), PB, smem, st>>>(N, xyz, f_dc, f_rest, scales_log, rot_raw, op_logit, vp, tma_ok, rec, tile_rects,
+                                                                      touched, depth_keys, radii_out, vis_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_project_fused_fwd(cudaStream_t st, int N, const ViewParams& vp, const float* xyz, const float* f_dc,
                                      const float* f_rest, const float* scales_log, const float* rot_raw,
                                      const float* op_logit, float* rec, uint2* tile_rects, uint32_t* touched,
-                                     uint32_t* depth_keys, float* radii_out, uint8_t* vis_out)
+                                     uint32_t* depth_keys, float* radii_out, uint8_t* vis_out, int part)
 {
     if (N <= 0) return cudaSuccess;
     int tma_ok = aligned16(xyz) && aligned16(f_dc) && aligned16(f_rest) && aligned16(scales_log) && aligned16(rot_raw) &&
                  aligned16(op_logit) && aligned16(rec);
-    size_t smem = project_fused_smem_bytes(vp.K);
-    cudaError_t e;
-    if (vp.coeffCount > 16 || vp.K > 16) {
-        e = cudaFuncSetAttribute(k_project_fused_fwd<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_project_fused_fwd<25><<<cdiv(N, PB), PB, smem, st>>>(N, xyz, f_dc, f_rest, scales_log, rot_raw, op_logit, vp, tma_ok, rec, tile_rects, touched, depth_keys, radii_out, vis_out);
-    } else {
-        e = cudaFuncSetAttribute(k_project_fused_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_project_fused_fwd<16><<<cdiv(N, PB), PB, smem, st>>>(N, xyz, f_dc, f_rest, scales_log, rot_raw, op_logit, vp, tma_ok, rec, tile_rects, touched, depth_keys, radii_out, vis_out);
-    }
-    return cudaGetLastError();
+    const size_t smem = project_fused_smem_bytes(vp.K);
+    const bool big = vp.coeffCount > 16 || vp.K > 16;
+#define GSB_FWD_CASE(MAXK, PART)                                                                                                             \
+    return launch_fused_fwd_t<MAXK, PART>(st, N, vp, xyz, f_dc, f_rest, scales_log, rot_raw, op_logit, tma_ok, smem, rec, tile_rects, touched, \
+                                          depth_keys, radii_out, vis_out)
+    if (part == 1) { if (big) GSB_FWD_CASE(25, 1); GSB_FWD_CASE(16, 1); }
+    if (part == 2) { if (big) GSB_FWD_CASE(25, 2); GSB_FWD_CASE(16, 2); }
+    if (big) GSB_FWD_CASE(25, 3);
+    GSB_FWD_CASE(16, 3);
+#undef GSB_FWD_CASE
 }
 
 }  // namespace gsb

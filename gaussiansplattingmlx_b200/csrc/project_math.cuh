@@ -197,8 +197,28 @@ struct ProjOut {
     float rect[4];               // minX minY maxX maxY (clamped)
 };
 
-// K1 body (kernels.slang:36-173).  shfun(k, c) returns SH coefficient (k, c).
+// SH colour of K1 (shared.slang:257-319): un-normalised direction, max(sum + 0.5, 0).  It depends on the position, the
+// camera centre and the SH coefficients only, so it can run as its own kernel (project.cu: the data-parallel step evaluates
+// it after the binning, when the SH parameters of the previous step's exchange have landed).
 template <int MAXK, class ShFun>
+__device__ __forceinline__ void project_color(float m0, float m1, float m2, ShFun sh, const ViewParams& vp, float* color)
+{
+    float dx = m0 - vp.cam[0], dy = m1 - vp.cam[1], dz = m2 - vp.cam[2];
+    float basis[MAXK];
+    sh_basis<MAXK>(dx, dy, dz, vp.degree, basis);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float acc = basis[0] * sh(0, c);
+#pragma unroll
+        for (int k = 1; k < MAXK; ++k)
+            if (k < vp.coeffCount) acc += basis[k] * sh(k, c);
+        acc += 0.5f;
+        color[c] = fmaxf(acc, 0.0f);
+    }
+}
+
+// K1 body (kernels.slang:36-173).  shfun(k, c) returns SH coefficient (k, c).  PART: bit 0 = geometry, bit 1 = colour.
+template <int MAXK, int PART = 3, class ShFun>
 __device__ __forceinline__ void project_forward(float m0, float m1, float m2, float s0, float s1, float s2, float rw,
                                                 float rx, float ry, float rz, ShFun sh, const ViewParams& vp, ProjOut& o)
 {
@@ -217,18 +237,8 @@ __device__ __forceinline__ void project_forward(float m0, float m1, float m2, fl
     o.sx = ((ndcX + 1.0f) * vp.imageW - 1.0f) * 0.5f;
     o.sy = ((ndcY + 1.0f) * vp.imageH - 1.0f) * 0.5f;
     o.depth = pv2;
-    float dx = m0 - vp.cam[0], dy = m1 - vp.cam[1], dz = m2 - vp.cam[2];
-    float basis[MAXK];
-    sh_basis<MAXK>(dx, dy, dz, vp.degree, basis);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float acc = basis[0] * sh(0, c);
-#pragma unroll
-        for (int k = 1; k < MAXK; ++k)
-            if (k < vp.coeffCount) acc += basis[k] * sh(k, c);
-        acc += 0.5f;
-        o.color[c] = fmaxf(acc, 0.0f);
-    }
+    if (PART & 2) project_color<MAXK>(m0, m1, m2, sh, vp, o.color);
+    if (!(PART & 1)) return;
     Cov3d c3;
     build_cov3d(s0, s1, s2, rw, rx, ry, rz, c3);
     Cov2d c2;
