@@ -499,6 +499,44 @@ def test_train_steps_vs_oracle(gsb, best_oracle, port):
     print(f"train steps: worst pre-Adam gradient error {worst:.2e} relative")
 
 
+@pytest.mark.parametrize("chunks,phased", [(1, 1), (2, 1), (4, 1), (2, 0)])
+def test_step_protocol_on_one_replica_matches_plain_steps(gsb, monkeypatch, chunks, phased):
+    """gsb_trainer_step_peers with a world of ONE replica (its own flags, its own slab): the whole device-side protocol -
+    flag waits, the projection split into a geometry and a colour kernel around the binning, the last view's projection
+    backward in Gaussian chunks, the exchange kernels per chunk and tensor group (geometry first, SH second), the
+    announcements - must reproduce gsb_train_step: same losses, same D1 accumulators, Adam deltas within the run-to-run
+    noise of float atomics."""
+    Context, L = gsb
+    monkeypatch.setenv("GSB_PEER_CHUNKS", str(chunks))
+    monkeypatch.setenv("GSB_PEER_PHASED", str(phased))
+    n, W, H = 5000, 96, 64
+    params = make_gaussians(n, 33, 3)
+    cams = [L.make_camera(c) for c in make_cameras(W, H, 3)]
+    tg = [torch.from_numpy(t).cuda() for t in make_targets(W, H, 3, 33)]
+    ref = Context(W, H)
+    ref.trainer_init({k: torch.from_numpy(v) for k, v in params.items()})
+    want = [ref.train_step(cams, tg, it, 100) for it in range(3)]
+    rt = ref.trainer_tensors()
+    ctx = Context(W, H)
+    ctx.trainer_init({k: torch.from_numpy(v) for k, v in params.items()})
+    ctx.trainer_peers_import(1, 0, [ctx.trainer_peers_export()])
+    got = [ctx.trainer_step_peers(cams, tg, 1.0 / 3, it, 100, want_loss=True) for it in range(3)]
+    ctx.trainer_peers_check()
+    tt = ctx.trainer_tensors()
+    for a, b in zip(got, want):
+        assert abs(a - b) < 1e-6
+    assert rel_err(tt["accum"].cpu().numpy(), rt["accum"].cpu().numpy()) < 1e-4
+    for k in params:
+        d_g = tt["params"][k].cpu().numpy() - params[k].reshape(tt["params"][k].shape)
+        d_r = rt["params"][k].cpu().numpy() - params[k].reshape(tt["params"][k].shape)
+        assert rel_err(d_g, d_r) < 5e-2, k
+    # a step without views (B = 0) in the same protocol: zero gradients, Adam still decays m / v identically everywhere
+    ctx.trainer_step_peers([], [], 1.0, 3, 100)
+    ctx.trainer_peers_check()
+    ctx.trainer_peers_close()
+    ctx.close(); ref.close()
+
+
 def test_view_pipeline_matches_serial_and_regrows(gsb):
     """The two-stream view pipeline of gsb_trainer_accumulate (front of view b+1 overlapping the back of view b)
     must give the same steps as the serial schedule, including when the pair buffers overflow mid-batch."""

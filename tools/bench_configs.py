@@ -87,6 +87,40 @@ def bench_c5(sizes=(100_000, 300_000, 1_000_000, 3_000_000, 10_000_000), reps=20
         torch.cuda.empty_cache()
 
 
+def bench_app_default(sizes=(("C2", 300_000, 800, 800, 1), ("C3", 1_000_000, 1920, 1080, 8)), steps=6):
+    """The configuration the reference APP runs (UI/TrainView.swift:160-188, Data/ColmapDataLoader.swift:495): SH degree 4
+    (K = 25 coefficients) and TILE_SIZE = W/4 x H/4 - 16 tiles per image, every one covered by many 16x16 raster blocks that
+    all walk the same (long) tile list - next to the same scene with the benchmark's 16x16 tiles.  Per-stage times from a
+    pass with the view pipeline off."""
+    for name, n, W, H, views in sizes:
+        params = make_gaussians(n, 3 if name == "C3" else 2, 4)
+        cams = make_cameras(W, H, views)
+        targets = make_targets(W, H, views, 3 if name == "C3" else 2)
+        for label, tile in (("app default: tile W/4 x H/4", (W // 4, H // 4)), ("16x16 tiles", (16, 16))):
+            ctx = Context(W, H, tile_w=tile[0], tile_h=tile[1], sh_degree=4, max_gaussians=n)
+            ctx.trainer_init({k: torch.from_numpy(v) for k, v in params.items()})
+            gc = [_lib.make_camera(c) for c in cams]
+            tg = [torch.from_numpy(t).cuda() for t in targets]
+            for it in range(3):
+                ctx.train_step(gc, tg, it, 30000, want_loss=False)
+            ms = cuda_ms(lambda i: ctx.train_step(gc, tg, 3 + i, 30000, want_loss=False), steps)
+            ctx.set_flags(_lib.GSB_FLAG_NO_OVERLAP)
+            ctx.stats_reset(); ctx.enable_stage_timing(True)
+            ms_serial = cuda_ms(lambda i: ctx.train_step(gc, tg, 3 + steps + i, 30000, want_loss=False), steps)
+            st = ctx.stats()
+            ctx.render_forward(ctx.trainer_tensors()["params"], gc[0], want_outputs=False)
+            evals = ctx.last_contrib_sum()
+            per_view = {k: round(v / (steps * views), 4) for k, v in st["stage_ms"].items() if st["stage_calls"][k] and k != "adam"}
+            per_view["adam_per_step"] = round(st["stage_ms"]["adam"] / steps, 4)
+            print(json.dumps({"config": f"{name} scene, SH degree 4 (K=25), {label}", "gaussians": n, "image": [W, H], "tile": list(tile),
+                              "tiles": ctx.num_tiles, "views_per_step": views, "ms_per_step": ms, "steps_per_s": 1e3 / ms,
+                              "ms_per_step_serialized": ms_serial, "pairs_last_view": st["pairs_last_view"], "blend_evals_view0": evals,
+                              "stage_ms_per_view": per_view}), flush=True)
+            ctx.close()
+            del ctx, tg
+            torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="C2,C4,C5")
@@ -97,5 +131,7 @@ if __name__ == "__main__":
         bench_train("C2")[0].close()
     if "C4" in sel:
         bench_c4()
+    if "APP" in sel:
+        bench_app_default()
     if "C5" in sel:
         bench_c5(tuple(n for n in (100_000, 300_000, 1_000_000, 3_000_000, 10_000_000) if n <= a.max_n))
