@@ -1523,7 +1523,11 @@ static int trainer_accumulate_impl(Ctx* c, int32_t B, const gsb_camera* host_cam
         const gsb::ViewParams vp = gsb::make_view(c, &host_cams[b]);
         cudaStream_t st = overlap ? c->front_streams[b % gsb::GSB_VIEW_SETS] : c->stream;
         if (overlap) GSB_CUDA_CHECK(c, cudaStreamWaitEvent(st, v.ev_back, 0));   // set free again
-        int rc = enqueue_front(c, v, st, N, rp, vp, nullptr, nullptr, sh_event);
+        // phased exchange: only the step's FIRST view splits its projection around the binning (its front is the one on the
+        // critical path while the SH parameters arrive); the later views' fronts run ahead of their rasterisers anyway
+        // and simply start once the SH rows have been announced
+        if (sh_event && b > 0) GSB_CUDA_CHECK(c, cudaStreamWaitEvent(st, sh_event, 0));
+        int rc = enqueue_front(c, v, st, N, rp, vp, nullptr, nullptr, b == 0 ? sh_event : nullptr);
         if (rc != GSB_OK) return rc;
         if (overlap) GSB_CUDA_CHECK(c, cudaEventRecord(v.ev_front, st));
         front_issued = b;
