@@ -92,6 +92,7 @@ struct Ctx {
     float* grad_rec = nullptr;         // [N,12] raster backward -> projection backward
     float* grad_rec2 = nullptr;        // second buffer (trainer: projection backward of view b overlaps the raster of b+1)
     cudaStream_t tail_stream = nullptr;
+    cudaStream_t xchg_stream = nullptr;   // exchange kernels of gsb_trainer_step_peers (ordered against the rest by flags and events)
     cudaEvent_t ev_rb[2] = {nullptr, nullptr};   // raster backward into gradient-record buffer i finished (work stream)
     cudaEvent_t ev_pb[2] = {nullptr, nullptr};   // projection backward out of buffer i finished (tail stream)
     uint32_t* offsets_ref = nullptr;   // [N] scan in index order (parity API: reference emission order)
@@ -306,6 +307,7 @@ static ViewParams make_view_nocam(const Ctx* c)
 static void sync_all_streams(Ctx* c)
 {
     cudaStreamSynchronize(c->stream);
+    if (c->xchg_stream) cudaStreamSynchronize(c->xchg_stream);
     for (cudaStream_t fs : c->front_streams) if (fs) cudaStreamSynchronize(fs);
     if (c->tail_stream) cudaStreamSynchronize(c->tail_stream);
 }
@@ -586,6 +588,7 @@ static void destroy_ctx(Ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (cudaStream_t fs : c->front_streams) if (fs) cudaStreamSynchronize(fs);
     if (c->tail_stream) cudaStreamSynchronize(c->tail_stream);
+    if (c->xchg_stream) cudaStreamSynchronize(c->xchg_stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     for (Ctx::ViewBufs& v : c->vb) {
         dev_free(v.rec); dev_free(v.tile_rects); dev_free(v.touched); dev_free(v.offsets); dev_free(v.d_nvalue);
@@ -625,6 +628,7 @@ static void destroy_ctx(Ctx* c)
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (cudaStream_t fs : c->front_streams) if (fs) cudaStreamDestroy(fs);
     if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
+    if (c->xchg_stream) cudaStreamDestroy(c->xchg_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -722,6 +726,7 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
     for (cudaStream_t& fs : c->front_streams) CREATE_CHECK(cudaStreamCreateWithPriority(&fs, cudaStreamNonBlocking, prio_hi));
     c->front_stream = c->front_streams[0];
     CREATE_CHECK(cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, prio_hi));
+    CREATE_CHECK(cudaStreamCreateWithPriority(&c->xchg_stream, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < 2; ++i) {
         CREATE_CHECK(cudaEventCreateWithFlags(&c->ev_rb[i], cudaEventDisableTiming));
         CREATE_CHECK(cudaEventCreateWithFlags(&c->ev_pb[i], cudaEventDisableTiming));
@@ -1832,14 +1837,19 @@ int gsb_trainer_step_peers(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
     }
     int rc = trainer_accumulate_impl(c, B, host_cams, host_targets, nullptr, nullptr, 0.0f, targets_on_host, 1, grad_scale, host_loss, &sig);
     if (rc != GSB_OK) return rc;
-    if (reset_state) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + 2 * c->t_floats, 0, 2 * c->t_floats * sizeof(float), c->stream));
+    // The exchange kernels run on their own stream: what they wait for (every replica's gradients of a chunk) and what
+    // waits for them (the next batch, through the "parameters written" flags - this replica announces to itself as well)
+    // is expressed in flags, so the work stream is free to start the next step's first front as soon as the geometry rows
+    // are in, while this replica's own SH exchange kernel is still running.
+    cudaStream_t xs = c->xchg_stream;
+    if (reset_state) GSB_CUDA_CHECK(c, cudaMemsetAsync(c->t_block + 2 * c->t_floats, 0, 2 * c->t_floats * sizeof(float), xs));
     const float* param_base = c->sym ? c->sym_params : c->t_block;
     // Phased: the geometry tensors (19 % of the bytes) of every chunk first, then the SH tensors - the next step's
     // projection + binning only need the former (enqueue_front), so most of the exchange hides behind them.
     const bool phased = c->peer_phased != 0 && 2 * sig.chunks <= gsb::GSB_MAX_CHUNKS;
     for (int phase = 0; phase < (phased ? 2 : 1); ++phase) {
         for (int k = 0; k < sig.chunks; ++k) {
-            GSB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_chunk[k], 0));   // my own chunk k is done (other stream)
+            GSB_CUDA_CHECK(c, cudaStreamWaitEvent(xs, c->ev_chunk[k], 0));   // my own chunk k is done (tail / work stream)
             gsb::AdamTensors t{};
             gsb::AdamPeers pr{};
             fill_exchange(c, W, R, sig.begin[k], sig.begin[k + 1], iteration, total_iterations, param_base, t, pr,
@@ -1851,13 +1861,13 @@ int gsb_trainer_step_peers(gsb_ctx* ctx, int32_t B, const gsb_camera* host_cams,
             for (int r = 0; r < W; ++r) sy.announce[r] = &c->peer_sync[r]->params_ready[row][R];
             sy.error = &c->t_sync->error;
             sy.step = step;
-            gsb::StageTimer tm(c, GSB_STAGE_ADAM);
+            gsb::StageTimer tm(c, GSB_STAGE_ADAM, xs);
             int launches = 0;
             if (c->sym)
-                GSB_CUDA_CHECK(c, gsb::launch_adam_multicast(c->stream, t, pr, c->mc_grads, c->mc_params, c->cfg.adam_beta1, c->cfg.adam_beta2,
+                GSB_CUDA_CHECK(c, gsb::launch_adam_multicast(xs, t, pr, c->mc_grads, c->mc_params, c->cfg.adam_beta1, c->cfg.adam_beta2,
                                                              c->cfg.adam_eps, 1.0f, c->tN, &sy, c->mc_blocks, &launches));
             else
-                GSB_CUDA_CHECK(c, gsb::launch_adam_peers(c->stream, t, pr, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, &sy,
+                GSB_CUDA_CHECK(c, gsb::launch_adam_peers(xs, t, pr, c->cfg.adam_beta1, c->cfg.adam_beta2, c->cfg.adam_eps, 1.0f, &sy,
                                                          c->peer_blocks, &launches));
             c->stats.kernel_launches += launches;
         }
