@@ -316,7 +316,7 @@ __device__ __forceinline__ void mc_st(float* mc, float v)
 
 constexpr int MC_UNROLL = 4;
 
-__global__ void __launch_bounds__(AD_THREADS) k_adam_multicast(const __grid_constant__ AdamTensors t, const __grid_constant__ AdamPeers pr,
+__global__ void __launch_bounds__(1024) k_adam_multicast(const __grid_constant__ AdamTensors t, const __grid_constant__ AdamPeers pr,
                                                                const __grid_constant__ AdamSeg seg, const __grid_constant__ PeerStepSync sy,
                                                                const float* __restrict__ mc_grads, float* __restrict__ mc_params, float b1,
                                                                float b2, float eps, float gscale, int N)
@@ -407,15 +407,19 @@ cudaError_t launch_adam_multicast(cudaStream_t st, const AdamTensors& t, const A
     const bool own_d1 = pr.accum[pr.rank] && pr.accum_all;
     const long long d1 = pr.accum[pr.rank] ? (own_d1 ? pr.g1 - pr.g0 : N) : 0;
     const long long total = std::max<long long>(seg.vec_begin[6], d1);
-    long long blocks = (std::max<long long>((total + MC_UNROLL - 1) / MC_UNROLL, 1) + AD_THREADS - 1) / AD_THREADS;
-    // one CTA per SM: measured at 8 GPUs (profiles/r2/r2e_exchange_8gpu.jsonl) 148 CTAs 0.65 ms, 296 0.66 ms, 1184 0.70 ms per
-    // step - the switch, not the SMs, sets the pace, and fewer requesters keep it streaming
-    long long cap = 148LL;
+    // Few, fat CTAs: the NVSwitch, not the SMs, sets the pace (148 x 256 threads 0.65 ms, 1184 x 256 0.70 ms per step at 8
+    // GPUs, profiles/r2/r2e_exchange_8gpu.jsonl), and every SM that hosts a CTA of this kernel has its memory pipeline full
+    // of multi-microsecond multimem requests - the projection / binning kernels of the next step that share those SMs slow
+    // down 3-4x (r2r).  32 CTAs of 1024 threads keep the same bytes in flight on 32 SMs and leave the other 116 alone.
+    static const int env_threads = getenv("GSB_MC_THREADS") ? atoi(getenv("GSB_MC_THREADS")) : 0;
+    const int threads = env_threads > 0 ? std::min(1024, (env_threads + 31) & ~31) : 1024;
+    long long blocks = (std::max<long long>((total + MC_UNROLL - 1) / MC_UNROLL, 1) + threads - 1) / threads;
+    long long cap = 32;
     if (blocks_override > 0) cap = blocks_override;   // gsb_trainer_peers_tune
     if (blocks > cap) blocks = cap;
     PeerStepSync sy{};
     if (sync) sy = *sync;
-    k_adam_multicast<<<(int)blocks, AD_THREADS, 0, st>>>(t, pr, seg, sy, mc_grads, mc_params, beta1, beta2, eps, gscale, N);
+    k_adam_multicast<<<(int)blocks, threads, 0, st>>>(t, pr, seg, sy, mc_grads, mc_params, beta1, beta2, eps, gscale, N);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
