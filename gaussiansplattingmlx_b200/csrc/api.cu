@@ -56,7 +56,6 @@ struct Ctx {
         void* scan_ws = nullptr;
         const float* depth_src = nullptr;          // depth of Gaussian g at depth_src[g * depth_src_stride]
         int depth_src_stride = 1;
-        uint32_t* sbcnt = nullptr;     // [N] superblocks touched, in DEPTH order (input of the level-1 scan)
         // level 1: (superblock id, Gaussian) pairs (capacity capL1), ping-pong for the sort
         uint32_t* keys[2] = {nullptr, nullptr};
         uint32_t* vals[2] = {nullptr, nullptr};
@@ -72,6 +71,7 @@ struct Ctx {
         void* tile_scan_ws = nullptr;
         uint32_t* tile_ranges = nullptr;  // [numTiles,2] (reference convention: (0,0) for an empty tile)
         uint32_t* tile_order = nullptr;   // [numTiles] tile ids, longest list first
+        uint32_t* order_ws = nullptr;     // [2 * TO_BUCKETS] bucket histogram + cursors of the heavy-first order
         // control words: [0] = M of the current view, [1] = overflow flag, [2] scratch, [3] raster work counter,
         //                [4] = level-1 pair count, [5] = list total after the tile scan
         uint32_t* d_ctl = nullptr;
@@ -333,7 +333,7 @@ static int ensure_gaussians(Ctx* c, int N)
     GSB_CUDA_CHECK(c, dev_alloc(&c->offsets_ref, (size_t)cap));
     c->dplan = sort_plan((uint32_t)cap, 32u);
     for (Ctx::ViewBufs& v : c->vb) {
-        dev_free(v.rec); dev_free(v.tile_rects); dev_free(v.touched); dev_free(v.offsets); dev_free(v.sbcnt);
+        dev_free(v.rec); dev_free(v.tile_rects); dev_free(v.touched); dev_free(v.offsets);
         for (int i = 0; i < 2; ++i) { dev_free(v.dkeys[i]); dev_free(v.dvals[i]); }
         if (v.dsort_ws) { cudaFree(v.dsort_ws); v.dsort_ws = nullptr; }
         if (v.scan_ws) { cudaFree(v.scan_ws); v.scan_ws = nullptr; }
@@ -341,7 +341,6 @@ static int ensure_gaussians(Ctx* c, int N)
         GSB_CUDA_CHECK(c, dev_alloc(&v.tile_rects, (size_t)cap));
         GSB_CUDA_CHECK(c, dev_alloc(&v.touched, (size_t)cap));
         GSB_CUDA_CHECK(c, dev_alloc(&v.offsets, (size_t)cap));
-        GSB_CUDA_CHECK(c, dev_alloc(&v.sbcnt, (size_t)cap));
         GSB_CUDA_CHECK(c, cudaMalloc(&v.scan_ws, scan_ws_bytes(cap)));
         for (int i = 0; i < 2; ++i) {
             GSB_CUDA_CHECK(c, dev_alloc(&v.dkeys[i], (size_t)cap));
@@ -439,9 +438,9 @@ static int enqueue_binning(Ctx* c, Ctx::ViewBufs& v, cudaStream_t st, int N, con
     {
         StageTimer t(c, GSB_STAGE_SCAN, st);
         // 2. superblocks touched per Gaussian in depth order (+ M = sum of tiles touched), offsets of the level-1 pairs
-        GSB_CUDA_CHECK(c, launch_sb_counts(st, N, v.tile_rects, v.touched, v.dvals[0], v.dvals[1], v.d_dresult_buf, v.sbcnt, &v.d_ctl[0]));
-        GSB_CUDA_CHECK(c, launch_exclusive_scan(st, N, v.sbcnt, nullptr, nullptr, nullptr, v.offsets, &v.d_ctl[4], v.scan_ws));
-        launches += 2;
+        GSB_CUDA_CHECK(c, launch_sb_scan(st, N, v.tile_rects, v.touched, v.dvals[0], v.dvals[1], v.d_dresult_buf, v.offsets, &v.d_ctl[4],
+                                         &v.d_ctl[0], v.scan_ws));
+        launches += 1;
     }
     GSB_CUDA_CHECK(c, cudaMemcpyAsync(v.h_ctl, v.d_ctl, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     GSB_CUDA_CHECK(c, cudaEventRecord(v.ev_ctl, st));
@@ -481,8 +480,7 @@ static int enqueue_binning(Ctx* c, Ctx::ViewBufs& v, cudaStream_t st, int N, con
         GSB_CUDA_CHECK(c, launch_exclusive_scan(st, c->numTiles, v.tile_counts, nullptr, nullptr, nullptr, v.tile_starts, &v.d_ctl[5],
                                                 v.tile_scan_ws));
         GSB_CUDA_CHECK(c, launch_tile_bases(st, c->gridW, c->gridH, c->sbGridW, v.tile_counts, v.tile_starts, v.slice_counts, v.slice_base,
-                                            v.tile_ranges));
-        GSB_CUDA_CHECK(c, launch_tile_order(st, c->numTiles, v.tile_ranges, v.tile_order));
+                                            v.tile_ranges, v.order_ws, v.tile_order));
         launches += 2;
         GSB_CUDA_CHECK(c, launch_l2_fill(st, c->numSB, c->sbGridW, v.sb_ranges, v.vals[0], v.vals[1], v.d_result_buf, v.tile_rects,
                                          v.slice_base, v.list, c->capM));
@@ -596,7 +594,7 @@ static void destroy_ctx(Ctx* c)
         if (v.dsort_ws) cudaFree(v.dsort_ws);
         if (v.scan_ws) cudaFree(v.scan_ws);
         if (v.sort_ws) cudaFree(v.sort_ws);
-        dev_free(v.tile_ranges); dev_free(v.tile_order); dev_free(v.d_ctl); dev_free(v.sbcnt); dev_free(v.list);
+        dev_free(v.tile_ranges); dev_free(v.tile_order); dev_free(v.order_ws); dev_free(v.d_ctl); dev_free(v.list);
         dev_free(v.sb_ranges); dev_free(v.slice_counts); dev_free(v.slice_base); dev_free(v.tile_starts); dev_free(v.tile_counts);
         if (v.tile_scan_ws) cudaFree(v.tile_scan_ws);
         if (v.h_ctl) cudaFreeHost(v.h_ctl);
@@ -744,6 +742,7 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
         CREATE_CHECK(cudaEventCreateWithFlags(&v.ev_back, cudaEventDisableTiming));
         CREATE_CHECK(dev_alloc(&v.tile_ranges, (size_t)c->numTiles * 2));
         CREATE_CHECK(dev_alloc(&v.tile_order, (size_t)c->numTiles));
+        CREATE_CHECK(dev_alloc(&v.order_ws, (size_t)2 * gsb::TO_BUCKETS));
         CREATE_CHECK(dev_alloc(&v.tile_starts, (size_t)c->numTiles + 1));
         CREATE_CHECK(dev_alloc(&v.tile_counts, (size_t)c->numTiles));
         CREATE_CHECK(cudaMalloc(&v.tile_scan_ws, scan_ws_bytes(c->numTiles)));

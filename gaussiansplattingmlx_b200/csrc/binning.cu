@@ -97,12 +97,17 @@ __device__ __forceinline__ void st_release_u64(uint64_t* p, uint64_t v)
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// SBCOUNT: the scanned value of element i is the number of SUPERBLOCKS the tile rect of Gaussian perm[i] touches, computed
+// on the fly (rects = packed tile rects), and the tiles-touched of the same Gaussians are summed into *touched_total
+// (the pair count M) - what used to be a kernel of its own (k_sb_counts) with a 4 MB round trip.
+template <bool SBCOUNT>
 __global__ void __launch_bounds__(SC_THREADS) k_exclusive_scan(int N, const uint32_t* __restrict__ in,
                                                                const uint32_t* __restrict__ perm,
                                                                const uint32_t* __restrict__ perm_sel,
                                                                const uint32_t* __restrict__ perm_alt,
                                                                uint32_t* __restrict__ out, uint32_t* __restrict__ total,
-                                                               uint32_t* counter, uint64_t* status)
+                                                               uint32_t* counter, uint64_t* status,
+                                                               const uint2* __restrict__ rects, uint32_t* __restrict__ touched_total)
 {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[SC_THREADS / 32];
@@ -114,10 +119,30 @@ __global__ void __launch_bounds__(SC_THREADS) k_exclusive_scan(int N, const uint
     const int base = tile * SC_TILE + threadIdx.x * SC_IPT;
     uint32_t v[SC_IPT];
     uint32_t sum = 0;
+    if (SBCOUNT) {
+        uint32_t g[SC_IPT];
 #pragma unroll
-    for (int i = 0; i < SC_IPT; ++i) {
-        v[i] = (base + i < N) ? (perm ? in[perm[base + i]] : in[base + i]) : 0u;
-        sum += v[i];
+        for (int i = 0; i < SC_IPT; ++i) g[i] = (base + i < N) ? perm[base + i] : 0xffffffffu;
+        uint32_t tsum = 0;
+#pragma unroll
+        for (int i = 0; i < SC_IPT; ++i) {
+            v[i] = 0u;
+            if (g[i] != 0xffffffffu) {
+                const uint2 r = rects[g[i]];
+                const int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
+                if (x1 > x0 && y1 > y0) v[i] = (uint32_t)((((x1 - 1) / SBW) - (x0 / SBW) + 1) * (((y1 - 1) / SBH) - (y0 / SBH) + 1));
+                tsum += in[g[i]];   // in = tiles-touched per Gaussian
+            }
+            sum += v[i];
+        }
+        tsum = __reduce_add_sync(0xffffffffu, tsum);
+        if ((threadIdx.x & 31) == 0 && tsum) atomicAdd(touched_total, tsum);
+    } else {
+#pragma unroll
+        for (int i = 0; i < SC_IPT; ++i) {
+            v[i] = (base + i < N) ? (perm ? in[perm[base + i]] : in[base + i]) : 0u;
+            sum += v[i];
+        }
     }
     // block inclusive scan of per-thread sums
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -191,7 +216,23 @@ cudaError_t launch_exclusive_scan(cudaStream_t st, int N, const uint32_t* in, co
     if (e != cudaSuccess) return e;
     uint32_t* counter = reinterpret_cast<uint32_t*>(scan_ws);
     uint64_t* status = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(scan_ws) + 16);
-    k_exclusive_scan<<<cdiv(N, SC_TILE), SC_THREADS, 0, st>>>(N, in, perm0, perm_sel, perm1, offsets, total, counter, status);
+    k_exclusive_scan<false><<<cdiv(N, SC_TILE), SC_THREADS, 0, st>>>(N, in, perm0, perm_sel, perm1, offsets, total, counter, status, nullptr, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sb_scan(cudaStream_t st, int N, const uint2* tile_rects, const uint32_t* touched, const uint32_t* perm0,
+                           const uint32_t* perm1, const uint32_t* perm_sel, uint32_t* offsets, uint32_t* total_sb_pairs,
+                           uint32_t* total_pairs, void* scan_ws)
+{
+    cudaError_t e = cudaMemsetAsync(total_pairs, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    if (N <= 0) return cudaMemsetAsync(total_sb_pairs, 0, sizeof(uint32_t), st);
+    e = cudaMemsetAsync(scan_ws, 0, scan_ws_bytes(N), st);
+    if (e != cudaSuccess) return e;
+    uint32_t* counter = reinterpret_cast<uint32_t*>(scan_ws);
+    uint64_t* status = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(scan_ws) + 16);
+    k_exclusive_scan<true><<<cdiv(N, SC_TILE), SC_THREADS, 0, st>>>(N, touched, perm0, perm_sel, perm1, offsets, total_sb_pairs, counter, status,
+                                                                      tile_rects, total_pairs);
     return cudaGetLastError();
 }
 
@@ -707,67 +748,6 @@ cudaError_t launch_key_ranges(cudaStream_t st, const uint32_t* keys0, const uint
     if (capacity == 0) return cudaSuccess;
     const int blocks = (int)std::min<uint64_t>(((uint64_t)capacity + 255) / 256, 148ull * 16ull);
     k_key_ranges<<<blocks, 256, 0, st>>>(keys0, keys1, d_result_buf, d_count, capacity, ranges);
-    return cudaGetLastError();
-}
-
-// Heavy tiles first: tile ids sorted by descending list length (counting sort over 1024 length buckets,
-// one CTA).  The rasterisers map blockIdx -> order[blockIdx], so the longest lists start in the first
-// wave and the tail of the launch is made of short ones.
-constexpr int TO_THREADS = 256;   // small footprint: this kernel must fit beside the resident rasteriser CTAs of the previous view
-constexpr int TO_BUCKETS = 1024;
-__global__ void __launch_bounds__(TO_THREADS) k_tile_order(int numTiles, const uint32_t* __restrict__ ranges, uint32_t* __restrict__ order)
-{
-    __shared__ uint32_t s_hist[TO_BUCKETS];
-    __shared__ uint32_t s_warp[TO_THREADS / 32];
-    __shared__ uint32_t s_max;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // one 8-byte load per tile, four tiles in flight per thread: the kernel is a chain of dependent L2 round trips
-    const uint2* __restrict__ ranges2 = reinterpret_cast<const uint2*>(ranges);
-    auto count_of = [&](int t) { const uint2 r = __ldg(ranges2 + t); return r.y > r.x ? r.y - r.x : 0u; };
-    uint32_t mx = 0;
-#pragma unroll 4
-    for (int t = tid; t < numTiles; t += TO_THREADS) mx = max(mx, count_of(t));
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    if (lane == 0) s_warp[warp] = mx;
-    for (int i = tid; i < TO_BUCKETS; i += TO_THREADS) s_hist[i] = 0;
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t m = 0;
-        for (int w = 0; w < TO_THREADS / 32; ++w) m = max(m, s_warp[w]);
-        s_max = m;
-    }
-    __syncthreads();
-    const uint32_t maxc = max(s_max, 1u);
-    auto bucket_of = [&](uint32_t c) { return (uint32_t)(TO_BUCKETS - 1) - (uint32_t)(((unsigned long long)c * (TO_BUCKETS - 1)) / maxc); };
-#pragma unroll 4
-    for (int t = tid; t < numTiles; t += TO_THREADS) atomicAdd(&s_hist[bucket_of(count_of(t))], 1u);
-    __syncthreads();
-    // exclusive scan of the buckets: thread tid owns buckets [4 tid, 4 tid + 4)
-    constexpr int PER = TO_BUCKETS / TO_THREADS;
-    uint32_t v[PER], sum = 0;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) { v[i] = s_hist[tid * PER + i]; sum += v[i]; }
-    uint32_t inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += n;
-    }
-    __syncthreads();
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    uint32_t run = inc - sum;
-    for (int w = 0; w < warp; ++w) run += s_warp[w];
-#pragma unroll
-    for (int i = 0; i < PER; ++i) { s_hist[tid * PER + i] = run; run += v[i]; }
-    __syncthreads();
-#pragma unroll 4
-    for (int t = tid; t < numTiles; t += TO_THREADS) order[atomicAdd(&s_hist[bucket_of(count_of(t))], 1u)] = (uint32_t)t;
-}
-
-cudaError_t launch_tile_order(cudaStream_t st, int numTiles, const uint32_t* tile_ranges, uint32_t* order)
-{
-    if (numTiles > 0) k_tile_order<<<1, TO_THREADS, 0, st>>>(numTiles, tile_ranges, order);
     return cudaGetLastError();
 }
 

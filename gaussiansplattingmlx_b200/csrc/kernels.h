@@ -54,6 +54,11 @@ cudaError_t launch_count_tiles(cudaStream_t st, int N, const ViewParams& vp, con
 size_t scan_ws_bytes(int N);
 cudaError_t launch_exclusive_scan(cudaStream_t st, int N, const uint32_t* in, const uint32_t* perm0, const uint32_t* perm1,
                                   const uint32_t* perm_sel, uint32_t* offsets, uint32_t* total, void* scan_ws);
+// The level-1 scan: offsets[i] = exclusive prefix, in DEPTH order (perm), of the superblocks the tile rect of Gaussian
+// perm[i] touches; *total_sb_pairs = their sum; *total_pairs = sum of tiles-touched = M.
+cudaError_t launch_sb_scan(cudaStream_t st, int N, const uint2* tile_rects, const uint32_t* touched, const uint32_t* perm0,
+                           const uint32_t* perm1, const uint32_t* perm_sel, uint32_t* offsets, uint32_t* total_sb_pairs,
+                           uint32_t* total_pairs, void* scan_ws);
 // K4 in depth order: cell-id keys + Gaussian indices, one thread per output pair (coalesced).  A cell is cw x ch
 // tiles (1 x 1 = the reference's tiles, SBW x SBH = the superblocks of tilelists.cu); cellGridW = cells per row.
 cudaError_t launch_generate_keys(cudaStream_t st, int N, int cellGridW, int cw, int ch, const uint2* tile_rects,
@@ -95,8 +100,6 @@ cudaError_t launch_iota(cudaStream_t st, uint32_t n, uint32_t* v);
 // K6 on a sorted key list: ranges[key] = (first, last + 1), (0, 0) for absent keys
 cudaError_t launch_key_ranges(cudaStream_t st, const uint32_t* keys0, const uint32_t* keys1, const uint32_t* d_result_buf,
                               const uint32_t* d_count, uint32_t capacity, uint32_t* ranges, int numKeys);
-// tile ids by descending list length (raster launch order)
-cudaError_t launch_tile_order(cudaStream_t st, int numTiles, const uint32_t* tile_ranges, uint32_t* order);
 cudaError_t launch_tile_counts(cudaStream_t st, int numTiles, const uint32_t* tile_ranges, uint32_t* tile_counts);
 // packed[N,11] (reference layout) → rec[N,12]
 cudaError_t launch_packed_to_rec(cudaStream_t st, int N, const float* packed, float* rec);
@@ -107,16 +110,16 @@ cudaError_t launch_merge_keys(cudaStream_t st, uint32_t M, const uint32_t* hi, c
                               uint64_t* keys);
 
 // ---- tilelists.cu ------------------------------------------------------------------------------
-cudaError_t launch_sb_counts(cudaStream_t st, int N, const uint2* tile_rects, const uint32_t* touched, const uint32_t* perm0,
-                             const uint32_t* perm1, const uint32_t* perm_sel, uint32_t* sb_counts, uint32_t* total_pairs);
 cudaError_t launch_l2_count(cudaStream_t st, int numSB, int sbGridW, int gridW, int gridH, const uint32_t* sb_ranges, const uint32_t* vals0,
                             const uint32_t* vals1, const uint32_t* d_result_buf, const uint2* tile_rects, uint32_t* slice_counts,
                             uint32_t* tile_counts);
 cudaError_t launch_l2_fill(cudaStream_t st, int numSB, int sbGridW, const uint32_t* sb_ranges, const uint32_t* vals0,
                            const uint32_t* vals1, const uint32_t* d_result_buf, const uint2* tile_rects, const uint32_t* slice_base,
                            uint32_t* list, uint32_t capacity);
+constexpr int TO_BUCKETS = 256;   // length buckets of the heavy-first tile order
+// CSR ranges + slice bases, and (order_ws != NULL: 2 * TO_BUCKETS words of scratch) the heavy-first tile order
 cudaError_t launch_tile_bases(cudaStream_t st, int gridW, int gridH, int sbGridW, const uint32_t* tile_counts, const uint32_t* tile_starts,
-                              const uint32_t* slice_counts, uint32_t* slice_base, uint32_t* tile_ranges);
+                              const uint32_t* slice_counts, uint32_t* slice_base, uint32_t* tile_ranges, uint32_t* order_ws, uint32_t* order);
 cudaError_t launch_expand_sorted_keys(cudaStream_t st, uint32_t M, int numTiles, const uint32_t* tile_starts, const uint32_t* list,
                                       const float* depth_ptr, int depth_stride, uint32_t* hi, uint32_t* lo);
 

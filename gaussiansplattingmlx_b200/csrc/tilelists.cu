@@ -13,7 +13,7 @@
 //             32 entries at a time, rebuilds the 8-bit "which of my 8 tiles does this rect cover" mask from the
 //             packed tile rect and counts per tile with ballots.  The per-tile totals are scanned
 //             (binning.cu), k_tile_bases turns them into CSR ranges and (superblock, warp slice, tile) bases, and
-//             k_tile_order (binning.cu) gives the heavy-first launch order.  FILL: the same walk again; lane ranks from the ballots give every (Gaussian, tile) pair its
+//             k_tile_order2 gives the heavy-first launch order.  FILL: the same walk again; lane ranks from the ballots give every (Gaussian, tile) pair its
 //             final slot — stable by construction, no atomics, writes coalesced per tile.
 //
 // HBM traffic per view at C3: ~3.4 M pairs x (8 B keygen + 36 B sort) + 2 x (3.4 M x 12 B) walks + 48 MB of list
@@ -35,44 +35,6 @@ __device__ __forceinline__ uint32_t sb_tile_mask(uint2 r, int tx0, int ty0)
     for (int y = 0; y < SBH; ++y)
         if (y >= ly && y < hy) m |= xm << (y * SBW);
     return m;
-}
-
-// ------------------------------------------------------------------------------------------------
-// superblock counts in depth order (input of the level-1 scan) + M = sum of tiles-touched
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sb_counts(int N, const uint2* __restrict__ tile_rects, const uint32_t* __restrict__ touched,
-                                                   const uint32_t* __restrict__ perm0, const uint32_t* __restrict__ perm1,
-                                                   const uint32_t* __restrict__ perm_sel, uint32_t* __restrict__ sb_counts,
-                                                   uint32_t* __restrict__ total_pairs)
-{
-    const uint32_t* perm = (perm_sel && *perm_sel) ? perm1 : perm0;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t t = 0;
-    if (i < N) {
-        const uint32_t g = perm ? perm[i] : (uint32_t)i;
-        const uint2 r = tile_rects[g];
-        const int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
-        uint32_t c = 0;
-        if (x1 > x0 && y1 > y0) c = (uint32_t)((((x1 - 1) / SBW) - (x0 / SBW) + 1) * (((y1 - 1) / SBH) - (y0 / SBH) + 1));
-        sb_counts[i] = c;
-        t = touched[g];
-    }
-    t = __reduce_add_sync(0xffffffffu, t);
-    __shared__ uint32_t s_sum;
-    if (threadIdx.x == 0) s_sum = 0;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0 && t) atomicAdd(&s_sum, t);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_sum) atomicAdd(total_pairs, s_sum);
-}
-
-cudaError_t launch_sb_counts(cudaStream_t st, int N, const uint2* tile_rects, const uint32_t* touched, const uint32_t* perm0,
-                             const uint32_t* perm1, const uint32_t* perm_sel, uint32_t* sb_counts, uint32_t* total_pairs)
-{
-    cudaError_t e = cudaMemsetAsync(total_pairs, 0, sizeof(uint32_t), st);
-    if (e != cudaSuccess) return e;
-    if (N > 0) k_sb_counts<<<cdiv(N, 256), 256, 0, st>>>(N, tile_rects, touched, perm0, perm1, perm_sel, sb_counts, total_pairs);
-    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -173,12 +135,27 @@ cudaError_t launch_l2_fill(cudaStream_t st, int numSB, int sbGridW, const uint32
 // tile ranges in the reference convention ((0,0) for an empty tile) and the base of every (superblock, warp
 // slice, tile) run.  One thread per tile.
 // ------------------------------------------------------------------------------------------------
+// Heavy-first launch order of the rasterisers: tiles are dropped into TO_BUCKETS log-spaced length buckets (8 per octave,
+// longest first).  k_tile_bases counts the tiles per bucket, k_tile_order2 turns the counts into bucket bases and hands out the
+// slots with one atomic per tile - the order inside a bucket is arbitrary (it only schedules work; results do not depend on
+// it).  Replaces a single-CTA counting sort (18 us on the critical path of every view) by a 32-CTA kernel.
+__device__ __forceinline__ uint32_t tile_order_bucket(uint32_t c)
+{
+    if (c == 0u) return TO_BUCKETS - 1;
+    const int msb = 31 - __clz(c);
+    const uint32_t sub = msb >= 3 ? ((c >> (msb - 3)) & 7u) : ((c << (3 - msb)) & 7u);
+    const uint32_t rank = (uint32_t)msb * 8u + sub;          // monotone in c, < 256
+    return (TO_BUCKETS - 2) - min(rank, (uint32_t)(TO_BUCKETS - 2));
+}
+
 __global__ void __launch_bounds__(256) k_tile_bases(int gridW, int gridH, int sbGridW, const uint32_t* __restrict__ tile_counts,
                                                     const uint32_t* __restrict__ tile_starts, const uint32_t* __restrict__ slice_counts,
-                                                    uint32_t* __restrict__ slice_base, uint32_t* __restrict__ tile_ranges)
+                                                    uint32_t* __restrict__ slice_base, uint32_t* __restrict__ tile_ranges,
+                                                    uint32_t* __restrict__ bucket_hist)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= gridW * gridH) return;
+    if (bucket_hist) atomicAdd(&bucket_hist[tile_order_bucket(tile_counts[t])], 1u);
     const int tx = t % gridW, ty = t / gridW;
     const int s = (ty / SBH) * sbGridW + tx / SBW;
     const size_t sl = (size_t)s * L2_WARPS * SB_TILES + (size_t)((ty % SBH) * SBW + tx % SBW);
@@ -193,11 +170,45 @@ __global__ void __launch_bounds__(256) k_tile_bases(int gridW, int gridH, int sb
     tile_ranges[t * 2 + 1] = c ? start + c : 0u;
 }
 
+__global__ void __launch_bounds__(256) k_tile_order2(int numTiles, const uint32_t* __restrict__ tile_counts, const uint32_t* __restrict__ bucket_hist,
+                                                     uint32_t* __restrict__ bucket_cursor, uint32_t* __restrict__ order)
+{
+    __shared__ uint32_t s_base[TO_BUCKETS];
+    __shared__ uint32_t s_warp[8];
+    static_assert(TO_BUCKETS == 256, "one bucket per thread");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t c = bucket_hist[tid];
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t pre = 0;
+    for (int w = 0; w < warp; ++w) pre += s_warp[w];
+    s_base[tid] = pre + inc - c;
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + tid;
+    if (t < numTiles) {
+        const uint32_t b = tile_order_bucket(tile_counts[t]);
+        order[s_base[b] + atomicAdd(&bucket_cursor[b], 1u)] = (uint32_t)t;
+    }
+}
+
+// order_ws: 2 * TO_BUCKETS words (bucket histogram, bucket cursors), zeroed here
 cudaError_t launch_tile_bases(cudaStream_t st, int gridW, int gridH, int sbGridW, const uint32_t* tile_counts, const uint32_t* tile_starts,
-                              const uint32_t* slice_counts, uint32_t* slice_base, uint32_t* tile_ranges)
+                              const uint32_t* slice_counts, uint32_t* slice_base, uint32_t* tile_ranges, uint32_t* order_ws, uint32_t* order)
 {
     const int n = gridW * gridH;
-    if (n > 0) k_tile_bases<<<cdiv(n, 256), 256, 0, st>>>(gridW, gridH, sbGridW, tile_counts, tile_starts, slice_counts, slice_base, tile_ranges);
+    if (n <= 0) return cudaSuccess;
+    if (order_ws) {
+        cudaError_t e = cudaMemsetAsync(order_ws, 0, 2 * TO_BUCKETS * sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
+    }
+    k_tile_bases<<<cdiv(n, 256), 256, 0, st>>>(gridW, gridH, sbGridW, tile_counts, tile_starts, slice_counts, slice_base, tile_ranges, order_ws);
+    if (order_ws) k_tile_order2<<<cdiv(n, 256), 256, 0, st>>>(n, tile_counts, order_ws, order_ws + TO_BUCKETS, order);
     return cudaGetLastError();
 }
 
