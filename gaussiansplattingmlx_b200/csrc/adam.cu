@@ -316,7 +316,8 @@ __device__ __forceinline__ void mc_st(float* mc, float v)
 
 constexpr int MC_UNROLL = 4;
 
-__global__ void __launch_bounds__(1024) k_adam_multicast(const __grid_constant__ AdamTensors t, const __grid_constant__ AdamPeers pr,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_adam_multicast(const __grid_constant__ AdamTensors t, const __grid_constant__ AdamPeers pr,
                                                                const __grid_constant__ AdamSeg seg, const __grid_constant__ PeerStepSync sy,
                                                                const float* __restrict__ mc_grads, float* __restrict__ mc_params, float b1,
                                                                float b2, float eps, float gscale, int N)
@@ -412,14 +413,20 @@ cudaError_t launch_adam_multicast(cudaStream_t st, const AdamTensors& t, const A
     // of multi-microsecond multimem requests - the projection / binning kernels of the next step that share those SMs slow
     // down 3-4x (r2r).  32 CTAs of 1024 threads keep the same bytes in flight on 32 SMs and leave the other 116 alone.
     static const int env_threads = getenv("GSB_MC_THREADS") ? atoi(getenv("GSB_MC_THREADS")) : 0;
-    const int threads = env_threads > 0 ? std::min(1024, (env_threads + 31) & ~31) : 1024;
+    // (2 replicas: each owns half of Adam's state, the launch is bound by LOCAL HBM traffic and wants every SM:
+    // 148 x 256 threads 7.32 ms per strong-scaling step against 7.59 ms with 32 x 1024, profiles/r2/r2q vs r2z)
+    const bool wide = pr.world <= 2;
+    const int threads = env_threads > 0 ? std::min(1024, (env_threads + 31) & ~31) : (wide ? 256 : 1024);
     long long blocks = (std::max<long long>((total + MC_UNROLL - 1) / MC_UNROLL, 1) + threads - 1) / threads;
-    long long cap = 32;
+    long long cap = wide ? 148 : 32;
     if (blocks_override > 0) cap = blocks_override;   // gsb_trainer_peers_tune
     if (blocks > cap) blocks = cap;
     PeerStepSync sy{};
     if (sync) sy = *sync;
-    k_adam_multicast<<<(int)blocks, threads, 0, st>>>(t, pr, seg, sy, mc_grads, mc_params, beta1, beta2, eps, gscale, N);
+    if (threads <= 256)   // compiled for 256 threads: no register cap, no spills
+        k_adam_multicast<256><<<(int)blocks, threads, 0, st>>>(t, pr, seg, sy, mc_grads, mc_params, beta1, beta2, eps, gscale, N);
+    else
+        k_adam_multicast<1024><<<(int)blocks, threads, 0, st>>>(t, pr, seg, sy, mc_grads, mc_params, beta1, beta2, eps, gscale, N);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
