@@ -64,8 +64,8 @@ struct Ctx {
         // level 2 / per tile
         uint32_t* list = nullptr;         // [capM] Gaussian indices in (tile, depth, index) order = the tile lists
         uint32_t* sb_ranges = nullptr;    // [numSB,2] slice of every superblock in the sorted level-1 list
-        uint32_t* slice_counts = nullptr; // [numSB,8 warps,8 tiles]
-        uint32_t* slice_base = nullptr;   // [numSB,8 warps,8 tiles]
+        uint32_t* slice_counts = nullptr; // [numSB, L2_SLICES warp slices, 8 tiles]
+        uint32_t* slice_base = nullptr;   // [numSB, L2_SLICES warp slices, 8 tiles]
         uint32_t* tile_starts = nullptr;  // [numTiles+1] monotone CSR offsets
         uint32_t* tile_counts = nullptr;  // [numTiles]
         void* tile_scan_ws = nullptr;
@@ -747,8 +747,8 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
         CREATE_CHECK(dev_alloc(&v.tile_counts, (size_t)c->numTiles));
         CREATE_CHECK(cudaMalloc(&v.tile_scan_ws, scan_ws_bytes(c->numTiles)));
         CREATE_CHECK(dev_alloc(&v.sb_ranges, (size_t)c->numSB * 2));
-        CREATE_CHECK(dev_alloc(&v.slice_counts, (size_t)c->numSB * gsb::L2_WARPS * gsb::SB_TILES));
-        CREATE_CHECK(dev_alloc(&v.slice_base, (size_t)c->numSB * gsb::L2_WARPS * gsb::SB_TILES));
+        CREATE_CHECK(dev_alloc(&v.slice_counts, (size_t)c->numSB * gsb::L2_SLICES * gsb::SB_TILES));
+        CREATE_CHECK(dev_alloc(&v.slice_base, (size_t)c->numSB * gsb::L2_SLICES * gsb::SB_TILES));
         CREATE_CHECK(dev_alloc(&v.d_ctl, 8));
         CREATE_CHECK(dev_alloc(&v.d_nvalue, 4));
         CREATE_CHECK(cudaMallocHost(reinterpret_cast<void**>(&v.h_ctl), 8 * sizeof(uint32_t)));

@@ -14,7 +14,13 @@ namespace gsb {
 #ifndef GSB_L2_WARPS
 #define GSB_L2_WARPS 8
 #endif
+// a superblock's slice is walked by L2_SPLIT CTAs of L2_WARPS warps = L2_SLICES warp slices: the kernel lasts as long as the
+// heaviest superblock (3x the mean at C3), so the heavy ones must spread over several CTAs
+#ifndef GSB_L2_SPLIT
+#define GSB_L2_SPLIT 4
+#endif
 constexpr int SBW = GSB_SBW, SBH = GSB_SBH, L2_WARPS = GSB_L2_WARPS, SB_TILES = SBW * SBH;
+constexpr int L2_SPLIT = GSB_L2_SPLIT, L2_SLICES = L2_WARPS * L2_SPLIT;
 static_assert(SB_TILES <= 32 && L2_WARPS * 32 <= 1024, "superblock geometry");
 
 // ---- project.cu --------------------------------------------------------------------------------

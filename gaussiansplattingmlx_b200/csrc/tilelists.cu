@@ -55,12 +55,13 @@ __global__ void __launch_bounds__(L2_WARPS * 32) k_l2_walk(int sbGridW, const ui
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t begin = sb_ranges[s * 2], end = sb_ranges[s * 2 + 1];
     const uint32_t n = end > begin ? end - begin : 0u;
-    const uint32_t per = (n + L2_WARPS - 1) / L2_WARPS;
-    const uint32_t w0 = min(begin + warp * per, end), w1 = min(w0 + per, end);
+    const int slice = blockIdx.y * L2_WARPS + warp;      // blockIdx.y < L2_SPLIT
+    const uint32_t per = (n + L2_SLICES - 1) / L2_SLICES;
+    const uint32_t w0 = min(begin + slice * per, end), w1 = min(w0 + per, end);
     const uint32_t* __restrict__ vals = (d_result_buf && *d_result_buf) ? vals1 : vals0;
     const int tx0 = (s % sbGridW) * SBW, ty0 = (s / sbGridW) * SBH;
     const uint32_t lt = (1u << lane) - 1u;
-    const size_t slot = ((size_t)s * L2_WARPS + warp) * SB_TILES;
+    const size_t slot = ((size_t)s * L2_SLICES + slice) * SB_TILES;
     uint32_t run[SB_TILES];
 #pragma unroll
     for (int t = 0; t < SB_TILES; ++t) run[t] = FILL ? slice_base[slot + t] : 0u;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(L2_WARPS * 32) k_l2_walk(int sbGridW, const ui
                 uint32_t c = 0;
 #pragma unroll
                 for (int w = 0; w < L2_WARPS; ++w) c += s_cnt[w][t];
-                tile_counts[ty * gridW + tx] = c;
+                if (c) atomicAdd(&tile_counts[ty * gridW + tx], c);   // L2_SPLIT CTAs per superblock: zeroed by the launcher
             }
         }
     }
@@ -115,9 +116,12 @@ cudaError_t launch_l2_count(cudaStream_t st, int numSB, int sbGridW, int gridW, 
                             const uint32_t* vals1, const uint32_t* d_result_buf, const uint2* tile_rects, uint32_t* slice_counts,
                             uint32_t* tile_counts)
 {
-    if (numSB > 0)
-        k_l2_walk<false><<<numSB, L2_WARPS * 32, 0, st>>>(sbGridW, sb_ranges, vals0, vals1, d_result_buf, tile_rects, slice_counts, nullptr,
-                                                          nullptr, 0u, tile_counts, gridW, gridH);
+    if (numSB > 0) {
+        cudaError_t e = cudaMemsetAsync(tile_counts, 0, (size_t)gridW * gridH * sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
+        k_l2_walk<false><<<dim3(numSB, L2_SPLIT), L2_WARPS * 32, 0, st>>>(sbGridW, sb_ranges, vals0, vals1, d_result_buf, tile_rects, slice_counts,
+                                                                          nullptr, nullptr, 0u, tile_counts, gridW, gridH);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_l2_fill(cudaStream_t st, int numSB, int sbGridW, const uint32_t* sb_ranges, const uint32_t* vals0,
@@ -125,7 +129,7 @@ cudaError_t launch_l2_fill(cudaStream_t st, int numSB, int sbGridW, const uint32
                            uint32_t* list, uint32_t capacity)
 {
     if (numSB > 0)
-        k_l2_walk<true><<<numSB, L2_WARPS * 32, 0, st>>>(sbGridW, sb_ranges, vals0, vals1, d_result_buf, tile_rects, nullptr, slice_base,
+        k_l2_walk<true><<<dim3(numSB, L2_SPLIT), L2_WARPS * 32, 0, st>>>(sbGridW, sb_ranges, vals0, vals1, d_result_buf, tile_rects, nullptr, slice_base,
                                                          list, capacity, nullptr, 0, 0);
     return cudaGetLastError();
 }
@@ -158,11 +162,11 @@ __global__ void __launch_bounds__(256) k_tile_bases(int gridW, int gridH, int sb
     if (bucket_hist) atomicAdd(&bucket_hist[tile_order_bucket(tile_counts[t])], 1u);
     const int tx = t % gridW, ty = t / gridW;
     const int s = (ty / SBH) * sbGridW + tx / SBW;
-    const size_t sl = (size_t)s * L2_WARPS * SB_TILES + (size_t)((ty % SBH) * SBW + tx % SBW);
+    const size_t sl = (size_t)s * L2_SLICES * SB_TILES + (size_t)((ty % SBH) * SBW + tx % SBW);
     const uint32_t start = tile_starts[t], c = tile_counts[t];
     uint32_t b = start;
-#pragma unroll
-    for (int w = 0; w < L2_WARPS; ++w) {
+#pragma unroll 8
+    for (int w = 0; w < L2_SLICES; ++w) {
         slice_base[sl + (size_t)w * SB_TILES] = b;
         b += slice_counts[sl + (size_t)w * SB_TILES];
     }
