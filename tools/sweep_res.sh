@@ -9,7 +9,7 @@ for v in "${VARS[@]}"; do
 import json,sys
 d=json.loads(sys.stdin.read())
 k=d['roofline_kernels']
-print('[$v] ms/step %.3f serialized %.3f e2e %.3f' % (d['ms_per_step'], d['ms_per_step_serialized'], d['e2e']['ms_per_step']))
+print('[$v] ms/step %.3f serialized %.3f e2e %.3f  clocks %s' % (d['ms_per_step'], d['ms_per_step_serialized'], d['e2e']['ms_per_step'], d.get('clocks')))
 print('  serial: ' + ', '.join('%s %.3f' % (n, v['ms']) for n, v in k.items()))"
   grep "overlap on" gpurun_out/sweep.err
 done
