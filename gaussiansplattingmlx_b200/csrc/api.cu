@@ -767,10 +767,10 @@ int gsb_create(const gsb_config* cfg, gsb_ctx** out)
         CREATE_CHECK(dev_alloc(&c->ck.depth, (size_t)c->ck.capacity * 256));
         CREATE_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->ck.header), (size_t)c->ck.capacity * sizeof(uint2)));
         CREATE_CHECK(dev_alloc(&c->ck.count, 4));
-        CREATE_CHECK(dev_alloc(&c->ck.written, (size_t)std::max(blocks, 1) * 2));   // per half-block
+        CREATE_CHECK(dev_alloc(&c->ck.written, (size_t)std::max(blocks, 1)));
         CREATE_CHECK(dev_alloc(&c->ck.table, (size_t)std::max(blocks, 1) * 17));
         CREATE_CHECK(cudaMemset(c->ck.count, 0, 4 * sizeof(uint32_t)));
-        CREATE_CHECK(cudaMemset(c->ck.written, 0, (size_t)std::max(blocks, 1) * 2 * sizeof(uint32_t)));
+        CREATE_CHECK(cudaMemset(c->ck.written, 0, (size_t)std::max(blocks, 1) * sizeof(uint32_t)));
     }
     CREATE_CHECK(dev_alloc(&c->mapA, P * 3));
     CREATE_CHECK(dev_alloc(&c->mapB, P * 3));

@@ -120,13 +120,6 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar)
 {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// per-thread completion of the same copies (a thread that only touches the bytes it copied itself needs no mbarrier)
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -140,7 +140,7 @@ struct RasterCkpt {
     uint2* header = nullptr;      // [capacity] (block work id, checkpoint index | 0xffffffff = final partial segment sums)
     uint32_t* table = nullptr;    // [blocks][17] slot of checkpoint c (c < written), [16] = slot of the final segment sums
     uint32_t* count = nullptr;    // slots requested by the last forward (may exceed capacity)
-    uint32_t* written = nullptr;  // [blocks][2] checkpoints each 16x8 half of a block managed to write
+    uint32_t* written = nullptr;  // [blocks] checkpoints each block managed to write
     uint32_t capacity = 0;
 };
 int raster_block_count(const ViewParams& vp);

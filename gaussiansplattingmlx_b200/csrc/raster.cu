@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(RT, GSB_FWD_CTAS) k_raster_fwd(const __grid_co
                 }
             }
         }
-        if (tid < 2 && ck.written) ck.written[2 * work + tid] = ck_written;   // per half (k_raster_fwd_half): here both alike
+        if (tid == 0 && ck.written) ck.written[work] = ck_written;
         // epilogue: exact lastContrib / transmittance at termination, then the outputs
 #pragma unroll
         for (int r = 0; r < FPPT; ++r) {
@@ -442,379 +442,8 @@ __global__ void __launch_bounds__(RT, GSB_FWD_CTAS) k_raster_fwd(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward, half-block work items (the product path; k_raster_fwd above is kept as the checked predecessor, GSB_FWD_HALF=0)
-// ------------------------------------------------------------------------------------------------
-// ONE WARP = one 16 x 8 half of a 16x16 block = one work item = one CTA.  Against the 64-thread kernel above:
-//   * no CTA barrier and no idle sibling: a half that has terminated pulls the next item (early exit at 16 x 8 instead of
-//     16 x 16 granularity: 1.29 E instead of 1.365 E evaluated at C3, tools/analysis/raster_work_model.py), and the
-//     persistent grid balances twice as many, half as long items;
-//   * the warp stages its own batches (64 records, two per lane, 16-byte LDGSTS tracked per thread by cp.async groups) and
-//     every lane rewrites the records IT copied before the warp blends them: the row-dependent terms of the exponent
-//         P = C dy^2 + log2(opacity),  Q = B dy,  R = 2 C dy        (dy = first row of a row group - mean.y)
-//     are the same for the 16 threads of a row group, so they are computed once per (record, row group) - a 64-byte staged
-//     record carries them for the warp's two row groups - and a thread is left with dx, E0 = dx (A dx + Q) + P,
-//     E1 = B dx + R: 4 instructions instead of 9, the SAME operations on the same values as fwd_exponents (bit-identical
-//     pixels, checkpoints and lastContrib; tests compare the two kernels).
-// Checkpoints keep their 256-pixel slots (the backward works on whole blocks): the half that reaches checkpoint c of a
-// block first allocates the slot and publishes it in ck.table[block][c] with a compare-and-swap; its sibling finds it there
-// (or loses the race, adopts the published slot and retires its own allocation as a non-item).  Each half stores only its
-// 128 pixels; a half that stops earlier leaves its part of later slots untouched and its pixels never read them
-// (ck.written is per half).  ck.table must hold CK_EMPTY on entry (launcher).
-constexpr int HRB = 64;          // records per batch
-constexpr int HQ = 4;            // float4 quads per staged record
-constexpr uint32_t CK_EMPTY = 0xffffffffu, CK_FAILED = 0xfffffffeu;
-#ifndef GSB_FWDH_CTAS
-#define GSB_FWDH_CTAS 24
-#endif
-static_assert(HRB % FCHUNK == 0 && CK % HRB == 0, "checkpoints sit on batch boundaries");
-
-struct FwdRow {
-    float P, Q, R;
-};
-// same operations as fwd_exponents (explicit roundings: no contraction in either)
-__device__ __forceinline__ FwdRow fwd_row_terms(float B, float C, float lo, float dyb)
-{
-    const float Cd = __fmul_rn(C, dyb);
-    FwdRow t;
-    t.P = fmaf(Cd, dyb, lo);
-    t.Q = __fmul_rn(B, dyb);
-    t.R = __fadd_rn(Cd, Cd);
-    return t;
-}
-__device__ __forceinline__ FwdExp fwd_exponents_rows(float A, float B, float C, float P, float Q, float R, float dx)
-{
-    FwdExp e;
-    e.E0 = fmaf(dx, fmaf(A, dx, Q), P);
-    e.E1 = fmaf(B, dx, R);
-    e.C = C;
-    return e;
-}
-
-// lane 0 of a half: the slot of checkpoint c < CK_MAX of `block` (CK_FAILED: pool exhausted - for both halves)
-__device__ __forceinline__ uint32_t ck_acquire(const RasterCkpt& ck, uint32_t block, uint32_t c)
-{
-    uint32_t* entry = ck.table + (size_t)block * (CK_MAX + 1) + c;
-    uint32_t cur = *reinterpret_cast<volatile uint32_t*>(entry);
-    if (cur != CK_EMPTY) return cur;
-    // the first checkpoint also reserves the slot of the block's final (partial) segment sums: slot of checkpoint 0 - 1
-    uint32_t mine = CK_FAILED;
-    const uint32_t want = c == 0u ? 2u : 1u;
-    const uint32_t first = atomicAdd(ck.count, want);
-    if (first + want > ck.capacity) {   // pool exhausted; every slot below min(count, capacity) keeps a valid header
-        if (first < ck.capacity) ck.header[first] = make_uint2(block, 0xffffffffu);
-    } else {
-        mine = first + want - 1u;
-        if (want == 2u) ck.header[first] = make_uint2(block, 0xffffffffu);   // not a work item
-        ck.header[mine] = make_uint2(block, c);
-    }
-    const uint32_t old = atomicCAS(entry, CK_EMPTY, mine);
-    if (old == CK_EMPTY) return mine;
-    if (mine != CK_FAILED) ck.header[mine] = make_uint2(block, 0xffffffffu);     // the sibling published first: retire ours
-    return old;
-}
-
-template <bool DEPTH>
-__global__ void __launch_bounds__(32, GSB_FWDH_CTAS) k_raster_fwd_half(const __grid_constant__ ViewParams vp,
-                                                       const uint32_t* __restrict__ tile_ranges,
-                                                       const uint32_t* __restrict__ tile_order,
-                                                       const float4* __restrict__ rec, const uint32_t* __restrict__ vals0,
-                                                       const uint32_t* __restrict__ vals1,
-                                                       const uint32_t* __restrict__ d_result_buf, float* __restrict__ out_color,
-                                                       float* __restrict__ out_depth, float* __restrict__ out_alpha,
-                                                       uint32_t* __restrict__ out_last, uint32_t* __restrict__ work_counter,
-                                                       uint32_t total_work, const RasterCkpt ck)
-{
-    __shared__ __align__(128) float4 s_rec[2][HRB * HQ];
-    __shared__ uint32_t s_slots[CK_MAX + 1];
-    const int lane = threadIdx.x;
-    const int grp = lane >> 4;   // row group of this thread inside the half
-    const uint32_t* __restrict__ vals = (*d_result_buf) ? vals1 : vals0;
-    const uint32_t rec_base = smem_u32(&s_rec[0][0]);
-
-    for (;;) {
-        __syncwarp();   // every lane is done with the previous item's shared memory
-        uint32_t work = 0;
-        if (lane == 0) work = atomicAdd(work_counter, 1u);
-        work = __shfl_sync(0xffffffffu, work, 0);
-        if (work >= total_work) break;
-        const uint32_t block = work >> 1;
-        const int half = (int)(work & 1u);
-        const BlockMap bm = map_block(vp, tile_order, block);
-        const int row0 = half * 8 + grp * FPPT;                  // this thread's first row inside the block
-        const int pxi = bm.x0 + (lane & 15), py0 = bm.y0 + row0;
-        bool active[FPPT];
-        bool any = false;
-#pragma unroll
-        for (int r = 0; r < FPPT; ++r) {
-            active[r] = pxi < bm.xmax && py0 + r < bm.ymax;
-            any = any || active[r];
-        }
-        if (!__any_sync(0xffffffffu, any)) {   // the half lies outside the image (1080 = 67.5 blocks)
-            if (lane == 0 && ck.written) ck.written[work] = 0u;
-            continue;
-        }
-        const uint32_t start = tile_ranges[bm.tile * 2], end = tile_ranges[bm.tile * 2 + 1];
-        const uint32_t count = end > start ? end - start : 0u;
-        const int nb = (int)((count + HRB - 1) / HRB);
-
-        // staging: two records per lane and batch; slots past the end of the list hold a null record (alpha = +0)
-        uint32_t idx_next[2];
-        auto load_idx = [&](int b) {
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const uint32_t j = (uint32_t)b * HRB + s * 32 + lane;
-                idx_next[s] = (b < nb && j < count) ? vals[start + j] : 0xffffffffu;
-            }
-        };
-        auto issue = [&](int b) {
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                float4* dst = &s_rec[b & 1][(s * 32 + lane) * HQ];
-                if (idx_next[s] != 0xffffffffu) {
-                    const float4* src = rec + (size_t)idx_next[s] * 3;
-                    cp_async16(dst, src);
-                    cp_async16(dst + 1, src + 1);
-                    cp_async16(dst + 2, src + 2);
-                } else {
-                    dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    dst[1] = make_float4(0.f, __int_as_float(0xff800000), 0.f, 0.f);
-                    dst[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-            cp_async_commit();
-        };
-        // (mean.xy, A, B | C, lo, r, g | b, opacity, depth, idx) -> (mean.x, A, B, C | r, g, b, depth | P Q R of row group 0 | of 1)
-        const float y0h = (float)(bm.y0 + half * 8), y1h = (float)(bm.y0 + half * 8 + FPPT);
-        auto to_rows = [&](int b) {
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                float4* p = &s_rec[b & 1][(s * 32 + lane) * HQ];
-                const float4 a = p[0], q = p[1], c = p[2];
-                const FwdRow t0 = fwd_row_terms(a.w, q.x, q.y, y0h - a.y), t1 = fwd_row_terms(a.w, q.x, q.y, y1h - a.y);
-                p[0] = make_float4(a.x, a.z, a.w, q.x);
-                p[1] = make_float4(q.z, q.w, c.x, c.z);
-                p[2] = make_float4(t0.P, t0.Q, t0.R, 0.f);
-                p[3] = make_float4(t1.P, t1.Q, t1.R, 0.f);
-            }
-        };
-        load_idx(0);
-        if (nb > 0) issue(0);
-        load_idx(1);
-
-        const float pxf = (float)pxi, pyf = (float)py0;
-        const uint32_t row_off = 32u + 16u * (uint32_t)grp;   // this thread's row-group quad inside a staged record
-        constexpr int FPAIRS = FPPT / 2;
-        f32x2 T2[FPAIRS], ncx[FPAIRS], ncy[FPAIRS], ncz[FPAIRS], ndep[FPAIRS];
-        float Ts[FPPT];
-        uint32_t ci[FPPT];
-#pragma unroll
-        for (int r = 0; r < FPPT; ++r) {
-            Ts[r] = 0.f;
-            ci[r] = 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < FPAIRS; ++k) {
-            T2[k] = f2_make(active[2 * k] ? 1.0f : 0.0f, active[2 * k + 1] ? 1.0f : 0.0f);
-            ncx[k] = ncy[k] = ncz[k] = ndep[k] = f2_bc(0.0f);
-        }
-        bool ck_ok = ck.state != nullptr;
-        uint32_t ck_written = 0;
-
-        // one Gaussian for the thread's FPPT pixels (see k_raster_fwd: negated sums, termination cut once per chunk)
-        auto blend = [&](uint32_t addr) {
-            const float4 a = lds128(addr), col = lds128(addr + 16), t = lds128(addr + row_off);
-            const FwdExp e = fwd_exponents_rows(a.y, a.z, a.w, t.x, t.y, t.z, pxf - a.x);
-            const f32x2 E0b = f2_bc(e.E0), E1b = f2_bc(e.E1), Cb = f2_bc(e.C);
-            const f32x2 colR = f2_bc(col.x), colG = f2_bc(col.y), colB = f2_bc(col.z), colD = f2_bc(col.w);
-#pragma unroll
-            for (int k = 0; k < FPAIRS; ++k) {
-                const f32x2 rf = f2_make((float)(2 * k), (float)(2 * k + 1));
-                const f32x2 p = f2_fma(rf, f2_fma(rf, Cb, E1b), E0b);
-                const f32x2 na = f2_make(fmaxf(-ex2_approx(f2_lo(p)), -0.99f), fmaxf(-ex2_approx(f2_hi(p)), -0.99f));
-                const f32x2 nc = f2_mul(T2[k], na);   // -T * alpha
-                ncx[k] = f2_fma(nc, colR, ncx[k]);
-                ncy[k] = f2_fma(nc, colG, ncy[k]);
-                ncz[k] = f2_fma(nc, colB, ncz[k]);
-                if (DEPTH) ndep[k] = f2_fma(nc, colD, ndep[k]);
-                T2[k] = f2_fma(T2[k], na, T2[k]);
-            }
-        };
-        auto Trow = [&](int r) { return (r & 1) ? f2_hi(T2[r >> 1]) : f2_lo(T2[r >> 1]); };
-        // this thread's FPPT pixels of checkpoint slot `slot`: (sum r, sum g, sum b, T) [+ depth plane]
-        auto store_sums = [&](uint32_t slot) {
-#pragma unroll
-            for (int r = 0; r < FPPT; ++r) {
-                const int k = r >> 1;
-                const bool hi = (r & 1) != 0;
-                const size_t o = (size_t)slot * 256 + (size_t)((row0 + r) * 16 + (lane & 15));
-                ck.state[o] = make_float4(-(hi ? f2_hi(ncx[k]) : f2_lo(ncx[k])), -(hi ? f2_hi(ncy[k]) : f2_lo(ncy[k])),
-                                          -(hi ? f2_hi(ncz[k]) : f2_lo(ncz[k])), Trow(r));
-                if (DEPTH) ck.depth[o] = -(hi ? f2_hi(ndep[k]) : f2_lo(ndep[k]));
-            }
-        };
-
-        bool done_all = false;
-        for (int b = 0; b < nb && !done_all; ++b) {
-            if (b + 1 < nb) {
-                issue(b + 1);
-                cp_async_wait<1>();   // this lane's copies of batch b have landed
-            } else {
-                cp_async_wait<0>();
-            }
-            load_idx(b + 2);
-            to_rows(b);
-            __syncwarp();
-            const int n = (int)min((uint32_t)HRB, count - (uint32_t)b * HRB);
-            uint32_t addr = rec_base + (uint32_t)(b & 1) * (HRB * HQ * 16u);
-            uint32_t chunk = (uint32_t)b * (HRB / FCHUNK);
-            for (int j = 0; j < n; j += FCHUNK, addr += FCHUNK * HQ * 16u, ++chunk) {
-                // remember where (and with which transmittance) each live pixel entered this chunk
-#pragma unroll
-                for (int r = 0; r < FPPT; ++r) {
-                    const float t = Trow(r);
-                    const bool live = t != 0.0f;
-                    Ts[r] = live ? t : Ts[r];
-                    ci[r] = live ? chunk : ci[r];
-                }
-#pragma unroll
-                for (int g = 0; g < FCHUNK; ++g) blend(addr + g * (HQ * 16u));
-                // the termination cut, once per chunk: a finished pixel continues with T = 0 (adds exact zeros)
-                float tmax = 0.0f;
-#pragma unroll
-                for (int k = 0; k < FPAIRS; ++k) {
-                    float t0 = f2_lo(T2[k]), t1 = f2_hi(T2[k]);
-                    t0 = t0 < 1e-4f ? 0.0f : t0;
-                    t1 = t1 < 1e-4f ? 0.0f : t1;
-                    T2[k] = f2_make(t0, t1);
-                    tmax = fmaxf(tmax, fmaxf(t0, t1));
-                }
-                if (__all_sync(0xffffffffu, tmax == 0.0f)) { done_all = true; break; }
-            }
-            __syncwarp();   // the stage may be refilled by the copy issued in the next iteration
-            // The half goes on past a multiple of CK Gaussians: checkpoint its 128 pixels (see k_raster_fwd)
-            const uint32_t done = (uint32_t)(b + 1) * HRB;
-            if (!done_all && ck_ok && done % CK == 0u && done < count) {
-                uint32_t slot = CK_FAILED;
-                if (lane == 0 && ck_written < (uint32_t)CK_MAX) {   // (a longer list ends in one long backward item)
-                    slot = ck_acquire(ck, block, ck_written);
-                    if (slot < CK_FAILED) {
-                        s_slots[ck_written] = slot;
-                        if (ck_written == 0u) s_slots[CK_MAX] = slot - 1u;
-                    }
-                }
-                slot = __shfl_sync(0xffffffffu, slot, 0);
-                if (slot < CK_FAILED) {
-                    store_sums(slot);
-#pragma unroll
-                    for (int k = 0; k < FPAIRS; ++k) ncx[k] = ncy[k] = ncz[k] = ndep[k] = f2_bc(0.0f);
-                    ++ck_written;
-                } else {
-                    ck_ok = false;   // pool exhausted: the backward handles the rest of this block as one item
-                }
-            }
-        }
-        cp_async_wait<0>();   // a copy still in flight belongs to a batch that early exit skipped
-        __syncwarp();         // s_slots visible to every lane
-
-        // Segment sums -> totals (this thread re-reads its own stores); the final (partial) segment sums go to the slot
-        // reserved with the block's first checkpoint
-        float tot[FPPT][4];
-#pragma unroll
-        for (int r = 0; r < FPPT; ++r) tot[r][0] = tot[r][1] = tot[r][2] = tot[r][3] = 0.0f;
-        if (ck_written) {   // warp-uniform
-            if (lane == 0) ck.table[(size_t)block * (CK_MAX + 1) + CK_MAX] = s_slots[CK_MAX];   // both halves store the same value
-            for (uint32_t c = 0; c < ck_written; ++c) {
-                const uint32_t slot = s_slots[c];
-#pragma unroll
-                for (int r = 0; r < FPPT; ++r) {
-                    const size_t o = (size_t)slot * 256 + (size_t)((row0 + r) * 16 + (lane & 15));
-                    const float4 v = ck.state[o];
-                    tot[r][0] += v.x; tot[r][1] += v.y; tot[r][2] += v.z;
-                    if (DEPTH) tot[r][3] += ck.depth[o];
-                }
-            }
-        }
-        if (lane == 0 && ck.written) ck.written[work] = ck_written;
-        // epilogue: exact lastContrib / transmittance at termination, then the outputs (see k_raster_fwd)
-#pragma unroll
-        for (int r = 0; r < FPPT; ++r) {
-            if (!active[r]) continue;
-            float Tend = Trow(r);
-            uint32_t nContrib = count;
-            auto row = [&](const f32x2* v) { return -((r & 1) ? f2_hi(v[r >> 1]) : f2_lo(v[r >> 1])); };
-            float cur[4] = {row(ncx), row(ncy), row(ncz), DEPTH ? row(ndep) : 0.0f};   // sums since the last checkpoint
-            const size_t po = (size_t)((row0 + r) * 16 + (lane & 15));                  // pixel inside a checkpoint slot
-            if (Tend == 0.0f) {
-                float t = Ts[r];
-                uint32_t i = ci[r] * FCHUNK;
-                float sur[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                bool found = false;
-                for (int g = 0; g < FCHUNK && i < count; ++g, ++i) {
-                    const float4* src = rec + (size_t)vals[start + i] * 3;
-                    const float4 a = __ldg(src), q = __ldg(src + 1);
-                    const FwdRow tr = fwd_row_terms(a.w, q.x, q.y, pyf - a.y);
-                    const FwdExp e = fwd_exponents_rows(a.z, a.w, q.x, tr.P, tr.Q, tr.R, pxf - a.x);
-                    const float alpha = fwd_alpha_rt(e, r);
-                    if (found) {
-                        const float4 c = __ldg(src + 2);
-                        const float w = t * alpha;
-                        sur[0] = fmaf(w, q.z, sur[0]); sur[1] = fmaf(w, q.w, sur[1]); sur[2] = fmaf(w, c.x, sur[2]);
-                        if (DEPTH) sur[3] = fmaf(w, c.z, sur[3]);
-                    }
-                    const float Tn = fmaf(-t, alpha, t);
-                    if (!found && Tn < 1e-4f) {
-                        nContrib = i + 1u;
-                        Tend = Tn;
-                        found = true;
-                    }
-                    t = Tn;
-                }
-                const uint32_t seg = ci[r] * FCHUNK / (uint32_t)CK;   // the segment (between checkpoints) the surplus went into
-                if (seg < ck_written) {
-                    const size_t o = (size_t)s_slots[seg] * 256 + po;
-                    float4 v = ck.state[o];
-                    v.x -= sur[0]; v.y -= sur[1]; v.z -= sur[2];
-                    ck.state[o] = v;
-                    if (DEPTH) ck.depth[o] -= sur[3];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) tot[r][q] -= sur[q];
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) cur[q] -= sur[q];
-                }
-            }
-            const size_t p = (size_t)(py0 + r) * vp.W + pxi;
-            const float bg = vp.whiteBg ? Tend : 0.0f;
-            if (ck_written) {
-                // final (partial) segment sums + the exact final transmittance (out_alpha = 1 - T loses its low bits)
-                const size_t o = (size_t)s_slots[CK_MAX] * 256 + po;
-                ck.state[o] = make_float4(cur[0], cur[1], cur[2], Tend);
-                if (DEPTH) ck.depth[o] = cur[3];
-            }
-            out_color[p * 3 + 0] = (tot[r][0] + cur[0]) + bg;
-            out_color[p * 3 + 1] = (tot[r][1] + cur[1]) + bg;
-            out_color[p * 3 + 2] = (tot[r][2] + cur[2]) + bg;
-            if (DEPTH) out_depth[p] = tot[r][3] + cur[3];
-            out_alpha[p] = 1.0f - Tend;
-            out_last[p] = nContrib;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-#ifndef GSB_BWD_SCALAR_ACC
-#define GSB_BWD_SCALAR_ACC 0   // tuning: the three-vector-operand FFMA2 of the backward (colour gradients, kT) as pairs of scalar FFMA (same bits)
-#endif
-__device__ __forceinline__ f32x2 acc_fma(f32x2 a, f32x2 b, f32x2 c)
-{
-#if GSB_BWD_SCALAR_ACC
-    return f2_make(fmaf(f2_lo(a), f2_lo(b), f2_lo(c)), fmaf(f2_hi(a), f2_hi(b), f2_hi(c)));
-#else
-    return f2_fma(a, b, c);
-#endif
-}
 template <bool DEPTH>
 __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_constant__ ViewParams vp,
                                                        const uint32_t* __restrict__ tile_ranges,
@@ -884,13 +513,11 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
         if (h.y == 0xffffffffu) continue;  // the slot holding a block's final segment sums is not a work item
         block_id = h.x;
         ck_index = h.y;
-        // checkpoints the forward wrote for THIS lane's half of the block (rows 0-7: lanes 0-15); a half that stopped
-        // earlier has no pixel that reads a later slot
-        ck_written = ck.written[2 * block_id + (uint32_t)(lane >> 4)];
+        ck_written = ck.written[block_id];
         seg_begin = h.y * (uint32_t)CK;
     } else {
         block_id = work - num_slots;
-        seg_begin = ck.written ? max(ck.written[2 * block_id], ck.written[2 * block_id + 1]) * (uint32_t)CK : 0u;
+        seg_begin = ck.written ? ck.written[block_id] * (uint32_t)CK : 0u;
     }
     const BlockMap bm = map_block(vp, tile_order, block_id);
     const uint32_t start = tile_ranges[bm.tile * 2], end = tile_ranges[bm.tile * 2 + 1];
@@ -1061,11 +688,11 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
                 f32x2 dotc = f2_fma(kZ2[k], colB, f2_fma(kY2[k], colG, f2_mul(kX2[k], colR)));
                 if (DEPTH) dotc = f2_fma(kD2[k], colD, dotc);
                 const f32x2 d = f2_sub(dotc, kT2[k]);
-                kT2[k] = acc_fma(al, d, kT2[k]);
-                Cr2 = acc_fma(contrib, kX2[k], Cr2);
-                Cg2 = acc_fma(contrib, kY2[k], Cg2);
-                Cb2 = acc_fma(contrib, kZ2[k], Cb2);
-                if (DEPTH) Cd2 = acc_fma(contrib, kD2[k], Cd2);
+                kT2[k] = f2_fma(al, d, kT2[k]);
+                Cr2 = f2_fma(contrib, kX2[k], Cr2);
+                Cg2 = f2_fma(contrib, kY2[k], Cg2);
+                Cb2 = f2_fma(contrib, kZ2[k], Cb2);
+                if (DEPTH) Cd2 = f2_fma(contrib, kD2[k], Cd2);
                 // VJP of evaluateTileGlobalSample: everything geometric is a moment of h; the alpha clamp branch has
                 // zero gradient
                 f32x2 hh = f2_mul(contrib, d);
@@ -1216,29 +843,6 @@ cudaError_t launch_raster_fwd(cudaStream_t st, const ViewParams& vp, const uint3
         if (ck.state) {
             e = cudaMemsetAsync(ck.count, 0, sizeof(uint32_t), st);
             if (e != cudaSuccess) return e;
-        }
-        static int res_half = 0;
-        const int half = env_int("GSB_FWD_HALF", 1);   // 0: the 64-thread whole-block kernel (read per launch: tests compare the two)
-        if (!res_half) {
-            cudaFuncSetAttribute(k_raster_fwd_half<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(k_raster_fwd_half<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            int fit = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, k_raster_fwd_half<false>, 32, 0) != cudaSuccess || fit < 1) fit = GSB_FWDH_CTAS;
-            res_half = std::max(1, std::min(env_int("GSB_FWDH_RES", GSB_FWDH_CTAS), fit));
-        }
-        if (half) {
-            if (ck.state) {   // the halves of a block find each other's checkpoint slots in the table
-                e = cudaMemsetAsync(ck.table, 0xff, (size_t)blocks * (CK_MAX + 1) * sizeof(uint32_t), st);
-                if (e != cudaSuccess) return e;
-            }
-            const int gridh = std::min(2 * blocks, sm_count() * res_half);
-            if (out_depth)
-                k_raster_fwd_half<true><<<gridh, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
-                                                              d_result_buf, out_color, out_depth, out_alpha, out_last, work_counter, (uint32_t)(2 * blocks), ck);
-            else
-                k_raster_fwd_half<false><<<gridh, 32, 0, st>>>(vp, tile_ranges, tile_order, reinterpret_cast<const float4*>(rec), vals0, vals1,
-                                                               d_result_buf, out_color, out_depth, out_alpha, out_last, work_counter, (uint32_t)(2 * blocks), ck);
-            return cudaGetLastError();
         }
         const int grid = std::min(blocks, sm_count() * res);
         if (out_depth)

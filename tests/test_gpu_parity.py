@@ -447,47 +447,6 @@ def test_segmented_backward_checkpoint_pool_exhausted(gsb, monkeypatch):
             assert rel_err(grads[slots][0][k].cpu().numpy(), grads[None][0][k].cpu().numpy()) < 1e-4, (slots, k)
 
 
-@pytest.mark.parametrize("white", [False, True])
-@pytest.mark.parametrize("slots", [None, "7", "1"])
-def test_half_block_forward_matches_whole_block_forward(gsb, monkeypatch, white, slots):
-    """The product forward works on 16x8 half-block items (one warp each, records re-staged with the row terms of the
-    exponent, checkpoint slots shared by the two halves of a block through compare-and-swap); the 64-thread whole-block
-    kernel it replaced (GSB_FWD_HALF=0) does the same arithmetic per pixel: alpha and lastContrib must be BIT-identical,
-    colour and depth equal up to the grouping of the checkpoint sums, and the gradients through the checkpoints (long translucent lists: several checkpoints per block; pools of 7 / 1 slots: most
-    blocks cannot checkpoint, or only one of the two halves asks) must agree."""
-    Context, L = gsb
-    n, W, H, degree = 6000, 72, 40, 1          # 72 x 40: ragged block columns / rows, 8 valid rows in the last block row
-    params = make_gaussians(n, 21, degree)
-    params["_scales"] = params["_scales"] + np.float32(1.1)
-    params["_opacity"] = params["_opacity"] - np.float32(2.0)
-    cam = L.make_camera(make_cameras(W, H, 3)[2])
-    rng = np.random.default_rng(5)
-    cot = dev(rng.standard_normal((H, W, 3)).astype(np.float32))
-    cot_d = dev(rng.standard_normal((H, W, 1)).astype(np.float32) * 0.1)
-    dparams = {k: dev(v) for k, v in params.items()}
-    if slots is None:
-        monkeypatch.delenv("GSB_CKPT_SLOTS", raising=False)
-    else:
-        monkeypatch.setenv("GSB_CKPT_SLOTS", slots)
-    out = {}
-    for half in ("0", "1"):
-        monkeypatch.setenv("GSB_FWD_HALF", half)
-        ctx = Context(W, H, sh_degree=degree, white_background=white)
-        render, depth, alpha, *_ = ctx.render_forward(dparams, cam)
-        last = ctx.last_contrib_sum()
-        grads = {k: v.clone() for k, v in ctx.render_backward(cot, cot_depth=cot_d).items()}
-        out[half] = (render.clone(), depth.clone(), alpha.clone(), last, grads)
-        ctx.close()
-    # alpha (1 - T at termination) is bit-identical; colour / depth of a pixel that ended in a segment after which only the
-    # OTHER half of its block went on are summed in a different grouping ((prefix + S) - surplus vs prefix + (S - surplus))
-    assert torch.equal(out["0"][2].view(torch.int32), out["1"][2].view(torch.int32))
-    assert float((out["0"][0] - out["1"][0]).abs().max()) <= 5e-7
-    assert float((out["0"][1] - out["1"][1]).abs().max()) <= 5e-6
-    assert out["0"][3] == out["1"][3] and out["0"][3] > 0
-    for k in out["0"][4]:
-        assert rel_err(out["1"][4][k].cpu().numpy(), out["0"][4][k].cpu().numpy()) < 1e-5, k
-
-
 def test_train_steps_vs_oracle(gsb, best_oracle, port):
     """Three batched train steps (B = 2 views).  Every iteration is checked in two tight halves instead of through
     parameter deltas (Adam without bias correction turns a first-step gradient into ~3.2 lr sign(g), which amplifies
