@@ -40,6 +40,9 @@ constexpr int RB_FWD = 128;      // records per forward batch (6 KB)
 #ifndef GSB_BWD_WARPS
 #define GSB_BWD_WARPS 16
 #endif
+#ifndef GSB_BWD_COMPACT
+#define GSB_BWD_COMPACT 1    // the sparse tail of a backward item one pixel per lane (0: every Gaussian on the dense 8-rows-per-lane body)
+#endif
 constexpr int RB_BWD = GSB_RB_BWD;   // records per backward batch
 constexpr int BWD_WARPS = GSB_BWD_WARPS;   // resident one-warp CTAs per SM the backward is compiled for (register budget)
 constexpr int BPPT = 8;          // backward: pixels per thread (rows)
@@ -596,6 +599,88 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
     if (nb == 0) continue;
     const uint32_t lstart = start + seg_begin;   // list position of the item's first Gaussian
 
+#if GSB_BWD_COMPACT
+    // ---- Sparse tail.  Back to front an item begins where FEWEST pixels are still active: at C3 11 % of all
+    // (block, Gaussian) iterations have at most 32 of the 256 pixels active (6 % at most 16; oracle work model, DESIGN.md
+    // section 7), yet the dense body below costs the same whatever the number of active pixels.  Those iterations run
+    // ONE PIXEL PER LANE instead: i_split = the smallest Gaussian index from which on at most 32 pixels are active
+    // (binary search over the block's 256 nContrib values, warp-wide counts); the <= 32 pixels with nContrib > i_split
+    // hand their state (transmittance, kT, cotangents) to one lane each through shared memory, the Gaussians
+    // [i_split, end) are differentiated by the scalar body gaussian_c (a fifth of the dense body's arithmetic, same
+    // parked sums -> same cross-lane reduction and flush), then transmittance and kT go back to the owning lanes and the
+    // dense bodies take over at i_split.
+    constexpr uint32_t CMIN = 12;   // fewer compact Gaussians than this do not pay for the search and the two hand-overs
+    uint32_t i_split = used_abs, cnC = 0u;
+    bool compact_on = false;
+    float cpx = 0.f, cpy = 0.f, csT = 0.f, ckT = 0.f, ckX = 0.f, ckY = 0.f, ckZ = 0.f, ckD = 0.f;
+    // Hand-over area (s_part is idle at both hand-overs): transmittance and kT of all 256 pixels as [column][row] with a
+    // row stride of 18 floats - a dense lane moves its four row pairs as 64-bit words (its packed registers are never
+    // taken apart: conditional half updates made the compiler keep every pair split across the dense loops, +45 MOV per
+    // Gaussian), a compact lane reads / writes the one float of its pixel - and the pixel of each compact lane.
+    constexpr int CSTRIDE = 18;
+    float* const s_cst = &s_part[0][0][0];
+    float* const s_ckt = s_cst + 16 * CSTRIDE;
+    uint32_t* const s_cpid = reinterpret_cast<uint32_t*>(s_ckt + 16 * CSTRIDE);
+    static_assert(2 * 16 * CSTRIDE + 32 <= BGRP * 10 * BPAD, "hand-over area must fit into s_part");
+    const uint32_t cpair_addr = smem_u32(s_cst) + (uint32_t)(((lane & 15) * CSTRIDE + (lane >> 4) * BPPT) * 4);   // this lane's pair 0
+    uint32_t cidx = 0u;   // compact lane: its pixel inside the hand-over arrays
+    {
+        auto count_gt = [&](uint32_t t) {
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int p = 0; p < BPPT; ++p) cnt += nC[p] > t ? 1u : 0u;
+            return __reduce_add_sync(0xffffffffu, cnt);
+        };
+        const uint32_t lo_bound = max(nmin_block, seg_begin);   // below it every pixel of the block is active
+        if (used_abs > lo_bound + CMIN && count_gt(used_abs - CMIN) <= 32u) {
+            uint32_t lo = lo_bound, hi = used_abs - CMIN;        // invariant: count_gt(hi) <= 32
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (count_gt(mid) <= 32u) hi = mid;
+                else lo = mid + 1u;
+            }
+            i_split = hi;
+            uint32_t sel = 0u;
+#pragma unroll
+            for (int p = 0; p < BPPT; ++p) sel |= (nC[p] > i_split ? 1u : 0u) << p;
+            const uint32_t mine = (uint32_t)__popc(sel);
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t ctotal = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t r = incl - mine;
+#pragma unroll
+            for (int p = 0; p < BPPT; ++p)
+                if ((sel >> p) & 1u) s_cpid[r++] = (uint32_t)(((lane >> 4) * BPPT + p) * 16 + (lane & 15));
+#pragma unroll
+            for (int k = 0; k < BPAIRS; ++k) {
+                asm volatile("st.shared.b64 [%0], %1;" ::"r"(cpair_addr + 8u * k), "l"(sT2[k].v) : "memory");
+                asm volatile("st.shared.b64 [%0], %1;" ::"r"(cpair_addr + 8u * k + 16u * CSTRIDE * 4u), "l"(kT2[k].v) : "memory");
+            }
+            __syncwarp();
+            if ((uint32_t)lane < ctotal) {
+                // the constant part of the pixel state comes from where the dense prologue took it (L2)
+                const uint32_t pid = s_cpid[lane];
+                const int col = (int)(pid & 15u), row = (int)(pid >> 4);
+                cidx = (uint32_t)(col * CSTRIDE + row);
+                cpx = (float)(bm.x0 + col);
+                cpy = (float)(bm.y0 + row);
+                const size_t pix = (size_t)(bm.y0 + row) * vp.W + (bm.x0 + col);
+                ckX = cot_color[pix * 3]; ckY = cot_color[pix * 3 + 1]; ckZ = cot_color[pix * 3 + 2];
+                ckD = cot_depth ? cot_depth[pix] : 0.0f;
+                cnC = min(min(last_contrib[pix], count), seg_limit);
+                csT = s_cst[cidx];
+                ckT = s_ckt[cidx];
+            }
+            __syncwarp();   // s_part is about to park sums again
+            compact_on = true;
+        }
+    }
+#endif
+
     // batches are visited last -> first; sequence number s = nb-1-b selects stage / parity
     // gather staging as in the forward: each lane pulls two 48-byte records per batch
     uint32_t ia = 0xffffffffu, ib = 0xffffffffu;   // indices of this lane's two slots of the next batch to issue
@@ -626,7 +711,12 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
     const float pxf = (float)pxi, pyf = (float)py0;
     const uint32_t rec_base = smem_u32(&s_rec[0][0]);
 
-    for (int b = nb - 1; b >= 0; --b) {
+    // per batch: begin (refill the other stage, clear the batch sums, wait for this batch's records) - the Gaussians,
+    // back to front - end (cross-lane sums of the last group, flush).  The state of the open batch:
+    int n = 0;                     // Gaussians in it
+    uint32_t stage_addr = 0u;      // its records in shared memory
+    uint32_t bstart = 0u;          // absolute index of its first Gaussian
+    auto begin_batch = [&](int b) {
         const uint32_t s = seq + (uint32_t)(nb - 1 - b);
         __syncwarp();                               // every lane is done with the stage being refilled
         if (b > 0) issue(b - 1);
@@ -637,8 +727,132 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
         }
         mbar_wait(&s_bar[s & 1], (s >> 1) & 1u);
         __syncwarp();
-        const int n = (int)min((uint32_t)RB_BWD, used - (uint32_t)b * RB_BWD);
-        const uint32_t stage_addr = rec_base + (s & 1u) * (RB_BWD * 48u);
+        n = (int)min((uint32_t)RB_BWD, used - (uint32_t)b * RB_BWD);
+        stage_addr = rec_base + (s & 1u) * (RB_BWD * 48u);
+        bstart = seg_begin + (uint32_t)b * RB_BWD;
+    };
+    auto end_batch = [&]() {
+        if (gcnt) {
+            reduce_group(gcnt);
+            gcnt = 0;
+            jpack = 0u;
+        }
+        __syncwarp();
+        // flush: finish the per-Gaussian chain rule on the block sums and send one 16-byte vector
+        // reduction per quad to L2 (records that no pixel of this block reached are skipped)
+        for (int j = lane; j < n; j += 32) {
+            const float4 s0 = *reinterpret_cast<const float4*>(&s_out[j][0]);   // Cr Cg Cb Cd
+            const float4 s1 = *reinterpret_cast<const float4*>(&s_out[j][4]);   // S0 Sx Sy Sxx
+            const float4 s2 = *reinterpret_cast<const float4*>(&s_out[j][8]);   // Sxy Syy - -
+            const bool any = s0.x != 0.f || s0.y != 0.f || s0.z != 0.f || s0.w != 0.f || s1.x != 0.f || s1.y != 0.f ||
+                             s1.z != 0.f || s1.w != 0.f || s2.x != 0.f || s2.y != 0.f;
+            if (!any) continue;
+            const uint32_t addr = stage_addr + (uint32_t)j * 48u;
+            const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
+            // h carries the opacity factor (alpha-weighted): the opacity gradient is H0 / opacity.  opacity == 0
+            // (sigmoid underflow) gives 0; the activation VJP multiplies it by opacity (1 - opacity) = 0 anyway
+            const float g_op = c.y > 0.0f ? s1.x / c.y : 0.0f;
+            const float kc = -0.5f;                      // d(natural exponent)/d conic = -0.5 * (dx^2, dx dy, dy^2)
+            const float km = -(1.0f / LOG2E_F);          // d(natural exponent)/d mean = -(2a dx + b dy, ...), (a,b,c) = (A,B,C)/log2 e
+            const float g_mx = km * fmaf(a.z + a.z, s1.y, a.w * s1.z);
+            const float g_my = km * fmaf(q.x + q.x, s1.z, a.w * s1.y);
+            const float g_c00 = kc * s1.w, g_c01 = kc * s2.x, g_c11 = kc * s2.y;
+            float* dst = grad_rec + (size_t)(__float_as_uint(c.w) & REC_IDX_MASK) * REC_FLOATS;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g_mx), "f"(g_my), "f"(g_c00), "f"(g_c01) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(g_c01), "f"(g_c11), "f"(s0.x), "f"(s0.y) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8), "f"(s0.z), "f"(g_op), "f"(s0.w), "f"(0.0f) : "memory");
+        }
+    };
+    int b_dense = nb - 1;          // first (highest) batch of the dense phase
+    int j_open = -2;               // >= -1: batch b_dense is already open, the dense bodies continue below Gaussian j_open + 1
+#if GSB_BWD_COMPACT
+    if (compact_on) {
+        // One Gaussian for this lane's ONE pixel: the scalar restatement of `gaussian` (masked), parking the same ten sums
+        auto gaussian_c = [&](int jj, const float4& a, const float4& q, const float4& c, auto clamp_c) {
+            constexpr bool CLAMP = decltype(clamp_c)::value;
+            const uint32_t i = bstart + (uint32_t)jj;
+            const float dx = cpx - a.x, dy = cpy - a.y;
+            const float e = fmaf(dx, fmaf(a.z, dx, a.w * dy), fmaf(q.x * dy, dy, q.y));
+            float al = ex2_approx(e);
+            al = i < cnC ? al : 0.0f;
+            const float raw = al;
+            if (CLAMP) al = fminf(al, 0.99f);
+            const float prevT = csT * rcp_approx(1.0f - al);
+            const float contrib = prevT * al;
+            csT = prevT;
+            float dotc = fmaf(ckZ, c.x, fmaf(ckY, q.w, ckX * q.z));
+            if (DEPTH) dotc = fmaf(ckD, c.z, dotc);
+            const float d = dotc - ckT;
+            ckT = fmaf(al, d, ckT);
+            float hh = contrib * d;
+            if (CLAMP) hh = raw > 0.99f ? 0.0f : hh;
+            const float Sx = hh * dx, Sy = hh * dy;
+            float* dst = &s_part[gcnt][0][lane];
+            dst[0 * BPAD] = contrib * ckX; dst[1 * BPAD] = contrib * ckY; dst[2 * BPAD] = contrib * ckZ;
+            if (DEPTH) dst[3 * BPAD] = contrib * ckD;
+            dst[4 * BPAD] = hh;
+            dst[5 * BPAD] = Sx; dst[6 * BPAD] = Sy; dst[7 * BPAD] = dx * Sx; dst[8 * BPAD] = dx * Sy; dst[9 * BPAD] = dy * Sy;
+            jpack |= (uint32_t)jj << (8 * gcnt);
+            if (++gcnt == BGRP) {
+                reduce_group(BGRP);
+                gcnt = 0;
+                jpack = 0u;
+            }
+        };
+        int b = nb - 1, j = 0;
+        for (;; --b) {
+            begin_batch(b);
+            const int jc = (int)min((uint32_t)n, max(i_split, bstart) - bstart);
+            for (j = n - 1; j >= jc; --j) {
+                const uint32_t addr = stage_addr + (uint32_t)j * 48u;
+                const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
+                if (__float_as_uint(c.w) & REC_MAYCLAMP) gaussian_c(j, a, q, c, std::true_type{});   // warp-uniform
+                else gaussian_c(j, a, q, c, std::false_type{});
+            }
+            if (i_split >= bstart) break;   // the compact phase ends in this batch (i_split >= seg_begin: at the latest in batch 0)
+            end_batch();
+        }
+        // transmittance and kT return to the owning lanes; the dense bodies continue in the open batch below Gaussian j + 1
+        if (gcnt) {
+            reduce_group(gcnt);
+            gcnt = 0;
+            jpack = 0u;
+        }
+        __syncwarp();
+        b_dense = b;
+        j_open = j;
+    }
+    // The dense loops always start from packed state that came back through the hand-over area - whether or not a compact
+    // phase ran - so that they see ONE definition of it (a second, conditional definition made the compiler keep the pairs
+    // split: 12 MOV per Gaussian).  The parked sums of the compact phase have overwritten the area: every lane lays its
+    // pairs out again, then the compact lanes put the new values of their pixels on top.
+#pragma unroll
+    for (int k = 0; k < BPAIRS; ++k) {
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(cpair_addr + 8u * k), "l"(sT2[k].v) : "memory");
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(cpair_addr + 8u * k + 16u * CSTRIDE * 4u), "l"(kT2[k].v) : "memory");
+    }
+    __syncwarp();
+    if (compact_on && cnC) {   // a lane without a pixel has cnC == 0 (a selected pixel has nContrib > i_split >= 0)
+        s_cst[cidx] = csT;
+        s_ckt[cidx] = ckT;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < BPAIRS; ++k) {
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(sT2[k].v) : "r"(cpair_addr + 8u * k) : "memory");
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(kT2[k].v) : "r"(cpair_addr + 8u * k + 16u * CSTRIDE * 4u) : "memory");
+    }
+    __syncwarp();
+#endif
+    for (int b = b_dense; b >= 0; --b) {
+        int j;
+        if (j_open >= -1) {
+            j = j_open;
+            j_open = -2;
+        } else {
+            begin_batch(b);
+            j = n - 1;
+        }
         // One Gaussian for the thread's 8 pixels.  MASKED = false when every pixel of the block is known to be active
         // (i < block-wide min nContrib); CLAMP = false when the record says alpha cannot reach 0.99 (REC_MAYCLAMP clear).
         // The four variants are whole loop bodies (no join inside an iteration), so the pixel state is updated in
@@ -646,7 +860,7 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
         // (i >= nContrib) of the masked variant sees alpha = 0: contrib = 0, kT unchanged, h = 0, transmittance unchanged.
         auto gaussian = [&](int j, const float4& a, const float4& q, const float4& c, auto masked_c, auto clamp_c) {
             constexpr bool MASKED = decltype(masked_c)::value, CLAMP = decltype(clamp_c)::value;
-            const uint32_t i = seg_begin + (uint32_t)(b * RB_BWD + j);
+            const uint32_t i = bstart + (uint32_t)j;
             const float dx = pxf - a.x, dyb = pyf - a.y;
             // The thread's 8 pixels share dx and have dy = dyb + p, so the exponent is a quadratic in the
             // compile-time row offset p:  e(p) = E0 + p*E1 + p^2*C  (log2 units).  log2(opacity) is folded in, so
@@ -729,9 +943,7 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
         };
         // back to front: the Gaussians at or beyond the block-wide min nContrib come first (masked), the rest have
         // every pixel of the block active
-        const uint32_t bstart = seg_begin + (uint32_t)b * RB_BWD;   // absolute index of the batch's first Gaussian
         const int jsplit = (int)min((uint32_t)n, max(nmin_block, bstart) - bstart);
-        int j = n - 1;
         for (; j >= jsplit; --j) {
             const uint32_t addr = stage_addr + (uint32_t)j * 48u;
             const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
@@ -744,36 +956,7 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
             if (__float_as_uint(c.w) & REC_MAYCLAMP) gaussian(j, a, q, c, std::false_type{}, std::true_type{});
             else gaussian(j, a, q, c, std::false_type{}, std::false_type{});
         }
-        if (gcnt) {
-            reduce_group(gcnt);
-            gcnt = 0;
-            jpack = 0u;
-        }
-        __syncwarp();
-        // flush: finish the per-Gaussian chain rule on the block sums and send one 16-byte vector
-        // reduction per quad to L2 (records that no pixel of this block reached are skipped)
-        for (int j = lane; j < n; j += 32) {
-            const float4 s0 = *reinterpret_cast<const float4*>(&s_out[j][0]);   // Cr Cg Cb Cd
-            const float4 s1 = *reinterpret_cast<const float4*>(&s_out[j][4]);   // S0 Sx Sy Sxx
-            const float4 s2 = *reinterpret_cast<const float4*>(&s_out[j][8]);   // Sxy Syy - -
-            const bool any = s0.x != 0.f || s0.y != 0.f || s0.z != 0.f || s0.w != 0.f || s1.x != 0.f || s1.y != 0.f ||
-                             s1.z != 0.f || s1.w != 0.f || s2.x != 0.f || s2.y != 0.f;
-            if (!any) continue;
-            const uint32_t addr = stage_addr + (uint32_t)j * 48u;
-            const float4 a = lds128(addr), q = lds128(addr + 16), c = lds128(addr + 32);
-            // h carries the opacity factor (alpha-weighted): the opacity gradient is H0 / opacity.  opacity == 0
-            // (sigmoid underflow) gives 0; the activation VJP multiplies it by opacity (1 - opacity) = 0 anyway
-            const float g_op = c.y > 0.0f ? s1.x / c.y : 0.0f;
-            const float kc = -0.5f;                      // d(natural exponent)/d conic = -0.5 * (dx^2, dx dy, dy^2)
-            const float km = -(1.0f / LOG2E_F);          // d(natural exponent)/d mean = -(2a dx + b dy, ...), (a,b,c) = (A,B,C)/log2 e
-            const float g_mx = km * fmaf(a.z + a.z, s1.y, a.w * s1.z);
-            const float g_my = km * fmaf(q.x + q.x, s1.z, a.w * s1.y);
-            const float g_c00 = kc * s1.w, g_c01 = kc * s2.x, g_c11 = kc * s2.y;
-            float* dst = grad_rec + (size_t)(__float_as_uint(c.w) & REC_IDX_MASK) * REC_FLOATS;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g_mx), "f"(g_my), "f"(g_c00), "f"(g_c01) : "memory");
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(g_c01), "f"(g_c11), "f"(s0.x), "f"(s0.y) : "memory");
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8), "f"(s0.z), "f"(g_op), "f"(s0.w), "f"(0.0f) : "memory");
-        }
+        end_batch();
     }
     seq += (uint32_t)nb;
     }   // persistent loop
