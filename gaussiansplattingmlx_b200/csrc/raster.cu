@@ -609,7 +609,10 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
     // [i_split, end) are differentiated by the scalar body gaussian_c (a fifth of the dense body's arithmetic, same
     // parked sums -> same cross-lane reduction and flush), then transmittance and kT go back to the owning lanes and the
     // dense bodies take over at i_split.
-    constexpr uint32_t CMIN = 12;   // fewer compact Gaussians than this do not pay for the search and the two hand-overs
+#ifndef GSB_BWD_CMIN
+#define GSB_BWD_CMIN 12
+#endif
+    constexpr uint32_t CMIN = GSB_BWD_CMIN;   // fewer compact Gaussians than this do not pay for the search and the two hand-overs
     uint32_t i_split = used_abs, cnC = 0u;
     bool compact_on = false;
     float cpx = 0.f, cpy = 0.f, csT = 0.f, ckT = 0.f, ckX = 0.f, ckY = 0.f, ckZ = 0.f, ckD = 0.f;
