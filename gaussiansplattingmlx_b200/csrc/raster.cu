@@ -3,8 +3,9 @@
 // Reference: slang/gaussian_tile_global_kernels.slang:437-614 (forward), :501-521 + :648-881
 // (backward), call sites Trainer/GaussianRenderer.swift:124-147,187-226.
 //
-// Both kernels are FP32-issue bound (ncu: issue slots ~82 % busy), so the design goal is the fewest
-// instructions per (pixel, Gaussian) evaluation:
+// Both kernels are bound by their packed FP32 arithmetic (tools/microbench/issue_model.cu: an FFMA2 with two or three
+// vector operands holds the FMA pipe for 2.8-3.8 cycles per warp and nothing issues in its shadow; ncu: issue slots
+// ~62 % busy, insensitive to occupancy), so the design goal is the least arithmetic per (pixel, Gaussian) evaluation:
 //   * a tile's list is (tile_ranges, Gaussian indices in depth order) from tilelists.cu; the 48-byte records are
 //     gathered from the L2-resident record table straight into shared memory by 16-byte async copies (LDGSTS)
 //     completing on mbarriers, double-buffered;
@@ -17,7 +18,8 @@
 //   * backward: ONE WARP per 16x16 block.  The per-Gaussian gradient sums are first accumulated over the thread's 8
 //     pixels in registers (geometry as three moments of h), parked in shared memory and summed across lanes by
 //     column reads every 3 Gaussians; one vector red per (block, Gaussian, quad) then goes to L2.  Records flagged
-//     "cannot reach the alpha clamp" take a path without the clamp logic;
+//     "cannot reach the alpha clamp" take a path without the clamp logic; the sparse tail of an item (<= 32 of the 256
+//     pixels still active) runs one pixel per lane;
 //   * both kernels are persistent: CTAs pull blocks heavy-first from a device counter.
 // Work per evaluation: forward 27 flop + 1 ex2; backward ~80 flop + 1 ex2 + 1 rcp.
 #include <stdlib.h>
