@@ -607,7 +607,8 @@ __global__ void __launch_bounds__(32, BWD_WARPS) k_raster_bwd(const __grid_const
     // section 7), yet the dense body below costs the same whatever the number of active pixels.  Those iterations run
     // ONE PIXEL PER LANE instead: i_split = the smallest Gaussian index from which on at most 32 pixels are active
     // (binary search over the block's 256 nContrib values, warp-wide counts); the <= 32 pixels with nContrib > i_split
-    // hand their state (transmittance, kT, cotangents) to one lane each through shared memory, the Gaussians
+    // hand transmittance and kT to one lane each through shared memory (the constant part of a pixel's state - cotangents,
+    // nContrib - is re-read from where the dense prologue took it), the Gaussians
     // [i_split, end) are differentiated by the scalar body gaussian_c (a fifth of the dense body's arithmetic, same
     // parked sums -> same cross-lane reduction and flush), then transmittance and kT go back to the owning lanes and the
     // dense bodies take over at i_split.
