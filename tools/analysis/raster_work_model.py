@@ -61,6 +61,31 @@ def main(name="C3"):
     print("  footprint evaluations if a block ran only to its k-th smallest lastContrib (k of 256): " +
           ", ".join(f"k={k + 1}: {q[:, k].sum() * 256 / E:.3f}" for k in (127, 191, 223, 239, 255)))
 
+    # ---- activity of the (block, Gaussian) iterations: what a lower-cost body for sparsely active iterations can recover
+    total_it = int(used.sum())
+    print(f"\nbackward / forward iterations by the number of pixels still active (one 16x16 block x one Gaussian; {total_it} in all):")
+    for m in (16, 32, 64, 96, 128, 192):
+        km = q[:, 256 - m - 1]                       # the (m+1)-th largest lastContrib: from there on <= m pixels are active
+        print(f"  <= {m:3d} of 256 active: {(used - np.maximum(km, nmin)).clip(0).sum() / total_it:.3f}")
+    masked = int((used - nmin).sum())
+    print(f"  masked iterations (at least one pixel inactive): {masked / total_it:.3f}; mean active pixels in them: "
+          f"{(B - nmin[:, None]).clip(0).sum() / masked:.1f}")
+    # the backward's row pairs: lane = column x half, pair k = rows (2k, 2k+1) of both halves = block rows {2k, 2k+1, 8+2k, 9+2k}
+    B3 = B.reshape(-1, 16, 16)
+    amax = np.stack([B3[:, [2 * k, 2 * k + 1, 8 + 2 * k, 9 + 2 * k], :].reshape(len(B3), -1).max(1) for k in range(4)], 1)
+    am = np.sort(amax, 1)
+    frac = []
+    for j in range(1, 5):                            # iterations with exactly j of the 4 pairs holding an active pixel
+        hi, lo = am[:, 4 - j], (am[:, 4 - j - 1] if j < 4 else np.zeros(len(B3), np.int64))
+        frac.append((np.maximum(hi, nmin) - np.maximum(lo, nmin)).clip(0).sum() / masked)
+    print("  masked iterations by the number of row pairs (64 pixels each) with an active pixel, 1..4: " +
+          ", ".join(f"{f:.3f}" for f in frac) + "  (skipping dead pairs: warp-uniform, but rarely applicable)")
+    H8 = blocks(8, 16)
+    u8 = H8.max(axis=1)
+    q8 = np.sort(H8, axis=1)
+    print("  forward, one warp = a 16x8 half (128 pixels): iterations with <= 32 live pixels "
+          f"{(u8 - q8[:, 128 - 33]).sum() / u8.sum():.3f}, <= 64: {(u8 - q8[:, 128 - 65]).sum() / u8.sum():.3f}")
+
     cost = used + 10.0
     print("\nbackward, greedy list scheduling, makespan / ideal:")
     for workers in (148 * 16, 148 * 12):
